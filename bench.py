@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- FGN guided RoIAlign + support-guided fusion throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # reference CPU path (oracle port)
+
+Metric (BASELINE.json): RoIs/s of the guided RoIAlign + fusion hot path (episodes/s reported beside
+it).  Workload at every N: cfg3 of BASELINE.json -- COCO2VOC 1-way 1-shot, R50-FPN pyramid, 256
+channels, query 800x1344, 1000 proposals per image, random support masks -- the configuration the
+metric is quoted on (it fits one GPU).  One *step* = one pass of the whole hot path (AG-RPN
+attention on P2-P6, support vectors, guided multi-level RoIAlign + relation fusion + heads, mask
+branch RoIAlign with AG-FCN attention) over a block of E distinct episodes per GPU.  Episodes are
+sharded over ranks (weak scaling: E per rank fixed), the only collective is the NCCL all_gather of
+the per-episode results.
+
+`value`  : inputs resident in HBM (channels_last) when the timed region starts.
+`e2e`    : same path through the module API from pinned HOST buffers in the reference's NCHW
+           layout; H2D of every input, device repack, D2H of cls/bbox results inside the timed region.
+`roofline`: the multi-level RoIAlign kernel, timed alone with CUDA events on its launch stream.
+`cpu_baseline`: the oracle (torchvision CPU roi_align + torch CPU fusion, materialised concat form)
+           on this box's host cores, rank 0, N=1 only, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "cfg3_coco2voc_n1k1_fpn"
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML, 5 ms period)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for b, n in self._NAMES.items():
+            if bits & b and n != "gpu_idle":
+                self.reasons.add(n)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._once()
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- algorithmic bytes ----------------------------------------------------------------------------------
+def roi_align_algorithmic_bytes(cfg, rois: torch.Tensor, P: int = 7) -> int:
+    """sum_l min(H_l W_l, sum_{roi in l} (ceil(w)+1)(ceil(h)+1)) * C*4 + R*20 + out bytes."""
+    from oracle import fgn_oracle as O
+    from fgn_b200.episodes import level_hw
+    lv = O.map_roi_levels_c(rois, len(cfg.strides))
+    total = 0
+    for l, s in enumerate(cfg.strides):
+        h, w = level_hw(cfg.img_h, cfg.img_w, s)
+        r = rois[lv == l]
+        cells = ((torch.ceil((r[:, 3] - r[:, 1]) / s) + 1) * (torch.ceil((r[:, 4] - r[:, 2]) / s) + 1)).sum().item()
+        total += min(h * w * cfg.batch, int(cells)) * cfg.channels * 4
+    return int(total + rois.shape[0] * 20 + rois.shape[0] * cfg.channels * P * P * 4)
+
+
+# ---- the CPU reference path (oracle) --------------------------------------------------------------------
+def cpu_reference_episode(ep, w):
+    """The reference's path on CPU for one episode: torchvision CPU roi_align (stand-in for mmcv's CPU
+    RoIAlign: same algorithm) + torch CPU fusion exactly as fgn_roi_head.py:253-279,419-449 and
+    fgn_ag_rpn_head.py:37-46 (materialised concat form)."""
+    from oracle import fgn_oracle as O
+    cfg = ep["cfg"]
+    n_ext = len(cfg.strides)
+    for q, s in zip(ep["qry"], ep["spp"]):
+        O.agrpn_attention(q, s, cfg.n_ways, cfg.k_shots)
+    if cfg.mode == "fpn":
+        cat_mean, mp, _, _ = O.count_spp_fpn(ep["spp"][:n_ext], cfg.strides, ep["spp_bboxes"].clone(), ep["spp_masks"],
+                                             cfg.n_ways, cfg.k_shots)
+    else:
+        cat_mean, mp, _, _ = O.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"], cfg.n_ways, cfg.k_shots, 16)
+    res = O.bbox_forward(ep["qry"][:n_ext], cfg.strides, ep["rois"], cat_mean, cfg.n_ways, w,
+                         chunk=max(1, 4000 // cfg.n_ways))
+    det = ep["det_rois"]
+    labels = [ep["det_labels"][det[:, 0] == b] for b in range(cfg.batch)]
+    O.mask_attention(ep["qry"][:n_ext], cfg.strides, det, mp, labels, cfg.n_ways, cfg.mask_size)
+    return res
+
+
+def time_cpu_reference(cfg, steps: int, warmup: int, episodes_per_step: int = 1):
+    from fgn_b200.episodes import make_episode, make_weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = make_weights(cfg.channels, 0)
+    eps = [make_episode(cfg, seed=i) for i in range(min(4, max(1, episodes_per_step)))]
+    with torch.no_grad():
+        for i in range(warmup):
+            cpu_reference_episode(eps[i % len(eps)], w)
+        t0 = time.perf_counter()
+        n = 0
+        for i in range(steps):
+            for j in range(episodes_per_step):
+                cpu_reference_episode(eps[(i + j) % len(eps)], w)
+                n += 1
+        dt = time.perf_counter() - t0
+    return n, dt
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ---- main -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fgn_b200", choices=["fgn_b200", "reference"])
+    ap.add_argument("--episodes-per-step", type=int, default=16, help="distinct episodes per GPU per step")
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from fgn_b200.episodes import CONFIGS
+    cfg = CONFIGS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{cfg.name}: {cfg.n_ways}-way {cfg.k_shots}-shot, {cfg.mode.upper()} strides {list(cfg.strides)}"
+                          f" (+P6 for AG-RPN), C={cfg.channels}, query {cfg.img_h}x{cfg.img_w}, R={cfg.num_rois} proposals/img,"
+                          f" {cfg.mask_rois} mask RoIs/img, support {cfg.spp_size}px",
+              "episodes_per_gpu_per_step": args.episodes_per_step, "sharding": f"episodes x{max(world, 1)}"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n, dt = time_cpu_reference(cfg, args.steps, min(args.warmup, 1), 1)
+        rois_s = n * cfg.num_rois * cfg.batch / dt
+        cores = torch.get_num_threads()
+        sample = f"{n} episodes of {cfg.name} ({args.steps} steps x 1 episode), {cpu_model()}"
+        line = {"impl": "reference", "metric": "guided RoIAlign+fusion RoIs/s", "value": rois_s, "unit": "RoIs/s",
+                "episodes_per_s": n / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": dict(config, episodes_per_gpu_per_step=1),
+                "cpu_baseline": {"value": rois_s, "unit": "RoIs/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": rois_s, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fgn_b200 arm has no CPU fallback (use --impl reference)")
+    import torch.distributed as dist
+    from fgn_b200 import ops
+    from fgn_b200.episodes import build_heads, episode_to_device, gather_results, make_episode, run_guided_path
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    E = args.episodes_per_step
+
+    # ---- inputs: E distinct episodes per rank, resident in HBM (channels_last) and mirrored in pinned host memory
+    host_eps = [make_episode(cfg, seed=rank * E + i) for i in range(min(E, 4))]
+    dev_eps = []
+    for i in range(E):
+        ep = episode_to_device(host_eps[i % len(host_eps)], device, channels_last=True)
+        if i >= len(host_eps):      # distinct data without the CPU RNG cost: perturb on device
+            ep["qry"] = [q + 0.01 * i for q in ep["qry"]]
+        dev_eps.append(ep)
+    rpn, head = build_heads(cfg, device, seed=0, shared_head=None if cfg.mode == "fpn" else "c4")
+    bytes_resident = sum(t.numel() * 4 for ep in dev_eps for t in ep["qry"] + ep["spp"])
+    config["l2"] = f"no flush: episode stream of {E} x {bytes_resident / E / 1e6:.0f} MB distinct inputs > 126 MB L2"
+
+    def step_resident():
+        outs = []
+        for ep in dev_eps:
+            o = run_guided_path(rpn, head, ep)
+            outs.append(torch.cat([o["cls_score"], o["bbox_pred"]], 1))
+        res = torch.stack(outs)                               # [E, R, 5N+1]
+        if world > 1:
+            res = gather_results(res, E * world)
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            sync_all()
+            if sampler:
+                sampler.start()
+            l0 = ops.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            sync_all()
+            ms = e0.elapsed_time(e1)
+            clocks = sampler.stop() if sampler else None
+            launches = ops.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    sampler = ClockSampler(local_rank)
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    episodes = E * world * args.steps
+    rois_total = episodes * cfg.num_rois * cfg.batch
+    value = rois_total / (ms * 1e-3)
+
+    # ---- e2e: pinned host buffers in the reference's NCHW layout -> H2D -> path -> D2H of results
+    pinned = []
+    for ep in host_eps:
+        p = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else (v.pin_memory() if torch.is_tensor(v) else v))
+             for k, v in ep.items()}
+        pinned.append(p)
+    h2d = sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
+              for k, v in pinned[0].items() if isinstance(v, list) or torch.is_tensor(v)) * E
+    out_host = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * 4
+
+    def step_e2e():
+        for i in range(E):
+            ep = episode_to_device(pinned[i % len(pinned)], device, channels_last=False)   # H2D, NCHW
+            o = run_guided_path(rpn, head, ep)                                              # repack + path
+            out_host[i].copy_(torch.cat([o["cls_score"], o["bbox_pred"]], 1), non_blocking=True)
+        if world > 1:
+            torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream().synchronize()                                           # results on host
+
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 1)
+    e2e_value = E * world * e2e_steps * cfg.num_rois * cfg.batch / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel: multi-level RoIAlign, timed alone on its stream
+    n_ext = len(cfg.strides)
+    scales = [1.0 / s for s in cfg.strides]
+    alg_bytes = roi_align_algorithmic_bytes(cfg, host_eps[0]["rois"])
+
+    def roi_only():
+        for ep in dev_eps:
+            ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], scales, 7, 0, True, out_format="nhwc")
+
+    ms_roi, l_roi, _ = timed(roi_only, max(args.steps, 10), args.warmup)
+    per_launch_s = ms_roi * 1e-3 / (max(args.steps, 10) * E)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / per_launch_s / 1e9
+    roofline = {"kernel": "roi_align_sep_nhwc_kernel<7> (multi-level RoIAlign, NHWC out)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "traffic": None}
+
+    if rank == 0:
+        line = {"metric": "guided RoIAlign+fusion RoIs/s", "value": value, "unit": "RoIs/s",
+                "episodes_per_s": episodes / (ms * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "host_layout": "NCHW fp32 pinned"},
+                "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            n, dt = time_cpu_reference(cfg, 1, 1, 1)
+            reps = max(1, min(20, int(args.cpu_seconds / max(dt, 1e-3)) - 1))
+            if reps > 1:
+                n, dt = time_cpu_reference(cfg, reps, 0, 1)
+            v = n * cfg.num_rois * cfg.batch / dt
+            line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{n} episodes of {cfg.name}, {cpu_model()}, {time.perf_counter() - t0:.1f}s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,81 @@
+"""Attention-Guided RPN head -- host-side mirror of AGRPNHead (fgn_ag_rpn_head.py:14-118).
+
+The attention part (class vectors :37-41, channel attention :44-46) and the best-class selection
+(:87-108) run in libfgn_b200 kernels.  The RPN convolutions in between are mmdet RPNHead's [3P]
+3x3 conv + two 1x1 convs (cuDNN through torch.nn); they are adjacent to the path, not part of it
+(SURVEY section 8f).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class AGRPNHead(nn.Module):
+    n_ways = 3
+    k_shots = 3
+    verbose = False
+    subsampling_ratio = 16
+    log_mode = False
+
+    def __init__(self, in_channels: int = 1024, feat_channels: int = 1024, anchor_generator: Optional[dict] = None,
+                 num_anchors: Optional[int] = None, loss_cls: Optional[dict] = None, n_ways: Optional[int] = None,
+                 k_shots: Optional[int] = None, **kwargs):
+        super().__init__()
+        if num_anchors is None:
+            ag = anchor_generator or dict(scales=[2, 4, 8, 16, 32], ratios=[0.5, 1.0, 2.0])
+            num_anchors = len(ag["scales"]) * len(ag["ratios"])          # fgn_r50_c4_densecl.py:48-54
+        use_sigmoid = True if loss_cls is None else loss_cls.get("use_sigmoid", True)
+        if not use_sigmoid:
+            raise NotImplementedError("AGRPNHead: the FGN configs use sigmoid objectness (one score per anchor)")
+        self.in_channels, self.feat_channels, self.num_anchors = in_channels, feat_channels, num_anchors
+        self.cls_out_channels = 1
+        # mmdet RPNHead._init_layers [3P]
+        self.rpn_conv = nn.Conv2d(in_channels, feat_channels, 3, padding=1)
+        self.rpn_cls = nn.Conv2d(feat_channels, num_anchors * self.cls_out_channels, 1)
+        self.rpn_reg = nn.Conv2d(feat_channels, num_anchors * 4, 1)
+        if n_ways is not None:
+            self.n_ways = n_ways
+        if k_shots is not None:
+            self.k_shots = k_shots
+
+    # mmdet RPNHead.forward_single [3P]
+    def _rpn_forward_single(self, x: torch.Tensor):
+        x = F.relu(self.rpn_conv(x), inplace=True)
+        return self.rpn_cls(x), self.rpn_reg(x)
+
+    def attention(self, qry_fmap: torch.Tensor, spp_fmaps: torch.Tensor):
+        """fgn_ag_rpn_head.py:33-46 -> (spp_fvecs_cat_mean [B,N,C,1,1], qry_fmap_mod [B*N,C,H,W])."""
+        batch, c = qry_fmap.shape[:2]
+        if spp_fmaps.shape[0] != batch * self.n_ways * self.k_shots or spp_fmaps.shape[1] != c:
+            raise ops.FgnError(f"spp_fmaps {tuple(spp_fmaps.shape)} is not [B*N*K={batch * self.n_ways * self.k_shots}, C={c}, h, w]")
+        vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
+        return vec, ops.channel_attention(qry_fmap, vec)
+
+    def forward_single(self, qry_fmap: torch.Tensor, spp_fmaps: Optional[torch.Tensor] = None, qry_bboxes=None,
+                       qry_cat_ids=None, img_metas_cpu: Optional[list] = None, train_mode: bool = False,
+                       log_mode: bool = False):
+        assert train_mode ^ (qry_bboxes is None and qry_cat_ids is None)
+        if train_mode:
+            raise NotImplementedError("AGRPNHead train_mode (RPN loss over per-class GT lists, "
+                                      "fgn_ag_rpn_head.py:58-79) is outside the forward hot path")
+        batch = qry_fmap.shape[0]
+        _, qry_fmap_mod = self.attention(qry_fmap, spp_fmaps)
+        rpn_cls_score, rpn_bbox_pred = self._rpn_forward_single(qry_fmap_mod)
+        if log_mode:
+            self.qry_fmap_mod, self.rpn_cls_score, self.rpn_bbox_pred = qry_fmap_mod, rpn_cls_score, rpn_bbox_pred
+        if self.n_ways > 1:
+            return ops.best_class_select(rpn_cls_score, rpn_bbox_pred, batch, self.n_ways)
+        c, h, w = rpn_cls_score.shape[-3:]
+        c4 = rpn_bbox_pred.shape[1]
+        return rpn_cls_score.reshape(batch, c, h, w), rpn_bbox_pred.reshape(batch, c4, h, w)
+
+    def forward(self, qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor]):
+        """FPN mode (SURVEY A.9, A-FPN): forward_single per level with that level's support maps."""
+        outs = [self.forward_single(q, s) for q, s in zip(qry_feats, spp_feats)]
+        return [o[0] for o in outs], [o[1] for o in outs]

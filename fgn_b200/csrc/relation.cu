@@ -1,0 +1,317 @@
+// relation.cu -- Relation-Guided Detector fusion + box head, fused.
+//
+// Reference: FGNRoIHead.count_one_roi_by_n_spp (fgn_roi_head.py:253-279), BBoxHead.forward with
+// with_avg_pool=True [3P] (called at fgn_roi_head.py:338, config fgn_r50_c4_densecl.py:76-93) and
+// count_modified_cls_bbox (fgn_roi_head.py:302-326).
+//
+// The reference materialises X[r*N+n] = cat(q[r], s[b(r),n]) ([R*N,2C,P,P]) and runs a 1x1 conv
+// over it.  Here the conv is split by linearity,
+//     conv(cat(q,s)) = Wq q[r] + (Ws s[b,n] + bias)            Wq = W[:, :C], Ws = W[:, C:]
+// so the contraction runs once per RoI (M = R*P*P rows) and once per class (M = B*N*P*P rows),
+// not once per (RoI, class) pair.  The (RoI, class) work that remains is elementwise: add,
+// GroupNorm(32) statistics, affine + ReLU, PxP average pool and the two tiny FCs, all done in
+// registers by relation_epilogue_kernel; the re-assembly to [R,N+1]/[R,4N] rides in the finalize
+// kernel.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace fgn {
+
+constexpr int kEpiThreads = 256;
+constexpr int kMaxPP = 49;          // epilogue register tile is P*P = 49 (P = 7)
+
+__device__ __forceinline__ float group_sum_shfl(float v, int cg)
+{
+    for (int o = cg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// grid (R, nblk); block kEpiThreads; thread = one channel of the block.
+// Yq [R*PP, C] and Ys [BN*PP, C] are the split-conv outputs (Ys already carries the conv bias).
+// partial [R, N, 6, nblk]: per-channel-block partial dot products of the pooled vector with the
+// 2 cls rows and 4 reg rows.
+template <int PP>
+__global__ void __launch_bounds__(kEpiThreads, 2)
+relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__ Ys,
+                         const int32_t *__restrict__ roi_batch, const int R, const int B, const int N,
+                         const int C, const int cblk, const int cg, const float eps,
+                         const float *__restrict__ gn_w, const float *__restrict__ gn_b,
+                         const float *__restrict__ fc_cls_w, const float *__restrict__ fc_reg_w,
+                         float *__restrict__ partial)
+{
+    extern __shared__ float sm[];                 // [N][6][nwarps] + [blockDim] scratch
+    const int r = blockIdx.x, blk = blockIdx.y, nblk = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    float *fc_part = sm;                          // [N*6*nwarps]
+    float *scratch = sm + (size_t)N * 6 * nwarps; // [blockDim.x]
+    const int c = blk * cblk + tid;
+    const bool active = tid < cblk && c < C;
+    const bool shfl_ok = (cg & (cg - 1)) == 0 && cg <= 32;
+    int b = roi_batch[r];
+    b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+
+    float yq[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) yq[p] = active ? __ldg(Yq + ((size_t)r * PP + p) * C + c) : 0.f;
+    const float gamma = active ? __ldg(gn_w + c) : 0.f, beta = active ? __ldg(gn_b + c) : 0.f;
+    float wfc[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        wfc[j] = active ? (j < 2 ? __ldg(fc_cls_w + (size_t)j * C + c) : __ldg(fc_reg_w + (size_t)(j - 2) * C + c)) : 0.f;
+    const float inv_cnt = 1.0f / (float)(cg * PP);
+
+    for (int n = 0; n < N; ++n) {
+        const float *ys = Ys + ((size_t)(b * N + n) * PP) * C + c;
+        float y[PP];
+        float s1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            y[p] = active ? yq[p] + __ldg(ys + (size_t)p * C) : 0.f;
+            s1 += y[p];
+        }
+        float gs;
+        if (shfl_ok) gs = group_sum_shfl(s1, cg);
+        else {
+            __syncthreads(); scratch[tid] = s1; __syncthreads();
+            const int g0 = (tid / cg) * cg; gs = 0.f;
+            for (int i = 0; i < cg; ++i) gs += scratch[g0 + i];
+        }
+        const float mean = gs * inv_cnt;
+        float s2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) { const float d = y[p] - mean; s2 = fmaf(d, d, s2); }
+        if (!active) s2 = 0.f;
+        if (shfl_ok) gs = group_sum_shfl(s2, cg);
+        else {
+            __syncthreads(); scratch[tid] = s2; __syncthreads();
+            const int g0 = (tid / cg) * cg; gs = 0.f;
+            for (int i = 0; i < cg; ++i) gs += scratch[g0 + i];
+        }
+        const float rstd = 1.0f / sqrtf(gs * inv_cnt + eps);
+        // GroupNorm affine as torch does it: y*scale + shift, scale = rstd*gamma
+        const float scale = rstd * gamma, shift = beta - mean * scale;
+        float z = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) z += fmaxf(fmaf(y[p], scale, shift), 0.f);
+        z = active ? z / (float)PP : 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float v = warp_sum(z * wfc[j]);
+            if (lane == 0) fc_part[((size_t)n * 6 + j) * nwarps + warp] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N * 6; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += fc_part[(size_t)i * nwarps + w];
+        partial[((size_t)r * N * 6 + i) * nblk + blk] = s;
+    }
+}
+
+// One thread per RoI: sum channel-block partials, add FC biases, write raw [R*N,2]/[R*N,4] if
+// asked, and re-assemble (count_modified_cls_bbox, generalised from N in {1,3} to any N):
+//   N == 1: cls_out = raw[:, [1,0]]
+//   N  > 1: fg_n = raw[n,1]; j = argmax_n fg_n (first max); cls_out = (fg_0..fg_{N-1}, raw[j,0])
+//   reg_out = raw_reg.view(R, 4N)
+__global__ void relation_finalize_kernel(const float *__restrict__ partial, const int R, const int N,
+                                         const int nblk, const float *__restrict__ fc_cls_b,
+                                         const float *__restrict__ fc_reg_b,
+                                         float *__restrict__ cls_out, float *__restrict__ reg_out,
+                                         float *__restrict__ raw_cls, float *__restrict__ raw_reg)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float bc0 = fc_cls_b[0], bc1 = fc_cls_b[1];
+    float best_fg = 0.f, best_bg = 0.f;
+    for (int n = 0; n < N; ++n) {
+        float v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            float s = 0.f;
+            const float *p = partial + ((size_t)r * N * 6 + (size_t)n * 6 + j) * nblk;
+            for (int k = 0; k < nblk; ++k) s += p[k];
+            v[j] = s + (j == 0 ? bc0 : j == 1 ? bc1 : fc_reg_b[j - 2]);
+        }
+        if (raw_cls) { raw_cls[((size_t)r * N + n) * 2] = v[0]; raw_cls[((size_t)r * N + n) * 2 + 1] = v[1]; }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            reg_out[(size_t)r * 4 * N + 4 * n + d] = v[2 + d];
+            if (raw_reg) raw_reg[((size_t)r * N + n) * 4 + d] = v[2 + d];
+        }
+        cls_out[(size_t)r * (N + 1) + n] = v[1];
+        const bool better = n == 0 || v[1] > best_fg || (v[1] != v[1] && best_fg == best_fg);
+        if (better) { best_fg = v[1]; best_bg = v[0]; }
+    }
+    cls_out[(size_t)r * (N + 1) + N] = best_bg;
+}
+
+// Stand-alone count_modified_cls_bbox (fgn_roi_head.py:302-326) on already computed head outputs.
+__global__ void cls_bbox_reassemble_kernel(const float *__restrict__ raw_cls, const float *__restrict__ raw_reg,
+                                           const int R, const int N, float *__restrict__ cls_out,
+                                           float *__restrict__ reg_out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float best_fg = 0.f, best_bg = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float bg = raw_cls[((size_t)r * N + n) * 2], fg = raw_cls[((size_t)r * N + n) * 2 + 1];
+        cls_out[(size_t)r * (N + 1) + n] = fg;
+        if (n == 0 || fg > best_fg || (fg != fg && best_fg == best_fg)) { best_fg = fg; best_bg = bg; }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) reg_out[(size_t)r * 4 * N + 4 * n + d] = raw_reg[((size_t)r * N + n) * 4 + d];
+    }
+    cls_out[(size_t)r * (N + 1) + N] = best_bg;
+}
+
+struct RelationWs {
+    float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc;
+    size_t bytes;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static RelationWs carve(void *base, int R, int BN, int C, int P, int N_for_partial)
+{
+    RelationWs w;
+    const size_t PP = (size_t)P * P;
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align256(bytes); return (float *)p; };
+    w.yq      = take((size_t)R * PP * C * 4);
+    w.ys      = take((size_t)BN * PP * C * 4);
+    w.xq_nhwc = take((size_t)R * PP * C * 4);     // only used when roi_feat arrives NCHW
+    w.xs_nhwc = take((size_t)BN * PP * C * 4);
+    const int nblk_max = ceil_div(C, 32);
+    w.partial = take((size_t)R * (size_t)N_for_partial * 6 * nblk_max * 4);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace fgn
+
+using namespace fgn;
+
+extern "C" size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P)
+{
+    if (R < 0 || BN <= 0 || C <= 0 || P <= 0) return 0;
+    // partial is sized for N <= BN classes per RoI
+    return carve(nullptr, R, BN, C, P, BN).bytes;
+}
+
+extern "C" int fgn_nchw_to_nhwc(const float *, int, int, int, int, float *, void *);
+
+extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
+                                       const int32_t *roi_batch, const float *spp_cat_mean, int R,
+                                       int B, int N, int C, int P, const float *conv_w,
+                                       const float *conv_b, const float *gn_w, const float *gn_b,
+                                       int gn_groups, float gn_eps, const float *fc_cls_w,
+                                       const float *fc_cls_b, const float *fc_reg_w,
+                                       const float *fc_reg_b, float *cls_out, float *reg_out,
+                                       float *raw_cls_out, float *raw_reg_out, int precision,
+                                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(R >= 0 && B > 0 && N > 0 && C > 0 && P > 0, "bad dims R=%d B=%d N=%d C=%d P=%d", R, B, N, C, P);
+    FGN_CHECK_ARG(gn_groups > 0 && C % gn_groups == 0, "GroupNorm groups=%d does not divide C=%d", gn_groups, C);
+    FGN_CHECK_ARG(precision == 0 || precision == 1, "precision=%d", precision);
+    if (R == 0) return FGN_OK;
+    if (P * P != kMaxPP) { set_error("relation_fusion: P=%d not instantiated (7)", P); return FGN_ERR_UNSUPPORTED; }
+    FGN_CHECK_ARG(roi_feat && roi_batch && spp_cat_mean && conv_w && conv_b && gn_w && gn_b &&
+                  fc_cls_w && fc_cls_b && fc_reg_w && fc_reg_b && cls_out && reg_out, "NULL pointer");
+    const int BN = B * N, PP = P * P;
+    const size_t need = fgn_relation_fusion_workspace_bytes(R, BN, C, P);
+    if (!workspace || workspace_bytes < need) {
+        set_error("relation_fusion: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RelationWs w = carve(workspace, R, BN, C, P, BN);
+
+    // operands as row-major [rows, C] (NHWC); repack when the caller hands over NCHW
+    const float *xq = roi_feat, *xs = spp_cat_mean;
+    if (feat_layout == FGN_LAYOUT_NCHW) {
+        int rc = fgn_nchw_to_nhwc(roi_feat, R, C, P, P, w.xq_nhwc, stream);
+        if (rc) return rc;
+        rc = fgn_nchw_to_nhwc(spp_cat_mean, BN, C, P, P, w.xs_nhwc, stream);
+        if (rc) return rc;
+        xq = w.xq_nhwc; xs = w.xs_nhwc;
+    }
+    // Yq = Xq Wq^T ; Ys = Xs Ws^T + bias        (conv_w is [C, 2C] row-major)
+    int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, st);
+    if (rc) return rc;
+    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, st);
+    if (rc) return rc;
+
+    const int cg = C / gn_groups;
+    FGN_CHECK_ARG(cg <= kEpiThreads, "channels per group %d > %d", cg, kEpiThreads);
+    const int cblk = (kEpiThreads / cg) * cg;
+    const int nblk = ceil_div(C, cblk);
+    const int nwarps = kEpiThreads / 32;
+    const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
+    if (smem > 48 * 1024)
+        FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FGN_CHECK_ARG(nblk <= 65535, "nblk");
+    relation_epilogue_kernel<kMaxPP><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
+        w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
+    FGN_LAUNCH_OK();
+    relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(w.partial, R, N, nblk, fc_cls_b, fc_reg_b,
+                                                              cls_out, reg_out, raw_cls_out, raw_reg_out);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+extern "C" int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, int N,
+                                       float *cls_out, float *reg_out, void *stream)
+{
+    FGN_CHECK_ARG(R >= 0 && N > 0, "bad dims R=%d N=%d", R, N);
+    if (R == 0) return FGN_OK;
+    FGN_CHECK_ARG(raw_cls && raw_reg && cls_out && reg_out, "NULL pointer");
+    cls_bbox_reassemble_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(raw_cls, raw_reg, R, N,
+                                                                                cls_out, reg_out);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P)
+{
+    if (R < 0 || BN <= 0 || C <= 0 || P <= 0) return 0;
+    return align256((size_t)R * P * P * C * 4) + align256((size_t)R * 4) +
+           fgn_relation_fusion_workspace_bytes(R, BN, C, P);
+}
+
+__global__ void roi_batch_kernel(const float *__restrict__ rois, int R, int32_t *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) out[r] = (int)rois[5 * (size_t)r];
+}
+
+extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois,
+                                        int R, int P, int sampling_ratio, int aligned,
+                                        float finest_scale, const float *spp_cat_mean, int N,
+                                        const float *conv_w, const float *conv_b,
+                                        const float *gn_w, const float *gn_b, int gn_groups,
+                                        float gn_eps, const float *fc_cls_w, const float *fc_cls_b,
+                                        const float *fc_reg_w, const float *fc_reg_b,
+                                        float *cls_out, float *reg_out, int32_t *lvl_out,
+                                        int precision, void *workspace, size_t workspace_bytes,
+                                        void *stream)
+{
+    FGN_CHECK_ARG(R >= 0 && B > 0 && N > 0 && C > 0 && P > 0, "bad dims");
+    if (R == 0) return FGN_OK;
+    const size_t need = fgn_guided_roi_fused_workspace_bytes(R, B * N, C, P);
+    if (!workspace || workspace_bytes < need) {
+        set_error("guided_roi_fused: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    char *ws = (char *)workspace;
+    float *feat = (float *)ws;                ws += align256((size_t)R * P * P * C * 4);
+    int32_t *rb = (int32_t *)ws;              ws += align256((size_t)R * 4);
+    int rc = fgn_roi_align_ml_fwd(pyr, B, C, FGN_LAYOUT_NHWC, rois, R, P, sampling_ratio, aligned,
+                                  finest_scale, nullptr, nullptr, feat, FGN_LAYOUT_NHWC, lvl_out, stream);
+    if (rc) return rc;
+    roi_batch_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(rois, R, rb);
+    FGN_LAUNCH_OK();
+    return fgn_relation_fusion_fwd(feat, FGN_LAYOUT_NHWC, rb, spp_cat_mean, R, B, N, C, P, conv_w,
+                                   conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b,
+                                   fc_reg_w, fc_reg_b, cls_out, reg_out, nullptr, nullptr, precision,
+                                   ws, workspace_bytes - (size_t)(ws - (char *)workspace), stream);
+}

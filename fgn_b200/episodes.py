@@ -1,0 +1,221 @@
+"""Episodes: synthetic inputs for the BASELINE.json configs, the per-episode hot-path driver, and
+episode sharding across the GPUs of one box.
+
+An *episode* is one query image with its N-way K-shot support set.  Episodes
+are independent (RoIs only ever meet their own query's supports: fgn_roi_head.py:266-268), so the
+multi-GPU scheme is: contiguous episode blocks per rank, weights replicated, no data-path
+collective; NCCL only gathers the fixed-size per-episode results.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class EpisodeConfig:
+    name: str
+    mode: str                    # "c4" (the reference's actual single-level path) or "fpn"
+    n_ways: int
+    k_shots: int
+    channels: int
+    img_h: int
+    img_w: int
+    spp_size: int
+    strides: Tuple[int, ...]     # RoI-extractor levels
+    rpn_strides: Tuple[int, ...]  # levels the AG-RPN attention is applied to (adds P6 in FPN mode)
+    num_rois: int
+    mask_rois: int = 100
+    mask_size: int = 7
+    batch: int = 1               # query images per episode call
+    cfg_id: int = 0
+
+
+FPN = (4, 8, 16, 32)
+FPN_RPN = (4, 8, 16, 32, 64)
+
+# SURVEY section 8d "Config shapes"
+CONFIGS: Dict[str, EpisodeConfig] = {c.name: c for c in [
+    EpisodeConfig("cfg1_mnistiseg_n1k1_c4", "c4", 1, 1, 1024, 480, 480, 128, (16,), (16,), 300, cfg_id=1),
+    EpisodeConfig("cfg2_omniiseg_n3k1_c4", "c4", 3, 1, 1024, 512, 512, 128, (16,), (16,), 300, cfg_id=2),
+    EpisodeConfig("cfg3_coco2voc_n1k1_fpn", "fpn", 1, 1, 256, 800, 1344, 256, FPN, FPN_RPN, 1000, cfg_id=3),
+    EpisodeConfig("cfg4_coco2voc_n20k5_fpn", "fpn", 20, 5, 256, 800, 1344, 256, FPN, FPN_RPN, 1000, cfg_id=4),
+    EpisodeConfig("cfg5_coco2voc_mask_fpn", "fpn", 1, 1, 256, 800, 1344, 256, FPN, FPN_RPN, 512,
+                  mask_rois=100, mask_size=14, batch=16, cfg_id=5),
+    EpisodeConfig("cfg3_c4_exact", "c4", 1, 1, 1024, 800, 1344, 256, (16,), (16,), 1000, cfg_id=6),
+    # small shapes for tests / smoke
+    EpisodeConfig("tiny_fpn", "fpn", 3, 2, 64, 128, 192, 64, FPN, FPN_RPN, 96, mask_rois=16, cfg_id=7),
+    EpisodeConfig("tiny_c4", "c4", 3, 1, 64, 128, 160, 64, (16,), (16,), 64, mask_rois=16, cfg_id=8),
+]}
+
+
+def level_hw(img_h: int, img_w: int, stride: int) -> Tuple[int, int]:
+    return math.ceil(img_h / stride), math.ceil(img_w / stride)
+
+
+def synth_rois(g: torch.Generator, n: int, img_h: int, img_w: int, batch: int, smin: float = 16.0) -> torch.Tensor:
+    """R proposals per call: centre uniform in the image, log2(sqrt(area)) uniform in
+    [log2 smin, log2 min(H,W)], aspect log-uniform in [1/3,3], clipped to the image, sorted by image
+    then by a descending fake score (i.e. spatially unsorted, like RPN output)."""
+    cx = torch.rand(n, generator=g) * img_w
+    cy = torch.rand(n, generator=g) * img_h
+    s = torch.exp(torch.rand(n, generator=g) * math.log(min(img_h, img_w) / smin)) * smin
+    ar = torch.exp((torch.rand(n, generator=g) - 0.5) * 2 * math.log(3.0))
+    w, h = s * torch.sqrt(ar), s / torch.sqrt(ar)
+    x1, y1 = (cx - w / 2).clamp(0, img_w), (cy - h / 2).clamp(0, img_h)
+    x2, y2 = (cx + w / 2).clamp(0, img_w), (cy + h / 2).clamp(0, img_h)
+    b = (torch.arange(n) * batch // max(n, 1)).float()          # equal split, grouped by image
+    return torch.stack([b, x1, y1, x2, y2], 1).float()
+
+
+def synth_support(g: torch.Generator, m: int, s: int):
+    """Support boxes: centred, side 0.8*S (spp_fill_ratio, fgn_train.py:40), +-4 px jitter.
+    Masks: random ellipse xor Bernoulli(0.1) speckle inside the box.  -> ([m,1,4] XYXY, [m,1,s,s] bool)."""
+    side = 0.8 * s
+    c = s / 2 + (torch.rand(m, 2, generator=g) - 0.5) * 8
+    boxes = torch.stack([c[:, 0] - side / 2, c[:, 1] - side / 2, c[:, 0] + side / 2, c[:, 1] + side / 2], 1)
+    yy, xx = torch.meshgrid(torch.arange(s).float(), torch.arange(s).float(), indexing="ij")
+    ax = (side / 2 * (0.5 + 0.5 * torch.rand(m, generator=g))).view(m, 1, 1)
+    ay = (side / 2 * (0.5 + 0.5 * torch.rand(m, generator=g))).view(m, 1, 1)
+    ell = ((xx - c[:, 0].view(m, 1, 1)) / ax) ** 2 + ((yy - c[:, 1].view(m, 1, 1)) / ay) ** 2 <= 1
+    inside = (xx >= boxes[:, 0].view(m, 1, 1)) & (xx <= boxes[:, 2].view(m, 1, 1)) & \
+             (yy >= boxes[:, 1].view(m, 1, 1)) & (yy <= boxes[:, 3].view(m, 1, 1))
+    speck = (torch.rand(m, s, s, generator=g) < 0.1) & inside
+    return boxes.float().view(m, 1, 4), (ell ^ speck).view(m, 1, s, s)
+
+
+def make_episode(cfg: EpisodeConfig, seed: int = 0, relu: bool = False) -> Dict[str, object]:
+    """CPU tensors (reference layout: NCHW fp32) for one episode call of `cfg`.
+    RNG: torch.Generator().manual_seed(1234 + cfg_id + 1000*seed) on CPU."""
+    g = torch.Generator().manual_seed(1234 + cfg.cfg_id + 1000 * seed)
+    m = cfg.batch * cfg.n_ways * cfg.k_shots
+    act = (lambda t: t.relu_()) if relu else (lambda t: t)
+    qry = [act(torch.randn(cfg.batch, cfg.channels, *level_hw(cfg.img_h, cfg.img_w, s), generator=g))
+           for s in cfg.rpn_strides]
+    spp = [act(torch.randn(m, cfg.channels, *level_hw(cfg.spp_size, cfg.spp_size, s), generator=g))
+           for s in cfg.rpn_strides]
+    spp_bboxes, spp_masks = synth_support(g, m, cfg.spp_size)
+    rois = synth_rois(g, cfg.num_rois * cfg.batch, cfg.img_h, cfg.img_w, cfg.batch)
+    det = synth_rois(g, cfg.mask_rois * cfg.batch, cfg.img_h, cfg.img_w, cfg.batch)
+    det_labels = torch.randint(0, cfg.n_ways, (det.shape[0],), generator=g)
+    return dict(cfg=cfg, qry=qry, spp=spp, spp_bboxes=spp_bboxes, spp_masks=spp_masks, rois=rois,
+                det_rois=det, det_labels=det_labels)
+
+
+def episode_to_device(ep: Dict[str, object], device, channels_last: bool = True, pin: bool = False):
+    """Copy an episode to `device`; feature maps optionally as channels_last (the fast layout)."""
+    out = {}
+    for k, v in ep.items():
+        if isinstance(v, list):
+            vs = []
+            for t in v:
+                t = t.to(device, non_blocking=True)
+                if channels_last:
+                    t = t.contiguous(memory_format=torch.channels_last)
+                vs.append(t)
+            out[k] = vs
+        elif torch.is_tensor(v):
+            out[k] = v.to(device, non_blocking=True)
+        else:
+            out[k] = v
+    return out
+
+
+def make_weights(channels: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Relation-head parameters: Kaiming-normal conv (fgn_roi_head.py:247), Xavier-normal FCs,
+    GN affine perturbed around (1,0) so the affine path is exercised."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    c = channels
+    return dict(
+        conv_w=torch.randn(c, 2 * c, generator=g) * math.sqrt(2.0 / (2 * c)),
+        conv_b=torch.randn(c, generator=g) * 0.05,
+        gn_w=1.0 + 0.1 * torch.randn(c, generator=g), gn_b=0.1 * torch.randn(c, generator=g),
+        fc_cls_w=torch.randn(2, c, generator=g) * math.sqrt(2.0 / (c + 2)), fc_cls_b=torch.randn(2, generator=g) * 0.05,
+        fc_reg_w=torch.randn(4, c, generator=g) * math.sqrt(2.0 / (c + 4)), fc_reg_b=torch.randn(4, generator=g) * 0.05,
+    )
+
+
+def load_weights(head, w: Dict[str, torch.Tensor]) -> None:
+    c = w["conv_w"].shape[0]
+    with torch.no_grad():
+        head.cls_reg_shared_conv.weight.copy_(w["conv_w"].view(c, 2 * c, 1, 1))
+        head.cls_reg_shared_conv.bias.copy_(w["conv_b"])
+        head.cls_reg_shared_conv_norm.weight.copy_(w["gn_w"])
+        head.cls_reg_shared_conv_norm.bias.copy_(w["gn_b"])
+        head.bbox_head.fc_cls.weight.copy_(w["fc_cls_w"])
+        head.bbox_head.fc_cls.bias.copy_(w["fc_cls_b"])
+        head.bbox_head.fc_reg.weight.copy_(w["fc_reg_w"])
+        head.bbox_head.fc_reg.bias.copy_(w["fc_reg_b"])
+    head._params_cache = None
+
+
+def build_heads(cfg: EpisodeConfig, device, seed: int = 0, shared_head=None):
+    """(AGRPNHead, FGNRoIHead) for `cfg` with make_weights() loaded; eval mode, on `device`."""
+    from .ag_rpn_head import AGRPNHead
+    from .roi_head import FGNRoIHead
+    ext = dict(type="SingleRoIExtractor", roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+               out_channels=cfg.channels, featmap_strides=list(cfg.strides))
+    mext = None
+    if cfg.mask_size != 7:
+        mext = dict(type="SingleRoIExtractor", roi_layer=dict(type="RoIAlign", output_size=cfg.mask_size, sampling_ratio=0),
+                    out_channels=cfg.channels, featmap_strides=list(cfg.strides))
+    head = FGNRoIHead(bbox_roi_extractor=ext, mask_roi_extractor=mext, shared_head=shared_head, channels=cfg.channels,
+                      n_ways=cfg.n_ways, k_shots=cfg.k_shots)
+    load_weights(head, make_weights(cfg.channels, seed))
+    rpn = AGRPNHead(in_channels=cfg.channels, feat_channels=cfg.channels, n_ways=cfg.n_ways, k_shots=cfg.k_shots)
+    return rpn.to(device).eval(), head.to(device).eval()
+
+
+def run_guided_path(rpn, head, ep: Dict[str, object], with_attention: bool = True, with_mask: bool = True):
+    """One pass of the hot path over one episode call (device tensors):
+       a1 AG-RPN attention on every RPN level, a2 support vectors, a4-a8 guided RoIAlign + relation
+       fusion + heads, a9 mask-branch RoIAlign with AG-FCN attention.  Returns the result dict."""
+    cfg: EpisodeConfig = ep["cfg"]
+    out = {}
+    n_ext = len(cfg.strides)
+    if with_attention:
+        mods = []
+        for q, s in zip(ep["qry"], ep["spp"]):
+            _, mod = rpn.attention(q, s)
+            mods.append(mod)
+        out["qry_fmap_mod"] = mods
+    ext_levels = ep["qry"][:n_ext] if cfg.mode == "fpn" else ep["qry"][0]
+    spp_levels = ep["spp"][:n_ext] if cfg.mode == "fpn" else ep["spp"][0]
+    head.count_spp(spp_levels, ep["spp_bboxes"].clone() if not head.mutate_inputs else ep["spp_bboxes"].clone(),
+                   ep["spp_masks"])
+    res = head._bbox_forward(ext_levels, ep["rois"], need_feats=False)
+    out["cls_score"], out["bbox_pred"] = res["cls_score"], res["bbox_pred"]
+    if with_mask:
+        det = ep["det_rois"]
+        labels = [ep["det_labels"][det[:, 0] == b] for b in range(cfg.batch)]
+        head.gather_mask_vectors(labels)
+        out["mask_feats"] = head._mask_forward(ext_levels, det)["mask_feats"]
+    return out
+
+
+# ---- sharding across the GPUs of one box ----------------------------------------------------------
+def shard_range(num_episodes: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of episodes for `rank`; remainders go to the low ranks."""
+    base, rem = divmod(num_episodes, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local: torch.Tensor, num_episodes: int, group=None) -> torch.Tensor:
+    """all_gather of per-episode results [E_local, ...] -> [E, ...] on every rank (NCCL on GPU, gloo
+    in the CPU tests).  Blocks may differ by one episode, so they are padded to the largest block."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_range(num_episodes, world, r) for r in range(world)]
+    emax = max(hi - lo for lo, hi in sizes)
+    pad = local.new_zeros((emax,) + tuple(local.shape[1:]))
+    pad[: local.shape[0]] = local
+    out = local.new_empty((world * emax,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, pad, group=group)
+    chunks = [out[r * emax: r * emax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    return torch.cat(chunks, 0)

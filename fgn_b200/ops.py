@@ -1,0 +1,405 @@
+"""Tensor-level wrappers over the C ABI (include/fgn_b200.h).
+
+PyTorch is used for device memory and streams only; every computation below is a call into
+libfgn_b200.so.  There is no CPU path: CPU tensors raise ``FgnError``.
+
+Layouts: tensors keep the reference's *logical* NCHW shapes.  Storage may be contiguous NCHW
+(the reference's layout) or ``torch.channels_last`` (NHWC, the fast layout).  Kernels read
+either; outputs follow ``out_format``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, FgnError, Pyramid
+
+__all__ = [
+    "map_roi_levels", "roi_align_multilevel", "roi_align_sample_indices", "to_nhwc", "support_mask_pool",
+    "support_pool", "attention_vectors", "channel_attention", "best_class_select",
+    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "launch_count",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FgnError("fgn_b200 has no CPU fallback: expected CUDA tensors, got device=%s" % t.device)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise FgnError(f"{name}: expected float32, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def storage_layout(t: torch.Tensor) -> Optional[int]:
+    """LAYOUT_NHWC / LAYOUT_NCHW for a densely packed 4-D tensor, None if it is neither."""
+    if t.dim() != 4:
+        return None
+    b, c, h, w = t.shape
+    st = t.stride()
+
+    def ok(expected):
+        # strides of size-1 dims are irrelevant
+        return all(s == e or n == 1 for s, e, n in zip(st, expected, t.shape))
+
+    nchw = ok((c * h * w, h * w, w, 1))
+    nhwc = ok((h * w * c, 1, w * c, c))
+    if nhwc and not nchw:
+        return LAYOUT_NHWC
+    if nchw:
+        return LAYOUT_NCHW
+    return None
+
+
+def _dense(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    lay = storage_layout(t)
+    if lay is None:
+        t = t.contiguous()
+        lay = LAYOUT_NCHW
+    return t, lay
+
+
+def _empty_like_format(shape, device, layout: int) -> torch.Tensor:
+    """Logical NCHW-shaped fp32 tensor whose storage is NCHW or NHWC."""
+    n, c, h, w = shape
+    if layout == LAYOUT_NHWC:
+        return torch.empty((n, h, w, c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+    return torch.empty((n, c, h, w), device=device, dtype=torch.float32)
+
+
+def _fmt(name: str) -> int:
+    if name in ("nchw", "contiguous"):
+        return LAYOUT_NCHW
+    if name in ("nhwc", "channels_last"):
+        return LAYOUT_NHWC
+    raise ValueError(f"unknown memory format {name!r}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().fgn_launch_count())
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Repack a contiguous NCHW tensor to channels_last storage with the library's own kernel."""
+    _need_cuda(x)
+    x, lay = _dense(_f32(x, "x"))
+    if lay == LAYOUT_NHWC:
+        return x
+    b, c, h, w = x.shape
+    out = _empty_like_format(x.shape, x.device, LAYOUT_NHWC)
+    _lib.check(_lib.load().fgn_nchw_to_nhwc(x.data_ptr(), b, c, h, w, out.data_ptr(), _stream()), "fgn_nchw_to_nhwc")
+    return out
+
+
+def to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x, lay = _dense(_f32(x, "x"))
+    if lay == LAYOUT_NCHW:
+        return x
+    b, c, h, w = x.shape
+    out = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_nhwc_to_nchw(x.data_ptr(), b, c, h, w, out.data_ptr(), _stream()), "fgn_nhwc_to_nchw")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def map_roi_levels(rois: torch.Tensor, num_levels: int, finest_scale: float = 56.0) -> torch.Tensor:
+    """mmdet SingleRoIExtractor.map_roi_levels; returns int64 like ``.long()`` in the reference."""
+    _need_cuda(rois)
+    rois = _f32(rois, "rois").contiguous()
+    r = rois.shape[0]
+    out = torch.empty((r,), device=rois.device, dtype=torch.int32)
+    _lib.check(_lib.load().fgn_map_roi_levels(rois.data_ptr(), r, int(num_levels), float(finest_scale),
+                                              out.data_ptr(), _stream()), "fgn_map_roi_levels")
+    return out.long()
+
+
+def _make_pyramid(feats: Sequence[torch.Tensor], scales: Sequence[float]):
+    if len(feats) != len(scales) or not (1 <= len(feats) <= _lib.FGN_MAX_LEVELS):
+        raise FgnError(f"pyramid needs 1..{_lib.FGN_MAX_LEVELS} levels with one scale each")
+    keep = []
+    lay0 = None
+    b0, c0 = feats[0].shape[:2]
+    pyr = Pyramid()
+    pyr.num_levels = len(feats)
+    for i, (f, s) in enumerate(zip(feats, scales)):
+        _need_cuda(f)
+        f, lay = _dense(_f32(f, f"feats[{i}]"))
+        if f.shape[0] != b0 or f.shape[1] != c0:
+            raise FgnError("all pyramid levels must share batch and channel dims")
+        if lay0 is None:
+            lay0 = lay
+        elif lay != lay0:   # mixed storage: bring everything to the first level's layout
+            f = to_nhwc(f) if lay0 == LAYOUT_NHWC else to_nchw(f)
+        keep.append(f)
+        pyr.feat[i] = f.data_ptr()
+        pyr.H[i] = f.shape[2]
+        pyr.W[i] = f.shape[3]
+        pyr.spatial_scale[i] = float(s)
+    return pyr, keep, lay0, b0, c0
+
+
+def roi_align_multilevel(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: Sequence[float],
+                         output_size: int = 7, sampling_ratio: int = 0, aligned: bool = True,
+                         finest_scale: float = 56.0, chan_scale: Optional[torch.Tensor] = None,
+                         scale_index: Optional[torch.Tensor] = None, out_format: str = "nchw",
+                         return_levels: bool = False, nchw_input: str = "repack", force_direct: bool = False):
+    """Level assignment + RoIAlign (avg) in one kernel.  ``feats``: list of [B,C,H_l,W_l].
+
+    ``nchw_input``: what to do with reference-layout (contiguous NCHW) inputs --
+    "repack" converts them to channels_last with fgn_nchw_to_nhwc and runs the fast kernel,
+    "direct" runs the NCHW kernel that keeps the reference's exact summation order.
+    """
+    _need_cuda(rois, chan_scale, scale_index)
+    rois = _f32(rois, "rois").contiguous()
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        raise FgnError("rois must be [R,5] (batch_idx, x1, y1, x2, y2)")
+    feats = list(feats)
+    c = feats[0].shape[1]
+    if nchw_input == "repack" and not force_direct and c % 4 == 0:
+        feats = [to_nhwc(f) if storage_layout(f) != LAYOUT_NHWC else f for f in feats]
+    pyr, keep, lay, b, c = _make_pyramid(feats, scales)
+    r = rois.shape[0]
+    p = int(output_size)
+    out_lay = _fmt(out_format)
+    out = _empty_like_format((r, c, p, p), rois.device, out_lay)
+    lvl = torch.empty((r,), device=rois.device, dtype=torch.int32) if return_levels else None
+    if chan_scale is not None:
+        chan_scale = _f32(chan_scale, "chan_scale").reshape(-1, c).contiguous()
+        if scale_index is not None:
+            scale_index = scale_index.to(torch.int32).contiguous()
+    lib = _lib.load()
+    fn = lib.fgn_roi_align_ml_fwd_direct if force_direct else lib.fgn_roi_align_ml_fwd
+    _lib.check(fn(ctypes.byref(pyr), b, c, lay, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)),
+                  float(finest_scale), _ptr(chan_scale), _ptr(scale_index), out.data_ptr(), out_lay,
+                  _ptr(lvl), _stream()), "fgn_roi_align_ml_fwd")
+    return (out, lvl.long()) if return_levels else out
+
+
+def roi_align_sample_indices(hw: Sequence[Tuple[int, int]], rois: torch.Tensor, scales: Sequence[float],
+                             output_size: int = 7, sampling_ratio: int = 0, aligned: bool = True,
+                             finest_scale: float = 56.0, max_grid: int = 32):
+    """Integer side of roi_align_multilevel: (levels [R], grid [R,2], ytab [R,P,G,3], xtab [R,P,G,3])."""
+    _need_cuda(rois)
+    rois = _f32(rois, "rois").contiguous()
+    pyr = Pyramid()
+    pyr.num_levels = len(hw)
+    for i, ((h, w), s) in enumerate(zip(hw, scales)):
+        pyr.feat[i] = None
+        pyr.H[i], pyr.W[i], pyr.spatial_scale[i] = int(h), int(w), float(s)
+    r, p = rois.shape[0], int(output_size)
+    dev = rois.device
+    lvl = torch.empty((r,), device=dev, dtype=torch.int32)
+    grid = torch.empty((r, 2), device=dev, dtype=torch.int32)
+    ytab = torch.empty((r, p, max_grid, 3), device=dev, dtype=torch.int32)
+    xtab = torch.empty((r, p, max_grid, 3), device=dev, dtype=torch.int32)
+    _lib.check(_lib.load().fgn_roi_align_sample_indices(
+        ctypes.byref(pyr), rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
+        int(max_grid), lvl.data_ptr(), grid.data_ptr(), ytab.data_ptr(), xtab.data_ptr(), _stream()),
+        "fgn_roi_align_sample_indices")
+    return lvl, grid, ytab, xtab
+
+
+# --------------------------------------------------------------------------------------------
+def support_mask_pool(masks: torch.Tensor, boxes: torch.Tensor, output_size: int = 7) -> torch.Tensor:
+    """roi_align(spp_isegmaps.float(), boxes, 7) of fgn_roi_head.py:429 -> [M,1,P,P]."""
+    _need_cuda(masks, boxes)
+    if masks.dim() == 4:
+        masks = masks[:, 0]
+    if masks.dtype == torch.bool:
+        m8 = masks.contiguous().view(torch.uint8)
+    elif masks.dtype == torch.uint8:
+        m8 = masks.contiguous()
+    else:
+        raise FgnError("support masks must be bool/uint8 (binary), got %s" % masks.dtype)
+    m, sh, sw = m8.shape
+    boxes = _f32(boxes, "boxes").reshape(m, 4).contiguous()
+    p = int(output_size)
+    out = torch.empty((m, 1, p, p), device=m8.device, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_support_mask_pool(m8.data_ptr(), boxes.data_ptr(), m, sh, sw, p, out.data_ptr(),
+                                                 _stream()), "fgn_support_mask_pool")
+    return out
+
+
+def support_pool(f: torch.Tensor, m: torch.Tensor, n_ways: int, k_shots: int, out_format: Optional[str] = None):
+    """Class mean and masked GAP of fgn_roi_head.py:439-447.
+
+    f [B*N*K,C,P,P], m [B*N*K,1,P,P] -> cat_mean [B,N,C,P,P], masked_gap [B,N,C,1,1].
+    """
+    _need_cuda(f, m)
+    f, lay = _dense(_f32(f, "f"))
+    bnk, c, p, _ = f.shape
+    if bnk % (n_ways * k_shots):
+        raise FgnError(f"{bnk} support maps is not a multiple of N*K={n_ways * k_shots}")
+    bn = bnk // k_shots
+    m = _f32(m, "m").reshape(bnk, p * p).contiguous()
+    out_lay = lay if out_format is None else _fmt(out_format)
+    cat = _empty_like_format((bn, c, p, p), f.device, out_lay)
+    gap = torch.empty((bn, c), device=f.device, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_support_pool(f.data_ptr(), lay, m.data_ptr(), bn, int(k_shots), c, p,
+                                            cat.data_ptr(), out_lay, gap.data_ptr(), _stream()), "fgn_support_pool")
+    b = bn // n_ways
+    return cat.view(b, n_ways, c, p, p) if out_lay == LAYOUT_NCHW else cat.unflatten(0, (b, n_ways)), \
+        gap.view(b, n_ways, c, 1, 1)
+
+
+def attention_vectors(spp_fmaps: torch.Tensor, n_ways: int, k_shots: int) -> torch.Tensor:
+    """fgn_ag_rpn_head.py:37-41 -> [B,N,C,1,1]."""
+    _need_cuda(spp_fmaps)
+    x, lay = _dense(_f32(spp_fmaps, "spp_fmaps"))
+    bnk, c, h, w = x.shape
+    if bnk % (n_ways * k_shots):
+        raise FgnError(f"{bnk} support maps is not a multiple of N*K={n_ways * k_shots}")
+    bn = bnk // k_shots
+    if lay == LAYOUT_NHWC and (c % 4 or c > 1024):
+        x, lay = to_nchw(x), LAYOUT_NCHW
+    lib = _lib.load()
+    ws_bytes = lib.fgn_attention_vectors_workspace_bytes(bn, k_shots, c, h, w, lay)
+    ws = torch.empty((max(ws_bytes, 1),), device=x.device, dtype=torch.uint8)
+    vec = torch.empty((bn, c), device=x.device, dtype=torch.float32)
+    _lib.check(lib.fgn_attention_vectors(x.data_ptr(), lay, bn, int(k_shots), c, h, w, vec.data_ptr(),
+                                         ws.data_ptr(), ws_bytes, _stream()), "fgn_attention_vectors")
+    return vec.view(bn // n_ways, n_ways, c, 1, 1)
+
+
+def channel_attention(qry: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    """fgn_ag_rpn_head.py:44-46: [B,C,H,W] x [B,N,C,1,1] -> [B*N,C,H,W] (same storage format as qry)."""
+    _need_cuda(qry, vec)
+    q, lay = _dense(_f32(qry, "qry_fmap"))
+    b, c, h, w = q.shape
+    n = vec.shape[1]
+    v = _f32(vec, "vec").reshape(b * n, c).contiguous()
+    if lay == LAYOUT_NHWC and c % 4:
+        q, lay = to_nchw(q), LAYOUT_NCHW
+    out = _empty_like_format((b * n, c, h, w), q.device, lay)
+    _lib.check(_lib.load().fgn_channel_attention(q.data_ptr(), v.data_ptr(), b, n, c, h, w, lay, out.data_ptr(),
+                                                 _stream()), "fgn_channel_attention")
+    return out
+
+
+def best_class_select(cls: torch.Tensor, reg: torch.Tensor, batch: int, n_ways: int):
+    """fgn_ag_rpn_head.py:87-108 for sigmoid objectness (one score per anchor)."""
+    _need_cuda(cls, reg)
+    cls = to_nchw(_f32(cls, "rpn_cls_score"))
+    reg = to_nchw(_f32(reg, "rpn_bbox_pred"))
+    bn, a, h, w = cls.shape
+    if bn != batch * n_ways or reg.shape != (bn, 4 * a, h, w):
+        raise FgnError("best_class_select: cls [B*N,A,H,W] / reg [B*N,4A,H,W] expected")
+    cls_out = torch.empty((batch, a, h, w), device=cls.device, dtype=torch.float32)
+    reg_out = torch.empty((batch, 4 * a, h, w), device=cls.device, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_best_class_select(cls.data_ptr(), reg.data_ptr(), batch, n_ways, a, h, w,
+                                                 cls_out.data_ptr(), reg_out.data_ptr(), _stream()),
+               "fgn_best_class_select")
+    return cls_out, reg_out
+
+
+# --------------------------------------------------------------------------------------------
+class RelationParams:
+    """Device-resident, contiguous copies of the relation head's parameters."""
+
+    def __init__(self, conv_w, conv_b, gn_w, gn_b, fc_cls_w, fc_cls_b, fc_reg_w, fc_reg_b,
+                 gn_groups: int = 32, gn_eps: float = 1e-5):
+        c = conv_w.shape[0]
+        self.C = c
+        self.conv_w = conv_w.detach().reshape(c, 2 * c).contiguous().float()
+        self.conv_b = (conv_b.detach() if conv_b is not None else torch.zeros(c, device=conv_w.device)).contiguous().float()
+        self.gn_w, self.gn_b = gn_w.detach().contiguous().float(), gn_b.detach().contiguous().float()
+        self.fc_cls_w, self.fc_cls_b = fc_cls_w.detach().contiguous().float(), fc_cls_b.detach().contiguous().float()
+        self.fc_reg_w, self.fc_reg_b = fc_reg_w.detach().contiguous().float(), fc_reg_b.detach().contiguous().float()
+        if self.fc_cls_w.shape != (2, c) or self.fc_reg_w.shape != (4, c):
+            raise FgnError("relation head expects fc_cls [2,C] (num_classes=1) and fc_reg [4,C]")
+        self.gn_groups, self.gn_eps = int(gn_groups), float(gn_eps)
+        _need_cuda(self.conv_w, self.gn_w, self.fc_cls_w, self.fc_reg_w)
+
+
+def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mean: torch.Tensor, n_ways: int,
+                    params: RelationParams, precision: str = "fp32", return_raw: bool = False):
+    """count_one_roi_by_n_spp + bbox_head.forward + count_modified_cls_bbox (fgn_roi_head.py:336-339).
+
+    roi_feat [R,C,P,P]; roi_batch [R] (rois[:,0]); spp_cat_mean [B,N,C,P,P] -> cls [R,N+1], reg [R,4N].
+    """
+    _need_cuda(roi_feat, roi_batch, spp_cat_mean)
+    x, lay = _dense(_f32(roi_feat, "roi_feat"))
+    r, c, p, _ = x.shape
+    s = spp_cat_mean.reshape(-1, c, p, p)
+    s, slay = _dense(_f32(s, "spp_cat_mean"))
+    if slay != lay:
+        s = to_nhwc(s) if lay == LAYOUT_NHWC else to_nchw(s)
+    bn = s.shape[0]
+    b = bn // n_ways
+    rb = roi_batch.to(torch.int32).contiguous()
+    dev = x.device
+    cls = torch.empty((r, n_ways + 1), device=dev, dtype=torch.float32)
+    reg = torch.empty((r, 4 * n_ways), device=dev, dtype=torch.float32)
+    raw_c = torch.empty((r * n_ways, 2), device=dev, dtype=torch.float32) if return_raw else None
+    raw_r = torch.empty((r * n_ways, 4), device=dev, dtype=torch.float32) if return_raw else None
+    lib = _lib.load()
+    wsb = lib.fgn_relation_fusion_workspace_bytes(r, bn, c, p)
+    ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
+    pr = params
+    _lib.check(lib.fgn_relation_fusion_fwd(
+        x.data_ptr(), lay, rb.data_ptr(), s.data_ptr(), r, b, n_ways, c, p,
+        pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(), pr.gn_groups, pr.gn_eps,
+        pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(), pr.fc_reg_b.data_ptr(),
+        cls.data_ptr(), reg.data_ptr(), _ptr(raw_c), _ptr(raw_r), {"fp32": 0, "bf16": 1}[precision],
+        ws.data_ptr(), wsb, _stream()), "fgn_relation_fusion_fwd")
+    return (cls, reg, raw_c, raw_r) if return_raw else (cls, reg)
+
+
+def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: Sequence[float],
+                     spp_cat_mean: torch.Tensor, n_ways: int, params: RelationParams, output_size: int = 7,
+                     sampling_ratio: int = 0, aligned: bool = True, finest_scale: float = 56.0,
+                     precision: str = "fp32", return_levels: bool = False):
+    """FPN-mode single call: level assignment + RoIAlign + relation fusion + heads."""
+    _need_cuda(rois, spp_cat_mean)
+    rois = _f32(rois, "rois").contiguous()
+    feats = [to_nhwc(f) if storage_layout(f) != LAYOUT_NHWC else f for f in feats]
+    pyr, keep, lay, b, c = _make_pyramid(feats, scales)
+    p = int(output_size)
+    s = to_nhwc(_f32(spp_cat_mean.reshape(-1, c, p, p), "spp_cat_mean"))
+    bn = s.shape[0]
+    if bn != b * n_ways:
+        raise FgnError(f"spp_cat_mean has {bn} class maps, expected B*N={b * n_ways}")
+    r = rois.shape[0]
+    dev = rois.device
+    cls = torch.empty((r, n_ways + 1), device=dev, dtype=torch.float32)
+    reg = torch.empty((r, 4 * n_ways), device=dev, dtype=torch.float32)
+    lvl = torch.empty((r,), device=dev, dtype=torch.int32) if return_levels else None
+    lib = _lib.load()
+    wsb = lib.fgn_guided_roi_fused_workspace_bytes(r, bn, c, p)
+    ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
+    pr = params
+    _lib.check(lib.fgn_guided_roi_fused_fwd(
+        ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
+        s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
+        pr.gn_groups, pr.gn_eps, pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(),
+        pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), {"fp32": 0, "bf16": 1}[precision],
+        ws.data_ptr(), wsb, _stream()), "fgn_guided_roi_fused_fwd")
+    return (cls, reg, lvl.long()) if return_levels else (cls, reg)
+
+
+def cls_bbox_reassemble(raw_cls: torch.Tensor, raw_reg: torch.Tensor, rois_amount: int, n_ways: int):
+    """count_modified_cls_bbox (fgn_roi_head.py:302-326), generalised to any N."""
+    _need_cuda(raw_cls, raw_reg)
+    raw_cls = _f32(raw_cls, "cls_score").contiguous()
+    raw_reg = _f32(raw_reg, "bbox_pred").contiguous()
+    dev = raw_cls.device
+    cls = torch.empty((rois_amount, n_ways + 1), device=dev, dtype=torch.float32)
+    reg = torch.empty((rois_amount, 4 * n_ways), device=dev, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_cls_bbox_reassemble(raw_cls.data_ptr(), raw_reg.data_ptr(), rois_amount, n_ways,
+                                                   cls.data_ptr(), reg.data_ptr(), _stream()),
+               "fgn_cls_bbox_reassemble")
+    return cls, reg

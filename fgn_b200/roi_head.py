@@ -1,0 +1,271 @@
+"""Relation-Guided Detector / Attention-Guided FCN RoI head -- host-side mirror of FGNRoIHead
+(fgn_roi_head.py:181-719) for the forward hot path.
+
+Method names, argument meaning, tensor layouts and the attributes the reference leaves on ``self``
+(``spp_fmaps_roi_aligned_cat_mean``, ``spp_fvecs_roi_aligned_cat_mean_mp``, ``spp_vecs_mask``) are
+kept.  All RoIAlign / fusion arithmetic runs in libfgn_b200; ``shared_head`` (C4 res5, cuDNN via
+torch.nn) and ``mask_head`` are adjacent modules the head merely hosts.
+Losses, samplers and box post-processing (mmdet [3P]) are not part of this path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .roi_extractor import SingleRoIExtractor, bbox2roi
+
+
+class _Bottleneck(nn.Module):
+    """mmdet Bottleneck [3P] with expansion=2 and no downsample (fgn_roi_head.py:202-233)."""
+
+    def __init__(self, inplanes: int, planes: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, inplanes, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(inplanes)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return self.relu(out + x)
+
+
+def make_c4_shared_head(inplanes: int = 1024, planes: int = 512, num_blocks: int = 3) -> nn.Module:
+    head = nn.Sequential(*[_Bottleneck(inplanes, planes) for _ in range(num_blocks)])
+    for m in head.modules():                                     # fgn_roi_head.py:224-231
+        if isinstance(m, (nn.BatchNorm2d, nn.GroupNorm)):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+    return head
+
+
+class FGNBBoxHead(nn.Module):
+    """Forward part of FGNBBoxHead(BBoxHead) with with_avg_pool=True, num_classes=1,
+    reg_class_agnostic=False (fgn_r50_c4_densecl.py:76-93): holds fc_cls [2,C] and fc_reg [4,C];
+    the avg-pool + FCs themselves run fused inside fgn_relation_fusion_fwd."""
+    n_ways = 3
+    k_shots = 3
+
+    def __init__(self, in_channels: int = 1024, roi_feat_size: int = 7, num_classes: int = 1,
+                 with_avg_pool: bool = True, reg_class_agnostic: bool = False, **kwargs):
+        super().__init__()
+        if not with_avg_pool or num_classes != 1 or reg_class_agnostic:
+            raise NotImplementedError("FGNBBoxHead: the FGN config uses with_avg_pool, num_classes=1, class-specific reg")
+        self.in_channels, self.roi_feat_size = in_channels, roi_feat_size
+        self.fc_cls = nn.Linear(in_channels, num_classes + 1)
+        self.fc_reg = nn.Linear(in_channels, 4 * num_classes)
+        nn.init.xavier_normal_(self.fc_cls.weight)               # init_cfg Xavier/normal for Linear
+        nn.init.xavier_normal_(self.fc_reg.weight)
+        nn.init.zeros_(self.fc_cls.bias)
+        nn.init.zeros_(self.fc_reg.bias)
+
+
+class FGNRoIHead(nn.Module):
+    n_ways = 3
+    k_shots = 3
+    subsampling_ratio = 16
+    spp_fmaps_roi_aligned_cat_mean: torch.Tensor
+    spp_fvecs_roi_aligned_cat_mean_mp: torch.Tensor
+    spp_vecs_mask: torch.Tensor
+
+    def __init__(self, bbox_roi_extractor: Optional[dict] = None, bbox_head: Optional[dict] = None,
+                 mask_roi_extractor: Optional[dict] = None, mask_head: Optional[nn.Module] = None,
+                 shared_head: Union[None, str, nn.Module] = "c4", channels: int = 1024, n_ways: Optional[int] = None,
+                 k_shots: Optional[int] = None, mutate_inputs: bool = True, precision: str = "fp32",
+                 train_cfg=None, test_cfg=None, **kwargs):
+        """``shared_head='c4'`` reproduces the reference, which always builds its res5 ResLayer and
+        ignores the config's ``shared_head=None`` (fgn_roi_head.py:197-200); pass ``None`` for FPN mode.
+        ``channels`` replaces the hard-coded 1024/2048 of fgn_roi_head.py:212,241-243."""
+        super().__init__()
+        bre = bbox_roi_extractor or dict(type="SingleRoIExtractor",
+                                         roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                         out_channels=channels, featmap_strides=[16])
+        bre = {k: v for k, v in bre.items() if k != "type"}
+        self.bbox_roi_extractor = SingleRoIExtractor(**bre)
+        if mask_roi_extractor is not None:
+            mre = {k: v for k, v in mask_roi_extractor.items() if k != "type"}
+            self.mask_roi_extractor = SingleRoIExtractor(**mre)
+            self.share_roi_extractor = False
+        else:                                                      # mmdet shares the bbox extractor [3P]
+            self.mask_roi_extractor = self.bbox_roi_extractor
+            self.share_roi_extractor = True
+        bh = dict(bbox_head or {})
+        bh.pop("type", None)
+        bh.setdefault("in_channels", channels)
+        self.bbox_head = FGNBBoxHead(**bh)
+        self.mask_head = mask_head
+        if shared_head == "c4":
+            self.shared_head = make_c4_shared_head(channels, channels // 2, 3)
+        else:
+            self.shared_head = shared_head
+        self.channels = channels
+        self.init_cls_reg_shared_conv()
+        if n_ways is not None:
+            self.n_ways = n_ways
+        if k_shots is not None:
+            self.k_shots = k_shots
+        self.mutate_inputs = mutate_inputs
+        self.precision = precision
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self._params_cache = None
+
+    # ---- construction (fgn_roi_head.py:240-251) -------------------------------------------------
+    def init_cls_reg_shared_conv(self):
+        c = self.channels
+        self.cls_reg_shared_conv = nn.Conv2d(2 * c, c, kernel_size=(1, 1), stride=(1, 1), padding=0)
+        self.cls_reg_shared_conv_norm = nn.GroupNorm(num_groups=32, num_channels=c, affine=True)
+        nn.init.kaiming_normal_(self.cls_reg_shared_conv.weight, nonlinearity="relu")
+        nn.init.ones_(self.cls_reg_shared_conv_norm.weight)
+        nn.init.zeros_(self.cls_reg_shared_conv_norm.bias)
+
+    @property
+    def with_shared_head(self) -> bool:
+        return getattr(self, "shared_head", None) is not None
+
+    @property
+    def with_bbox(self) -> bool:
+        return self.bbox_head is not None
+
+    @property
+    def with_mask(self) -> bool:
+        return self.mask_head is not None
+
+    def shared_head_layer(self, x: torch.Tensor) -> torch.Tensor:
+        return self.shared_head(x)
+
+    def relation_params(self, refresh: bool = False) -> ops.RelationParams:
+        """Packed device copies of the relation-head weights (re-packed when ``refresh`` or in training)."""
+        if self._params_cache is None or refresh or self.training:
+            n = self.cls_reg_shared_conv_norm
+            self._params_cache = ops.RelationParams(
+                self.cls_reg_shared_conv.weight, self.cls_reg_shared_conv.bias, n.weight, n.bias,
+                self.bbox_head.fc_cls.weight, self.bbox_head.fc_cls.bias,
+                self.bbox_head.fc_reg.weight, self.bbox_head.fc_reg.bias, n.num_groups, n.eps)
+        return self._params_cache
+
+    @staticmethod
+    def _as_levels(fmap) -> List[torch.Tensor]:
+        # the reference emulates mmdet's tuple-of-levels with unsqueeze(0) (fgn_roi_head.py:330,365)
+        return list(fmap) if isinstance(fmap, (list, tuple)) else [fmap]
+
+    # ---- support branch (fgn_roi_head.py:419-449) -----------------------------------------------
+    def count_spp(self, spp_fmaps, spp_bboxes: torch.Tensor, spp_isegmaps: torch.Tensor):
+        """
+        :param spp_fmaps: [B*N*K, C, H, W] (C4) or list of such levels (FPN mode)
+        :param spp_bboxes: [B*N*K, 1, 4] XYXY px; divided in place by subsampling_ratio in C4 mode
+        :param spp_isegmaps: [B*N*K, 1, H, W] bool
+        """
+        levels = self._as_levels(spp_fmaps)
+        m = spp_bboxes.shape[0]
+        mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429
+        idx = torch.arange(m, device=spp_bboxes.device, dtype=torch.float32).view(m, 1)
+        if len(levels) == 1:
+            if self.mutate_inputs:
+                spp_bboxes /= self.subsampling_ratio                                             # :430
+                boxes = spp_bboxes
+            else:
+                boxes = spp_bboxes / self.subsampling_ratio
+            rois = torch.cat([idx, boxes.reshape(m, 4).float()], 1)
+            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False)       # :432
+        else:   # A-FPN: level from map_roi_levels on the pixel box, spatial_scale = 1/stride
+            rois = torch.cat([idx, spp_bboxes.reshape(m, 4).float()], 1)
+            ext = self.bbox_roi_extractor
+            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0 / s for s in ext.featmap_strides[: len(levels)]],
+                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale))
+        if self.with_shared_head:
+            feat_ra = self.shared_head_layer(feat_ra)                                            # :435-436
+        cat_mean, mp = ops.support_pool(feat_ra, mask_ra, self.n_ways, self.k_shots)             # :439-447
+        self.spp_fmaps_roi_aligned_cat_mean = cat_mean
+        self.spp_fvecs_roi_aligned_cat_mean_mp = mp
+        return
+
+    # ---- relation-guided detector (fgn_roi_head.py:253-342) ------------------------------------
+    def count_modified_cls_bbox(self, rois_amount: int, cls_score: torch.Tensor, bbox_pred: torch.Tensor):
+        return ops.cls_bbox_reassemble(cls_score, bbox_pred, rois_amount, self.n_ways)
+
+    def _bbox_forward(self, qry_fmap, rois: torch.Tensor, need_feats: Optional[bool] = None):
+        """Box head forward (fgn_roi_head.py:328-342) -> dict(cls_score [R,N+1], bbox_pred [R,4N], bbox_feats).
+
+        ``bbox_feats`` is materialised when a ``shared_head`` sits between RoIAlign and the fusion (C4),
+        or when ``need_feats`` (default: ``self.training``, because the train-time mask branch re-reads
+        it, :373-374); otherwise the FPN single-pass entry point is used and ``bbox_feats`` is None.
+        """
+        levels = self._as_levels(qry_fmap)[: self.bbox_roi_extractor.num_inputs]
+        need_feats = self.training if need_feats is None else need_feats
+        params = self.relation_params()
+        if rois.shape[0] == 0:
+            z = rois.new_zeros
+            return dict(cls_score=z((0, self.n_ways + 1)), bbox_pred=z((0, 4 * self.n_ways)), bbox_feats=None)
+        ext = self.bbox_roi_extractor
+        layer = ext.roi_layers[0]
+        if not self.with_shared_head and not need_feats and layer.output_size[0] == 7:
+            cls, reg = ops.guided_roi_fused(levels, rois, [l.spatial_scale for l in ext.roi_layers][: len(levels)],
+                                            self.spp_fmaps_roi_aligned_cat_mean, self.n_ways, params, 7,
+                                            layer.sampling_ratio, layer.aligned, float(ext.finest_scale), self.precision)
+            return dict(cls_score=cls, bbox_pred=reg, bbox_feats=None)
+        bbox_feats = ext(levels, rois, out_format="nhwc" if not self.with_shared_head else "nchw")
+        if self.with_shared_head:
+            bbox_feats = self.shared_head_layer(bbox_feats)
+        cls, reg = ops.relation_fusion(bbox_feats, rois[:, 0], self.spp_fmaps_roi_aligned_cat_mean, self.n_ways,
+                                       params, self.precision)
+        return dict(cls_score=cls, bbox_pred=reg, bbox_feats=bbox_feats)
+
+    # ---- attention-guided FCN (fgn_roi_head.py:360-382) -----------------------------------------
+    def gather_mask_vectors(self, labels: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Vector gather of simple_test (:707-714) / forward_train (:516-522): label + N * image index."""
+        gather = torch.cat([labels[i] + self.n_ways * i for i in range(len(labels))])
+        batch, n, c = self.spp_fvecs_roi_aligned_cat_mean_mp.shape[:3]
+        assert batch == len(labels) and n == self.n_ways
+        self._spp_vec_index = gather.to(torch.int32)
+        self.spp_vecs_mask = self.spp_fvecs_roi_aligned_cat_mean_mp.view(batch * self.n_ways, c, 1, 1)[gather]
+        return self.spp_vecs_mask
+
+    def _mask_forward(self, qry_fmap, rois=None, pos_inds=None, bbox_feats=None):
+        assert (rois is not None) ^ (pos_inds is not None and bbox_feats is not None)
+        vec = self.spp_vecs_mask
+        if rois is not None:
+            levels = self._as_levels(qry_fmap)[: self.mask_roi_extractor.num_inputs]
+            if not self.with_shared_head:
+                # RoIAlign with the channel attention multiply in its epilogue (K12 fused into K1)
+                mask_feats = self.mask_roi_extractor(levels, rois, chan_scale=vec.reshape(vec.shape[0], -1))
+            else:
+                mask_feats = self.shared_head(self.mask_roi_extractor(levels, rois))
+                mask_feats = ops.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
+        else:
+            pos_inds_new = torch.nonzero(pos_inds).view(-1)
+            mask_feats = ops.channel_attention(bbox_feats[pos_inds_new], vec.reshape(vec.shape[0], 1, -1, 1, 1))
+        assert mask_feats.shape[:2] == vec.shape[:2]
+        mask_pred = self.mask_head(mask_feats) if self.mask_head is not None else None
+        return dict(mask_pred=mask_pred, mask_feats=mask_feats)
+
+    # ---- test-time driver (fgn_roi_head.py:531-616, 675-719), without mmdet post-processing ----
+    def simple_test_bboxes(self, x, img_metas, proposals: Sequence[torch.Tensor], rcnn_test_cfg=None, rescale=False):
+        """Returns per-image (cls_score, bbox_pred) splits.  mmdet's bbox_head.get_bboxes (softmax,
+        delta decode, multiclass NMS) is downstream of the hot path and is not re-implemented."""
+        rois = bbox2roi(proposals)
+        res = self._bbox_forward(x, rois, need_feats=False)
+        n_per = tuple(len(p) for p in proposals)
+        return res["cls_score"].split(n_per, 0), res["bbox_pred"].split(n_per, 0)
+
+    def simple_test_mask(self, x, det_bboxes: Sequence[torch.Tensor], det_labels: Sequence[torch.Tensor]):
+        self.gather_mask_vectors(det_labels)
+        mask_rois = bbox2roi([d[:, :4] for d in det_bboxes])
+        if mask_rois.shape[0] == 0:
+            return dict(mask_pred=None, mask_feats=mask_rois.new_zeros((0, self.channels, 7, 7)))
+        return self._mask_forward(x, mask_rois)
+
+    def simple_test(self, qry_fmap, proposal_list, img_metas=None, proposals=None, rescale=False,
+                    spp_fmaps=None, spp_bboxes=None, spp_isegmaps=None):
+        assert self.with_bbox, "Bbox head must be implemented."
+        self.count_spp(spp_fmaps, spp_bboxes, spp_isegmaps)
+        return self.simple_test_bboxes(qry_fmap, img_metas, proposal_list, self.test_cfg, rescale=rescale)

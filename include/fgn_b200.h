@@ -1,0 +1,179 @@
+/*
+ * fgn_b200.h -- C ABI of libfgn_b200.so: the B200 (sm_100a) implementation of FGN's guided
+ * RoIAlign + support-guided fusion hot path.
+ *
+ * The reference (tooHotSpot/FGN) has no native code and no FFI; the path sits behind Python
+ * modules registered with mmdet.  Each entry point below names the
+ * reference call site (file:line under /root/reference/subprojects/sp02_omniiseg_fgn_mmdet/)
+ * whose device work it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - all tensors are fp32 and densely packed in the stated layout; int tensors are int32;
+ *   - outputs are caller-allocated; no entry point allocates, frees or keeps device memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host;
+ *   - return value: 0 on success, <0 = FGN_ERR_* ; fgn_last_error_string() (thread-local)
+ *     describes the last failure on the calling thread;
+ *   - zero-size problems (R == 0 ...) return 0 without launching anything
+ *     (reference early-outs: fgn_roi_head.py:558-567,596-603,638-640).
+ */
+#ifndef FGN_B200_H_
+#define FGN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGN_ABI_VERSION 1
+
+#define FGN_OK                 0
+#define FGN_ERR_INVALID_ARG   -1
+#define FGN_ERR_UNSUPPORTED   -2
+#define FGN_ERR_CUDA          -3
+#define FGN_ERR_WORKSPACE     -4
+
+/* feature-map / RoI-feature memory layouts */
+#define FGN_LAYOUT_NCHW 0      /* [B,C,H,W]  the reference's layout                      */
+#define FGN_LAYOUT_NHWC 1      /* [B,H,W,C]  torch.channels_last storage; the fast layout */
+
+#define FGN_MAX_LEVELS 8
+
+int         fgn_abi_version(void);
+const char *fgn_last_error_string(void);
+/* number of SMs / compute capability of the current device (host query, for tests/bench) */
+int         fgn_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* mmdet SingleRoIExtractor.map_roi_levels [3P] (config fgn_r50_c4_densecl.py:69-73, reached
+ * from fgn_roi_head.py:331-332,366-367):
+ *   lvl = clamp(floor(log2(sqrt((x2-x1)(y2-y1)) / finest_scale + 1e-6)), 0, L-1)
+ * rois [R,5] (batch_idx,x1,y1,x2,y2) -> lvl_out [R] int32. */
+int fgn_map_roi_levels(const float *rois, int R, int num_levels, float finest_scale,
+                       int32_t *lvl_out, void *stream);
+
+/* Pyramid descriptor passed by value (host struct holding device pointers). */
+typedef struct {
+    int          num_levels;                 /* 1 = the reference's C4 single-level mode */
+    const float *feat[FGN_MAX_LEVELS];       /* level l: [B,C,H_l,W_l] in `layout`       */
+    int          H[FGN_MAX_LEVELS];
+    int          W[FGN_MAX_LEVELS];
+    float        spatial_scale[FGN_MAX_LEVELS];   /* 1/stride_l                          */
+} fgn_pyramid_t;
+
+/* SingleRoIExtractor.forward + mmcv.ops.RoIAlign (avg) [3P], fgn_roi_head.py:331-332,366-367,
+ * and torchvision.ops.roi_align, fgn_roi_head.py:429,432.  Level assignment, the adaptive
+ * sampling grid and bilinear pooling run in one kernel; with num_levels == 1 the level step is
+ * skipped exactly like mmdet's short-circuit.
+ *   rois [R,5]; out [R,C,P,P] in out_layout (NCHW = [R,C,P,P], NHWC = [R,P,P,C]).
+ *   sampling_ratio <= 0 -> adaptive grid ceil(roi/P); aligned: 1 = mmcv default, 0 = torchvision default.
+ *   chan_scale (optional, may be NULL): [S,C] vectors; out[r,c,:,:] *= chan_scale[scale_index[r],c]
+ *     (the AG-FCN attention multiply fgn_roi_head.py:379 with the gather :707-714 fused in);
+ *   lvl_out (optional): [R] int32 level each RoI was pooled from.
+ * in_layout NHWC is the fast path (128-bit channel-vector loads); NCHW input is served by a
+ * direct kernel that keeps the reference layout. */
+int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int in_layout,
+                         const float *rois, int R, int P, int sampling_ratio, int aligned,
+                         float finest_scale,
+                         const float *chan_scale, const int32_t *scale_index,
+                         float *out, int out_layout, int32_t *lvl_out, void *stream);
+
+/* Integer side of the same kernel for the bit-exact check (test/debug export).  For RoI r,
+ * pooled from the level fgn_roi_align_ml_fwd would choose:
+ *   grid_out [R,2]              = (grid_h, grid_w)
+ *   ytab_out [R,P,max_grid,3]   = (valid, y_low, y_high) per (ph, iy), -1 padded past grid_h
+ *   xtab_out [R,P,max_grid,3]   = (valid, x_low, x_high) per (pw, ix)
+ * The (r,ph,pw,iy,ix) sample tuple of the reference is the cartesian product of the two. */
+int fgn_roi_align_sample_indices(const fgn_pyramid_t *pyr, const float *rois, int R, int P,
+                                 int sampling_ratio, int aligned, float finest_scale,
+                                 int max_grid, int32_t *lvl_out, int32_t *grid_out,
+                                 int32_t *ytab_out, int32_t *xtab_out, void *stream);
+
+/* NCHW -> NHWC repack of a feature map (one read, one write); used by the host shim when a
+ * caller hands over reference-layout tensors and wants the fast path. */
+int fgn_nchw_to_nhwc(const float *in, int B, int C, int H, int W, float *out, void *stream);
+int fgn_nhwc_to_nchw(const float *in, int B, int C, int H, int W, float *out, void *stream);
+
+/* count_spp, mask part (fgn_roi_head.py:429): roi_align(spp_isegmaps.float(), boxes, 7) with
+ * spatial_scale=1, sampling_ratio=-1, aligned=False, one box per support image.
+ *   mask [M,S_h,S_w] uint8 (torch.bool storage); boxes [M,4] XYXY px -> out [M,P,P]. */
+int fgn_support_mask_pool(const uint8_t *mask, const float *boxes, int M, int S_h, int S_w,
+                          int P, float *out, void *stream);
+
+/* count_spp, reduction part (fgn_roi_head.py:439-447):
+ *   cat_mean[b,n,c,p] = mean_k f[(b*N+n)*K+k, c, p]
+ *   masked_gap[b,n,c] = mean_{k,p} f[..]*m[(b*N+n)*K+k, p]          (divides by K*P*P)
+ *   f [B*N*K,C,P,P] in f_layout; m [B*N*K,P,P]; cat_mean [B*N,C,P,P] in out_layout;
+ *   masked_gap [B*N,C]. */
+int fgn_support_pool(const float *f, int f_layout, const float *m, int BN, int K, int C, int P,
+                     float *cat_mean, int out_layout, float *masked_gap, void *stream);
+
+/* AGRPNHead class attention vector (fgn_ag_rpn_head.py:37-41):
+ *   vec[b,n,c] = mean_{k,h,w} spp_fmaps[(b*N+n)*K+k, c, h, w]      -> vec [B*N,C]
+ * workspace: fgn_attention_vectors_workspace_bytes(...) bytes (may be 0). */
+size_t fgn_attention_vectors_workspace_bytes(int BN, int K, int C, int H, int W, int layout);
+int fgn_attention_vectors(const float *spp_fmaps, int layout, int BN, int K, int C, int H, int W,
+                          float *vec, void *workspace, size_t workspace_bytes, void *stream);
+
+/* AGRPNHead channel attention (fgn_ag_rpn_head.py:44-46):
+ *   out[b*N+n, c, h, w] = qry[b,c,h,w] * vec[b*N+n, c]
+ *   qry [B,C,H,W], out [B*N,C,H,W], both in `layout`. */
+int fgn_channel_attention(const float *qry, const float *vec, int B, int N, int C, int H, int W,
+                          int layout, float *out, void *stream);
+
+/* AGRPNHead best-class selection (fgn_ag_rpn_head.py:87-108): per anchor position take the
+ * score and the 4 deltas of the class with the largest score (first max wins).
+ *   cls [B*N,A,H,W], reg [B*N,4A,H,W] (NCHW) -> cls_out [B,A,H,W], reg_out [B,4A,H,W]. */
+int fgn_best_class_select(const float *cls, const float *reg, int B, int N, int A, int H, int W,
+                          float *cls_out, float *reg_out, void *stream);
+
+/* Relation-Guided Detector: count_one_roi_by_n_spp (fgn_roi_head.py:253-279) + BBoxHead.forward
+ * with_avg_pool [3P] (:338) + count_modified_cls_bbox (:302-326), fused.  The [R*N,2C,P,P]
+ * concat is never built: conv1x1(cat(q,s)) = Wq q + Ws s + b.
+ *   roi_feat [R,C,P,P] in feat_layout; roi_batch [R] int32 (rois[:,0]);
+ *   spp_cat_mean [B*N,C,P,P] in feat_layout (count_spp's first output);
+ *   conv_w [C,2C] (Conv2d(2C->C,1x1).weight), conv_b [C]; gn_w, gn_b [C] (GroupNorm(32,C));
+ *   fc_cls_w [2,C], fc_cls_b [2]; fc_reg_w [4,C], fc_reg_b [4];
+ *   cls_out [R,N+1], reg_out [R,4N];  raw_cls_out/raw_reg_out optional ([R*N,2]/[R*N,4]).
+ *   precision: 0 = fp32 (3xTF32 error-compensated tensor-core contraction, fp32 parity),
+ *              1 = bf16 operands / fp32 accumulate (reported separately).
+ * workspace: fgn_relation_fusion_workspace_bytes(R, BN, C, P) bytes. */
+size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P);
+int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout, const int32_t *roi_batch,
+                            const float *spp_cat_mean, int R, int B, int N, int C, int P,
+                            const float *conv_w, const float *conv_b,
+                            const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
+                            const float *fc_cls_w, const float *fc_cls_b,
+                            const float *fc_reg_w, const float *fc_reg_b,
+                            float *cls_out, float *reg_out, float *raw_cls_out, float *raw_reg_out,
+                            int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* count_modified_cls_bbox alone (fgn_roi_head.py:302-326), generalised from N in {1,3} to any N:
+ *   raw_cls [R*N,2] (bg,fg), raw_reg [R*N,4] -> cls_out [R,N+1] = (fg_0..fg_{N-1}, bg of the
+ *   first-max fg class), reg_out [R,4N]. */
+int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, int N,
+                            float *cls_out, float *reg_out, void *stream);
+
+/* FPN-mode single pass (no shared_head between RoIAlign and the relation conv): level
+ * assignment + RoIAlign + relation fusion + heads; RoI features never reach HBM.
+ * Same arguments as the two calls it replaces. */
+size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P);
+int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
+                             int P, int sampling_ratio, int aligned, float finest_scale,
+                             const float *spp_cat_mean /* [B*N,P,P,C] NHWC */, int N,
+                             const float *conv_w, const float *conv_b,
+                             const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
+                             const float *fc_cls_w, const float *fc_cls_b,
+                             const float *fc_reg_w, const float *fc_reg_b,
+                             float *cls_out, float *reg_out, int32_t *lvl_out,
+                             int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernels this library has launched in the calling process since load
+ * (bench.py's gpu_launches). */
+uint64_t fgn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGN_B200_H_ */

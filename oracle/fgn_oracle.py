@@ -1,0 +1,309 @@
+"""oracle/fgn_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement (torch CPU, fp32) of FGN's guided RoIAlign + support-guided fusion hot path.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module; nothing under fgn_b200/ does.
+
+Every function cites the reference lines it follows (paths relative to
+/root/reference/subprojects/sp02_omniiseg_fgn_mmdet/).  Third-party arithmetic ([3P]: mmcv-full
+1.3.16 RoIAlign, mmdet 2.18.0 SingleRoIExtractor/bbox2roi/BBoxHead, torchvision 0.10 roi_align --
+requirements.txt:45-46,100-101, none of them under /root/reference) is restated from SURVEY.md
+appendix A; RoIAlign itself is served either by oracle/roi_align_ref.c (plain C, also emits the
+sample indices) or by torch.ops.torchvision.roi_align on CPU (the very op fgn_roi_head.py:429 calls).
+
+Parity pin (see tests/test_oracle.py, tests/golden/make_golden.py):
+  * the FGN-owned functions here are checked against fixtures produced by executing the
+    reference's own, unmodified methods (imported from /root/reference with the mmdet/mmcv
+    imports stubbed) -- tests/golden/fgn_reference_*.npz;
+  * roi_align_ref.c is checked bit-for-bit against torchvision's CPU op;
+  * map_roi_levels and the mmcv RoIAlign (aligned=True) have no reference-side test or golden
+    vector and mmcv/mmdet cannot be installed here: that part is "parity unpinned" beyond
+    torchvision's own aligned=True mode.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_C_SRC = os.path.join(HERE, "roi_align_ref.c")
+_C_LIB = os.path.join(HERE, "_build", "liboracle.so")
+_clib = None
+
+
+def build_c_oracle(force: bool = False) -> str:
+    """gcc -O2 -ffp-contract=off (no FMA, like the CPU wheels) -> oracle/_build/liboracle.so."""
+    if force or not os.path.exists(_C_LIB) or os.path.getmtime(_C_LIB) < os.path.getmtime(_C_SRC):
+        os.makedirs(os.path.dirname(_C_LIB), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _C_LIB, _C_SRC, "-lm"])
+    return _C_LIB
+
+
+def _c():
+    global _clib
+    if _clib is None:
+        _clib = ctypes.CDLL(build_c_oracle())
+    return _clib
+
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(_f32p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(_i32p)
+
+
+# ------------------------------------------------------------------------------------------------
+# [3P] pieces
+# ------------------------------------------------------------------------------------------------
+def bbox2roi(bbox_list: Sequence[torch.Tensor]) -> torch.Tensor:
+    """mmdet.core.bbox2roi [3P] (called at fgn_roi_head.py:348,390,556,654); SURVEY A.2."""
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
+def map_roi_levels(rois: torch.Tensor, num_levels: int, finest_scale: float = 56.0) -> torch.Tensor:
+    """mmdet SingleRoIExtractor.map_roi_levels [3P], SURVEY A.2, as the torch expression."""
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    target_lvls = torch.floor(torch.log2(scale / finest_scale + 1e-6))
+    target_lvls = target_lvls.clamp(min=0, max=num_levels - 1).long()
+    return target_lvls
+
+
+def map_roi_levels_c(rois: torch.Tensor, num_levels: int, finest_scale: float = 56.0) -> torch.Tensor:
+    """Same, through oracle/roi_align_ref.c (the exact contract the CUDA kernel implements)."""
+    r = np.ascontiguousarray(rois.detach().cpu().numpy(), dtype=np.float32)
+    out = np.zeros((r.shape[0],), np.int32)
+    _c().fgn_oracle_map_roi_levels(_fp(r), r.shape[0], int(num_levels), ctypes.c_float(finest_scale), _ip(out))
+    return torch.from_numpy(out).long()
+
+
+def roi_align_tv(feat: torch.Tensor, rois: torch.Tensor, spatial_scale: float, output_size: int,
+                 sampling_ratio: int, aligned: bool) -> torch.Tensor:
+    """torch.ops.torchvision.roi_align on CPU (Detectron ROIAlign; same algorithm as mmcv's)."""
+    import torchvision  # noqa: F401  (registers the op)
+    return torch.ops.torchvision.roi_align(feat.float().contiguous(), rois.float().contiguous(), float(spatial_scale),
+                                           int(output_size), int(output_size), int(sampling_ratio), bool(aligned))
+
+
+def roi_align_c(feat: torch.Tensor, rois: torch.Tensor, spatial_scale: float, output_size: int,
+                sampling_ratio: int, aligned: bool) -> torch.Tensor:
+    """oracle/roi_align_ref.c: SURVEY A.1 restated in plain C, no FMA."""
+    f = np.ascontiguousarray(feat.detach().cpu().numpy(), dtype=np.float32)
+    r = np.ascontiguousarray(rois.detach().cpu().numpy(), dtype=np.float32)
+    b, c, h, w = f.shape
+    n, p = r.shape[0], int(output_size)
+    out = np.zeros((n, c, p, p), np.float32)
+    if n:
+        _c().fgn_oracle_roi_align(_fp(f), b, c, h, w, _fp(r), n, ctypes.c_float(spatial_scale), p, p,
+                                  int(sampling_ratio), int(bool(aligned)), _fp(out))
+    return torch.from_numpy(out)
+
+
+def roi_align(feat, rois, spatial_scale, output_size, sampling_ratio, aligned, impl: str = "tv"):
+    return (roi_align_tv if impl == "tv" else roi_align_c)(feat, rois, spatial_scale, output_size, sampling_ratio, aligned)
+
+
+def roi_align_indices_c(rois: torch.Tensor, lvls: torch.Tensor, hw: Sequence[Tuple[int, int]],
+                        scales: Sequence[float], output_size: int, sampling_ratio: int, aligned: bool,
+                        max_grid: int):
+    """Per-axis sample tables (valid, low, high) of RoIAlign for each RoI at its level."""
+    r = np.ascontiguousarray(rois.detach().cpu().numpy(), dtype=np.float32)
+    n, p = r.shape[0], int(output_size)
+    lv = lvls.cpu().numpy().astype(np.int64)
+    sc = np.asarray([scales[l] for l in lv], np.float32)
+    hws = np.asarray([hw[l] for l in lv], np.int32).reshape(n, 2)
+    grid = np.zeros((n, 2), np.int32)
+    ytab = np.zeros((n, p, max_grid, 3), np.int32)
+    xtab = np.zeros((n, p, max_grid, 3), np.int32)
+    if n:
+        _c().fgn_oracle_roi_align_indices(_fp(r), n, _fp(sc), _ip(hws), p, p, int(sampling_ratio),
+                                          int(bool(aligned)), int(max_grid), _ip(grid), _ip(ytab), _ip(xtab))
+    return torch.from_numpy(grid), torch.from_numpy(ytab), torch.from_numpy(xtab)
+
+
+def single_roi_extractor(feats: Sequence[torch.Tensor], rois: torch.Tensor, strides: Sequence[int],
+                         output_size: int = 7, sampling_ratio: int = 0, aligned: bool = True,
+                         finest_scale: float = 56.0, impl: str = "tv"):
+    """mmdet SingleRoIExtractor.forward [3P], reached from fgn_roi_head.py:331-332,366-367.
+    Returns (roi_feats [R,C,P,P], levels [R])."""
+    num_levels = len(feats)
+    c = feats[0].shape[1]
+    out = feats[0].new_zeros((rois.shape[0], c, output_size, output_size))
+    if num_levels == 1:
+        lv = torch.zeros((rois.shape[0],), dtype=torch.long)
+        if rois.shape[0] == 0:
+            return out, lv
+        return roi_align(feats[0], rois, 1.0 / strides[0], output_size, sampling_ratio, aligned, impl), lv
+    lv = map_roi_levels(rois, num_levels, finest_scale)
+    for i in range(num_levels):
+        inds = (lv == i).nonzero(as_tuple=False).squeeze(1)
+        if inds.numel() > 0:
+            out[inds] = roi_align(feats[i], rois[inds], 1.0 / strides[i], output_size, sampling_ratio, aligned, impl)
+    return out, lv
+
+
+def bbox_head_forward(x: torch.Tensor, fc_cls_w, fc_cls_b, fc_reg_w, fc_reg_b):
+    """mmdet BBoxHead.forward [3P] with with_avg_pool=True (fgn_r50_c4_densecl.py:76-93), SURVEY A.6."""
+    x = F.avg_pool2d(x, x.shape[-1])
+    x = x.view(x.size(0), -1)
+    return F.linear(x, fc_cls_w, fc_cls_b), F.linear(x, fc_reg_w, fc_reg_b)
+
+
+# ------------------------------------------------------------------------------------------------
+# FGN-owned pieces (restated from the reference's own lines)
+# ------------------------------------------------------------------------------------------------
+def agrpn_attention(qry_fmap: torch.Tensor, spp_fmaps: torch.Tensor, n_ways: int, k_shots: int):
+    """fgn_ag_rpn_head.py:33-46 -> (spp_fvecs_cat_mean [B,N,C,1,1], qry_fmap_mod [B*N,C,H,W])."""
+    batch, c, x_h, x_w = qry_fmap.shape
+    qry = qry_fmap[:, None, :, :, :]
+    c, h, w = spp_fmaps.shape[-3:]
+    vec = spp_fmaps.view(batch, n_ways, k_shots, c, h, w).mean(axis=(2, 4, 5)).view(batch, n_ways, c, 1, 1)
+    mod = (qry * vec).view(batch * n_ways, c, x_h, x_w)
+    return vec, mod
+
+
+def best_class_selection(rpn_cls_score: torch.Tensor, rpn_bbox_pred: torch.Tensor, batch: int, n_ways: int):
+    """fgn_ag_rpn_head.py:82-113."""
+    _, c, x_h, x_w = rpn_cls_score.shape
+    cls = rpn_cls_score.view(batch, n_ways, c, x_h, x_w)
+    _, c4, x_h, x_w = rpn_bbox_pred.shape
+    reg = rpn_bbox_pred.view(batch, n_ways, c4, x_h, x_w)
+    if n_ways > 1:
+        cls_all, reg_all = [], []
+        for i in range(batch):
+            a_scores = cls[i].permute(0, 2, 3, 1).reshape(n_ways, -1, 1)
+            a_deltas = reg[i].permute(0, 2, 3, 1).reshape(n_ways, -1, 4)
+            index = 1 if a_scores.shape[-1] == 2 else 0
+            argmax = torch.argmax(a_scores[:, :, index], dim=0)
+            arranged = torch.arange(len(argmax))
+            cls_new = a_scores[argmax, arranged, :]
+            reg_new = a_deltas[argmax, arranged, :]
+            _, na, h, w = cls[i].shape
+            cls_all.append(cls_new.view(1, h, w, na).permute(0, 3, 1, 2))
+            _, nb, h, w = reg[i].shape
+            reg_all.append(reg_new.view(1, h, w, nb).permute(0, 3, 1, 2))
+        return torch.cat(cls_all, 0), torch.cat(reg_all, 0)
+    return cls.view(batch, c, x_h, x_w), reg.view(batch, c4, x_h, x_w)
+
+
+def count_spp(spp_fmaps: torch.Tensor, spp_bboxes: torch.Tensor, spp_isegmaps: torch.Tensor, n_ways: int,
+              k_shots: int, subsampling_ratio: float = 16, shared_head=None, impl: str = "tv"):
+    """fgn_roi_head.py:419-449.  Mutates spp_bboxes in place (/= subsampling_ratio) like the reference.
+    Returns (cat_mean [B,N,C,7,7], masked_gap [B,N,C,1,1], mask_roi [BNK,1,7,7], feat_roi [BNK,C,7,7])."""
+    m = spp_bboxes.shape[0]
+    idx = torch.arange(m, dtype=torch.float32).view(m, 1)
+    rois = torch.cat([idx, spp_bboxes.reshape(m, 4)], 1)      # torchvision list-of-[1,4] form (:429)
+    mask_ra = roi_align(spp_isegmaps.float(), rois, 1.0, 7, -1, False, impl)
+    spp_bboxes /= subsampling_ratio                             # :430, in place
+    rois = torch.cat([idx, spp_bboxes.reshape(m, 4)], 1)
+    feat_ra = roi_align(spp_fmaps, rois, 1.0, 7, -1, False, impl)
+    if shared_head is not None:
+        feat_ra = shared_head(feat_ra)                          # :435-436 (C4 only)
+    c, h, w = feat_ra.shape[-3:]
+    cat_mean = feat_ra.view(-1, n_ways, k_shots, c, h, w).mean(dim=2).view(-1, n_ways, c, h, w)
+    mp = (feat_ra * mask_ra).view(-1, n_ways, k_shots, c, h, w).mean(dim=(2, 4, 5)).view(-1, n_ways, c, 1, 1)
+    return cat_mean, mp, mask_ra, feat_ra
+
+
+def count_spp_fpn(spp_feats: Sequence[torch.Tensor], strides: Sequence[int], spp_bboxes: torch.Tensor,
+                  spp_isegmaps: torch.Tensor, n_ways: int, k_shots: int, finest_scale: float = 56.0,
+                  impl: str = "tv"):
+    """FPN generalisation of count_spp (SURVEY A.9 assumption A-FPN): the support box is pooled from
+    the level map_roi_levels assigns it, with spatial_scale = 1/stride_l, otherwise identical
+    (sampling_ratio=-1, aligned=False).  With one level of stride 16 this is count_spp."""
+    m = spp_bboxes.shape[0]
+    idx = torch.arange(m, dtype=torch.float32).view(m, 1)
+    rois = torch.cat([idx, spp_bboxes.reshape(m, 4)], 1)
+    mask_ra = roi_align(spp_isegmaps.float(), rois, 1.0, 7, -1, False, impl)
+    feat_ra, _ = single_roi_extractor(spp_feats, rois, strides, 7, -1, False, finest_scale, impl)
+    c, h, w = feat_ra.shape[-3:]
+    cat_mean = feat_ra.view(-1, n_ways, k_shots, c, h, w).mean(dim=2).view(-1, n_ways, c, h, w)
+    mp = (feat_ra * mask_ra).view(-1, n_ways, k_shots, c, h, w).mean(dim=(2, 4, 5)).view(-1, n_ways, c, 1, 1)
+    return cat_mean, mp, mask_ra, feat_ra
+
+
+def count_one_roi_by_n_spp(bbox_feats: torch.Tensor, rois: torch.Tensor, spp_cat_mean: torch.Tensor, n_ways: int,
+                           conv_w, conv_b, gn_w, gn_b, gn_groups: int = 32, gn_eps: float = 1e-5):
+    """fgn_roi_head.py:253-279, materialised concat form, line for line."""
+    rois_amount = bbox_feats.shape[0]
+    batch = spp_cat_mean.shape[0]
+    indexes = torch.repeat_interleave(torch.arange(len(rois)), n_ways)
+    c, h, w = bbox_feats.shape[-3:]
+    rois_repeated = bbox_feats[indexes].view(rois_amount * n_ways, c, h, w)
+    c, h, w = spp_cat_mean.shape[-3:]
+    spps_repeated = spp_cat_mean.view(batch, n_ways, c, h, w)
+    indexes = rois[:, 0].long()
+    spps_repeated = spps_repeated[indexes].view(rois_amount * n_ways, c, h, w)
+    x = torch.cat((rois_repeated, spps_repeated), dim=1)
+    y = F.conv2d(x, conv_w.view(conv_w.shape[0], -1, 1, 1), conv_b)
+    y = F.group_norm(y, gn_groups, gn_w, gn_b, gn_eps)
+    return rois_amount, F.relu(y)
+
+
+def count_modified_cls_bbox(rois_amount: int, cls_score: torch.Tensor, bbox_pred: torch.Tensor, n_ways: int):
+    """fgn_roi_head.py:302-326; the hard-coded [1,3,5] generalised to 1::2."""
+    if n_ways == 1:
+        return cls_score[:, [1, 0]], bbox_pred
+    reshaped = cls_score.view(rois_amount, n_ways * 2)
+    top = reshaped[:, 1::2].argmax(dim=-1) * 2
+    indexes = torch.arange(rois_amount)
+    bg_class = reshaped[indexes, top].view(rois_amount, 1)
+    pr_class = reshaped[:, 1::2]
+    return torch.cat((pr_class, bg_class), dim=1), bbox_pred.view(rois_amount, n_ways * 4)
+
+
+def bbox_forward(feats: Sequence[torch.Tensor], strides: Sequence[int], rois: torch.Tensor,
+                 spp_cat_mean: torch.Tensor, n_ways: int, w: dict, shared_head=None, impl: str = "tv",
+                 chunk: Optional[int] = None):
+    """fgn_roi_head.py:328-342 (_bbox_forward).  `chunk` bounds the [R*N,2C,7,7] concat by looping over
+    RoI chunks (results are per-RoI independent); used for the N=20 stress config."""
+    bbox_feats, lv = single_roi_extractor(feats, rois, strides, 7, 0, True, 56.0, impl)
+    if shared_head is not None:
+        bbox_feats = shared_head(bbox_feats)
+    r = rois.shape[0]
+    step = r if not chunk else chunk
+    cls_l, reg_l = [], []
+    for s in range(0, r, max(step, 1)):
+        e = min(r, s + step)
+        n_r, fused = count_one_roi_by_n_spp(bbox_feats[s:e], rois[s:e], spp_cat_mean, n_ways, w["conv_w"], w["conv_b"],
+                                            w["gn_w"], w["gn_b"], w.get("gn_groups", 32), w.get("gn_eps", 1e-5))
+        cls_raw, reg_raw = bbox_head_forward(fused, w["fc_cls_w"], w["fc_cls_b"], w["fc_reg_w"], w["fc_reg_b"])
+        c_, r_ = count_modified_cls_bbox(n_r, cls_raw, reg_raw, n_ways)
+        cls_l.append(c_)
+        reg_l.append(r_)
+    if r == 0:
+        return dict(cls_score=rois.new_zeros((0, n_ways + 1)), bbox_pred=rois.new_zeros((0, 4 * n_ways)),
+                    bbox_feats=bbox_feats, levels=lv)
+    return dict(cls_score=torch.cat(cls_l), bbox_pred=torch.cat(reg_l), bbox_feats=bbox_feats, levels=lv)
+
+
+def mask_attention(feats: Sequence[torch.Tensor], strides: Sequence[int], rois: torch.Tensor,
+                   masked_gap: torch.Tensor, det_labels: List[torch.Tensor], n_ways: int,
+                   output_size: int = 7, shared_head=None, impl: str = "tv"):
+    """fgn_roi_head.py:360-382 with the vector gather of :707-714 (test) / :516-522 (train)."""
+    gather = torch.cat([det_labels[i] + n_ways * i for i in range(len(det_labels))])
+    batch, n, c = masked_gap.shape[:3]
+    vecs = masked_gap.view(batch * n_ways, c, 1, 1)[gather]
+    mask_feats, _ = single_roi_extractor(feats, rois, strides, output_size, 0, True, 56.0, impl)
+    if shared_head is not None:
+        mask_feats = shared_head(mask_feats)
+    return mask_feats * vecs

@@ -1,0 +1,374 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact for RoI level assignment and RoIAlign sample indices;
+fp32 features/logits within |a-b| <= 1e-4 + 1e-5*|b| of the reference.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ATOL, GOLDEN, RTOL
+from oracle import fgn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REF_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "fgn_reference_*.npz")))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(got, want, atol=ATOL, rtol=RTOL, what=""):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs()
+    bound = atol + rtol * want.abs()
+    bad = err > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tol, max abs err {float(err.max()):.3e}"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_convs():
+    # the adjacent torch/cuDNN modules (RPN convs, shared_head) must not run in TF32 during parity
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_library_is_native_and_on_blackwell():
+    import ctypes
+    from fgn_b200 import _lib
+    lib = _lib.load()
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.fgn_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)) == 0
+    assert major.value == 10, "libfgn_b200 is built for sm_100a only"
+    assert sm.value > 0
+
+
+# ---- a4: map_roi_levels, bit-exact --------------------------------------------------------------
+def test_map_roi_levels_bit_exact_on_boundaries():
+    from fgn_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "map_roi_levels_kat.npz"))
+    rois = _t(z["rois"])
+    area = (z["rois"][:, 3] - z["rois"][:, 1]) * (z["rois"][:, 4] - z["rois"][:, 2])
+    ok = ~(area < 0)
+    for L in (1, 2, 4, 5):
+        got = ops.map_roi_levels(rois.to(dev()), L).cpu().numpy()
+        assert got.dtype == np.int64
+        assert np.array_equal(got[ok], z[f"L{L}"][ok])
+        assert np.array_equal(got, O.map_roi_levels_c(rois, L).numpy())
+        # torch's own CUDA evaluation of the mmdet expression agrees as well
+        r = rois.to(dev())
+        scale = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
+        tc = torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=L - 1).long().cpu().numpy()
+        assert np.array_equal(got[ok], tc[ok])
+
+
+# ---- a5: RoIAlign sample indices, bit-exact -----------------------------------------------------
+@pytest.mark.parametrize("aligned,sr,P", [(True, 0, 7), (False, -1, 7), (True, 0, 14), (True, 2, 7)])
+def test_sample_indices_bit_exact(aligned, sr, P):
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(11)
+    hw = [(200, 336), (100, 168), (50, 84), (25, 42)]
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    rois = synth_rois(g, 1500, 800, 1344, 1, smin=2.0)
+    z = np.load(os.path.join(GOLDEN, "map_roi_levels_kat.npz"))
+    edge = torch.tensor([[0, 5., 5., 5., 5.], [0, 10., 10., 4., 4.], [0, -500., -500., -400., -400.],
+                         [0, -50., -50., 1400., 860.], [0, 0., 0., 1344., 800.], [0, 1343., 799., 1344., 800.],
+                         [0, -4., -4., 0., 0.], [0, 1344., 800., 1360., 816.], [0, 0., 0., 3000., 10.]])
+    rois = torch.cat([edge, _t(z["rois"][:200]), rois], 0)
+    ok = ~(((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2])) < 0)
+    rois = rois[ok]
+    G = 64
+    lvl, grid, ytab, xtab = ops.roi_align_sample_indices(hw, rois.to(dev()), scales, P, sr, aligned, 56.0, G)
+    lv_o = O.map_roi_levels_c(rois, 4)
+    assert torch.equal(lvl.cpu().long(), lv_o)
+    grid_o, ytab_o, xtab_o = O.roi_align_indices_c(rois, lv_o, hw, scales, P, sr, aligned, G)
+    assert torch.equal(grid.cpu(), grid_o)
+    assert torch.equal(ytab.cpu(), ytab_o)
+    assert torch.equal(xtab.cpu(), xtab_o)
+    assert int(grid_o.max()) > 4           # the adaptive grid really varies
+
+
+# ---- a5: RoIAlign values -------------------------------------------------------------------------
+def test_roi_align_kats_all_kernels():
+    from fgn_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "roi_align_kat.npz"))
+    for n in sorted({k.split(".")[0] for k in z.files}):
+        feat, rois, want = _t(z[f"{n}.feat"]), _t(z[f"{n}.rois"]), _t(z[f"{n}.out"])
+        scale, P, sr, aligned = float(z[f"{n}.scale"]), int(z[f"{n}.P"]), int(z[f"{n}.sr"]), bool(z[f"{n}.aligned"])
+        f, r = feat.to(dev()), rois.to(dev())
+        # direct kernel, reference layout: the reference's own summation order -> bit-exact
+        d = ops.roi_align_multilevel([f], r, [scale], P, sr, aligned, force_direct=True)
+        assert torch.equal(d.cpu(), want), n
+        d2 = ops.roi_align_multilevel([f.contiguous(memory_format=torch.channels_last)], r, [scale], P, sr, aligned,
+                                      force_direct=True, out_format="nhwc")
+        assert torch.equal(d2.cpu().contiguous(), want), n
+        if feat.shape[1] % 4 == 0 and P in (7, 14):
+            for fmt in ("nchw", "nhwc"):
+                s = ops.roi_align_multilevel([f], r, [scale], P, sr, aligned, out_format=fmt)
+                close(s, want, what=f"{n}/{fmt}")
+            cl = ops.roi_align_multilevel([f.contiguous(memory_format=torch.channels_last)], r, [scale], P, sr, aligned)
+            close(cl, want, what=n)
+
+
+@pytest.mark.parametrize("C,P", [(64, 7), (256, 7), (1024, 7), (256, 14), (132, 7)])
+def test_roi_align_multilevel_vs_oracle(C, P):
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(20 + C + P)
+    strides = [4, 8, 16, 32]
+    B, img_h, img_w = 2, 256, 384
+    feats = [torch.randn(B, C, img_h // s, img_w // s, generator=g) for s in strides]
+    rois = synth_rois(g, 300, img_h, img_w, B, smin=6.0)
+    want, lv = O.single_roi_extractor(feats, rois, strides, P, 0, True, 56.0, "tv")
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    got, lvl = ops.roi_align_multilevel(fd, rois.to(dev()), [1 / s for s in strides], P, 0, True, return_levels=True)
+    assert torch.equal(lvl.cpu(), lv)
+    close(got, want, what="multilevel")
+    got2 = ops.roi_align_multilevel(fd, rois.to(dev()), [1 / s for s in strides], P, 0, True, out_format="nhwc")
+    assert torch.equal(got2.contiguous(), got)                                   # layouts agree bitwise
+    got3 = ops.roi_align_multilevel([f.to(dev()) for f in feats], rois.to(dev()), [1 / s for s in strides], P, 0, True)
+    assert torch.equal(got3, got)                                                # NCHW input (repacked) too
+
+
+def test_roi_align_edge_cases():
+    from fgn_b200 import ops
+    f = torch.randn(1, 8, 12, 12, device=dev()).contiguous(memory_format=torch.channels_last)
+    empty = ops.roi_align_multilevel([f], torch.zeros(0, 5, device=dev()), [1 / 16])
+    assert empty.shape == (0, 8, 7, 7)
+    rois = torch.tensor([[0, -900., -900., -800., -800.], [0, 50., 50., 50., 50.], [0, 80., 80., 20., 20.]], device=dev())
+    out = ops.roi_align_multilevel([f], rois, [1 / 16])
+    want = O.roi_align_tv(f.cpu().contiguous(), rois.cpu(), 1 / 16, 7, 0, True)
+    close(out, want, what="degenerate")
+    assert (out[0] == 0).all()
+
+
+# ---- full-size, size-independent properties (cfg3 pyramid) ---------------------------------------
+def test_full_size_properties_cfg3():
+    from fgn_b200 import ops
+    from fgn_b200.episodes import CONFIGS, make_episode, episode_to_device
+    ep = episode_to_device(make_episode(CONFIGS["cfg3_coco2voc_n1k1_fpn"], seed=3), dev())
+    feats, rois = ep["qry"][:4], ep["rois"]
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    a, lv = ops.roi_align_multilevel(feats, rois, scales, 7, 0, True, return_levels=True)
+    assert torch.equal(lv.cpu(), O.map_roi_levels_c(rois.cpu(), 4))
+    # (1) fast kernel == direct kernel (reference summation order) within tolerance, all 1000 RoIs
+    d = ops.roi_align_multilevel(feats, rois, scales, 7, 0, True, force_direct=True)
+    close(a, d, what="separable vs direct")
+    # (2) linearity: RA(2x + y) == 2 RA(x) + RA(y)
+    g = torch.Generator(device="cpu").manual_seed(8)
+    other = [torch.randn(f.shape, generator=g).to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    b = ops.roi_align_multilevel(other, rois, scales, 7, 0, True)
+    mix = [2 * x + y for x, y in zip(feats, other)]
+    c = ops.roi_align_multilevel(mix, rois, scales, 7, 0, True)
+    close(c, 2 * a + b, atol=2e-4, what="linearity")
+    # (3) a constant map pools to the constant wherever every sample is inside the map
+    ones = [torch.ones_like(f) for f in feats]
+    o = ops.roi_align_multilevel(ones, rois, scales, 7, 0, True)
+    inside = (rois[:, 1] > 40) & (rois[:, 2] > 40) & (rois[:, 3] < 1344 - 40) & (rois[:, 4] < 800 - 40)
+    assert inside.sum() > 100
+    assert (o[inside] - 1).abs().max() < 1e-5
+    # (4) channel-permutation equivariance, bitwise
+    perm = torch.randperm(256, generator=g).to(dev())
+    pf = [f[:, perm].contiguous(memory_format=torch.channels_last) for f in feats]
+    p = ops.roi_align_multilevel(pf, rois, scales, 7, 0, True)
+    assert torch.equal(p, a[:, perm])
+    # (5) an oracle spot check on a 64-RoI subset of the full-size episode
+    sub = rois[::16]
+    want, _ = O.single_roi_extractor([f.cpu().contiguous() for f in feats], sub.cpu(), [4, 8, 16, 32], 7, 0, True, 56.0, "tv")
+    close(a[::16], want, what="cfg3 subset vs oracle")
+
+
+# ---- a2: support branch -------------------------------------------------------------------------
+def test_support_mask_pool_vs_oracle():
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_support
+    g = torch.Generator().manual_seed(31)
+    for S in (64, 128, 256):
+        boxes, masks = synth_support(g, 6, S)
+        boxes[0, 0] = torch.tensor([-10., -10., S + 5., S + 5.])
+        boxes[1, 0] = torch.tensor([3., 4., 3.5, 4.2])
+        m = boxes.shape[0]
+        rois = torch.cat([torch.arange(m).float().view(m, 1), boxes.view(m, 4)], 1)
+        want = O.roi_align_tv(masks.float(), rois, 1.0, 7, -1, False)
+        got = ops.support_mask_pool(masks.to(dev()), boxes.to(dev()), 7)
+        close(got, want, what=f"mask pool S={S}")
+
+
+@pytest.mark.parametrize("path", REF_FIXTURES, ids=[os.path.basename(p)[14:-4] for p in REF_FIXTURES])
+def test_reference_fixture_end_to_end(path):
+    """The reference's own outputs (tests/golden/fgn_reference_*.npz) through the mirror modules."""
+    from fgn_b200 import AGRPNHead, FGNRoIHead, ops
+    z = np.load(path)
+    B, N, K, C, stride = (int(z[k]) for k in ("B", "N", "K", "C", "stride"))
+    shared = None
+    if "w.shared_head.0.weight" in z.files:
+        shared = torch.nn.Sequential(torch.nn.Conv2d(C, C, 3, padding=1), torch.nn.ReLU())
+        shared[0].weight.data.copy_(_t(z["w.shared_head.0.weight"]))
+        shared[0].bias.data.copy_(_t(z["w.shared_head.0.bias"]))
+    head = FGNRoIHead(bbox_roi_extractor=dict(type="SingleRoIExtractor",
+                                              roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                              out_channels=C, featmap_strides=[stride]),
+                      shared_head=shared, channels=C, n_ways=N, k_shots=K)
+    sd = {k[2:]: _t(z[k]) for k in z.files if k.startswith("w.") and not k.startswith("w.shared_head")}
+    missing = head.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if not k.startswith("shared_head")]
+    head = head.to(dev()).eval()
+    head.subsampling_ratio = stride
+    qry, spp = _t(z["qry"]).to(dev()), _t(z["spp"]).to(dev())
+    boxes = _t(z["spp_bboxes"].copy()).to(dev())
+    with torch.no_grad():
+        head.count_spp(spp, boxes, _t(z["spp_masks"]).to(dev()))
+        assert torch.equal(boxes.cpu(), _t(z["spp_bboxes_after"]))              # side effect of :430 kept
+        close(head.spp_fmaps_roi_aligned_cat_mean, _t(z["cat_mean"]), what="cat_mean")
+        close(head.spp_fvecs_roi_aligned_cat_mean_mp, _t(z["masked_gap"]), what="masked_gap")
+        assert head.spp_fmaps_roi_aligned_cat_mean.shape == (B, N, C, 7, 7)
+        assert head.spp_fvecs_roi_aligned_cat_mean_mp.shape == (B, N, C, 1, 1)
+
+        rpn = AGRPNHead(in_channels=C, feat_channels=C, num_anchors=15, n_ways=N, k_shots=K)
+        rpn.load_state_dict({k[5:]: _t(z[k]) for k in z.files if k.startswith("rpnw.")})
+        rpn = rpn.to(dev()).eval()
+        vec, mod = rpn.attention(qry, spp)
+        close(mod, _t(z["rpn_qry_fmap_mod"]), what="qry_fmap_mod")
+        cls, reg = rpn.forward_single(qry, spp)
+        close(cls, _t(z["rpn_cls"]), atol=2e-4, what="rpn_cls")               # includes cuDNN convs
+        close(reg, _t(z["rpn_reg"]), atol=2e-4, what="rpn_reg")
+        if N > 1:   # selection alone, on the reference's own conv outputs: exact
+            c2, r2 = ops.best_class_select(_t(z["rpn_cls_raw"]).to(dev()), _t(z["rpn_reg_raw"]).to(dev()), B, N)
+            assert torch.equal(c2.cpu(), _t(z["rpn_cls"])) and torch.equal(r2.cpu(), _t(z["rpn_reg"]))
+        if "cls_score" not in z.files:
+            return
+        rois = _t(z["rois"]).to(dev())
+        res = head._bbox_forward(qry, rois, need_feats=True)
+        close(res["bbox_feats"], _t(z["bbox_feats"]), what="bbox_feats")
+        close(res["cls_score"], _t(z["cls_score"]), what="cls_score")
+        close(res["bbox_pred"], _t(z["bbox_pred"]), what="bbox_pred")
+        assert res["cls_score"].shape == (rois.shape[0], N + 1) and res["bbox_pred"].shape == (rois.shape[0], 4 * N)
+        # relation fusion alone on the reference's RoI features, with the raw head outputs
+        c3, r3, rawc, rawr = ops.relation_fusion(_t(z["bbox_feats"]).to(dev()), rois[:, 0], head.spp_fmaps_roi_aligned_cat_mean,
+                                                 N, head.relation_params(), return_raw=True)
+        close(rawc, _t(z["raw_cls"]), what="raw_cls")
+        close(rawr, _t(z["raw_reg"]), what="raw_reg")
+        c4, r4 = head.count_modified_cls_bbox(rois.shape[0], _t(z["raw_cls"]).to(dev()), _t(z["raw_reg"]).to(dev()))
+        assert torch.equal(c4.cpu(), _t(z["cls_score"])) and torch.equal(r4.cpu(), _t(z["bbox_pred"]))
+        if shared is None:      # FPN-style single call (no shared head between RoIAlign and fusion)
+            fused = head._bbox_forward(qry, rois, need_feats=False)
+            assert fused["bbox_feats"] is None
+            close(fused["cls_score"], _t(z["cls_score"]), what="fused cls")
+            close(fused["bbox_pred"], _t(z["bbox_pred"]), what="fused reg")
+        # mask branch
+        det_rois, labels = _t(z["det_rois"]).to(dev()), _t(z["det_labels"]).to(dev())
+        det_labels = [labels[det_rois[:, 0] == b] for b in range(B)]
+        head.gather_mask_vectors(det_labels)
+        mres = head._mask_forward(qry, det_rois)
+        close(mres["mask_feats"], _t(z["mask_feats"]), what="mask_feats")
+        # train-time form: pos_inds + bbox_feats (fgn_roi_head.py:371-374)
+        pos = torch.zeros(rois.shape[0], dtype=torch.uint8, device=dev())
+        pos[: det_rois.shape[0]] = 1
+        m2 = head._mask_forward(qry, pos_inds=pos, bbox_feats=res["bbox_feats"])
+        close(m2["mask_feats"], _t(z["mask_feats"]), what="mask_feats (pos_inds)")
+
+
+# ---- FPN-mode configs vs the oracle ---------------------------------------------------------------
+@pytest.mark.parametrize("name,R", [("tiny_fpn", 96), ("tiny_c4", 64)])
+def test_guided_path_small_configs_vs_oracle(name, R):
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode, make_weights, run_guided_path
+    cfg = CONFIGS[name]
+    ep = make_episode(cfg, seed=2)
+    rpn, head = build_heads(cfg, dev(), seed=0)
+    with torch.no_grad():
+        out = run_guided_path(rpn, head, episode_to_device(ep, dev()))
+    w = make_weights(cfg.channels, 0)
+    n_ext = len(cfg.strides)
+    for lvl in range(len(cfg.rpn_strides)):
+        _, mod = O.agrpn_attention(ep["qry"][lvl], ep["spp"][lvl], cfg.n_ways, cfg.k_shots)
+        close(out["qry_fmap_mod"][lvl], mod, what=f"attention level {lvl}")
+    if cfg.mode == "fpn":
+        cat_mean, mp, _, _ = O.count_spp_fpn(ep["spp"][:n_ext], cfg.strides, ep["spp_bboxes"].clone(), ep["spp_masks"],
+                                             cfg.n_ways, cfg.k_shots)
+    else:
+        cat_mean, mp, _, _ = O.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"], cfg.n_ways, cfg.k_shots, 16)
+    close(head.spp_fmaps_roi_aligned_cat_mean, cat_mean, what="cat_mean")
+    close(head.spp_fvecs_roi_aligned_cat_mean_mp, mp, what="masked_gap")
+    res = O.bbox_forward(ep["qry"][:n_ext], cfg.strides, ep["rois"], cat_mean, cfg.n_ways, w)
+    close(out["cls_score"], res["cls_score"], what="cls_score")
+    close(out["bbox_pred"], res["bbox_pred"], what="bbox_pred")
+    det = ep["det_rois"]
+    labels = [ep["det_labels"][det[:, 0] == b] for b in range(cfg.batch)]
+    mf = O.mask_attention(ep["qry"][:n_ext], cfg.strides, det, mp, labels, cfg.n_ways, cfg.mask_size)
+    close(out["mask_feats"], mf, what="mask_feats")
+
+
+def test_relation_stress_n20_k5_vs_oracle():
+    """cfg4's shape family (N=20, K=5, C=256) at a RoI count the CPU oracle finishes in seconds."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import make_weights
+    g = torch.Generator().manual_seed(44)
+    N, C, R, B = 20, 256, 40, 2
+    w = make_weights(C, 1)
+    feats = torch.randn(R, C, 7, 7, generator=g)
+    cat_mean = torch.randn(B, N, C, 7, 7, generator=g)
+    rois = torch.zeros(R, 5)
+    rois[R // 2:, 0] = 1
+    _, fused = O.count_one_roi_by_n_spp(feats, rois, cat_mean, N, w["conv_w"], w["conv_b"], w["gn_w"], w["gn_b"])
+    rc, rr = O.bbox_head_forward(fused, w["fc_cls_w"], w["fc_cls_b"], w["fc_reg_w"], w["fc_reg_b"])
+    wc, wr = O.count_modified_cls_bbox(R, rc, rr, N)
+    params = ops.RelationParams(*[w[k].to(dev()) for k in ("conv_w", "conv_b", "gn_w", "gn_b", "fc_cls_w", "fc_cls_b",
+                                                            "fc_reg_w", "fc_reg_b")])
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        c, r, rawc, rawr = ops.relation_fusion(feats.to(dev()).contiguous(memory_format=fmt), rois[:, 0].to(dev()),
+                                               cat_mean.to(dev()), N, params, return_raw=True)
+        close(rawc, rc, what="raw cls")
+        close(rawr, rr, what="raw reg")
+        close(c, wc, what="cls")
+        close(r, wr, what="reg")
+        assert c.shape == (R, N + 1) and r.shape == (R, 4 * N)
+
+
+def test_mask_branch_p14_vs_oracle():
+    """cfg5's op: 14x14 multi-level RoIAlign with the AG-FCN vector multiply fused in."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(55)
+    strides, B, C, N = [4, 8, 16, 32], 4, 256, 3
+    feats = [torch.randn(B, C, 160 // s, 224 // s, generator=g) for s in strides]
+    rois = synth_rois(g, 64, 160, 224, B, smin=6.0)
+    mp = torch.randn(B, N, C, 1, 1, generator=g)
+    labels = torch.randint(0, N, (64,), generator=g)
+    det_labels = [labels[rois[:, 0] == b] for b in range(B)]
+    want = O.mask_attention(feats, strides, rois, mp, det_labels, N, 14)
+    gather = torch.cat([det_labels[i] + N * i for i in range(B)]).to(torch.int32)
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    got = ops.roi_align_multilevel(fd, rois.to(dev()), [1 / s for s in strides], 14, 0, True,
+                                   chan_scale=mp.view(B * N, C).to(dev()), scale_index=gather.to(dev()))
+    close(got, want, what="p14 mask feats")
+
+
+def test_empty_proposals():
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
+    cfg = CONFIGS["tiny_fpn"]
+    ep = episode_to_device(make_episode(cfg, seed=0), dev())
+    rpn, head = build_heads(cfg, dev())
+    with torch.no_grad():
+        head.count_spp(ep["spp"][:4], ep["spp_bboxes"], ep["spp_masks"])
+        res = head._bbox_forward(ep["qry"][:4], torch.zeros(0, 5, device=dev()))
+    assert res["cls_score"].shape == (0, cfg.n_ways + 1) and res["bbox_pred"].shape == (0, 4 * cfg.n_ways)
+
+
+def test_launches_are_counted():
+    from fgn_b200 import ops
+    before = ops.launch_count()
+    ops.map_roi_levels(torch.rand(10, 5, device=dev()) * 100, 4)
+    assert ops.launch_count() == before + 1

@@ -1,0 +1,117 @@
+"""Host-side logic that needs no GPU: layout detection, episode sharding, the N>1 gather path on
+world_size-2 gloo, synthetic generators, module construction."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fgn_b200 import episodes as E
+from fgn_b200 import ops
+from fgn_b200._lib import LAYOUT_NCHW, LAYOUT_NHWC
+from oracle import fgn_oracle as O
+
+
+def test_storage_layout_detection():
+    x = torch.zeros(2, 8, 5, 6)
+    assert ops.storage_layout(x) == LAYOUT_NCHW
+    assert ops.storage_layout(x.contiguous(memory_format=torch.channels_last)) == LAYOUT_NHWC
+    assert ops.storage_layout(x[:, ::2]) is None
+    assert ops.storage_layout(torch.zeros(3, 7, 7, 8).permute(0, 3, 1, 2)) == LAYOUT_NHWC
+    # ambiguous shapes resolve to NCHW (both descriptions are valid)
+    assert ops.storage_layout(torch.zeros(2, 1, 5, 6)) == LAYOUT_NCHW
+
+
+def test_shard_range_partitions_contiguously():
+    for n in (0, 1, 7, 8, 64, 1000):
+        for w in (1, 2, 4, 8):
+            blocks = [E.shard_range(n, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            for (a, b), (c, d) in zip(blocks, blocks[1:]):
+                assert b == c and b - a >= d - c >= 0
+            assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+
+
+def test_bbox2roi_matches_oracle():
+    from fgn_b200 import bbox2roi
+    g = torch.Generator().manual_seed(0)
+    boxes = [torch.rand(5, 5, generator=g), torch.zeros(0, 5), torch.rand(3, 4, generator=g)]
+    assert torch.equal(bbox2roi(boxes), O.bbox2roi(boxes))
+
+
+def test_synthetic_episode_shapes():
+    cfg = E.CONFIGS["cfg3_coco2voc_n1k1_fpn"]
+    assert [E.level_hw(cfg.img_h, cfg.img_w, s) for s in cfg.rpn_strides] == [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    ep = E.make_episode(E.CONFIGS["tiny_fpn"], seed=1)
+    cfg = ep["cfg"]
+    assert len(ep["qry"]) == 5 and ep["qry"][0].shape == (1, 64, 32, 48)
+    assert ep["spp"][0].shape == (cfg.n_ways * cfg.k_shots, 64, 16, 16)
+    assert ep["spp_masks"].dtype == torch.bool and ep["spp_bboxes"].shape == (6, 1, 4)
+    r = ep["rois"]
+    assert r.shape == (96, 5) and (r[:, 3] >= r[:, 1]).all() and (r[:, 1] >= 0).all() and (r[:, 3] <= cfg.img_w).all()
+    ep2 = E.make_episode(E.CONFIGS["tiny_fpn"], seed=1)
+    assert torch.equal(ep["rois"], ep2["rois"]) and torch.equal(ep["qry"][2], ep2["qry"][2])
+    # every FPN level receives RoIs under the stated size distribution
+    big = E.synth_rois(torch.Generator().manual_seed(1), 1000, 800, 1344, 1)
+    lv = O.map_roi_levels(big, 4)
+    assert all((lv == l).sum() > 20 for l in range(4))
+
+
+def test_modules_construct_with_reference_kwargs():
+    from fgn_b200 import AGRPNHead, FGNRoIHead, SingleRoIExtractor
+    rpn = AGRPNHead(in_channels=64, feat_channels=64,
+                    anchor_generator=dict(type="AnchorGenerator", scales=[2, 4, 8, 16, 32], ratios=[0.5, 1.0, 2.0], strides=[16]),
+                    loss_cls=dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0))
+    assert rpn.num_anchors == 15 and rpn.rpn_cls.out_channels == 15 and rpn.rpn_reg.out_channels == 60
+    head = FGNRoIHead(bbox_roi_extractor=dict(type="SingleRoIExtractor",
+                                              roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                              out_channels=64, featmap_strides=[16]),
+                      bbox_head=dict(type="FGNBBoxHead", with_avg_pool=True, roi_feat_size=7, in_channels=64, num_classes=1,
+                                     reg_class_agnostic=False), channels=64, shared_head="c4")
+    assert head.bbox_roi_extractor.num_inputs == 1 and head.with_shared_head and head.share_roi_extractor
+    assert head.cls_reg_shared_conv.weight.shape == (64, 128, 1, 1)
+    assert head.cls_reg_shared_conv_norm.num_groups == 32
+    assert len(head.shared_head) == 3
+    ext = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), 256, [4, 8, 16, 32])
+    assert ext.num_inputs == 4 and ext.finest_scale == 56 and ext.roi_layers[2].spatial_scale == 1 / 16
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, num_episodes, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = E.shard_range(num_episodes, world, rank)
+    # per-episode "result" is a deterministic function of the global episode id
+    local = torch.stack([torch.full((3, 2), float(e)) + torch.arange(6).view(3, 2) for e in range(lo, hi)]) \
+        if hi > lo else torch.zeros(0, 3, 2)
+    full = E.gather_results(local, num_episodes)
+    q.put((rank, full.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_episodes", [5, 8])
+def test_gather_results_world_size_2_gloo(num_episodes):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, num_episodes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([np.full((3, 2), float(e)) + np.arange(6).reshape(3, 2) for e in range(num_episodes)])
+    for r in range(2):
+        assert np.array_equal(got[r], want)      # world-size-2 result == unsharded result, on every rank

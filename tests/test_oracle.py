@@ -1,0 +1,190 @@
+"""Pin the oracle (CPU) against the committed golden fixtures -- runs without a GPU.
+
+fgn_reference_*.npz hold outputs of the reference's own unmodified methods (tests/golden/make_golden.py);
+roi_align_kat.npz / map_roi_levels_kat.npz hold torchvision / torch known-answer vectors.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import fgn_oracle as O
+
+REF_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "fgn_reference_*.npz")))
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _weights(z):
+    c = int(z["C"])
+    return dict(conv_w=_t(z["w.cls_reg_shared_conv.weight"]).view(c, 2 * c), conv_b=_t(z["w.cls_reg_shared_conv.bias"]),
+                gn_w=_t(z["w.cls_reg_shared_conv_norm.weight"]), gn_b=_t(z["w.cls_reg_shared_conv_norm.bias"]),
+                fc_cls_w=_t(z["w.bbox_head.fc_cls.weight"]), fc_cls_b=_t(z["w.bbox_head.fc_cls.bias"]),
+                fc_reg_w=_t(z["w.bbox_head.fc_reg.weight"]), fc_reg_b=_t(z["w.bbox_head.fc_reg.bias"]))
+
+
+def _shared_head(z):
+    if "w.shared_head.0.weight" not in z.files:
+        return None
+    w, b = _t(z["w.shared_head.0.weight"]), _t(z["w.shared_head.0.bias"])
+    return lambda x: torch.relu(torch.nn.functional.conv2d(x, w, b, padding=1))
+
+
+def test_fixtures_exist():
+    assert len(REF_FIXTURES) >= 4
+    for f in ("roi_align_kat.npz", "map_roi_levels_kat.npz"):
+        assert os.path.exists(os.path.join(GOLDEN, f))
+
+
+# ---- [3P] arithmetic: C restatement vs torchvision known answers ---------------------------------
+def test_c_roi_align_is_bit_exact_against_torchvision_kats():
+    z = np.load(os.path.join(GOLDEN, "roi_align_kat.npz"))
+    names = sorted({k.split(".")[0] for k in z.files})
+    assert len(names) >= 6
+    for n in names:
+        out = O.roi_align_c(_t(z[f"{n}.feat"]), _t(z[f"{n}.rois"]), float(z[f"{n}.scale"]), int(z[f"{n}.P"]),
+                            int(z[f"{n}.sr"]), bool(z[f"{n}.aligned"]))
+        assert np.array_equal(out.numpy(), z[f"{n}.out"]), n           # bit-exact, incl. degenerate RoIs
+
+
+def test_c_roi_align_matches_live_torchvision_op():
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(2, 6, 40, 56, generator=g)
+    from fgn_b200.episodes import synth_rois
+    rois = synth_rois(g, 128, 640, 896, 2, smin=4.0)
+    for aligned, sr in ((True, 0), (False, -1), (True, 3)):
+        a = O.roi_align_c(feat, rois, 1 / 16, 7, sr, aligned)
+        b = O.roi_align_tv(feat, rois, 1 / 16, 7, sr, aligned)
+        assert torch.equal(a, b)
+
+
+def test_map_roi_levels_c_matches_torch_expression_on_boundaries():
+    z = np.load(os.path.join(GOLDEN, "map_roi_levels_kat.npz"))
+    rois = _t(z["rois"])
+    for L in (1, 2, 4, 5):
+        want = z[f"L{L}"]
+        assert np.array_equal(O.map_roi_levels(rois, L).numpy(), want)         # torch expression, live
+        got = O.map_roi_levels_c(rois, L).numpy()
+        # NaN scale (x2<x1 xor y2<y1): torch's NaN->long cast is platform-defined; contract = level 0
+        area = (z["rois"][:, 3] - z["rois"][:, 1]) * (z["rois"][:, 4] - z["rois"][:, 2])
+        ok = ~(area < 0)
+        assert np.array_equal(got[ok], want[ok])
+        assert (got[~ok] == 0).all()
+
+
+def test_log2_contract_next_to_powers_of_two():
+    # the C/CUDA contract (float)log2((double)v) must agree with torch.log2 on fp32 at every value
+    # within 8 ulp of 2^k, k = -2..6 (this is where floor() can flip)
+    vals = []
+    for k in range(-2, 7):
+        v = np.float32(2.0 ** k)
+        lo = v
+        for _ in range(8):
+            lo = np.nextafter(lo, np.float32(0), dtype=np.float32)
+        x = lo
+        for _ in range(17):
+            vals.append(x)
+            x = np.nextafter(x, np.float32(np.inf), dtype=np.float32)
+    v = np.asarray(vals, np.float32)
+    torch_l2 = torch.log2(torch.from_numpy(v)).numpy()
+    mine = np.log2(v.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(np.floor(torch_l2), np.floor(mine))
+
+
+def test_index_tables_are_consistent_with_values():
+    # rebuild RoIAlign from the exported per-axis (valid, low, high) tables with float64 weights and
+    # compare with the op: checks the tables really are the indices the values were gathered from
+    g = torch.Generator().manual_seed(9)
+    H, W, P, scale = 20, 28, 7, 1 / 8
+    feat = torch.randn(1, 2, H, W, generator=g)
+    from fgn_b200.episodes import synth_rois
+    rois = synth_rois(g, 24, H / scale, W / scale, 1, smin=4.0)
+    rois[0, 1:] = torch.tensor([-40., -30., 60., 50.])
+    lv = torch.zeros(24, dtype=torch.long)
+    grid, ytab, xtab = O.roi_align_indices_c(rois, lv, [(H, W)], [scale], P, 0, True, 16)
+    ref = O.roi_align_tv(feat, rois, scale, P, 0, True).numpy()
+    f = feat.numpy().astype(np.float64)
+    for r in range(rois.shape[0]):
+        gh, gw = grid[r].tolist()
+        assert gh <= 16 and gw <= 16
+        x1, y1, x2, y2 = (rois[r, 1:].numpy().astype(np.float64) * scale - 0.5)
+        bh, bw = (y2 - y1) / P, (x2 - x1) / P
+        for ph in range(P):
+            for pw in range(P):
+                acc = 0.0
+                for iy in range(gh):
+                    vy, yl, yh = ytab[r, ph, iy].tolist()
+                    y = min(max(y1 + ph * bh + (iy + .5) * bh / gh, 0.0), H - 1)
+                    for ix in range(gw):
+                        vx, xl, xh = xtab[r, pw, ix].tolist()
+                        if not (vy and vx):
+                            continue
+                        x = min(max(x1 + pw * bw + (ix + .5) * bw / gw, 0.0), W - 1)
+                        ly, lx = y - yl, x - xl
+                        acc += ((1 - ly) * (1 - lx) * f[0, :, yl, xl] + (1 - ly) * lx * f[0, :, yl, xh]
+                                + ly * (1 - lx) * f[0, :, yh, xl] + ly * lx * f[0, :, yh, xh])
+                acc = acc / max(gh * gw, 1)
+                assert np.allclose(acc, ref[r, :, ph, pw], atol=2e-5), (r, ph, pw)
+
+
+# ---- FGN-owned arithmetic: restatement vs the reference's own code -------------------------------
+@pytest.mark.parametrize("path", REF_FIXTURES, ids=[os.path.basename(p)[14:-4] for p in REF_FIXTURES])
+def test_oracle_matches_reference_fixture(path):
+    z = np.load(path)
+    B, N, K, C, stride = (int(z[k]) for k in ("B", "N", "K", "C", "stride"))
+    sh = _shared_head(z)
+    qry, spp, rois = _t(z["qry"]), _t(z["spp"]), _t(z["rois"])
+    boxes = _t(z["spp_bboxes"].copy())
+    for impl in ("tv", "c"):
+        b = boxes.clone()
+        cat_mean, mp, _, _ = O.count_spp(spp, b, _t(z["spp_masks"]), N, K, stride, sh, impl)
+        assert torch.equal(b, _t(z["spp_bboxes_after"]))                      # in-place /= 16 (:430)
+        assert torch.equal(cat_mean, _t(z["cat_mean"])), impl
+        assert torch.equal(mp, _t(z["masked_gap"])), impl
+    vec, mod = O.agrpn_attention(qry, spp, N, K)
+    assert torch.equal(mod, _t(z["rpn_qry_fmap_mod"]))
+    cls, reg = O.best_class_selection(_t(z["rpn_cls_raw"]), _t(z["rpn_reg_raw"]), B, N)
+    assert torch.equal(cls, _t(z["rpn_cls"])) and torch.equal(reg, _t(z["rpn_reg"]))
+    if "cls_score" not in z.files:
+        return
+    w = _weights(z)
+    res = O.bbox_forward([qry], [stride], rois, cat_mean, N, w, sh, "tv")
+    assert torch.equal(res["bbox_feats"], _t(z["bbox_feats"]))
+    assert torch.equal(res["cls_score"], _t(z["cls_score"]))
+    assert torch.equal(res["bbox_pred"], _t(z["bbox_pred"]))
+    # chunked evaluation (used for the N=20 stress config) only changes GEMM blocking
+    res_c = O.bbox_forward([qry], [stride], rois, cat_mean, N, w, sh, "tv", chunk=7)
+    assert torch.allclose(res_c["cls_score"], _t(z["cls_score"]), atol=1e-5, rtol=1e-5)
+    det_rois, labels = _t(z["det_rois"]), _t(z["det_labels"])
+    det_labels = [labels[det_rois[:, 0] == b] for b in range(B)]
+    mf = O.mask_attention([qry], [stride], det_rois, mp, det_labels, N, 7, sh, "tv")
+    assert torch.equal(mf, _t(z["mask_feats"]))
+
+
+def test_count_modified_cls_bbox_generalisation():
+    g = torch.Generator().manual_seed(3)
+    R = 50
+    cls, reg = torch.randn(R * 3, 2, generator=g), torch.randn(R * 3, 4, generator=g)
+    c, r = O.count_modified_cls_bbox(R, cls, reg, 3)
+    t = cls.view(R, 6)
+    top = t[:, [1, 3, 5]].argmax(-1) * 2                                      # reference's literal form
+    assert torch.equal(c, torch.cat((t[:, [1, 3, 5]], t[torch.arange(R), top].view(R, 1)), 1))
+    assert torch.equal(r, reg.view(R, 12))
+    c1, r1 = O.count_modified_cls_bbox(R, cls[:R], reg[:R], 1)
+    assert torch.equal(c1, cls[:R][:, [1, 0]]) and torch.equal(r1, reg[:R])
+
+
+def test_split_weight_identity():
+    # conv1x1(cat(q,s)) == Wq q + Ws s + b : the algebra the CUDA path relies on
+    g = torch.Generator().manual_seed(4)
+    C = 32
+    q, s = torch.randn(5, C, 7, 7, generator=g), torch.randn(5, C, 7, 7, generator=g)
+    w, b = torch.randn(C, 2 * C, generator=g) / 8, torch.randn(C, generator=g)
+    full = torch.nn.functional.conv2d(torch.cat((q, s), 1), w.view(C, 2 * C, 1, 1), b)
+    split = torch.einsum("oc,rchw->rohw", w[:, :C], q) + torch.einsum("oc,rchw->rohw", w[:, C:], s) + b.view(1, C, 1, 1)
+    assert torch.allclose(full, split, atol=1e-5)
