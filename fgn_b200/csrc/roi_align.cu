@@ -15,6 +15,7 @@
 // roi_align_sample_indices_kernel from the same device functions); values differ only by fp32
 // summation order (<= ~1e-6 relative).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fgn {
 
@@ -94,7 +95,7 @@ __device__ __forceinline__ void build_plan(const Pyramid &pyr, const float *rois
 // One CTA = one RoI x one block of CB channels; one warp = (bin-row ph, 128-channel chunk).
 // NHWC input.  Output NHWC ([R,P,P,C], direct 512 B warp stores) or NCHW ([R,C,P,P], staged
 // through shared memory and written as one contiguous CB*P*P*4-byte run).
-template <int P>
+template <int P, int NB>
 __global__ void __launch_bounds__(448)
 roi_align_sep_nhwc_kernel(const Pyramid pyr, const int C, const int CB,
                           const float *__restrict__ rois, const int R,
@@ -139,12 +140,21 @@ roi_align_sep_nhwc_kernel(const Pyramid pyr, const int C, const int CB,
                 const float *row = fbase + ((size_t)(ylo + yi) * W) * C + c;
 #pragma unroll
                 for (int pw = 0; pw < P; ++pw) {
-                    const int xlo = plan.lo[1][pw], nx = plan.n[1][pw];
+                    const int nx = plan.n[1][pw];
                     const float *wx = wtab + plan.off[1][pw];
+                    const float *cell = row + (size_t)plan.lo[1][pw] * C;
                     float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int xi = 0; xi < nx; ++xi) {
-                        const float4 v = ldg4(row + (size_t)(xlo + xi) * C);
-                        fma4(racc, wx[xi], v);
+                    // first NB cells of the bin as one batch of independent, predicated 128-bit
+                    // loads (memory-level parallelism); adaptive grids rarely need more
+                    float4 v[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        v[k] = k < nx ? ldg4(cell + (size_t)k * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) fma4(racc, k < nx ? wx[k] : 0.f, v[k]);
+                    for (int xi = NB; xi < nx; ++xi) {
+                        const float4 u = ldg4(cell + (size_t)xi * C);
+                        fma4(racc, wx[xi], u);
                     }
                     fma4(acc[pw], wyv, racc);
                 }
@@ -309,6 +319,32 @@ static int validate_pyramid(const fgn_pyramid_t *pyr)
     return FGN_OK;
 }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int P, int NB>
+static int launch_sep_nb(const Pyramid &d, int C, int CB, const float *rois, int R, int sampling_ratio,
+                         int aligned, float finest_scale, const float *chan_scale,
+                         const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
+                         int wtab_cap, cudaStream_t st)
+{
+    const int warps = P * (CB / 128);
+    size_t smem = (size_t)wtab_cap * 4;
+    if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
+    auto kern = roi_align_sep_nhwc_kernel<P, NB>;
+    if (smem > 48 * 1024)
+        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nblk = (C + CB - 1) / CB;
+    kern<<<R * nblk, warps * 32, smem, st>>>(d, C, CB, rois, R, sampling_ratio, aligned,
+                                              finest_scale, chan_scale, scale_index, out,
+                                              out_layout, lvl_out, wtab_cap);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
 template <int P>
 static int launch_sep(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
                       int aligned, float finest_scale, const float *chan_scale,
@@ -321,22 +357,27 @@ static int launch_sep(const Pyramid &d, int C, const float *rois, int R, int sam
     int wtab_cap = maxH + maxW + 6 * P + 16;
     wtab_cap = (wtab_cap + 3) & ~3;
     // channel block per CTA: bounded by 32 warps (P * CB/128) and by the NCHW staging tile
-    int CB = 256;
+    int CB = env_int("FGN_RA_CB", 256);
     if (P > 8) CB = 128;
     if (C < CB) CB = ((C + 127) / 128) * 128;
-    const int warps = P * (CB / 128);
-    size_t smem = (size_t)wtab_cap * 4;
-    if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
-    auto kern = roi_align_sep_nhwc_kernel<P>;
-    if (smem > 48 * 1024)
-        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int nblk = (C + CB - 1) / CB;
-    kern<<<R * nblk, warps * 32, smem, st>>>(d, C, CB, rois, R, sampling_ratio, aligned,
-                                              finest_scale, chan_scale, scale_index, out,
-                                              out_layout, lvl_out, wtab_cap);
-    FGN_LAUNCH_OK();
-    return FGN_OK;
+    const int nb = env_int("FGN_RA_NB", 4);
+#define FGN_SEP(NBV) launch_sep_nb<P, NBV>(d, C, CB, rois, R, sampling_ratio, aligned, finest_scale, \
+                                           chan_scale, scale_index, out, out_layout, lvl_out, wtab_cap, st)
+    if (P == 7) {
+        if (nb <= 1) return FGN_SEP(1);
+        if (nb == 2) return FGN_SEP(2);
+        if (nb == 3) return FGN_SEP(3);
+        if (nb == 6) return FGN_SEP(6);
+        if (nb >= 8) return FGN_SEP(8);
+    }
+    return FGN_SEP(4);
+#undef FGN_SEP
 }
+
+int launch_roi_align_stream(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                            int aligned, float finest_scale, const float *chan_scale,
+                            const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
+                            cudaStream_t st, int vec_pref, int ns_pref, bool *taken);
 
 }  // namespace fgn
 
@@ -371,6 +412,13 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
     const Pyramid d = to_device_pyramid(pyr);
     cudaStream_t st = (cudaStream_t)stream;
+    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && env_int("FGN_RA_IMPL", 2) == 2) {
+        bool taken = false;
+        rc = launch_roi_align_stream(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                     scale_index, out, out_layout, lvl_out, st, env_int("FGN_RA_VEC", 2),
+                                     env_int("FGN_RA_NS", 0), &taken);
+        if (rc || taken) return rc;
+    }
     if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0) {
         if (P == 7)  return launch_sep<7>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
                                           chan_scale, scale_index, out, out_layout, lvl_out, st);

@@ -67,11 +67,16 @@ def test_map_roi_levels_bit_exact_on_boundaries():
         assert got.dtype == np.int64
         assert np.array_equal(got[ok], z[f"L{L}"][ok])
         assert np.array_equal(got, O.map_roi_levels_c(rois, L).numpy())
-        # torch's own CUDA evaluation of the mmdet expression agrees as well
+        # torch's own CUDA evaluation of the mmdet expression: libdevice log2f is not correctly rounded,
+        # so it may disagree with torch-CPU (our contract) ONLY on the crafted rows within a few ulp of a
+        # level boundary -- never on ordinary proposals.  The count is printed for DESIGN.md.
         r = rois.to(dev())
         scale = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
         tc = torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=L - 1).long().cpu().numpy()
-        assert np.array_equal(got[ok], tc[ok])
+        diff = np.nonzero((got != tc) & ok)[0]
+        n_crafted = z["rois"].shape[0] - 4000
+        print(f"L={L}: torch-CUDA vs torch-CPU level disagreements on boundary rows: {len(diff)} of {n_crafted}")
+        assert (diff < n_crafted).all()
 
 
 # ---- a5: RoIAlign sample indices, bit-exact -----------------------------------------------------
@@ -98,7 +103,8 @@ def test_sample_indices_bit_exact(aligned, sr, P):
     assert torch.equal(grid.cpu(), grid_o)
     assert torch.equal(ytab.cpu(), ytab_o)
     assert torch.equal(xtab.cpu(), xtab_o)
-    assert int(grid_o.max()) > 4           # the adaptive grid really varies
+    if sr <= 0:
+        assert int(grid_o.max()) > 4       # the adaptive grid really varies
 
 
 # ---- a5: RoIAlign values -------------------------------------------------------------------------
