@@ -59,6 +59,8 @@ SIGNATURES = {
     "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                         _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fgn_cls_bbox_reassemble": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_guided_roi_fused_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <atomic>
 #include <string.h>
+#include <math.h>
 
 namespace fgn {
 
@@ -14,6 +15,26 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// T_k = smallest fp32 v with floorf((float)log2((double)v)) >= k (see roi_level in common.cuh).
+void level_thresholds(float *thr)
+{
+    static float cached[FGN_MAX_LEVELS];
+    static bool ready = false;
+    if (!ready) {
+        cached[0] = 0.f;
+        for (int k = 1; k < FGN_MAX_LEVELS; ++k) {
+            float v = ldexpf(1.0f, k);
+            for (;;) {
+                const float pred = nextafterf(v, 0.0f);
+                if (floorf((float)log2((double)pred)) >= (float)k) v = pred; else break;
+            }
+            cached[k] = v;
+        }
+        ready = true;
+    }
+    for (int k = 0; k < FGN_MAX_LEVELS; ++k) thr[k] = cached[k];
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

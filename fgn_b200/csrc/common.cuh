@@ -83,22 +83,6 @@ __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int gr
     return s;
 }
 
-// mmdet map_roi_levels.  floor(log2f) is taken on the correctly rounded fp32 logarithm, formed
-// as (float)log2((double)v): margins to the rounding boundary are >= 3e-8 for every fp32 v next
-// to a power of two, far above the 1-ulp error of the fp64 log2.
-__device__ __forceinline__ int roi_level(const float *roi, int L, float finest_scale)
-{
-    if (L <= 1) return 0;
-    const float area  = __fmul_rn(__fsub_rn(roi[3], roi[1]), __fsub_rn(roi[4], roi[2]));
-    const float scale = __fsqrt_rn(area);
-    const float v     = __fadd_rn(__fdiv_rn(scale, finest_scale), 1e-6f);
-    const float lg    = (float)log2((double)v);
-    const float fl    = floorf(lg);
-    if (!(fl >= 0.f)) return 0;                 // NaN / -inf / negative
-    if (fl > (float)(L - 1)) return L - 1;
-    return (int)fl;
-}
-
 // Pyramid by value in kernel parameter space.
 struct Pyramid {
     int          L;
@@ -106,7 +90,28 @@ struct Pyramid {
     int          H[FGN_MAX_LEVELS];
     int          W[FGN_MAX_LEVELS];
     float        scale[FGN_MAX_LEVELS];
+    float        lvl_thr[FGN_MAX_LEVELS];   // lvl_thr[k]: smallest fp32 v with floor(log2f(v)) >= k
 };
+
+// mmdet map_roi_levels: lvl = clamp(floor(log2(sqrt(w*h)/finest + 1e-6)), 0, L-1), all fp32.
+// floor(log2f(v)) is taken on the correctly rounded fp32 logarithm (what torch CPU returns for the
+// values next to powers of two, tests/test_oracle.py).  Because v -> floor(fl(log2 v)) is monotone,
+// the level is the number of thresholds T_k <= v, with T_k the smallest fp32 whose rounded log2 is
+// >= k; the host derives T_k from (float)log2((double)v) (level_thresholds below), the same
+// expression oracle/roi_align_ref.c evaluates per RoI.  NaN (negative area) compares false -> 0.
+__device__ __forceinline__ int roi_level(const float *roi, const Pyramid &pyr, float finest_scale)
+{
+    if (pyr.L <= 1) return 0;
+    const float area  = __fmul_rn(__fsub_rn(roi[3], roi[1]), __fsub_rn(roi[4], roi[2]));
+    const float scale = __fsqrt_rn(area);
+    const float v     = __fadd_rn(__fdiv_rn(scale, finest_scale), 1e-6f);
+    int lvl = 0;
+#pragma unroll
+    for (int k = 1; k < FGN_MAX_LEVELS; ++k) lvl += (k < pyr.L && v >= pyr.lvl_thr[k]) ? 1 : 0;
+    return lvl;
+}
+
+void level_thresholds(float *thr /* [FGN_MAX_LEVELS] */);
 
 static inline Pyramid to_device_pyramid(const fgn_pyramid_t *p)
 {
@@ -118,6 +123,7 @@ static inline Pyramid to_device_pyramid(const fgn_pyramid_t *p)
         d.W[i]     = i < p->num_levels ? p->W[i] : 0;
         d.scale[i] = i < p->num_levels ? p->spatial_scale[i] : 0.f;
     }
+    level_thresholds(d.lvl_thr);
     return d;
 }
 

@@ -1,23 +1,45 @@
 // gemm.cu -- dispatcher for the relation head's contraction.
 #include "gemm.cuh"
+#include <stdlib.h>
 
 namespace fgn {
 
 int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-               int M, int N, int K, int precision, cudaStream_t st, bool *taken);
+               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken);
 
 int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-            int M, int N, int K, int precision, cudaStream_t st)
+            int M, int N, int K, int precision, float *split_ws, cudaStream_t st)
 {
     bool taken = false;
-    const int rc = gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, st, &taken);
+    const char *force = getenv("FGN_GEMM_IMPL");          // "simt" forces the fp32 SIMT kernel (cross-checks)
+    const bool simt_only = force != nullptr && force[0] == 's';
+    const int rc = simt_only ? FGN_OK : gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, &taken);
     if (rc) return rc;
     if (taken) return FGN_OK;
     if (precision != 0) {
-        set_error("gemm: bf16 precision needs the tcgen05 path (M=%d N=%d K=%d not supported by it)", M, N, K);
+        set_error("gemm: tf32 precision needs the tcgen05 path (M=%d N=%d K=%d not supported by it)", M, N, K);
         return FGN_ERR_UNSUPPORTED;
     }
     return gemm_nt_simt(A, lda, B, ldb, bias, C, ldc, M, N, K, st);
 }
 
 }  // namespace fgn
+
+using namespace fgn;
+
+extern "C" size_t fgn_gemm_workspace_bytes(int N, int K)
+{
+    return (N > 0 && K > 0) ? gemm_tc_workspace_bytes(N, K) : 0;
+}
+
+extern "C" int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C,
+                           int ldc, int M, int N, int K, int precision, void *workspace,
+                           size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm dims M=%d N=%d K=%d", M, N, K);
+    FGN_CHECK_ARG(precision == 0 || precision == 1, "precision=%d", precision);
+    if (M == 0) return FGN_OK;
+    FGN_CHECK_ARG(A && B && C, "NULL pointer");
+    float *ws = workspace_bytes >= gemm_tc_workspace_bytes(N, K) ? (float *)workspace : nullptr;
+    return gemm_nt(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, ws, (cudaStream_t)stream);
+}

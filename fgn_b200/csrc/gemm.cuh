@@ -5,10 +5,13 @@
 
 namespace fgn {
 
-// precision 0: fp32 parity (tcgen05 3xTF32 split when the shape qualifies, else fp32 SIMT)
-// precision 1: bf16 operands, fp32 accumulate (tcgen05 kind::f16)
+// precision 0: fp32 parity (tcgen05 3xTF32 error-compensated split when the shape qualifies, else
+//              the fp32 SIMT kernel)
+// precision 1: single-pass TF32 on tcgen05 (10-bit mantissa operands, fp32 accumulate)
+// split_ws: gemm_tc_workspace_bytes(N, K) bytes of scratch for the TF32 split of B.
+size_t gemm_tc_workspace_bytes(int N, int K);
 int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-            int M, int N, int K, int precision, cudaStream_t st);
+            int M, int N, int K, int precision, float *split_ws, cudaStream_t st);
 
 // always the SIMT fp32 kernel (exported for cross-checks)
 int gemm_nt_simt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C,

@@ -1,14 +1,358 @@
-// gemm_tc.cu -- tcgen05 (5th-gen tensor core) contraction for the relation head.
+// gemm_tc.cu -- tcgen05 (5th-gen tensor core) contraction for the relation head's 1x1 conv
+// (fgn_roi_head.py:272): C[M,N] = A[M,K] * B[N,K]^T (+ bias), fp32 in / fp32 out.
+//
+// fp32 parity on tensor cores: 3xTF32 error compensation.  Every operand is split as
+//   x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly a TF32 value),
+//                 lo = x - hi (exact in fp32; its own TF32 truncation error is ~2^-21 |x|)
+// and D += A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in fp32 in tensor memory.  The dropped
+// term A_lo B_lo is ~2^-22 relative.  precision=1 runs the single A_hi B_hi pass (plain TF32).
+//
+// Kernel anatomy (persistent, one CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of A, B_hi, B_lo per
+//               32-wide k-block into a 2-stage shared-memory ring, mbarrier complete_tx;
+//   warps 8-11  operand splitters: rewrite the landed fp32 A tile as A_hi in place and A_lo beside
+//               it (same swizzled positions), fence.proxy.async, signal the MMA warp;
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32
+//               (M=128, N<=256, K=8 per instruction, 3 passes), tcgen05.commit frees ring slots and
+//               publishes the accumulator;
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered);
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32, + bias, 128-bit global stores.
 #include "gemm.cuh"
+#include <cuda.h>
 
 namespace fgn {
 
-// Placeholder until the tcgen05 kernel lands: declines every shape so the dispatcher uses the
-// fp32 SIMT kernel.
-int gemm_nt_tc(const float *, int, const float *, int, const float *, float *, int, int, int, int,
-               int, cudaStream_t, bool *taken)
+constexpr int TC_BM = 128;          // rows per tile (UMMA_M, cta_group::1)
+constexpr int TC_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_BN_MAX = 256;      // UMMA_N max
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 384;
+
+struct TcSmem {
+    // per stage: A (hi, in place) | A_lo | B_hi | B_lo ; every tile 1024-byte aligned
+    static constexpr int kA = TC_BM * TC_BK * 4;            // 16 KB
+    static constexpr int kB = TC_BN_MAX * TC_BK * 4;        // 32 KB
+    static constexpr int kStage = 2 * kA + 2 * kB;          // 96 KB
+    static constexpr int kTotal = TC_STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B)
+// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+
+// B [N,K] -> B_hi, B_lo (the TF32 split of the weights; tiny, once per call)
+__global__ void split_tf32_kernel(const float *__restrict__ in, int rows, int cols, int ld,
+                                  float *__restrict__ hi, float *__restrict__ lo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i % cols;
+    const float x = in[(size_t)r * ld + c];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = x - h;
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                    const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
+                    float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TcSmem::kStage);
+    uint64_t *full_bar = bars, *conv_bar = bars + TC_STAGES, *empty_bar = bars + 2 * TC_STAGES;
+    uint64_t *tmem_full = bars + 3 * TC_STAGES, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles, num_kb = K / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc_mbar_init(&full_bar[s], 1);
+            tc_mbar_init(&conv_bar[s], 4);                 // one arrive per splitter warp
+            tc_mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====================================================================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    tc_mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
+                    unsigned char *st = smem + (size_t)s * TcSmem::kStage;
+                    const uint32_t bytes = TC_BM * TC_BK * 4 + (PASSES == 3 ? 2 : 1) * BN * TC_BK * 4;
+                    tc_mbar_expect_tx(&full_bar[s], bytes);
+                    tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);
+                    tma_load_2d(st + 2 * TcSmem::kA, &map_bhi, kb * TC_BK, n0, &full_bar[s]);
+                    if (PASSES == 3) tma_load_2d(st + 2 * TcSmem::kA + TcSmem::kB, &map_blo, kb * TC_BK, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ========================================================================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
+        // B=TF32 [10,13)=2, K-major A/B, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int it = 0, local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const int a = local_tile & 1;
+            tc_mbar_wait(&tmem_empty[a], ((local_tile >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(a * TC_BN_MAX);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t par = (it / TC_STAGES) & 1;
+                tc_mbar_wait(&full_bar[s], par);
+                if (PASSES == 3) tc_mbar_wait(&conv_bar[s], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t st = s_u32(smem + (size_t)s * TcSmem::kStage);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + TcSmem::kA);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * TcSmem::kA);
+                    const uint64_t b_lo = umma_desc_sw128(st + 2 * TcSmem::kA + TcSmem::kB);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);      // +32 B inside the swizzle row
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, acc);
+                        if (PASSES == 3) {
+                            umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                            umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);                               // frees the ring slot when the MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[a]);         // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== operand splitters (A tile -> A_hi in place, A_lo) ================================
+        if (PASSES == 3) {
+            const int tid = threadIdx.x - 256;                                // 0..127
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    tc_mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * TcSmem::kStage);
+                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * TcSmem::kStage + TcSmem::kA);
+#pragma unroll
+                    for (int j = 0; j < TcSmem::kA / 16 / 128; ++j) {         // 8 float4 per thread
+                        const int i = j * 128 + tid;
+                        const float4 x = hi[i];
+                        float4 h;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                        hi[i] = h;
+                        lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> tensor-core reads
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive(&conv_bar[s]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias) -> global =================================
+        const int ew = warp - 4;                                              // TMEM lanes 32*ew .. +31
+        int local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const int a = local_tile & 1;
+            const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
+            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + ew * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+                    float *dst = C + (size_t)row * ldc + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + c0 + j < N) {
+                            float4 o;
+                            o.x = __uint_as_float(r[j]);     o.y = __uint_as_float(r[j + 1]);
+                            o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
+                            if (bias != nullptr) {
+                                const float4 b = ldg4(bias + n0 + c0 + j);
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            *reinterpret_cast<float4 *>(dst + j) = o;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&tmem_empty[a]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2D fp32 row-major [rows, cols] with row pitch ld (floats); box = 32 cols x box_rows, 128B swizzle.
+static bool make_map(CUtensorMap *m, const float *base, int rows, int cols, int ld, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t gemm_tc_workspace_bytes(int N, int K) { return (size_t)2 * N * K * sizeof(float); }
+
+int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
+               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken)
 {
     *taken = false;
+    if (M <= 0) return FGN_OK;
+    // shapes the kernel takes: K in whole 128-byte k-blocks, N tiles of <=256 that are UMMA_N-legal
+    if ((K % TC_BK) != 0 || (N % 16) != 0 || (N > TC_BN_MAX && (N % TC_BN_MAX) != 0)) return FGN_OK;
+    if ((lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15)) return FGN_OK;
+    if (split_ws == nullptr) return FGN_OK;
+    const int BN = N > TC_BN_MAX ? TC_BN_MAX : N;
+    const int passes = precision == 0 ? 3 : 1;
+
+    float *bhi = split_ws, *blo = split_ws + (size_t)N * K;
+    split_tf32_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(B, N, K, ldb, bhi, blo);
+    FGN_LAUNCH_OK();
+
+    CUtensorMap ma, mbh, mbl;
+    if (!make_map(&ma, A, M, K, lda, TC_BM) || !make_map(&mbh, bhi, N, K, K, BN) || !make_map(&mbl, blo, N, K, K, BN)) {
+        set_error("cuTensorMapEncodeTiled unavailable or failed");
+        return FGN_ERR_CUDA;
+    }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        FGN_CUDA_OK(cudaGetDevice(&dev));
+        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
+    const int grid = min(sm_count, m_tiles * n_tiles);
+    static bool attr3 = false, attr1 = false;
+    if (passes == 3) {
+        if (!attr3) { FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal)); attr3 = true; }
+        gemm_tf32_tc_kernel<3><<<grid, TC_THREADS, TcSmem::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN);
+    } else {
+        if (!attr1) { FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal)); attr1 = true; }
+        gemm_tf32_tc_kernel<1><<<grid, TC_THREADS, TcSmem::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN);
+    }
+    FGN_LAUNCH_OK();
+    *taken = true;
     return FGN_OK;
 }
 

@@ -164,7 +164,7 @@ __global__ void cls_bbox_reassemble_kernel(const float *__restrict__ raw_cls, co
 }
 
 struct RelationWs {
-    float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc;
+    float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc, *split_q, *split_s;
     size_t bytes;
 };
 
@@ -181,6 +181,8 @@ static RelationWs carve(void *base, int R, int BN, int C, int P, int N_for_parti
     w.ys      = take((size_t)BN * PP * C * 4);
     w.xq_nhwc = take((size_t)R * PP * C * 4);     // only used when roi_feat arrives NCHW
     w.xs_nhwc = take((size_t)BN * PP * C * 4);
+    w.split_q = take(gemm_tc_workspace_bytes(C, C));
+    w.split_s = take(gemm_tc_workspace_bytes(C, C));
     const int nblk_max = ceil_div(C, 32);
     w.partial = take((size_t)R * (size_t)N_for_partial * 6 * nblk_max * 4);
     w.bytes = off;
@@ -236,9 +238,9 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
         xq = w.xq_nhwc; xs = w.xs_nhwc;
     }
     // Yq = Xq Wq^T ; Ys = Xs Ws^T + bias        (conv_w is [C, 2C] row-major)
-    int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, st);
+    int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, w.split_q, st);
     if (rc) return rc;
-    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, st);
+    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, w.split_s, st);
     if (rc) return rc;
 
     const int cg = C / gn_groups;

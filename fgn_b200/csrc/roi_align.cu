@@ -41,7 +41,7 @@ __device__ __forceinline__ void build_plan(const Pyramid &pyr, const float *rois
     const int t = threadIdx.x;
     if (t == 0) {
         const float *roi = rois + 5 * (size_t)r;
-        const int lvl = roi_level(roi, pyr.L, finest_scale);
+        const int lvl = roi_level(roi, pyr, finest_scale);
         g_s = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
         plan.level = lvl; plan.batch = g_s.batch;
         plan.H = pyr.H[lvl]; plan.W = pyr.W[lvl];
@@ -226,7 +226,7 @@ __global__ void roi_align_direct_kernel(const Pyramid pyr, const int C, const in
         const int c = (idx / ((size_t)P * P)) % C;
         const int r = idx / ((size_t)P * P * C);
         const float *roi = rois + 5 * (size_t)r;
-        const int lvl = roi_level(roi, pyr.L, finest_scale);
+        const int lvl = roi_level(roi, pyr, finest_scale);
         const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
         const int H = pyr.H[lvl], W = pyr.W[lvl];
         if (lvl_out != nullptr && c == 0 && ph == 0 && pw == 0) lvl_out[r] = lvl;
@@ -282,7 +282,7 @@ __global__ void roi_align_sample_indices_kernel(const Pyramid pyr, const float *
         const int axis = rem / (P * max_grid);
         const int p = (rem / max_grid) % P, i = rem % max_grid;
         const float *roi = rois + 5 * (size_t)r;
-        const int lvl = roi_level(roi, pyr.L, finest_scale);
+        const int lvl = roi_level(roi, pyr, finest_scale);
         const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
         if (rem == 0) {
             if (lvl_out) lvl_out[r] = lvl;
@@ -298,11 +298,11 @@ __global__ void roi_align_sample_indices_kernel(const Pyramid pyr, const float *
     }
 }
 
-__global__ void map_roi_levels_kernel(const float *__restrict__ rois, const int R, const int L,
+__global__ void map_roi_levels_kernel(const Pyramid pyr, const float *__restrict__ rois, const int R,
                                       const float finest_scale, int32_t *__restrict__ lvl)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R) lvl[r] = roi_level(rois + 5 * (size_t)r, L, finest_scale);
+    if (r < R) lvl[r] = roi_level(rois + 5 * (size_t)r, pyr, finest_scale);
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -390,8 +390,11 @@ extern "C" int fgn_map_roi_levels(const float *rois, int R, int num_levels, floa
     FGN_CHECK_ARG(num_levels >= 1 && num_levels <= FGN_MAX_LEVELS, "num_levels=%d", num_levels);
     if (R == 0) return FGN_OK;
     FGN_CHECK_ARG(rois && lvl_out, "NULL pointer");
-    map_roi_levels_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(rois, R, num_levels,
-                                                                            finest_scale, lvl_out);
+    Pyramid d;
+    d.L = num_levels;
+    for (int i = 0; i < FGN_MAX_LEVELS; ++i) { d.feat[i] = nullptr; d.H[i] = d.W[i] = 0; d.scale[i] = 0.f; }
+    level_thresholds(d.lvl_thr);
+    map_roi_levels_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(d, rois, R, finest_scale, lvl_out);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

@@ -59,209 +59,271 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-struct StreamPlan {
-    int   level, batch, H, W;
+struct StreamPlan {              // written by warp 0, read by the other consumer warps
+    int   level;
     float count;
     int   xlo[kStreamMaxP], xn[kStreamMaxP], xoff[kStreamMaxP];   // per bin column: cells + weights
-    int   ylo[kStreamMaxP], yn[kStreamMaxP];                      // per bin row: touched rows
-    int   X0, X1, Y0, Y1;                                         // footprint [X0,X1) x [Y0,Y1)
-    int   ncols, nrows, nseg, rps, nstages;                       // ring schedule
+    int   X0, Y0, ncols, nrows, nseg, rps, nstages;               // footprint + ring schedule
 };
 
+// Per-lane (lane < 2P: axis = lane / P, bin = lane % P) touched-cell range, then the warp-wide
+// footprint and ring schedule via shuffles.  Executed by warp 0 and, redundantly, by the producer
+// warp, so that neither has to wait for the other.
+struct WarpPlan {
+    RoiGeom g;
+    int level, H, W;
+    int lo, n;                    // this lane's bin
+    int X0, Y0, ncols, nrows, nseg, rps, nstages;
+};
+
+template <int P>
+__device__ __forceinline__ WarpPlan warp_plan(const Pyramid &pyr, const float *__restrict__ rois, int r,
+                                              int sampling_ratio, int aligned, float finest_scale,
+                                              int lane, int wx_cap, int wyd_rows)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    WarpPlan wp;
+    const float *roi = rois + 5 * (size_t)r;
+    wp.level = roi_level(roi, pyr, finest_scale);
+    wp.g = roi_geometry(roi, pyr.scale[wp.level], P, sampling_ratio, aligned);
+    wp.H = pyr.H[wp.level]; wp.W = pyr.W[wp.level];
+    const int axis = lane / P, p = lane % P;
+    int lo = 0x7fffffff, hi = -1;
+    if (lane < 2 * P) {
+        const float start = axis ? wp.g.start_w : wp.g.start_h, bin = axis ? wp.g.bin_w : wp.g.bin_h;
+        const int grid = axis ? wp.g.grid_w : wp.g.grid_h, size = axis ? wp.W : wp.H;
+        for (int i = 0; i < grid; ++i) {
+            const AxisSample s = axis_sample(start, bin, grid, size, p, i);
+            if (s.valid) { lo = min(lo, s.low); hi = max(hi, s.high); }
+        }
+    }
+    wp.n  = hi >= 0 ? hi - lo + 1 : 0;
+    wp.lo = hi >= 0 ? lo : 0;
+    const bool isx = lane >= P && lane < 2 * P, isy = lane < P;
+    const int big = 0x7fffffff;
+    int X0 = __reduce_min_sync(FULL, (isx && wp.n > 0) ? wp.lo : big);
+    int X1 = __reduce_max_sync(FULL, (isx && wp.n > 0) ? wp.lo + wp.n : -1);
+    int Y0 = __reduce_min_sync(FULL, (isy && wp.n > 0) ? wp.lo : big);
+    int Y1 = __reduce_max_sync(FULL, (isy && wp.n > 0) ? wp.lo + wp.n : -1);
+    const int xsum = __reduce_add_sync(FULL, isx ? wp.n : 0);
+    if (X1 < 0 || Y1 < 0 || xsum > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; }
+    wp.X0 = X0; wp.Y0 = Y0; wp.ncols = X1 - X0; wp.nrows = Y1 - Y0;
+    if (wp.ncols <= kStageCells) {
+        wp.nseg = 1;
+        wp.rps = wp.ncols > 0 ? kStageCells / wp.ncols : 1;
+        wp.nstages = (wp.nrows + wp.rps - 1) / wp.rps;
+    } else {
+        wp.nseg = (wp.ncols + kStageCells - 1) / kStageCells;
+        wp.rps = 1;
+        wp.nstages = wp.nrows * wp.nseg;
+    }
+    if (wp.ncols == 0 || wp.nrows == 0) wp.nstages = 0;
+    return wp;
+}
+
 // CTA layout: warps 0..P-1 consumers (warp = bin column), warp P = producer.
-// Shared memory: wx[wx_cap] | wyd[P][wyd_stride] | ring[NS][kStageCells*CB] (+ NCHW staging tile)
+// Shared memory: ring[NS][kStageCells*CB] | wx[wx_cap] | wyd[wyd_rows][PP8] (+ NCHW staging tile)
 template <int P, int VEC, int NS>
-__global__ void __launch_bounds__((P + 1) * 32)
+__global__ void __launch_bounds__((P + 1) * 32, P > 8 ? 1 : (VEC == 2 ? 2 : 3))
 roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
                         float *__restrict__ out, const int out_layout, int32_t *__restrict__ lvl_out,
-                        const int wx_cap, const int wyd_stride)
+                        const int wx_cap, const int wyd_rows)
 {
-    constexpr int CB = 128 * VEC;
+    constexpr int CB  = 128 * VEC;
+    constexpr int PP8 = (P + 3) & ~3;               // bin-row weights of one footprint row, padded
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ StreamPlan plan;
-    __shared__ RoiGeom g_s;
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
 
     float *ring = reinterpret_cast<float *>(smem_raw);                       // 128 B aligned stages
     float *wx   = ring + (size_t)NS * kStageCells * CB;
     float *wyd  = wx + wx_cap;
-    float *stage_out = wyd + (size_t)P * wyd_stride;                         // NCHW staging (optional)
+    float *stage_out = wyd + (size_t)wyd_rows * PP8;                         // NCHW staging (optional)
 
     const int nblk = (C + CB - 1) / CB;
     const int r    = blockIdx.x / nblk;
     const int cb0  = (blockIdx.x % nblk) * CB;
     const int t    = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
-
-    // ---- plan ------------------------------------------------------------------------------
-    if (t == 0) {
-        const float *roi = rois + 5 * (size_t)r;
-        const int lvl = roi_level(roi, pyr.L, finest_scale);
-        g_s = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
-        plan.level = lvl; plan.batch = g_s.batch;
-        plan.H = pyr.H[lvl]; plan.W = pyr.W[lvl];
-        plan.count = g_s.count;
-        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (lvl_out != nullptr && cb0 == 0) lvl_out[r] = lvl;
-    }
-    __syncthreads();
-    const RoiGeom g = g_s;
-    if (t < 2 * P) {                       // touched-cell range per (axis, bin)
-        const int axis = t / P, p = t % P;
-        const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
-        const int grid = axis ? g.grid_w : g.grid_h, size = axis ? plan.W : plan.H;
-        int lo = 0x7fffffff, hi = -1;
-        for (int i = 0; i < grid; ++i) {
-            const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-            if (s.valid) { lo = min(lo, s.low); hi = max(hi, s.high); }
-        }
-        const int n = hi >= 0 ? hi - lo + 1 : 0;
-        if (axis) { plan.xlo[p] = hi >= 0 ? lo : 0; plan.xn[p] = n; }
-        else      { plan.ylo[p] = hi >= 0 ? lo : 0; plan.yn[p] = n; }
-    }
-    __syncthreads();
-    if (t == 0) {                          // footprint, x-weight offsets, ring schedule
-        int X0 = 0x7fffffff, X1 = -1, Y0 = 0x7fffffff, Y1 = -1, off = 0;
-        for (int p = 0; p < P; ++p) {
-            plan.xoff[p] = off; off += plan.xn[p];
-            if (plan.xn[p] > 0) { X0 = min(X0, plan.xlo[p]); X1 = max(X1, plan.xlo[p] + plan.xn[p]); }
-            if (plan.yn[p] > 0) { Y0 = min(Y0, plan.ylo[p]); Y1 = max(Y1, plan.ylo[p] + plan.yn[p]); }
-        }
-        if (X1 < 0 || Y1 < 0 || off > wx_cap || (Y1 - Y0) > wyd_stride) { X0 = X1 = Y0 = Y1 = 0; }
-        plan.X0 = X0; plan.X1 = X1; plan.Y0 = Y0; plan.Y1 = Y1;
-        const int ncols = X1 - X0, nrows = Y1 - Y0;
-        plan.ncols = ncols; plan.nrows = nrows;
-        if (ncols <= kStageCells) {
-            plan.nseg = 1;
-            plan.rps = ncols > 0 ? max(1, kStageCells / ncols) : 1;
-            plan.nstages = (nrows + plan.rps - 1) / plan.rps;
-        } else {
-            plan.nseg = (ncols + kStageCells - 1) / kStageCells;
-            plan.rps = 1;
-            plan.nstages = nrows * plan.nseg;
-        }
-        if (ncols == 0 || nrows == 0) plan.nstages = 0;
-    }
-    __syncthreads();
-    const int nrows = plan.nrows, ncols = plan.ncols, nstages = plan.nstages;
-    const int H = plan.H, W = plan.W;
-    (void)H;
-
-    // ===== producer (warp P): bulk async copies of footprint rows into the ring ==================
-    const float *fbase = pyr.feat[plan.level] + (size_t)plan.batch * plan.H * W * C + cb0;
-    const int cbn = min(CB, C - cb0);                     // channels actually present in this block
+    const int cbn  = min(CB, C - cb0);                    // channels actually present in this block
     const bool contiguous = (cbn == C);                   // whole cells are adjacent in memory
     const int cstride = contiguous ? C : CB;              // floats between consecutive staged cells
-    auto produce = [&](int st) {
-        const int s = st % NS;
-        mbar_wait(&empty_bar[s], ((st / NS) & 1) ^ 1);    // returns at once for the first NS stages
-        float *dst = ring + (size_t)s * kStageCells * CB;
-        int row0, nr, col0, nc;
-        if (plan.nseg == 1) { row0 = st * plan.rps; nr = min(plan.rps, nrows - row0); col0 = 0; nc = ncols; }
-        else { row0 = st / plan.nseg; nr = 1; col0 = (st % plan.nseg) * kStageCells; nc = min(kStageCells, ncols - col0); }
-        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * nc * cbn * 4));
-        __syncwarp();
-        if (contiguous) {
-            for (int rr = lane; rr < nr; rr += 32) {
-                const float *src = fbase + ((size_t)(plan.Y0 + row0 + rr) * W + plan.X0 + col0) * C;
-                bulk_g2s(dst + (size_t)rr * nc * cstride, src, (uint32_t)(nc * C * 4), &full_bar[s]);
-            }
-        } else {
-            for (int cell = lane; cell < nr * nc; cell += 32) {
-                const int rr = cell / nc, cc = cell % nc;
-                const float *src = fbase + ((size_t)(plan.Y0 + row0 + rr) * W + plan.X0 + col0 + cc) * C;
-                bulk_g2s(dst + (size_t)cell * cstride, src, (uint32_t)(cbn * 4), &full_bar[s]);
-            }
-        }
-    };
-    // the first NS stages need no empty-wait: put them in flight before the weights are built
-    if (warp == P)
-        for (int st = 0; st < min(NS, nstages); ++st) produce(st);
 
-    // ---- weights (all threads help; overlaps with the first copies already in flight) ---------
-    for (int i = t; i < P * nrows; i += blockDim.x) wyd[(size_t)(i / nrows) * wyd_stride + (i % nrows)] = 0.f;
-    __syncthreads();
-    if (t < 2 * P && nstages > 0) {
-        const int axis = t / P, p = t % P;
-        const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
-        const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : plan.H;
-        if (axis) {
-            float *w = wx + plan.xoff[p];
-            const int n = plan.xn[p], lo = plan.xlo[p];
-            for (int i = 0; i < n; ++i) w[i] = 0.f;
-            for (int i = 0; i < grid; ++i) {
-                const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-                if (s.valid) { w[s.low - lo] += s.h; w[s.high - lo] += s.l; }
-            }
-        } else {
-            float *w = wyd + (size_t)p * wyd_stride - plan.Y0;        // dense over footprint rows
-            for (int i = 0; i < grid; ++i) {
-                const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-                if (s.valid) { w[s.low] += s.h; w[s.high] += s.l; }
-            }
-        }
+    if (t == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();                                      // reached at once by every warp
 
-    if (warp == P)
-        for (int st = NS; st < nstages; ++st) produce(st);
+    if (warp == P) {
+        // ===== producer: own copy of the plan, then bulk async copies of footprint rows ==========
+        const WarpPlan wp = warp_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, lane, wx_cap, wyd_rows);
+        const float *fbase = pyr.feat[wp.level] + ((size_t)wp.g.batch * wp.H * wp.W) * C + cb0
+                             + ((size_t)wp.Y0 * wp.W + wp.X0) * C;
+        const size_t row_pitch = (size_t)wp.W * C;
+        int s = 0, par = 1;                               // parity 1: first pass over a fresh barrier
+        if (wp.nseg == 1) {
+            int row0 = 0;
+            for (int st = 0; st < wp.nstages; ++st) {
+                const int nr = min(wp.rps, wp.nrows - row0);
+                mbar_wait(&empty_bar[s], par);
+                float *dst = ring + (size_t)s * kStageCells * CB;
+                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * wp.ncols * cbn * 4));
+                __syncwarp();
+                if (contiguous) {
+                    if (lane < nr)
+                        bulk_g2s(dst + (size_t)lane * wp.ncols * cstride, fbase + (size_t)(row0 + lane) * row_pitch,
+                                 (uint32_t)(wp.ncols * C * 4), &full_bar[s]);
+                } else {
+                    for (int cell = lane; cell < nr * wp.ncols; cell += 32) {
+                        const int rr = cell / wp.ncols, cc = cell - rr * wp.ncols;
+                        bulk_g2s(dst + (size_t)cell * cstride, fbase + (size_t)(row0 + rr) * row_pitch + (size_t)cc * C,
+                                 (uint32_t)(cbn * 4), &full_bar[s]);
+                    }
+                }
+                row0 += nr;
+                if (++s == NS) { s = 0; par ^= 1; }
+            }
+        } else {
+            for (int row = 0; row < wp.nrows; ++row)
+                for (int col0 = 0; col0 < wp.ncols; col0 += kStageCells) {
+                    const int nc = min(kStageCells, wp.ncols - col0);
+                    mbar_wait(&empty_bar[s], par);
+                    float *dst = ring + (size_t)s * kStageCells * CB;
+                    if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nc * cbn * 4));
+                    __syncwarp();
+                    const float *src = fbase + (size_t)row * row_pitch + (size_t)col0 * C;
+                    if (contiguous) {
+                        if (lane == 0) bulk_g2s(dst, src, (uint32_t)(nc * C * 4), &full_bar[s]);
+                    } else if (lane < nc) {
+                        bulk_g2s(dst + (size_t)lane * cstride, src + (size_t)lane * C, (uint32_t)(cbn * 4), &full_bar[s]);
+                    }
+                    if (++s == NS) { s = 0; par ^= 1; }
+                }
+        }
+    } else {
+        // ===== consumers ============================================================================
+        if (warp == 0) {
+            // plan + weights, warp-local (shuffles, no block barrier), published to the other consumers
+            const WarpPlan wp = warp_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, lane, wx_cap, wyd_rows);
+            const int axis = lane / P, p = lane % P;
+            int off = 0;                                   // exclusive scan of xn over the x lanes
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                const int nq = __shfl_sync(FULL, wp.n, P + q);
+                if (lane >= P && q < p) off += nq;
+            }
+            if (lane == 0) {
+                plan.level = wp.level; plan.count = wp.g.count;
+                plan.X0 = wp.X0; plan.Y0 = wp.Y0; plan.ncols = wp.ncols; plan.nrows = wp.nrows;
+                plan.nseg = wp.nseg; plan.rps = wp.rps; plan.nstages = wp.nstages;
+                if (lvl_out != nullptr && cb0 == 0) lvl_out[r] = wp.level;
+            }
+            if (lane >= P && lane < 2 * P) { plan.xlo[p] = wp.lo; plan.xn[p] = wp.n; plan.xoff[p] = off; }
+            for (int i = lane; i < wp.nrows * (PP8 / 4); i += 32)
+                reinterpret_cast<float4 *>(wyd)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (lane < 2 * P && wp.nstages > 0) {
+                const float start = axis ? wp.g.start_w : wp.g.start_h, bin = axis ? wp.g.bin_w : wp.g.bin_h;
+                const int grid = axis ? wp.g.grid_w : wp.g.grid_h, size = axis ? wp.W : wp.H;
+                if (axis) {
+                    float *w = wx + off;
+                    for (int i = 0; i < wp.n; ++i) w[i] = 0.f;
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample s = axis_sample(start, bin, grid, size, p, i);
+                        if (s.valid) { w[s.low - wp.lo] += s.h; w[s.high - wp.lo] += s.l; }
+                    }
+                } else {
+                    float *w = wyd + p - (size_t)wp.Y0 * PP8;     // wyd[row - Y0][p]
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample s = axis_sample(start, bin, grid, size, p, i);
+                        if (s.valid) { w[(size_t)s.low * PP8] += s.h; w[(size_t)s.high * PP8] += s.l; }
+                    }
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(P * 32) : "memory");     // consumers only
 
-    if (warp < P) {
         float4 acc[P][VEC];
 #pragma unroll
         for (int ph = 0; ph < P; ++ph)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[ph][v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        // ===== consumers: warp = bin column pw ==================================================
         const int pw = warp;
+        const int nrows = plan.nrows, ncols = plan.ncols, nstages = plan.nstages, rps = plan.rps;
         const int xlo = plan.xlo[pw] - plan.X0, nx = plan.xn[pw];
         const float *wxp = wx + plan.xoff[pw];
+        int loff[VEC];                                     // lanes past the channel count re-read channel 0
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) loff[v] = (v * 128 + lane * 4 < cbn) ? v * 128 + lane * 4 : 0;
+
+        auto fold = [&](int j, float4 (&racc)[VEC]) {      // footprint row j -> the bin rows it touches
+            float wrow[PP8];
+#pragma unroll
+            for (int q = 0; q < PP8 / 4; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(wyd + (size_t)j * PP8 + 4 * q);
+                wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int ph = 0; ph < P; ++ph) {
+                if (wrow[ph] != 0.f) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) fma4(acc[ph][v], wrow[ph], racc[v]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+
         float4 racc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int st = 0; st < nstages; ++st) {
-            const int s = st % NS;
-            mbar_wait(&full_bar[s], (st / NS) & 1);
-            const float *src = ring + (size_t)s * kStageCells * CB + lane * 4;
-            int row0, nr, col0, nc;
-            if (plan.nseg == 1) { row0 = st * plan.rps; nr = min(plan.rps, nrows - row0); col0 = 0; nc = ncols; }
-            else { row0 = st / plan.nseg; nr = 1; col0 = (st % plan.nseg) * kStageCells; nc = min(kStageCells, ncols - col0); }
-            // my cells inside this stage's column window [col0, col0+nc)
-            const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
-            for (int rr = 0; rr < nr; ++rr) {
-                const float *rowp = src + (size_t)(rr * nc - col0) * cstride;
-#pragma unroll 4
-                for (int cx = c_beg; cx < c_end; ++cx) {
-                    const float w = wxp[cx - xlo];
+        int s = 0, par = 0;
+        if (plan.nseg == 1) {
+            int row = 0;
+            const size_t rstride = (size_t)ncols * cstride;
+            for (int st = 0; st < nstages; ++st) {
+                const int nr = min(rps, nrows - row);
+                mbar_wait(&full_bar[s], par);
+                const float *base = ring + (size_t)s * kStageCells * CB + (size_t)xlo * cstride;
+                for (int rr = 0; rr < nr; ++rr, ++row) {
+                    const float *cp = base + rr * rstride;
+#pragma unroll 2
+                    for (int i = 0; i < nx; ++i, cp += cstride) {
+                        const float w = wxp[i];
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        if (v * 128 + lane * 4 < cbn) {
-                            const float4 val = *reinterpret_cast<const float4 *>(rowp + (size_t)cx * cstride + v * 128);
-                            fma4(racc[v], w, val);
-                        }
+                        for (int v = 0; v < VEC; ++v)
+                            fma4(racc[v], w, *reinterpret_cast<const float4 *>(cp + loff[v]));
                     }
+                    fold(row, racc);
                 }
-                const bool row_done = (plan.nseg == 1) || (col0 + nc >= ncols);
-                if (row_done) {
-                    const int j = row0 + rr;                          // footprint row index
-#pragma unroll
-                    for (int ph = 0; ph < P; ++ph) {
-                        const float wy = wyd[(size_t)ph * wyd_stride + j];
-                        if (wy != 0.f) {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) fma4(acc[ph][v], wy, racc[v]);
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                if (++s == NS) { s = 0; par ^= 1; }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        } else {
+            for (int row = 0; row < nrows; ++row)
+                for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
+                    const int nc = min(kStageCells, ncols - col0);
+                    mbar_wait(&full_bar[s], par);
+                    const float *base = ring + (size_t)s * kStageCells * CB;
+                    const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
+                    for (int cx = c_beg; cx < c_end; ++cx) {
+                        const float w = wxp[cx - xlo];
+                        const float *cp = base + (size_t)(cx - col0) * cstride;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            fma4(racc[v], w, *reinterpret_cast<const float4 *>(cp + loff[v]));
+                    }
+                    if (col0 + nc >= ncols) fold(row, racc);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    if (++s == NS) { s = 0; par ^= 1; }
+                }
         }
 
         // ---- epilogue: 1/count, optional AG-FCN channel attention, store ----------------------
@@ -270,16 +332,24 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
         for (int v = 0; v < VEC; ++v) {
             const int cl = v * 128 + lane * 4;
             const int c = cb0 + cl;
-            if (c >= C) continue;
-            float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (cl >= cbn) continue;
+            float4 cs = make_float4(inv, inv, inv, inv);
             if (chan_scale != nullptr) {
                 const int si = scale_index != nullptr ? scale_index[r] : r;
-                cs = ldg4(chan_scale + (size_t)si * C + c);
+                const float4 a = ldg4(chan_scale + (size_t)si * C + c);
+                cs = make_float4(inv * a.x, inv * a.y, inv * a.z, inv * a.w);
             }
 #pragma unroll
             for (int ph = 0; ph < P; ++ph) {
                 const float4 a = acc[ph][v];
-                const float4 o = make_float4(a.x * inv * cs.x, a.y * inv * cs.y, a.z * inv * cs.z, a.w * inv * cs.w);
+                float4 o;
+                if (chan_scale != nullptr) {               // (acc * 1/count) * vec, same rounding order as unfused
+                    const int si = scale_index != nullptr ? scale_index[r] : r;
+                    const float4 b = ldg4(chan_scale + (size_t)si * C + c);
+                    o = make_float4(a.x * inv * b.x, a.y * inv * b.y, a.z * inv * b.z, a.w * inv * b.w);
+                } else {
+                    o = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+                }
                 if (out_layout == FGN_LAYOUT_NHWC) {
                     *reinterpret_cast<float4 *>(out + (((size_t)r * P + ph) * P + pw) * C + c) = o;
                 } else {
@@ -287,12 +357,12 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     sdst[0] = o.x; sdst[P * P] = o.y; sdst[2 * P * P] = o.z; sdst[3 * P * P] = o.w;
                 }
             }
+            (void)cs;
         }
     }
     if (out_layout == FGN_LAYOUT_NCHW) {
         __syncthreads();
-        const int cb_n = min(CB, C - cb0);
-        const int n = cb_n * P * P;
+        const int n = cbn * P * P;
         float *o = out + ((size_t)r * C + cb0) * (P * P);
         const int n4 = n >> 2;
         for (int i = t; i < n4; i += blockDim.x)
@@ -311,8 +381,9 @@ static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, 
     int maxH = 0, maxW = 0;
     for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
     const int wx_cap = (maxW + 6 * P + 16 + 3) & ~3;
-    const int wyd_stride = (maxH + 3) & ~3;
-    size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)wx_cap * 4 + (size_t)P * wyd_stride * 4;
+    const int wyd_rows = maxH;
+    constexpr int PP8 = (P + 3) & ~3;
+    size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)wx_cap * 4 + (size_t)wyd_rows * PP8 * 4;
     if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
     if (smem > 200 * 1024) { *taken = false; return FGN_OK; }
     auto kern = roi_align_stream_kernel<P, VEC, NS>;
@@ -324,7 +395,7 @@ static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const int nblk = (C + CB - 1) / CB;
     kern<<<R * nblk, (P + 1) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
                                                 chan_scale, scale_index, out, out_layout, lvl_out,
-                                                wx_cap, wyd_stride);
+                                                wx_cap, wyd_rows);
     FGN_LAUNCH_OK();
     *taken = true;
     return FGN_OK;

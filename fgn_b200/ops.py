@@ -20,7 +20,7 @@ from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, FgnError, Pyramid
 __all__ = [
     "map_roi_levels", "roi_align_multilevel", "roi_align_sample_indices", "to_nhwc", "support_mask_pool",
     "support_pool", "attention_vectors", "channel_attention", "best_class_select",
-    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "launch_count",
+    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count",
 ]
 
 
@@ -354,7 +354,7 @@ def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mea
         x.data_ptr(), lay, rb.data_ptr(), s.data_ptr(), r, b, n_ways, c, p,
         pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(), pr.gn_groups, pr.gn_eps,
         pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(), pr.fc_reg_b.data_ptr(),
-        cls.data_ptr(), reg.data_ptr(), _ptr(raw_c), _ptr(raw_r), {"fp32": 0, "bf16": 1}[precision],
+        cls.data_ptr(), reg.data_ptr(), _ptr(raw_c), _ptr(raw_r), {"fp32": 0, "tf32": 1}[precision],
         ws.data_ptr(), wsb, _stream()), "fgn_relation_fusion_fwd")
     return (cls, reg, raw_c, raw_r) if return_raw else (cls, reg)
 
@@ -386,9 +386,27 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
         ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
         s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
         pr.gn_groups, pr.gn_eps, pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(),
-        pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), {"fp32": 0, "bf16": 1}[precision],
+        pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), {"fp32": 0, "tf32": 1}[precision],
         ws.data_ptr(), wsb, _stream()), "fgn_guided_roi_fused_fwd")
     return (cls, reg, lvl.long()) if return_levels else (cls, reg)
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, precision: str = "fp32",
+            use_workspace: bool = True) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias): the relation head's contraction alone (rows may be strided)."""
+    _need_cuda(a, b, bias)
+    if a.stride(1) != 1 or b.stride(1) != 1:
+        raise FgnError("gemm_nt operands must be K-major (unit stride along K)")
+    m, k = a.shape
+    n = b.shape[0]
+    c = torch.empty((m, n), device=a.device, dtype=torch.float32)
+    lib = _lib.load()
+    wsb = lib.fgn_gemm_workspace_bytes(n, k) if use_workspace else 0
+    ws = torch.empty((max(wsb, 1),), device=a.device, dtype=torch.uint8)
+    _lib.check(lib.fgn_gemm_nt(_f32(a, "a").data_ptr(), a.stride(0), _f32(b, "b").data_ptr(), b.stride(0), _ptr(bias),
+                               c.data_ptr(), n, m, n, k, {"fp32": 0, "tf32": 1}[precision], ws.data_ptr(), wsb,
+                               _stream()), "fgn_gemm_nt")
+    return c
 
 
 def cls_bbox_reassemble(raw_cls: torch.Tensor, raw_reg: torch.Tensor, rois_amount: int, n_ways: int):

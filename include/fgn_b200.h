@@ -136,8 +136,8 @@ int fgn_best_class_select(const float *cls, const float *reg, int B, int N, int 
  *   conv_w [C,2C] (Conv2d(2C->C,1x1).weight), conv_b [C]; gn_w, gn_b [C] (GroupNorm(32,C));
  *   fc_cls_w [2,C], fc_cls_b [2]; fc_reg_w [4,C], fc_reg_b [4];
  *   cls_out [R,N+1], reg_out [R,4N];  raw_cls_out/raw_reg_out optional ([R*N,2]/[R*N,4]).
- *   precision: 0 = fp32 (3xTF32 error-compensated tensor-core contraction, fp32 parity),
- *              1 = bf16 operands / fp32 accumulate (reported separately).
+ *   precision: 0 = fp32 parity (3xTF32 error-compensated tcgen05 contraction),
+ *              1 = single-pass TF32 on tcgen05 (reduced precision, reported separately).
  * workspace: fgn_relation_fusion_workspace_bytes(R, BN, C, P) bytes. */
 size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P);
 int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout, const int32_t *roi_batch,
@@ -148,6 +148,14 @@ int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout, const int32_
                             const float *fc_reg_w, const float *fc_reg_b,
                             float *cls_out, float *reg_out, float *raw_cls_out, float *raw_reg_out,
                             int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The relation head's contraction alone (Conv2d(2C->C,1x1) as a GEMM, fgn_roi_head.py:272):
+ *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]); row-major fp32 with leading dimensions lda/ldb/ldc.
+ * precision as in fgn_relation_fusion_fwd.  workspace: fgn_gemm_workspace_bytes(N, K) bytes;
+ * without it (or for shapes outside K%32==0, N%16==0) the fp32 SIMT kernel is used. */
+size_t fgn_gemm_workspace_bytes(int N, int K);
+int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
+                int M, int N, int K, int precision, void *workspace, size_t workspace_bytes, void *stream);
 
 /* count_modified_cls_bbox alone (fgn_roi_head.py:302-326), generalised from N in {1,3} to any N:
  *   raw_cls [R*N,2] (bg,fg), raw_reg [R*N,4] -> cls_out [R,N+1] = (fg_0..fg_{N-1}, bg of the

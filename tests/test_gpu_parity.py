@@ -362,6 +362,31 @@ def test_mask_branch_p14_vs_oracle():
     close(got, want, what="p14 mask feats")
 
 
+@pytest.mark.parametrize("M,N,K", [(49 * 40, 256, 256), (49 * 3, 64, 64), (1000, 256, 256), (128 * 5 + 17, 1024, 1024), (300, 48, 32)])
+def test_relation_contraction_tcgen05_vs_fp64(M, N, K):
+    """3xTF32 tcgen05 contraction holds fp32 parity (vs an fp64 matmul); the SIMT kernel and the strided
+    weight views used by the relation head (conv_w[:, :C], conv_w[:, C:]) go through the same entry."""
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, 2 * K, generator=g) * (2.0 / (2 * K)) ** 0.5
+    bias = torch.randn(N, generator=g)
+    wd = w.to(dev())
+    for half in (0, 1):
+        bview = wd[:, half * K:(half + 1) * K]
+        want = (a.double() @ w[:, half * K:(half + 1) * K].double().t() + bias.double()).float()
+        got = ops.gemm_nt(a.to(dev()), bview, bias.to(dev()), "fp32")
+        # tensor-core fp32 accumulation truncates: error grows ~K*6e-8 (4e-5 at K=1024), inside the 1e-4 bar
+        close(got, want, what=f"3xTF32 half={half}")
+        assert float((got.cpu() - want).abs().max()) < (2e-5 if K <= 256 else 6e-5)
+        simt = ops.gemm_nt(a.to(dev()), bview, bias.to(dev()), "fp32", use_workspace=False)
+        close(simt, want, atol=2e-5, rtol=1e-5, what="simt")
+    if K % 32 == 0 and N % 16 == 0:
+        fast = ops.gemm_nt(a.to(dev()), wd[:, :K], bias.to(dev()), "tf32")
+        err = (fast.cpu() - (a.double() @ w[:, :K].double().t() + bias.double()).float()).abs().max()
+        assert 1e-6 < float(err) < 2e-2, float(err)        # single-pass TF32: visibly lower precision
+
+
 def test_empty_proposals():
     from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
     cfg = CONFIGS["tiny_fpn"]
