@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying one CUDA graph per episode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -205,7 +206,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the fgn_b200 arm has no CPU fallback (use --impl reference)")
     import torch.distributed as dist
     from fgn_b200 import ops
-    from fgn_b200.episodes import build_heads, episode_to_device, gather_results, make_episode, run_guided_path
+    from fgn_b200.episodes import EpisodeRunner, build_heads, episode_to_device, gather_results, make_episode, run_guided_path
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -225,12 +226,16 @@ def main():
     bytes_resident = sum(t.numel() * 4 for ep in dev_eps for t in ep["qry"] + ep["spp"])
     config["l2"] = f"no flush: episode stream of {E} x {bytes_resident / E / 1e6:.0f} MB distinct inputs > 126 MB L2"
 
+    runner = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs)
+    config["launch"] = "eager" if args.no_graphs else "one CUDA graph per resident episode"
+    res_buf = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), device=device)
+
     def step_resident():
-        outs = []
-        for ep in dev_eps:
-            o = run_guided_path(rpn, head, ep)
-            outs.append(torch.cat([o["cls_score"], o["bbox_pred"]], 1))
-        res = torch.stack(outs)                               # [E, R, 5N+1]
+        for i in range(E):
+            o = runner.run(i)
+            res_buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
+            res_buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+        res = res_buf                                         # [E, R, 5N+1]
         if world > 1:
             res = gather_results(res, E * world)
         return res
@@ -248,7 +253,7 @@ def main():
             sync_all()
             if sampler:
                 sampler.start()
-            l0 = ops.launch_count()
+            l0 = ops.launch_count() + runner.launches
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
@@ -257,7 +262,7 @@ def main():
             sync_all()
             ms = e0.elapsed_time(e1)
             clocks = sampler.stop() if sampler else None
-            launches = ops.launch_count() - l0
+            launches = ops.launch_count() + runner.launches - l0
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -54,6 +54,9 @@ SIGNATURES = {
     "fgn_attention_vectors_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "fgn_attention_vectors": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "fgn_channel_attention": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "fgn_attention_vectors_ml_workspace_bytes": (c_size_t, [POINTER(Pyramid), c_int, c_int, c_int]),
+    "fgn_attention_vectors_ml": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "fgn_channel_attention_ml": (c_int, [POINTER(Pyramid), _P, c_int, c_int, c_int, POINTER(c_void_p), _P]),
     "fgn_best_class_select": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "fgn_relation_fusion_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,

@@ -57,6 +57,10 @@ class AGRPNHead(nn.Module):
         vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
         return vec, ops.channel_attention(qry_fmap, vec)
 
+    def attention_multilevel(self, qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor]):
+        """``attention`` for every pyramid level at once (FPN mode; three launches for channels_last inputs)."""
+        return ops.attention_multilevel(qry_feats, spp_feats, self.n_ways, self.k_shots)
+
     def forward_single(self, qry_fmap: torch.Tensor, spp_fmaps: Optional[torch.Tensor] = None, qry_bboxes=None,
                        qry_cat_ids=None, img_metas_cpu: Optional[list] = None, train_mode: bool = False,
                        log_mode: bool = False):

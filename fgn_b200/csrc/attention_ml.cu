@@ -1,0 +1,178 @@
+// attention_ml.cu -- AG-RPN attention (fgn_ag_rpn_head.py:37-46) for a whole pyramid in three
+// launches instead of three per level: the coarse levels (P5, P6) are a few KB and purely
+// launch-latency bound when done one by one.  NHWC (channels_last) only; other layouts go through
+// the per-level entry points.
+#include "common.cuh"
+
+namespace fgn {
+
+constexpr int kMlSlab = 64;       // pixels per partial-sum block
+constexpr int kMlChunk = 4;       // float4 per thread per block in the multiply kernel
+
+struct MlLevels {
+    int          L;
+    const float *in[FGN_MAX_LEVELS];
+    float       *out[FGN_MAX_LEVELS];
+    int          HW[FGN_MAX_LEVELS];
+    int          blk_off[FGN_MAX_LEVELS + 1];   // block ranges per level (grid.x)
+};
+
+__device__ __forceinline__ int ml_level_of(const MlLevels &lv, int blk)
+{
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < FGN_MAX_LEVELS; ++i) l += (i < lv.L && blk >= lv.blk_off[i]) ? 1 : 0;
+    return l;
+}
+
+// partial[(blk_off[l] + slab) * BN + bn][C] = sum over the slab's pixels (K consecutive images = one run)
+__global__ void __launch_bounds__(256)
+attention_vec_ml_partial_kernel(const MlLevels lv, const int BN, const int K, const int C,
+                                float *__restrict__ partial)
+{
+    const int bn = blockIdx.y;
+    const int l = ml_level_of(lv, blockIdx.x), slab = blockIdx.x - lv.blk_off[l];
+    const int c4 = C >> 2;
+    const int total = K * lv.HW[l];
+    const int p0 = slab * kMlSlab, p1 = min(total, p0 + kMlSlab);
+    extern __shared__ __align__(16) float red[];   // [rows][C]
+    const int rows = max(1, (int)blockDim.x / c4);
+    const float *base = lv.in[l] + (size_t)bn * total * C;
+    const int cv = threadIdx.x % c4, rowi = threadIdx.x / c4;
+    if (rowi < rows) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = p0 + rowi; p < p1; p += rows) {
+            const float4 v = ldg4(base + (size_t)p * C + cv * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(red + (size_t)rowi * C + cv * 4) = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += red[(size_t)rr * C + c];
+        partial[((size_t)blockIdx.x * BN + bn) * C + c] = s;
+    }
+}
+
+// vec[l][bn][c] = (sum of the level's slabs, in slab order) / (K*HW_l)
+__global__ void attention_vec_ml_finalize_kernel(const MlLevels lv, const int BN, const int K, const int C,
+                                                 const float *__restrict__ partial, float *__restrict__ vec)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= lv.L * BN * C) return;
+    const int c = idx % C, bn = (idx / C) % BN, l = idx / (C * BN);
+    float s = 0.f;
+    for (int b = lv.blk_off[l]; b < lv.blk_off[l + 1]; ++b) s += partial[((size_t)b * BN + bn) * C + c];
+    vec[idx] = s * (1.0f / (float)(K * lv.HW[l]));
+}
+
+// out_l[b*N+n, :, :, c] = qry_l[b, :, :, c] * vec[l][b*N+n][c]; one read, N streaming writes
+__global__ void __launch_bounds__(256)
+channel_attention_ml_kernel(const MlLevels lv, const float *__restrict__ vec, const int B, const int N, const int C)
+{
+    const int l = ml_level_of(lv, blockIdx.x), blk = blockIdx.x - lv.blk_off[l];
+    const int c4 = C >> 2;
+    const size_t per_img = (size_t)lv.HW[l] * c4, total = (size_t)B * per_img;
+    const float *q = lv.in[l];
+    float *o = lv.out[l];
+    const float *v = vec + (size_t)l * B * N * C;
+    const size_t i0 = (size_t)blk * (256 * kMlChunk) + threadIdx.x;
+    float4 x[kMlChunk];
+#pragma unroll
+    for (int j = 0; j < kMlChunk; ++j) {
+        const size_t i = i0 + (size_t)j * 256;
+        x[j] = i < total ? ldg4(q + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kMlChunk; ++j) {
+        const size_t i = i0 + (size_t)j * 256;
+        if (i >= total) continue;
+        const int b = i / per_img;
+        const size_t rem = i - (size_t)b * per_img;
+        const int cv = rem % c4;
+        for (int n = 0; n < N; ++n) {
+            const float4 s = ldg4(v + ((size_t)b * N + n) * C + cv * 4);
+            __stcs(reinterpret_cast<float4 *>(o + ((size_t)b * N + n) * per_img * 4) + rem,
+                   make_float4(x[j].x * s.x, x[j].y * s.y, x[j].z * s.z, x[j].w * s.w));
+        }
+    }
+}
+
+static int fill_levels(const fgn_pyramid_t *p, MlLevels &lv)
+{
+    FGN_CHECK_ARG(p != nullptr && p->num_levels >= 1 && p->num_levels <= FGN_MAX_LEVELS, "bad pyramid");
+    lv.L = p->num_levels;
+    for (int l = 0; l < FGN_MAX_LEVELS; ++l) {
+        lv.in[l] = l < lv.L ? p->feat[l] : nullptr;
+        lv.out[l] = nullptr;
+        lv.HW[l] = l < lv.L ? p->H[l] * p->W[l] : 0;
+        FGN_CHECK_ARG(l >= lv.L || (lv.HW[l] > 0 && lv.in[l] != nullptr), "level %d is empty", l);
+    }
+    return FGN_OK;
+}
+
+}  // namespace fgn
+
+using namespace fgn;
+
+extern "C" size_t fgn_attention_vectors_ml_workspace_bytes(const fgn_pyramid_t *spp, int BN, int K, int C)
+{
+    if (!spp || BN <= 0 || K <= 0 || C <= 0) return 0;
+    size_t blocks = 0;
+    for (int l = 0; l < spp->num_levels && l < FGN_MAX_LEVELS; ++l)
+        blocks += (size_t)ceil_div(K * spp->H[l] * spp->W[l], kMlSlab);
+    return blocks * BN * C * sizeof(float);
+}
+
+extern "C" int fgn_attention_vectors_ml(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec,
+                                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(BN >= 0 && K > 0 && C > 0, "bad dims");
+    if (BN == 0) return FGN_OK;
+    if ((C & 3) || C > 1024) { set_error("attention_vectors_ml needs C%%4==0 and C<=1024 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
+    MlLevels lv;
+    int rc = fill_levels(spp, lv);
+    if (rc) return rc;
+    FGN_CHECK_ARG(vec != nullptr, "NULL pointer");
+    lv.blk_off[0] = 0;
+    for (int l = 0; l < lv.L; ++l) lv.blk_off[l + 1] = lv.blk_off[l] + ceil_div(K * lv.HW[l], kMlSlab);
+    for (int l = lv.L + 1; l <= FGN_MAX_LEVELS; ++l) lv.blk_off[l] = lv.blk_off[lv.L];
+    const size_t need = fgn_attention_vectors_ml_workspace_bytes(spp, BN, K, C);
+    if (!workspace || workspace_bytes < need) {
+        set_error("attention_vectors_ml: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    FGN_CHECK_ARG(BN <= 65535, "BN too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int c4 = C >> 2, rows = max(1, 256 / c4);
+    attention_vec_ml_partial_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
+        lv, BN, K, C, (float *)workspace);
+    FGN_LAUNCH_OK();
+    attention_vec_ml_finalize_kernel<<<ceil_div(lv.L * BN * C, 256), 256, 0, st>>>(lv, BN, K, C, (const float *)workspace, vec);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+extern "C" int fgn_channel_attention_ml(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                                        float *const *out_host, void *stream)
+{
+    FGN_CHECK_ARG(B >= 0 && N > 0 && C > 0, "bad dims");
+    if (B == 0) return FGN_OK;
+    if (C & 3) { set_error("channel_attention_ml needs C%%4==0 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
+    MlLevels lv;
+    int rc = fill_levels(qry, lv);
+    if (rc) return rc;
+    FGN_CHECK_ARG(vec && out_host, "NULL pointer");
+    lv.blk_off[0] = 0;
+    for (int l = 0; l < lv.L; ++l) {
+        FGN_CHECK_ARG(out_host[l] != nullptr, "output level %d is NULL", l);
+        lv.out[l] = out_host[l];
+        const size_t elems = (size_t)B * lv.HW[l] * (C >> 2);
+        lv.blk_off[l + 1] = lv.blk_off[l] + (int)((elems + 256 * kMlChunk - 1) / (256 * kMlChunk));
+    }
+    for (int l = lv.L + 1; l <= FGN_MAX_LEVELS; ++l) lv.blk_off[l] = lv.blk_off[lv.L];
+    channel_attention_ml_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}

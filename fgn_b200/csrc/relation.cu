@@ -249,8 +249,11 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
     const int nblk = ceil_div(C, cblk);
     const int nwarps = kEpiThreads / 32;
     const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
-    if (smem > 48 * 1024)
+    static int epi_attr = 48 * 1024;
+    if ((int)smem > epi_attr) {
         FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        epi_attr = (int)smem;
+    }
     FGN_CHECK_ARG(nblk <= 65535, "nblk");
     relation_epilogue_kernel<kMaxPP><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
         w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);

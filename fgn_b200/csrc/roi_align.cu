@@ -335,8 +335,11 @@ static int launch_sep_nb(const Pyramid &d, int C, int CB, const float *rois, int
     size_t smem = (size_t)wtab_cap * 4;
     if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
     auto kern = roi_align_sep_nhwc_kernel<P, NB>;
-    if (smem > 48 * 1024)
+    static int attr_set = 48 * 1024;      // per instantiation
+    if ((int)smem > attr_set) {
         FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = (int)smem;
+    }
     const int nblk = (C + CB - 1) / CB;
     kern<<<R * nblk, warps * 32, smem, st>>>(d, C, CB, rois, R, sampling_ratio, aligned,
                                               finest_scale, chan_scale, scale_index, out,

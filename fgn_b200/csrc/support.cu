@@ -8,16 +8,27 @@ namespace fgn {
 // ---- K2: roi_align(spp_isegmaps.float(), boxes, 7)  (fgn_roi_head.py:429) --------------------
 // One CTA per support image.  spatial_scale=1, sampling_ratio=-1 (adaptive), aligned=False,
 // one box per image, one channel.  The adaptive grid is ~ceil(0.8*S/7)^2 (~900 samples per bin
-// for S=256), so the separable form matters most here: row pass with lanes along x and a
-// warp-shuffle reduction per (row, bin), then a 49-thread column pass.
+// for S=256), so the separable form matters most here:
+//   1. every (axis, bin, sample) coordinate is evaluated by its own thread (exact reference
+//      arithmetic) into shared memory;
+//   2. one thread per (axis, bin) folds its samples, in sample order, into per-cell weights;
+//   3. row pass: t[y][pw] = sum_x wx[pw][x] * mask[y][x], one (row, bin) pair per thread;
+//   4. column pass: out[ph][pw] = sum_y wy[ph][y] * t[y][pw] / count, one bin per thread.
+constexpr int kMaskThreads = 512;
+
 template <int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMaskThreads)
 support_mask_pool_kernel(const uint8_t *__restrict__ mask, const float *__restrict__ boxes,
-                         const int S_h, const int S_w, float *__restrict__ out, const int cap)
+                         const int S_h, const int S_w, float *__restrict__ out, const int cap,
+                         const int gcap)
 {
     extern __shared__ __align__(16) float smem[];
-    // layout: wy[cap] | wx[cap] | t[S_h * P]
+    // layout: wy[cap] | wx[cap] | t[S_h * P] | samples: low[2P*gcap] high[2P*gcap] l[2P*gcap] h[2P*gcap]
     float *wy = smem, *wx = smem + cap, *t = smem + 2 * cap;
+    int   *s_low  = reinterpret_cast<int *>(t + (size_t)S_h * P);
+    int   *s_high = s_low + 2 * P * gcap;
+    float *s_l    = reinterpret_cast<float *>(s_high + 2 * P * gcap);
+    float *s_h    = s_l + 2 * P * gcap;
     __shared__ int lo[2][P], n[2][P], off[2][P];
     __shared__ RoiGeom g_s;
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -27,14 +38,29 @@ support_mask_pool_kernel(const uint8_t *__restrict__ mask, const float *__restri
     }
     __syncthreads();
     const RoiGeom g = g_s;
+    const bool staged = g.grid_h <= gcap && g.grid_w <= gcap;      // else: recompute samples on the fly
+    if (staged) {
+        for (int i = tid; i < 2 * P * gcap; i += blockDim.x) {
+            const int axis = i / (P * gcap), p = (i / gcap) % P, k = i % gcap;
+            const int grid = axis ? g.grid_w : g.grid_h;
+            if (k < grid) {
+                const AxisSample s = axis ? axis_sample(g.start_w, g.bin_w, g.grid_w, S_w, p, k)
+                                          : axis_sample(g.start_h, g.bin_h, g.grid_h, S_h, p, k);
+                s_low[i] = s.valid ? s.low : -1; s_high[i] = s.high; s_l[i] = s.l; s_h[i] = s.h;
+            }
+        }
+    }
+    __syncthreads();
     if (tid < 2 * P) {
         const int axis = tid / P, p = tid % P;
         const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
         const int grid = axis ? g.grid_w : g.grid_h, size = axis ? S_w : S_h;
         int l = 0x7fffffff, h = -1;
         for (int i = 0; i < grid; ++i) {
-            const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-            if (s.valid) { l = min(l, s.low); h = max(h, s.high); }
+            int sl, sh;
+            if (staged) { sl = s_low[tid * gcap + i]; sh = s_high[tid * gcap + i]; }
+            else { const AxisSample s = axis_sample(start, bin, grid, size, p, i); sl = s.valid ? s.low : -1; sh = s.high; }
+            if (sl >= 0) { l = min(l, sl); h = max(h, sh); }
         }
         lo[axis][p] = h >= 0 ? l : 0;
         n[axis][p]  = h >= 0 ? h - l + 1 : 0;
@@ -52,34 +78,34 @@ support_mask_pool_kernel(const uint8_t *__restrict__ mask, const float *__restri
         const int grid = axis ? g.grid_w : g.grid_h, size = axis ? S_w : S_h;
         const int l = lo[axis][p];
         for (int i = 0; i < grid; ++i) {
-            const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-            if (s.valid && s.high - l < cnt) { w[s.low - l] += s.h; w[s.high - l] += s.l; }
+            int sl, sh; float fl, fh;
+            if (staged) { sl = s_low[tid * gcap + i]; sh = s_high[tid * gcap + i]; fl = s_l[tid * gcap + i]; fh = s_h[tid * gcap + i]; }
+            else { const AxisSample s = axis_sample(start, bin, grid, size, p, i); sl = s.valid ? s.low : -1; sh = s.high; fl = s.l; fh = s.h; }
+            if (sl >= 0 && sh - l < cnt) { w[sl - l] += fh; w[sh - l] += fl; }
         }
     }
     __syncthreads();
-    // row pass: t[y][pw] = sum_x wx[pw][x] * mask[y][x] for every touched row
-    const int y0 = lo[0][0];
-    int y1 = y0;
-    for (int p = 0; p < P; ++p) if (n[0][p] > 0) y1 = max(y1, lo[0][p] + n[0][p]);
+    int ymin = 0x7fffffff, ymax = 0;
+    for (int p = 0; p < P; ++p)
+        if (n[0][p] > 0) { ymin = min(ymin, lo[0][p]); ymax = max(ymax, lo[0][p] + n[0][p]); }
+    if (ymin == 0x7fffffff) ymin = ymax = 0;
     const uint8_t *mk = mask + (size_t)m * S_h * S_w;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    int ymin = 0x7fffffff;
-    for (int p = 0; p < P; ++p) if (n[0][p] > 0) ymin = min(ymin, lo[0][p]);
-    if (ymin == 0x7fffffff) ymin = y1 = 0;
-    for (int y = ymin + warp; y < y1; y += nwarps) {
-        const uint8_t *row = mk + (size_t)y * S_w;
-#pragma unroll
-        for (int pw = 0; pw < P; ++pw) {
-            const int xl = lo[1][pw], nx = n[1][pw];
-            const float *w = wx + off[1][pw];
-            float s = 0.f;
-            for (int xi = lane; xi < nx; xi += 32) s = fmaf(w[xi], row[xl + xi] ? 1.f : 0.f, s);
-            s = warp_sum(s);
-            if (lane == 0) t[(size_t)(y - ymin) * P + pw] = s;
+    // row pass: consecutive threads take consecutive bins of the same row -> neighbouring byte runs
+    for (int i = tid; i < (ymax - ymin) * P; i += blockDim.x) {
+        const int y = ymin + i / P, pw = i % P;
+        const uint8_t *row = mk + (size_t)y * S_w + lo[1][pw];
+        const float *w = wx + off[1][pw];
+        const int nx = n[1][pw];
+        float s0 = 0.f, s1 = 0.f;
+        int xi = 0;
+        for (; xi + 1 < nx; xi += 2) {
+            s0 = fmaf(w[xi], row[xi] ? 1.f : 0.f, s0);
+            s1 = fmaf(w[xi + 1], row[xi + 1] ? 1.f : 0.f, s1);
         }
+        if (xi < nx) s0 = fmaf(w[xi], row[xi] ? 1.f : 0.f, s0);
+        t[i] = s0 + s1;
     }
     __syncthreads();
-    (void)y0;
     if (tid < P * P) {
         const int ph = tid / P, pw = tid % P;
         const int yl = lo[0][ph], ny = n[0][ph];
@@ -245,14 +271,16 @@ extern "C" int fgn_support_mask_pool(const uint8_t *mask, const float *boxes, in
     FGN_CHECK_ARG(mask && boxes && out, "NULL pointer");
     if (P != 7 && P != 14) { set_error("support_mask_pool: P=%d not instantiated (7, 14)", P); return FGN_ERR_UNSUPPORTED; }
     const int cap = ((max(S_h, S_w) + 6 * P + 16) + 3) & ~3;
-    const size_t smem = ((size_t)2 * cap + (size_t)S_h * P) * 4;
+    const int gcap = 64;                                          // staged samples per bin (adaptive grid <= 64)
+    const size_t smem = ((size_t)2 * cap + (size_t)S_h * P + (size_t)4 * 2 * P * gcap) * 4;
     cudaStream_t st = (cudaStream_t)stream;
+    static int attr7 = 48 * 1024, attr14 = 48 * 1024;
     if (P == 7) {
-        if (smem > 48 * 1024) FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        support_mask_pool_kernel<7><<<M, 256, smem, st>>>(mask, boxes, S_h, S_w, out, cap);
+        if ((int)smem > attr7) { FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr7 = (int)smem; }
+        support_mask_pool_kernel<7><<<M, kMaskThreads, smem, st>>>(mask, boxes, S_h, S_w, out, cap, gcap);
     } else {
-        if (smem > 48 * 1024) FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        support_mask_pool_kernel<14><<<M, 256, smem, st>>>(mask, boxes, S_h, S_w, out, cap);
+        if ((int)smem > attr14) { FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr14 = (int)smem; }
+        support_mask_pool_kernel<14><<<M, kMaskThreads, smem, st>>>(mask, boxes, S_h, S_w, out, cap, gcap);
     }
     FGN_LAUNCH_OK();
     return FGN_OK;

@@ -101,8 +101,10 @@ def make_episode(cfg: EpisodeConfig, seed: int = 0, relu: bool = False) -> Dict[
     rois = synth_rois(g, cfg.num_rois * cfg.batch, cfg.img_h, cfg.img_w, cfg.batch)
     det = synth_rois(g, cfg.mask_rois * cfg.batch, cfg.img_h, cfg.img_w, cfg.batch)
     det_labels = torch.randint(0, cfg.n_ways, (det.shape[0],), generator=g)
+    # the reference hands labels over as one tensor per image (fgn_roi_head.py:707-709)
+    det_labels_list = [det_labels[det[:, 0] == b] for b in range(cfg.batch)]
     return dict(cfg=cfg, qry=qry, spp=spp, spp_bboxes=spp_bboxes, spp_masks=spp_masks, rois=rois,
-                det_rois=det, det_labels=det_labels)
+                det_rois=det, det_labels=det_labels, det_labels_list=det_labels_list)
 
 
 def episode_to_device(ep: Dict[str, object], device, channels_last: bool = True, pin: bool = False):
@@ -113,7 +115,7 @@ def episode_to_device(ep: Dict[str, object], device, channels_last: bool = True,
             vs = []
             for t in v:
                 t = t.to(device, non_blocking=True)
-                if channels_last:
+                if channels_last and t.dim() == 4:
                     t = t.contiguous(memory_format=torch.channels_last)
                 vs.append(t)
             out[k] = vs
@@ -177,23 +179,60 @@ def run_guided_path(rpn, head, ep: Dict[str, object], with_attention: bool = Tru
     out = {}
     n_ext = len(cfg.strides)
     if with_attention:
-        mods = []
-        for q, s in zip(ep["qry"], ep["spp"]):
-            _, mod = rpn.attention(q, s)
-            mods.append(mod)
-        out["qry_fmap_mod"] = mods
+        _, out["qry_fmap_mod"] = rpn.attention_multilevel(ep["qry"], ep["spp"])
     ext_levels = ep["qry"][:n_ext] if cfg.mode == "fpn" else ep["qry"][0]
     spp_levels = ep["spp"][:n_ext] if cfg.mode == "fpn" else ep["spp"][0]
-    head.count_spp(spp_levels, ep["spp_bboxes"].clone() if not head.mutate_inputs else ep["spp_bboxes"].clone(),
-                   ep["spp_masks"])
+    head.count_spp(spp_levels, ep["spp_bboxes"].clone(), ep["spp_masks"])     # clone: count_spp divides in place
     res = head._bbox_forward(ext_levels, ep["rois"], need_feats=False)
     out["cls_score"], out["bbox_pred"] = res["cls_score"], res["bbox_pred"]
     if with_mask:
-        det = ep["det_rois"]
-        labels = [ep["det_labels"][det[:, 0] == b] for b in range(cfg.batch)]
-        head.gather_mask_vectors(labels)
-        out["mask_feats"] = head._mask_forward(ext_levels, det)["mask_feats"]
+        head.gather_mask_vectors(ep["det_labels_list"])
+        out["mask_feats"] = head._mask_forward(ext_levels, ep["det_rois"])["mask_feats"]
     return out
+
+
+class EpisodeRunner:
+    """Runs the hot path for a fixed set of device-resident episodes, optionally replaying one CUDA
+    graph per episode (the path is a fixed sequence of ~30 short kernels: launch-bound when eager)."""
+
+    def __init__(self, rpn, head, episodes: Sequence[Dict[str, object]], use_graphs: bool = True,
+                 with_attention: bool = True, with_mask: bool = True):
+        self.rpn, self.head, self.episodes = rpn, head, list(episodes)
+        self.kw = dict(with_attention=with_attention, with_mask=with_mask)
+        self.graphs, self.outs = [], []
+        self.launches_per_episode: List[int] = []          # libfgn_b200 kernels inside each captured graph
+        self.launches = 0                                  # libfgn_b200 kernels launched through run()
+        if use_graphs:
+            with torch.no_grad():
+                for ep in self.episodes:                   # warm-up: lazy inits must not happen under capture
+                    run_guided_path(rpn, head, ep, **self.kw)
+                torch.cuda.synchronize()
+                pool = None
+                for ep in self.episodes:
+                    g = torch.cuda.CUDAGraph()
+                    from . import ops
+                    l0 = ops.launch_count()
+                    with torch.cuda.graph(g, pool=pool):
+                        out = run_guided_path(rpn, head, ep, **self.kw)
+                    self.launches_per_episode.append(ops.launch_count() - l0)
+                    pool = g.pool()
+                    self.graphs.append(g)
+                    self.outs.append(out)
+
+    def run(self, i: int) -> Dict[str, object]:
+        if self.graphs:
+            self.graphs[i].replay()
+            self.launches += self.launches_per_episode[i]
+            return self.outs[i]
+        from . import ops
+        l0 = ops.launch_count()
+        with torch.no_grad():
+            out = run_guided_path(self.rpn, self.head, self.episodes[i], **self.kw)
+        self.launches += ops.launch_count() - l0
+        return out
+
+    def __len__(self):
+        return len(self.episodes)
 
 
 # ---- sharding across the GPUs of one box ----------------------------------------------------------

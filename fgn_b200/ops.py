@@ -19,7 +19,7 @@ from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, FgnError, Pyramid
 
 __all__ = [
     "map_roi_levels", "roi_align_multilevel", "roi_align_sample_indices", "to_nhwc", "support_mask_pool",
-    "support_pool", "attention_vectors", "channel_attention", "best_class_select",
+    "support_pool", "attention_vectors", "channel_attention", "attention_multilevel", "best_class_select",
     "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count",
 ]
 
@@ -288,6 +288,43 @@ def channel_attention(qry: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.load().fgn_channel_attention(q.data_ptr(), v.data_ptr(), b, n, c, h, w, lay, out.data_ptr(),
                                                  _stream()), "fgn_channel_attention")
     return out
+
+
+def attention_multilevel(qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor], n_ways: int,
+                         k_shots: int):
+    """AG-RPN attention for every level of a pyramid in three launches (channels_last inputs).
+    Returns (vecs: list of [B,N,C,1,1], mods: list of [B*N,C,H_l,W_l]).  Falls back to the per-level
+    entry points for other storage layouts."""
+    qs, ss = list(qry_feats), list(spp_feats)
+    _need_cuda(*qs, *ss)
+    c = qs[0].shape[1]
+    fast = c % 4 == 0 and c <= 1024 and all(storage_layout(t) == LAYOUT_NHWC and t.dtype == torch.float32 for t in qs + ss)
+    if not fast:
+        vecs = [attention_vectors(s, n_ways, k_shots) for s in ss]
+        return vecs, [channel_attention(q, v) for q, v in zip(qs, vecs)]
+    b = qs[0].shape[0]
+    bn = b * n_ways
+    L = len(qs)
+    spyr, qpyr = Pyramid(), Pyramid()
+    spyr.num_levels = qpyr.num_levels = L
+    outs = []
+    for i, (q, s) in enumerate(zip(qs, ss)):
+        if s.shape[0] != bn * k_shots or s.shape[1] != c or q.shape[1] != c or q.shape[0] != b:
+            raise FgnError("attention_multilevel: level shapes must be [B,C,H,W] / [B*N*K,C,h,w]")
+        spyr.feat[i], spyr.H[i], spyr.W[i] = s.data_ptr(), s.shape[2], s.shape[3]
+        qpyr.feat[i], qpyr.H[i], qpyr.W[i] = q.data_ptr(), q.shape[2], q.shape[3]
+        outs.append(_empty_like_format((bn, c, q.shape[2], q.shape[3]), q.device, LAYOUT_NHWC))
+    lib = _lib.load()
+    dev = qs[0].device
+    vec = torch.empty((L, bn, c), device=dev, dtype=torch.float32)
+    wsb = lib.fgn_attention_vectors_ml_workspace_bytes(ctypes.byref(spyr), bn, k_shots, c)
+    ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
+    _lib.check(lib.fgn_attention_vectors_ml(ctypes.byref(spyr), bn, int(k_shots), c, vec.data_ptr(), ws.data_ptr(), wsb,
+                                            _stream()), "fgn_attention_vectors_ml")
+    ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+    _lib.check(lib.fgn_channel_attention_ml(ctypes.byref(qpyr), vec.data_ptr(), b, n_ways, c, ptrs, _stream()),
+               "fgn_channel_attention_ml")
+    return [vec[i].view(b, n_ways, c, 1, 1) for i in range(L)], outs
 
 
 def best_class_select(cls: torch.Tensor, reg: torch.Tensor, batch: int, n_ways: int):

@@ -122,6 +122,16 @@ int fgn_attention_vectors(const float *spp_fmaps, int layout, int BN, int K, int
 int fgn_channel_attention(const float *qry, const float *vec, int B, int N, int C, int H, int W,
                           int layout, float *out, void *stream);
 
+/* The two calls above for a whole pyramid (FPN mode, SURVEY A.9: per level, the vector comes from
+ * the same level's support maps) in three launches.  NHWC storage only.
+ *   spp: level l = [B*N*K,h_l,w_l,C]; vec [L,B*N,C];  qry: level l = [B,H_l,W_l,C];
+ *   out_host: HOST array of L device pointers, level l = [B*N,H_l,W_l,C]. */
+size_t fgn_attention_vectors_ml_workspace_bytes(const fgn_pyramid_t *spp, int BN, int K, int C);
+int fgn_attention_vectors_ml(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec,
+                             void *workspace, size_t workspace_bytes, void *stream);
+int fgn_channel_attention_ml(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                             float *const *out_host, void *stream);
+
 /* AGRPNHead best-class selection (fgn_ag_rpn_head.py:87-108): per anchor position take the
  * score and the 4 deltas of the class with the largest score (first max wins).
  *   cls [B*N,A,H,W], reg [B*N,4A,H,W] (NCHW) -> cls_out [B,A,H,W], reg_out [B,4A,H,W]. */
