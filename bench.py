@@ -164,7 +164,7 @@ def cpu_model():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="fgn_b200", choices=["fgn_b200", "reference"])
     ap.add_argument("--episodes-per-step", type=int, default=16, help="distinct episodes per GPU per step")
@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying one CUDA graph per episode")
+    ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -226,15 +227,20 @@ def main():
     bytes_resident = sum(t.numel() * 4 for ep in dev_eps for t in ep["qry"] + ep["spp"])
     config["l2"] = f"no flush: episode stream of {E} x {bytes_resident / E / 1e6:.0f} MB distinct inputs > 126 MB L2"
 
-    runner = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs)
-    config["launch"] = "eager" if args.no_graphs else "one CUDA graph per resident episode"
+    runner = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, n_streams=args.streams)
+    config["launch"] = ("eager" if args.no_graphs else "one CUDA graph per resident episode") + \
+        f", episodes round-robin on {max(1, args.streams)} stream(s)"
     res_buf = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), device=device)
 
+    def sink(i, o):
+        res_buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
+        res_buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+
     def step_resident():
+        runner.begin()
         for i in range(E):
-            o = runner.run(i)
-            res_buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
-            res_buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+            runner.run(i, sink)
+        runner.end()
         res = res_buf                                         # [E, R, 5N+1]
         if world > 1:
             res = gather_results(res, E * world)
@@ -268,6 +274,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, launches, clocks
+
+    # the overlapped graph replay must reproduce the plain eager, single-stream results bit for bit
+    with torch.no_grad():
+        step_resident()
+        torch.cuda.synchronize()
+        for i in (0, E // 2, E - 1):
+            ref = run_guided_path(rpn, head, dev_eps[i])
+            torch.cuda.synchronize()
+            if not (torch.equal(res_buf[i, :, : cfg.n_ways + 1], ref["cls_score"]) and
+                    torch.equal(res_buf[i, :, cfg.n_ways + 1:], ref["bbox_pred"])):
+                raise SystemExit(f"bench.py: episode {i} differs between graph/multi-stream replay and eager execution")
 
     sampler = ClockSampler(local_rank)
     ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
@@ -317,7 +334,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / per_launch_s / 1e9
-    roofline = {"kernel": "roi_align_sep_nhwc_kernel<7> (multi-level RoIAlign, NHWC out)", "bound": "hbm",
+    roofline = {"kernel": "roi_align_stream_kernel<7,2,3,1> (level assignment + multi-level RoIAlign, NHWC in/out)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "traffic": None}

@@ -19,21 +19,24 @@
 //   warps 4-7   epilogue: tcgen05.ld 32x32b.x32, + bias, 128-bit global stores.
 #include "gemm.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace fgn {
 
 constexpr int TC_BM = 128;          // rows per tile (UMMA_M, cta_group::1)
-constexpr int TC_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_BN_MAX = 256;      // UMMA_N max
-constexpr int TC_STAGES = 2;
 constexpr int TC_THREADS = 384;
 
+// BK = fp32 elements per k-block = one swizzle row: 32 (128-byte swizzle, 2-stage ring) or
+// 16 (64-byte swizzle, 4-stage ring: same shared memory, twice the copies in flight).
+template <int BK>
 struct TcSmem {
+    static constexpr int kStages = BK == 32 ? 2 : 4;
     // per stage: A (hi, in place) | A_lo | B_hi | B_lo ; every tile 1024-byte aligned
-    static constexpr int kA = TC_BM * TC_BK * 4;            // 16 KB
-    static constexpr int kB = TC_BN_MAX * TC_BK * 4;        // 32 KB
-    static constexpr int kStage = 2 * kA + 2 * kB;          // 96 KB
-    static constexpr int kTotal = TC_STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kA = TC_BM * BK * 4;               // 16 / 8 KB
+    static constexpr int kB = TC_BN_MAX * BK * 4;           // 32 / 16 KB
+    static constexpr int kStage = 2 * kA + 2 * kB;          // 96 / 48 KB
+    static constexpr int kTotal = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,14 +71,16 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B)
 // | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+// ... for BK=16 the rows are 64 bytes: SBO = 8 rows x 64 B, layout_type = SWIZZLE_64B (4).
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -113,7 +118,7 @@ __global__ void split_tf32_kernel(const float *__restrict__ in, int rows, int co
     lo[i] = x - h;
 }
 
-template <int PASSES>
+template <int PASSES, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                     const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
@@ -121,7 +126,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TcSmem::kStage);
+    using Sm = TcSmem<BK>;
+    constexpr int TC_STAGES = Sm::kStages;
+    constexpr int TC_BK = BK;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * Sm::kStage);
     uint64_t *full_bar = bars, *conv_bar = bars + TC_STAGES, *empty_bar = bars + 2 * TC_STAGES;
     uint64_t *tmem_full = bars + 3 * TC_STAGES, *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
@@ -157,12 +165,12 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     tc_mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
-                    unsigned char *st = smem + (size_t)s * TcSmem::kStage;
+                    unsigned char *st = smem + (size_t)s * Sm::kStage;
                     const uint32_t bytes = TC_BM * TC_BK * 4 + (PASSES == 3 ? 2 : 1) * BN * TC_BK * 4;
                     tc_mbar_expect_tx(&full_bar[s], bytes);
                     tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);
-                    tma_load_2d(st + 2 * TcSmem::kA, &map_bhi, kb * TC_BK, n0, &full_bar[s]);
-                    if (PASSES == 3) tma_load_2d(st + 2 * TcSmem::kA + TcSmem::kB, &map_blo, kb * TC_BK, n0, &full_bar[s]);
+                    tma_load_2d(st + 2 * Sm::kA, &map_bhi, kb * TC_BK, n0, &full_bar[s]);
+                    if (PASSES == 3) tma_load_2d(st + 2 * Sm::kA + Sm::kB, &map_blo, kb * TC_BK, n0, &full_bar[s]);
                 }
             }
         }
@@ -184,10 +192,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (PASSES == 3) tc_mbar_wait(&conv_bar[s], par);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t st = s_u32(smem + (size_t)s * TcSmem::kStage);
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + TcSmem::kA);
-                    const uint64_t b_hi = umma_desc_sw128(st + 2 * TcSmem::kA);
-                    const uint64_t b_lo = umma_desc_sw128(st + 2 * TcSmem::kA + TcSmem::kB);
+                    const uint32_t st = s_u32(smem + (size_t)s * Sm::kStage);
+                    const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + Sm::kA);
+                    const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * Sm::kA);
+                    const uint64_t b_lo = umma_desc_kmajor<BK>(st + 2 * Sm::kA + Sm::kB);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);      // +32 B inside the swizzle row
@@ -213,10 +221,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     tc_mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
-                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * TcSmem::kStage);
-                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * TcSmem::kStage + TcSmem::kA);
+                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage);
+                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage + Sm::kA);
 #pragma unroll
-                    for (int j = 0; j < TcSmem::kA / 16 / 128; ++j) {         // 8 float4 per thread
+                    for (int j = 0; j < Sm::kA / 16 / 128; ++j) {         // 8 float4 per thread
                         const int i = j * 128 + tid;
                         const float4 x = hi[i];
                         float4 h;
@@ -298,17 +306,18 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
-// 2D fp32 row-major [rows, cols] with row pitch ld (floats); box = 32 cols x box_rows, 128B swizzle.
-static bool make_map(CUtensorMap *m, const float *base, int rows, int cols, int ld, int box_rows)
+// 2D fp32 row-major [rows, cols] with row pitch ld (floats); box = bk cols x box_rows, 128B/64B swizzle.
+static bool make_map(CUtensorMap *m, const float *base, int rows, int cols, int ld, int box_rows, int bk)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -320,18 +329,20 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
     *taken = false;
     if (M <= 0) return FGN_OK;
     // shapes the kernel takes: K in whole 128-byte k-blocks, N tiles of <=256 that are UMMA_N-legal
-    if ((K % TC_BK) != 0 || (N % 16) != 0 || (N > TC_BN_MAX && (N % TC_BN_MAX) != 0)) return FGN_OK;
+    if ((K % 32) != 0 || (N % 16) != 0 || (N > TC_BN_MAX && (N % TC_BN_MAX) != 0)) return FGN_OK;
     if ((lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15)) return FGN_OK;
     if (split_ws == nullptr) return FGN_OK;
     const int BN = N > TC_BN_MAX ? TC_BN_MAX : N;
     const int passes = precision == 0 ? 3 : 1;
+    const char *e = getenv("FGN_GEMM_BK");
+    const int bk = (e != nullptr && atoi(e) == 32) ? 32 : 16;
 
     float *bhi = split_ws, *blo = split_ws + (size_t)N * K;
     split_tf32_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(B, N, K, ldb, bhi, blo);
     FGN_LAUNCH_OK();
 
     CUtensorMap ma, mbh, mbl;
-    if (!make_map(&ma, A, M, K, lda, TC_BM) || !make_map(&mbh, bhi, N, K, K, BN) || !make_map(&mbl, blo, N, K, K, BN)) {
+    if (!make_map(&ma, A, M, K, lda, TC_BM, bk) || !make_map(&mbh, bhi, N, K, K, BN, bk) || !make_map(&mbl, blo, N, K, K, BN, bk)) {
         set_error("cuTensorMapEncodeTiled unavailable or failed");
         return FGN_ERR_CUDA;
     }
@@ -343,14 +354,21 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
     }
     const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
     const int grid = min(sm_count, m_tiles * n_tiles);
-    static bool attr3 = false, attr1 = false;
-    if (passes == 3) {
-        if (!attr3) { FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal)); attr3 = true; }
-        gemm_tf32_tc_kernel<3><<<grid, TC_THREADS, TcSmem::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN);
-    } else {
-        if (!attr1) { FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal)); attr1 = true; }
-        gemm_tf32_tc_kernel<1><<<grid, TC_THREADS, TcSmem::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN);
-    }
+    static bool attr_done[4] = {false, false, false, false};
+#define FGN_TC_LAUNCH(PS, BKV, IDX)                                                                                  \
+    do {                                                                                                           \
+        if (!attr_done[IDX]) {                                                                                     \
+            FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<PS, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             TcSmem<BKV>::kTotal));                                                \
+            attr_done[IDX] = true;                                                                                 \
+        }                                                                                                          \
+        gemm_tf32_tc_kernel<PS, BKV><<<grid, TC_THREADS, TcSmem<BKV>::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN); \
+    } while (0)
+    if (passes == 3 && bk == 32) FGN_TC_LAUNCH(3, 32, 0);
+    else if (passes == 3)        FGN_TC_LAUNCH(3, 16, 1);
+    else if (bk == 32)           FGN_TC_LAUNCH(1, 32, 2);
+    else                         FGN_TC_LAUNCH(1, 16, 3);
+#undef FGN_TC_LAUNCH
     FGN_LAUNCH_OK();
     *taken = true;
     return FGN_OK;

@@ -418,10 +418,11 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
     const Pyramid d = to_device_pyramid(pyr);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && env_int("FGN_RA_IMPL", 2) == 2) {
+    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && env_int("FGN_RA_IMPL", 2) >= 2) {
         bool taken = false;
         rc = launch_roi_align_stream(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
-                                     scale_index, out, out_layout, lvl_out, st, env_int("FGN_RA_VEC", 2),
+                                     scale_index, out, out_layout, lvl_out, st,
+                                     env_int("FGN_RA_IMPL", 2) == 2 ? -env_int("FGN_RA_VEC", 2) : env_int("FGN_RA_VEC", 2),
                                      env_int("FGN_RA_NS", 0), &taken);
         if (rc || taken) return rc;
     }

@@ -192,47 +192,83 @@ def run_guided_path(rpn, head, ep: Dict[str, object], with_attention: bool = Tru
 
 
 class EpisodeRunner:
-    """Runs the hot path for a fixed set of device-resident episodes, optionally replaying one CUDA
-    graph per episode (the path is a fixed sequence of ~30 short kernels: launch-bound when eager)."""
+    """Runs the hot path for a fixed set of device-resident episodes.
+
+    ``use_graphs``: replay one CUDA graph per episode (the path is a fixed sequence of ~25 short kernels:
+    launch-bound when eager).  ``n_streams`` > 1: episodes are independent, so consecutive episodes
+    are replayed round-robin on side streams and overlap on the GPU (the HBM-bound attention kernels of
+    one episode run beside the L2/tensor-bound RoIAlign + contraction of another).  Each stream owns
+    its graph memory pool; ``begin()``/``end()`` fork from / join back into the caller's stream.
+    """
 
     def __init__(self, rpn, head, episodes: Sequence[Dict[str, object]], use_graphs: bool = True,
-                 with_attention: bool = True, with_mask: bool = True):
+                 with_attention: bool = True, with_mask: bool = True, n_streams: int = 1):
+        from . import ops
         self.rpn, self.head, self.episodes = rpn, head, list(episodes)
         self.kw = dict(with_attention=with_attention, with_mask=with_mask)
         self.graphs, self.outs = [], []
         self.launches_per_episode: List[int] = []          # libfgn_b200 kernels inside each captured graph
         self.launches = 0                                  # libfgn_b200 kernels launched through run()
+        self.n_streams = max(1, int(n_streams))
+        self.streams = [torch.cuda.Stream() for _ in range(self.n_streams)] if self.n_streams > 1 else []
+        self._fork, self._joins = torch.cuda.Event(), [torch.cuda.Event() for _ in self.streams]
         if use_graphs:
             with torch.no_grad():
                 for ep in self.episodes:                   # warm-up: lazy inits must not happen under capture
                     run_guided_path(rpn, head, ep, **self.kw)
                 torch.cuda.synchronize()
-                pool = None
-                for ep in self.episodes:
+                pools = [None] * self.n_streams
+                for i, ep in enumerate(self.episodes):
                     g = torch.cuda.CUDAGraph()
-                    from . import ops
                     l0 = ops.launch_count()
-                    with torch.cuda.graph(g, pool=pool):
+                    with torch.cuda.graph(g, pool=pools[i % self.n_streams]):
                         out = run_guided_path(rpn, head, ep, **self.kw)
                     self.launches_per_episode.append(ops.launch_count() - l0)
-                    pool = g.pool()
+                    pools[i % self.n_streams] = g.pool()
                     self.graphs.append(g)
                     self.outs.append(out)
 
-    def run(self, i: int) -> Dict[str, object]:
-        if self.graphs:
-            self.graphs[i].replay()
-            self.launches += self.launches_per_episode[i]
-            return self.outs[i]
+    def begin(self) -> None:
+        """Side streams wait for everything already queued on the caller's stream."""
+        if self.streams:
+            self._fork.record()
+            for st in self.streams:
+                st.wait_event(self._fork)
+
+    def end(self) -> None:
+        """The caller's stream waits for the side streams."""
+        for st, ev in zip(self.streams, self._joins):
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
+
+    def run(self, i: int, sink=None) -> Dict[str, object]:
+        """Episode i; ``sink(i, out)`` (optional) is called on the stream the episode ran on."""
         from . import ops
-        l0 = ops.launch_count()
-        with torch.no_grad():
-            out = run_guided_path(self.rpn, self.head, self.episodes[i], **self.kw)
-        self.launches += ops.launch_count() - l0
+        ctx = torch.cuda.stream(self.streams[i % self.n_streams]) if self.streams else _NullCtx()
+        with ctx:
+            if self.graphs:
+                self.graphs[i].replay()
+                self.launches += self.launches_per_episode[i]
+                out = self.outs[i]
+            else:
+                l0 = ops.launch_count()
+                with torch.no_grad():
+                    out = run_guided_path(self.rpn, self.head, self.episodes[i], **self.kw)
+                self.launches += ops.launch_count() - l0
+            if sink is not None:
+                sink(i, out)
         return out
 
     def __len__(self):
         return len(self.episodes)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 # ---- sharding across the GPUs of one box ----------------------------------------------------------
