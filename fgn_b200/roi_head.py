@@ -169,6 +169,8 @@ class FGNRoIHead(nn.Module):
         m = spp_bboxes.shape[0]
         mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429
         idx = torch.arange(m, device=spp_bboxes.device, dtype=torch.float32).view(m, 1)
+        # without a shared_head the class maps feed the relation GEMM directly: keep them channels_last
+        fmt = "nchw" if self.with_shared_head else "nhwc"
         if len(levels) == 1:
             if self.mutate_inputs:
                 spp_bboxes /= self.subsampling_ratio                                             # :430
@@ -176,12 +178,12 @@ class FGNRoIHead(nn.Module):
             else:
                 boxes = spp_bboxes / self.subsampling_ratio
             rois = torch.cat([idx, boxes.reshape(m, 4).float()], 1)
-            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False)       # :432
+            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False, out_format=fmt)  # :432
         else:   # A-FPN: level from map_roi_levels on the pixel box, spatial_scale = 1/stride
             rois = torch.cat([idx, spp_bboxes.reshape(m, 4).float()], 1)
             ext = self.bbox_roi_extractor
             feat_ra = ops.roi_align_multilevel(levels, rois, [1.0 / s for s in ext.featmap_strides[: len(levels)]],
-                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale))
+                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale), out_format=fmt)
         if self.with_shared_head:
             feat_ra = self.shared_head_layer(feat_ra)                                            # :435-436
         cat_mean, mp = ops.support_pool(feat_ra, mask_ra, self.n_ways, self.k_shots)             # :439-447
