@@ -17,6 +17,7 @@
 // re-reads that adjacent bins share (about 1.5x in the bin-centric kernel) are served from
 // shared memory.  full/empty mbarriers form the usual producer/consumer pipeline.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fgn {
 
@@ -129,7 +130,7 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
                         float *__restrict__ out, const int out_layout, int32_t *__restrict__ lvl_out,
-                        const int wx_cap, const int wyd_rows)
+                        const int wx_cap, const int wyd_rows, const int size_classes)
 {
     constexpr int CB  = 128 * VEC * WS;
     constexpr int NCW = P * WS;                     // consumer warps
@@ -144,20 +145,37 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
     float *wyd  = wx + wx_cap;
     float *stage_out = wyd + (size_t)wyd_rows * PP8;                         // NCHW staging (optional)
 
-    const int nblk = (C + CB - 1) / CB;
-    const int r    = blockIdx.x / nblk;
-    const int cb0  = (blockIdx.x % nblk) * CB;
-    const int t    = threadIdx.x;
-    const int warp = t >> 5, lane = t & 31;
-    const int cbn  = min(CB, C - cb0);                    // channels actually present in this block
+    // Largest-first scheduling without a sort: the grid is `size_classes` copies of the work list;
+    // copy k only keeps the RoIs of size class k (0 = largest footprints) and the rest of its CTAs
+    // retire at once, so the hardware's in-order CTA dispatch starts the long RoIs first and the
+    // short ones fill the tail.
+    const int nblk  = (C + CB - 1) / CB;
+    const int items = R * nblk;
+    const int cls   = blockIdx.x / items, item = blockIdx.x - cls * items;
+    const int r     = item / nblk;
+    const int cb0   = (item % nblk) * CB;
+    const int t     = threadIdx.x;
+    const int warp  = t >> 5, lane = t & 31;
+    const int cbn   = min(CB, C - cb0);                   // channels actually present in this block
     const bool contiguous = (cbn == C);                   // whole cells are adjacent in memory
     const int cstride = contiguous ? C : CB;              // floats between consecutive staged cells
+    __shared__ int my_class;
 
     if (t == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int c = 0;
+        if (size_classes > 1) {
+            const float *roi = rois + 5 * (size_t)r;
+            const float sc = pyr.scale[roi_level(roi, pyr, finest_scale)];
+            const float cells = (roi[3] - roi[1]) * sc * (roi[4] - roi[2]) * sc;     // scheduling hint only
+            c = cells >= 384.f ? 0 : (cells >= 96.f ? 1 : 2);
+            c = min(c, size_classes - 1);
+        }
+        my_class = c;
     }
     __syncthreads();                                      // reached at once by every warp
+    if (my_class != cls) return;
 
     if (warp == NCW) {
         // ===== producer: own copy of the plan, then bulk async copies of footprint rows ==========
@@ -700,9 +718,12 @@ static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, 
         attr_set = (int)smem;
     }
     const int nblk = (C + CB - 1) / CB;
-    kern<<<R * nblk, (P * WS + 1) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
-                                                chan_scale, scale_index, out, out_layout, lvl_out,
-                                                wx_cap, wyd_rows);
+    // largest-first needs enough RoIs to matter; a handful of RoIs run as one class
+    const char *e = getenv("FGN_RA_CLASSES");
+    const int size_classes = e != nullptr ? max(1, min(3, atoi(e))) : (R >= 256 ? 3 : 1);
+    kern<<<R * nblk * size_classes, (P * WS + 1) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
+                                                                    chan_scale, scale_index, out, out_layout, lvl_out,
+                                                                    wx_cap, wyd_rows, size_classes);
     FGN_LAUNCH_OK();
     *taken = true;
     return FGN_OK;

@@ -149,6 +149,34 @@ def test_roi_align_multilevel_vs_oracle(C, P):
     assert torch.equal(got3, got)                                                # NCHW input (repacked) too
 
 
+@pytest.mark.parametrize("env", [{"FGN_RA_IMPL": "3"}, {"FGN_RA_IMPL": "1"}, {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "1"},
+                                 {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "3"}, {"FGN_RA_IMPL": "2", "FGN_RA_CLASSES": "1"}],
+                         ids=["persistent", "bin-centric", "cb128", "sliced", "one-class"])
+def test_roi_align_kernel_variants_agree(env, monkeypatch):
+    """Every RoIAlign kernel variant the library can dispatch to (selected through its tuning
+    environment knobs) reproduces the oracle and, among the streaming variants, each other bitwise."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(77)
+    strides, B, C = [4, 8, 16, 32], 2, 256
+    feats = [torch.randn(B, C, 256 // s, 320 // s, generator=g) for s in strides]
+    rois = synth_rois(g, 400, 256, 320, B, smin=4.0)
+    rois[0, 1:] = torch.tensor([-30., -30., 400., 300.])            # wider than 32 cells on level 3: segmented rows
+    rois[1, 1:] = torch.tensor([0., 100., 320., 104.])              # 80 cells wide, 1 cell tall on level 0
+    want, lv = O.single_roi_extractor(feats, rois, strides, 7, 0, True, 56.0, "tv")
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    scales = [1 / s for s in strides]
+    base = ops.roi_align_multilevel(fd, rois.to(dev()), scales, 7, 0, True, out_format="nhwc")
+    close(base, want, what="default")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, lvl = ops.roi_align_multilevel(fd, rois.to(dev()), scales, 7, 0, True, out_format="nhwc", return_levels=True)
+    assert torch.equal(lvl.cpu(), lv)
+    close(got, want, what=str(env))
+    if env.get("FGN_RA_IMPL") != "1":
+        assert torch.equal(got, base), "streaming variants share one summation order"
+
+
 def test_roi_align_edge_cases():
     from fgn_b200 import ops
     f = torch.randn(1, 8, 12, 12, device=dev()).contiguous(memory_format=torch.channels_last)
@@ -385,6 +413,63 @@ def test_relation_contraction_tcgen05_vs_fp64(M, N, K):
         fast = ops.gemm_nt(a.to(dev()), wd[:, :K], bias.to(dev()), "tf32")
         err = (fast.cpu() - (a.double() @ w[:, :K].double().t() + bias.double()).float()).abs().max()
         assert 1e-6 < float(err) < 2e-2, float(err)        # single-pass TF32: visibly lower precision
+
+
+def test_c4_full_size_cfg2_subset_vs_oracle():
+    """cfg2 (OMNIISEG N3K1, C4 1024 channels, 32x32 map) at full tensor sizes; the oracle is run on a
+    60-RoI subset so the CPU side stays within seconds."""
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode, make_weights
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    ep = make_episode(cfg, seed=5)
+    rpn, head = build_heads(cfg, dev(), seed=0, shared_head=None)
+    epd = episode_to_device(ep, dev())
+    with torch.no_grad():
+        head.count_spp(epd["spp"][0], epd["spp_bboxes"].clone(), epd["spp_masks"])
+        res = head._bbox_forward(epd["qry"][0], epd["rois"], need_feats=True)
+    w = make_weights(cfg.channels, 0)
+    cat_mean, mp, _, _ = O.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"], cfg.n_ways, cfg.k_shots, 16)
+    close(head.spp_fmaps_roi_aligned_cat_mean, cat_mean, what="cat_mean")
+    close(head.spp_fvecs_roi_aligned_cat_mean_mp, mp, what="masked_gap")
+    sub = ep["rois"][::5]
+    want = O.bbox_forward([ep["qry"][0]], cfg.strides, sub, cat_mean, cfg.n_ways, w)
+    close(res["bbox_feats"][::5], want["bbox_feats"], what="bbox_feats")
+    close(res["cls_score"][::5], want["cls_score"], what="cls_score")
+    close(res["bbox_pred"][::5], want["bbox_pred"], what="bbox_pred")
+
+
+def test_support_pool_layouts_agree():
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(91)
+    N, K, C = 4, 3, 96
+    f = torch.randn(2 * N * K, C, 7, 7, generator=g)
+    m = torch.rand(2 * N * K, 1, 7, 7, generator=g)
+    want_cat = f.view(2, N, K, C, 7, 7).mean(2)
+    want_gap = (f * m).view(2, N, K, C, 7, 7).mean((2, 4, 5)).view(2, N, C, 1, 1)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        for out_fmt in ("nchw", "nhwc"):
+            cat, gap = ops.support_pool(f.to(dev()).contiguous(memory_format=fmt), m.to(dev()), N, K, out_format=out_fmt)
+            close(cat, want_cat, what=f"cat {fmt} {out_fmt}")
+            close(gap, want_gap, what=f"gap {fmt} {out_fmt}")
+            assert cat.shape == (2, N, C, 7, 7) and gap.shape == (2, N, C, 1, 1)
+
+
+def test_attention_layouts_and_multilevel_agree():
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(92)
+    B, N, K, C = 2, 3, 2, 64
+    qs = [torch.randn(B, C, h, w, generator=g) for h, w in ((24, 36), (12, 18), (6, 9), (3, 5))]
+    ss = [torch.randn(B * N * K, C, h, h, generator=g) for h in (16, 8, 4, 2)]
+    want = [O.agrpn_attention(q, s, N, K) for q, s in zip(qs, ss)]
+    cl = lambda t: t.to(dev()).contiguous(memory_format=torch.channels_last)
+    vecs, mods = ops.attention_multilevel([cl(q) for q in qs], [cl(s) for s in ss], N, K)
+    for l in range(4):
+        close(vecs[l], want[l][0], what=f"vec ml {l}")
+        close(mods[l], want[l][1], what=f"mod ml {l}")
+        v = ops.attention_vectors(ss[l].to(dev()), N, K)                     # NCHW single-level path
+        close(v, want[l][0], what=f"vec nchw {l}")
+        close(ops.channel_attention(qs[l].to(dev()), v), want[l][1], what=f"mod nchw {l}")
+        v2 = ops.attention_vectors(cl(ss[l]), N, K)                          # NHWC single-level path
+        close(ops.channel_attention(cl(qs[l]), v2), want[l][1], what=f"mod nhwc {l}")
 
 
 def test_empty_proposals():
