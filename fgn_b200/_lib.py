@@ -64,7 +64,16 @@ SIGNATURES = {
                                         _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "fgn_gemm_nt_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fgn_cls_bbox_reassemble": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "fgn_attention_vectors_ml_bf16": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "fgn_channel_attention_ml_bf16": (c_int, [POINTER(Pyramid), _P, c_int, c_int, c_int, POINTER(c_void_p), _P]),
+    "fgn_roi_align_ml_fwd_bf16": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
+                                          _P, _P, _P, c_int, _P, _P]),
+    "fgn_guided_roi_fused_bf16_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "fgn_guided_roi_fused_fwd_bf16": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
+                                              _P, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
+                                              _P, _P, _P, _P, c_size_t, _P]),
     "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_guided_roi_fused_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
                                          _P, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,

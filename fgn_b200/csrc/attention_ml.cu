@@ -99,6 +99,90 @@ channel_attention_ml_kernel(const MlLevels lv, const float *__restrict__ vec, co
     }
 }
 
+// ---- bf16 variants: 8 channels per 128-bit access, fp32 accumulation / multiply ----------------
+__device__ __forceinline__ void unpack8(const uint4 &q, float (&f)[8])
+{
+    f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
+    f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+    f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xffff0000u);
+    f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+__device__ __forceinline__ unsigned pack2(float a, float b)       // round to nearest even
+{
+    unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    ua += 0x7fffu + ((ua >> 16) & 1u);
+    ub += 0x7fffu + ((ub >> 16) & 1u);
+    return (ua >> 16) | (ub & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(256)
+attention_vec_ml_partial_bf16_kernel(const MlLevels lv, const int BN, const int K, const int C,
+                                     float *__restrict__ partial)
+{
+    const int bn = blockIdx.y;
+    const int l = ml_level_of(lv, blockIdx.x), slab = blockIdx.x - lv.blk_off[l];
+    const int c8 = C >> 3;
+    const int total = K * lv.HW[l];
+    const int p0 = slab * kMlSlab, p1 = min(total, p0 + kMlSlab);
+    extern __shared__ __align__(16) float red[];   // [rows][C]
+    const int rows = max(1, (int)blockDim.x / c8);
+    const unsigned short *base = reinterpret_cast<const unsigned short *>(lv.in[l]) + (size_t)bn * total * C;
+    const int cv = threadIdx.x % c8, rowi = threadIdx.x / c8;
+    if (rowi < rows) {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int p = p0 + rowi; p < p1; p += rows) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(base + (size_t)p * C + cv * 8)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(size_t)rowi * C + cv * 8 + j] = a[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += red[(size_t)rr * C + c];
+        partial[((size_t)blockIdx.x * BN + bn) * C + c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+channel_attention_ml_bf16_kernel(const MlLevels lv, const float *__restrict__ vec, const int B, const int N, const int C)
+{
+    const int l = ml_level_of(lv, blockIdx.x), blk = blockIdx.x - lv.blk_off[l];
+    const int c8 = C >> 3;
+    const size_t per_img = (size_t)lv.HW[l] * c8, total = (size_t)B * per_img;
+    const uint4 *q = reinterpret_cast<const uint4 *>(lv.in[l]);
+    uint4 *o = reinterpret_cast<uint4 *>(lv.out[l]);
+    const float *v = vec + (size_t)l * B * N * C;
+    const size_t i0 = (size_t)blk * (256 * kMlChunk) + threadIdx.x;
+    uint4 x[kMlChunk];
+#pragma unroll
+    for (int j = 0; j < kMlChunk; ++j) {
+        const size_t i = i0 + (size_t)j * 256;
+        x[j] = i < total ? __ldg(q + i) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kMlChunk; ++j) {
+        const size_t i = i0 + (size_t)j * 256;
+        if (i >= total) continue;
+        const int b = i / per_img;
+        const size_t rem = i - (size_t)b * per_img;
+        const int cv = rem % c8;
+        float f[8];
+        unpack8(x[j], f);
+        for (int n = 0; n < N; ++n) {
+            const float *s = v + ((size_t)b * N + n) * C + cv * 8;
+            const float4 s0 = ldg4(s), s1 = ldg4(s + 4);
+            uint4 r;
+            r.x = pack2(f[0] * s0.x, f[1] * s0.y); r.y = pack2(f[2] * s0.z, f[3] * s0.w);
+            r.z = pack2(f[4] * s1.x, f[5] * s1.y); r.w = pack2(f[6] * s1.z, f[7] * s1.w);
+            __stcs(o + ((size_t)b * N + n) * per_img + rem, r);
+        }
+    }
+}
+
 static int fill_levels(const fgn_pyramid_t *p, MlLevels &lv)
 {
     FGN_CHECK_ARG(p != nullptr && p->num_levels >= 1 && p->num_levels <= FGN_MAX_LEVELS, "bad pyramid");
@@ -125,12 +209,27 @@ extern "C" size_t fgn_attention_vectors_ml_workspace_bytes(const fgn_pyramid_t *
     return blocks * BN * C * sizeof(float);
 }
 
+static int attention_vectors_ml_impl(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec, void *workspace,
+                                     size_t workspace_bytes, void *stream, bool bf16);
+
 extern "C" int fgn_attention_vectors_ml(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec,
                                         void *workspace, size_t workspace_bytes, void *stream)
 {
+    return attention_vectors_ml_impl(spp, BN, K, C, vec, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int fgn_attention_vectors_ml_bf16(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec,
+                                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    return attention_vectors_ml_impl(spp, BN, K, C, vec, workspace, workspace_bytes, stream, true);
+}
+
+static int attention_vectors_ml_impl(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec, void *workspace,
+                                     size_t workspace_bytes, void *stream, bool bf16)
+{
     FGN_CHECK_ARG(BN >= 0 && K > 0 && C > 0, "bad dims");
     if (BN == 0) return FGN_OK;
-    if ((C & 3) || C > 1024) { set_error("attention_vectors_ml needs C%%4==0 and C<=1024 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
+    if ((C & (bf16 ? 7 : 3)) || C > 1024) { set_error("attention_vectors_ml needs C%%4==0 (bf16: C%%8==0) and C<=1024 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
     MlLevels lv;
     int rc = fill_levels(spp, lv);
     if (rc) return rc;
@@ -145,21 +244,38 @@ extern "C" int fgn_attention_vectors_ml(const fgn_pyramid_t *spp, int BN, int K,
     }
     FGN_CHECK_ARG(BN <= 65535, "BN too large");
     cudaStream_t st = (cudaStream_t)stream;
-    const int c4 = C >> 2, rows = max(1, 256 / c4);
-    attention_vec_ml_partial_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
-        lv, BN, K, C, (float *)workspace);
+    const int cvec = bf16 ? C >> 3 : C >> 2, rows = max(1, 256 / cvec);
+    if (bf16) attention_vec_ml_partial_bf16_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
+                  lv, BN, K, C, (float *)workspace);
+    else      attention_vec_ml_partial_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
+                  lv, BN, K, C, (float *)workspace);
     FGN_LAUNCH_OK();
     attention_vec_ml_finalize_kernel<<<ceil_div(lv.L * BN * C, 256), 256, 0, st>>>(lv, BN, K, C, (const float *)workspace, vec);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }
 
+static int channel_attention_ml_impl(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                                     float *const *out_host, void *stream, bool bf16);
+
 extern "C" int fgn_channel_attention_ml(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
                                         float *const *out_host, void *stream)
 {
+    return channel_attention_ml_impl(qry, vec, B, N, C, out_host, stream, false);
+}
+
+extern "C" int fgn_channel_attention_ml_bf16(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                                             void *const *out_host, void *stream)
+{
+    return channel_attention_ml_impl(qry, vec, B, N, C, (float *const *)out_host, stream, true);
+}
+
+static int channel_attention_ml_impl(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                                     float *const *out_host, void *stream, bool bf16)
+{
     FGN_CHECK_ARG(B >= 0 && N > 0 && C > 0, "bad dims");
     if (B == 0) return FGN_OK;
-    if (C & 3) { set_error("channel_attention_ml needs C%%4==0 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
+    if (C & (bf16 ? 7 : 3)) { set_error("channel_attention_ml needs C%%4==0 (bf16: C%%8==0) (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
     MlLevels lv;
     int rc = fill_levels(qry, lv);
     if (rc) return rc;
@@ -168,11 +284,12 @@ extern "C" int fgn_channel_attention_ml(const fgn_pyramid_t *qry, const float *v
     for (int l = 0; l < lv.L; ++l) {
         FGN_CHECK_ARG(out_host[l] != nullptr, "output level %d is NULL", l);
         lv.out[l] = out_host[l];
-        const size_t elems = (size_t)B * lv.HW[l] * (C >> 2);
+        const size_t elems = (size_t)B * lv.HW[l] * (bf16 ? C >> 3 : C >> 2);
         lv.blk_off[l + 1] = lv.blk_off[l] + (int)((elems + 256 * kMlChunk - 1) / (256 * kMlChunk));
     }
     for (int l = lv.L + 1; l <= FGN_MAX_LEVELS; ++l) lv.blk_off[l] = lv.blk_off[lv.L];
-    channel_attention_ml_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    if (bf16) channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    else      channel_attention_ml_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

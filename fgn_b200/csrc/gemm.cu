@@ -7,6 +7,9 @@ namespace fgn {
 int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
                int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken);
 
+int gemm_nt_tc_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C, int ldc,
+                    int M, int N, int K, cudaStream_t st);
+
 int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
             int M, int N, int K, int precision, float *split_ws, cudaStream_t st)
 {
@@ -42,4 +45,13 @@ extern "C" int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, con
     FGN_CHECK_ARG(A && B && C, "NULL pointer");
     float *ws = workspace_bytes >= gemm_tc_workspace_bytes(N, K) ? (float *)workspace : nullptr;
     return gemm_nt(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, ws, (cudaStream_t)stream);
+}
+
+extern "C" int fgn_gemm_nt_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C,
+                                int ldc, int M, int N, int K, void *stream)
+{
+    FGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm dims M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return FGN_OK;
+    FGN_CHECK_ARG(A && B && C, "NULL pointer");
+    return gemm_nt_tc_bf16(A, lda, B, ldb, bias, C, ldc, M, N, K, (cudaStream_t)stream);
 }

@@ -89,6 +89,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
@@ -118,7 +124,9 @@ __global__ void split_tf32_kernel(const float *__restrict__ in, int rows, int co
     lo[i] = x - h;
 }
 
-template <int PASSES, int BK>
+// BF16 = true: operands are bf16 (kind::f16, K=16 per instruction, single pass); the byte geometry of
+// the ring (row bytes = 4*BK) is unchanged, a k-block then holds 2*BK elements.
+template <int PASSES, int BK, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                     const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
@@ -136,7 +144,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = (N + BN - 1) / BN;
-    const int num_tiles = m_tiles * n_tiles, num_kb = K / TC_BK;
+    constexpr int KE = BF16 ? 2 * BK : BK;                  // elements per k-block
+    const int num_tiles = m_tiles * n_tiles, num_kb = K / KE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -168,9 +177,9 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     unsigned char *st = smem + (size_t)s * Sm::kStage;
                     const uint32_t bytes = TC_BM * TC_BK * 4 + (PASSES == 3 ? 2 : 1) * BN * TC_BK * 4;
                     tc_mbar_expect_tx(&full_bar[s], bytes);
-                    tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);
-                    tma_load_2d(st + 2 * Sm::kA, &map_bhi, kb * TC_BK, n0, &full_bar[s]);
-                    if (PASSES == 3) tma_load_2d(st + 2 * Sm::kA + Sm::kB, &map_blo, kb * TC_BK, n0, &full_bar[s]);
+                    tma_load_2d(st, &map_a, kb * KE, m0, &full_bar[s]);
+                    tma_load_2d(st + 2 * Sm::kA, &map_bhi, kb * KE, n0, &full_bar[s]);
+                    if (PASSES == 3) tma_load_2d(st + 2 * Sm::kA + Sm::kB, &map_blo, kb * KE, n0, &full_bar[s]);
                 }
             }
         }
@@ -178,7 +187,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== MMA issuer ========================================================================
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
         // B=TF32 [10,13)=2, K-major A/B, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t fmt = BF16 ? 1u : 2u;          // F16F32Format: BF16 = 1, TF32 = 2
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         int it = 0, local_tile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
             const int a = local_tile & 1;
@@ -200,7 +210,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);      // +32 B inside the swizzle row
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, acc);
+                        if (BF16) umma_bf16(tmem_d, a_hi + ko, b_hi + ko, idesc, acc);
+                        else      umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, acc);
                         if (PASSES == 3) {
                             umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
                             umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
@@ -307,15 +318,15 @@ static EncodeTiledFn get_encode()
 }
 
 // 2D fp32 row-major [rows, cols] with row pitch ld (floats); box = bk cols x box_rows, 128B/64B swizzle.
-static bool make_map(CUtensorMap *m, const float *base, int rows, int cols, int ld, int box_rows, int bk)
+static bool make_map(CUtensorMap *m, const void *base, int rows, int cols, int ld, int box_rows, int bk, bool bf16 = false)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * bk : bk), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+    return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -371,6 +382,42 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
 #undef FGN_TC_LAUNCH
     FGN_LAUNCH_OK();
     *taken = true;
+    return FGN_OK;
+}
+
+// bf16 operands (A [M,K], B [N,K], both K-major bf16), fp32 accumulate and output.  The bf16 variant
+// of the relation contraction: one pass at the bf16 tensor rate, a quarter of the 3xTF32 operand bytes.
+int gemm_nt_tc_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C, int ldc,
+                    int M, int N, int K, cudaStream_t st)
+{
+    FGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm dims M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return FGN_OK;
+    if ((K % 64) != 0 || (N % 16) != 0 || (N > TC_BN_MAX && (N % TC_BN_MAX) != 0) || (lda & 7) || (ldb & 7) || (ldc & 3) ||
+        ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15)) {
+        set_error("bf16 contraction needs K%%64==0, N%%16==0 (N<=256 or N%%256==0) and 16-byte aligned rows (M=%d N=%d K=%d)", M, N, K);
+        return FGN_ERR_UNSUPPORTED;
+    }
+    const int BN = N > TC_BN_MAX ? TC_BN_MAX : N;
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, A, M, K, lda, TC_BM, 32, true) || !make_map(&mb, B, N, K, ldb, BN, 32, true)) {
+        set_error("cuTensorMapEncodeTiled unavailable or failed");
+        return FGN_ERR_CUDA;
+    }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        FGN_CUDA_OK(cudaGetDevice(&dev));
+        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
+    const int grid = min(sm_count, m_tiles * n_tiles);
+    static bool attr = false;
+    if (!attr) {
+        FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<1, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::kTotal));
+        attr = true;
+    }
+    gemm_tf32_tc_kernel<1, 32, true><<<grid, TC_THREADS, TcSmem<32>::kTotal, st>>>(ma, mb, mb, bias, C, ldc, M, N, K, BN);
+    FGN_LAUNCH_OK();
     return FGN_OK;
 }
 

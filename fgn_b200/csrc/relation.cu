@@ -163,6 +163,12 @@ __global__ void cls_bbox_reassemble_kernel(const float *__restrict__ raw_cls, co
     cls_out[(size_t)r * (N + 1) + N] = best_bg;
 }
 
+__global__ void roi_batch_kernel(const float *__restrict__ rois, int R, int32_t *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) out[r] = (int)rois[5 * (size_t)r];
+}
+
 struct RelationWs {
     float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc, *split_q, *split_s;
     size_t bytes;
@@ -276,6 +282,100 @@ extern "C" int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_re
     return FGN_OK;
 }
 
+// fp32 [rows, cols] (row pitch ld) -> dense bf16 [rows, cols], round to nearest even
+__global__ void f32_to_bf16_kernel(const float *__restrict__ in, int rows, int cols, int ld, uint16_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const float x = in[(size_t)(i / cols) * ld + (i % cols)];
+    unsigned u = __float_as_uint(x);
+    if ((u & 0x7fffffffu) > 0x7f800000u) { out[i] = (uint16_t)((u >> 16) | 0x40u); return; }   // NaN stays NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    out[i] = (uint16_t)(u >> 16);
+}
+
+extern "C" int fgn_roi_align_ml_fwd_bf16(const fgn_pyramid_t *, int, int, const float *, int, int, int, int, float,
+                                         const float *, const int32_t *, void *, int, int32_t *, void *);
+extern "C" int fgn_gemm_nt_bf16(const uint16_t *, int, const uint16_t *, int, const float *, float *, int, int, int, int, void *);
+
+extern "C" size_t fgn_guided_roi_fused_bf16_workspace_bytes(int R, int BN, int C, int P)
+{
+    if (R < 0 || BN <= 0 || C <= 0 || P <= 0) return 0;
+    const size_t PP = (size_t)P * P;
+    return align256((size_t)R * PP * C * 2) + align256((size_t)R * 4) + align256((size_t)BN * PP * C * 2) +
+           2 * align256((size_t)C * C * 2) + align256((size_t)R * PP * C * 4) + align256((size_t)BN * PP * C * 4) +
+           align256((size_t)R * BN * 6 * ceil_div(C, 32) * 4);
+}
+
+// bf16 variant of fgn_guided_roi_fused_fwd: bf16 NHWC pyramid -> bf16 RoI features -> bf16 tcgen05
+// contraction (fp32 accumulate) -> the fp32 GroupNorm/ReLU/pool/FC epilogue.  Weights and the class
+// maps arrive in fp32 and are rounded to bf16 here.
+extern "C" int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
+                                             int P, int sampling_ratio, int aligned, float finest_scale,
+                                             const float *spp_cat_mean /* [B*N,P,P,C] NHWC fp32 */, int N,
+                                             const float *conv_w, const float *conv_b, const float *gn_w,
+                                             const float *gn_b, int gn_groups, float gn_eps,
+                                             const float *fc_cls_w, const float *fc_cls_b,
+                                             const float *fc_reg_w, const float *fc_reg_b, float *cls_out,
+                                             float *reg_out, int32_t *lvl_out, void *workspace,
+                                             size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(R >= 0 && B > 0 && N > 0 && C > 0 && P > 0, "bad dims");
+    FGN_CHECK_ARG(gn_groups > 0 && C % gn_groups == 0, "GroupNorm groups=%d does not divide C=%d", gn_groups, C);
+    if (R == 0) return FGN_OK;
+    if (P * P != kMaxPP) { set_error("guided_roi_fused_bf16: P=%d not instantiated (7)", P); return FGN_ERR_UNSUPPORTED; }
+    const int BN = B * N, PP = P * P;
+    const size_t need = fgn_guided_roi_fused_bf16_workspace_bytes(R, BN, C, P);
+    if (!workspace || workspace_bytes < need) {
+        set_error("guided_roi_fused_bf16: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    uint16_t *feat = (uint16_t *)ws;  ws += align256((size_t)R * PP * C * 2);
+    int32_t *rb = (int32_t *)ws;      ws += align256((size_t)R * 4);
+    uint16_t *spp16 = (uint16_t *)ws; ws += align256((size_t)BN * PP * C * 2);
+    uint16_t *wq16 = (uint16_t *)ws;  ws += align256((size_t)C * C * 2);
+    uint16_t *ws16 = (uint16_t *)ws;  ws += align256((size_t)C * C * 2);
+    float *yq = (float *)ws;          ws += align256((size_t)R * PP * C * 4);
+    float *ys = (float *)ws;          ws += align256((size_t)BN * PP * C * 4);
+    float *partial = (float *)ws;
+
+    int rc = fgn_roi_align_ml_fwd_bf16(pyr, B, C, rois, R, P, sampling_ratio, aligned, finest_scale, nullptr, nullptr,
+                                       feat, 1, lvl_out, stream);
+    if (rc) return rc;
+    roi_batch_kernel<<<ceil_div(R, 128), 128, 0, st>>>(rois, R, rb);
+    FGN_LAUNCH_OK();
+    f32_to_bf16_kernel<<<ceil_div(C * C, 256), 256, 0, st>>>(conv_w, C, C, 2 * C, wq16);
+    FGN_LAUNCH_OK();
+    f32_to_bf16_kernel<<<ceil_div(C * C, 256), 256, 0, st>>>(conv_w + C, C, C, 2 * C, ws16);
+    FGN_LAUNCH_OK();
+    f32_to_bf16_kernel<<<ceil_div(BN * PP * C, 256), 256, 0, st>>>(spp_cat_mean, BN * PP, C, C, spp16);
+    FGN_LAUNCH_OK();
+    rc = fgn_gemm_nt_bf16(feat, C, wq16, C, nullptr, yq, C, R * PP, C, C, stream);
+    if (rc) return rc;
+    rc = fgn_gemm_nt_bf16(spp16, C, ws16, C, conv_b, ys, C, BN * PP, C, C, stream);
+    if (rc) return rc;
+    const int cg = C / gn_groups;
+    FGN_CHECK_ARG(cg <= kEpiThreads, "channels per group %d > %d", cg, kEpiThreads);
+    const int cblk = (kEpiThreads / cg) * cg;
+    const int nblk = ceil_div(C, cblk);
+    const int nwarps = kEpiThreads / 32;
+    const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
+    static int epi_attr = 48 * 1024;
+    if ((int)smem > epi_attr) {
+        FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        epi_attr = (int)smem;
+    }
+    relation_epilogue_kernel<kMaxPP><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
+                                                                              fc_cls_w, fc_reg_w, partial);
+    FGN_LAUNCH_OK();
+    relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(partial, R, N, nblk, fc_cls_b, fc_reg_b, cls_out, reg_out,
+                                                              nullptr, nullptr);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
 extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P)
 {
     if (R < 0 || BN <= 0 || C <= 0 || P <= 0) return 0;
@@ -283,11 +383,6 @@ extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int
            fgn_relation_fusion_workspace_bytes(R, BN, C, P);
 }
 
-__global__ void roi_batch_kernel(const float *__restrict__ rois, int R, int32_t *__restrict__ out)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R) out[r] = (int)rois[5 * (size_t)r];
-}
 
 extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois,
                                         int R, int P, int sampling_ratio, int aligned,

@@ -382,6 +382,11 @@ int launch_roi_align_stream(const Pyramid &d, int C, int P, const float *rois, i
                             const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
                             cudaStream_t st, int vec_pref, int ns_pref, bool *taken);
 
+int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                                 int aligned, float finest_scale, const float *chan_scale,
+                                 const int32_t *scale_index, void *out, int out_is_bf16, int32_t *lvl_out,
+                                 cudaStream_t st);
+
 }  // namespace fgn
 
 using namespace fgn;
@@ -482,4 +487,20 @@ extern "C" int fgn_roi_align_sample_indices(const fgn_pyramid_t *pyr, const floa
         ytab_out, xtab_out);
     FGN_LAUNCH_OK();
     return FGN_OK;
+}
+
+extern "C" int fgn_roi_align_ml_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R, int P,
+                                         int sampling_ratio, int aligned, float finest_scale,
+                                         const float *chan_scale, const int32_t *scale_index, void *out,
+                                         int out_is_bf16, int32_t *lvl_out, void *stream)
+{
+    int rc = validate_pyramid(pyr);
+    if (rc) return rc;
+    FGN_CHECK_ARG(R >= 0 && B >= 0 && C > 0 && P > 0, "bad dims R=%d B=%d C=%d P=%d", R, B, C, P);
+    if (R == 0) return FGN_OK;
+    FGN_CHECK_ARG(rois && out, "NULL pointer");
+    for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
+    const Pyramid d = to_device_pyramid(pyr);
+    return launch_roi_align_stream_bf16(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                        scale_index, out, out_is_bf16, lvl_out, (cudaStream_t)stream);
 }

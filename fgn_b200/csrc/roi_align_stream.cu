@@ -17,6 +17,7 @@
 // re-reads that adjacent bins share (about 1.5x in the bin-centric kernel) are served from
 // shared memory.  full/empty mbarriers form the usual producer/consumer pipeline.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace fgn {
@@ -388,6 +389,228 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
             reinterpret_cast<float4 *>(o)[i] = reinterpret_cast<const float4 *>(stage_out)[i];
         for (int i = (n4 << 2) + t; i < n; i += blockDim.x) o[i] = stage_out[i];
     }
+}
+
+// ================================================================================================
+// bf16 variant (reported separately from the fp32 contract): the pyramid is stored as NHWC bf16, so
+// every footprint cell moves half the bytes through HBM / L2 / shared memory; weights, accumulation
+// and the 1/count scaling stay fp32; the pooled features leave as bf16 (the A operand of the bf16
+// contraction) or fp32.  One CTA = RoI x 256 channels, lane = 8 contiguous channels (one 128-bit LDS).
+// ================================================================================================
+template <int P, int NS>
+__global__ void __launch_bounds__((P + 1) * 32, P > 8 ? 1 : 2)
+roi_align_stream_bf16_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
+                             const int sampling_ratio, const int aligned, const float finest_scale,
+                             const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
+                             void *__restrict__ out, const int out_is_bf16, int32_t *__restrict__ lvl_out,
+                             const int wx_cap, const int wyd_rows)
+{
+    constexpr int CB  = 256;
+    constexpr int PP8 = (P + 3) & ~3;
+    constexpr unsigned FULL = 0xffffffffu;
+    typedef unsigned short bf16_t;                          // raw bf16 storage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ StreamPlan plan;
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+
+    bf16_t *ring = reinterpret_cast<bf16_t *>(smem_raw);
+    float *wx   = reinterpret_cast<float *>(ring + (size_t)NS * kStageCells * CB);
+    float *wyd  = wx + wx_cap;
+
+    const int nblk = (C + CB - 1) / CB;
+    const int r    = blockIdx.x / nblk;
+    const int cb0  = (blockIdx.x % nblk) * CB;
+    const int t    = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cbn  = min(CB, C - cb0);
+    const bool contiguous = (cbn == C);
+    const int cstride = contiguous ? C : CB;
+
+    if (t == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == P) {
+        const WarpPlan wp = warp_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, lane, wx_cap, wyd_rows);
+        const bf16_t *fbase = reinterpret_cast<const bf16_t *>(pyr.feat[wp.level]) + ((size_t)wp.g.batch * wp.H * wp.W) * C + cb0
+                              + ((size_t)wp.Y0 * wp.W + wp.X0) * C;
+        const size_t row_pitch = (size_t)wp.W * C;
+        int s = 0, par = 1, row0 = 0, col0 = 0;
+        for (int st = 0; st < wp.nstages; ++st) {
+            int nr, nc;
+            if (wp.nseg == 1) { nr = min(wp.rps, wp.nrows - row0); nc = wp.ncols; }
+            else              { nr = 1; nc = min(kStageCells, wp.ncols - col0); }
+            mbar_wait(&empty_bar[s], par);
+            bf16_t *dst = ring + (size_t)s * kStageCells * CB;
+            if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * nc * cbn * 2));
+            __syncwarp();
+            const bf16_t *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
+            if (contiguous) {
+                if (lane < nr)
+                    bulk_g2s(dst + (size_t)lane * nc * cstride, src + (size_t)lane * row_pitch, (uint32_t)(nc * C * 2), &full_bar[s]);
+            } else {
+                for (int cell = lane; cell < nr * nc; cell += 32) {
+                    const int rr = cell / nc, cc = cell - rr * nc;
+                    bulk_g2s(dst + (size_t)cell * cstride, src + (size_t)rr * row_pitch + (size_t)cc * C, (uint32_t)(cbn * 2), &full_bar[s]);
+                }
+            }
+            if (wp.nseg == 1) row0 += nr;
+            else { col0 += nc; if (col0 >= wp.ncols) { col0 = 0; ++row0; } }
+            if (++s == NS) { s = 0; par ^= 1; }
+        }
+    } else {
+        if (warp == 0) {
+            const WarpPlan wp = warp_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, lane, wx_cap, wyd_rows);
+            const int axis = lane / P, p = lane % P;
+            int off = 0;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                const int nq = __shfl_sync(FULL, wp.n, P + q);
+                if (lane >= P && q < p) off += nq;
+            }
+            if (lane == 0) {
+                plan.level = wp.level; plan.count = wp.g.count;
+                plan.X0 = wp.X0; plan.Y0 = wp.Y0; plan.ncols = wp.ncols; plan.nrows = wp.nrows;
+                plan.nseg = wp.nseg; plan.rps = wp.rps; plan.nstages = wp.nstages;
+                if (lvl_out != nullptr && cb0 == 0) lvl_out[r] = wp.level;
+            }
+            if (lane >= P && lane < 2 * P) { plan.xlo[p] = wp.lo; plan.xn[p] = wp.n; plan.xoff[p] = off; }
+            for (int i = lane; i < wp.nrows * (PP8 / 4); i += 32)
+                reinterpret_cast<float4 *>(wyd)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (lane < 2 * P && wp.nstages > 0) {
+                const float start = axis ? wp.g.start_w : wp.g.start_h, bin = axis ? wp.g.bin_w : wp.g.bin_h;
+                const int grid = axis ? wp.g.grid_w : wp.g.grid_h, size = axis ? wp.W : wp.H;
+                if (axis) {
+                    float *w = wx + off;
+                    for (int i = 0; i < wp.n; ++i) w[i] = 0.f;
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { w[sm.low - wp.lo] += sm.h; w[sm.high - wp.lo] += sm.l; }
+                    }
+                } else {
+                    float *w = wyd + p - (size_t)wp.Y0 * PP8;
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { w[(size_t)sm.low * PP8] += sm.h; w[(size_t)sm.high * PP8] += sm.l; }
+                    }
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(P * 32) : "memory");
+
+        float4 acc[P][2];
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) { acc[ph][0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[ph][1] = acc[ph][0]; }
+        const int pw = warp;
+        const int nrows = plan.nrows, ncols = plan.ncols, nstages = plan.nstages, rps = plan.rps, nseg = plan.nseg;
+        const int xlo = plan.xlo[pw] - plan.X0, nx = plan.xn[pw];
+        const float *wxp = wx + plan.xoff[pw];
+        const int loff = (lane * 8 < cbn) ? lane * 8 : 0;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+
+        auto cell_fma = [&](const bf16_t *cp, float w) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(cp + loff);
+            ra.x = fmaf(w, __uint_as_float(q.x << 16), ra.x); ra.y = fmaf(w, __uint_as_float(q.x & 0xffff0000u), ra.y);
+            ra.z = fmaf(w, __uint_as_float(q.y << 16), ra.z); ra.w = fmaf(w, __uint_as_float(q.y & 0xffff0000u), ra.w);
+            rb.x = fmaf(w, __uint_as_float(q.z << 16), rb.x); rb.y = fmaf(w, __uint_as_float(q.z & 0xffff0000u), rb.y);
+            rb.z = fmaf(w, __uint_as_float(q.w << 16), rb.z); rb.w = fmaf(w, __uint_as_float(q.w & 0xffff0000u), rb.w);
+        };
+        auto fold = [&](int j) {
+            float wrow[PP8];
+#pragma unroll
+            for (int q = 0; q < PP8 / 4; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(wyd + (size_t)j * PP8 + 4 * q);
+                wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int ph = 0; ph < P; ++ph)
+                if (wrow[ph] != 0.f) { fma4(acc[ph][0], wrow[ph], ra); fma4(acc[ph][1], wrow[ph], rb); }
+            ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = ra;
+        };
+
+        int s = 0, par = 0, row = 0, col0 = 0;
+        for (int st = 0; st < nstages; ++st) {
+            int nr, nc;
+            if (nseg == 1) { nr = min(rps, nrows - row); nc = ncols; }
+            else           { nr = 1; nc = min(kStageCells, ncols - col0); }
+            mbar_wait(&full_bar[s], par);
+            const bf16_t *base = ring + (size_t)s * kStageCells * CB;
+            const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
+            for (int rr = 0; rr < nr; ++rr) {
+                const bf16_t *cp = base + (size_t)(rr * nc + c_beg - col0) * cstride;
+#pragma unroll 4
+                for (int cx = c_beg; cx < c_end; ++cx, cp += cstride) cell_fma(cp, wxp[cx - xlo]);
+                if (nseg == 1) { fold(row); ++row; }
+            }
+            if (nseg != 1) { col0 += nc; if (col0 >= ncols) { fold(row); col0 = 0; ++row; } }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == NS) { s = 0; par ^= 1; }
+        }
+
+        if (lane * 8 < cbn) {
+            const int c = cb0 + lane * 8;
+            const float inv = 1.0f / plan.count;
+            float4 sa = make_float4(inv, inv, inv, inv), sb = sa;
+            if (chan_scale != nullptr) {
+                const int si = scale_index != nullptr ? scale_index[r] : r;
+                const float4 a = ldg4(chan_scale + (size_t)si * C + c), b = ldg4(chan_scale + (size_t)si * C + c + 4);
+                sa = make_float4(inv * a.x, inv * a.y, inv * a.z, inv * a.w);
+                sb = make_float4(inv * b.x, inv * b.y, inv * b.z, inv * b.w);
+            }
+#pragma unroll
+            for (int ph = 0; ph < P; ++ph) {
+                const float4 a = acc[ph][0], b = acc[ph][1];
+                const size_t o = (((size_t)r * P + ph) * P + pw) * C + c;
+                if (out_is_bf16) {
+                    uint4 q;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x * sa.x, a.y * sa.y), t1 = __floats2bfloat162_rn(a.z * sa.z, a.w * sa.w);
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x * sb.x, b.y * sb.y), t3 = __floats2bfloat162_rn(b.z * sb.z, b.w * sb.w);
+                    q.x = *reinterpret_cast<unsigned *>(&t0); q.y = *reinterpret_cast<unsigned *>(&t1);
+                    q.z = *reinterpret_cast<unsigned *>(&t2); q.w = *reinterpret_cast<unsigned *>(&t3);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16_t *>(out) + o) = q;
+                } else {
+                    float *of = reinterpret_cast<float *>(out) + o;
+                    *reinterpret_cast<float4 *>(of) = make_float4(a.x * sa.x, a.y * sa.y, a.z * sa.z, a.w * sa.w);
+                    *reinterpret_cast<float4 *>(of + 4) = make_float4(b.x * sb.x, b.y * sb.y, b.z * sb.z, b.w * sb.w);
+                }
+            }
+        }
+    }
+}
+
+int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                                 int aligned, float finest_scale, const float *chan_scale,
+                                 const int32_t *scale_index, void *out, int out_is_bf16, int32_t *lvl_out,
+                                 cudaStream_t st)
+{
+    if ((C & 7) != 0 || (P != 7 && P != 14)) {
+        set_error("bf16 RoIAlign needs C%%8==0 and P in {7,14} (C=%d P=%d)", C, P);
+        return FGN_ERR_UNSUPPORTED;
+    }
+    int maxH = 0, maxW = 0;
+    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
+    const int wx_cap = (maxW + 6 * P + 16 + 3) & ~3;
+    const int wyd_rows = maxH;
+    const int PP8 = (P + 3) & ~3;
+    constexpr int NS = 4;
+    const size_t smem = (size_t)NS * kStageCells * 256 * 2 + (size_t)wx_cap * 4 + (size_t)wyd_rows * PP8 * 4;
+    if (smem > 200 * 1024) { set_error("bf16 RoIAlign: feature map too tall for the weight table (%d rows)", maxH); return FGN_ERR_UNSUPPORTED; }
+    const int nblk = (C + 255) / 256;
+    static int attr7 = 0, attr14 = 0;
+    if (P == 7) {
+        if ((int)smem > attr7) { FGN_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_bf16_kernel<7, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr7 = (int)smem; }
+        roi_align_stream_bf16_kernel<7, NS><<<R * nblk, 8 * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                                                         scale_index, out, out_is_bf16, lvl_out, wx_cap, wyd_rows);
+    } else {
+        if ((int)smem > attr14) { FGN_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_bf16_kernel<14, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr14 = (int)smem; }
+        roi_align_stream_bf16_kernel<14, NS><<<R * nblk, 15 * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                                                           scale_index, out, out_is_bf16, lvl_out, wx_cap, wyd_rows);
+    }
+    FGN_LAUNCH_OK();
+    return FGN_OK;
 }
 
 // ================================================================================================

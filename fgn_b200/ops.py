@@ -127,7 +127,11 @@ def map_roi_levels(rois: torch.Tensor, num_levels: int, finest_scale: float = 56
     return out.long()
 
 
-def _make_pyramid(feats: Sequence[torch.Tensor], scales: Sequence[float]):
+def _is_bf16(feats: Sequence[torch.Tensor]) -> bool:
+    return all(f.dtype == torch.bfloat16 for f in feats)
+
+
+def _make_pyramid(feats: Sequence[torch.Tensor], scales: Sequence[float], dtype=torch.float32):
     if len(feats) != len(scales) or not (1 <= len(feats) <= _lib.FGN_MAX_LEVELS):
         raise FgnError(f"pyramid needs 1..{_lib.FGN_MAX_LEVELS} levels with one scale each")
     keep = []
@@ -137,7 +141,11 @@ def _make_pyramid(feats: Sequence[torch.Tensor], scales: Sequence[float]):
     pyr.num_levels = len(feats)
     for i, (f, s) in enumerate(zip(feats, scales)):
         _need_cuda(f)
-        f, lay = _dense(_f32(f, f"feats[{i}]"))
+        if f.dtype != dtype:
+            raise FgnError(f"feats[{i}]: expected {dtype}, got {f.dtype}")
+        if dtype == torch.bfloat16 and storage_layout(f) != LAYOUT_NHWC:
+            raise FgnError("bf16 feature maps must be channels_last (the bf16 variant has no NCHW kernels)")
+        f, lay = _dense(f)
         if f.shape[0] != b0 or f.shape[1] != c0:
             raise FgnError("all pyramid levels must share batch and channel dims")
         if lay0 is None:
@@ -156,7 +164,8 @@ def roi_align_multilevel(feats: Sequence[torch.Tensor], rois: torch.Tensor, scal
                          output_size: int = 7, sampling_ratio: int = 0, aligned: bool = True,
                          finest_scale: float = 56.0, chan_scale: Optional[torch.Tensor] = None,
                          scale_index: Optional[torch.Tensor] = None, out_format: str = "nchw",
-                         return_levels: bool = False, nchw_input: str = "repack", force_direct: bool = False):
+                         return_levels: bool = False, nchw_input: str = "repack", force_direct: bool = False,
+                         out_dtype: Optional[torch.dtype] = None):
     """Level assignment + RoIAlign (avg) in one kernel.  ``feats``: list of [B,C,H_l,W_l].
 
     ``nchw_input``: what to do with reference-layout (contiguous NCHW) inputs --
@@ -169,6 +178,21 @@ def roi_align_multilevel(feats: Sequence[torch.Tensor], rois: torch.Tensor, scal
         raise FgnError("rois must be [R,5] (batch_idx, x1, y1, x2, y2)")
     feats = list(feats)
     c = feats[0].shape[1]
+    if _is_bf16(feats):       # bf16 variant: NHWC in, NHWC out (bf16 unless out_dtype=torch.float32)
+        pyr, keep, lay, b, c = _make_pyramid(feats, scales, torch.bfloat16)
+        r, p = rois.shape[0], int(output_size)
+        odt = out_dtype or torch.bfloat16
+        out = torch.empty((r, p, p, c), device=rois.device, dtype=odt).permute(0, 3, 1, 2)
+        lvl = torch.empty((r,), device=rois.device, dtype=torch.int32) if return_levels else None
+        if chan_scale is not None:
+            chan_scale = _f32(chan_scale, "chan_scale").reshape(-1, c).contiguous()
+            if scale_index is not None:
+                scale_index = scale_index.to(torch.int32).contiguous()
+        _lib.check(_lib.load().fgn_roi_align_ml_fwd_bf16(
+            ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
+            _ptr(chan_scale), _ptr(scale_index), out.data_ptr(), int(odt == torch.bfloat16), _ptr(lvl), _stream()),
+            "fgn_roi_align_ml_fwd_bf16")
+        return (out, lvl.long()) if return_levels else out
     if nchw_input == "repack" and not force_direct and c % 4 == 0:
         feats = [to_nhwc(f) if storage_layout(f) != LAYOUT_NHWC else f for f in feats]
     pyr, keep, lay, b, c = _make_pyramid(feats, scales)
@@ -298,7 +322,13 @@ def attention_multilevel(qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[
     qs, ss = list(qry_feats), list(spp_feats)
     _need_cuda(*qs, *ss)
     c = qs[0].shape[1]
-    fast = c % 4 == 0 and c <= 1024 and all(storage_layout(t) == LAYOUT_NHWC and t.dtype == torch.float32 for t in qs + ss)
+    bf16 = _is_bf16(qs + ss)
+    if bf16:
+        if c % 8 or c > 1024 or not all(storage_layout(t) == LAYOUT_NHWC for t in qs + ss):
+            raise FgnError("bf16 attention needs channels_last maps with C%8==0 and C<=1024")
+        fast = True
+    else:
+        fast = c % 4 == 0 and c <= 1024 and all(storage_layout(t) == LAYOUT_NHWC and t.dtype == torch.float32 for t in qs + ss)
     if not fast:
         vecs = [attention_vectors(s, n_ways, k_shots) for s in ss]
         return vecs, [channel_attention(q, v) for q, v in zip(qs, vecs)]
@@ -313,17 +343,21 @@ def attention_multilevel(qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[
             raise FgnError("attention_multilevel: level shapes must be [B,C,H,W] / [B*N*K,C,h,w]")
         spyr.feat[i], spyr.H[i], spyr.W[i] = s.data_ptr(), s.shape[2], s.shape[3]
         qpyr.feat[i], qpyr.H[i], qpyr.W[i] = q.data_ptr(), q.shape[2], q.shape[3]
-        outs.append(_empty_like_format((bn, c, q.shape[2], q.shape[3]), q.device, LAYOUT_NHWC))
+        if bf16:
+            outs.append(torch.empty((bn, q.shape[2], q.shape[3], c), device=q.device, dtype=torch.bfloat16).permute(0, 3, 1, 2))
+        else:
+            outs.append(_empty_like_format((bn, c, q.shape[2], q.shape[3]), q.device, LAYOUT_NHWC))
     lib = _lib.load()
     dev = qs[0].device
     vec = torch.empty((L, bn, c), device=dev, dtype=torch.float32)
     wsb = lib.fgn_attention_vectors_ml_workspace_bytes(ctypes.byref(spyr), bn, k_shots, c)
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
-    _lib.check(lib.fgn_attention_vectors_ml(ctypes.byref(spyr), bn, int(k_shots), c, vec.data_ptr(), ws.data_ptr(), wsb,
-                                            _stream()), "fgn_attention_vectors_ml")
+    fvec = lib.fgn_attention_vectors_ml_bf16 if bf16 else lib.fgn_attention_vectors_ml
+    fmul = lib.fgn_channel_attention_ml_bf16 if bf16 else lib.fgn_channel_attention_ml
+    _lib.check(fvec(ctypes.byref(spyr), bn, int(k_shots), c, vec.data_ptr(), ws.data_ptr(), wsb, _stream()),
+               "fgn_attention_vectors_ml")
     ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
-    _lib.check(lib.fgn_channel_attention_ml(ctypes.byref(qpyr), vec.data_ptr(), b, n_ways, c, ptrs, _stream()),
-               "fgn_channel_attention_ml")
+    _lib.check(fmul(ctypes.byref(qpyr), vec.data_ptr(), b, n_ways, c, ptrs, _stream()), "fgn_channel_attention_ml")
     return [vec[i].view(b, n_ways, c, 1, 1) for i in range(L)], outs
 
 
@@ -403,8 +437,10 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
     """FPN-mode single call: level assignment + RoIAlign + relation fusion + heads."""
     _need_cuda(rois, spp_cat_mean)
     rois = _f32(rois, "rois").contiguous()
-    feats = [to_nhwc(f) if storage_layout(f) != LAYOUT_NHWC else f for f in feats]
-    pyr, keep, lay, b, c = _make_pyramid(feats, scales)
+    bf16 = _is_bf16(list(feats))
+    if not bf16:
+        feats = [to_nhwc(f) if storage_layout(f) != LAYOUT_NHWC else f for f in feats]
+    pyr, keep, lay, b, c = _make_pyramid(feats, scales, torch.bfloat16 if bf16 else torch.float32)
     p = int(output_size)
     s = to_nhwc(_f32(spp_cat_mean.reshape(-1, c, p, p), "spp_cat_mean"))
     bn = s.shape[0]
@@ -416,9 +452,19 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
     reg = torch.empty((r, 4 * n_ways), device=dev, dtype=torch.float32)
     lvl = torch.empty((r,), device=dev, dtype=torch.int32) if return_levels else None
     lib = _lib.load()
+    pr = params
+    if bf16:
+        wsb = lib.fgn_guided_roi_fused_bf16_workspace_bytes(r, bn, c, p)
+        ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.fgn_guided_roi_fused_fwd_bf16(
+            ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
+            s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
+            pr.gn_groups, pr.gn_eps, pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(),
+            pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), ws.data_ptr(), wsb, _stream()),
+            "fgn_guided_roi_fused_fwd_bf16")
+        return (cls, reg, lvl.long()) if return_levels else (cls, reg)
     wsb = lib.fgn_guided_roi_fused_workspace_bytes(r, bn, c, p)
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
-    pr = params
     _lib.check(lib.fgn_guided_roi_fused_fwd(
         ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
         s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
@@ -438,6 +484,12 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
     n = b.shape[0]
     c = torch.empty((m, n), device=a.device, dtype=torch.float32)
     lib = _lib.load()
+    if a.dtype == torch.bfloat16 or b.dtype == torch.bfloat16:
+        if not (a.dtype == b.dtype == torch.bfloat16):
+            raise FgnError("bf16 contraction needs both operands in bfloat16")
+        _lib.check(lib.fgn_gemm_nt_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(bias), c.data_ptr(), n,
+                                        m, n, k, _stream()), "fgn_gemm_nt_bf16")
+        return c
     wsb = lib.fgn_gemm_workspace_bytes(n, k) if use_workspace else 0
     ws = torch.empty((max(wsb, 1),), device=a.device, dtype=torch.uint8)
     _lib.check(lib.fgn_gemm_nt(_f32(a, "a").data_ptr(), a.stride(0), _f32(b, "b").data_ptr(), b.stride(0), _ptr(bias),

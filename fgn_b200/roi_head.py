@@ -178,12 +178,14 @@ class FGNRoIHead(nn.Module):
             else:
                 boxes = spp_bboxes / self.subsampling_ratio
             rois = torch.cat([idx, boxes.reshape(m, 4).float()], 1)
-            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False, out_format=fmt)  # :432
+            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False, out_format=fmt,
+                                               out_dtype=torch.float32)                          # :432
         else:   # A-FPN: level from map_roi_levels on the pixel box, spatial_scale = 1/stride
             rois = torch.cat([idx, spp_bboxes.reshape(m, 4).float()], 1)
             ext = self.bbox_roi_extractor
             feat_ra = ops.roi_align_multilevel(levels, rois, [1.0 / s for s in ext.featmap_strides[: len(levels)]],
-                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale), out_format=fmt)
+                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale), out_format=fmt,
+                                               out_dtype=torch.float32)
         if self.with_shared_head:
             feat_ra = self.shared_head_layer(feat_ra)                                            # :435-436
         cat_mean, mp = ops.support_pool(feat_ra, mask_ra, self.n_ways, self.k_shots)             # :439-447

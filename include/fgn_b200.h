@@ -167,6 +167,12 @@ size_t fgn_gemm_workspace_bytes(int N, int K);
 int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
                 int M, int N, int K, int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* bf16 variant of the contraction (reported separately, never the fp32 default): A [M,K] and B [N,K]
+ * hold bf16 (uint16 storage), accumulation and C are fp32; tcgen05 kind::f16, one pass.
+ * Needs K%64==0, N%16==0 (N<=256 or N%256==0), 16-byte aligned rows. */
+int fgn_gemm_nt_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C,
+                     int ldc, int M, int N, int K, void *stream);
+
 /* count_modified_cls_bbox alone (fgn_roi_head.py:302-326), generalised from N in {1,3} to any N:
  *   raw_cls [R*N,2] (bg,fg), raw_reg [R*N,4] -> cls_out [R,N+1] = (fg_0..fg_{N-1}, bg of the
  *   first-max fg class), reg_out [R,4N]. */
@@ -186,6 +192,29 @@ int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float
                              const float *fc_reg_w, const float *fc_reg_b,
                              float *cls_out, float *reg_out, int32_t *lvl_out,
                              int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- bf16 variant (reported separately; the fp32 entry points above are the parity contract) ----
+ * Pyramid levels hold bf16 in NHWC storage (fgn_pyramid_t.feat reinterpreted as uint16 pointers);
+ * coordinates, weights and accumulation stay fp32, so level assignment and sample indices are the
+ * same bit-exact contract.  out is bf16 (out_is_bf16 = 1) or fp32, NHWC [R,P,P,C].  Needs C%8==0. */
+int fgn_roi_align_ml_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R, int P,
+                              int sampling_ratio, int aligned, float finest_scale,
+                              const float *chan_scale, const int32_t *scale_index, void *out,
+                              int out_is_bf16, int32_t *lvl_out, void *stream);
+int fgn_attention_vectors_ml_bf16(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec,
+                                  void *workspace, size_t workspace_bytes, void *stream);   /* vec stays fp32 */
+int fgn_channel_attention_ml_bf16(const fgn_pyramid_t *qry, const float *vec, int B, int N, int C,
+                                  void *const *out_host, void *stream);                     /* bf16 in, bf16 out */
+size_t fgn_guided_roi_fused_bf16_workspace_bytes(int R, int BN, int C, int P);
+int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
+                                  int P, int sampling_ratio, int aligned, float finest_scale,
+                                  const float *spp_cat_mean /* [B*N,P,P,C] NHWC fp32 */, int N,
+                                  const float *conv_w, const float *conv_b,
+                                  const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
+                                  const float *fc_cls_w, const float *fc_cls_b,
+                                  const float *fc_reg_w, const float *fc_reg_b,
+                                  float *cls_out, float *reg_out, int32_t *lvl_out,
+                                  void *workspace, size_t workspace_bytes, void *stream);
 
 /* Number of kernels this library has launched in the calling process since load
  * (bench.py's gpu_launches). */

@@ -472,6 +472,67 @@ def test_attention_layouts_and_multilevel_agree():
         close(ops.channel_attention(cl(qs[l]), v2), want[l][1], what=f"mod nhwc {l}")
 
 
+@pytest.mark.parametrize("M,N,K", [(49 * 40, 256, 256), (1000, 64, 64), (700, 1024, 1024)])
+def test_bf16_contraction_variant(M, N, K):
+    """bf16 variant (reported separately): exact products of bf16 operands, fp32 accumulation.  Against an
+    fp64 matmul of the SAME bf16-rounded operands the error is fp32-accumulation sized; against the
+    un-rounded fp32 operands it is the bf16 input rounding, ~2^-9 relative per term (stated tolerance 3e-2)."""
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    a, w, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * K ** -0.5, torch.randn(N, generator=g)
+    ab, wb = a.bfloat16(), w.bfloat16()
+    got = ops.gemm_nt(ab.to(dev()), wb.to(dev()), bias.to(dev()))
+    want_same_inputs = (ab.double() @ wb.double().t() + bias.double()).float()
+    close(got, want_same_inputs, atol=1e-4, rtol=1e-5, what="bf16 operands, fp32 accumulate")
+    want_fp32 = (a.double() @ w.double().t() + bias.double()).float()
+    assert float((got.cpu() - want_fp32).abs().max()) < 3e-2
+
+
+def test_bf16_guided_path_variant():
+    """bf16 variant of the FPN path (reported separately): bf16 NHWC pyramid, bf16 RoI features and
+    contraction operands, fp32 everywhere else.  Levels stay bit-exact; RoI features are compared with
+    the fp32 oracle evaluated on the SAME bf16-rounded maps (tolerance = one bf16 rounding of the
+    output, 2^-8 relative); logits carry the stated bf16 tolerance of 3e-2 absolute."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode, make_weights
+    cfg = CONFIGS["tiny_fpn"]
+    ep = make_episode(cfg, seed=4)
+    rpn, head = build_heads(cfg, dev(), seed=0)
+    epd = episode_to_device(ep, dev())
+    q16 = [q.bfloat16().contiguous(memory_format=torch.channels_last) for q in epd["qry"][:4]]
+    s16 = [s.bfloat16().contiguous(memory_format=torch.channels_last) for s in epd["spp"][:4]]
+    qr = [q.float().cpu().contiguous() for q in q16]                         # the rounded maps, as fp32, for the oracle
+    sr = [s.float().cpu().contiguous() for s in s16]
+    scales = [1 / s for s in cfg.strides]
+    feats, lvl = ops.roi_align_multilevel(q16, epd["rois"], scales, 7, 0, True, return_levels=True)
+    want, lv = O.single_roi_extractor(qr, ep["rois"], cfg.strides, 7, 0, True, 56.0, "tv")
+    assert feats.dtype == torch.bfloat16 and torch.equal(lvl.cpu(), lv)
+    close(feats.float(), want, atol=1e-3, rtol=2 ** -8, what="bf16 roi feats")
+    f32out = ops.roi_align_multilevel(q16, epd["rois"], scales, 7, 0, True, out_dtype=torch.float32)
+    close(f32out, want, what="bf16 maps, fp32 accumulate + fp32 out")       # only summation order differs
+    with torch.no_grad():
+        head.count_spp(s16, epd["spp_bboxes"].clone(), epd["spp_masks"])
+        res = head._bbox_forward(q16, epd["rois"], need_feats=False)
+        head.gather_mask_vectors(epd["det_labels_list"])
+        mres = head._mask_forward(q16, epd["det_rois"])
+    vecs, mods = rpn.attention_multilevel(q16, s16)
+    for l in range(4):
+        wv, wm = O.agrpn_attention(qr[l], sr[l], cfg.n_ways, cfg.k_shots)
+        close(vecs[l], wv, what=f"bf16 attention vec {l}")                     # fp32 accumulation of bf16 maps
+        assert mods[l].dtype == torch.bfloat16
+        close(mods[l].float(), wm, atol=1e-3, rtol=2 ** -8, what=f"bf16 attention out {l}")
+    w = make_weights(cfg.channels, 0)
+    cat_mean, mp, _, _ = O.count_spp_fpn(sr, cfg.strides, ep["spp_bboxes"].clone(), ep["spp_masks"], cfg.n_ways, cfg.k_shots)
+    close(head.spp_fmaps_roi_aligned_cat_mean, cat_mean, what="cat_mean from bf16 maps (fp32 out)")
+    ref = O.bbox_forward(qr, cfg.strides, ep["rois"], cat_mean, cfg.n_ways, w)
+    for k in ("cls_score", "bbox_pred"):
+        err = float((res[k].cpu() - ref[k]).abs().max())
+        assert err < 3e-2, (k, err)
+    mf = O.mask_attention(qr, cfg.strides, ep["det_rois"], mp, ep["det_labels_list"], cfg.n_ways, 7)
+    assert mres["mask_feats"].dtype == torch.bfloat16
+    close(mres["mask_feats"].float(), mf, atol=1e-3, rtol=2 ** -7, what="bf16 mask feats")
+
+
 def test_empty_proposals():
     from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
     cfg = CONFIGS["tiny_fpn"]
