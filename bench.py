@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying one CUDA graph per episode")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the separately reported bf16 variant")
     ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -347,7 +348,37 @@ def main():
     roofline = {"kernel": "roi_align_stream_kernel<7,2,3,1> (level assignment + multi-level RoIAlign, NHWC in/out)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "traffic": None}
+                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+                # (profiles/r01_roi_align_stream_ncu.txt): 97.7 MB + 29.8 MB
+                "traffic": 127.5e6 if cfg.name == WORKLOAD else None}
+
+    # ---- bf16 variant, reported separately (bf16 NHWC maps + bf16 contraction operands; stated tolerance 3e-2
+    #      abs on logits, see tests/test_gpu_parity.py::test_bf16_guided_path_variant)
+    bf16_line = None
+    if not args.no_bf16:
+        eps16 = []
+        for ep in dev_eps:
+            e16 = dict(ep)
+            e16["qry"] = [q.bfloat16().contiguous(memory_format=torch.channels_last) for q in ep["qry"]]
+            e16["spp"] = [q.bfloat16().contiguous(memory_format=torch.channels_last) for q in ep["spp"]]
+            eps16.append(e16)
+        runner16 = EpisodeRunner(rpn, head, eps16, use_graphs=not args.no_graphs, n_streams=args.streams)
+
+        def step16():
+            runner16.begin()
+            for i in range(E):
+                runner16.run(i)
+            runner16.end()
+
+        ms16, _, _ = timed(step16, args.steps, args.warmup)
+        with torch.no_grad():
+            a = run_guided_path(rpn, head, eps16[0])["cls_score"]
+            b = run_guided_path(rpn, head, dev_eps[0])["cls_score"]
+        bf16_line = {"value": E * world * args.steps * cfg.num_rois * cfg.batch / (ms16 * 1e-3), "unit": "RoIs/s",
+                     "ms_per_step": ms16 / args.steps, "max_abs_logit_diff_vs_fp32": float((a - b).abs().max()),
+                     "stated_tolerance": 3e-2, "dtype": "bf16 maps/operands, f32 accumulate"}
+        del runner16, eps16
 
     if rank == 0:
         line = {"metric": "guided RoIAlign+fusion RoIs/s", "value": value, "unit": "RoIs/s",
@@ -356,7 +387,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "host_layout": "NCHW fp32 pinned"},
-                "gpu_launches": int(launches), "roofline": roofline}
+                "gpu_launches": int(launches), "roofline": roofline, "bf16_variant": bf16_line}
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             n, dt = time_cpu_reference(cfg, 1, 1, 1)

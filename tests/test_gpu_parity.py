@@ -533,6 +533,63 @@ def test_bf16_guided_path_variant():
     close(mres["mask_feats"].float(), mf, atol=1e-3, rtol=2 ** -7, what="bf16 mask feats")
 
 
+def test_full_size_properties_cfg4_relation():
+    """cfg4 at BASELINE size (N=20 ways, K=5 shots, R=1000, C=256): size-independent properties of the
+    relation fusion -- (1) each class's (bg,fg) logits and box deltas equal a 1-way run with that class
+    alone, (2) permuting the classes permutes the outputs, (3) the background column follows the
+    first-max foreground class, (4) chunking the RoIs changes nothing."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import make_weights
+    g = torch.Generator().manual_seed(404)
+    N, C, R = 20, 256, 1000
+    w = make_weights(C, 3)
+    params = ops.RelationParams(*[w[k].to(dev()) for k in ("conv_w", "conv_b", "gn_w", "gn_b", "fc_cls_w", "fc_cls_b",
+                                                            "fc_reg_w", "fc_reg_b")])
+    feats = torch.randn(R, C, 7, 7, generator=g).to(dev()).contiguous(memory_format=torch.channels_last)
+    cat = torch.randn(1, N, C, 7, 7, generator=g).to(dev())
+    rb = torch.zeros(R, device=dev())
+    cls, reg, rawc, rawr = ops.relation_fusion(feats, rb, cat, N, params, return_raw=True)
+    assert cls.shape == (R, N + 1) and reg.shape == (R, 4 * N) and torch.isfinite(cls).all()
+    for n in (0, 7, 19):                                                     # (1)
+        c1, r1 = ops.relation_fusion(feats, rb, cat[:, n:n + 1].contiguous(), 1, params)
+        assert torch.equal(c1[:, 0], cls[:, n]) and torch.equal(r1, reg[:, 4 * n:4 * n + 4])
+        assert torch.equal(c1[:, 1], rawc.view(R, N, 2)[:, n, 0])
+    perm = torch.randperm(N, generator=g).to(dev())                          # (2)
+    cp, rp = ops.relation_fusion(feats, rb, cat[:, perm].contiguous(), N, params)
+    assert torch.equal(cp[:, :N], cls[:, perm]) and torch.equal(rp.view(R, N, 4), reg.view(R, N, 4)[:, perm])
+    top = cls[:, :N].argmax(1)                                               # (3)
+    assert torch.equal(cls[:, N], rawc.view(R, N, 2)[torch.arange(R, device=dev()), top, 0])
+    ca, ra = ops.relation_fusion(feats[:300].contiguous(memory_format=torch.channels_last), rb[:300], cat, N, params)   # (4)
+    assert torch.equal(ca, cls[:300]) and torch.equal(ra, reg[:300])
+
+
+def test_full_size_properties_cfg5_mask_branch():
+    """cfg5 at BASELINE size (16 images/GPU, P=14, C=256, 100 detections per image): batched extraction
+    equals per-image extraction bitwise, and the fused AG-FCN multiply equals RoIAlign followed by the
+    channel-attention kernel."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import CONFIGS, episode_to_device, make_episode
+    cfg = CONFIGS["cfg5_coco2voc_mask_fpn"]
+    ep = episode_to_device(make_episode(cfg, seed=1), dev())
+    feats, det = ep["qry"][:4], ep["det_rois"]
+    scales = [1 / s for s in cfg.strides]
+    D, Cc = det.shape[0], cfg.channels
+    vec = torch.randn(D, Cc, device=dev())
+    fused = ops.roi_align_multilevel(feats, det, scales, 14, 0, True, chan_scale=vec, out_format="nhwc")
+    plain = ops.roi_align_multilevel(feats, det, scales, 14, 0, True, out_format="nhwc")
+    two_step = ops.channel_attention(plain, vec.view(D, 1, Cc, 1, 1))
+    assert fused.shape == (D, Cc, 14, 14)
+    assert torch.equal(fused, two_step)
+    for b in (0, 9, 15):
+        sel = det[:, 0] == b
+        rois_b = det[sel].clone()
+        rois_b[:, 0] = 0
+        one = ops.roi_align_multilevel([f[b:b + 1] for f in feats], rois_b, scales, 14, 0, True, out_format="nhwc")
+        assert torch.equal(one, plain[sel])
+    lv = ops.map_roi_levels(det, 4)
+    assert torch.equal(lv.cpu(), O.map_roi_levels_c(det.cpu(), 4))
+
+
 def test_empty_proposals():
     from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
     cfg = CONFIGS["tiny_fpn"]
