@@ -10,9 +10,10 @@ for M, N, K in shapes:
     a = [torch.randn(M, K, generator=g).to(dev) for _ in range(4)]
     w = (torch.randn(N, 2 * K, generator=g) * (1.0 / K) ** 0.5).to(dev)
     want = (a[0].double() @ w[:, :K].double().t()).float()
-    for bk in (32, 16):
-        for prec in ("fp32", "tf32"):
+    for bk, pair in ((32, 0), (16, 0), (16, 1)):
+        for prec in ("fp32",) if pair else ("fp32", "tf32"):
             os.environ["FGN_GEMM_BK"] = str(bk)
+            os.environ["FGN_GEMM_PAIR"] = str(pair)
             got = ops.gemm_nt(a[0], w[:, :K], None, prec)
             err = float((got - want).abs().max())
             for _ in range(3):
@@ -29,5 +30,5 @@ for M, N, K in shapes:
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (reps * len(a))
             flops = 2.0 * M * N * K * (3 if prec == "fp32" else 1)
-            print(json.dumps({"M": M, "N": N, "K": K, "bk": bk, "precision": prec, "us": round(us, 1),
+            print(json.dumps({"M": M, "N": N, "K": K, "bk": bk, "pair": pair, "precision": prec, "us": round(us, 1),
                               "tensor_tflops": round(flops / us / 1e6, 1), "max_abs_err": err}), flush=True)
