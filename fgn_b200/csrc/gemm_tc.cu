@@ -36,7 +36,7 @@ struct TcSmem {
     static constexpr int kA = TC_BM * BK * 4;               // 16 / 8 KB
     static constexpr int kB = TC_BN_MAX * BK * 4;           // 32 / 16 KB
     static constexpr int kStage = 2 * kA + 2 * kB;          // 96 / 48 KB
-    static constexpr int kTotal = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kTotal = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue tiles*/;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +109,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
+}
+
+// Epilogue store of one 32-row x 32-column accumulator chunk held row-per-lane (tcgen05.ld 32x32b.x32).
+// Storing it straight from registers makes every warp-wide 128-bit store touch 32 different rows
+// (32 half-written sectors); that alone bounded the K=256 contraction (epilogue ~12 us per tile vs
+// 6.3 us of MMAs).  The chunk is transposed through a padded shared-memory tile instead, and each
+// store instruction then writes 4 complete 128-byte row segments.
+constexpr int kEpiPitch = 36;                                  // floats per staged row: 16-byte aligned, conflict-free
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;              // four epilogue warps
+
+__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile, int lane, int row0, int M,
+                                            int col0, int N, const float *__restrict__ bias,
+                                            float *__restrict__ C, int ldc)
+{
+    float4 *mine = reinterpret_cast<float4 *>(tile + lane * kEpiPitch);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        mine[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    __syncwarp();
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const bool col_ok = col0 + c4 < N;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr && col_ok) b = ldg4(bias + col0 + c4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        float4 o = *reinterpret_cast<const float4 *>(tile + rr * kEpiPitch + c4);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        if (row0 + rr < M && col_ok) *reinterpret_cast<float4 *>(C + (size_t)(row0 + rr) * ldc + col0 + c4) = o;
+    }
+    __syncwarp();
 }
 
 // B [N,K] -> B_hi, B_lo (the TF32 split of the weights; tiny, once per call)
@@ -255,6 +287,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias) -> global =================================
         const int ew = warp - 4;                                              // TMEM lanes 32*ew .. +31
+        float *epi_tile = reinterpret_cast<float *>(smem + TC_STAGES * Sm::kStage + 256) + ew * 32 * kEpiPitch;
         int local_tile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
             const int a = local_tile & 1;
@@ -267,22 +300,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-                    float *dst = C + (size_t)row * ldc + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (n0 + c0 + j < N) {
-                            float4 o;
-                            o.x = __uint_as_float(r[j]);     o.y = __uint_as_float(r[j + 1]);
-                            o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-                            if (bias != nullptr) {
-                                const float4 b = ldg4(bias + n0 + c0 + j);
-                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                            }
-                            *reinterpret_cast<float4 *>(dst + j) = o;
-                        }
-                    }
-                }
+                store_chunk(r, epi_tile, lane, m0 + ew * 32, M, n0 + c0, N, bias, C, ldc);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             tc_mbar_arrive(&tmem_empty[a]);
@@ -308,7 +326,7 @@ struct TcPairSmem {
     static constexpr int kA = TC_BM * kBK * 4;              // 8 KB
     static constexpr int kB = TC_BN_MAX * kBK * 4;          // 16 KB
     static constexpr int kStage = 4 * kA + 2 * kB;          // 64 KB
-    static constexpr int kTotal = kStages * kStage + 1024 + 256;
+    static constexpr int kTotal = kStages * kStage + 1024 + 256 + 4 * 32 * 36 * 4;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -425,6 +443,7 @@ gemm_tf32_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;
+        float *epi_tile = reinterpret_cast<float *>(smem + ST * Sm::kStage + 256) + ew * 32 * kEpiPitch;
         int local = 0;
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++local) {
             const int m0 = (pair / n_tiles) * 2 * TC_BM, n0 = (pair % n_tiles) * BN;
@@ -438,22 +457,7 @@ gemm_tf32_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     uint32_t r[32];
                     tmem_ld32(taddr + (uint32_t)c0, r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row < M) {
-                        float *dst = C + (size_t)row * ldc + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (n0 + c0 + j < N) {
-                                float4 o;
-                                o.x = __uint_as_float(r[j]);     o.y = __uint_as_float(r[j + 1]);
-                                o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-                                if (bias != nullptr) {
-                                    const float4 b = ldg4(bias + n0 + c0 + j);
-                                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                                }
-                                *reinterpret_cast<float4 *>(dst + j) = o;
-                            }
-                        }
-                    }
+                    store_chunk(r, epi_tile, lane, m0 + t * TC_BM + ew * 32, M, n0 + c0, N, bias, C, ldc);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -463,6 +467,171 @@ gemm_tf32_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ---- cluster variant: a CTA pair shares every B stage through TMA multicast ------------------------
+// At M=128 rows per tile the 3xTF32 contraction needs 640 KB of operands per 12.3k tensor-pipe cycles
+// -- more than the L2 can feed all 148 SMs (measured: tensor pipe 49% busy, the rest waiting on
+// operands).  Two CTAs of a cluster work on neighbouring row tiles of the same column tile; each
+// loads its own A tile and HALF of the B stage, multicast into both CTAs' shared memory
+// (cp.async.bulk.tensor ... .multicast::cluster), so B costs one L2 read per pair.  A stage is free
+// when BOTH CTAs' MMAs retired it: tcgen05.commit ... .multicast::cluster arrives on both empty barriers.
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_tc_mc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
+                       float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    using Sm = TcSmem<BK>;
+    constexpr int ST = Sm::kStages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ST * Sm::kStage);
+    uint64_t *full_bar = bars, *conv_bar = bars + ST, *empty_bar = bars + 2 * ST;
+    uint64_t *tmem_full = bars + 3 * ST, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = (N + BN - 1) / BN;
+    const int m_pairs = (m_tiles + 1) / 2;
+    const int num_pairs = m_pairs * n_tiles, num_kb = K / BK;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int half_rows = BN / 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) {
+            tc_mbar_init(&full_bar[s], 1);
+            tc_mbar_init(&conv_bar[s], 4);
+            tc_mbar_init(&empty_bar[s], 2);                // both CTAs of the pair retire the stage
+        }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");     // peer's barriers are initialised
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+                const int m0 = (2 * (pair / n_tiles) + (int)rank) * TC_BM, n0 = (pair % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % ST;
+                    tc_mbar_wait(&empty_bar[s], ((it / ST) & 1) ^ 1);
+                    unsigned char *st = smem + (size_t)s * Sm::kStage;
+                    tc_mbar_expect_tx(&full_bar[s], (uint32_t)(TC_BM * BK * 4 + 2 * BN * BK * 4));
+                    tma_load_2d(st, &map_a, kb * BK, m0, &full_bar[s]);
+                    const size_t hoff = (size_t)rank * half_rows * BK * 4;     // my half of the B rows, in both CTAs
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                                 " [%0], [%1, {%3, %4}], [%2], %5;"
+                                 ::"r"(s_u32(st + 2 * Sm::kA + hoff)), "l"(&map_bhi), "r"(s_u32(&full_bar[s])),
+                                   "r"(kb * BK), "r"(n0 + (int)rank * half_rows), "h"((unsigned short)3) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                                 " [%0], [%1, {%3, %4}], [%2], %5;"
+                                 ::"r"(s_u32(st + 2 * Sm::kA + Sm::kB + hoff)), "l"(&map_blo), "r"(s_u32(&full_bar[s])),
+                                   "r"(kb * BK), "r"(n0 + (int)rank * half_rows), "h"((unsigned short)3) : "memory");
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int it = 0, local_tile = 0;
+        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++local_tile) {
+            const int a = local_tile & 1;
+            tc_mbar_wait(&tmem_empty[a], ((local_tile >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(a * TC_BN_MAX);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % ST;
+                const uint32_t par = (it / ST) & 1;
+                tc_mbar_wait(&full_bar[s], par);
+                tc_mbar_wait(&conv_bar[s], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t st = s_u32(smem + (size_t)s * Sm::kStage);
+                    const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + Sm::kA);
+                    const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * Sm::kA), b_lo = umma_desc_kmajor<BK>(st + 2 * Sm::kA + Sm::kB);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+                        umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                        umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(s_u32(&empty_bar[s])), "h"((unsigned short)3) : "memory");
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        const int tid = threadIdx.x - 256;
+        int it = 0;
+        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % ST;
+                tc_mbar_wait(&full_bar[s], (it / ST) & 1);
+                float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage);
+                float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage + Sm::kA);
+#pragma unroll
+                for (int j = 0; j < Sm::kA / 16 / 128; ++j) {
+                    const int i = j * 128 + tid;
+                    const float4 x = hi[i];
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    hi[i] = h;
+                    lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&conv_bar[s]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        float *epi_tile = reinterpret_cast<float *>(smem + ST * Sm::kStage + 256) + ew * 32 * kEpiPitch;
+        int local_tile = 0;
+        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++local_tile) {
+            const int a = local_tile & 1;
+            const int m0 = (2 * (pair / n_tiles) + (int)rank) * TC_BM, n0 = (pair % n_tiles) * BN;
+            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + ew * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                store_chunk(r, epi_tile, lane, m0 + ew * 32, M, n0 + c0, N, bias, C, ldc);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&tmem_empty[a]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // neither CTA may leave while the peer can still multicast into it or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -554,6 +723,27 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
         }
         const int pairs = ceil_div(m_tiles, 2) * n_tiles;
         gemm_tf32_tc_pair_kernel<<<min(sm_count, pairs), TC_THREADS, TcPairSmem::kTotal, st>>>(pa, pbh, pbl, bias, C, ldc, M, N, K, BN);
+        FGN_LAUNCH_OK();
+        *taken = true;
+        return FGN_OK;
+    }
+    // CTA-pair multicast of the B stages: FGN_GEMM_MC=1
+    const char *emc = getenv("FGN_GEMM_MC");
+    const bool want_mc = emc != nullptr && atoi(emc) != 0;   // measured equal to the plain kernel (44 us): opt-in
+    if (passes == 3 && want_mc && m_tiles >= 2 && (BN % 16) == 0 && sm_count >= 2) {
+        static bool mc_attr = false;
+        if (!mc_attr) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_mc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16>::kTotal));
+            mc_attr = true;
+        }
+        CUtensorMap pa, pbh, pbl;
+        if (!make_map(&pa, A, M, K, lda, TC_BM, 16) || !make_map(&pbh, bhi, N, K, K, BN / 2, 16) || !make_map(&pbl, blo, N, K, K, BN / 2, 16)) {
+            set_error("cuTensorMapEncodeTiled unavailable or failed");
+            return FGN_ERR_CUDA;
+        }
+        const int pairs = ceil_div(m_tiles, 2) * n_tiles;
+        const int clusters = min(sm_count / 2, pairs);
+        gemm_tf32_tc_mc_kernel<16><<<2 * clusters, TC_THREADS, TcSmem<16>::kTotal, st>>>(pa, pbh, pbl, bias, C, ldc, M, N, K, BN);
         FGN_LAUNCH_OK();
         *taken = true;
         return FGN_OK;
