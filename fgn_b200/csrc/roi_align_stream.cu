@@ -131,8 +131,10 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
                         float *__restrict__ out, const int out_layout, int32_t *__restrict__ lvl_out,
-                        const int wx_cap, const int wyd_rows, const int size_classes)
+                        const int wx_cap, const int wyd_rows, const int size_classes, const int debug_mode)
 {
+    // debug_mode (development only): 1 = skip the copies (consumers run on stale shared memory),
+    //                                2 = skip the consumer arithmetic (copies + pipeline only)
     constexpr int CB  = 128 * VEC * WS;
     constexpr int NCW = P * WS;                     // consumer warps
     constexpr int PP8 = (P + 3) & ~3;               // bin-row weights of one footprint row, padded
@@ -191,6 +193,7 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 const int nr = min(wp.rps, wp.nrows - row0);
                 mbar_wait(&empty_bar[s], par);
                 float *dst = ring + (size_t)s * kStageCells * CB;
+                if (debug_mode == 1) { if (lane == 0) mbar_arrive(&full_bar[s]); row0 += nr; if (++s == NS) { s = 0; par ^= 1; } continue; }
                 if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * wp.ncols * cbn * 4));
                 __syncwarp();
                 if (contiguous) {
@@ -311,6 +314,7 @@ roi_align_stream_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 mbar_wait(&full_bar[s], par);
                 const float *base = ring + (size_t)s * kStageCells * CB + (size_t)xlo * cstride;
                 for (int rr = 0; rr < nr; ++rr, ++row) {
+                    if (debug_mode == 2) continue;
                     const float *cp = base + rr * rstride;
 #pragma unroll 2
                     for (int i = 0; i < nx; ++i, cp += cstride) {
@@ -945,9 +949,11 @@ static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, 
     // default 1: the 3-class order shortens the kernel alone by ~3% but its retiring CTAs cost more than that
     // when several episodes overlap on the GPU (bench.py); FGN_RA_CLASSES=3 turns it on
     const int size_classes = e != nullptr ? max(1, min(3, atoi(e))) : 1;
+    const char *ed = getenv("FGN_RA_DEBUG");
+    const int dbg = ed != nullptr ? atoi(ed) : 0;
     kern<<<R * nblk * size_classes, (P * WS + 1) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
                                                                     chan_scale, scale_index, out, out_layout, lvl_out,
-                                                                    wx_cap, wyd_rows, size_classes);
+                                                                    wx_cap, wyd_rows, size_classes, dbg);
     FGN_LAUNCH_OK();
     *taken = true;
     return FGN_OK;

@@ -150,40 +150,54 @@ support_pool_kernel(const float *__restrict__ f, const int f_layout, const float
     if (lane == 0) masked_gap[(size_t)bn * C + c] = gap / (float)(K * PP);
 }
 
-// NHWC variant: one thread per (bn, 4 channels); coalesced 128-bit loads across channels.
-__global__ void __launch_bounds__(128)
+// NHWC variant: one CTA per (bn): threads = (C/4 channel vectors) x (cell groups); each thread walks
+// its cells with coalesced 128-bit loads, the masked GAP is reduced over the cell groups in shared
+// memory in a fixed order.
+__global__ void __launch_bounds__(256)
 support_pool_nhwc_kernel(const float *__restrict__ f, const float *__restrict__ m, const int BN,
                          const int K, const int C, const int PP, float *__restrict__ cat_mean,
                          const int out_layout, float *__restrict__ masked_gap)
 {
+    extern __shared__ __align__(16) float red[];          // [groups][C]
+    const int bn = blockIdx.x;
     const int c4 = C >> 2;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= BN * c4) return;
-    const int bn = idx / c4, c = (idx % c4) * 4;
+    const int lanes = min(c4, (int)blockDim.x);            // channel vectors handled per pass
+    const int groups = max(1, (int)blockDim.x / lanes);
+    const int cvl = threadIdx.x % lanes, pg = threadIdx.x / lanes;
     const float invK = 1.0f / (float)K;
-    float4 gap = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < PP; ++p) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < K; ++k) {
-            const size_t img = (size_t)bn * K + k;
-            const float4 v = ldg4(f + (img * PP + p) * C + c);
-            const float mv = __ldg(m + img * PP + p);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            fma4(gap, mv, v);
-        }
-        if (K != 1) { s.x *= invK; s.y *= invK; s.z *= invK; s.w *= invK; }
-        if (out_layout == FGN_LAYOUT_NHWC) {
-            *reinterpret_cast<float4 *>(cat_mean + ((size_t)bn * PP + p) * C + c) = s;
-        } else {
-            cat_mean[((size_t)bn * C + c + 0) * PP + p] = s.x;
-            cat_mean[((size_t)bn * C + c + 1) * PP + p] = s.y;
-            cat_mean[((size_t)bn * C + c + 2) * PP + p] = s.z;
-            cat_mean[((size_t)bn * C + c + 3) * PP + p] = s.w;
+    for (int cv = cvl; cv < c4; cv += lanes) {
+        const int c = cv * 4;
+        float4 gap = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pg < groups) {
+            for (int p = pg; p < PP; p += groups) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < K; ++k) {
+                    const size_t img = (size_t)bn * K + k;
+                    const float4 v = ldg4(f + (img * PP + p) * C + c);
+                    const float mv = __ldg(m + img * PP + p);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    fma4(gap, mv, v);
+                }
+                if (K != 1) { s.x *= invK; s.y *= invK; s.z *= invK; s.w *= invK; }
+                if (out_layout == FGN_LAYOUT_NHWC) {
+                    *reinterpret_cast<float4 *>(cat_mean + ((size_t)bn * PP + p) * C + c) = s;
+                } else {
+                    cat_mean[((size_t)bn * C + c + 0) * PP + p] = s.x;
+                    cat_mean[((size_t)bn * C + c + 1) * PP + p] = s.y;
+                    cat_mean[((size_t)bn * C + c + 2) * PP + p] = s.z;
+                    cat_mean[((size_t)bn * C + c + 3) * PP + p] = s.w;
+                }
+            }
+            *reinterpret_cast<float4 *>(red + (size_t)pg * C + c) = gap;
         }
     }
+    __syncthreads();
     const float d = (float)(K * PP);
-    float4 o = make_float4(gap.x / d, gap.y / d, gap.z / d, gap.w / d);
-    *reinterpret_cast<float4 *>(masked_gap + (size_t)bn * C + c) = o;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < groups; ++g) s += red[(size_t)g * C + c];
+        masked_gap[(size_t)bn * C + c] = s / d;
+    }
 }
 
 // ---- K6: AG-RPN class attention vector (fgn_ag_rpn_head.py:37-41) ----------------------------
@@ -295,9 +309,10 @@ extern "C" int fgn_support_pool(const float *f, int f_layout, const float *m, in
     FGN_CHECK_ARG(f && m && cat_mean && masked_gap, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (f_layout == FGN_LAYOUT_NHWC && (C & 3) == 0) {
-        const int n = BN * (C >> 2);
-        support_pool_nhwc_kernel<<<ceil_div(n, 128), 128, 0, st>>>(f, m, BN, K, C, P * P, cat_mean,
-                                                                   out_layout, masked_gap);
+        const int c4 = C >> 2, lanes = min(c4, 256), groups = max(1, 256 / lanes);
+        const size_t smem = (size_t)groups * C * 4;
+        if (smem > 48 * 1024) { set_error("support_pool: C=%d too large for the NHWC kernel", C); return FGN_ERR_UNSUPPORTED; }
+        support_pool_nhwc_kernel<<<BN, 256, smem, st>>>(f, m, BN, K, C, P * P, cat_mean, out_layout, masked_gap);
     } else {
         const long warps = (long)BN * C;
         support_pool_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(
