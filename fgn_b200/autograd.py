@@ -1,0 +1,151 @@
+"""autograd.Function wrappers: forward = the C-ABI forward kernels, backward = the hand-written adjoint
+kernels of fgn_b200/csrc/backward.cu.  The guided heads call the functions
+at the bottom of this file; they fall through to the plain ``ops`` when no input requires grad.
+
+The reference gets these gradients from autograd over mmcv / torchvision / ATen ops
+(fgn_roi_head.py:344-358,451-529, fgn_ag_rpn_head.py:58-79).  Feature tensors travel channels_last.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from ._lib import LAYOUT_NHWC, FgnError, Pyramid
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    """channels_last fp32 view/copy of a logical-NCHW tensor."""
+    t = t.float() if t.dtype != torch.float32 else t
+    return t if ops.storage_layout(t) == LAYOUT_NHWC else ops.to_nhwc(t.contiguous() if ops.storage_layout(t) is None else t)
+
+
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+class _RoIAlignML(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, scales, output_size, sampling_ratio, aligned, finest_scale, *feats):
+        feats = [_cl(f) for f in feats]
+        out = ops.roi_align_multilevel(feats, rois, scales, output_size, sampling_ratio, aligned, finest_scale,
+                                       out_format="nhwc")
+        ctx.save_for_backward(rois)
+        ctx.meta = (tuple(scales), int(output_size), int(sampling_ratio), bool(aligned), float(finest_scale),
+                    [tuple(f.shape) for f in feats])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        scales, p, sr, aligned, finest, shapes = ctx.meta
+        g = _cl(g)
+        b, c = shapes[0][:2]
+        grads = [torch.zeros((s[0], s[2], s[3], s[1]), device=g.device, dtype=torch.float32).permute(0, 3, 1, 2)
+                 for s in shapes]
+        pyr = Pyramid()
+        pyr.num_levels = len(shapes)
+        for i, (gr, s) in enumerate(zip(grads, shapes)):
+            pyr.feat[i], pyr.H[i], pyr.W[i], pyr.spatial_scale[i] = gr.data_ptr(), s[2], s[3], float(scales[i])
+        r = rois.shape[0]
+        _lib.check(_lib.load().fgn_roi_align_ml_bwd(ctypes.byref(pyr), b, c, rois.contiguous().data_ptr(), r, p, sr,
+                                                    int(aligned), finest, None, None, g.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "fgn_roi_align_ml_bwd")
+        return (None,) * 6 + tuple(grads)
+
+
+class _ChannelAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qry, vec):
+        q = _cl(qry)
+        ctx.save_for_backward(q, vec)
+        return ops.channel_attention(q, vec)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, vec = ctx.saved_tensors
+        g = _cl(g)
+        b, c, h, w = q.shape
+        n = vec.shape[1]
+        v = vec.reshape(b * n, c).contiguous()
+        lib = _lib.load()
+        need_q, need_v = ctx.needs_input_grad
+        gq = torch.empty((b, h, w, c), device=g.device, dtype=torch.float32).permute(0, 3, 1, 2) if need_q else None
+        gv = torch.empty((b * n, c), device=g.device, dtype=torch.float32) if need_v else None
+        wsb = lib.fgn_channel_attention_bwd_workspace_bytes(b, n, c, h, w) if need_v else 0
+        ws = torch.empty((max(wsb, 1),), device=g.device, dtype=torch.uint8)
+        _lib.check(lib.fgn_channel_attention_bwd(q.data_ptr(), v.data_ptr(), g.data_ptr(), b, n, c, h, w,
+                                                 None if gq is None else gq.data_ptr(),
+                                                 None if gv is None else gv.data_ptr(), ws.data_ptr(), wsb,
+                                                 torch.cuda.current_stream().cuda_stream), "fgn_channel_attention_bwd")
+        return gq, None if gv is None else gv.view_as(vec)
+
+
+class _AttentionVectors(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spp, n_ways, k_shots):
+        x = _cl(spp)
+        ctx.meta = (tuple(x.shape), int(n_ways), int(k_shots))
+        return ops.attention_vectors(x, n_ways, k_shots)
+
+    @staticmethod
+    def backward(ctx, g):
+        (bnk, c, h, w), n, k = ctx.meta
+        bn = bnk // k
+        gv = g.reshape(bn, c).contiguous().float()
+        out = torch.empty((bnk, h, w, c), device=g.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        _lib.check(_lib.load().fgn_attention_vectors_bwd(gv.data_ptr(), bn, k, c, h, w, out.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream), "fgn_attention_vectors_bwd")
+        return out, None, None
+
+
+class _SupportPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, m, n_ways, k_shots):
+        x = _cl(f)
+        mm = m.reshape(x.shape[0], -1).contiguous().float()
+        ctx.save_for_backward(mm)
+        ctx.meta = (tuple(x.shape), int(n_ways), int(k_shots))
+        cat, gap = ops.support_pool(x, mm, n_ways, k_shots, out_format="nhwc")
+        return cat, gap
+
+    @staticmethod
+    def backward(ctx, g_cat, g_gap):
+        (mm,) = ctx.saved_tensors
+        (bnk, c, p, _), n, k = ctx.meta
+        bn = bnk // k
+        gc = _cl(g_cat.reshape(bn, c, p, p)) if g_cat is not None else None
+        gg = g_gap.reshape(bn, c).contiguous().float() if g_gap is not None else None
+        out = torch.empty((bnk, p, p, c), device=mm.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        _lib.check(_lib.load().fgn_support_pool_bwd(None if gc is None else gc.data_ptr(), None if gg is None else gg.data_ptr(),
+                                                    mm.data_ptr(), bn, k, c, p, out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "fgn_support_pool_bwd")
+        return out, None, None, None
+
+
+# ---- what the heads call ---------------------------------------------------------------------------
+def roi_align_multilevel(feats: Sequence[torch.Tensor], rois, scales, output_size=7, sampling_ratio=0, aligned=True,
+                         finest_scale=56.0, **kw):
+    """ops.roi_align_multilevel, differentiable w.r.t. the feature maps when they require grad."""
+    if _needs_grad(*feats):
+        if kw.get("chan_scale") is not None:
+            raise FgnError("fused chan_scale has no adjoint: use roi_align_multilevel + channel_attention under autograd")
+        out = _RoIAlignML.apply(rois, list(scales), output_size, sampling_ratio, aligned, finest_scale, *feats)
+        return (out, ops.map_roi_levels(rois, len(feats), finest_scale)) if kw.get("return_levels") else out
+    return ops.roi_align_multilevel(feats, rois, scales, output_size, sampling_ratio, aligned, finest_scale, **kw)
+
+
+def channel_attention(qry: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    return _ChannelAttention.apply(qry, vec) if _needs_grad(qry, vec) else ops.channel_attention(qry, vec)
+
+
+def attention_vectors(spp: torch.Tensor, n_ways: int, k_shots: int) -> torch.Tensor:
+    return _AttentionVectors.apply(spp, n_ways, k_shots) if _needs_grad(spp) else ops.attention_vectors(spp, n_ways, k_shots)
+
+
+def support_pool(f: torch.Tensor, m: torch.Tensor, n_ways: int, k_shots: int, out_format: Optional[str] = None):
+    if _needs_grad(f):
+        return _SupportPool.apply(f, m, n_ways, k_shots)
+    return ops.support_pool(f, m, n_ways, k_shots, out_format)

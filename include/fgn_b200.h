@@ -216,6 +216,30 @@ int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C, const 
                                   float *cls_out, float *reg_out, int32_t *lvl_out,
                                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- gradients (what the training configs need under autograd) ----------
+ * All feature tensors NHWC fp32.  The reference obtains these through autograd over mmcv /
+ * torchvision / ATen ops (fgn_roi_head.py:344-358,451-529). */
+
+/* Adjoint of fgn_roi_align_ml_fwd w.r.t. the feature maps: grad_pyr->feat[l] is the gradient buffer of
+ * level l ([B,H_l,W_l,C], zero-initialised or holding a running sum: the kernel accumulates with
+ * vector atomics); grad_out [R,P,P,C].  Same level assignment / sample indices as the forward. */
+int fgn_roi_align_ml_bwd(const fgn_pyramid_t *grad_pyr, int B, int C, const float *rois, int R, int P,
+                         int sampling_ratio, int aligned, float finest_scale,
+                         const float *chan_scale, const int32_t *scale_index,
+                         const float *grad_out, void *stream);
+/* Adjoint of fgn_channel_attention: grad_qry [B,H,W,C] = sum_n g*vec, grad_vec [B*N,C] = sum_hw g*qry;
+ * either output may be NULL. */
+size_t fgn_channel_attention_bwd_workspace_bytes(int B, int N, int C, int H, int W);
+int fgn_channel_attention_bwd(const float *qry, const float *vec, const float *grad_out, int B, int N, int C,
+                              int H, int W, float *grad_qry, float *grad_vec, void *workspace,
+                              size_t workspace_bytes, void *stream);
+/* Adjoint of fgn_attention_vectors: grad_spp [B*N*K,H,W,C] = grad_vec / (K*H*W). */
+int fgn_attention_vectors_bwd(const float *grad_vec, int BN, int K, int C, int H, int W, float *grad_spp, void *stream);
+/* Adjoint of fgn_support_pool: grad_f [B*N*K,P,P,C] = grad_cat/K + grad_gap*m/(K*P*P); grad_cat [B*N,P,P,C]
+ * and grad_gap [B*N,C] may each be NULL. */
+int fgn_support_pool_bwd(const float *grad_cat, const float *grad_gap, const float *m, int BN, int K, int C, int P,
+                         float *grad_f, void *stream);
+
 /* Number of kernels this library has launched in the calling process since load
  * (bench.py's gpu_launches). */
 uint64_t fgn_launch_count(void);
