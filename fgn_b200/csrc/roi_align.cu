@@ -387,6 +387,12 @@ int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *ro
                                  const int32_t *scale_index, void *out, int out_is_bf16, int32_t *lvl_out,
                                  cudaStream_t st);
 
+int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                            int aligned, float finest_scale, const float *chan_scale,
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                            int ns_pref, bool *taken);
+unsigned int roi_align_window_violations();
+
 }  // namespace fgn
 
 using namespace fgn;
@@ -423,15 +429,24 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
     const Pyramid d = to_device_pyramid(pyr);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && env_int("FGN_RA_IMPL", 2) >= 2) {
+    // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
+    // 3 / 2 = row-streaming kernel with / without its older persistent variant, 1 = bin-centric, 0 = direct
+    const int impl = env_int("FGN_RA_IMPL", 4);
+    if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4) {
+        bool taken = false;
+        rc = launch_roi_align_window(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                     scale_index, out, lvl_out, st, env_int("FGN_RA_NS", 0), &taken);
+        if (rc || taken) return rc;
+    }
+    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 2) {
         bool taken = false;
         rc = launch_roi_align_stream(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                      scale_index, out, out_layout, lvl_out, st,
-                                     env_int("FGN_RA_IMPL", 2) == 2 ? -env_int("FGN_RA_VEC", 2) : env_int("FGN_RA_VEC", 2),
+                                     impl == 3 ? env_int("FGN_RA_VEC", 2) : -env_int("FGN_RA_VEC", 2),
                                      env_int("FGN_RA_NS", 0), &taken);
         if (rc || taken) return rc;
     }
-    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0) {
+    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 1) {
         if (P == 7)  return launch_sep<7>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
                                           chan_scale, scale_index, out, out_layout, lvl_out, st);
         if (P == 14) return launch_sep<14>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
@@ -444,6 +459,13 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
                                                     out, out_layout, lvl_out);
     FGN_LAUNCH_OK();
     return FGN_OK;
+}
+
+// Planner self-check of the rotating-window kernel (test/debug export): number of (row, bin) weights
+// that fell outside the register window since the library was loaded.  Must be 0.
+extern "C" unsigned int fgn_debug_roi_window_violations(void)
+{
+    return roi_align_window_violations();
 }
 
 // Same entry, forcing the direct kernel (exported for the in-library cross-check in tests).

@@ -1,0 +1,530 @@
+// roi_align_window.cu -- persistent, planner-fed, rotating-window multi-level RoIAlign (sm_100a).
+//
+// Same separable formulation and exact coordinate arithmetic as roi_align_stream.cu
+//   out[ph,pw] = 1/count * sum_y Ay[ph][y] * sum_x Ax[pw][x] * v[y,x]
+// reorganised so that the SMs spend their issue slots on the row pass and nothing else:
+//
+//   * PERSISTENT CTAs (2 per SM at P=7) pull work items from a ticket counter.  An item is
+//     (RoI, chunk of bin rows, channel block); almost every RoI is a single item.
+//   * a PLANNER warp works ahead of everyone else: it takes the ticket, assigns the FPN level,
+//     evaluates the reference coordinate arithmetic once per (axis, bin, sample) and leaves the
+//     footprint, ring schedule and weight tables in a double-buffered shared-memory slot.  The
+//     per-RoI prologue is therefore off the critical path of the copy and the math.
+//   * a PRODUCER warp streams the footprint rows NHWC -> shared-memory ring with bulk async copies
+//     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); the ring keeps running across items.
+//   * P CONSUMER warps (warp = bin column) do the row pass out of shared memory with 128-bit loads
+//     at compile-time offsets, then fold the row into a WINDOW of kWin bin rows held in registers.
+//     Footprint rows are visited top to bottom and the set of bin rows a footprint row touches is a
+//     contiguous range whose first member never decreases, so the window only ever slides down:
+//     when the row passes the last row of the window's first bin, that bin is scaled by 1/count
+//     (and the AG-FCN channel attention) and stored, and the window rotates.  The accumulators of
+//     one RoI shrink from P to kWin rows of registers, the fold loses its P compare-and-branch
+//     pairs, and the output stores are spread over the item instead of bursting at its end.
+//   * a footprint row can touch more than kWin bin rows only when a bin is shorter than 2/3 of a
+//     cell ((dph - 1 + 1/g) * bin_h < 2); such RoIs (and very large ones, to shorten the tail) are
+//     planned as ceil(P / kWin) items of kWin bin rows each, for which the bound holds trivially.
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace fgn {
+
+namespace {
+
+constexpr int kWin        = 4;      // bin rows held in registers per consumer warp
+constexpr int kStageCells = 32;     // cells (of CB channels) per ring stage
+constexpr unsigned kTicketSlots = 1024;
+
+__device__ unsigned int g_window_ticket[kTicketSlots];
+__device__ unsigned int g_window_violation;           // planner self-check (must stay 0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int N> struct IntTag { static constexpr int value = N; };
+
+// packed fp32 FMA / MUL (Blackwell FFMA2 / FMUL2: two IEEE fp32 results per lane per issue slot)
+__device__ __forceinline__ void fma4x2(float4 &a, const float w, const float4 v)
+{
+    unsigned long long a0, a1, v0, v1, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v0) : "f"(v.x), "f"(v.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v1) : "f"(v.z), "f"(v.w));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(ww), "l"(v0));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(ww), "l"(v1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.z), "=f"(a.w) : "l"(a1));
+}
+__device__ __forceinline__ float4 mul4x2(const float w, const float4 v)
+{
+    unsigned long long r0, r1, v0, v1, ww;
+    float4 o;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v0) : "f"(v.x), "f"(v.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v1) : "f"(v.z), "f"(v.w));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r0) : "l"(ww), "l"(v0));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r1) : "l"(ww), "l"(v1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.z), "=f"(o.w) : "l"(r1));
+    return o;
+}
+
+template <int P>
+struct WinSlot {
+    int   r, cb0, level, batch, H, W;
+    int   pa, pb;                                  // bin rows [pa, pb) of this item
+    float count;
+    int   X0, Y0, ncols, nrows, nseg, rps, nstages;
+    int   xlo[P], xn[P], xoff[P];
+    int   hi[P + 1];                               // last footprint row (relative to Y0) of bins <= ph
+};
+
+}  // namespace
+
+// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
+// Dynamic shared memory: ring[NS][kStageCells*CB] | 2 x { wx[wx_cap] | wrow[wyd_rows] float4 }
+template <int P, int VEC, int NS, int MINB>
+__global__ void __launch_bounds__((P + 2) * 32, MINB)
+roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
+                        const int sampling_ratio, const int aligned, const float finest_scale,
+                        const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
+                        float *__restrict__ out, int32_t *__restrict__ lvl_out,
+                        const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells)
+{
+    constexpr int CB = 128 * VEC;                   // channels per item; cell stride in the ring
+    constexpr int S  = (P + kWin - 1) / kWin;       // bin-row chunks of a split RoI
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ WinSlot<P> slot[2];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[2], plan_empty[2];
+
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    float *wtab = ring + (size_t)NS * kStageCells * CB;
+    const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
+
+    const int nblk  = (C + CB - 1) / CB;
+    const int items = R * S * nblk;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (t == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&plan_full[b], 1); mbar_init(&plan_empty[b], P + 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == P + 1) {
+        // ===== planner ===================================================================================
+        for (int k = 0;; ++k) {
+            const int b = k & 1;
+            WinSlot<P> &ps = slot[b];
+            float *wx = wtab + (size_t)b * wslot;
+            float *wrow = wx + wx_cap;                                   // [nrows][4]
+            mbar_wait(&plan_empty[b], ((k >> 1) & 1) ^ 1);               // item k-2 fully consumed
+            bool done = false;
+            for (;;) {                                                   // tickets of unused chunks are skipped
+                unsigned int ticket = 0;
+                if (lane == 0) {
+                    ticket = atomicAdd(&g_window_ticket[ticket_slot], 1u);
+                    if (ticket == (unsigned)(items + gridDim.x - 1)) g_window_ticket[ticket_slot] = 0u;   // last of the launch
+                }
+                ticket = __shfl_sync(FULL, ticket, 0);
+                if ((int)ticket >= items) { done = true; break; }
+                const int cbi = (int)ticket % nblk, chunk = ((int)ticket / nblk) % S, r = (int)ticket / (nblk * S);
+                const float *roi = rois + 5 * (size_t)r;
+                const int level = roi_level(roi, pyr, finest_scale);
+                const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
+                const int H = pyr.H[level], W = pyr.W[level];
+                // chunking rule (any rule is correct as long as every planner evaluates the same one):
+                // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row; big footprints are
+                // split to shorten the tail of the launch
+                const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
+                const bool split = S > 1 && (g.bin_h < 0.75f || est > split_cells);
+                if (chunk > 0 && !split) continue;
+                const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
+
+                // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns
+                const int axis = lane / P, p = lane % P;
+                const bool isy = lane < P && p >= pa && p < pb, isx = lane >= P && lane < 2 * P;
+                const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
+                const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
+                int lo = 0x7fffffff, hi = -1;
+                if (isx || isy) {
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { lo = min(lo, sm.low); hi = max(hi, sm.high); }
+                    }
+                }
+                int n = hi >= 0 ? hi - lo + 1 : 0;
+                if (hi < 0) lo = 0;
+                const int big = 0x7fffffff;
+                int X0 = __reduce_min_sync(FULL, (isx && n > 0) ? lo : big);
+                int X1 = __reduce_max_sync(FULL, (isx && n > 0) ? lo + n : -1);
+                int Y0 = __reduce_min_sync(FULL, (isy && n > 0) ? lo : big);
+                int Y1 = __reduce_max_sync(FULL, (isy && n > 0) ? lo + n : -1);
+                const int n4 = (n + 3) & ~3;                            // weight runs start 16 B aligned
+                const int xsum = __reduce_add_sync(FULL, isx ? n4 : 0);
+                if (X1 < 0 || Y1 < 0 || xsum > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; }
+                const int ncols = X1 - X0, nrows = Y1 - Y0;
+                int nseg, rps, nstages;
+                if (ncols <= kStageCells) {
+                    nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
+                } else {
+                    nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
+                }
+                if (ncols == 0 || nrows == 0) nstages = 0;
+
+                int off = 0;                                             // exclusive scan of the padded x runs
+                int him = -1;                                            // running max of the bin rows' last footprint row
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    const int nq = __shfl_sync(FULL, n4, P + q);
+                    if (lane >= P && q < p) off += nq;
+                    const int hq = __shfl_sync(FULL, (isy && n > 0) ? lo + n - 1 - Y0 : -1, q);
+                    if (lane < P && q <= p) him = max(him, hq);
+                }
+                if (lane == 0) {
+                    ps.r = r; ps.cb0 = cbi * CB; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
+                    ps.pa = pa; ps.pb = pb; ps.count = g.count;
+                    ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
+                    ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
+                    if (lvl_out != nullptr && cbi == 0 && chunk == 0) lvl_out[r] = level;
+                }
+                if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
+                if (lane < P) ps.hi[p] = him;
+                for (int i = lane; i < nrows; i += 32)
+                    reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                if (nstages > 0 && n > 0) {
+                    if (isx) {
+                        float *w = wx + off;
+                        for (int i = 0; i < n4; ++i) w[i] = 0.f;
+                        for (int i = 0; i < grid; ++i) {
+                            const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                            if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
+                        }
+                    } else if (isy) {
+                        // footprint row j lives in window slot (p - base_j), base_j = first bin row of the
+                        // item whose (running-max) last row is >= j
+                        auto put = [&](int j, float wgt) {
+                            int base = pa;
+                            for (int q = pa; q < pb; ++q) base += (ps.hi[q] < j) ? 1 : 0;
+                            const int comp = p - base;
+                            if (comp >= 0 && comp < kWin) wrow[4 * j + comp] += wgt;
+                            else atomicAdd(&g_window_violation, 1u);
+                        };
+                        for (int i = 0; i < grid; ++i) {
+                            const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                            if (sm.valid) { put(sm.low - Y0, sm.h); put(sm.high - Y0, sm.l); }
+                        }
+                    }
+                }
+                break;
+            }
+            if (done) {
+                if (lane == 0) { ps.r = -1; ps.nstages = 0; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&plan_full[b]);
+            if (done) break;
+        }
+    } else if (warp == P) {
+        // ===== producer: bulk async copies of footprint rows, ring runs across items =======================
+        int s = 0, par = 1;                                              // parity 1: first pass over a fresh barrier
+        for (int k = 0;; ++k) {
+            const int b = k & 1;
+            mbar_wait(&plan_full[b], (k >> 1) & 1);
+            const WinSlot<P> &ps = slot[b];
+            if (ps.r < 0) break;
+            const int cbn = min(CB, C - ps.cb0);
+            const bool rowcopy = (C == CB);                              // a row segment is one contiguous run
+            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
+            const float *fbase = pyr.feat[ps.level] + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
+                                 + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
+            const size_t row_pitch = (size_t)ps.W * C;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&plan_empty[b]);                  // everything needed is in registers now
+            int row0 = 0, col0 = 0;
+            for (int st = 0; st < nstages; ++st) {
+                int nr, nc;
+                if (nseg == 1) { nr = min(rps, nrows - row0); nc = ncols; }
+                else           { nr = 1; nc = min(kStageCells, ncols - col0); }
+                mbar_wait(&empty_bar[s], par);
+                float *dst = ring + (size_t)s * kStageCells * CB;
+                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * nc * cbn * 4));
+                __syncwarp();
+                const float *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
+                if (rowcopy) {
+                    if (lane < nr)
+                        bulk_g2s(dst + (size_t)lane * nc * CB, src + (size_t)lane * row_pitch,
+                                 (uint32_t)(nc * CB * 4), &full_bar[s]);
+                } else {
+                    for (int cell = lane; cell < nr * nc; cell += 32) {
+                        const int rr = cell / nc, cc = cell - rr * nc;
+                        bulk_g2s(dst + (size_t)cell * CB, src + (size_t)rr * row_pitch + (size_t)cc * C,
+                                 (uint32_t)(cbn * 4), &full_bar[s]);
+                    }
+                }
+                if (nseg == 1) row0 += nr;
+                else { col0 += nc; if (col0 >= ncols) { col0 = 0; ++row0; } }
+                if (++s == NS) { s = 0; par ^= 1; }
+            }
+        }
+    } else {
+        // ===== consumers: warp = bin column pw ==============================================================
+        const int pw = warp;
+        int s = 0, par = 0;
+        for (int k = 0;; ++k) {
+            const int b = k & 1;
+            mbar_wait(&plan_full[b], (k >> 1) & 1);
+            const WinSlot<P> &ps = slot[b];
+            const int r = ps.r;
+            if (r < 0) break;
+            const float *wx = wtab + (size_t)b * wslot;
+            const float4 *wrow = reinterpret_cast<const float4 *>(wx + wx_cap);
+            const int cb0 = ps.cb0, cbn = min(CB, C - cb0);
+            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
+            const int xlo = ps.xlo[pw] - ps.X0, nx = ps.xn[pw];
+            const float *wxp = wx + ps.xoff[pw];
+            const int pb = ps.pb;
+            const float inv = 1.0f / ps.count;          // count is a small exact integer; <= 1 ulp vs acc/count
+            int base = ps.pa;
+            int hi_cur = ps.hi[base];
+            // lane -> channels [4*lane, 4*lane+4) + 128*v of the block.  Lanes past the channel count of a
+            // ragged last block read stale ring bytes (the cell stride is CB) and never store.
+            const int lch = lane * 4;
+            float4 cs[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) cs[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (chan_scale != nullptr) {
+                const int si = scale_index != nullptr ? scale_index[r] : r;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (v * 128 + lch < cbn) cs[v] = ldg4(chan_scale + (size_t)si * C + cb0 + v * 128 + lch);
+            }
+            float *obase = out + ((size_t)r * P * P + pw) * C + cb0 + lch;
+
+            float4 a[kWin][VEC], racc[VEC];
+#pragma unroll
+            for (int q = 0; q < kWin; ++q)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) a[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+            // store bin row `base` (window slot 0) and slide the window down by one
+            auto rotate = [&]() {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float4 q = a[0][v];
+                    float4 o;
+                    if (chan_scale != nullptr)          // (acc * 1/count) * vec, same rounding order as unfused
+                        o = make_float4(q.x * inv * cs[v].x, q.y * inv * cs[v].y, q.z * inv * cs[v].z, q.w * inv * cs[v].w);
+                    else
+                        o = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                    if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(obase + (size_t)base * P * C + v * 128) = o;
+#pragma unroll
+                    for (int w = 0; w + 1 < kWin; ++w) a[w][v] = a[w + 1][v];
+                    a[kWin - 1][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                ++base;
+            };
+            // footprint row j is complete in racc: fold it into the window
+            auto fold = [&](int j) {
+                while (j > hi_cur) { rotate(); hi_cur = base < pb ? ps.hi[base] : 0x7fffffff; }
+                const float4 w4 = wrow[j];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { fma4x2(a[0][v], w4.x, racc[v]); fma4x2(a[1][v], w4.y, racc[v]); }
+                if (w4.z != 0.f || w4.w != 0.f) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { fma4x2(a[2][v], w4.z, racc[v]); fma4x2(a[3][v], w4.w, racc[v]); }
+                }
+            };
+
+            // Row pass, specialised on the number of cells NX this warp's bin column covers (constant over
+            // the item): weights live in registers, every cell is a 128-bit LDS at a compile-time offset
+            // followed by packed FMAs.  NX = 0 is the generic loop (wide bins, segmented rows).
+            auto run = [&](auto nx_tag) {
+                constexpr int NX = decltype(nx_tag)::value;
+                float wreg[NX > 0 ? NX : 1];
+                if (NX > 0) {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) wreg[i] = wxp[i];
+                }
+                if (NX > 0 || nseg == 1) {
+                    int row = 0;
+                    const int rstride = ncols * CB;
+                    for (int st = 0; st < nstages; ++st) {
+                        const int nr = min(rps, nrows - row);
+                        mbar_wait(&full_bar[s], par);
+                        const float *rp = ring + (size_t)s * kStageCells * CB + xlo * CB + lch;
+                        for (int rr = 0; rr < nr; ++rr, ++row, rp += rstride) {
+                            if (NX > 0) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) racc[v] = mul4x2(wreg[0], *reinterpret_cast<const float4 *>(rp + v * 128));
+#pragma unroll
+                                for (int i = 1; i < NX; ++i)
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v)
+                                        fma4x2(racc[v], wreg[i], *reinterpret_cast<const float4 *>(rp + i * CB + v * 128));
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float *cp = rp;
+                                for (int i = 0; i < nx; ++i, cp += CB) {
+                                    const float w = wxp[i];
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(cp + v * 128));
+                                }
+                            }
+                            fold(row);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[s]);
+                        if (++s == NS) { s = 0; par ^= 1; }
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int row = 0; row < nrows; ++row)
+                        for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
+                            const int nc = min(kStageCells, ncols - col0);
+                            mbar_wait(&full_bar[s], par);
+                            const float *sb = ring + (size_t)s * kStageCells * CB + lch;
+                            const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
+                            for (int cx = c_beg; cx < c_end; ++cx) {
+                                const float w = wxp[cx - xlo];
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v)
+                                    fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(sb + (cx - col0) * CB + v * 128));
+                            }
+                            if (col0 + nc >= ncols) {
+                                fold(row);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty_bar[s]);
+                            if (++s == NS) { s = 0; par ^= 1; }
+                        }
+                }
+            };
+            if (nseg == 1) {
+                switch (nx) {
+                case 1: run(IntTag<1>{}); break;
+                case 2: run(IntTag<2>{}); break;
+                case 3: run(IntTag<3>{}); break;
+                case 4: run(IntTag<4>{}); break;
+                case 5: run(IntTag<5>{}); break;
+                case 6: run(IntTag<6>{}); break;
+                case 7: run(IntTag<7>{}); break;
+                case 8: run(IntTag<8>{}); break;
+                default: run(IntTag<0>{}); break;
+                }
+            } else {
+                run(IntTag<0>{});
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&plan_empty[b]);  // the slot's tables are no longer needed
+            while (base < pb) rotate();                  // bins below the last footprint row (or with no samples)
+        }
+    }
+}
+
+template <int P, int VEC, int NS, int MINB>
+static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
+                             int aligned, float finest_scale, const float *chan_scale,
+                             const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                             bool *taken)
+{
+    constexpr int CB = 128 * VEC;
+    constexpr int S  = (P + kWin - 1) / kWin;
+    int maxH = 0, maxW = 0;
+    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
+    const int wx_cap = (maxW + 9 * P + 16 + 3) & ~3;           // touched cells <= extent + 2 per bin boundary, runs padded to 4
+    const int wyd_rows = maxH;
+    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)2 * (wx_cap + 4 * wyd_rows) * 4;
+    const size_t cap = MINB == 2 ? 115200 : 230000;            // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
+    if (smem > cap) { *taken = false; return FGN_OK; }
+    auto kern = roi_align_window_kernel<P, VEC, NS, MINB>;
+    static int attr_set = 0;                                   // per instantiation
+    if ((int)smem > attr_set) {
+        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = (int)smem;
+    }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        FGN_CUDA_OK(cudaGetDevice(&dev));
+        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static unsigned int launch_seq = 0;                        // one ticket counter per launch in flight (graphs bake theirs in)
+    const int slot = (int)(launch_seq++ % kTicketSlots);
+    const int nblk = (C + CB - 1) / CB;
+    const char *e = getenv("FGN_RA_SPLIT");
+    const float split_cells = e != nullptr ? (float)atof(e) : 512.f;
+    const int grid = min(MINB * sm_count, R * nblk);
+    kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                           scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
+                                           split_cells > 0.f ? split_cells : 3.0e38f);
+    FGN_LAUNCH_OK();
+    (void)S;
+    *taken = true;
+    return FGN_OK;
+}
+
+// NHWC in, NHWC out.  Declines (taken=false) shapes it has no instantiation for.
+int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                            int aligned, float finest_scale, const float *chan_scale,
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                            int ns_pref, bool *taken)
+{
+    *taken = false;
+    if ((C & 3) != 0) return FGN_OK;
+#define FGN_WIN(PV, VV, NV, MB) launch_window_cfg<PV, VV, NV, MB>(d, C, rois, R, sampling_ratio, aligned, finest_scale, \
+                                                                  chan_scale, scale_index, out, lvl_out, st, taken)
+    if (P == 7) {
+        if (C > 128) return ns_pref == 2 ? FGN_WIN(7, 2, 2, 2) : FGN_WIN(7, 2, 3, 2);
+        return ns_pref == 3 ? FGN_WIN(7, 1, 3, 2) : FGN_WIN(7, 1, 4, 2);
+    }
+    if (P == 14) {
+        if (C > 128) return ns_pref == 3 ? FGN_WIN(14, 2, 3, 1) : FGN_WIN(14, 2, 5, 1);
+        return FGN_WIN(14, 1, 6, 1);
+    }
+#undef FGN_WIN
+    return FGN_OK;
+}
+
+unsigned int roi_align_window_violations()
+{
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_window_violation, sizeof(v));
+    return v;
+}
+
+}  // namespace fgn

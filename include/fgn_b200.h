@@ -244,6 +244,11 @@ int fgn_support_pool_bwd(const float *grad_cat, const float *grad_gap, const flo
  * (bench.py's gpu_launches). */
 uint64_t fgn_launch_count(void);
 
+/* Test/debug export: self-check counter of the rotating-window RoIAlign planner -- the number of
+ * (footprint row, bin row) weights that did not fit the register window.  Always 0 unless the
+ * chunking rule in roi_align_window.cu is broken. */
+unsigned int fgn_debug_roi_window_violations(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,9 +149,12 @@ def test_roi_align_multilevel_vs_oracle(C, P):
     assert torch.equal(got3, got)                                                # NCHW input (repacked) too
 
 
-@pytest.mark.parametrize("env", [{"FGN_RA_IMPL": "3"}, {"FGN_RA_IMPL": "1"}, {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "1"},
-                                 {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "3"}, {"FGN_RA_IMPL": "2", "FGN_RA_CLASSES": "1"}],
-                         ids=["persistent", "bin-centric", "cb128", "sliced", "one-class"])
+@pytest.mark.parametrize("env", [{"FGN_RA_IMPL": "2"}, {"FGN_RA_IMPL": "3"}, {"FGN_RA_IMPL": "1"},
+                                 {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "1"}, {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "3"},
+                                 {"FGN_RA_IMPL": "2", "FGN_RA_CLASSES": "3"}, {"FGN_RA_SPLIT": "0"},
+                                 {"FGN_RA_SPLIT": "40"}, {"FGN_RA_NS": "2"}],
+                         ids=["stream", "persistent-v1", "bin-centric", "cb128", "sliced", "three-class",
+                              "window-nosplit", "window-split40", "window-ns2"])
 def test_roi_align_kernel_variants_agree(env, monkeypatch):
     """Every RoIAlign kernel variant the library can dispatch to (selected through its tuning
     environment knobs) reproduces the oracle and, among the streaming variants, each other bitwise."""
@@ -175,6 +178,62 @@ def test_roi_align_kernel_variants_agree(env, monkeypatch):
     close(got, want, what=str(env))
     if env.get("FGN_RA_IMPL") != "1":
         assert torch.equal(got, base), "streaming variants share one summation order"
+
+
+@pytest.mark.parametrize("P,C,B", [(7, 256, 2), (14, 256, 2), (7, 128, 1), (7, 64, 1), (7, 1024, 1), (14, 128, 1), (7, 320, 1)])
+def test_roi_align_window_kernel_chunked_and_ragged(P, C, B, monkeypatch):
+    """The default (persistent rotating-window) kernel on the shapes that exercise its planner: RoIs
+    smaller than the bin grid (split into bin-row chunks), huge and out-of-image RoIs, P=14, channel
+    counts below / above / not a multiple of its channel block, the fused channel attention.  Bitwise
+    equal to the row-streaming kernel (same summation order), within tolerance of the oracle, and the
+    planner's window self-check stays at zero."""
+    from fgn_b200 import _lib, ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(100 + P + C)
+    strides = [4, 8, 16, 32]
+    feats = [torch.randn(B, C, 192 // s, 256 // s, generator=g) for s in strides]
+    rois = synth_rois(g, 300, 192, 256, B, smin=4.0)
+    n = rois.shape[0]
+    # tiny boxes (bins far smaller than a cell), slivers, boxes hanging over every border, full image
+    rois[0, 1:] = torch.tensor([10.2, 11.7, 12.9, 13.1])
+    rois[1, 1:] = torch.tensor([100., 50., 100.5, 120.])
+    rois[2, 1:] = torch.tensor([-40., -40., 30., 20.])
+    rois[3, 1:] = torch.tensor([200., 150., 300., 260.])
+    rois[4, 1:] = torch.tensor([0., 0., 256., 192.])
+    rois[5, 1:] = torch.tensor([-500., -500., -400., -300.])
+    rois[6, 1:] = torch.tensor([3., 3., 9., 30.])
+    rois[7, 1:] = torch.tensor([60., 60., 60., 60.])
+    for i in range(8, 40):                                    # a run of very small boxes
+        cx, cy = float(torch.rand(1, generator=g)) * 256, float(torch.rand(1, generator=g)) * 192
+        w, h = 1 + 11 * float(torch.rand(1, generator=g)), 1 + 11 * float(torch.rand(1, generator=g))
+        rois[i, 1:] = torch.tensor([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+    vec = torch.randn(5, C, generator=g)
+    idx = torch.randint(0, 5, (n,), generator=g)
+    want, lv = O.single_roi_extractor(feats, rois, strides, P, 0, True, 56.0, "tv")
+    want_s = want * vec[idx][:, :, None, None]
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    scales = [1 / s for s in strides]
+    kw = dict(out_format="nhwc", return_levels=True)
+    before = _lib.load().fgn_launch_count()
+    got, lvl = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, **kw)
+    got_s, _ = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, chan_scale=vec.to(dev()),
+                                        scale_index=idx.to(dev()), **kw)
+    assert _lib.load().fgn_launch_count() == before + 2      # one kernel per call
+    assert torch.equal(lvl.cpu(), lv)
+    close(got, want, what="window vs oracle")
+    close(got_s, want_s, what="window + channel attention vs oracle")
+    # fixed sampling grids and the torchvision (aligned=False) convention
+    for sr, al in ((2, True), (-1, False), (3, False)):
+        w2, _ = O.single_roi_extractor(feats, rois, strides, P, sr, al, 56.0, "tv")
+        g2 = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, sr, al, out_format="nhwc")
+        close(g2, w2, what=f"window sr={sr} aligned={al}")
+    monkeypatch.setenv("FGN_RA_IMPL", "2")
+    ref, _ = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, **kw)
+    ref_s, _ = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, chan_scale=vec.to(dev()),
+                                        scale_index=idx.to(dev()), **kw)
+    assert torch.equal(got, ref) and torch.equal(got_s, ref_s), "window and streaming kernels share one summation order"
+    torch.cuda.synchronize()
+    assert _lib.load().fgn_debug_roi_window_violations() == 0
 
 
 def test_roi_align_edge_cases():
