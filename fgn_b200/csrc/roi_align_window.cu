@@ -96,22 +96,40 @@ __device__ __forceinline__ float4 mul4x2(const float w, const float4 v)
     return o;
 }
 
+constexpr int kPlanSlots = 3;       // plans in flight per CTA (the planners run up to two items ahead)
+
 template <int P>
 struct WinSlot {
+    // written by the Y planner
     int   r, cb0, level, batch, H, W;
     int   pa, pb;                                  // bin rows [pa, pb) of this item
     float count;
-    int   X0, Y0, ncols, nrows, nseg, rps, nstages;
-    int   xlo[P], xn[P], xoff[P];
+    int   Y0, nrows;                               // nrows < 0: the tables cannot hold this axis -> empty footprint
     int   hi[P + 1];                               // last footprint row (relative to Y0) of bins <= ph
+    // written by the X planner
+    int   X0, ncols;
+    int   xlo[P], xn[P], xoff[P];
 };
+
+// ring schedule of a footprint, evaluated identically by the producer and the consumers
+struct RingPlan { int ncols, nrows, nseg, rps, nstages; };
+__device__ __forceinline__ RingPlan ring_plan(int ncols, int nrows)
+{
+    RingPlan rp;
+    if (ncols <= 0 || nrows <= 0) { rp.ncols = rp.nrows = rp.nstages = 0; rp.nseg = rp.rps = 1; return rp; }
+    rp.ncols = ncols; rp.nrows = nrows;
+    if (ncols <= kStageCells) { rp.nseg = 1; rp.rps = kStageCells / ncols; rp.nstages = (nrows + rp.rps - 1) / rp.rps; }
+    else { rp.nseg = (ncols + kStageCells - 1) / kStageCells; rp.rps = 1; rp.nstages = nrows * rp.nseg; }
+    return rp;
+}
 
 }  // namespace
 
-// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
-// Dynamic shared memory: ring[NS][kStageCells*CB] | 2 x { wx[wx_cap] | wrow[wyd_rows] float4 }
+// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = Y planner (tickets, level, bin rows),
+// P+2 = X planner (bin columns).  The two planners work on the same item and both arrive on its plan_full.
+// Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
 template <int P, int VEC, int NS, int MINB>
-__global__ void __launch_bounds__((P + 2) * 32, MINB)
+__global__ void __launch_bounds__((P + 3) * 32, MINB)
 roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
@@ -122,150 +140,176 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     constexpr int S  = (P + kWin - 1) / kWin;       // bin-row chunks of a split RoI
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ WinSlot<P> slot[2];
-    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[2], plan_empty[2];
+    __shared__ WinSlot<P> slot[kPlanSlots];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[kPlanSlots], plan_empty[kPlanSlots];
+    __shared__ unsigned int mailbox[2];             // Y planner -> X planner: the ticket of item k
 
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *wtab = ring + (size_t)NS * kStageCells * CB;
     const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
 
     const int nblk  = (C + CB - 1) / CB;
-    const int items = R * S * nblk;
+    const int items = R * S * nblk;                 // tickets = (RoI, bin-row chunk, channel block); unused chunks are skipped
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&plan_full[b], 1); mbar_init(&plan_empty[b], P + 1); }
+        for (int b = 0; b < kPlanSlots; ++b) { mbar_init(&plan_full[b], 2); mbar_init(&plan_empty[b], P + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == P + 1) {
-        // ===== planner ===================================================================================
-        for (int k = 0;; ++k) {
-            const int b = k & 1;
+    if (warp > P) {
+        // ===== planners ==================================================================================
+        const bool yplanner = (warp == P + 1);
+        // the Y planner always holds one prefetched ticket, so a launch draws items + 2 tickets per CTA in all;
+        // the last one resets the counter for the next launch that uses this slot
+        const unsigned last_ticket = (unsigned)items + 2u * gridDim.x - 1u;
+        auto take = [&]() {
+            unsigned int tk = 0;
+            if (lane == 0) {
+                tk = atomicAdd(&g_window_ticket[ticket_slot], 1u);
+                if (tk == last_ticket) g_window_ticket[ticket_slot] = 0u;
+            }
+            return tk;                                                   // valid in lane 0; broadcast at use
+        };
+        unsigned int tnext = yplanner ? take() : 0u;
+        int k = 0;                                                       // items published so far
+        for (unsigned int it = 0;; ++it) {
+            unsigned int ticket;
+            if (yplanner) {
+                ticket = __shfl_sync(FULL, tnext, 0);
+                tnext = take();                                          // in flight while this item is planned
+                if (lane == 0) mailbox[it & 1] = ticket;
+            }
+            asm volatile("bar.sync 2, 64;" ::: "memory");                // the two planner warps, once per ticket
+            if (!yplanner) ticket = mailbox[it & 1];
+            const int b = k % kPlanSlots;
+            const unsigned eparity = ((k / kPlanSlots) & 1) ^ 1;         // plan_empty: item k - kPlanSlots consumed
             WinSlot<P> &ps = slot[b];
-            float *wx = wtab + (size_t)b * wslot;
-            float *wrow = wx + wx_cap;                                   // [nrows][4]
-            mbar_wait(&plan_empty[b], ((k >> 1) & 1) ^ 1);               // item k-2 fully consumed
-            bool done = false;
-            for (;;) {                                                   // tickets of unused chunks are skipped
-                unsigned int ticket = 0;
-                if (lane == 0) {
-                    ticket = atomicAdd(&g_window_ticket[ticket_slot], 1u);
-                    if (ticket == (unsigned)(items + gridDim.x - 1)) g_window_ticket[ticket_slot] = 0u;   // last of the launch
-                }
-                ticket = __shfl_sync(FULL, ticket, 0);
-                if ((int)ticket >= items) { done = true; break; }
-                const int cbi = (int)ticket % nblk, chunk = ((int)ticket / nblk) % S, r = (int)ticket / (nblk * S);
-                const float *roi = rois + 5 * (size_t)r;
-                const int level = roi_level(roi, pyr, finest_scale);
-                const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
-                const int H = pyr.H[level], W = pyr.W[level];
-                // chunking rule (any rule is correct as long as every planner evaluates the same one):
-                // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row; big footprints are
-                // split to shorten the tail of the launch
-                const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
-                const bool split = S > 1 && (g.bin_h < 0.75f || est > split_cells);
-                if (chunk > 0 && !split) continue;
-                const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
+            if ((int)ticket >= items) {
+                mbar_wait(&plan_empty[b], eparity);
+                if (yplanner && lane == 0) ps.r = -1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&plan_full[b]);
+                break;
+            }
+            const int cbi = (int)ticket % nblk, chunk = ((int)ticket / nblk) % S, r = (int)ticket / (nblk * S);
+            const float *roi = rois + 5 * (size_t)r;
+            const int level = roi_level(roi, pyr, finest_scale);
+            const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
+            const int H = pyr.H[level], W = pyr.W[level];
+            // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
+            // as S items of kWin bin rows each; big footprints are chunked too, to shorten the launch's tail
+            const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
+            const bool split = S > 1 && (g.bin_h < 0.75f || est > split_cells);
+            if (chunk > 0 && !split) continue;
+            const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
 
-                // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns
-                const int axis = lane / P, p = lane % P;
-                const bool isy = lane < P && p >= pa && p < pb, isx = lane >= P && lane < 2 * P;
-                const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
-                const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
-                int lo = 0x7fffffff, hi = -1;
-                if (isx || isy) {
+            // lane = bin of this planner's axis.  Sample coordinates are monotone in the sample index, so when
+            // the first and last sample of a bin are valid they bound its cells.
+            const int p = lane;
+            const bool mine = yplanner ? (p >= pa && p < pb) : (p < P);
+            const float start = yplanner ? g.start_h : g.start_w, bin = yplanner ? g.bin_h : g.bin_w;
+            const int grid = yplanner ? g.grid_h : g.grid_w, size = yplanner ? H : W;
+            int lo = 0x7fffffff, hi = -1;
+            if (mine && grid > 0) {
+                const AxisSample s0 = axis_sample(start, bin, grid, size, p, 0);
+                const AxisSample s1 = axis_sample(start, bin, grid, size, p, grid - 1);
+                if (s0.valid && s1.valid) { lo = min(s0.low, s1.low); hi = max(s0.high, s1.high); }   // either direction (x2 < x1)
+                else {
                     for (int i = 0; i < grid; ++i) {
                         const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
                         if (sm.valid) { lo = min(lo, sm.low); hi = max(hi, sm.high); }
                     }
                 }
-                int n = hi >= 0 ? hi - lo + 1 : 0;
-                if (hi < 0) lo = 0;
-                const int big = 0x7fffffff;
-                int X0 = __reduce_min_sync(FULL, (isx && n > 0) ? lo : big);
-                int X1 = __reduce_max_sync(FULL, (isx && n > 0) ? lo + n : -1);
-                int Y0 = __reduce_min_sync(FULL, (isy && n > 0) ? lo : big);
-                int Y1 = __reduce_max_sync(FULL, (isy && n > 0) ? lo + n : -1);
-                const int n4 = (n + 3) & ~3;                            // weight runs start 16 B aligned
-                const int xsum = __reduce_add_sync(FULL, isx ? n4 : 0);
-                if (X1 < 0 || Y1 < 0 || xsum > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; }
-                const int ncols = X1 - X0, nrows = Y1 - Y0;
-                int nseg, rps, nstages;
-                if (ncols <= kStageCells) {
-                    nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
-                } else {
-                    nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
-                }
-                if (ncols == 0 || nrows == 0) nstages = 0;
+            }
+            int n = hi >= 0 ? hi - lo + 1 : 0;
+            if (hi < 0) lo = 0;
+            const int A0 = __reduce_min_sync(FULL, n > 0 ? lo : 0x7fffffff);      // first / one-past-last touched cell
+            const int A1 = __reduce_max_sync(FULL, n > 0 ? lo + n : -1);
+            float *wx = wtab + (size_t)b * wslot;
 
-                int off = 0;                                             // exclusive scan of the padded x runs
-                int him = -1;                                            // running max of the bin rows' last footprint row
+            if (yplanner) {
+                int Y0 = A0, nrows = A1 - A0;
+                if (A1 < 0) { Y0 = 0; nrows = 0; }
+                if (nrows > wyd_rows) { nrows = -1; n = 0; }
+                float *wrow = wx + wx_cap;                               // [nrows][4]
+                int hiall[P];                                            // running max of the bin rows' last footprint row
+                int him = -1, myhi = -1;
 #pragma unroll
-                for (int q = 0; q < P; ++q) {
-                    const int nq = __shfl_sync(FULL, n4, P + q);
-                    if (lane >= P && q < p) off += nq;
-                    const int hq = __shfl_sync(FULL, (isy && n > 0) ? lo + n - 1 - Y0 : -1, q);
-                    if (lane < P && q <= p) him = max(him, hq);
+                for (int qq = 0; qq < P; ++qq) {
+                    const int hq = __shfl_sync(FULL, n > 0 ? lo + n - 1 - Y0 : -1, qq);
+                    him = max(him, hq);
+                    hiall[qq] = him;
+                    if (qq == lane) myhi = him;
                 }
+                mbar_wait(&plan_empty[b], eparity);
                 if (lane == 0) {
                     ps.r = r; ps.cb0 = cbi * CB; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
-                    ps.pa = pa; ps.pb = pb; ps.count = g.count;
-                    ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
-                    ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
+                    ps.pa = pa; ps.pb = pb; ps.count = g.count; ps.Y0 = Y0; ps.nrows = nrows;
                     if (lvl_out != nullptr && cbi == 0 && chunk == 0) lvl_out[r] = level;
                 }
-                if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
-                if (lane < P) ps.hi[p] = him;
+                if (lane < P) ps.hi[lane] = myhi;
                 for (int i = lane; i < nrows; i += 32)
                     reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
-                if (nstages > 0 && n > 0) {
-                    if (isx) {
-                        float *w = wx + off;
-                        for (int i = 0; i < n4; ++i) w[i] = 0.f;
-                        for (int i = 0; i < grid; ++i) {
-                            const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                            if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
-                        }
-                    } else if (isy) {
-                        // footprint row j lives in window slot (p - base_j), base_j = first bin row of the
-                        // item whose (running-max) last row is >= j
-                        auto put = [&](int j, float wgt) {
-                            int base = pa;
-                            for (int q = pa; q < pb; ++q) base += (ps.hi[q] < j) ? 1 : 0;
-                            const int comp = p - base;
-                            if (comp >= 0 && comp < kWin) wrow[4 * j + comp] += wgt;
-                            else atomicAdd(&g_window_violation, 1u);
-                        };
-                        for (int i = 0; i < grid; ++i) {
-                            const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                            if (sm.valid) { put(sm.low - Y0, sm.h); put(sm.high - Y0, sm.l); }
-                        }
+                if (n > 0) {
+                    // footprint row j lives in window slot (p - base_j), base_j = first bin row of the item
+                    // whose (running-max) last row is >= j
+                    auto put = [&](int j, float wgt) {
+                        int base = pa;
+#pragma unroll
+                        for (int qq = 0; qq < P; ++qq) base += (qq >= pa && qq < pb && hiall[qq] < j) ? 1 : 0;
+                        const int comp = p - base;
+                        if (comp >= 0 && comp < kWin) wrow[4 * j + comp] += wgt;
+                        else atomicAdd(&g_window_violation, 1u);
+                    };
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { put(sm.low - Y0, sm.h); put(sm.high - Y0, sm.l); }
                     }
                 }
-                break;
-            }
-            if (done) {
-                if (lane == 0) { ps.r = -1; ps.nstages = 0; }
+            } else {
+                int X0 = A0, ncols = A1 - A0;
+                if (A1 < 0) { X0 = 0; ncols = 0; }
+                const int n4 = (n + 3) & ~3;                             // weight runs start 16 B aligned
+                const int xsum = __reduce_add_sync(FULL, n4);
+                if (xsum + 8 > wx_cap) { ncols = -1; n = 0; }
+                int off = 0;                                             // exclusive scan of the padded x runs
+#pragma unroll
+                for (int qq = 0; qq < P; ++qq) {
+                    const int nq = __shfl_sync(FULL, n4, qq);
+                    if (qq < p) off += nq;
+                }
+                mbar_wait(&plan_empty[b], eparity);
+                if (lane == 0) { ps.X0 = X0; ps.ncols = ncols; }
+                if (lane < P) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = ncols < 0 ? 0 : off; }
+                if (n > 0) {
+                    float *w = wx + off;
+                    for (int i = 0; i < n4; ++i) w[i] = 0.f;
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&plan_full[b]);
-            if (done) break;
+            ++k;
         }
     } else if (warp == P) {
         // ===== producer: bulk async copies of footprint rows, ring runs across items =======================
         int s = 0, par = 1;                                              // parity 1: first pass over a fresh barrier
         for (int k = 0;; ++k) {
-            const int b = k & 1;
-            mbar_wait(&plan_full[b], (k >> 1) & 1);
+            const int b = k % kPlanSlots;
+            mbar_wait(&plan_full[b], (k / kPlanSlots) & 1);
             const WinSlot<P> &ps = slot[b];
             if (ps.r < 0) break;
             const int cbn = min(CB, C - ps.cb0);
             const bool rowcopy = (C == CB);                              // a row segment is one contiguous run
-            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
+            const RingPlan rg = ring_plan(ps.nrows < 0 ? 0 : ps.ncols, ps.ncols < 0 ? 0 : ps.nrows);
+            const int nrows = rg.nrows, ncols = rg.ncols, nstages = rg.nstages, rps = rg.rps, nseg = rg.nseg;
             const float *fbase = pyr.feat[ps.level] + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
                                  + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
             const size_t row_pitch = (size_t)ps.W * C;
@@ -302,15 +346,16 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
         const int pw = warp;
         int s = 0, par = 0;
         for (int k = 0;; ++k) {
-            const int b = k & 1;
-            mbar_wait(&plan_full[b], (k >> 1) & 1);
+            const int b = k % kPlanSlots;
+            mbar_wait(&plan_full[b], (k / kPlanSlots) & 1);
             const WinSlot<P> &ps = slot[b];
             const int r = ps.r;
             if (r < 0) break;
             const float *wx = wtab + (size_t)b * wslot;
             const float4 *wrow = reinterpret_cast<const float4 *>(wx + wx_cap);
             const int cb0 = ps.cb0, cbn = min(CB, C - cb0);
-            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
+            const RingPlan rg = ring_plan(ps.nrows < 0 ? 0 : ps.ncols, ps.ncols < 0 ? 0 : ps.nrows);
+            const int nrows = rg.nrows, ncols = rg.ncols, nstages = rg.nstages, rps = rg.rps, nseg = rg.nseg;
             const int xlo = ps.xlo[pw] - ps.X0, nx = ps.xn[pw];
             const float *wxp = wx + ps.xoff[pw];
             const int pb = ps.pb;
@@ -330,23 +375,33 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     if (v * 128 + lch < cbn) cs[v] = ldg4(chan_scale + (size_t)si * C + cb0 + v * 128 + lch);
             }
             float *obase = out + ((size_t)r * P * P + pw) * C + cb0 + lch;
+            // the bin column's weights live in registers for the whole item (runs are padded to 4 floats and
+            // the table has 8 floats of slack, so reading 8 is always in bounds; entries past nx are unused)
+            float wreg[8];
+            {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wxp), w1 = *reinterpret_cast<const float4 *>(wxp + 4);
+                wreg[0] = w0.x; wreg[1] = w0.y; wreg[2] = w0.z; wreg[3] = w0.w;
+                wreg[4] = w1.x; wreg[5] = w1.y; wreg[6] = w1.z; wreg[7] = w1.w;
+            }
 
             float4 a[kWin][VEC], racc[VEC];
 #pragma unroll
-            for (int q = 0; q < kWin; ++q)
+            for (int qq = 0; qq < kWin; ++qq)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) a[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int v = 0; v < VEC; ++v) a[qq][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
             // store bin row `base` (window slot 0) and slide the window down by one
             auto rotate = [&]() {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    const float4 q = a[0][v];
+                    const float4 qv = a[0][v];
                     float4 o;
                     if (chan_scale != nullptr)          // (acc * 1/count) * vec, same rounding order as unfused
-                        o = make_float4(q.x * inv * cs[v].x, q.y * inv * cs[v].y, q.z * inv * cs[v].z, q.w * inv * cs[v].w);
+                        o = make_float4(qv.x * inv * cs[v].x, qv.y * inv * cs[v].y, qv.z * inv * cs[v].z, qv.w * inv * cs[v].w);
                     else
-                        o = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                        o = make_float4(qv.x * inv, qv.y * inv, qv.z * inv, qv.w * inv);
                     if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(obase + (size_t)base * P * C + v * 128) = o;
 #pragma unroll
                     for (int w = 0; w + 1 < kWin; ++w) a[w][v] = a[w + 1][v];
@@ -365,90 +420,73 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     for (int v = 0; v < VEC; ++v) { fma4x2(a[2][v], w4.z, racc[v]); fma4x2(a[3][v], w4.w, racc[v]); }
                 }
             };
+            // cell i of the row at rp: 128-bit LDS at a compile-time offset + packed FMAs (first cell: MUL)
+#define FGN_CELL0()                                                                                          \
+    _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                           \
+        racc[v] = mul4x2(wreg[0], *reinterpret_cast<const float4 *>(rp + v * 128))
+#define FGN_CELL(i)                                                                                          \
+    _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                           \
+        fma4x2(racc[v], wreg[i], *reinterpret_cast<const float4 *>(rp + (i) * CB + v * 128))
 
-            // Row pass, specialised on the number of cells NX this warp's bin column covers (constant over
-            // the item): weights live in registers, every cell is a 128-bit LDS at a compile-time offset
-            // followed by packed FMAs.  NX = 0 is the generic loop (wide bins, segmented rows).
-            auto run = [&](auto nx_tag) {
-                constexpr int NX = decltype(nx_tag)::value;
-                float wreg[NX > 0 ? NX : 1];
-                if (NX > 0) {
+            if (nseg == 1) {
+                int row = 0;
+                const int rstride = ncols * CB;
+                for (int st = 0; st < nstages; ++st) {
+                    const int nr = min(rps, nrows - row);
+                    mbar_wait(&full_bar[s], par);
+                    const float *rp = ring + (size_t)s * kStageCells * CB + xlo * CB + lch;
+                    for (int rr = 0; rr < nr; ++rr, ++row, rp += rstride) {
+                        switch (nx) {                    // constant over the item: one jump per row
+                        case 1: FGN_CELL0(); break;
+                        case 2: FGN_CELL0(); FGN_CELL(1); break;
+                        case 3: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); break;
+                        case 4: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); break;
+                        case 5: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); break;
+                        case 6: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); break;
+                        case 7: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); FGN_CELL(6); break;
+                        case 8: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); FGN_CELL(6); FGN_CELL(7); break;
+                        default: {
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) wreg[i] = wxp[i];
-                }
-                if (NX > 0 || nseg == 1) {
-                    int row = 0;
-                    const int rstride = ncols * CB;
-                    for (int st = 0; st < nstages; ++st) {
-                        const int nr = min(rps, nrows - row);
-                        mbar_wait(&full_bar[s], par);
-                        const float *rp = ring + (size_t)s * kStageCells * CB + xlo * CB + lch;
-                        for (int rr = 0; rr < nr; ++rr, ++row, rp += rstride) {
-                            if (NX > 0) {
+                            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float *cp = rp;
+                            for (int i = 0; i < nx; ++i, cp += CB) {
+                                const float w = wxp[i];
 #pragma unroll
-                                for (int v = 0; v < VEC; ++v) racc[v] = mul4x2(wreg[0], *reinterpret_cast<const float4 *>(rp + v * 128));
-#pragma unroll
-                                for (int i = 1; i < NX; ++i)
-#pragma unroll
-                                    for (int v = 0; v < VEC; ++v)
-                                        fma4x2(racc[v], wreg[i], *reinterpret_cast<const float4 *>(rp + i * CB + v * 128));
-                            } else {
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float *cp = rp;
-                                for (int i = 0; i < nx; ++i, cp += CB) {
-                                    const float w = wxp[i];
-#pragma unroll
-                                    for (int v = 0; v < VEC; ++v) fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(cp + v * 128));
-                                }
+                                for (int v = 0; v < VEC; ++v) fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(cp + v * 128));
                             }
+                        } break;
+                        }
+                        fold(row);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    if (++s == NS) { s = 0; par ^= 1; }
+                }
+            } else {
+                for (int row = 0; row < nrows; ++row)
+                    for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
+                        const int nc = min(kStageCells, ncols - col0);
+                        mbar_wait(&full_bar[s], par);
+                        const float *sb = ring + (size_t)s * kStageCells * CB + lch;
+                        const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
+                        for (int cx = c_beg; cx < c_end; ++cx) {
+                            const float w = wxp[cx - xlo];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v)
+                                fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(sb + (cx - col0) * CB + v * 128));
+                        }
+                        if (col0 + nc >= ncols) {
                             fold(row);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[s]);
                         if (++s == NS) { s = 0; par ^= 1; }
                     }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int row = 0; row < nrows; ++row)
-                        for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
-                            const int nc = min(kStageCells, ncols - col0);
-                            mbar_wait(&full_bar[s], par);
-                            const float *sb = ring + (size_t)s * kStageCells * CB + lch;
-                            const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
-                            for (int cx = c_beg; cx < c_end; ++cx) {
-                                const float w = wxp[cx - xlo];
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v)
-                                    fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(sb + (cx - col0) * CB + v * 128));
-                            }
-                            if (col0 + nc >= ncols) {
-                                fold(row);
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty_bar[s]);
-                            if (++s == NS) { s = 0; par ^= 1; }
-                        }
-                }
-            };
-            if (nseg == 1) {
-                switch (nx) {
-                case 1: run(IntTag<1>{}); break;
-                case 2: run(IntTag<2>{}); break;
-                case 3: run(IntTag<3>{}); break;
-                case 4: run(IntTag<4>{}); break;
-                case 5: run(IntTag<5>{}); break;
-                case 6: run(IntTag<6>{}); break;
-                case 7: run(IntTag<7>{}); break;
-                case 8: run(IntTag<8>{}); break;
-                default: run(IntTag<0>{}); break;
-                }
-            } else {
-                run(IntTag<0>{});
             }
+#undef FGN_CELL0
+#undef FGN_CELL
             __syncwarp();
             if (lane == 0) mbar_arrive(&plan_empty[b]);  // the slot's tables are no longer needed
             while (base < pb) rotate();                  // bins below the last footprint row (or with no samples)
@@ -466,9 +504,9 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     constexpr int S  = (P + kWin - 1) / kWin;
     int maxH = 0, maxW = 0;
     for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
-    const int wx_cap = (maxW + 9 * P + 16 + 3) & ~3;           // touched cells <= extent + 2 per bin boundary, runs padded to 4
+    const int wx_cap = (maxW + 9 * P + 24 + 3) & ~3;           // touched cells <= extent + 2 per bin boundary, runs padded to 4, 8 slack
     const int wyd_rows = maxH;
-    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)2 * (wx_cap + 4 * wyd_rows) * 4;
+    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * (wx_cap + 4 * wyd_rows) * 4;
     const size_t cap = MINB == 2 ? 115200 : 230000;            // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
     if (smem > cap) { *taken = false; return FGN_OK; }
     auto kern = roi_align_window_kernel<P, VEC, NS, MINB>;
@@ -489,7 +527,8 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const char *e = getenv("FGN_RA_SPLIT");
     const float split_cells = e != nullptr ? (float)atof(e) : 512.f;
     const int grid = min(MINB * sm_count, R * nblk);
-    kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+    (void)CB;
+    kern<<<grid, (P + 3) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                            scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
                                            split_cells > 0.f ? split_cells : 3.0e38f);
     FGN_LAUNCH_OK();
