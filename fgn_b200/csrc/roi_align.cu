@@ -392,6 +392,7 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
                             const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
                             int ns_pref, bool *taken);
 unsigned int roi_align_window_violations();
+void roi_align_window_trace(unsigned long long *dst, int n);
 
 }  // namespace fgn
 
@@ -466,6 +467,12 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
 extern "C" unsigned int fgn_debug_roi_window_violations(void)
 {
     return roi_align_window_violations();
+}
+
+// Development trace of the rotating-window kernel (FGN_RA_DEBUG bit 5); not declared in the public header.
+extern "C" void fgn_debug_roi_window_trace(unsigned long long *dst, int n)
+{
+    roi_align_window_trace(dst, n);
 }
 
 // Same entry, forcing the direct kernel (exported for the in-library cross-check in tests).

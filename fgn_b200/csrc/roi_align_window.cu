@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kWin        = 4;      // bin rows held in registers per consumer warp
 constexpr int kStageCells = 32;     // cells (of CB channels) per ring stage
-constexpr unsigned kTicketSlots = 1024;
+constexpr unsigned kTicketSlots = 65536;   // ticket counters: [0, half) for launches baked into CUDA graphs, [half, end) eager
 
 __device__ unsigned int g_window_ticket[kTicketSlots];
 __device__ unsigned int g_window_violation;           // planner self-check (must stay 0)
@@ -96,57 +96,83 @@ __device__ __forceinline__ float4 mul4x2(const float w, const float4 v)
     return o;
 }
 
-constexpr int kPlanSlots = 3;       // plans in flight per CTA (the planners run up to two items ahead)
+constexpr int kPlanSlots = 3;       // plans in flight per CTA (the planner runs up to two items ahead)
+
+// mbarrier ops on precomputed 32-bit shared addresses (the generic->shared conversion is done once per kernel)
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive32(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx32(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s32(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 template <int P>
 struct WinSlot {
-    // written by the Y planner
     int   r, cb0, level, batch, H, W;
     int   pa, pb;                                  // bin rows [pa, pb) of this item
     float count;
-    int   Y0, nrows;                               // nrows < 0: the tables cannot hold this axis -> empty footprint
-    int   hi[P + 1];                               // last footprint row (relative to Y0) of bins <= ph
-    // written by the X planner
-    int   X0, ncols;
+    int   X0, Y0, ncols, nrows, nseg, rps, nstages;
     int   xlo[P], xn[P], xoff[P];
+    int   hi[P + 1];                               // last footprint row (relative to Y0) of bins <= ph
 };
 
-// ring schedule of a footprint, evaluated identically by the producer and the consumers
-struct RingPlan { int ncols, nrows, nseg, rps, nstages; };
-__device__ __forceinline__ RingPlan ring_plan(int ncols, int nrows)
+// development trace (debug_mode bit 5): per CTA, per item (first 16), 12 globaltimer stamps
+constexpr int kTraceItems = 16, kTraceEvents = 12, kTraceCtas = 296;
+__device__ unsigned long long g_window_trace[kTraceCtas * kTraceItems * kTraceEvents];
+__device__ __forceinline__ void trace(int debug_mode, int item, int ev, int lane)
 {
-    RingPlan rp;
-    if (ncols <= 0 || nrows <= 0) { rp.ncols = rp.nrows = rp.nstages = 0; rp.nseg = rp.rps = 1; return rp; }
-    rp.ncols = ncols; rp.nrows = nrows;
-    if (ncols <= kStageCells) { rp.nseg = 1; rp.rps = kStageCells / ncols; rp.nstages = (nrows + rp.rps - 1) / rp.rps; }
-    else { rp.nseg = (ncols + kStageCells - 1) / kStageCells; rp.rps = 1; rp.nstages = nrows * rp.nseg; }
-    return rp;
+    if ((debug_mode & 32) && lane == 0 && item < kTraceItems && blockIdx.x < kTraceCtas) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_window_trace[((size_t)blockIdx.x * kTraceItems + item) * kTraceEvents + ev] = t;
+    }
 }
 
 }  // namespace
 
-// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = Y planner (tickets, level, bin rows),
-// P+2 = X planner (bin columns).  The two planners work on the same item and both arrive on its plan_full.
+// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
 // Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
 template <int P, int VEC, int NS, int MINB>
-__global__ void __launch_bounds__((P + 3) * 32, MINB)
+__global__ void __launch_bounds__((P + 2) * 32, MINB)
 roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
                         float *__restrict__ out, int32_t *__restrict__ lvl_out,
-                        const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells)
+                        const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells,
+                        const int debug_mode)
 {
+    // debug_mode (development only): bit 0 = no copies (producer only signals), bit 1 = no row math,
+    // bit 5 = record the per-CTA timeline
     constexpr int CB = 128 * VEC;                   // channels per item; cell stride in the ring
     constexpr int S  = (P + kWin - 1) / kWin;       // bin-row chunks of a split RoI
+    constexpr int kStageFloats = kStageCells * CB;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ WinSlot<P> slot[kPlanSlots];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[kPlanSlots], plan_empty[kPlanSlots];
-    __shared__ unsigned int mailbox[2];             // Y planner -> X planner: the ticket of item k
 
     float *ring = reinterpret_cast<float *>(smem_raw);
-    float *wtab = ring + (size_t)NS * kStageCells * CB;
+    float *wtab = ring + (size_t)NS * kStageFloats;
     const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
+    const uint32_t full32 = smem_u32(full_bar), empty32 = smem_u32(empty_bar);
+    const uint32_t pfull32 = smem_u32(plan_full), pempty32 = smem_u32(plan_empty);
 
     const int nblk  = (C + CB - 1) / CB;
     const int items = R * S * nblk;                 // tickets = (RoI, bin-row chunk, channel block); unused chunks are skipped
@@ -154,16 +180,15 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
 
     if (t == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
-        for (int b = 0; b < kPlanSlots; ++b) { mbar_init(&plan_full[b], 2); mbar_init(&plan_empty[b], P + 1); }
+        for (int b = 0; b < kPlanSlots; ++b) { mbar_init(&plan_full[b], 1); mbar_init(&plan_empty[b], P + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp > P) {
-        // ===== planners ==================================================================================
-        const bool yplanner = (warp == P + 1);
-        // the Y planner always holds one prefetched ticket, so a launch draws items + 2 tickets per CTA in all;
-        // the last one resets the counter for the next launch that uses this slot
+    if (warp == P + 1) {
+        // ===== planner ===================================================================================
+        // it always holds one prefetched ticket, so a launch draws items + 2 tickets per CTA in all; the last
+        // one resets the counter for the next launch that uses this slot
         const unsigned last_ticket = (unsigned)items + 2u * gridDim.x - 1u;
         auto take = [&]() {
             unsigned int tk = 0;
@@ -173,25 +198,19 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             }
             return tk;                                                   // valid in lane 0; broadcast at use
         };
-        unsigned int tnext = yplanner ? take() : 0u;
-        int k = 0;                                                       // items published so far
-        for (unsigned int it = 0;; ++it) {
-            unsigned int ticket;
-            if (yplanner) {
-                ticket = __shfl_sync(FULL, tnext, 0);
-                tnext = take();                                          // in flight while this item is planned
-                if (lane == 0) mailbox[it & 1] = ticket;
-            }
-            asm volatile("bar.sync 2, 64;" ::: "memory");                // the two planner warps, once per ticket
-            if (!yplanner) ticket = mailbox[it & 1];
-            const int b = k % kPlanSlots;
-            const unsigned eparity = ((k / kPlanSlots) & 1) ^ 1;         // plan_empty: item k - kPlanSlots consumed
+        unsigned int tnext = take();
+        int k = 0, b = 0;                                                // items published so far, their slot
+        unsigned eparity = 1;                                            // plan_empty: item k - kPlanSlots consumed
+        for (;;) {
+            const unsigned int ticket = __shfl_sync(FULL, tnext, 0);
+            tnext = take();                                              // in flight while this item is planned
+            trace(debug_mode, k, 0, lane);
             WinSlot<P> &ps = slot[b];
             if ((int)ticket >= items) {
-                mbar_wait(&plan_empty[b], eparity);
-                if (yplanner && lane == 0) ps.r = -1;
+                mbar_wait32(pempty32 + 8 * b, eparity);
+                if (lane == 0) ps.r = -1;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&plan_full[b]);
+                if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
                 break;
             }
             const int cbi = (int)ticket % nblk, chunk = ((int)ticket / nblk) % S, r = (int)ticket / (nblk * S);
@@ -206,14 +225,14 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             if (chunk > 0 && !split) continue;
             const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
 
-            // lane = bin of this planner's axis.  Sample coordinates are monotone in the sample index, so when
-            // the first and last sample of a bin are valid they bound its cells.
-            const int p = lane;
-            const bool mine = yplanner ? (p >= pa && p < pb) : (p < P);
-            const float start = yplanner ? g.start_h : g.start_w, bin = yplanner ? g.bin_h : g.bin_w;
-            const int grid = yplanner ? g.grid_h : g.grid_w, size = yplanner ? H : W;
+            // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns.  Sample coordinates are monotone in
+            // the sample index, so when the first and last sample of a bin are valid they bound its cells.
+            const int axis = lane >= P ? 1 : 0, p = lane - axis * P;
+            const bool isx = lane >= P && lane < 2 * P, isy = lane < P && p >= pa && p < pb;
+            const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
+            const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
             int lo = 0x7fffffff, hi = -1;
-            if (mine && grid > 0) {
+            if ((isx || isy) && grid > 0) {
                 const AxisSample s0 = axis_sample(start, bin, grid, size, p, 0);
                 const AxisSample s1 = axis_sample(start, bin, grid, size, p, grid - 1);
                 if (s0.valid && s1.valid) { lo = min(s0.low, s1.low); hi = max(s0.high, s1.high); }   // either direction (x2 < x1)
@@ -226,35 +245,60 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             }
             int n = hi >= 0 ? hi - lo + 1 : 0;
             if (hi < 0) lo = 0;
-            const int A0 = __reduce_min_sync(FULL, n > 0 ? lo : 0x7fffffff);      // first / one-past-last touched cell
-            const int A1 = __reduce_max_sync(FULL, n > 0 ? lo + n : -1);
-            float *wx = wtab + (size_t)b * wslot;
-
-            if (yplanner) {
-                int Y0 = A0, nrows = A1 - A0;
-                if (A1 < 0) { Y0 = 0; nrows = 0; }
-                if (nrows > wyd_rows) { nrows = -1; n = 0; }
-                float *wrow = wx + wx_cap;                               // [nrows][4]
-                int hiall[P];                                            // running max of the bin rows' last footprint row
-                int him = -1, myhi = -1;
+            const int big = 0x7fffffff;
+            int X0 = __reduce_min_sync(FULL, (isx && n > 0) ? lo : big);
+            int X1 = __reduce_max_sync(FULL, (isx && n > 0) ? lo + n : -1);
+            int Y0 = __reduce_min_sync(FULL, (isy && n > 0) ? lo : big);
+            int Y1 = __reduce_max_sync(FULL, (isy && n > 0) ? lo + n : -1);
+            const int n4 = (n + 3) & ~3;                                 // weight runs start 16 B aligned
+            const int xsum = __reduce_add_sync(FULL, isx ? n4 : 0);
+            if (X1 < 0 || Y1 < 0 || xsum + 8 > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; }
+            const int ncols = X1 - X0, nrows = Y1 - Y0;
+            int nseg, rps, nstages;
+            if (ncols <= kStageCells) {
+                nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
+            } else {
+                nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
+            }
+            if (ncols == 0 || nrows == 0) nstages = 0;
+            int off = 0;                                                 // exclusive scan of the padded x runs
+            int hiall[P];                                                // running max of the bin rows' last footprint row
+            int him = -1, myhi = -1;
 #pragma unroll
-                for (int qq = 0; qq < P; ++qq) {
-                    const int hq = __shfl_sync(FULL, n > 0 ? lo + n - 1 - Y0 : -1, qq);
-                    him = max(him, hq);
-                    hiall[qq] = him;
-                    if (qq == lane) myhi = him;
-                }
-                mbar_wait(&plan_empty[b], eparity);
-                if (lane == 0) {
-                    ps.r = r; ps.cb0 = cbi * CB; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
-                    ps.pa = pa; ps.pb = pb; ps.count = g.count; ps.Y0 = Y0; ps.nrows = nrows;
-                    if (lvl_out != nullptr && cbi == 0 && chunk == 0) lvl_out[r] = level;
-                }
-                if (lane < P) ps.hi[lane] = myhi;
-                for (int i = lane; i < nrows; i += 32)
-                    reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncwarp();
-                if (n > 0) {
+            for (int qq = 0; qq < P; ++qq) {
+                const int nq = __shfl_sync(FULL, n4, P + qq);
+                if (isx && qq < p) off += nq;
+                const int hq = __shfl_sync(FULL, (isy && n > 0) ? lo + n - 1 - Y0 : -1, qq);
+                him = max(him, hq);
+                hiall[qq] = him;
+                if (qq == lane) myhi = him;
+            }
+            float *wx = wtab + (size_t)b * wslot;
+            float *wrow = wx + wx_cap;                                   // [nrows][4]
+            trace(debug_mode, k, 1, lane);
+            mbar_wait32(pempty32 + 8 * b, eparity);
+            trace(debug_mode, k, 2, lane);
+            if (lane == 0) {
+                ps.r = r; ps.cb0 = cbi * CB; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
+                ps.pa = pa; ps.pb = pb; ps.count = g.count;
+                ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
+                ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
+                if (lvl_out != nullptr && cbi == 0 && chunk == 0) lvl_out[r] = level;
+            }
+            if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
+            if (lane < P) ps.hi[lane] = myhi;
+            for (int i = lane; i < nrows; i += 32)
+                reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (nstages > 0 && n > 0) {
+                if (isx) {
+                    float *w = wx + off;
+                    for (int i = 0; i < n4; ++i) w[i] = 0.f;
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
+                    }
+                } else if (isy) {
                     // footprint row j lives in window slot (p - base_j), base_j = first bin row of the item
                     // whose (running-max) last row is >= j
                     auto put = [&](int j, float wgt) {
@@ -270,101 +314,92 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         if (sm.valid) { put(sm.low - Y0, sm.h); put(sm.high - Y0, sm.l); }
                     }
                 }
-            } else {
-                int X0 = A0, ncols = A1 - A0;
-                if (A1 < 0) { X0 = 0; ncols = 0; }
-                const int n4 = (n + 3) & ~3;                             // weight runs start 16 B aligned
-                const int xsum = __reduce_add_sync(FULL, n4);
-                if (xsum + 8 > wx_cap) { ncols = -1; n = 0; }
-                int off = 0;                                             // exclusive scan of the padded x runs
-#pragma unroll
-                for (int qq = 0; qq < P; ++qq) {
-                    const int nq = __shfl_sync(FULL, n4, qq);
-                    if (qq < p) off += nq;
-                }
-                mbar_wait(&plan_empty[b], eparity);
-                if (lane == 0) { ps.X0 = X0; ps.ncols = ncols; }
-                if (lane < P) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = ncols < 0 ? 0 : off; }
-                if (n > 0) {
-                    float *w = wx + off;
-                    for (int i = 0; i < n4; ++i) w[i] = 0.f;
-                    for (int i = 0; i < grid; ++i) {
-                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                        if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
-                    }
-                }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&plan_full[b]);
+            trace(debug_mode, k, 3, lane);
+            if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
             ++k;
+            if (++b == kPlanSlots) { b = 0; eparity ^= 1; }
         }
     } else if (warp == P) {
         // ===== producer: bulk async copies of footprint rows, ring runs across items =======================
-        int s = 0, par = 1;                                              // parity 1: first pass over a fresh barrier
+        const uint32_t ring32 = smem_u32(ring);
+        int s = 0;
+        unsigned par = 1;                                                // parity 1: first pass over a fresh barrier
+        int b = 0;
+        unsigned fparity = 0;
         for (int k = 0;; ++k) {
-            const int b = k % kPlanSlots;
-            mbar_wait(&plan_full[b], (k / kPlanSlots) & 1);
+            mbar_wait32(pfull32 + 8 * b, fparity);
             const WinSlot<P> &ps = slot[b];
             if (ps.r < 0) break;
             const int cbn = min(CB, C - ps.cb0);
             const bool rowcopy = (C == CB);                              // a row segment is one contiguous run
-            const RingPlan rg = ring_plan(ps.nrows < 0 ? 0 : ps.ncols, ps.ncols < 0 ? 0 : ps.nrows);
-            const int nrows = rg.nrows, ncols = rg.ncols, nstages = rg.nstages, rps = rg.rps, nseg = rg.nseg;
+            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
             const float *fbase = pyr.feat[ps.level] + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
                                  + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
             const size_t row_pitch = (size_t)ps.W * C;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&plan_empty[b]);                  // everything needed is in registers now
+            if (lane == 0) mbar_arrive32(pempty32 + 8 * b);              // everything needed is in registers now
+            if (++b == kPlanSlots) { b = 0; fparity ^= 1; }
+            trace(debug_mode, k, 6, lane);
             int row0 = 0, col0 = 0;
             for (int st = 0; st < nstages; ++st) {
                 int nr, nc;
                 if (nseg == 1) { nr = min(rps, nrows - row0); nc = ncols; }
                 else           { nr = 1; nc = min(kStageCells, ncols - col0); }
-                mbar_wait(&empty_bar[s], par);
-                float *dst = ring + (size_t)s * kStageCells * CB;
-                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * nc * cbn * 4));
-                __syncwarp();
-                const float *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
-                if (rowcopy) {
-                    if (lane < nr)
-                        bulk_g2s(dst + (size_t)lane * nc * CB, src + (size_t)lane * row_pitch,
-                                 (uint32_t)(nc * CB * 4), &full_bar[s]);
+                mbar_wait32(empty32 + 8 * s, par);
+                const uint32_t dst = ring32 + (uint32_t)s * (kStageFloats * 4), fb = full32 + 8 * s;
+                if (debug_mode & 1) {
+                    if (lane == 0) mbar_arrive32(fb);
                 } else {
-                    for (int cell = lane; cell < nr * nc; cell += 32) {
-                        const int rr = cell / nc, cc = cell - rr * nc;
-                        bulk_g2s(dst + (size_t)cell * CB, src + (size_t)rr * row_pitch + (size_t)cc * C,
-                                 (uint32_t)(cbn * 4), &full_bar[s]);
+                    if (lane == 0) mbar_expect_tx32(fb, (uint32_t)(nr * nc * cbn * 4));
+                    __syncwarp();
+                    const float *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
+                    if (rowcopy) {
+                        if (lane < nr)
+                            bulk_g2s32(dst + (uint32_t)(lane * nc) * (CB * 4), src + (size_t)lane * row_pitch,
+                                       (uint32_t)(nc * CB * 4), fb);
+                    } else {
+                        for (int cell = lane; cell < nr * nc; cell += 32) {
+                            const int rr = cell / nc, cc = cell - rr * nc;
+                            bulk_g2s32(dst + (uint32_t)cell * (CB * 4), src + (size_t)rr * row_pitch + (size_t)cc * C,
+                                       (uint32_t)(cbn * 4), fb);
+                        }
                     }
                 }
                 if (nseg == 1) row0 += nr;
                 else { col0 += nc; if (col0 >= ncols) { col0 = 0; ++row0; } }
                 if (++s == NS) { s = 0; par ^= 1; }
             }
+            trace(debug_mode, k, 7, lane);
         }
     } else {
         // ===== consumers: warp = bin column pw ==============================================================
         const int pw = warp;
-        int s = 0, par = 0;
+        const int lch = lane * 4;                        // lane -> channels [4*lane, 4*lane+4) + 128*v of the block
+        int s = 0;
+        unsigned par = 0;
+        int b = 0;
+        unsigned fparity = 0;
         for (int k = 0;; ++k) {
-            const int b = k % kPlanSlots;
-            mbar_wait(&plan_full[b], (k / kPlanSlots) & 1);
+            mbar_wait32(pfull32 + 8 * b, fparity);
             const WinSlot<P> &ps = slot[b];
             const int r = ps.r;
             if (r < 0) break;
+            if (pw == 0) trace(debug_mode, k, 8, lane);
             const float *wx = wtab + (size_t)b * wslot;
-            const float4 *wrow = reinterpret_cast<const float4 *>(wx + wx_cap);
+            const float4 *wr = reinterpret_cast<const float4 *>(wx + wx_cap);   // y weights of the next footprint row
             const int cb0 = ps.cb0, cbn = min(CB, C - cb0);
-            const RingPlan rg = ring_plan(ps.nrows < 0 ? 0 : ps.ncols, ps.ncols < 0 ? 0 : ps.nrows);
-            const int nrows = rg.nrows, ncols = rg.ncols, nstages = rg.nstages, rps = rg.rps, nseg = rg.nseg;
+            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
             const int xlo = ps.xlo[pw] - ps.X0, nx = ps.xn[pw];
             const float *wxp = wx + ps.xoff[pw];
-            const int pb = ps.pb;
             const float inv = 1.0f / ps.count;          // count is a small exact integer; <= 1 ulp vs acc/count
-            int base = ps.pa;
-            int hi_cur = ps.hi[base];
-            // lane -> channels [4*lane, 4*lane+4) + 128*v of the block.  Lanes past the channel count of a
-            // ragged last block read stale ring bytes (the cell stride is CB) and never store.
-            const int lch = lane * 4;
+            const int *hip = &ps.hi[ps.pa];              // last footprint row of the window's first bin, next bins
+            int bins_left = ps.pb - ps.pa;               // bin rows of the item not stored yet
+            int rows_left = *hip + 1;                    // footprint rows before the window's first bin is complete
+            int prev_hi = *hip;
+            // Lanes past the channel count of a ragged last block read stale ring bytes (the cell stride is CB)
+            // and never store.
             float4 cs[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) cs[v] = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -374,7 +409,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 for (int v = 0; v < VEC; ++v)
                     if (v * 128 + lch < cbn) cs[v] = ldg4(chan_scale + (size_t)si * C + cb0 + v * 128 + lch);
             }
-            float *obase = out + ((size_t)r * P * P + pw) * C + cb0 + lch;
+            float *op = out + ((size_t)(r * P + ps.pa) * P + pw) * C + cb0 + lch;   // output of the window's first bin
             // the bin column's weights live in registers for the whole item (runs are padded to 4 floats and
             // the table has 8 floats of slack, so reading 8 is always in bounds; entries past nx are unused)
             float wreg[8];
@@ -383,6 +418,8 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 wreg[0] = w0.x; wreg[1] = w0.y; wreg[2] = w0.z; wreg[3] = w0.w;
                 wreg[4] = w1.x; wreg[5] = w1.y; wreg[6] = w1.z; wreg[7] = w1.w;
             }
+            __syncwarp();
+            // (the slot's header is in registers; its tables are read until the last row)
 
             float4 a[kWin][VEC], racc[VEC];
 #pragma unroll
@@ -392,7 +429,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
 #pragma unroll
             for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-            // store bin row `base` (window slot 0) and slide the window down by one
+            // store the window's first bin row and slide the window down by one
             auto rotate = [&]() {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
@@ -402,19 +439,31 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         o = make_float4(qv.x * inv * cs[v].x, qv.y * inv * cs[v].y, qv.z * inv * cs[v].z, qv.w * inv * cs[v].w);
                     else
                         o = make_float4(qv.x * inv, qv.y * inv, qv.z * inv, qv.w * inv);
-                    if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(obase + (size_t)base * P * C + v * 128) = o;
+                    if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(op + v * 128) = o;
 #pragma unroll
                     for (int w = 0; w + 1 < kWin; ++w) a[w][v] = a[w + 1][v];
                     a[kWin - 1][v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                ++base;
+                op += (size_t)P * C;
+                --bins_left;
             };
-            // footprint row j is complete in racc: fold it into the window
-            auto fold = [&](int j) {
-                while (j > hi_cur) { rotate(); hi_cur = base < pb ? ps.hi[base] : 0x7fffffff; }
-                const float4 w4 = wrow[j];
+            // the footprint row in racc is complete: fold it into the window
+            auto fold = [&]() {
+                while (rows_left <= 0) {                 // the row lies past the window's first bin: store it, slide
+                    rotate();
+                    ++hip;
+                    const int h = bins_left > 0 ? *hip : 0x3fffffff;
+                    rows_left += h - prev_hi;
+                    prev_hi = h;
+                }
+                --rows_left;
+                const float4 w4 = *wr++;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { fma4x2(a[0][v], w4.x, racc[v]); fma4x2(a[1][v], w4.y, racc[v]); }
+                for (int v = 0; v < VEC; ++v) fma4x2(a[0][v], w4.x, racc[v]);
+                if (w4.y != 0.f) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) fma4x2(a[1][v], w4.y, racc[v]);
+                }
                 if (w4.z != 0.f || w4.w != 0.f) {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) { fma4x2(a[2][v], w4.z, racc[v]); fma4x2(a[3][v], w4.w, racc[v]); }
@@ -428,46 +477,59 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                           \
         fma4x2(racc[v], wreg[i], *reinterpret_cast<const float4 *>(rp + (i) * CB + v * 128))
 
-            if (nseg == 1) {
-                int row = 0;
+            // Row pass over whole-row stages, specialised on the number of cells NX of this warp's bin column
+            // (constant over the item; NX = 0 is the generic loop): straight-line LDS / packed-FMA code per row.
+            auto run_rows = [&](auto nx_tag) {
+                constexpr int NX = decltype(nx_tag)::value;
+                int rows_todo = nrows;
                 const int rstride = ncols * CB;
+                const float *sp = ring + (size_t)s * kStageFloats + xlo * CB + lch;   // this warp's first cell in stage s
                 for (int st = 0; st < nstages; ++st) {
-                    const int nr = min(rps, nrows - row);
-                    mbar_wait(&full_bar[s], par);
-                    const float *rp = ring + (size_t)s * kStageCells * CB + xlo * CB + lch;
-                    for (int rr = 0; rr < nr; ++rr, ++row, rp += rstride) {
-                        switch (nx) {                    // constant over the item: one jump per row
-                        case 1: FGN_CELL0(); break;
-                        case 2: FGN_CELL0(); FGN_CELL(1); break;
-                        case 3: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); break;
-                        case 4: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); break;
-                        case 5: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); break;
-                        case 6: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); break;
-                        case 7: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); FGN_CELL(6); break;
-                        case 8: FGN_CELL0(); FGN_CELL(1); FGN_CELL(2); FGN_CELL(3); FGN_CELL(4); FGN_CELL(5); FGN_CELL(6); FGN_CELL(7); break;
-                        default: {
+                    const int nr = min(rps, rows_todo);
+                    rows_todo -= nr;
+                    mbar_wait32(full32 + 8 * s, par);
+                    const float *rp = sp;
+                    for (int rr = 0; rr < nr; ++rr, rp += rstride) {
+                        if (!(debug_mode & 2)) {
+                            if (NX > 0) {
+                                FGN_CELL0();
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float *cp = rp;
-                            for (int i = 0; i < nx; ++i, cp += CB) {
-                                const float w = wxp[i];
+                                for (int i = 1; i < NX; ++i) { FGN_CELL(i); }
+                            } else {
 #pragma unroll
-                                for (int v = 0; v < VEC; ++v) fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(cp + v * 128));
+                                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float *cp = rp;
+                                for (int i = 0; i < nx; ++i, cp += CB) {
+                                    const float w = wxp[i];
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(cp + v * 128));
+                                }
                             }
-                        } break;
                         }
-                        fold(row);
+                        fold();
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[s]);
-                    if (++s == NS) { s = 0; par ^= 1; }
+                    if (lane == 0) mbar_arrive32(empty32 + 8 * s);
+                    sp += kStageFloats;
+                    if (++s == NS) { s = 0; par ^= 1; sp -= (size_t)NS * kStageFloats; }
+                }
+            };
+            if (nseg == 1) {
+                switch (nx) {
+                case 1: run_rows(IntTag<1>{}); break;
+                case 2: run_rows(IntTag<2>{}); break;
+                case 3: run_rows(IntTag<3>{}); break;
+                case 4: run_rows(IntTag<4>{}); break;
+                case 5: run_rows(IntTag<5>{}); break;
+                case 6: run_rows(IntTag<6>{}); break;
+                default: run_rows(IntTag<0>{}); break;
                 }
             } else {
                 for (int row = 0; row < nrows; ++row)
                     for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
                         const int nc = min(kStageCells, ncols - col0);
-                        mbar_wait(&full_bar[s], par);
-                        const float *sb = ring + (size_t)s * kStageCells * CB + lch;
+                        mbar_wait32(full32 + 8 * s, par);
+                        const float *sb = ring + (size_t)s * kStageFloats + lch;
                         const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
                         for (int cx = c_beg; cx < c_end; ++cx) {
                             const float w = wxp[cx - xlo];
@@ -476,20 +538,23 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                                 fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(sb + (cx - col0) * CB + v * 128));
                         }
                         if (col0 + nc >= ncols) {
-                            fold(row);
+                            fold();
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[s]);
+                        if (lane == 0) mbar_arrive32(empty32 + 8 * s);
                         if (++s == NS) { s = 0; par ^= 1; }
                     }
             }
 #undef FGN_CELL0
 #undef FGN_CELL
+            if (pw == 0) trace(debug_mode, k, 9, lane);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&plan_empty[b]);  // the slot's tables are no longer needed
-            while (base < pb) rotate();                  // bins below the last footprint row (or with no samples)
+            if (lane == 0) mbar_arrive32(pempty32 + 8 * b);  // the slot's tables are no longer needed
+            if (++b == kPlanSlots) { b = 0; fparity ^= 1; }
+            while (bins_left > 0) rotate();              // bins below the last footprint row (or with no samples)
+            if (pw == 0) trace(debug_mode, k, 10, lane);
         }
     }
 }
@@ -507,8 +572,8 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const int wx_cap = (maxW + 9 * P + 24 + 3) & ~3;           // touched cells <= extent + 2 per bin boundary, runs padded to 4, 8 slack
     const int wyd_rows = maxH;
     const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * (wx_cap + 4 * wyd_rows) * 4;
-    const size_t cap = MINB == 2 ? 115200 : 230000;            // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
-    if (smem > cap) { *taken = false; return FGN_OK; }
+    const size_t smem_cap = MINB == 2 ? 115200 : 230000;           // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
+    if (smem > smem_cap) { *taken = false; return FGN_OK; }
     auto kern = roi_align_window_kernel<P, VEC, NS, MINB>;
     static int attr_set = 0;                                   // per instantiation
     if ((int)smem > attr_set) {
@@ -521,16 +586,32 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
         FGN_CUDA_OK(cudaGetDevice(&dev));
         FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    static unsigned int launch_seq = 0;                        // one ticket counter per launch in flight (graphs bake theirs in)
-    const int slot = (int)(launch_seq++ % kTicketSlots);
+    // One ticket counter per launch that can be in flight.  A launch captured into a CUDA graph bakes its
+    // counter in and may run at any later time, so captured launches draw from a range that is never
+    // recycled (when it is exhausted the caller falls back to the non-persistent kernel); eager launches
+    // cycle through the other half, far more slots than launches can be in flight at once.
+    static unsigned int eager_seq = 0, captured_seq = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    FGN_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+    int slot;
+    if (cap != cudaStreamCaptureStatusNone) {
+        if (captured_seq >= kTicketSlots / 2) { *taken = false; return FGN_OK; }
+        slot = (int)captured_seq++;
+    } else {
+        slot = (int)(kTicketSlots / 2 + (eager_seq++ % (kTicketSlots / 2)));
+    }
     const int nblk = (C + CB - 1) / CB;
     const char *e = getenv("FGN_RA_SPLIT");
     const float split_cells = e != nullptr ? (float)atof(e) : 512.f;
-    const int grid = min(MINB * sm_count, R * nblk);
+    const char *eg = getenv("FGN_RA_CTAS");                   // development knob: persistent CTAs per SM (<= MINB)
+    const int per_sm = eg != nullptr ? max(1, min(MINB, atoi(eg))) : MINB;
+    const int grid = min(per_sm * sm_count, R * nblk);
+    const char *ed = getenv("FGN_RA_DEBUG");
+    const int dbg = ed != nullptr ? atoi(ed) : 0;
     (void)CB;
-    kern<<<grid, (P + 3) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+    kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                            scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
-                                           split_cells > 0.f ? split_cells : 3.0e38f);
+                                           split_cells > 0.f ? split_cells : 3.0e38f, dbg);
     FGN_LAUNCH_OK();
     (void)S;
     *taken = true;
@@ -557,6 +638,12 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
     }
 #undef FGN_WIN
     return FGN_OK;
+}
+
+void roi_align_window_trace(unsigned long long *dst, int n)
+{
+    const int cap = kTraceCtas * kTraceItems * kTraceEvents;
+    cudaMemcpyFromSymbol(dst, g_window_trace, sizeof(unsigned long long) * (n < cap ? n : cap));
 }
 
 unsigned int roi_align_window_violations()
