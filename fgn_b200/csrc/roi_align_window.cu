@@ -96,6 +96,7 @@ __device__ __forceinline__ float4 mul4x2(const float w, const float4 v)
     return o;
 }
 
+constexpr int kSortCap = 2048;      // most RoIs per launch the sorted ticket scheme handles
 constexpr int kPlanSlots = 3;       // plans in flight per CTA (the planner runs up to two items ahead)
 
 // mbarrier ops on precomputed 32-bit shared addresses (the generic->shared conversion is done once per kernel)
@@ -167,6 +168,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ WinSlot<P> slot[kPlanSlots];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[kPlanSlots], plan_empty[kPlanSlots];
+    __shared__ unsigned int cls_mask[4][kSortCap / 32];   // size-class membership of every RoI (sorted ticket scheme)
 
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *wtab = ring + (size_t)NS * kStageFloats;
@@ -185,11 +187,48 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     }
     __syncthreads();
 
+    // Sorted ticket scheme (see the planner): while the planner works on the CTA's first RoI, the other warps
+    // classify every RoI by footprint size -- 32 RoIs per warp step, one ballot mask per class and block.
+    const bool sorted = (nblk == 1) && (R <= kSortCap) && !(debug_mode & 64);
+    const int nstatic = sorted ? (int)gridDim.x : 0;                     // grid <= R when nblk == 1
+    const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
+    if (sorted && warp <= P) {
+        for (int blk = warp; blk < nsb; blk += P + 1) {
+            const int idx = blk * 32 + lane;
+            int c = -1;
+            if (idx < R && idx >= nstatic) {
+                const float *roi = rois + 5 * (size_t)idx;
+                const int lv = roi_level(roi, pyr, finest_scale);
+                const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned);
+                const float est = (gg.bin_h * (float)P + 2.f) * (gg.bin_w * (float)P + 2.f);   // cells, from the box alone
+                c = est > 640.f ? 0 : (est > 320.f ? 1 : (est > 160.f ? 2 : 3));               // NaN -> 3
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned m = __ballot_sync(FULL, c == q);
+                if (lane == q) cls_mask[q][blk] = m;
+            }
+        }
+        // announce the masks to the planner without waiting for it (it reads them before its first lookup;
+        // blocking here could deadlock: a first RoI split into more items than plan slots needs the consumers)
+        __threadfence_block();
+        asm volatile("bar.arrive 1, %0;" ::"n"((P + 2) * 32) : "memory");
+    }
+
     if (warp == P + 1) {
         // ===== planner ===================================================================================
-        // it always holds one prefetched ticket, so a launch draws items + 2 tickets per CTA in all; the last
-        // one resets the counter for the next launch that uses this slot
-        const unsigned last_ticket = (unsigned)items + 2u * gridDim.x - 1u;
+        // Two ticket schemes.
+        //  * sorted (one channel block, R <= kSortCap): CTA i starts on RoI i with no ticket at all; while its
+        //    consumers work on that, the planner classifies every other RoI by footprint size into four classes
+        //    (ballot masks in shared memory, identical in every CTA because every CTA computes them from the
+        //    same rois) and ticket t then means "the t-th RoI in largest-class-first order".  Big footprints
+        //    start early, the launch ends on small ones, and nobody has to be split to balance the tail.
+        //  * plain (otherwise): ticket = (RoI, bin-row chunk, channel block) in index order; chunks a RoI does
+        //    not use are skipped.
+        // The planner always holds one prefetched ticket, so a launch draws ntickets + 2 per CTA in all; the
+        // last one resets the counter for the next launch that uses this slot.
+        const int ntickets = sorted ? R - nstatic : items;
+        const unsigned last_ticket = (unsigned)ntickets + 2u * gridDim.x - 1u;
         auto take = [&]() {
             unsigned int tk = 0;
             if (lane == 0) {
@@ -198,31 +237,85 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             }
             return tk;                                                   // valid in lane 0; broadcast at use
         };
+        int cls_total = 0;                                               // lane c < 4: RoIs in size class c
+        auto class_totals = [&]() {                                      // once the other warps have built the masks
+            asm volatile("bar.sync 1, %0;" ::"n"((P + 2) * 32) : "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int n = 0;
+                for (int i = lane; i < nsb; i += 32) n += __popc(cls_mask[q][i]);
+                n = __reduce_add_sync(FULL, n);
+                if (lane == q) cls_total = n;
+            }
+        };
+        auto lookup = [&](int tk) {                                      // tk-th RoI, largest class first
+            int c = 0, base = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int tq = __shfl_sync(FULL, cls_total, q);
+                if (c == q && tk >= base + tq) { base += tq; c = q + 1; }
+            }
+            int krem = tk - base, r = 0;
+            for (int b0 = 0; b0 < nsb; b0 += 32) {                       // 32 blocks per round
+                const unsigned m = (b0 + lane < nsb) ? cls_mask[c][b0 + lane] : 0u;
+                const int cnt = __popc(m);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const unsigned hit = __ballot_sync(FULL, incl > krem);
+                if (hit != 0u) {
+                    const int src = __ffs(hit) - 1;
+                    const unsigned mm = __shfl_sync(FULL, m, src);
+                    const int before = __shfl_sync(FULL, incl - cnt, src);
+                    r = (b0 + src) * 32 + (int)__fns(mm, 0, krem - before + 1);
+                    break;
+                }
+                krem -= __shfl_sync(FULL, incl, 31);
+            }
+            return r;
+        };
+
         unsigned int tnext = take();
         int k = 0, b = 0;                                                // items published so far, their slot
         unsigned eparity = 1;                                            // plan_empty: item k - kPlanSlots consumed
-        for (;;) {
-            const unsigned int ticket = __shfl_sync(FULL, tnext, 0);
-            tnext = take();                                              // in flight while this item is planned
-            trace(debug_mode, k, 0, lane);
-            WinSlot<P> &ps = slot[b];
-            if ((int)ticket >= items) {
-                mbar_wait32(pempty32 + 8 * b, eparity);
-                if (lane == 0) ps.r = -1;
-                __syncwarp();
-                if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
-                break;
+        for (unsigned int it = 0;; ++it) {
+            int r, cbi = 0, chunk_lo = 0, chunk_hi = S;                  // chunks [chunk_lo, chunk_hi) of RoI r to publish
+            if (sorted && it == 0) {
+                r = (int)blockIdx.x;
+            } else {
+                const unsigned int ticket = __shfl_sync(FULL, tnext, 0);
+                tnext = take();                                          // in flight while this item is planned
+                if (sorted && it == 1) class_totals();
+                if ((int)ticket >= ntickets) {
+                    mbar_wait32(pempty32 + 8 * b, eparity);
+                    if (lane == 0) slot[b].r = -1;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
+                    break;
+                }
+                if (sorted) r = lookup((int)ticket);
+                else {
+                    cbi = (int)ticket % nblk; chunk_lo = ((int)ticket / nblk) % S; chunk_hi = chunk_lo + 1;
+                    r = (int)ticket / (nblk * S);
+                }
             }
-            const int cbi = (int)ticket % nblk, chunk = ((int)ticket / nblk) % S, r = (int)ticket / (nblk * S);
+            trace(debug_mode, k, 0, lane);
             const float *roi = rois + 5 * (size_t)r;
             const int level = roi_level(roi, pyr, finest_scale);
             const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
             const int H = pyr.H[level], W = pyr.W[level];
             // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
-            // as S items of kWin bin rows each; big footprints are chunked too, to shorten the launch's tail
+            // as S items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
             const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
-            const bool split = S > 1 && (g.bin_h < 0.75f || est > split_cells);
-            if (chunk > 0 && !split) continue;
+            const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && est > split_cells));
+            if (!split) { if (chunk_lo > 0) continue; chunk_hi = 1; }
+            if (lane == 0 && lvl_out != nullptr && cbi == 0 && chunk_lo == 0) lvl_out[r] = level;
+
+            for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+            WinSlot<P> &ps = slot[b];
             const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
 
             // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns.  Sample coordinates are monotone in
@@ -283,7 +376,6 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 ps.pa = pa; ps.pb = pb; ps.count = g.count;
                 ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
                 ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
-                if (lvl_out != nullptr && cbi == 0 && chunk == 0) lvl_out[r] = level;
             }
             if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
             if (lane < P) ps.hi[lane] = myhi;
@@ -320,6 +412,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
             ++k;
             if (++b == kPlanSlots) { b = 0; eparity ^= 1; }
+            }   // chunks of this RoI
         }
     } else if (warp == P) {
         // ===== producer: bulk async copies of footprint rows, ring runs across items =======================
