@@ -157,7 +157,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
                         float *__restrict__ out, int32_t *__restrict__ lvl_out,
                         const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells,
-                        const int debug_mode)
+                        const float3 thr, const int debug_mode)
 {
     // debug_mode (development only): bit 0 = no copies (producer only signals), bit 1 = no row math,
     // bit 5 = record the per-CTA timeline
@@ -192,16 +192,19 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     const bool sorted = (nblk == 1) && (R <= kSortCap) && !(debug_mode & 64);
     const int nstatic = sorted ? (int)gridDim.x : 0;                     // grid <= R when nblk == 1
     const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
+    auto size_class = [&](const float *roi) {                            // 0 = largest footprints ... 3 = smallest (NaN -> 3)
+        const int lv = roi_level(roi, pyr, finest_scale);
+        const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned);
+        const float est = (gg.bin_h * (float)P + 2.f) * (gg.bin_w * (float)P + 2.f);   // cells, from the box alone
+        return est > thr.x ? 0 : (est > thr.y ? 1 : (est > thr.z ? 2 : 3));
+    };
     if (sorted && warp <= P) {
         for (int blk = warp; blk < nsb; blk += P + 1) {
             const int idx = blk * 32 + lane;
             int c = -1;
-            if (idx < R && idx >= nstatic) {
-                const float *roi = rois + 5 * (size_t)idx;
-                const int lv = roi_level(roi, pyr, finest_scale);
-                const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned);
-                const float est = (gg.bin_h * (float)P + 2.f) * (gg.bin_w * (float)P + 2.f);   // cells, from the box alone
-                c = est > 640.f ? 0 : (est > 320.f ? 1 : (est > 160.f ? 2 : 3));               // NaN -> 3
+            if (idx < R) {
+                c = size_class(rois + 5 * (size_t)idx);
+                if (idx < nstatic && c >= 2) c = -1;                     // CTA idx starts on it without a ticket
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -227,8 +230,9 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
         //    not use are skipped.
         // The planner always holds one prefetched ticket, so a launch draws ntickets + 2 per CTA in all; the
         // last one resets the counter for the next launch that uses this slot.
-        const int ntickets = sorted ? R - nstatic : items;
-        const unsigned last_ticket = (unsigned)ntickets + 2u * gridDim.x - 1u;
+        constexpr int S0 = (P + 1) / 2, S1 = (P + 3) / 4;                // chunks (of 2 / 4 bin rows) of a class 0 / 1 RoI
+        int ntickets = sorted ? 0x3fffffff : items;                      // sorted: known once the class totals are
+        unsigned last_ticket = sorted ? 0xffffffffu : (unsigned)items + 2u * gridDim.x - 1u;
         auto take = [&]() {
             unsigned int tk = 0;
             if (lane == 0) {
@@ -247,15 +251,22 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 n = __reduce_add_sync(FULL, n);
                 if (lane == q) cls_total = n;
             }
+            ntickets = __shfl_sync(FULL, cls_total, 0) * S0 + __shfl_sync(FULL, cls_total, 1) * S1
+                       + __shfl_sync(FULL, cls_total, 2) + __shfl_sync(FULL, cls_total, 3);
+            // (the one ticket this planner drew before it knew the totals is < 2 * gridDim.x - 1 <= last_ticket,
+            //  and the draw that returns exactly last_ticket comes after every planner's first, so none is missed)
+            last_ticket = (unsigned)ntickets + 2u * gridDim.x - 1u;
         };
-        auto lookup = [&](int tk) {                                      // tk-th RoI, largest class first
-            int c = 0, base = 0;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int tq = __shfl_sync(FULL, cls_total, q);
-                if (c == q && tk >= base + tq) { base += tq; c = q + 1; }
-            }
-            int krem = tk - base, r = 0;
+        auto lookup = [&](int tk, int &ba, int &bb) {                    // ticket -> (RoI, bin rows [ba, bb)), largest class first
+            const int t0 = __shfl_sync(FULL, cls_total, 0), t1 = __shfl_sync(FULL, cls_total, 1),
+                      t2 = __shfl_sync(FULL, cls_total, 2);
+            int c, krem, chunk = 0, cw = P;
+            if (tk < t0 * S0)                     { c = 0; krem = tk / S0; chunk = tk - krem * S0; cw = 2; }
+            else if ((tk -= t0 * S0) < t1 * S1)   { c = 1; krem = tk / S1; chunk = tk - krem * S1; cw = 4; }
+            else if ((tk -= t1 * S1) < t2)        { c = 2; krem = tk; }
+            else                                  { c = 3; krem = tk - t2; }
+            ba = chunk * cw; bb = min(P, ba + cw);
+            int r = 0;
             for (int b0 = 0; b0 < nsb; b0 += 32) {                       // 32 blocks per round
                 const unsigned m = (b0 + lane < nsb) ? cls_mask[c][b0 + lane] : 0u;
                 const int cnt = __popc(m);
@@ -281,14 +292,24 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
         unsigned int tnext = take();
         int k = 0, b = 0;                                                // items published so far, their slot
         unsigned eparity = 1;                                            // plan_empty: item k - kPlanSlots consumed
+        bool totals_known = false;
         for (unsigned int it = 0;; ++it) {
-            int r, cbi = 0, chunk_lo = 0, chunk_hi = S;                  // chunks [chunk_lo, chunk_hi) of RoI r to publish
-            if (sorted && it == 0) {
+            // the ticket's RoI, channel block and bin rows [ba, bb); window chunks [chunk_lo, chunk_hi) of them
+            int r = 0, cbi = 0, ba = 0, bb = P, chunk_lo = 0, chunk_hi = S;
+            bool have = false;
+            if (sorted && it == 0) {                                     // small first RoI: start on it right away
                 r = (int)blockIdx.x;
-            } else {
+                have = size_class(rois + 5 * (size_t)r) >= 2;
+            }
+            if (!have) {
                 const unsigned int ticket = __shfl_sync(FULL, tnext, 0);
+                if (sorted && !totals_known) {
+                    class_totals();
+                    totals_known = true;
+                    // `ticket` was drawn before last_ticket was known (a CTA that starts late can draw the last one)
+                    if (lane == 0 && ticket == last_ticket) g_window_ticket[ticket_slot] = 0u;
+                }
                 tnext = take();                                          // in flight while this item is planned
-                if (sorted && it == 1) class_totals();
                 if ((int)ticket >= ntickets) {
                     mbar_wait32(pempty32 + 8 * b, eparity);
                     if (lane == 0) slot[b].r = -1;
@@ -296,7 +317,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
                     break;
                 }
-                if (sorted) r = lookup((int)ticket);
+                if (sorted) r = lookup((int)ticket, ba, bb);
                 else {
                     cbi = (int)ticket % nblk; chunk_lo = ((int)ticket / nblk) % S; chunk_hi = chunk_lo + 1;
                     r = (int)ticket / (nblk * S);
@@ -308,15 +329,16 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
             const int H = pyr.H[level], W = pyr.W[level];
             // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
-            // as S items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
+            // as items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
             const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
             const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && est > split_cells));
             if (!split) { if (chunk_lo > 0) continue; chunk_hi = 1; }
-            if (lane == 0 && lvl_out != nullptr && cbi == 0 && chunk_lo == 0) lvl_out[r] = level;
+            else if (sorted) chunk_hi = (bb - ba + kWin - 1) / kWin;
+            if (lane == 0 && lvl_out != nullptr && cbi == 0 && chunk_lo == 0 && ba == 0) lvl_out[r] = level;
 
             for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
             WinSlot<P> &ps = slot[b];
-            const int pa = split ? chunk * kWin : 0, pb = split ? min(P, pa + kWin) : P;
+            const int pa = split ? ba + chunk * kWin : ba, pb = split ? min(bb, pa + kWin) : bb;
 
             // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns.  Sample coordinates are monotone in
             // the sample index, so when the first and last sample of a bin are valid they bound its cells.
@@ -381,29 +403,29 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             if (lane < P) ps.hi[lane] = myhi;
             for (int i = lane; i < nrows; i += 32)
                 reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = lane; i < (xsum >> 2); i += 32)
+                reinterpret_cast<float4 *>(wx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
             if (nstages > 0 && n > 0) {
-                if (isx) {
-                    float *w = wx + off;
-                    for (int i = 0; i < n4; ++i) w[i] = 0.f;
-                    for (int i = 0; i < grid; ++i) {
-                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                        if (sm.valid) { w[sm.low - lo] += sm.h; w[sm.high - lo] += sm.l; }
-                    }
-                } else if (isy) {
-                    // footprint row j lives in window slot (p - base_j), base_j = first bin row of the item
-                    // whose (running-max) last row is >= j
-                    auto put = [&](int j, float wgt) {
-                        int base = pa;
+                // Both axes run ONE instruction stream: a sample adds its two bilinear weights to two entries of
+                // the slot's table.  x: entry = run offset + cell.  y: footprint row j lives in window slot
+                // (p - base_j) of wrow[j], base_j = first bin row of the item whose (running-max) last row is >= j.
+                auto entry = [&](int cell) {
+                    if (isx) return off + cell - lo;
+                    const int j = cell - Y0;
+                    int base = pa;
 #pragma unroll
-                        for (int qq = 0; qq < P; ++qq) base += (qq >= pa && qq < pb && hiall[qq] < j) ? 1 : 0;
-                        const int comp = p - base;
-                        if (comp >= 0 && comp < kWin) wrow[4 * j + comp] += wgt;
-                        else atomicAdd(&g_window_violation, 1u);
-                    };
-                    for (int i = 0; i < grid; ++i) {
-                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                        if (sm.valid) { put(sm.low - Y0, sm.h); put(sm.high - Y0, sm.l); }
+                    for (int qq = 0; qq < P; ++qq) base += (qq >= pa && qq < pb && hiall[qq] < j) ? 1 : 0;
+                    const int comp = p - base;
+                    if (comp < 0 || comp >= kWin) { atomicAdd(&g_window_violation, 1u); return -1; }
+                    return wx_cap + 4 * j + comp;
+                };
+                for (int i = 0; i < grid; ++i) {
+                    const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                    if (sm.valid) {
+                        const int e0 = entry(sm.low), e1 = entry(sm.high);
+                        if (e0 >= 0) wx[e0] += sm.h;
+                        if (e1 >= 0) wx[e1] += sm.l;
                     }
                 }
             }
@@ -699,12 +721,15 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const char *eg = getenv("FGN_RA_CTAS");                   // development knob: persistent CTAs per SM (<= MINB)
     const int per_sm = eg != nullptr ? max(1, min(MINB, atoi(eg))) : MINB;
     const int grid = min(per_sm * sm_count, R * nblk);
+    // size classes of the sorted ticket scheme (footprint cells): > x: 4 chunks, > y: 2 chunks, > z / rest: whole
+    float3 thr = make_float3(1000.f, 500.f, 250.f);
+    if (const char *et = getenv("FGN_RA_THR")) sscanf(et, "%f,%f,%f", &thr.x, &thr.y, &thr.z);
     const char *ed = getenv("FGN_RA_DEBUG");
     const int dbg = ed != nullptr ? atoi(ed) : 0;
     (void)CB;
     kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                            scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
-                                           split_cells > 0.f ? split_cells : 3.0e38f, dbg);
+                                           split_cells > 0.f ? split_cells : 3.0e38f, thr, dbg);
     FGN_LAUNCH_OK();
     (void)S;
     *taken = true;

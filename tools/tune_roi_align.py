@@ -55,7 +55,7 @@ knobs = {"FGN_RA_NB": [1, 2, 3, 4, 6, 8], "FGN_RA_CB": [128, 256]}
 extra = [a for a in sys.argv[3:]]
 for e in extra:           # e.g. FGN_RA_X=1,2
     k, v = e.split("=")
-    knobs[k] = [int(x) for x in v.split(",")]
+    knobs[k] = [x for x in v.split(";")] if k == "FGN_RA_THR" else [int(x) for x in v.split(",")]
 keys = list(knobs)
 for combo in itertools.product(*[knobs[k] for k in keys]):
     for k, v in zip(keys, combo):
