@@ -150,7 +150,7 @@ __device__ __forceinline__ void trace(int debug_mode, int item, int ev, int lane
 
 // Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
 // Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
-template <int P, int VEC, int NS, int MINB>
+template <int P, int VEC, int NS, int MINB, bool SCALED>
 __global__ void __launch_bounds__((P + 2) * 32, MINB)
 roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
                         const int sampling_ratio, const int aligned, const float finest_scale,
@@ -515,10 +515,10 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             int prev_hi = *hip;
             // Lanes past the channel count of a ragged last block read stale ring bytes (the cell stride is CB)
             // and never store.
-            float4 cs[VEC];
+            float4 cs[SCALED ? VEC : 1];                 // AG-FCN channel attention of this RoI (SCALED kernels only)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) cs[v] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (chan_scale != nullptr) {
+            for (int v = 0; v < (SCALED ? VEC : 1); ++v) cs[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (SCALED) {
                 const int si = scale_index != nullptr ? scale_index[r] : r;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
@@ -550,8 +550,10 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 for (int v = 0; v < VEC; ++v) {
                     const float4 qv = a[0][v];
                     float4 o;
-                    if (chan_scale != nullptr)          // (acc * 1/count) * vec, same rounding order as unfused
-                        o = make_float4(qv.x * inv * cs[v].x, qv.y * inv * cs[v].y, qv.z * inv * cs[v].z, qv.w * inv * cs[v].w);
+                    if (SCALED) {                       // (acc * 1/count) * vec, same rounding order as unfused
+                        const float4 c4 = cs[SCALED ? v : 0];
+                        o = make_float4(qv.x * inv * c4.x, qv.y * inv * c4.y, qv.z * inv * c4.z, qv.w * inv * c4.w);
+                    }
                     else
                         o = make_float4(qv.x * inv, qv.y * inv, qv.z * inv, qv.w * inv);
                     if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(op + v * 128) = o;
@@ -607,9 +609,17 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     for (int rr = 0; rr < nr; ++rr, rp += rstride) {
                         if (!(debug_mode & 2)) {
                             if (NX > 0) {
-                                FGN_CELL0();
+                                // one channel half at a time: all NX loads of the half are issued back to back
+                                // into their own registers, then the packed-FMA chain (first cell: MUL)
 #pragma unroll
-                                for (int i = 1; i < NX; ++i) { FGN_CELL(i); }
+                                for (int v = 0; v < VEC; ++v) {
+                                    float4 cell[NX > 0 ? NX : 1];
+#pragma unroll
+                                    for (int i = 0; i < NX; ++i) cell[i] = *reinterpret_cast<const float4 *>(rp + i * CB + v * 128);
+                                    racc[v] = mul4x2(wreg[0], cell[0]);
+#pragma unroll
+                                    for (int i = 1; i < NX; ++i) fma4x2(racc[v], wreg[i], cell[i]);
+                                }
                             } else {
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -689,11 +699,13 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * (wx_cap + 4 * wyd_rows) * 4;
     const size_t smem_cap = MINB == 2 ? 115200 : 230000;           // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
     if (smem > smem_cap) { *taken = false; return FGN_OK; }
-    auto kern = roi_align_window_kernel<P, VEC, NS, MINB>;
-    static int attr_set = 0;                                   // per instantiation
-    if ((int)smem > attr_set) {
+    auto kern = chan_scale != nullptr ? roi_align_window_kernel<P, VEC, NS, MINB, true>
+                                      : roi_align_window_kernel<P, VEC, NS, MINB, false>;
+    static int attr_set[2] = {0, 0};                           // per instantiation and kernel flavour
+    int &attr = attr_set[chan_scale != nullptr ? 1 : 0];
+    if ((int)smem > attr) {
         FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = (int)smem;
+        attr = (int)smem;
     }
     static int sm_count = 0;
     if (sm_count == 0) {
