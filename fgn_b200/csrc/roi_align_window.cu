@@ -457,6 +457,29 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             if (lane == 0) mbar_arrive32(pempty32 + 8 * b);              // everything needed is in registers now
             if (++b == kPlanSlots) { b = 0; fparity ^= 1; }
             trace(debug_mode, k, 6, lane);
+            if (rowcopy && nseg == 1 && !(debug_mode & 1)) {
+                // Common case, kept short because this warp's latency per stage bounds the whole pipeline: a stage
+                // is rps whole rows; lane i owns row i of every stage, so its source and destination only advance
+                // by constants.  (No ordering is needed between lane 0's expect_tx and the other lanes' copies:
+                // the phase cannot complete before the expect_tx arrival.)
+                const uint32_t row_bytes = (uint32_t)ncols * (CB * 4);
+                const float *src = fbase + (size_t)lane * row_pitch;
+                const size_t src_step = (size_t)rps * row_pitch;
+                const uint32_t dst_lane = ring32 + (uint32_t)lane * row_bytes;
+                int rows_left = nrows;
+                for (int st = 0; st < nstages; ++st) {
+                    const int nr = min(rps, rows_left);
+                    rows_left -= nr;
+                    mbar_wait32(empty32 + 8 * s, par);
+                    const uint32_t fb = full32 + 8 * s;
+                    if (lane == 0) mbar_expect_tx32(fb, (uint32_t)nr * row_bytes);
+                    if (lane < nr) bulk_g2s32(dst_lane + (uint32_t)s * (kStageFloats * 4), src, row_bytes, fb);
+                    src += src_step;
+                    if (++s == NS) { s = 0; par ^= 1; }
+                }
+                trace(debug_mode, k, 7, lane);
+                continue;
+            }
             int row0 = 0, col0 = 0;
             for (int st = 0; st < nstages; ++st) {
                 int nr, nc;
