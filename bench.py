@@ -358,8 +358,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-                # (profiles/r01_roi_align_stream_ncu.txt): 97.7 MB + 29.8 MB
-                "traffic": 127.5e6 if cfg.name == WORKLOAD else None}
+                # (profiles/r01_roi_align_window_ncu.txt): 96.2 MB + 27.3 MB
+                "traffic": 123.4e6 if cfg.name == WORKLOAD else None}
 
     # ---- bf16 variant, reported separately (bf16 NHWC maps + bf16 contraction operands; stated tolerance 3e-2
     #      abs on logits, see tests/test_gpu_parity.py::test_bf16_guided_path_variant)
