@@ -236,6 +236,39 @@ def test_roi_align_window_kernel_chunked_and_ragged(P, C, B, monkeypatch):
     assert _lib.load().fgn_debug_roi_window_violations() == 0
 
 
+def test_roi_align_window_ticket_schemes():
+    """The window kernel's two ticket schemes give the same answer: R above its sort capacity (plain tickets in
+    index order), R below the number of resident CTAs (every RoI is some CTA's first, ticket-less item), the
+    sorted scheme switched off, and the default -- all bitwise equal to the row-streaming kernel."""
+    from fgn_b200 import _lib, ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(4242)
+    strides, B, C = [4, 8, 16, 32], 2, 256
+    feats = [torch.randn(B, C, 160 // s, 224 // s, generator=g) for s in strides]
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    scales = [1 / s for s in strides]
+    for R in (2500, 1100, 40):
+        rois = synth_rois(g, R, 160, 224, B, smin=6.0)
+        rd = rois.to(dev())
+        got, lvl = ops.roi_align_multilevel(fd, rd, scales, 7, 0, True, out_format="nhwc", return_levels=True)
+        assert torch.equal(lvl.cpu(), O.map_roi_levels_c(rois, 4))
+        want, _ = O.single_roi_extractor(feats, rois[:: max(1, R // 200)], strides, 7, 0, True, 56.0, "tv")
+        close(got[:: max(1, R // 200)], want, what=f"window R={R} vs oracle")
+        os.environ["FGN_RA_DEBUG"] = "64"                      # sorted tickets off
+        try:
+            plain = ops.roi_align_multilevel(fd, rd, scales, 7, 0, True, out_format="nhwc")
+        finally:
+            del os.environ["FGN_RA_DEBUG"]
+        os.environ["FGN_RA_IMPL"] = "2"
+        try:
+            ref = ops.roi_align_multilevel(fd, rd, scales, 7, 0, True, out_format="nhwc")
+        finally:
+            del os.environ["FGN_RA_IMPL"]
+        assert torch.equal(got, ref) and torch.equal(plain, ref), f"R={R}"
+    torch.cuda.synchronize()
+    assert _lib.load().fgn_debug_roi_window_violations() == 0
+
+
 def test_roi_align_edge_cases():
     from fgn_b200 import ops
     f = torch.randn(1, 8, 12, 12, device=dev()).contiguous(memory_format=torch.channels_last)
