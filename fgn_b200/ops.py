@@ -510,3 +510,53 @@ def cls_bbox_reassemble(raw_cls: torch.Tensor, raw_reg: torch.Tensor, rois_amoun
                                                    cls.data_ptr(), reg.data_ptr(), _stream()),
                "fgn_cls_bbox_reassemble")
     return cls, reg
+
+
+def det_postprocess(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torch.Tensor, num_per_img: Sequence[int],
+                    img_shapes: Optional[Sequence[Sequence[float]]] = None,
+                    scale_factors: Optional[Sequence[Sequence[float]]] = None,
+                    score_thr: float = 0.05, iou_thr: float = 0.5, max_per_img: int = 100,
+                    means: Sequence[float] = (0., 0., 0., 0.), stds: Sequence[float] = (0.1, 0.1, 0.2, 0.2),
+                    wh_ratio_clip: float = 16 / 1000):
+    """BBoxHead.get_bboxes [3P] per image (fgn_roi_head.py:606-613): softmax, delta decode, clip / rescale,
+    multiclass NMS, top ``max_per_img``.  ``rois`` [R,5] grouped by image, ``num_per_img`` the per-image counts
+    (host ints, as in the reference's ``rois.split``), ``img_shapes`` [(h, w, ...)] or None, ``scale_factors``
+    [4 floats per image] or None (= rescale False).
+    Returns ``(det [B,max_per_img,5], labels [B,max_per_img] int32, counts [B] int32)`` on the device; rows past
+    ``counts[b]`` are unspecified (see FGNRoIHead.simple_test_bboxes for the list-of-tensors form)."""
+    _need_cuda(rois, cls_score, bbox_pred)
+    rois = _f32(rois, "rois").contiguous()
+    cls_score = _f32(cls_score, "cls_score").contiguous()
+    bbox_pred = _f32(bbox_pred, "bbox_pred").contiguous()
+    r, b = rois.shape[0], len(num_per_img)
+    if b < 1 or sum(int(x) for x in num_per_img) != r:
+        raise FgnError("num_per_img must sum to the number of rois")
+    n = cls_score.shape[1] - 1
+    if cls_score.shape[0] != r or n < 1 or tuple(bbox_pred.shape) != (r, 4 * n):
+        raise FgnError(f"cls_score {tuple(cls_score.shape)} / bbox_pred {tuple(bbox_pred.shape)} do not match R={r}")
+    dev = rois.device
+    det = torch.empty((b, max_per_img, 5), device=dev, dtype=torch.float32)
+    lab = torch.empty((b, max_per_img), device=dev, dtype=torch.int32)
+    cnt = torch.empty((b,), device=dev, dtype=torch.int32)
+    offs, acc = [0], 0
+    for x in num_per_img:
+        acc += int(x)
+        offs.append(acc)
+    rmax = max(int(x) for x in num_per_img)
+    off_t = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+    hw_t = None
+    if img_shapes is not None:
+        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32).to(dev, non_blocking=True)
+    sf_t = None
+    if scale_factors is not None:
+        sf_t = torch.tensor([[float(v) for v in s] for s in scale_factors], dtype=torch.float32).reshape(b, 4).to(dev, non_blocking=True)
+    lib = _lib.load()
+    nbytes = int(lib.fgn_det_postprocess_workspace_bytes(r, n, b, rmax))
+    ws = torch.empty((max(nbytes, 256),), device=dev, dtype=torch.uint8)
+    m4 = (ctypes.c_float * 4)(*[float(v) for v in means])
+    s4 = (ctypes.c_float * 4)(*[float(v) for v in stds])
+    _lib.check(lib.fgn_det_postprocess(_ptr(rois), _ptr(cls_score), _ptr(bbox_pred), _ptr(off_t), r, n, b, rmax,
+                                       _ptr(hw_t), _ptr(sf_t), m4, s4, float(wh_ratio_clip), float(score_thr),
+                                       float(iou_thr), int(max_per_img), det.data_ptr(), lab.data_ptr(), cnt.data_ptr(),
+                                       ws.data_ptr(), nbytes, _stream()), "fgn_det_postprocess")
+    return det, lab, cnt

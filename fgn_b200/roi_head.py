@@ -68,6 +68,10 @@ class FGNBBoxHead(nn.Module):
         nn.init.xavier_normal_(self.fc_reg.weight)
         nn.init.zeros_(self.fc_cls.bias)
         nn.init.zeros_(self.fc_reg.bias)
+        # DeltaXYWHBBoxCoder of the config (fgn_r50_c4_densecl.py:91-94), used by the test-time decode
+        coder = dict(kwargs.get("bbox_coder") or {})
+        self.bbox_coder = dict(target_means=list(coder.get("target_means", [0., 0., 0., 0.])),
+                               target_stds=list(coder.get("target_stds", [0.1, 0.1, 0.2, 0.2])))
 
 
 class FGNRoIHead(nn.Module):
@@ -252,14 +256,32 @@ class FGNRoIHead(nn.Module):
         mask_pred = self.mask_head(mask_feats) if self.mask_head is not None else None
         return dict(mask_pred=mask_pred, mask_feats=mask_feats)
 
-    # ---- test-time driver (fgn_roi_head.py:531-616, 675-719), without mmdet post-processing ----
+    # ---- test-time driver (fgn_roi_head.py:531-616, 675-719) ----
     def simple_test_bboxes(self, x, img_metas, proposals: Sequence[torch.Tensor], rcnn_test_cfg=None, rescale=False):
-        """Returns per-image (cls_score, bbox_pred) splits.  mmdet's bbox_head.get_bboxes (softmax,
-        delta decode, multiclass NMS) is downstream of the hot path and is not re-implemented."""
+        """fgn_roi_head.py:531-616.  With ``rcnn_test_cfg`` (dict with ``score_thr``, ``nms=dict(iou_threshold=..)``,
+        ``max_per_img``, as fgn_r50_c4_densecl.py:181-185) and ``img_metas`` (``img_shape``, ``scale_factor``):
+        per-image ``(det_bboxes [D,5], det_labels [D] long)`` lists, i.e. bbox_head.get_bboxes [3P] on the device
+        (ops.det_postprocess).  With ``rcnn_test_cfg=None``: the raw per-image (cls_score, bbox_pred) splits."""
         rois = bbox2roi(proposals)
-        res = self._bbox_forward(x, rois, need_feats=False)
         n_per = tuple(len(p) for p in proposals)
-        return res["cls_score"].split(n_per, 0), res["bbox_pred"].split(n_per, 0)
+        if rois.shape[0] == 0:                                   # reference :558-567
+            if rcnn_test_cfg is None:
+                return [rois.new_zeros((0, 4))] * len(proposals), [rois.new_zeros((0, self.n_ways + 1))] * len(proposals)
+            return ([rois.new_zeros((0, 5))] * len(proposals),
+                    [rois.new_zeros((0,), dtype=torch.long)] * len(proposals))
+        res = self._bbox_forward(x, rois, need_feats=False)
+        if rcnn_test_cfg is None:
+            return res["cls_score"].split(n_per, 0), res["bbox_pred"].split(n_per, 0)
+        cfg = rcnn_test_cfg.get("rcnn", rcnn_test_cfg) if isinstance(rcnn_test_cfg, dict) else rcnn_test_cfg
+        shapes = [m["img_shape"] for m in img_metas] if img_metas is not None else None
+        scales = [m["scale_factor"] for m in img_metas] if (rescale and img_metas is not None) else None
+        coder = self.bbox_head.bbox_coder
+        det, lab, cnt = ops.det_postprocess(rois, res["cls_score"], res["bbox_pred"], n_per, shapes, scales,
+                                            score_thr=cfg["score_thr"], iou_thr=cfg["nms"]["iou_threshold"],
+                                            max_per_img=cfg["max_per_img"], means=coder["target_means"],
+                                            stds=coder["target_stds"])
+        counts = cnt.tolist()                                    # the reference's outputs are ragged: one host sync
+        return ([det[i, :c] for i, c in enumerate(counts)], [lab[i, :c].long() for i, c in enumerate(counts)])
 
     def simple_test_mask(self, x, det_bboxes: Sequence[torch.Tensor], det_labels: Sequence[torch.Tensor]):
         self.gather_mask_vectors(det_labels)

@@ -240,6 +240,26 @@ int fgn_attention_vectors_bwd(const float *grad_vec, int BN, int K, int C, int H
 int fgn_support_pool_bwd(const float *grad_cat, const float *grad_gap, const float *m, int BN, int K, int C, int P,
                          float *grad_f, void *stream);
 
+/* Test-time step between the relation head's outputs and the mask branch: BBoxHead.get_bboxes [3P, mmdet 2.18]
+ * as called from fgn_roi_head.py:606-613 with test_cfg.rcnn (fgn_r50_c4_densecl.py:181-185) -- softmax over the
+ * N+1 scores (background last), DeltaXYWHBBoxCoder.decode of the per-class deltas (bbox_coder, :91-94) against the
+ * proposals, clip to img_shape, optional division by scale_factor (rescale=True), multiclass_nms: score > score_thr,
+ * class-aware NMS through mmcv batched_nms' coordinate-offset trick, the max_per_img best by score.
+ *   rois [R,5] grouped by image (bbox2roi), cls_score [R,N+1], bbox_pred [R,4N];
+ *   img_offsets [B+1] int32 (device): first RoI of every image; Rmax = largest per-image RoI count;
+ *   img_hw [B,2] (h,w) or NULL (no clipping); scale_factor [B,4] or NULL (no rescale);
+ *   means/stds: HOST pointers to 4 floats; wh_ratio_clip = 16/1000 in mmdet.
+ *   det_out [B,max_per_img,5] (x1,y1,x2,y2,score), label_out [B,max_per_img], count_out [B] valid rows per image.
+ * Integer contract: which (RoI, class) pairs are kept and in what order. */
+size_t fgn_det_postprocess_workspace_bytes(int R, int N, int B, int Rmax);
+int fgn_det_postprocess(const float *rois, const float *cls_score, const float *bbox_pred,
+                        const int32_t *img_offsets, int R, int N, int B, int Rmax,
+                        const float *img_hw, const float *scale_factor,
+                        const float *means, const float *stds, float wh_ratio_clip,
+                        float score_thr, float iou_thr, int max_per_img,
+                        float *det_out, int32_t *label_out, int32_t *count_out,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* Number of kernels this library has launched in the calling process since load
  * (bench.py's gpu_launches). */
 uint64_t fgn_launch_count(void);

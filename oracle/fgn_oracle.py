@@ -23,6 +23,7 @@ Parity pin (see tests/test_oracle.py, tests/golden/make_golden.py):
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import subprocess
 from typing import List, Optional, Sequence, Tuple
@@ -307,3 +308,101 @@ def mask_attention(feats: Sequence[torch.Tensor], strides: Sequence[int], rois: 
     if shared_head is not None:
         mask_feats = shared_head(mask_feats)
     return mask_feats * vecs
+
+
+# ---- test-time box post-processing: BBoxHead.get_bboxes [3P] (called at fgn_roi_head.py:606-613) -------------
+def delta2bbox(rois4: torch.Tensor, deltas: torch.Tensor, means, stds, max_shape=None, wh_ratio_clip: float = 16 / 1000):
+    """mmdet 2.18 DeltaXYWHBBoxCoder.decode / delta2bbox [3P; mmdet absent from /root/reference, parity unpinned]:
+    restated from its published source, operation by operation.  rois4 [R,4], deltas [R,4N] -> [R,4N]."""
+    num_bboxes, num_classes = deltas.size(0), deltas.size(1) // 4
+    if num_bboxes == 0:
+        return deltas
+    deltas = deltas.reshape(-1, 4)
+    means_t = deltas.new_tensor(means).view(1, -1)
+    stds_t = deltas.new_tensor(stds).view(1, -1)
+    denorm = deltas * stds_t + means_t
+    dxy, dwh = denorm[:, :2], denorm[:, 2:]
+    rois_ = rois4.repeat(1, num_classes).reshape(-1, 4)
+    pxy = (rois_[:, :2] + rois_[:, 2:]) * 0.5
+    pwh = rois_[:, 2:] - rois_[:, :2]
+    dxy_wh = pwh * dxy
+    max_ratio = abs(math.log(wh_ratio_clip))
+    dwh = dwh.clamp(min=-max_ratio, max=max_ratio)
+    gxy = pxy + dxy_wh
+    gwh = pwh * dwh.exp()
+    x1y1 = gxy - (gwh * 0.5)
+    x2y2 = gxy + (gwh * 0.5)
+    bboxes = torch.cat([x1y1, x2y2], dim=-1)
+    if max_shape is not None:
+        bboxes[..., 0::2].clamp_(min=0, max=max_shape[1])
+        bboxes[..., 1::2].clamp_(min=0, max=max_shape[0])
+    return bboxes.reshape(num_bboxes, -1)
+
+
+def nms_greedy(boxes: torch.Tensor, scores: torch.Tensor, iou_thr: float) -> torch.Tensor:
+    """mmcv.ops.nms (offset=0) [3P] == torchvision.ops.nms: greedy suppression in (stable) descending score order,
+    IoU = inter / (area_a + area_b - inter) > thr.  Plain loops (small cases; tests pin it to torchvision's op)."""
+    order = torch.sort(scores, descending=True, stable=True).indices.tolist()
+    b = boxes.tolist()
+    f32 = np.float32
+    area = [f32(f32(x2) - f32(x1)) * f32(f32(y2) - f32(y1)) for x1, y1, x2, y2 in b]
+    dead, keep = set(), []
+    for a_pos, i in enumerate(order):
+        if i in dead:
+            continue
+        keep.append(i)
+        ix1, iy1, ix2, iy2 = (f32(v) for v in b[i])
+        for j in order[a_pos + 1:]:
+            if j in dead:
+                continue
+            jx1, jy1, jx2, jy2 = (f32(v) for v in b[j])
+            w = max(f32(0), f32(min(ix2, jx2) - max(ix1, jx1)))
+            h = max(f32(0), f32(min(iy2, jy2) - max(iy1, jy1)))
+            inter = f32(w * h)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                ovr = f32(inter / f32(f32(area[i] + area[j]) - inter))
+            if ovr > f32(iou_thr):
+                dead.add(j)
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def multiclass_nms(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score_thr: float, iou_thr: float,
+                   max_num: int = -1, nms_impl: str = "tv"):
+    """mmdet 2.18 multiclass_nms + mmcv batched_nms (class_agnostic=False) [3P, unpinned]: candidates = every
+    (RoI, class) with score > score_thr, flattened row-major; boxes shifted by label * (max coordinate + 1) so that
+    one NMS call is class-aware; survivors in descending score order, first max_num.
+    Returns (dets [D,5], labels [D], kept flat candidate indices r*N+n [D])."""
+    num_classes = multi_scores.size(1) - 1
+    bboxes = multi_bboxes.view(multi_scores.size(0), -1, 4)
+    scores = multi_scores[:, :-1]
+    labels = torch.arange(num_classes, dtype=torch.long).view(1, -1).expand_as(scores)
+    flat = torch.arange(scores.numel(), dtype=torch.long).view_as(scores)
+    bboxes, scores, labels, flat = bboxes.reshape(-1, 4), scores.reshape(-1), labels.reshape(-1), flat.reshape(-1)
+    inds = (scores > score_thr).nonzero(as_tuple=False).squeeze(1)
+    bboxes, scores, labels, flat = bboxes[inds], scores[inds], labels[inds], flat[inds]
+    if bboxes.numel() == 0:
+        return multi_bboxes.new_zeros((0, 5)), torch.zeros((0,), dtype=torch.long), torch.zeros((0,), dtype=torch.long)
+    max_coordinate = bboxes.max()
+    offsets = labels.to(bboxes) * (max_coordinate + torch.tensor(1).to(bboxes))
+    boxes_for_nms = bboxes + offsets[:, None]
+    if nms_impl == "tv":
+        import torchvision
+        keep = torchvision.ops.nms(boxes_for_nms, scores, iou_thr)
+    else:
+        keep = nms_greedy(boxes_for_nms, scores, iou_thr)
+    if max_num > 0:
+        keep = keep[:max_num]
+    return torch.cat([bboxes[keep], scores[keep, None]], -1), labels[keep], flat[keep]
+
+
+def bbox_head_get_bboxes(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torch.Tensor, img_shape=None,
+                         scale_factor=None, rescale: bool = False, score_thr: float = 0.05, iou_thr: float = 0.5,
+                         max_per_img: int = 100, means=(0., 0., 0., 0.), stds=(0.1, 0.1, 0.2, 0.2), nms_impl: str = "tv"):
+    """mmdet 2.18 BBoxHead.get_bboxes [3P, unpinned] for ONE image, as FGNBBoxHead.get_bboxes forwards to it
+    (fgn_roi_head.py:170-178) with the config's bbox_coder (fgn_r50_c4_densecl.py:91-94) and test_cfg.rcnn (:181-185)."""
+    scores = F.softmax(cls_score, dim=-1)
+    bboxes = delta2bbox(rois[:, 1:], bbox_pred, means, stds, max_shape=img_shape)
+    if rescale and bboxes.size(0) > 0:
+        sf = bboxes.new_tensor(scale_factor)
+        bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size(0), -1)
+    return multiclass_nms(bboxes, scores, score_thr, iou_thr, max_per_img, nms_impl)

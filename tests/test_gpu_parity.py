@@ -698,3 +698,83 @@ def test_launches_are_counted():
     before = ops.launch_count()
     ops.map_roi_levels(torch.rand(10, 5, device=dev()) * 100, 4)
     assert ops.launch_count() == before + 1
+
+
+# ---- test-time box post-processing between a8 and a9 (BBoxHead.get_bboxes [3P]) ---------------------------------
+def _det_case(g, n_per, N, img_h=800, img_w=1344, spread=2.0):
+    from fgn_b200.episodes import synth_rois
+    B = len(n_per)
+    rois = torch.cat([torch.cat([torch.full((n, 1), float(b)), synth_rois(g, n, img_h, img_w, 1)[:, 1:]], 1)
+                      for b, n in enumerate(n_per)]) if sum(n_per) else torch.zeros(0, 5)
+    R = rois.shape[0]
+    cls = torch.randn(R, N + 1, generator=g) * spread
+    reg = torch.randn(R, 4 * N, generator=g) * 0.8
+    return rois, cls, reg
+
+
+@pytest.mark.parametrize("n_per,N,rescale", [((300,), 1, False), ((1000,), 1, True), ((300,), 3, True),
+                                             ((1000,), 20, False), ((257, 0, 401), 3, True), ((64, 64), 5, False)])
+def test_det_postprocess_vs_oracle(n_per, N, rescale):
+    """Softmax + delta decode + clip / rescale + multiclass NMS + top-k through the C ABI against the restated
+    mmdet semantics: the kept (RoI, class) pairs, their order and labels are identical; boxes and scores within
+    the fp32 bar."""
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(900 + N + len(n_per))
+    rois, cls, reg = _det_case(g, n_per, N)
+    shapes = [(800, 1344, 3)] * len(n_per)
+    sfs = [(1.6, 1.5, 1.6, 1.5)] * len(n_per)
+    det, lab, cnt = ops.det_postprocess(rois.to(dev()), cls.to(dev()), reg.to(dev()), n_per, shapes,
+                                        sfs if rescale else None, score_thr=0.05, iou_thr=0.5, max_per_img=100)
+    cnt = cnt.cpu().tolist()
+    o = 0
+    for b, n in enumerate(n_per):
+        if n == 0:                                               # fgn_roi_head.py:596-603: no proposal in this image
+            assert cnt[b] == 0
+            continue
+        wd, wl, _ = O.bbox_head_get_bboxes(rois[o:o + n], cls[o:o + n], reg[o:o + n], shapes[b], sfs[b], rescale,
+                                           0.05, 0.5, 100)
+        o += n
+        assert cnt[b] == wd.shape[0], (b, cnt[b], wd.shape[0])
+        assert torch.equal(lab[b, :cnt[b]].cpu().long(), wl)
+        close(det[b, :cnt[b]], wd, what=f"image {b}")
+
+
+def test_det_postprocess_edge_cases():
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    rois, cls, reg = _det_case(g, (50,), 2)
+    d = dev()
+    # nothing passes the score threshold
+    _, _, cnt = ops.det_postprocess(rois.to(d), cls.to(d), reg.to(d), (50,), [(800, 1344)], None, score_thr=2.0)
+    assert cnt.tolist() == [0]
+    # no clipping, no proposals in one image, identical boxes (ties -> lower RoI index first, one survivor)
+    rois2 = rois.clone(); rois2[1:10, 1:] = rois2[0, 1:]
+    cls2 = cls.clone(); cls2[:10] = cls2[0]
+    reg2 = reg.clone(); reg2[:10] = reg2[0]
+    det, lab, cnt = ops.det_postprocess(rois2.to(d), cls2.to(d), reg2.to(d), (50, 0), None, None, max_per_img=7)
+    wd, wl, wf = O.bbox_head_get_bboxes(rois2, cls2, reg2, None, None, False, 0.05, 0.5, 7)
+    assert cnt.tolist() == [wd.shape[0], 0] and torch.equal(lab[0, :cnt[0]].cpu().long(), wl)
+    close(det[0, :wd.shape[0]], wd, what="ties / no clip")
+    # R == 0
+    _, _, cnt = ops.det_postprocess(torch.zeros(0, 5, device=d), torch.zeros(0, 3, device=d), torch.zeros(0, 8, device=d), (0,))
+    assert cnt.tolist() == [0]
+
+
+def test_simple_test_bboxes_returns_detections():
+    """FGNRoIHead.simple_test_bboxes with test_cfg.rcnn: per-image (det_bboxes [D,5], det_labels [D]) like the
+    reference (fgn_roi_head.py:531-616), equal to the oracle's get_bboxes on the head's own raw outputs."""
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    rpn, head = build_heads(cfg, dev(), shared_head=None)
+    ep = episode_to_device(make_episode(cfg, seed=1), dev())
+    qry = ep["qry"][0]
+    head.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"])
+    props = [ep["rois"][:, 1:]]
+    metas = [dict(img_shape=(cfg.img_h, cfg.img_w, 3), scale_factor=(1.0, 1.0, 1.0, 1.0))]
+    raw_cls, raw_reg = head.simple_test_bboxes(qry, metas, props, None)
+    rcnn = dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100)
+    dets, labels = head.simple_test_bboxes(qry, metas, props, rcnn)
+    wd, wl, _ = O.bbox_head_get_bboxes(ep["rois"].cpu(), raw_cls[0].cpu(), raw_reg[0].cpu(), metas[0]["img_shape"],
+                                       None, False, 0.05, 0.5, 100)
+    assert labels[0].dtype == torch.long and torch.equal(labels[0].cpu(), wl)
+    close(dets[0], wd, what="simple_test_bboxes")

@@ -6,6 +6,8 @@ roi_align_kat.npz / map_roi_levels_kat.npz hold torchvision / torch known-answer
 import glob
 import os
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -188,3 +190,58 @@ def test_split_weight_identity():
     full = torch.nn.functional.conv2d(torch.cat((q, s), 1), w.view(C, 2 * C, 1, 1), b)
     split = torch.einsum("oc,rchw->rohw", w[:, :C], q) + torch.einsum("oc,rchw->rohw", w[:, C:], s) + b.view(1, C, 1, 1)
     assert torch.allclose(full, split, atol=1e-5)
+
+
+# ---- test-time box post-processing (BBoxHead.get_bboxes [3P]) ---------------------------------------------------
+def _random_boxes(g, n, size=200.0):
+    c = torch.rand(n, 2, generator=g) * size
+    wh = torch.rand(n, 2, generator=g) * 60 + 2
+    return torch.cat([c - wh / 2, c + wh / 2], 1)
+
+
+def test_nms_restatement_matches_torchvision_op():
+    """The plain-loop NMS restatement (fp32 IoU, stable descending order) selects exactly what the compiled
+    torchvision CPU op selects -- the op mmcv's nms is equivalent to -- including on class-offset boxes."""
+    import torchvision
+    g = torch.Generator().manual_seed(5)
+    for n, thr in ((1, 0.5), (60, 0.5), (300, 0.7), (300, 0.3)):
+        boxes, scores = _random_boxes(g, n), torch.rand(n, generator=g)
+        scores[::7] = scores[0]                                  # ties: stable order decides
+        labels = torch.randint(0, 4, (n,), generator=g)
+        shifted = boxes + (labels.float() * (boxes.max() + 1))[:, None]
+        for b in (boxes, shifted):
+            assert torch.equal(O.nms_greedy(b, scores, thr), torchvision.ops.nms(b, scores, thr))
+
+
+def test_multiclass_nms_is_class_aware_and_score_ordered():
+    import torchvision
+    g = torch.Generator().manual_seed(6)
+    R, N = 120, 3
+    boxes = _random_boxes(g, R * N).view(R, N * 4)
+    scores = torch.softmax(torch.randn(R, N + 1, generator=g) * 2, -1)
+    dets, labels, flat = O.multiclass_nms(boxes, scores, 0.05, 0.5, 50)
+    assert dets.shape[0] == labels.shape[0] == flat.shape[0] <= 50
+    assert (dets[:-1, 4] >= dets[1:, 4]).all()
+    assert torch.equal(labels, flat % N) and torch.equal(dets[:, :4], boxes.view(R, N, 4).reshape(-1, 4)[flat])
+    # same selection as independent per-class NMS
+    want = []
+    for c in range(N):
+        sc = scores[:, c]
+        idx = (sc > 0.05).nonzero().squeeze(1)
+        keep = idx[torchvision.ops.nms(boxes.view(R, N, 4)[idx, c], sc[idx], 0.5)]
+        want += [(float(sc[i]), int(i) * N + c) for i in keep]
+    want.sort(key=lambda t: (-t[0], t[1]))
+    assert [w[1] for w in want[:50]] == flat.tolist()
+    # the loop restatement and the torchvision-backed path agree
+    d2, l2, f2 = O.multiclass_nms(boxes, scores, 0.05, 0.5, 50, nms_impl="loop")
+    assert torch.equal(f2, flat) and torch.equal(d2, dets)
+
+
+def test_delta2bbox_known_values():
+    rois = torch.tensor([[10., 20., 50., 100.]])
+    z = O.delta2bbox(rois, torch.zeros(1, 8), (0, 0, 0, 0), (0.1, 0.1, 0.2, 0.2), max_shape=(90, 45))
+    assert torch.equal(z, torch.tensor([[10., 20., 45., 90., 10., 20., 45., 90.]]))      # identity, then clipped
+    d = torch.tensor([[1.0, -1.0, math.log(2.0) / 0.2, 100.0]])                         # dw = log 2, dh clamped
+    out = O.delta2bbox(rois, d, (0, 0, 0, 0), (0.1, 0.1, 0.2, 0.2))
+    cx, cy, w, h = 30 + 40 * 0.1, 60 - 80 * 0.1, 80.0, 80 * 1000 / 16
+    assert torch.allclose(out, torch.tensor([[cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]]), rtol=1e-5)
