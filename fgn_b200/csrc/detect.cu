@@ -202,26 +202,38 @@ __global__ void det_nms_mask_kernel(const DetParams p, unsigned char *ws, const 
 }
 
 // ---- D4 -----------------------------------------------------------------------------------------------------
-// grid (N, B), one warp: greedy pass over the score-sorted list of one class
-__global__ void det_nms_reduce_kernel(const DetParams p, unsigned char *ws, const DetWs L)
+// grid (N, B), 256 threads: the class's bit matrix is staged in shared memory (as many rows as fit), then warp 0
+// makes the greedy pass over the score-sorted list, ORing the rows of the boxes it keeps
+__global__ void det_nms_reduce_kernel(const DetParams p, unsigned char *ws, const DetWs L, const int smem_rows)
 {
-    extern __shared__ unsigned long long remv[];                 // [words]
-    const int n = blockIdx.x, b = blockIdx.y, N = p.N, lane = threadIdx.x;
+    extern __shared__ unsigned long long sm[];                   // remv[words] | rows[smem_rows][words]
+    const int n = blockIdx.x, b = blockIdx.y, N = p.N, t = threadIdx.x, lane = t & 31;
     unsigned int *hdr = hdr_of(ws, L, b, N);
     const int m = (int)hdr[2 + n];
-    const int words = (m + 63) / 64;
-    for (int w = lane; w < words; w += 32) remv[w] = 0ull;
-    __syncwarp();
-    const unsigned long long *mask = reinterpret_cast<const unsigned long long *>(ws + L.mask) + ((size_t)b * N + n) * p.Rmax * L.words;
+    const int words = (m + 63) / 64, W = L.words;
+    unsigned long long *remv = sm, *rows = sm + W;
+    const unsigned long long *mask = reinterpret_cast<const unsigned long long *>(ws + L.mask) + ((size_t)b * N + n) * p.Rmax * W;
+    for (int w = t; w < words; w += blockDim.x) remv[w] = 0ull;
+    const int staged = min(m, smem_rows);
+    for (int e = t; e < staged * words; e += blockDim.x) {
+        const int i = e / words, w = e - i * words;
+        if (w >= (i >> 6)) rows[(size_t)i * W + w] = mask[(size_t)i * W + w];     // words below the row's block were never written
+    }
+    __syncthreads();
+    if (t >= 32) return;
     int *kept = reinterpret_cast<int *>(ws + L.kept) + ((size_t)b * N + n) * p.Rmax;
     int nk = 0;
-    for (int i = 0; i < m; ++i) {
-        const unsigned long long cur = remv[i >> 6];             // uniform read
-        if (!((cur >> (i & 63)) & 1ull)) {
+    for (int wb = 0; wb < words; ++wb) {                         // 64 boxes at a time: their removed-bits word lives in a register
+        unsigned long long cur = remv[wb];
+        const int base = wb * 64, lim = min(64, m - base);
+        for (int bit = 0; bit < lim; ++bit) {
+            if ((cur >> bit) & 1ull) continue;
+            const int i = base + bit;
             if (lane == 0) kept[nk] = i;
             ++nk;
-            // rows only hold words >= the row's own block (lower words were never written)
-            for (int w = (i >> 6) + lane; w < words; w += 32) remv[w] |= mask[(size_t)i * L.words + w];
+            const unsigned long long *row = i < staged ? rows + (size_t)i * W : mask + (size_t)i * W;
+            cur |= row[wb];                                      // the only load on the serial chain (uniform)
+            for (int w = wb + 1 + lane; w < words; w += 32) remv[w] |= row[w];    // each lane owns its words within a block
         }
         __syncwarp();
     }
@@ -309,8 +321,19 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
     FGN_LAUNCH_OK();
     det_nms_mask_kernel<<<dim3(L.words, L.words, B * N), 64, 0, st>>>(p, ws, L);
     FGN_LAUNCH_OK();
-    det_nms_reduce_kernel<<<dim3(N, B), 32, (size_t)L.words * sizeof(unsigned long long), st>>>(p, ws, L);
-    FGN_LAUNCH_OK();
+    {
+        // stage as many mask rows as fit in 200 KB of shared memory next to the removed-bits vector
+        const size_t row_bytes = (size_t)L.words * sizeof(unsigned long long);
+        const int smem_rows = (int)min((size_t)Rmax, (200 * 1024 - row_bytes) / row_bytes);
+        const size_t smem = row_bytes * (1 + (size_t)smem_rows);
+        static size_t attr = 48 * 1024;
+        if (smem > attr) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        det_nms_reduce_kernel<<<dim3(N, B), 256, smem, st>>>(p, ws, L, smem_rows);
+        FGN_LAUNCH_OK();
+    }
     det_merge_kernel<<<dim3(ceil_div(Rmax, 128), N, B), 128, 0, st>>>(p, ws, L, det_out, label_out, count_out);
     FGN_LAUNCH_OK();
     return FGN_OK;

@@ -543,13 +543,15 @@ def det_postprocess(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torc
         acc += int(x)
         offs.append(acc)
     rmax = max(int(x) for x in num_per_img)
-    off_t = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+    off_t = torch.tensor(offs, dtype=torch.int32, pin_memory=True).to(dev, non_blocking=True)   # (pinned: graph-capturable)
     hw_t = None
     if img_shapes is not None:
-        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32).to(dev, non_blocking=True)
+        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32,
+                            pin_memory=True).to(dev, non_blocking=True)
     sf_t = None
     if scale_factors is not None:
-        sf_t = torch.tensor([[float(v) for v in s] for s in scale_factors], dtype=torch.float32).reshape(b, 4).to(dev, non_blocking=True)
+        sf_t = torch.tensor([[float(v) for v in s] for s in scale_factors], dtype=torch.float32,
+                            pin_memory=True).reshape(b, 4).to(dev, non_blocking=True)
     lib = _lib.load()
     nbytes = int(lib.fgn_det_postprocess_workspace_bytes(r, n, b, rmax))
     ws = torch.empty((max(nbytes, 256),), device=dev, dtype=torch.uint8)
