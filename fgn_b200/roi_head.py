@@ -283,15 +283,29 @@ class FGNRoIHead(nn.Module):
         counts = cnt.tolist()                                    # the reference's outputs are ragged: one host sync
         return ([det[i, :c] for i, c in enumerate(counts)], [lab[i, :c].long() for i, c in enumerate(counts)])
 
-    def simple_test_mask(self, x, det_bboxes: Sequence[torch.Tensor], det_labels: Sequence[torch.Tensor]):
+    def simple_test_mask(self, x, det_bboxes: Sequence[torch.Tensor], det_labels: Sequence[torch.Tensor],
+                         img_metas=None, rescale: bool = False):
+        """fgn_roi_head.py:618-673 up to the mask head's input: support vectors gathered by (image, label)
+        (:707-714), boxes scaled back to the test scale when they were rescaled (:642-652), RoIAlign with the
+        AG-FCN multiply fused.  ``get_seg_masks`` (mask pasting) is mmdet's and stays downstream."""
         self.gather_mask_vectors(det_labels)
-        mask_rois = bbox2roi([d[:, :4] for d in det_bboxes])
+        boxes = [d[:, :4] for d in det_bboxes]
+        if rescale and img_metas is not None:
+            boxes = [bx * bx.new_tensor(m["scale_factor"]) for bx, m in zip(boxes, img_metas)]
+        mask_rois = bbox2roi(boxes)
         if mask_rois.shape[0] == 0:
             return dict(mask_pred=None, mask_feats=mask_rois.new_zeros((0, self.channels, 7, 7)))
         return self._mask_forward(x, mask_rois)
 
     def simple_test(self, qry_fmap, proposal_list, img_metas=None, proposals=None, rescale=False,
                     spp_fmaps=None, spp_bboxes=None, spp_isegmaps=None):
+        """fgn_roi_head.py:675-719.  Without ``test_cfg``: the raw per-image (cls_score, bbox_pred) splits.
+        With it: ``(det_bboxes, det_labels)`` and, when the head has a mask branch, the mask-branch result dict
+        (``mask_feats`` = attended RoI features, ``mask_pred`` if a mask head was given) as third element."""
         assert self.with_bbox, "Bbox head must be implemented."
         self.count_spp(spp_fmaps, spp_bboxes, spp_isegmaps)
-        return self.simple_test_bboxes(qry_fmap, img_metas, proposal_list, self.test_cfg, rescale=rescale)
+        out = self.simple_test_bboxes(qry_fmap, img_metas, proposal_list, self.test_cfg, rescale=rescale)
+        if self.test_cfg is None or not self.with_mask:
+            return out
+        det_bboxes, det_labels = out
+        return det_bboxes, det_labels, self.simple_test_mask(qry_fmap, det_bboxes, det_labels, img_metas, rescale)

@@ -778,3 +778,23 @@ def test_simple_test_bboxes_returns_detections():
                                        None, False, 0.05, 0.5, 100)
     assert labels[0].dtype == torch.long and torch.equal(labels[0].cpu(), wl)
     close(dets[0], wd, what="simple_test_bboxes")
+
+
+def test_simple_test_detections_feed_the_mask_branch():
+    """The a8 -> get_bboxes -> a9 chain of simple_test (fgn_roi_head.py:691-719): detections, the per-detection
+    support vector gather and the attended mask-branch RoI features equal the oracle's on the same detections."""
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    rpn, head = build_heads(cfg, dev(), shared_head=None)
+    ep = episode_to_device(make_episode(cfg, seed=2), dev())
+    qry = ep["qry"][0]
+    head.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"])
+    metas = [dict(img_shape=(cfg.img_h, cfg.img_w, 3), scale_factor=(1.0, 1.0, 1.0, 1.0))]
+    rcnn = dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100)
+    dets, labels = head.simple_test_bboxes(qry, metas, [ep["rois"][:, 1:]], rcnn)
+    assert 0 < dets[0].shape[0] <= 100 and int(labels[0].max()) < cfg.n_ways
+    res = head.simple_test_mask(qry, dets, labels, metas, rescale=False)
+    mask_rois = torch.cat([dets[0].new_zeros((dets[0].shape[0], 1)), dets[0][:, :4]], 1)
+    want = O.mask_attention([qry.cpu().contiguous()], [16], mask_rois.cpu(), head.spp_fvecs_roi_aligned_cat_mean_mp.cpu(),
+                            [labels[0].cpu()], cfg.n_ways, 7)
+    close(res["mask_feats"], want, what="simple_test mask feats")
