@@ -245,7 +245,10 @@ class FGNRoIHead(nn.Module):
             levels = self._as_levels(qry_fmap)[: self.mask_roi_extractor.num_inputs]
             if not self.with_shared_head:
                 # RoIAlign with the channel attention multiply in its epilogue (K12 fused into K1)
-                mask_feats = self.mask_roi_extractor(levels, rois, chan_scale=vec.reshape(vec.shape[0], -1))
+                # channels_last storage (logical shape unchanged): the fast RoIAlign kernel, and the layout cuDNN
+                # prefers for the mask head's convs
+                mask_feats = self.mask_roi_extractor(levels, rois, chan_scale=vec.reshape(vec.shape[0], -1),
+                                                     out_format="nhwc")
             else:
                 mask_feats = self.shared_head(self.mask_roi_extractor(levels, rois))
                 mask_feats = ops.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
