@@ -431,7 +431,7 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     const Pyramid d = to_device_pyramid(pyr);
     cudaStream_t st = (cudaStream_t)stream;
     // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
-    // 3 / 2 = row-streaming kernel with / without its older persistent variant, 1 = bin-centric, 0 = direct
+    // 3 / 2 = row-streaming kernel (one CTA per RoI), 1 = bin-centric, 0 = direct
     const int impl = env_int("FGN_RA_IMPL", 4);
     if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4) {
         bool taken = false;

@@ -617,312 +617,6 @@ int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *ro
     return FGN_OK;
 }
 
-// ================================================================================================
-// Persistent variant (NHWC output): 2 CTAs per SM stay resident and pull (RoI, channel block) work
-// items from a ticket counter.  A PLANNER warp builds the plan + weight tables of item i+1 into a
-// double-buffered shared-memory slot while the consumers are still on item i, and the producer's
-// ring keeps streaming across item boundaries -- the per-RoI prologue (about a quarter of the
-// non-persistent kernel's stall samples) and the pipeline drain/fill between RoIs disappear.
-// Warps: 0..P-1 consumers (warp = bin column), P = producer + planner (plans item i+1 right after
-// filling the ring for item i).
-// ================================================================================================
-constexpr unsigned kTicketSlots = 1024;     // one counter per launch in flight (graphs bake theirs in at capture)
-__device__ unsigned int g_roi_ticket[kTicketSlots];
-
-template <int P>
-struct PlanSlot {
-    int   r, cb0, level, batch;
-    float count;
-    int   xlo[P], xn[P], xoff[P];
-    int   X0, Y0, ncols, nrows, nseg, rps, nstages, H, W;
-};
-
-template <int P, int VEC, int NS>
-__global__ void __launch_bounds__((P + 1) * 32, 2)
-roi_align_persist_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
-                         const int sampling_ratio, const int aligned, const float finest_scale,
-                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
-                         float *__restrict__ out, int32_t *__restrict__ lvl_out,
-                         const int wx_cap, const int wyd_rows, const int ticket_slot)
-{
-    constexpr int CB  = 128 * VEC;
-    constexpr int PP8 = (P + 3) & ~3;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ PlanSlot<P> slot[2];
-    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[2], plan_empty[2];
-
-    float *ring = reinterpret_cast<float *>(smem_raw);
-    float *wtab = ring + (size_t)NS * kStageCells * CB;          // per slot: wx[wx_cap] | wyd[wyd_rows][PP8]
-    const int wslot = wx_cap + wyd_rows * PP8;
-
-    const int nblk = (C + CB - 1) / CB;
-    const int items = R * nblk;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-
-    if (t == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&plan_full[b], 1); mbar_init(&plan_empty[b], P); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == P) {
-        // ===== producer + planner ======================================================================
-        // plan(k): take a ticket, build item k's plan and weight tables into slot k&1, publish it
-        auto plan = [&](int k) {
-            const int b = k & 1;
-            unsigned int ticket = 0;
-            if (lane == 0) {
-                ticket = atomicAdd(&g_roi_ticket[ticket_slot], 1u);
-                if (ticket == (unsigned)(items + gridDim.x - 1)) g_roi_ticket[ticket_slot] = 0u;   // last ticket of the launch
-            }
-            ticket = __shfl_sync(FULL, ticket, 0);
-            mbar_wait(&plan_empty[b], ((k >> 1) & 1) ^ 1);            // consumers are done with item k-2
-            PlanSlot<P> &ps = slot[b];
-            if ((int)ticket >= items) {
-                if (lane == 0) { ps.r = -1; ps.nstages = 0; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&plan_full[b]);
-                return;
-            }
-            const int r = (int)ticket / nblk, cb0 = ((int)ticket % nblk) * CB;
-            const WarpPlan wp = warp_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, lane, wx_cap, wyd_rows);
-            float *wx = wtab + (size_t)b * wslot, *wyd = wx + wx_cap;
-            const int axis = lane / P, p = lane % P;
-            int off = 0;
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-                const int nq = __shfl_sync(FULL, wp.n, P + q);
-                if (lane >= P && q < p) off += nq;
-            }
-            if (lane == 0) {
-                ps.r = r; ps.cb0 = cb0; ps.level = wp.level; ps.batch = wp.g.batch; ps.count = wp.g.count;
-                ps.X0 = wp.X0; ps.Y0 = wp.Y0; ps.ncols = wp.ncols; ps.nrows = wp.nrows;
-                ps.nseg = wp.nseg; ps.rps = wp.rps; ps.nstages = wp.nstages; ps.H = wp.H; ps.W = wp.W;
-                if (lvl_out != nullptr && cb0 == 0) lvl_out[r] = wp.level;
-            }
-            if (lane >= P && lane < 2 * P) { ps.xlo[p] = wp.lo; ps.xn[p] = wp.n; ps.xoff[p] = off; }
-            for (int i = lane; i < wp.nrows * (PP8 / 4); i += 32)
-                reinterpret_cast<float4 *>(wyd)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-            if (lane < 2 * P && wp.nstages > 0) {
-                const float start = axis ? wp.g.start_w : wp.g.start_h, bin = axis ? wp.g.bin_w : wp.g.bin_h;
-                const int grid = axis ? wp.g.grid_w : wp.g.grid_h, size = axis ? wp.W : wp.H;
-                if (axis) {
-                    float *w = wx + off;
-                    for (int i = 0; i < wp.n; ++i) w[i] = 0.f;
-                    for (int i = 0; i < grid; ++i) {
-                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                        if (sm.valid) { w[sm.low - wp.lo] += sm.h; w[sm.high - wp.lo] += sm.l; }
-                    }
-                } else {
-                    float *w = wyd + p - (size_t)wp.Y0 * PP8;
-                    for (int i = 0; i < grid; ++i) {
-                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                        if (sm.valid) { w[(size_t)sm.low * PP8] += sm.h; w[(size_t)sm.high * PP8] += sm.l; }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&plan_full[b]);
-        };
-
-        int s = 0, par = 1;
-        plan(0);
-        for (int k = 0;; ++k) {
-            const PlanSlot<P> &ps = slot[k & 1];                       // written by this warp
-            if (ps.r < 0) break;
-            const int cbn = min(CB, C - ps.cb0);
-            const bool contiguous = (cbn == C);
-            const int cstride = contiguous ? C : CB;
-            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
-            const float *fbase = pyr.feat[ps.level] + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
-                                 + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
-            const size_t row_pitch = (size_t)ps.W * C;
-            int row0 = 0, col0 = 0;                                    // cursor of the next stage
-            auto issue = [&]() {
-                int nr, nc;
-                if (nseg == 1) { nr = min(rps, nrows - row0); nc = ncols; }
-                else           { nr = 1; nc = min(kStageCells, ncols - col0); }
-                mbar_wait(&empty_bar[s], par);
-                float *dst = ring + (size_t)s * kStageCells * CB;
-                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(nr * nc * cbn * 4));
-                __syncwarp();
-                const float *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
-                if (contiguous) {
-                    if (lane < nr)
-                        bulk_g2s(dst + (size_t)lane * nc * cstride, src + (size_t)lane * row_pitch,
-                                 (uint32_t)(nc * C * 4), &full_bar[s]);
-                } else {
-                    for (int cell = lane; cell < nr * nc; cell += 32) {
-                        const int rr = cell / nc, cc = cell - rr * nc;
-                        bulk_g2s(dst + (size_t)cell * cstride, src + (size_t)rr * row_pitch + (size_t)cc * C,
-                                 (uint32_t)(cbn * 4), &full_bar[s]);
-                    }
-                }
-                if (nseg == 1) row0 += nr;
-                else { col0 += nc; if (col0 >= ncols) { col0 = 0; ++row0; } }
-                if (++s == NS) { s = 0; par ^= 1; }
-            };
-            const int head = min(NS, nstages);
-            for (int st = 0; st < head; ++st) issue();                 // fill the ring for this item
-            plan(k + 1);                                               // ... then plan the next one
-            for (int st = head; st < nstages; ++st) issue();
-        }
-    } else {
-        // ===== consumers: warp = bin column pw =========================================================
-        const int pw = warp;
-        int s = 0, par = 0;
-        for (int k = 0;; ++k) {
-            const int b = k & 1;
-            mbar_wait(&plan_full[b], (k >> 1) & 1);
-            const PlanSlot<P> &ps = slot[b];
-            const int r = ps.r;
-            if (r < 0) break;
-            const float *wx = wtab + (size_t)b * wslot, *wyd = wx + wx_cap;
-            const int cb0 = ps.cb0, cbn = min(CB, C - cb0);
-            const int cstride = (cbn == C) ? C : CB;
-            const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps;
-            const int xlo = ps.xlo[pw] - ps.X0, nx = ps.xn[pw];
-            const float *wxp = wx + ps.xoff[pw];
-            const float inv = 1.0f / ps.count;
-            int loff[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) loff[v] = (v * 128 + lane * 4 < cbn) ? v * 128 + lane * 4 : 0;
-
-            float4 acc[P][VEC];
-#pragma unroll
-            for (int ph = 0; ph < P; ++ph)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[ph][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 racc[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-            auto fold = [&](int j) {
-                float wrow[PP8];
-#pragma unroll
-                for (int q = 0; q < PP8 / 4; ++q) {
-                    const float4 w4 = *reinterpret_cast<const float4 *>(wyd + (size_t)j * PP8 + 4 * q);
-                    wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
-                }
-#pragma unroll
-                for (int ph = 0; ph < P; ++ph) {
-                    if (wrow[ph] != 0.f) {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) fma4(acc[ph][v], wrow[ph], racc[v]);
-                    }
-                }
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-
-            if (ps.nseg == 1) {
-                int row = 0;
-                const size_t rstride = (size_t)ncols * cstride;
-                for (int st = 0; st < nstages; ++st) {
-                    const int nr = min(rps, nrows - row);
-                    mbar_wait(&full_bar[s], par);
-                    const float *base = ring + (size_t)s * kStageCells * CB + (size_t)xlo * cstride;
-                    for (int rr = 0; rr < nr; ++rr, ++row) {
-                        const float *cp = base + rr * rstride;
-#pragma unroll 4
-                        for (int i = 0; i < nx; ++i, cp += cstride) {
-                            const float w = wxp[i];
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v)
-                                fma4(racc[v], w, *reinterpret_cast<const float4 *>(cp + loff[v]));
-                        }
-                        fold(row);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[s]);
-                    if (++s == NS) { s = 0; par ^= 1; }
-                }
-            } else {
-                for (int row = 0; row < nrows; ++row)
-                    for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
-                        const int nc = min(kStageCells, ncols - col0);
-                        mbar_wait(&full_bar[s], par);
-                        const float *base = ring + (size_t)s * kStageCells * CB;
-                        const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
-                        for (int cx = c_beg; cx < c_end; ++cx) {
-                            const float w = wxp[cx - xlo];
-                            const float *cp = base + (size_t)(cx - col0) * cstride;
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v)
-                                fma4(racc[v], w, *reinterpret_cast<const float4 *>(cp + loff[v]));
-                        }
-                        if (col0 + nc >= ncols) fold(row);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[s]);
-                        if (++s == NS) { s = 0; par ^= 1; }
-                    }
-            }
-            // the plan slot (weights) is no longer needed by this warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&plan_empty[b]);
-
-            // ---- epilogue: 1/count, optional AG-FCN channel attention, 1 KB-contiguous NHWC stores ------
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const int cl = v * 128 + lane * 4;
-                if (cl >= cbn) continue;
-                const int c = cb0 + cl;
-                float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (chan_scale != nullptr) {
-                    const int si = scale_index != nullptr ? scale_index[r] : r;
-                    cs = ldg4(chan_scale + (size_t)si * C + c);
-                }
-#pragma unroll
-                for (int ph = 0; ph < P; ++ph) {
-                    const float4 a = acc[ph][v];
-                    const float4 o = make_float4(a.x * inv * cs.x, a.y * inv * cs.y, a.z * inv * cs.z, a.w * inv * cs.w);
-                    *reinterpret_cast<float4 *>(out + (((size_t)r * P + ph) * P + pw) * C + c) = o;
-                }
-            }
-        }
-    }
-}
-
-template <int P, int VEC, int NS>
-static int launch_persist_cfg(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
-                              int aligned, float finest_scale, const float *chan_scale,
-                              const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
-                              bool *taken)
-{
-    constexpr int CB = 128 * VEC;
-    constexpr int PP8 = (P + 3) & ~3;
-    int maxH = 0, maxW = 0;
-    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
-    const int wx_cap = (maxW + 6 * P + 16 + 3) & ~3;
-    const int wyd_rows = maxH;
-    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)2 * (wx_cap + wyd_rows * PP8) * 4;
-    if (smem > 115200) { *taken = false; return FGN_OK; }           // two CTAs (+1 KB reserved each) must fit one SM's 228 KB
-    auto kern = roi_align_persist_kernel<P, VEC, NS>;
-    static int attr_set = 0;
-    if ((int)smem > attr_set) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = (int)smem;
-    }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        FGN_CUDA_OK(cudaGetDevice(&dev));
-        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
-    static unsigned int launch_seq = 0;
-    const int slot = (int)(launch_seq++ % kTicketSlots);
-    const int nblk = (C + CB - 1) / CB;
-    const int grid = min(2 * sm_count, R * nblk);
-    kern<<<grid, (P + 1) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
-                                           scale_index, out, lvl_out, wx_cap, wyd_rows, slot);
-    FGN_LAUNCH_OK();
-    *taken = true;
-    return FGN_OK;
-}
-
 template <int P, int VEC, int NS, int WS = 1>
 static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
                              int aligned, float finest_scale, const float *chan_scale,
@@ -967,14 +661,6 @@ int launch_roi_align_stream(const Pyramid &d, int C, int P, const float *rois, i
 {
     *taken = false;
     if ((C & 3) != 0) return FGN_OK;
-    if (out_layout == FGN_LAYOUT_NHWC && P == 7 && vec_pref >= 0) {
-        int rc;
-        if (C > 128 && vec_pref != 1) rc = launch_persist_cfg<7, 2, 3>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
-                                                                     chan_scale, scale_index, out, lvl_out, st, taken);
-        else rc = launch_persist_cfg<7, 1, 4>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
-                                              chan_scale, scale_index, out, lvl_out, st, taken);
-        if (rc || *taken) return rc;
-    }
     if (vec_pref < 0) vec_pref = -vec_pref;
 #define FGN_STREAM(PV, VV, NV) launch_stream_cfg<PV, VV, NV>(d, C, rois, R, sampling_ratio, aligned, finest_scale, \
                                                              chan_scale, scale_index, out, out_layout, lvl_out, st, taken)

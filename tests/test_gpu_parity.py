@@ -149,11 +149,11 @@ def test_roi_align_multilevel_vs_oracle(C, P):
     assert torch.equal(got3, got)                                                # NCHW input (repacked) too
 
 
-@pytest.mark.parametrize("env", [{"FGN_RA_IMPL": "2"}, {"FGN_RA_IMPL": "3"}, {"FGN_RA_IMPL": "1"},
+@pytest.mark.parametrize("env", [{"FGN_RA_IMPL": "2"}, {"FGN_RA_IMPL": "2", "FGN_RA_NS": "2"}, {"FGN_RA_IMPL": "1"},
                                  {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "1"}, {"FGN_RA_IMPL": "2", "FGN_RA_VEC": "3"},
                                  {"FGN_RA_IMPL": "2", "FGN_RA_CLASSES": "3"}, {"FGN_RA_SPLIT": "0"},
                                  {"FGN_RA_SPLIT": "40"}, {"FGN_RA_NS": "2"}],
-                         ids=["stream", "persistent-v1", "bin-centric", "cb128", "sliced", "three-class",
+                         ids=["stream", "stream-ns2", "bin-centric", "cb128", "sliced", "three-class",
                               "window-nosplit", "window-split40", "window-ns2"])
 def test_roi_align_kernel_variants_agree(env, monkeypatch):
     """Every RoIAlign kernel variant the library can dispatch to (selected through its tuning
