@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying one CUDA graph per episode")
     ap.add_argument("--no-bf16", action="store_true", help="skip the separately reported bf16 variant")
     ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
+    ap.add_argument("--e2e-streams", type=int, default=8, help="streams the end-to-end leg overlaps copies and compute on")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -304,7 +305,7 @@ def main():
     out_host = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
 
-    e2e_streams = [torch.cuda.Stream() for _ in range(3)]      # copies of episode i+1 overlap compute of episode i
+    e2e_streams = [torch.cuda.Stream() for _ in range(max(1, args.e2e_streams))]   # copies of episode i+1 overlap compute of episode i
 
     def step_e2e():
         main = torch.cuda.current_stream()
