@@ -40,6 +40,10 @@ SIGNATURES = {
     "fgn_last_error_string": (c_char_p, []),
     "fgn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fgn_launch_count": (c_uint64, []),
+    "fgn_rpn_proposals_workspace_bytes": (c_size_t, [POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int]),
+    "fgn_rpn_proposals": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                  c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), c_float,
+                                  c_int, c_float, c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "fgn_det_postprocess_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_det_postprocess": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                     POINTER(c_float), POINTER(c_float), c_float, c_float, c_float, c_int,

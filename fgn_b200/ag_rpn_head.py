@@ -43,6 +43,34 @@ class AGRPNHead(nn.Module):
             self.n_ways = n_ways
         if k_shots is not None:
             self.k_shots = k_shots
+        # proposal generation (get_bboxes): anchors, coder and test_cfg.rpn of the config (fgn_r50_c4_densecl.py:48-58,175-180)
+        ag = anchor_generator or dict(scales=[2, 4, 8, 16, 32], ratios=[0.5, 1.0, 2.0], strides=[16])
+        self.anchor_scales, self.anchor_ratios = list(ag["scales"]), list(ag["ratios"])
+        self.anchor_strides = list(ag.get("strides", [16]))
+        coder = dict(kwargs.get("bbox_coder") or {})
+        self.bbox_coder = dict(target_means=list(coder.get("target_means", [0., 0., 0., 0.])),
+                               target_stds=list(coder.get("target_stds", [1., 1., 1., 1.])))
+        self.test_cfg = kwargs.get("test_cfg")
+
+    def get_bboxes(self, cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], img_metas=None,
+                   cfg: Optional[dict] = None, rescale: bool = False):
+        """mmdet RPNHead.get_bboxes [3P] as the reference calls it (fgn.py:229-235): per-level score / delta maps
+        (already best-class-selected) -> per-image proposal tensors [D,5] (x1,y1,x2,y2,score), D <= max_per_img.
+        One C-ABI call (ops.rpn_proposals -> fgn_rpn_proposals)."""
+        cfg = cfg if cfg is not None else self.test_cfg
+        if cfg is None:
+            raise ValueError("AGRPNHead.get_bboxes needs cfg (test_cfg.rpn: nms_pre, nms.iou_threshold, max_per_img, min_bbox_size)")
+        if rescale:
+            raise NotImplementedError("RPN proposals stay at the test scale (the reference calls get_bboxes without rescale)")
+        nl = len(cls_scores)
+        strides = self.anchor_strides if len(self.anchor_strides) == nl else self.anchor_strides[:1] * nl
+        anchors = torch.stack([ops.base_anchors(s, self.anchor_scales, self.anchor_ratios) for s in strides])
+        shapes = [m["img_shape"] for m in img_metas] if img_metas is not None else None
+        prop, _, cnt = ops.rpn_proposals(cls_scores, bbox_preds, strides, anchors, shapes, nms_pre=cfg["nms_pre"],
+                                         iou_thr=cfg["nms"]["iou_threshold"], max_per_img=cfg["max_per_img"],
+                                         min_bbox_size=cfg.get("min_bbox_size", 0),
+                                         means=self.bbox_coder["target_means"], stds=self.bbox_coder["target_stds"])
+        return [prop[i, :c] for i, c in enumerate(cnt.tolist())]       # ragged per-image lists: one host sync
 
     # mmdet RPNHead.forward_single [3P]
     def _rpn_forward_single(self, x: torch.Tensor):

@@ -14,6 +14,7 @@
 //   D4 reduce   per (image, class): one warp walks the sorted list and ORs the rows of kept boxes
 //   D5 merge    thread = kept box: global rank = sum over classes of a binary search; writes the top max_per_img
 #include "common.cuh"
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 namespace fgn {
 
@@ -63,6 +64,7 @@ struct DetParams {
     const float *img_hw;                // [B,2] (h, w) clip bounds, or NULL: no clipping
     const float *scale;                 // [B,4] rescale divisors, or NULL
     int   R, N, B, Rmax, max_per_img;
+    int   class_major_ties;             // equal scores: class (level) index first, then row (RPN); else row first
     float means[4], stds[4], score_thr, iou_thr, max_ratio;
 };
 
@@ -223,10 +225,10 @@ __global__ void det_nms_reduce_kernel(const DetParams p, unsigned char *ws, cons
     if (t >= 32) return;
     int *kept = reinterpret_cast<int *>(ws + L.kept) + ((size_t)b * N + n) * p.Rmax;
     int nk = 0;
-    for (int wb = 0; wb < words; ++wb) {                         // 64 boxes at a time: their removed-bits word lives in a register
+    for (int wb = 0; wb < words && nk < p.max_per_img; ++wb) {   // 64 boxes at a time: their removed-bits word lives in a register
         unsigned long long cur = remv[wb];
         const int base = wb * 64, lim = min(64, m - base);
-        for (int bit = 0; bit < lim; ++bit) {
+        for (int bit = 0; bit < lim && nk < p.max_per_img; ++bit) {
             if ((cur >> bit) & 1ull) continue;
             const int i = base + bit;
             if (lane == 0) kept[nk] = i;
@@ -265,7 +267,8 @@ __global__ void det_merge_kernel(const DetParams p, unsigned char *ws, const Det
             const int mid = (lo + hi) >> 1;
             const int rj = so[ks[mid]];
             const float sj = cscore[(size_t)(r0 + rj) * N + c];
-            const bool better = sj > ms || (sj == ms && ((size_t)rj * N + c) < ((size_t)me * N + n));
+            const bool before = p.class_major_ties ? (c < n || (c == n && rj < me)) : (((size_t)rj * N + c) < ((size_t)me * N + n));
+            const bool better = sj > ms || (sj == ms && before);
             if (better) lo = mid + 1; else hi = mid;
         }
         rank += lo;
@@ -276,6 +279,116 @@ __global__ void det_merge_kernel(const DetParams p, unsigned char *ws, const Det
         o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ms;
         label_out[(size_t)b * p.max_per_img + rank] = n;
     }
+}
+
+
+// ================================================================================================================
+// RPN proposals: RPNHead._get_bboxes_single [3P, mmdet 2.18] as called from fgn.py:229-235 on the outputs of
+// AGRPNHead.forward_single -- per level: sigmoid scores in (H, W, A) order, the nms_pre best (stable descending),
+// DeltaXYWHBBoxCoder.decode against the level's grid anchors, clip, min size filter; then NMS per level through
+// the same coordinate-offset trick (ids = level), and the max_per_img best by score.  The candidates are laid out
+// like the detections above with "class" = level and "RoI" = position in the level's sorted list, so kernels
+// D3 - D5 are reused as they are.
+struct RpnParams {
+    const float *cls[FGN_MAX_LEVELS], *reg[FGN_MAX_LEVELS];   // [B,A,H,W], [B,4A,H,W]
+    int   H[FGN_MAX_LEVELS], W[FGN_MAX_LEVELS], stride[FGN_MAX_LEVELS];
+    int   seg_off[FGN_MAX_LEVELS + 1];                         // first sort item of level l within one image
+    const float *base_anchors;                                 // [L,A,4]
+    int   L, A, B, K;                                          // K = candidates kept per level (<= nms_pre)
+    float min_size;                                            // < 0: no filter
+};
+
+// R1: sort keys (logits: monotone in the sigmoid score and free of its rounding ties) and anchor indices
+__global__ void rpn_keys_kernel(const RpnParams q, float *keys, int *vals, int *seg_begin, int *seg_end, int *img_off)
+{
+    const int per_img = q.seg_off[q.L];
+    const size_t total = (size_t)q.B * per_img;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img), j = (int)(i - (size_t)b * per_img);
+        int l = 0;
+        while (l + 1 < q.L && j >= q.seg_off[l + 1]) ++l;
+        const int idx = j - q.seg_off[l];                      // (y*W + x)*A + a
+        const int a = idx % q.A, cell = idx / q.A;
+        keys[i] = q.cls[l][((size_t)b * q.A + a) * q.H[l] * q.W[l] + cell];
+        vals[i] = idx;
+    }
+    if (blockIdx.x == 0) {
+        for (int sgm = threadIdx.x; sgm < q.B * q.L; sgm += blockDim.x) {
+            const int b = sgm / q.L, l = sgm % q.L;
+            seg_begin[sgm] = b * per_img + q.seg_off[l];
+            seg_end[sgm] = b * per_img + q.seg_off[l + 1];
+        }
+        for (int b = threadIdx.x; b <= q.B; b += blockDim.x) img_off[b] = b * q.K;
+    }
+}
+
+// R2: decode the K best of every (image, level); grid (ceil(K/128), L, B)
+__global__ void rpn_decode_kernel(const RpnParams q, const DetParams p, const float *keys, const int *vals,
+                                  unsigned char *ws, const DetWs Lw)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, b = blockIdx.z;
+    if (k >= q.K) return;
+    const int per_img = q.seg_off[q.L], m_l = q.seg_off[l + 1] - q.seg_off[l];
+    float *cscore = reinterpret_cast<float *>(ws + Lw.cand_score);
+    const size_t c = ((size_t)b * q.K + k) * q.L + l;
+    if (k >= m_l) { cscore[c] = -1.f; return; }
+    const size_t it = (size_t)b * per_img + q.seg_off[l] + k;
+    const int idx = vals[it];
+    const int a = idx % q.A, cell = idx / q.A, y = cell / q.W[l], x = cell % q.W[l];
+    const float score = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-keys[it])));                    // torch sigmoid
+    const float *ba = q.base_anchors + ((size_t)l * q.A + a) * 4;
+    const float sx = (float)(x * q.stride[l]), sy = (float)(y * q.stride[l]);
+    const float ax1 = __fadd_rn(ba[0], sx), ay1 = __fadd_rn(ba[1], sy), ax2 = __fadd_rn(ba[2], sx), ay2 = __fadd_rn(ba[3], sy);
+    const size_t hw = (size_t)q.H[l] * q.W[l];
+    const float *d = q.reg[l] + ((size_t)b * 4 * q.A + 4 * a) * hw + cell;
+    const float dx = __fadd_rn(__fmul_rn(d[0], p.stds[0]), p.means[0]);
+    const float dy = __fadd_rn(__fmul_rn(d[hw], p.stds[1]), p.means[1]);
+    float dw = __fadd_rn(__fmul_rn(d[2 * hw], p.stds[2]), p.means[2]);
+    float dh = __fadd_rn(__fmul_rn(d[3 * hw], p.stds[3]), p.means[3]);
+    dw = fminf(fmaxf(dw, -p.max_ratio), p.max_ratio);
+    dh = fminf(fmaxf(dh, -p.max_ratio), p.max_ratio);
+    const float px = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f), py = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+    const float pw = __fsub_rn(ax2, ax1), ph = __fsub_rn(ay2, ay1);
+    const float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
+    const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
+    float x1 = __fsub_rn(gx, __fmul_rn(gw, 0.5f)), y1 = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
+    float x2 = __fadd_rn(gx, __fmul_rn(gw, 0.5f)), y2 = __fadd_rn(gy, __fmul_rn(gh, 0.5f));
+    if (p.img_hw != nullptr) {
+        const float H = p.img_hw[2 * b], W = p.img_hw[2 * b + 1];
+        x1 = fminf(fmaxf(x1, 0.f), W); x2 = fminf(fmaxf(x2, 0.f), W);
+        y1 = fminf(fmaxf(y1, 0.f), H); y2 = fminf(fmaxf(y2, 0.f), H);
+    }
+    reinterpret_cast<float4 *>(ws + Lw.cand_box)[c] = make_float4(x1, y1, x2, y2);
+    const bool valid = q.min_size < 0.f || (__fsub_rn(x2, x1) > q.min_size && __fsub_rn(y2, y1) > q.min_size);
+    cscore[c] = valid ? score : -1.f;
+    if (valid) atomicMax(&hdr_of(ws, Lw, b, q.L)[0], f2ord(fmaxf(fmaxf(x1, y1), fmaxf(x2, y2))));
+}
+
+// R3: per (image, level) the list of valid positions in score order; grid (L, B), 1024 threads
+__global__ void rpn_compact_kernel(const RpnParams q, unsigned char *ws, const DetWs Lw)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int l = blockIdx.x, b = blockIdx.y, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const float *cscore = reinterpret_cast<const float *>(ws + Lw.cand_score);
+    int *sorted = reinterpret_cast<int *>(ws + Lw.sorted) + ((size_t)b * q.L + l) * q.K;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < q.K; k0 += blockDim.x) {
+        const int k = k0 + t;
+        const bool v = k < q.K && cscore[((size_t)b * q.K + k) * q.L + l] >= 0.f;
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        const int within = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int before = carry;
+        for (int w = 0; w < wid; ++w) before += warp_tot[w];
+        if (v) sorted[before + within] = k;
+        __syncthreads();
+        if (t == 0) { int s = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += warp_tot[w]; carry += s; }
+        __syncthreads();
+    }
+    if (t == 0) hdr_of(ws, Lw, b, q.L)[2 + l] = (unsigned)carry;
 }
 
 }  // namespace
@@ -312,7 +425,7 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
     p.rois = rois; p.cls = cls_score; p.reg = bbox_pred; p.img_off = img_offsets; p.img_hw = img_hw; p.scale = scale_factor;
     p.R = R; p.N = N; p.B = B; p.Rmax = Rmax; p.max_per_img = max_per_img;
     for (int i = 0; i < 4; ++i) { p.means[i] = means[i]; p.stds[i] = stds[i]; }
-    p.score_thr = score_thr; p.iou_thr = iou_thr;
+    p.score_thr = score_thr; p.iou_thr = iou_thr; p.class_major_ties = 0;
     p.max_ratio = fabsf(logf(wh_ratio_clip));
     FGN_CUDA_OK(cudaMemsetAsync(ws + L.hdr, 0, (size_t)B * (2 + 2 * N) * sizeof(unsigned int), st));
     det_decode_kernel<<<ceil_div(R, 128), 128, 0, st>>>(p, ws, L);
@@ -335,6 +448,118 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
         FGN_LAUNCH_OK();
     }
     det_merge_kernel<<<dim3(ceil_div(Rmax, 128), N, B), 128, 0, st>>>(p, ws, L, det_out, label_out, count_out);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+
+namespace {
+struct RpnWs { size_t det, keys_in, vals_in, keys_out, vals_out, seg_b, seg_e, img_off, cub, total; size_t cub_bytes; };
+
+RpnWs rpn_layout(const int *H, const int *W, int L, int A, int B, int K)
+{
+    RpnWs w;
+    size_t per_img = 0;
+    for (int l = 0; l < L; ++l) per_img += (size_t)H[l] * W[l] * A;
+    const size_t items = per_img * B;
+    size_t o = 0;
+    w.det = o;      o = align256(o + det_layout(B * K, L, B, K).total);
+    w.keys_in = o;  o = align256(o + items * 4);
+    w.vals_in = o;  o = align256(o + items * 4);
+    w.keys_out = o; o = align256(o + items * 4);
+    w.vals_out = o; o = align256(o + items * 4);
+    w.seg_b = o;    o = align256(o + (size_t)B * L * 4);
+    w.seg_e = o;    o = align256(o + (size_t)B * L * 4);
+    w.img_off = o;  o = align256(o + (size_t)(B + 1) * 4);
+    w.cub_bytes = 0;
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float *)nullptr, (float *)nullptr,
+                                                       (const int *)nullptr, (int *)nullptr, (int)items, B * L,
+                                                       (const int *)nullptr, (const int *)nullptr);
+    w.cub = o;      o = align256(o + w.cub_bytes);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t fgn_rpn_proposals_workspace_bytes(const int *H, const int *W, int L, int A, int B, int nms_pre)
+{
+    if (L < 1 || L > FGN_MAX_LEVELS || A < 1 || B < 1 || nms_pre < 1) return 256;
+    int maxm = 0;
+    for (int l = 0; l < L; ++l) maxm = max(maxm, H[l] * W[l] * A);
+    return rpn_layout(H, W, L, A, B, min(nms_pre, maxm)).total;
+}
+
+extern "C" int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const int *H, const int *W,
+                                 const int *strides, int L, int A, int B, const float *base_anchors,
+                                 const float *img_hw, const float *means, const float *stds, float wh_ratio_clip,
+                                 int nms_pre, float iou_thr, int max_per_img, float min_bbox_size,
+                                 float *prop_out, int32_t *level_out, int32_t *count_out,
+                                 void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(L >= 1 && L <= FGN_MAX_LEVELS && A >= 1 && B >= 1 && nms_pre >= 1 && max_per_img >= 1,
+                  "bad dims L=%d A=%d B=%d nms_pre=%d max_per_img=%d", L, A, B, nms_pre, max_per_img);
+    FGN_CHECK_ARG(cls && reg && H && W && strides && base_anchors && means && stds && prop_out && level_out && count_out,
+                  "NULL pointer");
+    FGN_CHECK_ARG(wh_ratio_clip > 0.f, "wh_ratio_clip=%f", wh_ratio_clip);
+    cudaStream_t st = (cudaStream_t)stream;
+    RpnParams q;
+    q.L = L; q.A = A; q.B = B; q.base_anchors = base_anchors; q.min_size = min_bbox_size;
+    int maxm = 0, off = 0;
+    for (int l = 0; l < FGN_MAX_LEVELS; ++l) {
+        q.cls[l] = l < L ? cls[l] : nullptr; q.reg[l] = l < L ? reg[l] : nullptr;
+        q.H[l] = l < L ? H[l] : 0; q.W[l] = l < L ? W[l] : 0; q.stride[l] = l < L ? strides[l] : 0;
+        q.seg_off[l] = off;
+        if (l < L) {
+            FGN_CHECK_ARG(cls[l] && reg[l] && H[l] > 0 && W[l] > 0, "level %d", l);
+            off += H[l] * W[l] * A; maxm = max(maxm, H[l] * W[l] * A);
+        }
+    }
+    for (int l = L; l <= FGN_MAX_LEVELS; ++l) q.seg_off[l] = off;
+    const int K = min(nms_pre, maxm);
+    q.K = K;
+    const RpnWs Wl = rpn_layout(H, W, L, A, B, K);
+    FGN_CHECK_ARG(workspace && workspace_bytes >= Wl.total, "workspace %zu < %zu bytes", workspace_bytes, Wl.total);
+    unsigned char *base = static_cast<unsigned char *>(workspace);
+    unsigned char *ws = base + Wl.det;
+    const DetWs Ld = det_layout(B * K, L, B, K);
+    float *keys_in = (float *)(base + Wl.keys_in), *keys_out = (float *)(base + Wl.keys_out);
+    int *vals_in = (int *)(base + Wl.vals_in), *vals_out = (int *)(base + Wl.vals_out);
+    int *seg_b = (int *)(base + Wl.seg_b), *seg_e = (int *)(base + Wl.seg_e), *img_off = (int *)(base + Wl.img_off);
+    const size_t items = (size_t)off * B;
+
+    DetParams p;
+    p.rois = nullptr; p.cls = nullptr; p.reg = nullptr; p.img_off = img_off; p.img_hw = img_hw; p.scale = nullptr;
+    p.R = B * K; p.N = L; p.B = B; p.Rmax = K; p.max_per_img = max_per_img; p.class_major_ties = 1;
+    for (int i = 0; i < 4; ++i) { p.means[i] = means[i]; p.stds[i] = stds[i]; }
+    p.score_thr = 0.f; p.iou_thr = iou_thr; p.max_ratio = fabsf(logf(wh_ratio_clip));
+
+    FGN_CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(int32_t) * B, st));
+    FGN_CUDA_OK(cudaMemsetAsync(ws + Ld.hdr, 0, (size_t)B * (2 + 2 * L) * sizeof(unsigned int), st));
+    rpn_keys_kernel<<<(int)min((size_t)1184, (items + 255) / 256), 256, 0, st>>>(q, keys_in, vals_in, seg_b, seg_e, img_off);
+    FGN_LAUNCH_OK();
+    size_t cub_bytes = Wl.cub_bytes;
+    FGN_CUDA_OK(cub::DeviceSegmentedRadixSort::SortPairsDescending(base + Wl.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                                   (int)items, B * L, seg_b, seg_e, 0, 32, st));
+    count_launch(2);                                             // (library sort: upsweep/downsweep passes, not counted exactly)
+    rpn_decode_kernel<<<dim3(ceil_div(K, 128), L, B), 128, 0, st>>>(q, p, keys_out, vals_out, ws, Ld);
+    FGN_LAUNCH_OK();
+    rpn_compact_kernel<<<dim3(L, B), 1024, 0, st>>>(q, ws, Ld);
+    FGN_LAUNCH_OK();
+    det_nms_mask_kernel<<<dim3(Ld.words, Ld.words, B * L), 64, 0, st>>>(p, ws, Ld);
+    FGN_LAUNCH_OK();
+    {
+        const size_t row_bytes = (size_t)Ld.words * sizeof(unsigned long long);
+        const int smem_rows = (int)min((size_t)K, (200 * 1024 - row_bytes) / row_bytes);
+        const size_t smem = row_bytes * (1 + (size_t)smem_rows);
+        static size_t attr = 48 * 1024;
+        if (smem > attr) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        det_nms_reduce_kernel<<<dim3(L, B), 256, smem, st>>>(p, ws, Ld, smem_rows);
+        FGN_LAUNCH_OK();
+    }
+    det_merge_kernel<<<dim3(ceil_div(K, 128), L, B), 128, 0, st>>>(p, ws, Ld, prop_out, level_out, count_out);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

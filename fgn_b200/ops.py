@@ -562,3 +562,59 @@ def det_postprocess(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torc
                                        float(iou_thr), int(max_per_img), det.data_ptr(), lab.data_ptr(), cnt.data_ptr(),
                                        ws.data_ptr(), nbytes, _stream()), "fgn_det_postprocess")
     return det, lab, cnt
+
+
+def base_anchors(base_size: float, scales: Sequence[float], ratios: Sequence[float]) -> torch.Tensor:
+    """mmdet AnchorGenerator.gen_single_level_base_anchors [3P] (scale_major=True, center_offset=0), evaluated
+    with the same fp32 torch expressions: [len(ratios)*len(scales), 4], ratio-major."""
+    sc = torch.tensor(list(scales), dtype=torch.float32)
+    ra = torch.tensor(list(ratios), dtype=torch.float32)
+    w = h = float(base_size)
+    h_ratios = torch.sqrt(ra)
+    w_ratios = 1 / h_ratios
+    ws = (w * w_ratios[:, None] * sc[None, :]).view(-1)
+    hs = (h * h_ratios[:, None] * sc[None, :]).view(-1)
+    xc = yc = 0.0
+    return torch.stack([xc - 0.5 * ws, yc - 0.5 * hs, xc + 0.5 * ws, yc + 0.5 * hs], dim=-1)
+
+
+def rpn_proposals(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], strides: Sequence[int],
+                  anchors: torch.Tensor, img_shapes: Optional[Sequence[Sequence[float]]] = None, nms_pre: int = 6000,
+                  iou_thr: float = 0.7, max_per_img: int = 300, min_bbox_size: float = 0.0,
+                  means: Sequence[float] = (0., 0., 0., 0.), stds: Sequence[float] = (1., 1., 1., 1.),
+                  wh_ratio_clip: float = 16 / 1000):
+    """RPNHead.get_bboxes [3P] (fgn.py:229-235): ``cls_scores[l]`` [B,A,H,W] sigmoid logits, ``bbox_preds[l]``
+    [B,4A,H,W], ``anchors`` [L,A,4] base anchors (ops.base_anchors per level, stacked).
+    Returns ``(proposals [B,max_per_img,5], levels [B,max_per_img] int32, counts [B] int32)`` on the device."""
+    _need_cuda(*cls_scores, *bbox_preds)
+    nl = len(cls_scores)
+    cls_scores = [_f32(t, "cls_score").contiguous() for t in cls_scores]
+    bbox_preds = [_f32(t, "bbox_pred").contiguous() for t in bbox_preds]
+    b, a = cls_scores[0].shape[0], cls_scores[0].shape[1]
+    for c, r in zip(cls_scores, bbox_preds):
+        if c.dim() != 4 or r.shape != (b, 4 * a, c.shape[2], c.shape[3]) or c.shape[:2] != (b, a):
+            raise FgnError(f"rpn_proposals: cls {tuple(c.shape)} / reg {tuple(r.shape)} do not match B={b} A={a}")
+    dev = cls_scores[0].device
+    anchors = _f32(anchors, "anchors").reshape(nl, a, 4).contiguous().to(dev)
+    hs = (ctypes.c_int * nl)(*[int(c.shape[2]) for c in cls_scores])
+    wsz = (ctypes.c_int * nl)(*[int(c.shape[3]) for c in cls_scores])
+    st = (ctypes.c_int * nl)(*[int(s) for s in strides])
+    cp = (ctypes.c_void_p * nl)(*[c.data_ptr() for c in cls_scores])
+    rp = (ctypes.c_void_p * nl)(*[r.data_ptr() for r in bbox_preds])
+    hw_t = None
+    if img_shapes is not None:
+        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32,
+                            pin_memory=True).to(dev, non_blocking=True)
+    prop = torch.empty((b, max_per_img, 5), device=dev, dtype=torch.float32)
+    lvl = torch.empty((b, max_per_img), device=dev, dtype=torch.int32)
+    cnt = torch.empty((b,), device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    nbytes = int(lib.fgn_rpn_proposals_workspace_bytes(hs, wsz, nl, a, b, int(nms_pre)))
+    ws = torch.empty((max(nbytes, 256),), device=dev, dtype=torch.uint8)
+    m4 = (ctypes.c_float * 4)(*[float(v) for v in means])
+    s4 = (ctypes.c_float * 4)(*[float(v) for v in stds])
+    _lib.check(lib.fgn_rpn_proposals(cp, rp, hs, wsz, st, nl, a, b, anchors.data_ptr(), _ptr(hw_t), m4, s4,
+                                     float(wh_ratio_clip), int(nms_pre), float(iou_thr), int(max_per_img),
+                                     float(min_bbox_size), prop.data_ptr(), lvl.data_ptr(), cnt.data_ptr(),
+                                     ws.data_ptr(), nbytes, _stream()), "fgn_rpn_proposals")
+    return prop, lvl, cnt

@@ -260,6 +260,23 @@ int fgn_det_postprocess(const float *rois, const float *cls_score, const float *
                         float *det_out, int32_t *label_out, int32_t *count_out,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* RPN proposals: RPNHead.get_bboxes / _get_bboxes_single [3P, mmdet 2.18] as called from fgn.py:229-235 on the
+ * (best-class-selected, fgn_ag_rpn_head.py:87-113) outputs of AGRPNHead with test_cfg.rpn
+ * (fgn_r50_c4_densecl.py:175-180) -- per level: sigmoid scores in (H,W,A) order, the nms_pre best, DeltaXYWHBBoxCoder
+ * decode against the grid anchors (base_anchors[l,a] + (x,y,x,y)*stride_l), clip to img_hw, w/h > min_bbox_size
+ * (negative: no filter), per-level NMS (mmcv batched_nms with ids = level), the max_per_img best by score.
+ *   cls[l] [B,A,H_l,W_l], reg[l] [B,4A,H_l,W_l] (device pointers in HOST arrays; H, W, strides HOST int arrays);
+ *   base_anchors [L,A,4] device (mmdet AnchorGenerator.base_anchors); means/stds HOST float[4];
+ *   prop_out [B,max_per_img,5] (x1,y1,x2,y2,score), level_out [B,max_per_img], count_out [B].
+ * The pre-NMS ordering uses cub::DeviceSegmentedRadixSort (CUDA toolkit library; adjacent to the hot path). */
+size_t fgn_rpn_proposals_workspace_bytes(const int *H, const int *W, int L, int A, int B, int nms_pre);
+int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const int *H, const int *W,
+                      const int *strides, int L, int A, int B, const float *base_anchors,
+                      const float *img_hw, const float *means, const float *stds, float wh_ratio_clip,
+                      int nms_pre, float iou_thr, int max_per_img, float min_bbox_size,
+                      float *prop_out, int32_t *level_out, int32_t *count_out,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* Number of kernels this library has launched in the calling process since load
  * (bench.py's gpu_launches). */
 uint64_t fgn_launch_count(void);

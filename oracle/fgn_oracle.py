@@ -406,3 +406,54 @@ def bbox_head_get_bboxes(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred:
         sf = bboxes.new_tensor(scale_factor)
         bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size(0), -1)
     return multiclass_nms(bboxes, scores, score_thr, iou_thr, max_per_img, nms_impl)
+
+
+# ---- RPN proposals: RPNHead.get_bboxes [3P] (called at fgn.py:229-235) ------------------------------------------
+def anchor_base(base_size: float, scales, ratios) -> torch.Tensor:
+    """mmdet 2.18 AnchorGenerator.gen_single_level_base_anchors [3P, unpinned] (scale_major, center_offset 0)."""
+    sc, ra = torch.tensor(list(scales), dtype=torch.float32), torch.tensor(list(ratios), dtype=torch.float32)
+    h_ratios = torch.sqrt(ra)
+    w_ratios = 1 / h_ratios
+    ws = (float(base_size) * w_ratios[:, None] * sc[None, :]).view(-1)
+    hs = (float(base_size) * h_ratios[:, None] * sc[None, :]).view(-1)
+    return torch.stack([-0.5 * ws, -0.5 * hs, 0.5 * ws, 0.5 * hs], dim=-1)
+
+
+def anchor_grid(base: torch.Tensor, h: int, w: int, stride: int) -> torch.Tensor:
+    """mmdet 2.18 AnchorGenerator.single_level_grid_priors [3P]: [(y*W + x)*A + a, 4]."""
+    shift_x = torch.arange(0, w, dtype=torch.float32) * stride
+    shift_y = torch.arange(0, h, dtype=torch.float32) * stride
+    xx = shift_x.repeat(h)
+    yy = shift_y.view(-1, 1).repeat(1, w).view(-1)
+    shifts = torch.stack([xx, yy, xx, yy], dim=-1)
+    return (base[None, :, :] + shifts[:, None, :]).view(-1, 4)
+
+
+def rpn_get_bboxes_single(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor],
+                          mlvl_anchors: Sequence[torch.Tensor], img_shape, nms_pre: int = 6000, iou_thr: float = 0.7,
+                          max_per_img: int = 300, min_bbox_size: float = 0.0, means=(0., 0., 0., 0.),
+                          stds=(1., 1., 1., 1.)):
+    """mmdet 2.18 RPNHead._get_bboxes_single [3P, unpinned], sigmoid scores, ONE image: cls_scores[l] [A,H,W],
+    bbox_preds[l] [4A,H,W].  The pre-NMS sort is made deterministic (stable, by logit: a refinement of the
+    reference's unstable sort by score).  Returns (dets [D,5], level ids [D])."""
+    import torchvision
+    lv_scores, lv_preds, lv_anchors, lv_ids = [], [], [], []
+    for idx, (c, r, anchors) in enumerate(zip(cls_scores, bbox_preds, mlvl_anchors)):
+        logit = c.permute(1, 2, 0).reshape(-1)
+        pred = r.permute(1, 2, 0).reshape(-1, 4)
+        order = torch.sort(logit, descending=True, stable=True).indices
+        if nms_pre > 0 and logit.shape[0] > nms_pre:
+            order = order[:nms_pre]
+        lv_scores.append(logit[order].sigmoid()); lv_preds.append(pred[order]); lv_anchors.append(anchors[order])
+        lv_ids.append(torch.full((order.shape[0],), idx, dtype=torch.long))
+    scores, anchors, preds, ids = torch.cat(lv_scores), torch.cat(lv_anchors), torch.cat(lv_preds), torch.cat(lv_ids)
+    proposals = delta2bbox(anchors, preds, means, stds, max_shape=img_shape)
+    if min_bbox_size >= 0:
+        w, h = proposals[:, 2] - proposals[:, 0], proposals[:, 3] - proposals[:, 1]
+        valid = (w > min_bbox_size) & (h > min_bbox_size)
+        proposals, scores, ids = proposals[valid], scores[valid], ids[valid]
+    if proposals.numel() == 0:
+        return proposals.new_zeros((0, 5)), ids
+    offsets = ids.to(proposals) * (proposals.max() + torch.tensor(1).to(proposals))
+    keep = torchvision.ops.nms(proposals + offsets[:, None], scores, iou_thr)[:max_per_img]
+    return torch.cat([proposals[keep], scores[keep, None]], -1), ids[keep]

@@ -798,3 +798,58 @@ def test_simple_test_detections_feed_the_mask_branch():
     want = O.mask_attention([qry.cpu().contiguous()], [16], mask_rois.cpu(), head.spp_fvecs_roi_aligned_cat_mean_mp.cpu(),
                             [labels[0].cpu()], cfg.n_ways, 7)
     close(res["mask_feats"], want, what="simple_test mask feats")
+
+
+# ---- RPN proposals (RPNHead.get_bboxes [3P], fgn.py:229-235) ---------------------------------------------------
+@pytest.mark.parametrize("levels,B,nms_pre,max_per_img", [([(32, 32, 16)], 1, 6000, 300), ([(50, 84, 16)], 2, 6000, 300),
+                                                           ([(48, 64, 4), (24, 32, 8), (12, 16, 16), (6, 8, 32), (3, 4, 64)], 2, 1000, 1000),
+                                                           ([(8, 8, 16)], 1, 6000, 300)])
+def test_rpn_proposals_vs_oracle(levels, B, nms_pre, max_per_img):
+    """Sigmoid + per-level top-k + anchor decode + clip + min-size filter + per-level NMS + top-k through the C ABI
+    against the restated mmdet RPNHead._get_bboxes_single: same proposals in the same order."""
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(31 + len(levels) + B)
+    scales, ratios = [2, 4, 8, 16, 32] if len(levels) == 1 else [8], [0.5, 1.0, 2.0]
+    A = len(scales) * len(ratios)
+    cls = [torch.randn(B, A, h, w, generator=g) * 2 for h, w, _ in levels]
+    reg = [torch.randn(B, 4 * A, h, w, generator=g) * 0.3 for h, w, _ in levels]
+    strides = [s for _, _, s in levels]
+    img_h, img_w = levels[0][0] * strides[0] - 5, levels[0][1] * strides[0] - 3
+    base = [O.anchor_base(s, scales, ratios) for s in strides]
+    assert torch.equal(torch.stack(base), torch.stack([ops.base_anchors(s, scales, ratios) for s in strides]))
+    prop, lvl, cnt = ops.rpn_proposals([c.to(dev()) for c in cls], [r.to(dev()) for r in reg], strides,
+                                       torch.stack(base), [(img_h, img_w, 3)] * B, nms_pre=nms_pre, iou_thr=0.7,
+                                       max_per_img=max_per_img, min_bbox_size=0)
+    cnt = cnt.cpu().tolist()
+    for b in range(B):
+        anchors = [O.anchor_grid(base[l], levels[l][0], levels[l][1], strides[l]) for l in range(len(levels))]
+        wd, wid = O.rpn_get_bboxes_single([c[b] for c in cls], [r[b] for r in reg], anchors, (img_h, img_w, 3),
+                                          nms_pre, 0.7, max_per_img, 0.0)
+        assert cnt[b] == wd.shape[0], (b, cnt[b], wd.shape[0])
+        assert torch.equal(lvl[b, :cnt[b]].cpu().long(), wid)
+        close(prop[b, :cnt[b]], wd, what=f"proposals image {b}")
+
+
+def test_agrpn_get_bboxes_feeds_the_roi_head():
+    """AGRPNHead.forward_single -> get_bboxes -> FGNRoIHead.simple_test_bboxes: the reference's test-time chain
+    (fgn.py:226-240) runs end to end on the device and yields detections."""
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    rpn, head = build_heads(cfg, dev(), shared_head=None)
+    ep = episode_to_device(make_episode(cfg, seed=4), dev())
+    qry = ep["qry"][0]
+    with torch.no_grad():
+        cls, reg = rpn.forward_single(qry, ep["spp"][0])
+    metas = [dict(img_shape=(cfg.img_h, cfg.img_w, 3), scale_factor=(1.0, 1.0, 1.0, 1.0))]
+    rpn_cfg = dict(nms_pre=6000, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300, min_bbox_size=0)
+    props = rpn.get_bboxes([cls], [reg], img_metas=metas, cfg=rpn_cfg)
+    assert len(props) == 1 and props[0].shape[1] == 5 and 0 < props[0].shape[0] <= 300
+    assert (props[0][:-1, 4] >= props[0][1:, 4]).all()
+    base = O.anchor_base(16, rpn.anchor_scales, rpn.anchor_ratios)
+    wd, _ = O.rpn_get_bboxes_single([cls[0].cpu()], [reg[0].cpu()], [O.anchor_grid(base, cls.shape[2], cls.shape[3], 16)],
+                                    metas[0]["img_shape"], 6000, 0.7, 300, 0.0)
+    close(props[0], wd, what="AGRPNHead.get_bboxes")
+    head.count_spp(ep["spp"][0], ep["spp_bboxes"].clone(), ep["spp_masks"])
+    rcnn = dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100)
+    dets, labels = head.simple_test_bboxes(qry, metas, [p[:, :4] for p in props], rcnn)
+    assert dets[0].shape[1] == 5 and dets[0].shape[0] == labels[0].shape[0] <= 100

@@ -245,3 +245,30 @@ def test_delta2bbox_known_values():
     out = O.delta2bbox(rois, d, (0, 0, 0, 0), (0.1, 0.1, 0.2, 0.2))
     cx, cy, w, h = 30 + 40 * 0.1, 60 - 80 * 0.1, 80.0, 80 * 1000 / 16
     assert torch.allclose(out, torch.tensor([[cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]]), rtol=1e-5)
+
+
+def test_anchor_grid_matches_mmdet_docstring_example():
+    """Known answer published in mmdet's AnchorGenerator docstring [3P]:
+    AnchorGenerator([16], [1.], [1.], [9]).grid_anchors([(2, 2)]) ->
+    [[-4.5,-4.5,4.5,4.5],[11.5,-4.5,20.5,4.5],[-4.5,11.5,4.5,20.5],[11.5,11.5,20.5,20.5]]."""
+    base = O.anchor_base(9, [1.0], [1.0])
+    got = O.anchor_grid(base, 2, 2, 16)
+    want = torch.tensor([[-4.5, -4.5, 4.5, 4.5], [11.5, -4.5, 20.5, 4.5], [-4.5, 11.5, 4.5, 20.5], [11.5, 11.5, 20.5, 20.5]])
+    assert torch.equal(got, want)
+    # ratio-major / scale-minor ordering of the base anchors, h/w = ratio
+    b = O.anchor_base(16, [2, 4], [0.5, 2.0])
+    wh = torch.stack([b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1)
+    assert torch.allclose(wh[:, 1] / wh[:, 0], torch.tensor([0.5, 0.5, 2.0, 2.0]))
+    assert torch.allclose((wh[:, 0] * wh[:, 1]).sqrt(), torch.tensor([32., 64., 32., 64.]))
+
+
+def test_rpn_restatement_small_case():
+    """_get_bboxes_single restatement on a hand-checkable case: zero deltas return the (clipped) anchors, NMS keeps
+    the best of coincident anchors, results are score-ordered and capped."""
+    base = O.anchor_base(16, [2], [1.0])                       # one 32x32 anchor per cell
+    cls = torch.tensor([[[2.0, 1.0], [0.5, -1.0]]])            # [A=1, H=2, W=2]
+    reg = torch.zeros(4, 2, 2)
+    dets, ids = O.rpn_get_bboxes_single([cls], [reg], [O.anchor_grid(base, 2, 2, 16)], (32, 32, 3), 6000, 0.7, 3, 0.0)
+    assert dets.shape == (3, 5) and torch.equal(ids, torch.zeros(3, dtype=torch.long))
+    assert torch.allclose(dets[:, 4], torch.tensor([2.0, 1.0, 0.5]).sigmoid())
+    assert torch.equal(dets[0, :4], torch.tensor([0., 0., 16., 16.]))          # anchor (-16,-16,16,16) clipped
