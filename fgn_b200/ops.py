@@ -595,7 +595,9 @@ def rpn_proposals(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch
         if c.dim() != 4 or r.shape != (b, 4 * a, c.shape[2], c.shape[3]) or c.shape[:2] != (b, a):
             raise FgnError(f"rpn_proposals: cls {tuple(c.shape)} / reg {tuple(r.shape)} do not match B={b} A={a}")
     dev = cls_scores[0].device
-    anchors = _f32(anchors, "anchors").reshape(nl, a, 4).contiguous().to(dev)
+    anchors = _f32(anchors, "anchors").reshape(nl, a, 4).contiguous()
+    if anchors.device != dev:                                    # (pinned staging: graph-capturable)
+        anchors = anchors.pin_memory().to(dev, non_blocking=True)
     hs = (ctypes.c_int * nl)(*[int(c.shape[2]) for c in cls_scores])
     wsz = (ctypes.c_int * nl)(*[int(c.shape[3]) for c in cls_scores])
     st = (ctypes.c_int * nl)(*[int(s) for s in strides])
