@@ -8,6 +8,7 @@ Host-side mirror of the reference's operator/plugin interface for this path only
   AGRPNHead.forward_single   (fgn_ag_rpn_head.py:26)        fgn_b200.AGRPNHead.forward_single
   FGNRoIHead.count_spp/_bbox_forward/_mask_forward/...      fgn_b200.FGNRoIHead (same names)
   (fgn_roi_head.py:253-449, 675-719)
+  FGN.simple_test            (fgn.py:186-240)               fgn_b200.FGN.simple_test (backbone = caller's module)
 
 All device work goes through the C ABI in include/fgn_b200.h (libfgn_b200.so, hand-written CUDA).
 There is no CPU fallback.
@@ -17,5 +18,6 @@ from . import ops  # noqa: F401
 from .roi_extractor import RoIAlign, SingleRoIExtractor, bbox2roi  # noqa: F401
 from .ag_rpn_head import AGRPNHead  # noqa: F401
 from .roi_head import FGNBBoxHead, FGNRoIHead  # noqa: F401
+from .detector import FGN  # noqa: F401
 
 __version__ = "0.1.0"

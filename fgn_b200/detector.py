@@ -1,0 +1,73 @@
+"""FGN test-time driver: host-side mirror of the reference detector's ``simple_test``
+(subprojects/sp02_omniiseg_fgn_mmdet/fgn.py:28-50,68-108,186-240) around the device path.
+
+The backbone (ResNet-C4 / R50-FPN in the reference's configs) is the caller's module -- convolutions are not on
+the path this package rebuilds -- everything after it runs through the C ABI:
+AGRPNHead.forward_single -> AGRPNHead.get_bboxes -> FGNRoIHead.simple_test.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .ag_rpn_head import AGRPNHead
+from .roi_head import FGNRoIHead
+
+
+class FGN(nn.Module):
+    """``FGN(n_ways, k_shots, backbone=..., rpn_head=..., roi_head=..., test_cfg=...)`` as fgn.py:41-50: the
+    episode shape is pushed onto the heads.  ``test_cfg`` = dict(rpn=dict(nms_pre, nms=dict(iou_threshold),
+    max_per_img, min_bbox_size), rcnn=dict(score_thr, nms=dict(iou_threshold), max_per_img))
+    (fgn_r50_c4_densecl.py:173-186)."""
+
+    def __init__(self, n_ways: int, k_shots: int, backbone: nn.Module, rpn_head: AGRPNHead, roi_head: FGNRoIHead,
+                 test_cfg: Optional[dict] = None, train_cfg: Optional[dict] = None):
+        super().__init__()
+        self.backbone, self.rpn_head, self.roi_head = backbone, rpn_head, roi_head
+        self.test_cfg, self.train_cfg = test_cfg, train_cfg
+        self.n_ways, self.k_shots = n_ways, k_shots
+        for m in (self.rpn_head, self.roi_head, self.roi_head.bbox_head):
+            m.n_ways, m.k_shots = n_ways, k_shots
+        if test_cfg is not None:
+            self.roi_head.test_cfg = test_cfg.get("rcnn", test_cfg)
+
+    def extract_feat(self, img: torch.Tensor):
+        """fgn.py:68-80: backbone output (a tuple of maps; the C4 configs use element 0)."""
+        x = self.backbone(img)
+        return x if isinstance(x, (tuple, list)) else (x,)
+
+    @staticmethod
+    def get_img_metas(img_shape: Sequence) -> List[dict]:
+        """fgn.py:110-123: one meta per query image, scale_factor 1."""
+        metas = []
+        for s in img_shape:
+            t = tuple(int(v) for v in (s.tolist() if torch.is_tensor(s) else s))
+            metas.append(dict(num_samples=1, pad_shape=t, img_shape=t, ori_shape=t, scale_factor=(1.0, 1.0, 1.0, 1.0)))
+        return metas
+
+    @torch.no_grad()
+    def simple_test(self, qry_img: torch.Tensor, spp_imgs: torch.Tensor, spp_bboxes: torch.Tensor,
+                    spp_isegmaps: torch.Tensor, img_shape: Sequence, rescale: bool = False, boxes_yxyx: bool = True):
+        """fgn.py:186-240.  ``qry_img`` [B,3,H,W]; ``spp_imgs`` [B,N,K,3,S,S] (or already flattened
+        [B*N*K,3,S,S]); ``spp_bboxes`` [...,4] in the dataset's YXYX order (``boxes_yxyx``, fgn.py:104-106) ;
+        ``spp_isegmaps`` [...,S,S] bool.  Returns what FGNRoIHead.simple_test returns: per-image
+        ``(det_bboxes, det_labels)`` lists (and the mask-branch dict when the head has a mask branch)."""
+        if self.test_cfg is None:
+            raise ValueError("FGN.simple_test needs test_cfg (rpn + rcnn)")
+        if boxes_yxyx:
+            spp_bboxes = spp_bboxes[..., [1, 0, 3, 2]]
+        img_metas = self.get_img_metas(img_shape)
+        qry_fmap = self.extract_feat(qry_img)[0]
+        c, h, w = spp_imgs.shape[-3:]
+        spp_fmaps = self.extract_feat(spp_imgs.reshape(-1, c, h, w))[0]
+        spp_bboxes = spp_bboxes.reshape(-1, 1, 4).to(torch.float32).contiguous()
+        h, w = spp_isegmaps.shape[-2:]
+        spp_isegmaps = spp_isegmaps.reshape(-1, 1, h, w)
+        self.rpn_head.log_mode = False
+        rpn_cls_score, rpn_bbox_pred = self.rpn_head.forward_single(qry_fmap, spp_fmaps)
+        proposal_cfg = self.test_cfg.get("rpn_proposal", self.test_cfg["rpn"])
+        proposal_list = self.rpn_head.get_bboxes([rpn_cls_score], [rpn_bbox_pred], img_metas=img_metas, cfg=proposal_cfg)
+        return self.roi_head.simple_test(qry_fmap, [p[:, :4] for p in proposal_list], img_metas, rescale=rescale,
+                                         spp_fmaps=spp_fmaps, spp_bboxes=spp_bboxes, spp_isegmaps=spp_isegmaps)

@@ -853,3 +853,39 @@ def test_agrpn_get_bboxes_feeds_the_roi_head():
     rcnn = dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100)
     dets, labels = head.simple_test_bboxes(qry, metas, [p[:, :4] for p in props], rcnn)
     assert dets[0].shape[1] == 5 and dets[0].shape[0] == labels[0].shape[0] <= 100
+
+
+def test_fgn_detector_simple_test_chain():
+    """fgn_b200.FGN.simple_test (fgn.py:186-240) with a toy stride-16 backbone: query image + N*K support images in,
+    per-image detections out; every stage after the backbone is the device path, and the result equals running
+    the stages by hand (rpn forward -> oracle proposals -> head with those proposals)."""
+    import fgn_b200
+    from fgn_b200.episodes import CONFIGS, build_heads
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    rpn, head = build_heads(cfg, dev(), shared_head=None)
+    torch.manual_seed(3)
+    backbone = torch.nn.Sequential(torch.nn.Conv2d(3, cfg.channels, 16, stride=16), torch.nn.ReLU()).to(dev())
+    test_cfg = dict(rpn=dict(nms_pre=6000, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300, min_bbox_size=0),
+                    rcnn=dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100))
+    det = fgn_b200.FGN(cfg.n_ways, cfg.k_shots, backbone, rpn, head, test_cfg).eval()
+    g = torch.Generator().manual_seed(11)
+    S = 128
+    qry = torch.randn(1, 3, 256, 320, generator=g).to(dev())
+    spp = torch.randn(1, cfg.n_ways, cfg.k_shots, 3, S, S, generator=g).to(dev())
+    spp_boxes_yxyx = torch.tensor([12.0, 10.0, 110.0, 100.0]).repeat(1, cfg.n_ways, cfg.k_shots, 1).to(dev())
+    masks = (torch.rand(1, cfg.n_ways, cfg.k_shots, S, S, generator=g) > 0.5).to(dev())
+    dets, labels = det.simple_test(qry, spp, spp_boxes_yxyx, masks, img_shape=[(256, 320, 3)])
+    assert len(dets) == 1 and dets[0].shape[1] == 5 and dets[0].shape[0] == labels[0].shape[0] <= 100
+    assert labels[0].dtype == torch.long and int(labels[0].max()) < cfg.n_ways
+    # by hand, with the oracle's proposals in the middle
+    with torch.no_grad():
+        qf, sf = backbone(qry), backbone(spp.reshape(-1, 3, S, S))
+        cls, reg = rpn.forward_single(qf, sf)
+    base = O.anchor_base(16, rpn.anchor_scales, rpn.anchor_ratios)
+    props, _ = O.rpn_get_bboxes_single([cls[0].cpu()], [reg[0].cpu()], [O.anchor_grid(base, cls.shape[2], cls.shape[3], 16)],
+                                       (256, 320, 3), 6000, 0.7, 300, 0.0)
+    head.count_spp(sf, spp_boxes_yxyx[..., [1, 0, 3, 2]].reshape(-1, 1, 4).clone(), masks.reshape(-1, 1, S, S))
+    metas = det.get_img_metas([(256, 320, 3)])
+    d2, l2 = head.simple_test_bboxes(qf, metas, [props[:, :4].to(dev())], test_cfg["rcnn"])
+    assert torch.equal(labels[0], l2[0])
+    close(dets[0], d2[0], what="FGN.simple_test vs stages by hand")
