@@ -208,18 +208,21 @@ __global__ void det_nms_mask_kernel(const DetParams p, unsigned char *ws, const 
 // makes the greedy pass over the score-sorted list, ORing the rows of the boxes it keeps
 __global__ void det_nms_reduce_kernel(const DetParams p, unsigned char *ws, const DetWs L, const int smem_rows)
 {
-    extern __shared__ unsigned long long sm[];                   // remv[words] | rows[smem_rows][words]
+    extern __shared__ unsigned long long sm[];                   // remv[W] | diag[Rmax] | rows[smem_rows][W]
     const int n = blockIdx.x, b = blockIdx.y, N = p.N, t = threadIdx.x, lane = t & 31;
     unsigned int *hdr = hdr_of(ws, L, b, N);
     const int m = (int)hdr[2 + n];
     const int words = (m + 63) / 64, W = L.words;
-    unsigned long long *remv = sm, *rows = sm + W;
+    unsigned long long *remv = sm, *diag = sm + W, *rows = diag + p.Rmax;
     const unsigned long long *mask = reinterpret_cast<const unsigned long long *>(ws + L.mask) + ((size_t)b * N + n) * p.Rmax * W;
     for (int w = t; w < words; w += blockDim.x) remv[w] = 0ull;
+    // the word a box needs at once when it is kept (its own 64-box block) is always served from shared memory;
+    // the rest of a kept box's row is ORed in off the serial chain (shared memory for the first rows, global after)
+    for (int i = t; i < m; i += blockDim.x) diag[i] = mask[(size_t)i * W + (i >> 6)];
     const int staged = min(m, smem_rows);
     for (int e = t; e < staged * words; e += blockDim.x) {
         const int i = e / words, w = e - i * words;
-        if (w >= (i >> 6)) rows[(size_t)i * W + w] = mask[(size_t)i * W + w];     // words below the row's block were never written
+        if (w > (i >> 6)) rows[(size_t)i * W + w] = mask[(size_t)i * W + w];      // words below the row's block were never written
     }
     __syncthreads();
     if (t >= 32) return;
@@ -233,8 +236,8 @@ __global__ void det_nms_reduce_kernel(const DetParams p, unsigned char *ws, cons
             const int i = base + bit;
             if (lane == 0) kept[nk] = i;
             ++nk;
+            cur |= diag[i];                                      // the only load on the serial chain (uniform, shared)
             const unsigned long long *row = i < staged ? rows + (size_t)i * W : mask + (size_t)i * W;
-            cur |= row[wb];                                      // the only load on the serial chain (uniform)
             for (int w = wb + 1 + lane; w < words; w += 32) remv[w] |= row[w];    // each lane owns its words within a block
         }
         __syncwarp();
@@ -303,7 +306,7 @@ __global__ void rpn_keys_kernel(const RpnParams q, float *keys, int *vals, int *
 {
     const int per_img = q.seg_off[q.L];
     const size_t total = (size_t)q.B * per_img;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; keys != nullptr && i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / per_img), j = (int)(i - (size_t)b * per_img);
         int l = 0;
         while (l + 1 < q.L && j >= q.seg_off[l + 1]) ++l;
@@ -320,6 +323,174 @@ __global__ void rpn_keys_kernel(const RpnParams q, float *keys, int *vals, int *
         }
         for (int b = threadIdx.x; b <= q.B; b += blockDim.x) img_off[b] = b * q.K;
     }
+}
+
+
+// ---- hand-written segmented top-K (K <= kSelCap) for the pre-NMS selection ----------------------------------------
+// One segment = one (image, level).  The K best logits by (value desc, anchor index asc) are found with a two-level
+// radix select on the order-preserving 32-bit image of the float (16 + 16 bits, histograms in global memory), the
+// winners are collected in anchor-index order by one block per segment (ties at the threshold value resolve to the
+// lowest indices, exactly like a stable sort) and sorted in shared memory (bitonic).  No library call.
+constexpr int kSelCap = 8192;                      // candidates one block sorts in shared memory
+constexpr int kSelBins = 65536;
+
+__device__ __forceinline__ float rpn_logit(const RpnParams &q, int b, int l, int idx)
+{
+    const int a = idx % q.A, cell = idx / q.A;
+    return q.cls[l][((size_t)b * q.A + a) * q.H[l] * q.W[l] + cell];
+}
+
+// S1: histogram of the high 16 bits; grid (blocks, L, B)
+__global__ void rpn_hist_hi_kernel(const RpnParams q, unsigned int *hist)
+{
+    const int l = blockIdx.y, b = blockIdx.z, m = q.seg_off[l + 1] - q.seg_off[l];
+    unsigned int *h = hist + ((size_t)b * q.L + l) * kSelBins;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m; idx += gridDim.x * blockDim.x)
+        atomicAdd(&h[f2ord(rpn_logit(q, b, l, idx)) >> 16], 1u);
+}
+
+// block-wide: largest bin T with  sum_{bin > T} h[bin] < want <= sum_{bin >= T} h[bin];  returns T and the count above it
+__device__ void select_bin(const unsigned int *h, unsigned int want, unsigned int *sm /*[1024 + 2]*/, unsigned int &T, unsigned int &above)
+{
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;   // blockDim.x == 1024: thread t owns bins [lo, lo + 64), t = 0 at the top
+    const int lo = kSelBins - 64 * (t + 1);
+    unsigned int mine = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint4 u = reinterpret_cast<const uint4 *>(h + lo)[i];
+        mine += u.x + u.y + u.z + u.w;
+    }
+    // exclusive prefix over threads (top bins first): warp scan, then the 32 warp totals
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) sm[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = sm[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+        sm[32 + lane] = wi - w;                                   // exclusive warp offsets
+    }
+    __syncthreads();
+    const unsigned int before = sm[32 + wid] + incl - mine;      // items in bins above this thread's range
+    __syncthreads();
+    if (before < want && before + mine >= want) {                // exactly one thread
+        unsigned int cum = before;
+        int bin = lo + 63;
+        for (int i = 63; i >= 0; --i) { const unsigned int c = h[lo + i]; if (cum + c >= want) { bin = lo + i; break; } cum += c; }
+        sm[1024] = (unsigned)bin; sm[1025] = cum;
+    }
+    __syncthreads();
+    T = sm[1024]; above = sm[1025];
+    __syncthreads();
+}
+
+// S2: every block finds the segment's high bin T (redundantly), then histograms the low 16 bits inside it
+__global__ void __launch_bounds__(1024) rpn_hist_lo_kernel(const RpnParams q, const unsigned int *hist_hi, unsigned int *hist_lo)
+{
+    __shared__ unsigned int sm[1026];
+    const int l = blockIdx.y, b = blockIdx.z, m = q.seg_off[l + 1] - q.seg_off[l];
+    if (m <= q.K) return;                           // everything is kept: no threshold
+    const size_t sgm = (size_t)b * q.L + l;
+    unsigned int T, above;
+    select_bin(hist_hi + sgm * kSelBins, (unsigned)q.K, sm, T, above);
+    unsigned int *h = hist_lo + sgm * kSelBins;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m; idx += gridDim.x * blockDim.x) {
+        const unsigned int o = f2ord(rpn_logit(q, b, l, idx));
+        if ((o >> 16) == T) atomicAdd(&h[o & 0xffffu], 1u);
+    }
+}
+
+// S3: one block per segment: exact threshold value, winners collected in index order, bitonic sort, output
+__global__ void __launch_bounds__(1024) rpn_select_sort_kernel(const RpnParams q, const unsigned int *hist_hi,
+                                                              const unsigned int *hist_lo, float *keys_out, int *vals_out)
+{
+    extern __shared__ unsigned int dyn[];           // ord[kSelCap] | idx[kSelCap]
+    __shared__ unsigned int sm[1026];
+    __shared__ int s_warp[32];
+    __shared__ int s_base, s_eq_taken;
+    unsigned int *sord = dyn;
+    int *sidx = reinterpret_cast<int *>(dyn + kSelCap);
+    const int l = blockIdx.x, b = blockIdx.y, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int m = q.seg_off[l + 1] - q.seg_off[l];
+    const int K = min(q.K, m);
+    const size_t sgm = (size_t)b * q.L + l;
+    unsigned int thr = 0, need_eq = 0;              // keep ord > thr, and the first need_eq (by index) with ord == thr
+    if (m > q.K) {
+        unsigned int T, above, Tl, above_l;
+        select_bin(hist_hi + sgm * kSelBins, (unsigned)q.K, sm, T, above);
+        select_bin(hist_lo + sgm * kSelBins, (unsigned)q.K - above, sm, Tl, above_l);
+        thr = (T << 16) | Tl;
+        need_eq = (unsigned)q.K - above - above_l;
+    }
+    if (t == 0) { s_base = 0; s_eq_taken = 0; }
+    __syncthreads();
+    // block-wide exclusive scan of one int per thread (returns the prefix; *total = block sum)
+    auto block_scan = [&](int v, int *total) {
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) { const int c = s_warp[w]; if (w < wid) woff += c; tot += c; }
+        __syncthreads();
+        *total = tot;
+        return woff + incl - v;
+    };
+    constexpr int kPer = 8;                          // consecutive anchor indices per thread and step
+    for (int i0 = 0; i0 < m; i0 += 1024 * kPer) {   // index order: the equal-valued winners are the lowest indices
+        const int first = i0 + t * kPer;
+        unsigned int o[kPer];
+        int ce = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int idx = first + j;
+            o[j] = idx < m ? f2ord(rpn_logit(q, b, l, idx)) : 0u;
+            ce += (idx < m && m > q.K && o[j] == thr) ? 1 : 0;
+        }
+        int eq_total, tk_total;
+        int eq_rank = s_eq_taken + block_scan(ce, &eq_total);
+        unsigned takes = 0;
+        int ct = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int idx = first + j;
+            const bool gt = idx < m && (m <= q.K || o[j] > thr), eq = idx < m && m > q.K && o[j] == thr;
+            const bool take = gt || (eq && (unsigned)eq_rank < need_eq);
+            eq_rank += eq ? 1 : 0;
+            if (take) { takes |= 1u << j; ++ct; }
+        }
+        int pos = s_base + block_scan(ct, &tk_total);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+            if ((takes >> j) & 1u) { if (pos < kSelCap) { sord[pos] = o[j]; sidx[pos] = first + j; } ++pos; }
+        __syncthreads();
+        if (t == 0) { s_base += tk_total; s_eq_taken += eq_total; }
+        __syncthreads();
+    }
+    // pad to a power of two with sentinels that sort last, then bitonic sort by (ord desc, idx asc)
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    for (int i = K + t; i < n2; i += 1024) { sord[i] = 0u; sidx[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int k2 = 2; k2 <= n2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < n2; i += 1024) {
+                const int p2 = i ^ j;
+                if (p2 > i) {
+                    const unsigned int oa = sord[i], ob = sord[p2];
+                    const int ia = sidx[i], ib = sidx[p2];
+                    const bool a_first = oa > ob || (oa == ob && ia < ib);      // a belongs before b
+                    const bool up = (i & k2) == 0;
+                    if (up ? !a_first : a_first) { sord[i] = ob; sord[p2] = oa; sidx[i] = ib; sidx[p2] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    const size_t out0 = (size_t)b * q.seg_off[q.L] + q.seg_off[l];
+    for (int i = t; i < K; i += 1024) { keys_out[out0 + i] = ord2f(sord[i]); vals_out[out0 + i] = sidx[i]; }
 }
 
 // R2: decode the K best of every (image, level); grid (ceil(K/128), L, B)
@@ -437,8 +608,9 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
     {
         // stage as many mask rows as fit in 200 KB of shared memory next to the removed-bits vector
         const size_t row_bytes = (size_t)L.words * sizeof(unsigned long long);
-        const int smem_rows = (int)min((size_t)Rmax, (200 * 1024 - row_bytes) / row_bytes);
-        const size_t smem = row_bytes * (1 + (size_t)smem_rows);
+        const size_t diag_bytes = (size_t)Rmax * sizeof(unsigned long long);
+        const int smem_rows = (int)min((size_t)Rmax, (200 * 1024 - row_bytes - diag_bytes) / row_bytes);
+        const size_t smem = row_bytes * (1 + (size_t)smem_rows) + diag_bytes;
         static size_t attr = 48 * 1024;
         if (smem > attr) {
             FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -454,7 +626,7 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
 
 
 namespace {
-struct RpnWs { size_t det, keys_in, vals_in, keys_out, vals_out, seg_b, seg_e, img_off, cub, total; size_t cub_bytes; };
+struct RpnWs { size_t det, keys_in, vals_in, keys_out, vals_out, seg_b, seg_e, img_off, hist, cub, total; size_t cub_bytes; };
 
 RpnWs rpn_layout(const int *H, const int *W, int L, int A, int B, int K)
 {
@@ -471,6 +643,7 @@ RpnWs rpn_layout(const int *H, const int *W, int L, int A, int B, int K)
     w.seg_b = o;    o = align256(o + (size_t)B * L * 4);
     w.seg_e = o;    o = align256(o + (size_t)B * L * 4);
     w.img_off = o;  o = align256(o + (size_t)(B + 1) * 4);
+    w.hist = o;     o = align256(o + (size_t)2 * B * L * kSelBins * 4);    // high-16 and low-16 histograms per segment
     w.cub_bytes = 0;
     cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float *)nullptr, (float *)nullptr,
                                                        (const int *)nullptr, (int *)nullptr, (int)items, B * L,
@@ -535,12 +708,33 @@ extern "C" int fgn_rpn_proposals(const float *const *cls, const float *const *re
 
     FGN_CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(int32_t) * B, st));
     FGN_CUDA_OK(cudaMemsetAsync(ws + Ld.hdr, 0, (size_t)B * (2 + 2 * L) * sizeof(unsigned int), st));
-    rpn_keys_kernel<<<(int)min((size_t)1184, (items + 255) / 256), 256, 0, st>>>(q, keys_in, vals_in, seg_b, seg_e, img_off);
-    FGN_LAUNCH_OK();
-    size_t cub_bytes = Wl.cub_bytes;
-    FGN_CUDA_OK(cub::DeviceSegmentedRadixSort::SortPairsDescending(base + Wl.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out,
-                                                                   (int)items, B * L, seg_b, seg_e, 0, 32, st));
-    count_launch(2);                                             // (library sort: upsweep/downsweep passes, not counted exactly)
+    if (K <= kSelCap) {
+        // hand-written segmented top-K: two histograms + one select-and-sort block per (image, level)
+        unsigned int *hist_hi = (unsigned int *)(base + Wl.hist), *hist_lo = hist_hi + (size_t)B * L * kSelBins;
+        FGN_CUDA_OK(cudaMemsetAsync(hist_hi, 0, (size_t)2 * B * L * kSelBins * 4, st));
+        rpn_keys_kernel<<<1, 256, 0, st>>>(q, nullptr, nullptr, seg_b, seg_e, img_off);     // only the small index tables
+        FGN_LAUNCH_OK();
+        const int hb = max(1, min(64, ceil_div(maxm, 4096)));
+        rpn_hist_hi_kernel<<<dim3(hb, L, B), 256, 0, st>>>(q, hist_hi);
+        FGN_LAUNCH_OK();
+        rpn_hist_lo_kernel<<<dim3(hb, L, B), 1024, 0, st>>>(q, hist_hi, hist_lo);
+        FGN_LAUNCH_OK();
+        static bool sel_attr = false;
+        if (!sel_attr) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(rpn_select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 8));
+            sel_attr = true;
+        }
+        rpn_select_sort_kernel<<<dim3(L, B), 1024, kSelCap * 8, st>>>(q, hist_hi, hist_lo, keys_out, vals_out);
+        FGN_LAUNCH_OK();
+    } else {
+        // more candidates than one block sorts in shared memory (nms_pre > 8192): library segmented sort
+        rpn_keys_kernel<<<(int)min((size_t)1184, (items + 255) / 256), 256, 0, st>>>(q, keys_in, vals_in, seg_b, seg_e, img_off);
+        FGN_LAUNCH_OK();
+        size_t cub_bytes = Wl.cub_bytes;
+        FGN_CUDA_OK(cub::DeviceSegmentedRadixSort::SortPairsDescending(base + Wl.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                                       (int)items, B * L, seg_b, seg_e, 0, 32, st));
+        count_launch(2);                                         // (library sort passes, not counted exactly)
+    }
     rpn_decode_kernel<<<dim3(ceil_div(K, 128), L, B), 128, 0, st>>>(q, p, keys_out, vals_out, ws, Ld);
     FGN_LAUNCH_OK();
     rpn_compact_kernel<<<dim3(L, B), 1024, 0, st>>>(q, ws, Ld);
@@ -549,8 +743,9 @@ extern "C" int fgn_rpn_proposals(const float *const *cls, const float *const *re
     FGN_LAUNCH_OK();
     {
         const size_t row_bytes = (size_t)Ld.words * sizeof(unsigned long long);
-        const int smem_rows = (int)min((size_t)K, (200 * 1024 - row_bytes) / row_bytes);
-        const size_t smem = row_bytes * (1 + (size_t)smem_rows);
+        const size_t diag_bytes = (size_t)K * sizeof(unsigned long long);
+        const int smem_rows = (int)min((size_t)K, (200 * 1024 - row_bytes - diag_bytes) / row_bytes);
+        const size_t smem = row_bytes * (1 + (size_t)smem_rows) + diag_bytes;
         static size_t attr = 48 * 1024;
         if (smem > attr) {
             FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -268,7 +268,8 @@ int fgn_det_postprocess(const float *rois, const float *cls_score, const float *
  *   cls[l] [B,A,H_l,W_l], reg[l] [B,4A,H_l,W_l] (device pointers in HOST arrays; H, W, strides HOST int arrays);
  *   base_anchors [L,A,4] device (mmdet AnchorGenerator.base_anchors); means/stds HOST float[4];
  *   prop_out [B,max_per_img,5] (x1,y1,x2,y2,score), level_out [B,max_per_img], count_out [B].
- * The pre-NMS ordering uses cub::DeviceSegmentedRadixSort (CUDA toolkit library; adjacent to the hot path). */
+ * The pre-NMS selection is a hand-written two-level radix select + shared-memory bitonic sort for nms_pre <= 8192
+ * (every test config); larger nms_pre falls back to cub::DeviceSegmentedRadixSort. */
 size_t fgn_rpn_proposals_workspace_bytes(const int *H, const int *W, int L, int A, int B, int nms_pre);
 int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const int *H, const int *W,
                       const int *strides, int L, int A, int B, const float *base_anchors,
