@@ -803,7 +803,9 @@ def test_simple_test_detections_feed_the_mask_branch():
 # ---- RPN proposals (RPNHead.get_bboxes [3P], fgn.py:229-235) ---------------------------------------------------
 @pytest.mark.parametrize("levels,B,nms_pre,max_per_img", [([(32, 32, 16)], 1, 6000, 300), ([(50, 84, 16)], 2, 6000, 300),
                                                            ([(48, 64, 4), (24, 32, 8), (12, 16, 16), (6, 8, 32), (3, 4, 64)], 2, 1000, 1000),
-                                                           ([(8, 8, 16)], 1, 6000, 300)])
+                                                           ([(8, 8, 16)], 1, 6000, 300),
+                                                           ([(50, 84, 16)], 1, 12000, 2000)],    # train-time rpn_proposal cfg: library sort path
+                         ids=["c4-32x32", "c4-50x84-b2", "fpn5-b2", "tiny", "nms_pre-12000"])
 def test_rpn_proposals_vs_oracle(levels, B, nms_pre, max_per_img):
     """Sigmoid + per-level top-k + anchor decode + clip + min-size filter + per-level NMS + top-k through the C ABI
     against the restated mmdet RPNHead._get_bboxes_single: same proposals in the same order."""
