@@ -190,7 +190,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     // Sorted ticket scheme (see the planner): while the planner works on the CTA's first RoI, the other warps
     // classify every RoI by footprint size -- 32 RoIs per warp step, one ballot mask per class and block.
     const bool sorted = (nblk == 1) && (R <= kSortCap) && !(debug_mode & 64);
-    const int nstatic = sorted ? (int)gridDim.x : 0;                     // grid <= R when nblk == 1
+    const int nstatic = sorted ? min(R, (int)gridDim.x) : 0;             // CTAs past R start on a ticket (small launches)
     const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
     auto size_class = [&](const float *roi) {                            // 0 = largest footprints ... 3 = smallest (NaN -> 3)
         const int lv = roi_level(roi, pyr, finest_scale);
@@ -297,7 +297,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             // the ticket's RoI, channel block and bin rows [ba, bb); window chunks [chunk_lo, chunk_hi) of them
             int r = 0, cbi = 0, ba = 0, bb = P, chunk_lo = 0, chunk_hi = S;
             bool have = false;
-            if (sorted && it == 0) {                                     // small first RoI: start on it right away
+            if (sorted && it == 0 && (int)blockIdx.x < nstatic) {        // small first RoI: start on it right away
                 r = (int)blockIdx.x;
                 have = size_class(rois + 5 * (size_t)r) >= 2;
             }
@@ -753,14 +753,17 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const int nblk = (C + CB - 1) / CB;
     const char *e = getenv("FGN_RA_SPLIT");
     const float split_cells = e != nullptr ? (float)atof(e) : 512.f;
+    const char *ed = getenv("FGN_RA_DEBUG");
+    const int dbg = ed != nullptr ? atoi(ed) : 0;
     const char *eg = getenv("FGN_RA_CTAS");                   // development knob: persistent CTAs per SM (<= MINB)
     const int per_sm = eg != nullptr ? max(1, min(MINB, atoi(eg))) : MINB;
-    const int grid = min(per_sm * sm_count, R * nblk);
+    // launches with fewer RoIs than resident CTAs still fill the machine: the chunks of their big RoIs (up to
+    // ceil(P/2) per RoI in the sorted ticket scheme) are taken by the extra CTAs
+    const bool sorted_scheme = nblk == 1 && R <= kSortCap && !(dbg & 64);
+    const int grid = min(per_sm * sm_count, sorted_scheme ? R * ((P + 1) / 2) : R * nblk);
     // size classes of the sorted ticket scheme (footprint cells): > x: 4 chunks, > y: 2 chunks, > z / rest: whole
     float3 thr = make_float3(1000.f, 500.f, 250.f);
     if (const char *et = getenv("FGN_RA_THR")) sscanf(et, "%f,%f,%f", &thr.x, &thr.y, &thr.z);
-    const char *ed = getenv("FGN_RA_DEBUG");
-    const int dbg = ed != nullptr ? atoi(ed) : 0;
     (void)CB;
     kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                            scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
