@@ -5,10 +5,13 @@
 // reorganised so that the SMs spend their issue slots on the row pass and nothing else:
 //
 //   * PERSISTENT CTAs (2 per SM at P=7) pull work items from a ticket counter.  An item is
-//     (RoI, chunk of bin rows, channel block); almost every RoI is a single item.
+//     (RoI, range of bin rows, channel block).  With one channel block the tickets are handed out
+//     largest-footprint-class first (the warps that idle during the first plan classify all RoIs into
+//     ballot masks; every CTA derives the same order), big RoIs as 2 or 4 items that different CTAs
+//     take, and CTA i starts on RoI i without a ticket when it is small.
 //   * a PLANNER warp works ahead of everyone else: it takes the ticket, assigns the FPN level,
 //     evaluates the reference coordinate arithmetic once per (axis, bin, sample) and leaves the
-//     footprint, ring schedule and weight tables in a double-buffered shared-memory slot.  The
+//     footprint, ring schedule and weight tables in one of three shared-memory plan slots.  The
 //     per-RoI prologue is therefore off the critical path of the copy and the math.
 //   * a PRODUCER warp streams the footprint rows NHWC -> shared-memory ring with bulk async copies
 //     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); the ring keeps running across items.
@@ -21,8 +24,10 @@
 //     one RoI shrink from P to kWin rows of registers, the fold loses its P compare-and-branch
 //     pairs, and the output stores are spread over the item instead of bursting at its end.
 //   * a footprint row can touch more than kWin bin rows only when a bin is shorter than 2/3 of a
-//     cell ((dph - 1 + 1/g) * bin_h < 2); such RoIs (and very large ones, to shorten the tail) are
-//     planned as ceil(P / kWin) items of kWin bin rows each, for which the bound holds trivially.
+//     cell ((dph - 1 + 1/g) * bin_h < 2); such RoIs are planned as ceil(P / kWin) items of kWin
+//     bin rows each, for which the bound holds trivially.
+// What bounds it on B200 (measurements in DESIGN.md section 5): the ring (bytes in flight / copy latency),
+// the planner and the consumers' per-row instruction chains all sit at 40-48 us per 1000 cfg3 RoIs.
 #include "common.cuh"
 #include <stdlib.h>
 
