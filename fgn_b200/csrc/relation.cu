@@ -30,7 +30,9 @@ __device__ __forceinline__ float group_sum_shfl(float v, int cg)
 // Yq [R*PP, C] and Ys [BN*PP, C] are the split-conv outputs (Ys already carries the conv bias).
 // partial [R, N, 6, nblk]: per-channel-block partial dot products of the pooled vector with the
 // 2 cls rows and 4 reg rows.
-template <int PP>
+// FAST: every thread owns a channel (C is a multiple of the block's channel count) and a GroupNorm group lies inside
+// one warp -- the production shapes (C = 256 / 1024, 32 groups); no per-element predication, reductions by shuffle.
+template <int PP, bool FAST>
 __global__ void __launch_bounds__(kEpiThreads, 2)
 relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__ Ys,
                          const int32_t *__restrict__ roi_batch, const int R, const int B, const int N,
@@ -45,8 +47,8 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
     float *fc_part = sm;                          // [N*6*nwarps]
     float *scratch = sm + (size_t)N * 6 * nwarps; // [blockDim.x]
     const int c = blk * cblk + tid;
-    const bool active = tid < cblk && c < C;
-    const bool shfl_ok = (cg & (cg - 1)) == 0 && cg <= 32;
+    const bool active = FAST || (tid < cblk && c < C);
+    const bool shfl_ok = FAST || ((cg & (cg - 1)) == 0 && cg <= 32);
     int b = roi_batch[r];
     b = b < 0 ? 0 : (b >= B ? B - 1 : b);
 
@@ -255,14 +257,21 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
     const int nblk = ceil_div(C, cblk);
     const int nwarps = kEpiThreads / 32;
     const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
-    static int epi_attr = 48 * 1024;
-    if ((int)smem > epi_attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        epi_attr = (int)smem;
-    }
     FGN_CHECK_ARG(nblk <= 65535, "nblk");
-    relation_epilogue_kernel<kMaxPP><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
-        w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
+    // production shapes (every thread owns a channel, a GroupNorm group inside one warp) take the unpredicated kernel
+    const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
+    static int epi_attr[2] = {48 * 1024, 48 * 1024};
+    if ((int)smem > epi_attr[fast]) {
+        if (fast) FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else      FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        epi_attr[fast] = (int)smem;
+    }
+    if (fast)
+        relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
+            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
+    else
+        relation_epilogue_kernel<kMaxPP, false><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
+            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
     FGN_LAUNCH_OK();
     relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(w.partial, R, N, nblk, fc_cls_b, fc_reg_b,
                                                               cls_out, reg_out, raw_cls_out, raw_reg_out);
@@ -362,13 +371,19 @@ extern "C" int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, in
     const int nblk = ceil_div(C, cblk);
     const int nwarps = kEpiThreads / 32;
     const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
-    static int epi_attr = 48 * 1024;
-    if ((int)smem > epi_attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        epi_attr = (int)smem;
+    const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
+    static int epi_attr[2] = {48 * 1024, 48 * 1024};
+    if ((int)smem > epi_attr[fast]) {
+        if (fast) FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else      FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        epi_attr[fast] = (int)smem;
     }
-    relation_epilogue_kernel<kMaxPP><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
-                                                                              fc_cls_w, fc_reg_w, partial);
+    if (fast)
+        relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
+                                                                                        fc_cls_w, fc_reg_w, partial);
+    else
+        relation_epilogue_kernel<kMaxPP, false><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
+                                                                                         fc_cls_w, fc_reg_w, partial);
     FGN_LAUNCH_OK();
     relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(partial, R, N, nblk, fc_cls_b, fc_reg_b, cls_out, reg_out,
                                                               nullptr, nullptr);
