@@ -71,3 +71,22 @@ class FGN(nn.Module):
         proposal_list = self.rpn_head.get_bboxes([rpn_cls_score], [rpn_bbox_pred], img_metas=img_metas, cfg=proposal_cfg)
         return self.roi_head.simple_test(qry_fmap, [p[:, :4] for p in proposal_list], img_metas, rescale=rescale,
                                          spp_fmaps=spp_fmaps, spp_bboxes=spp_bboxes, spp_isegmaps=spp_isegmaps)
+
+    @staticmethod
+    def format_results(outputs_all) -> List[dict]:
+        """fgn.py:262-303, the detector's own part of the per-image result dict consumed by FSISEGEval
+        (fsisegeval.py:51-104): ``dt_scores`` [D], ``dt_bboxes`` [D,4] back in the dataset's YXYX order
+        (fgn.py:275), ``dt_cat_ids`` [D], ``dt_isegmaps_rle`` (COCO RLE dicts, fgn.py:281) as numpy / bytes.
+        ``outputs_all`` = what ``simple_test`` returned: (det_bboxes, det_labels[, mask-branch dict])."""
+        det_bboxes, det_labels = outputs_all[0], outputs_all[1]
+        rles = outputs_all[2].get("segm_rles") if len(outputs_all) > 2 and isinstance(outputs_all[2], dict) else None
+        out = []
+        for i, (db, dl) in enumerate(zip(det_bboxes, det_labels)):
+            db = db.detach().cpu().numpy()
+            one = dict(dt_scores=db[:, -1].reshape(-1), dt_bboxes=db[:, [1, 0, 3, 2]].reshape(-1, 4),
+                       dt_cat_ids=dl.detach().cpu().numpy().reshape(-1))
+            if rles is not None:
+                one["dt_isegmaps_rle"] = rles[i]
+            out.append(one)
+        return out
+

@@ -620,3 +620,69 @@ def rpn_proposals(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch
                                      float(min_bbox_size), prop.data_ptr(), lvl.data_ptr(), cnt.data_ptr(),
                                      ws.data_ptr(), nbytes, _stream()), "fgn_rpn_proposals")
     return prop, lvl, cnt
+
+
+def mask_paste(mask_pred: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int,
+               mask_thr_binary: float = 0.5) -> torch.Tensor:
+    """FCNMaskHead.get_seg_masks' tensor [3P] for one image (fgn_roi_head.py:668-671): sigmoid, paste every
+    [M,M] mask over the whole ``img_h x img_w`` image (F.grid_sample semantics of _do_paste_mask), ``>= thr``.
+    ``mask_pred`` [D,1,M,M] or [D,M,M] logits; ``boxes`` [D,4+] (x1,y1,x2,y2,...).  Returns bool [D,img_h,img_w]."""
+    _need_cuda(mask_pred, boxes)
+    mask_pred = _f32(mask_pred, "mask_pred").contiguous()
+    boxes = _f32(boxes, "boxes").contiguous()
+    d, m = mask_pred.shape[0], mask_pred.shape[-1]
+    if mask_pred.numel() != d * m * m or boxes.dim() != 2 or boxes.shape[0] != d or boxes.shape[1] < 4:
+        raise FgnError(f"mask_pred {tuple(mask_pred.shape)} / boxes {tuple(boxes.shape)}: expected [D,(1,)M,M] and [D,>=4]")
+    out = torch.empty((d, int(img_h), int(img_w)), device=mask_pred.device, dtype=torch.uint8)
+    _lib.check(_lib.load().fgn_mask_paste(_ptr(mask_pred), _ptr(boxes), int(boxes.shape[1]), d, m, int(img_h), int(img_w),
+                                          float(mask_thr_binary), _ptr(out), _stream()), "fgn_mask_paste")
+    return out.view(torch.bool)
+
+
+def mask_paste_rle(mask_pred: torch.Tensor, boxes: torch.Tensor, img_hw: Sequence[Sequence[int]],
+                   det_img: Optional[torch.Tensor] = None, mask_thr_binary: float = 0.5, cap: int = 4096,
+                   return_counts: bool = False):
+    """get_seg_masks + encode_mask_results in one kernel (fgn_roi_head.py:668-671, fgn.py:281): the COCO RLE of
+    every pasted mask without materialising the masks.  ``img_hw``: (h, w) per image; ``det_img`` [D] image index
+    of every detection (None: all image 0).  Returns a list of ``dict(size=[h, w], counts=bytes)`` (the
+    pycocotools form encode_mask_results returns); with ``return_counts`` also the uncompressed run lengths as a
+    list of int lists.  One device->host copy of the encoded bytes; ``cap`` (runs per mask) grows on overflow."""
+    _need_cuda(mask_pred, boxes, det_img)
+    mask_pred = _f32(mask_pred, "mask_pred").contiguous()
+    boxes = _f32(boxes, "boxes").contiguous()
+    d, m = mask_pred.shape[0], mask_pred.shape[-1]
+    if mask_pred.numel() != d * m * m or boxes.dim() != 2 or boxes.shape[0] != d or boxes.shape[1] < 4:
+        raise FgnError(f"mask_pred {tuple(mask_pred.shape)} / boxes {tuple(boxes.shape)}: expected [D,(1,)M,M] and [D,>=4]")
+    hw = [[int(s[0]), int(s[1])] for s in img_hw]
+    if d == 0:
+        return ([], []) if return_counts else []
+    dev = mask_pred.device
+    hw_t = torch.tensor(hw, dtype=torch.int32, pin_memory=True).to(dev, non_blocking=True)
+    if det_img is not None:
+        det_img = det_img.to(torch.int32).contiguous()
+        img_of = det_img.tolist()
+    else:
+        img_of = [0] * d
+    lib = _lib.load()
+    while True:
+        cap_bytes = 2 * cap                           # a run costs 1-2 characters in practice, 7 at most
+        counts = torch.empty((d, cap), device=dev, dtype=torch.int32)
+        ncounts = torch.empty((d,), device=dev, dtype=torch.int32)
+        sbuf = torch.empty((d, cap_bytes), device=dev, dtype=torch.uint8)
+        slen = torch.empty((d,), device=dev, dtype=torch.int32)
+        _lib.check(lib.fgn_mask_paste_rle(_ptr(mask_pred), _ptr(boxes), int(boxes.shape[1]), _ptr(det_img), _ptr(hw_t),
+                                          d, m, float(mask_thr_binary), _ptr(counts), _ptr(ncounts), _ptr(sbuf),
+                                          _ptr(slen), cap, cap_bytes, _stream()), "fgn_mask_paste_rle")
+        nc, sl = ncounts.tolist(), slen.tolist()
+        need = max([-v for v in nc] + [(-v + 1) // 2 for v in sl] + [0])
+        if need == 0:
+            break
+        cap = max(2 * cap, need + 16)
+    smax = max(sl)
+    sbytes = sbuf[:, :max(smax, 1)].cpu().numpy()
+    rles = [dict(size=list(hw[img_of[i]]), counts=sbytes[i, :sl[i]].tobytes()) for i in range(d)]
+    if not return_counts:
+        return rles
+    cmax = max(nc)
+    ch = counts[:, :max(cmax, 1)].cpu().numpy()
+    return rles, [ch[i, :nc[i]].tolist() for i in range(d)]

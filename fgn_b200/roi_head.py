@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Union
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -298,7 +299,60 @@ class FGNRoIHead(nn.Module):
         mask_rois = bbox2roi(boxes)
         if mask_rois.shape[0] == 0:
             return dict(mask_pred=None, mask_feats=mask_rois.new_zeros((0, self.channels, 7, 7)))
-        return self._mask_forward(x, mask_rois)
+        res = self._mask_forward(x, mask_rois)
+        if res["mask_pred"] is not None and img_metas is not None:
+            # get_seg_masks + encode_mask_results (fgn_roi_head.py:668-671, fgn.py:281) for all images in one
+            # launch: per image the list of COCO RLE dicts of its detections (class-agnostic head: class 0)
+            res["segm_rles"] = self.get_seg_rles(res["mask_pred"], mask_rois, [len(bx) for bx in boxes], img_metas, rescale)
+        return res
+
+    def get_seg_rles(self, mask_pred: torch.Tensor, mask_rois: torch.Tensor, num_per_img: Sequence[int], img_metas,
+                     rescale: bool = False) -> List[List[dict]]:
+        """Batched get_seg_masks(..., encode=True): ``mask_rois`` [D,5] at test scale (bbox2roi of ``_bboxes``)."""
+        cfg = self.test_cfg or {}
+        cfg = cfg.get("rcnn", cfg) if isinstance(cfg, dict) else cfg
+        thr = float(cfg.get("mask_thr_binary", 0.5))
+        sfs = [[float(v) for v in m.get("scale_factor", (1.0, 1.0, 1.0, 1.0))] for m in img_metas]
+        hw = []
+        for m, sf in zip(img_metas, sfs):
+            oh, ow = m.get("ori_shape", m.get("img_shape"))[:2]
+            hw.append((int(oh), int(ow)) if rescale else
+                      (int(np.round(oh * sf[1]).astype(np.int32)), int(np.round(ow * sf[0]).astype(np.int32))))
+        det_img = mask_rois[:, 0].to(torch.int32)
+        boxes = mask_rois[:, 1:5]
+        if rescale:
+            boxes = boxes / boxes.new_tensor(sfs)[det_img.long()]
+        rles = ops.mask_paste_rle(mask_pred, boxes.contiguous(), hw, det_img=det_img, mask_thr_binary=thr)
+        out, k = [], 0
+        for n in num_per_img:
+            out.append(rles[k:k + n])
+            k += n
+        return out
+
+    def get_seg_masks(self, mask_pred: torch.Tensor, det_bboxes: torch.Tensor, det_labels: torch.Tensor,
+                      rcnn_test_cfg=None, ori_shape=None, scale_factor=None, rescale: bool = False, encode: bool = False):
+        """FCNMaskHead.get_seg_masks [3P] for the class-agnostic single-class mask head of this model
+        (fgn_r50_c4_densecl.py:123,127; labels forced to 0, fgn_roi_head.py:716), as called from
+        fgn_roi_head.py:668-671.  ``det_bboxes`` are the boxes at test scale (``_bboxes``); with ``rescale`` they are
+        divided by ``scale_factor`` and pasted on ``ori_shape``, else on the scaled shape.  Returns the
+        reference's ``cls_segms`` ([[bool [h,w] numpy] * D] for class 0); with ``encode`` the COCO RLE dicts
+        encode_mask_results would make of them (fgn.py:281), produced without materialising the masks."""
+        cfg = rcnn_test_cfg if rcnn_test_cfg is not None else (self.test_cfg or {})
+        cfg = cfg.get("rcnn", cfg) if isinstance(cfg, dict) else cfg
+        thr = float(cfg.get("mask_thr_binary", 0.5))
+        sf = [float(v) for v in (scale_factor if scale_factor is not None else (1.0, 1.0, 1.0, 1.0))]
+        boxes = det_bboxes[:, :4]
+        if rescale:
+            img_h, img_w = int(ori_shape[0]), int(ori_shape[1])
+            boxes = boxes / boxes.new_tensor(sf)
+        else:
+            img_h = int(np.round(ori_shape[0] * sf[1]).astype(np.int32))
+            img_w = int(np.round(ori_shape[1] * sf[0]).astype(np.int32))
+        boxes = boxes.contiguous()
+        if encode:
+            return [ops.mask_paste_rle(mask_pred, boxes, [(img_h, img_w)], mask_thr_binary=thr)]
+        dense = ops.mask_paste(mask_pred, boxes, img_h, img_w, thr).cpu().numpy()
+        return [[dense[i] for i in range(dense.shape[0])]]
 
     def simple_test(self, qry_fmap, proposal_list, img_metas=None, proposals=None, rescale=False,
                     spp_fmaps=None, spp_bboxes=None, spp_isegmaps=None):

@@ -278,6 +278,31 @@ int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const in
                       float *prop_out, int32_t *level_out, int32_t *count_out,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Test-time mask pasting fused with the result encoding (second part):
+ * FCNMaskHead.get_seg_masks / _do_paste_mask [3P, mmdet 2.18] as called from fgn_roi_head.py:668-671 (sigmoid,
+ * F.grid_sample(bilinear, zeros padding, align_corners=False) of every [M,M] mask over the whole image,
+ * ">= mask_thr_binary", test_cfg.rcnn fgn_r50_c4_densecl.py:186), then mmdet.core.encode_mask_results ->
+ * pycocotools mask.encode [3P] as called from fgn.py:281 (column-major run lengths + their compressed string).
+ * The dense [D,img_h,img_w] masks are never materialised: one CTA per detection walks the pixels its box can
+ * touch and emits the runs directly.
+ *   mask_pred [D,M,M] logits of a class-agnostic mask head (fgn_r50_c4_densecl.py:123,127; labels forced to 0,
+ *   fgn_roi_head.py:716); boxes: D rows of box_stride floats starting with x1,y1,x2,y2 (box_stride 5 takes
+ *   det_bboxes as they are); det_img [D] int32 image of every detection or NULL (all image 0); img_hw [B,2] int32
+ *   (h,w) of the pasted masks (ori_shape when rescale, else the scaled shape).
+ *   counts_out [D,cap] int32 run lengths (first run = zeros, may be 0); ncounts_out [D] runs, or -(runs needed)
+ *   when cap is too small; str_out [D,cap_bytes] the pycocotools "counts" string (NULL: skip), strlen_out [D]
+ *   its length, or -(bytes needed).
+ * Integer contract: identical runs to the reference wherever no pixel value lies within fp32 rounding of the
+ * threshold. */
+int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, int box_stride,
+                       const int32_t *det_img, const int32_t *img_hw, int D, int M, float mask_thr,
+                       int32_t *counts_out, int32_t *ncounts_out, unsigned char *str_out,
+                       int32_t *strlen_out, int cap, int cap_bytes, void *stream);
+
+/* get_seg_masks' own return value for one image: out [D,img_h,img_w] bytes (0/1). */
+int fgn_mask_paste(const float *mask_pred, const float *boxes, int box_stride, int D, int M, int img_h,
+                   int img_w, float mask_thr, unsigned char *out, void *stream);
+
 /* Number of kernels this library has launched in the calling process since load
  * (bench.py's gpu_launches). */
 uint64_t fgn_launch_count(void);

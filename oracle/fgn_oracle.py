@@ -457,3 +457,139 @@ def rpn_get_bboxes_single(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequen
     offsets = ids.to(proposals) * (proposals.max() + torch.tensor(1).to(proposals))
     keep = torchvision.ops.nms(proposals + offsets[:, None], scores, iou_thr)[:max_per_img]
     return torch.cat([proposals[keep], scores[keep, None]], -1), ids[keep]
+
+
+# ------------------------------------------------------------------------------------------------------
+# Mask pasting + RLE (second part): FCNMaskHead.get_seg_masks / _do_paste_mask [3P, mmdet
+# 2.18] as called from fgn_roi_head.py:668-671, then mmdet.core.encode_mask_results -> pycocotools
+# mask.encode [3P] as called from fgn.py:281.  mmdet and pycocotools are absent here ("parity unpinned" for
+# the RLE string); the paste is pinned to torch CPU F.grid_sample (the op _do_paste_mask calls) in
+# tests/test_oracle.py, the RLE to its own decoder and to run-length counts computed independently.
+# ------------------------------------------------------------------------------------------------------
+def paste_grid_coords(n_pix: int, b0: np.ndarray, b1: np.ndarray) -> np.ndarray:
+    """_do_paste_mask: ``(arange(n) + 0.5 - b0) / (b1 - b0) * 2 - 1`` in fp32, inf -> 0.  [D, n_pix]."""
+    p = np.arange(n_pix, dtype=np.float32)[None, :] + np.float32(0.5)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = (p - b0[:, None].astype(np.float32)) / (b1 - b0)[:, None].astype(np.float32) * np.float32(2) - np.float32(1)
+    g = g.astype(np.float32)
+    g[np.isinf(g)] = 0
+    return g
+
+
+def paste_values(mask_logits: np.ndarray, boxes: np.ndarray, img_h: int, img_w: int) -> np.ndarray:
+    """sigmoid + F.grid_sample(bilinear, zeros padding, align_corners=False) of every [M,M] mask over the whole
+    image (skip_empty=False: the reference runs on the GPU), in the op order of torch's CUDA grid sampler:
+    ``ix = ((g + 1) * M - 1) / 2``; weights ``nw = (ix_se - ix)(iy_se - iy)`` ...; ``out = nw_v*nw + ne_v*ne +
+    sw_v*sw + se_v*se`` left to right, no FMA.  Returns [D, img_h, img_w] fp32."""
+    f32 = np.float32
+    m = np.asarray(mask_logits, dtype=f32)
+    d, mm = m.shape[0], m.shape[-1]
+    m = m.reshape(d, mm, mm)
+    sig = (f32(1) / (f32(1) + np.exp(-m, dtype=f32))).astype(f32)
+    boxes = np.asarray(boxes, dtype=f32)
+    gx = paste_grid_coords(img_w, boxes[:, 0], boxes[:, 2])
+    gy = paste_grid_coords(img_h, boxes[:, 1], boxes[:, 3])
+    out = np.zeros((d, img_h, img_w), dtype=f32)
+    for i in range(d):
+        ix = ((gx[i] + f32(1)) * f32(mm) - f32(1)) / f32(2)
+        iy = ((gy[i] + f32(1)) * f32(mm) - f32(1)) / f32(2)
+        with np.errstate(invalid="ignore"):
+            okx = (ix > -1) & (ix < mm)
+            oky = (iy > -1) & (iy < mm)
+        ixc = np.where(okx, ix, f32(0)).astype(f32)
+        iyc = np.where(oky, iy, f32(0)).astype(f32)
+        x0 = np.floor(ixc)
+        y0 = np.floor(iyc)
+        wx1 = (ixc - x0).astype(f32)                 # ix - ix_nw
+        wx0 = ((x0 + f32(1)) - ixc).astype(f32)      # ix_se - ix
+        wy1 = (iyc - y0).astype(f32)
+        wy0 = ((y0 + f32(1)) - iyc).astype(f32)
+        x0i, y0i = x0.astype(np.int64), y0.astype(np.int64)
+        pad = np.zeros((mm + 2, mm + 2), dtype=f32)
+        pad[1:-1, 1:-1] = sig[i]
+        ya, yb = y0i + 1, y0i + 2                    # rows iy_nw, iy_sw in the padded map
+        xa, xb = x0i + 1, x0i + 2
+        nw = pad[np.ix_(ya, xa)] * (wy0[:, None] * wx0[None, :]).astype(f32)
+        ne = pad[np.ix_(ya, xb)] * (wy0[:, None] * wx1[None, :]).astype(f32)
+        sw = pad[np.ix_(yb, xa)] * (wy1[:, None] * wx0[None, :]).astype(f32)
+        se = pad[np.ix_(yb, xb)] * (wy1[:, None] * wx1[None, :]).astype(f32)
+        v = (((nw + ne).astype(f32) + sw).astype(f32) + se).astype(f32)
+        v[~oky, :] = 0
+        v[:, ~okx] = 0
+        out[i] = v
+    return out
+
+
+def get_seg_masks(mask_logits, boxes, img_h: int, img_w: int, mask_thr_binary: float = 0.5) -> np.ndarray:
+    """FCNMaskHead.get_seg_masks [3P] for a class-agnostic single-class mask head (fgn_r50_c4_densecl.py:123,127;
+    labels are forced to 0, fgn_roi_head.py:716): ``paste >= thr`` as bool [D, img_h, img_w]."""
+    return paste_values(mask_logits, boxes, img_h, img_w) >= np.float32(mask_thr_binary)
+
+
+def rle_counts(mask: np.ndarray) -> List[int]:
+    """pycocotools rleEncode [3P]: run lengths of the column-major (Fortran) scan, starting with a run of zeros
+    (possibly empty)."""
+    flat = np.asarray(mask, dtype=np.uint8).reshape(mask.shape[0], mask.shape[1]).T.reshape(-1)   # column-major
+    if flat.size == 0:
+        return []          # (pycocotools emits no run at all for an empty mask)
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    pos = np.concatenate([[0], change, [flat.size]])
+    counts = np.diff(pos).tolist()
+    if flat[0] == 1:
+        counts = [0] + counts
+    return [int(c) for c in counts]
+
+
+def rle_to_string(counts: Sequence[int]) -> bytes:
+    """pycocotools rleToString [3P]: counts beyond the second are stored as the difference to the count two
+    back; each value as 5-bit groups, low first, bit 5 = continuation, sign-extended stop rule, + 48."""
+    s = bytearray()
+    for i, c in enumerate(counts):
+        x = int(c)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            s.append(ch + 48)
+    return bytes(s)
+
+
+def rle_from_string(s: bytes) -> List[int]:
+    """pycocotools rleFrString [3P] (inverse of rle_to_string)."""
+    counts: List[int] = []
+    p = 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return counts
+
+
+def rle_decode(counts: Sequence[int], h: int, w: int) -> np.ndarray:
+    """pycocotools rleDecode [3P]: bool [h, w]."""
+    flat = np.zeros(h * w, dtype=bool)
+    pos, v = 0, False
+    for c in counts:
+        flat[pos:pos + c] = v
+        pos += c
+        v = not v
+    return flat.reshape(w, h).T
+
+
+def encode_mask_results(masks: np.ndarray) -> List[dict]:
+    """mmdet.core.encode_mask_results [3P] for one class list (fgn.py:281): a COCO RLE dict per mask."""
+    return [dict(size=[int(m.shape[0]), int(m.shape[1])], counts=rle_to_string(rle_counts(m))) for m in masks]

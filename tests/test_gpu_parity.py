@@ -891,3 +891,100 @@ def test_fgn_detector_simple_test_chain():
     d2, l2 = head.simple_test_bboxes(qf, metas, [props[:, :4].to(dev())], test_cfg["rcnn"])
     assert torch.equal(labels[0], l2[0])
     close(dets[0], d2[0], what="FGN.simple_test vs stages by hand")
+
+
+# ---- mask pasting + RLE (fgn_mask_paste / fgn_mask_paste_rle) vs the oracle ---------------------------------
+def _paste_case(seed, d, h, w, m=28, sharp=3.0):
+    rng = np.random.default_rng(seed)
+    logits = rng.normal(0, sharp, (d, 1, m, m)).astype(np.float32)
+    cx, cy = rng.uniform(0, w, d), rng.uniform(0, h, d)
+    bw, bh = rng.uniform(2, w * 0.7, d), rng.uniform(2, h * 0.7, d)
+    boxes = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2,  rng.uniform(0, 1, d)], 1).astype(np.float32)
+    return logits, boxes
+
+
+_PASTE_EDGE_BOXES = np.array([[10.3, 5.2, 50.7, 40.1, .9], [0, 0, 83, 61, .9], [-5.5, -3.2, 20.1, 70.3, .9],
+                              [30, 30, 30, 45.5, .9], [70.2, 50.1, 82.9, 60.9, .9], [40.5, 10.5, 12.5, 33.0, .9],
+                              [100, 100, 120, 130, .9], [-40, -40, -10, -5, .9], [0.5, 0.5, 82.5, 60.5, .9]], np.float32)
+
+
+def _assert_masks_match(got, values, thr):
+    """bool masks equal except where the reference value is within fp32 rounding of the threshold"""
+    want = values >= np.float32(thr)
+    differ = got != want
+    if differ.any():
+        assert np.abs(values[differ] - thr).max() < 2e-6, f"{int(differ.sum())} pixels differ away from the threshold"
+        assert differ.sum() <= max(2, got.size // 100000)
+
+
+@pytest.mark.parametrize("case", ["edge", "random", "thr0", "m14"])
+def test_mask_paste_dense_and_rle_match_oracle(case):
+    from fgn_b200 import ops
+    h, w, thr, m = 61, 83, 0.5, 28
+    if case == "edge":
+        boxes = _PASTE_EDGE_BOXES
+        logits = np.random.default_rng(5).normal(0, 3, (len(boxes), 1, m, m)).astype(np.float32)
+    elif case == "random":
+        h, w = 120, 161
+        logits, boxes = _paste_case(11, 40, h, w)
+    elif case == "thr0":                                  # threshold 0: every pixel no mask cell reaches is "on"
+        thr = 0.0
+        logits, boxes = _paste_case(12, 5, h, w)
+    else:
+        m = 14
+        logits, boxes = _paste_case(13, 12, h, w, m=m)
+    values = O.paste_values(logits, boxes[:, :4], h, w)
+    lt, bt = _t(logits).to(dev()), _t(boxes).to(dev())
+    dense = ops.mask_paste(lt, bt, h, w, thr).cpu().numpy()
+    _assert_masks_match(dense, values, thr)
+    rles, counts = ops.mask_paste_rle(lt, bt, [(h, w)], mask_thr_binary=thr, cap=64, return_counts=True)   # cap grows
+    for i in range(len(boxes)):
+        # the fused kernel encodes exactly the mask the dense kernel writes (same device functions) ...
+        assert counts[i] == O.rle_counts(dense[i]), (case, i)
+        assert rles[i]["size"] == [h, w]
+        assert rles[i]["counts"] == O.rle_to_string(counts[i])
+        # ... and decodes back to it
+        assert (O.rle_decode(O.rle_from_string(rles[i]["counts"]), h, w) == dense[i]).all()
+
+
+def test_mask_paste_rle_full_size_round_trip():
+    """cfg3 size (800x1344, 100 detections, two images of different shape in one launch): the RLE decodes to the
+    dense kernel's masks, the runs sum to h*w, empty input returns empty."""
+    from fgn_b200 import ops
+    hw = [(800, 1344), (640, 960)]
+    logits, boxes = _paste_case(21, 100, 640, 960)
+    img = (np.arange(100) % 2).astype(np.int32)
+    lt, bt = _t(logits).to(dev()), _t(boxes).to(dev())
+    rles, counts = ops.mask_paste_rle(lt, bt, hw, det_img=_t(img).to(dev()), return_counts=True)
+    for k in (0, 1):
+        sel = np.flatnonzero(img == k)
+        dense = ops.mask_paste(lt[sel], bt[sel], hw[k][0], hw[k][1]).cpu().numpy()
+        for j, i in enumerate(sel):
+            assert sum(counts[i]) == hw[k][0] * hw[k][1]
+            assert rles[i]["size"] == list(hw[k])
+            assert counts[i] == O.rle_counts(dense[j])
+            assert O.rle_from_string(rles[i]["counts"]) == counts[i]
+    assert ops.mask_paste_rle(lt[:0], bt[:0], hw) == []
+    # sampled oracle check at full size: three detections against the CPU restatement
+    sel = np.array([0, 2, 4])
+    values = O.paste_values(logits[sel], boxes[sel, :4], 800, 1344)
+    _assert_masks_match(ops.mask_paste(lt[sel], bt[sel], 800, 1344).cpu().numpy(), values, 0.5)
+
+
+def test_roi_head_get_seg_masks_and_rles():
+    """FGNRoIHead.get_seg_masks mirrors FCNMaskHead.get_seg_masks' call (fgn_roi_head.py:668-671) incl. rescale."""
+    from fgn_b200 import FGNRoIHead
+    head = FGNRoIHead(bbox_roi_extractor=dict(type="SingleRoIExtractor", roi_layer=dict(type="RoIAlign", output_size=7,
+                      sampling_ratio=0), out_channels=64, featmap_strides=[16]), shared_head=None, channels=64, n_ways=1, k_shots=1,
+                      test_cfg=dict(rcnn=dict(score_thr=0.05, nms=dict(iou_threshold=0.5), max_per_img=100,
+                                              mask_thr_binary=0.4))).to(dev())
+    logits, boxes = _paste_case(31, 9, 90, 70)
+    lt, bt = _t(logits).to(dev()), _t(boxes).to(dev())
+    sf = (1.5, 2.0, 1.5, 2.0)
+    segms = head.get_seg_masks(lt, bt, None, None, ori_shape=(60, 70, 3), scale_factor=sf, rescale=True)
+    rles = head.get_seg_masks(lt, bt, None, None, ori_shape=(60, 70, 3), scale_factor=sf, rescale=True, encode=True)
+    values = O.paste_values(logits, boxes[:, :4] / np.array(sf, np.float32), 60, 70)
+    _assert_masks_match(np.stack(segms[0]), values, 0.4)
+    assert [r["counts"] for r in rles[0]] == [r["counts"] for r in O.encode_mask_results(np.stack(segms[0]))]
+    segms2 = head.get_seg_masks(lt, bt, None, None, ori_shape=(60, 70, 3), scale_factor=sf, rescale=False)
+    assert segms2[0][0].shape == (120, 105)              # round(ori * scale): (60*2.0, 70*1.5)

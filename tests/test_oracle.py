@@ -272,3 +272,54 @@ def test_rpn_restatement_small_case():
     assert dets.shape == (3, 5) and torch.equal(ids, torch.zeros(3, dtype=torch.long))
     assert torch.allclose(dets[:, 4], torch.tensor([2.0, 1.0, 0.5]).sigmoid())
     assert torch.equal(dets[0, :4], torch.tensor([0., 0., 16., 16.]))          # anchor (-16,-16,16,16) clipped
+
+
+# ---- mask pasting + RLE (get_seg_masks / encode_mask_results restatements) ---------------------------------
+_PASTE_BOXES = np.array([[10.3, 5.2, 50.7, 40.1], [0, 0, 83, 61], [-5.5, -3.2, 20.1, 70.3], [30, 30, 30, 45.5],
+                         [70.2, 50.1, 82.9, 60.9], [40.5, 10.5, 12.5, 33.0], [100, 100, 120, 130]], np.float32)
+
+
+def _torch_paste(logits, boxes, h, w):
+    """mmdet _do_paste_mask(skip_empty=False) [3P] written with the very torch calls it makes (CPU)."""
+    import torch.nn.functional as F
+    mt, bt = torch.from_numpy(logits).sigmoid(), torch.from_numpy(boxes)
+    d = mt.shape[0]
+    x0, y0, x1, y1 = torch.split(bt, 1, dim=1)
+    iy = (torch.arange(0, h).float() + 0.5 - y0) / (y1 - y0) * 2 - 1
+    ix = (torch.arange(0, w).float() + 0.5 - x0) / (x1 - x0) * 2 - 1
+    ix[torch.isinf(ix)] = 0
+    iy[torch.isinf(iy)] = 0
+    gx = ix[:, None, :].expand(d, h, w)
+    gy = iy[:, :, None].expand(d, h, w)
+    return F.grid_sample(mt, torch.stack([gx, gy], 3), align_corners=False)[:, 0].numpy()
+
+
+def test_paste_restatement_matches_torch_grid_sample():
+    rng = np.random.default_rng(7)
+    h, w, m = 61, 83, 28
+    logits = rng.normal(0, 3, (len(_PASTE_BOXES), 1, m, m)).astype(np.float32)
+    got = O.paste_values(logits, _PASTE_BOXES, h, w)
+    want = _torch_paste(logits, _PASTE_BOXES, h, w)
+    assert np.nanmax(np.abs(got - want)) < 5e-6
+    differ = (got >= 0.5) != (want >= 0.5)
+    assert differ.sum() == 0 or np.abs(want[differ] - 0.5).max() < 5e-6
+
+
+def test_rle_restatement_round_trip_and_known_runs():
+    # known runs, column-major: a 3x4 mask whose columns are 010 / 111 / 000 / 001
+    mk = np.array([[0, 1, 0, 0], [1, 1, 0, 0], [0, 1, 0, 1]], dtype=bool)
+    assert O.rle_counts(mk) == [1, 1, 1, 3, 5, 1]
+    assert O.rle_counts(np.ones((2, 2), bool)) == [0, 4]
+    assert O.rle_counts(np.zeros((2, 3), bool)) == [6]
+    # string form: small values are one character (value + 48); from the fourth on, the difference to two back
+    assert O.rle_to_string([1, 1, 1, 3, 5, 1]) == bytes([49, 49, 49, 50, 52, 48 + (-2 & 0x1F)])
+    rng = np.random.default_rng(3)
+    for h, w, p in [(1, 1, 0.5), (7, 5, 0.5), (64, 48, 0.02), (33, 200, 0.9), (480, 640, 0.001)]:
+        mk = rng.random((h, w)) < p
+        c = O.rle_counts(mk)
+        assert sum(c) == h * w
+        s = O.rle_to_string(c)
+        assert O.rle_from_string(s) == c
+        assert (O.rle_decode(c, h, w) == mk).all()
+    big = [0, 1066400] + [3, 70000, 5, 2] * 3                   # multi-character values, negative differences
+    assert O.rle_from_string(O.rle_to_string(big)) == big
