@@ -161,36 +161,84 @@ mask_paste_rle_kernel(const float *__restrict__ mask_pred, const float *__restri
     paste_range(b.x0, b.x1, M, W, cx0, cx1);
     paste_range(b.y0, b.y1, M, H, ry0, ry1);
     if (zero_bit) { cx0 = 0; cx1 = W; ry0 = 0; ry1 = H; }
-    auto bit = [&](int x, int y) -> bool {
-        if (x < cx0 || x >= cx1 || y < ry0 || y >= ry1) return zero_bit;
+    // x half of the sample (shared by every pixel of a column) and the pixel test
+    struct ColX { float wx0, wx1; int xa, xb; bool any; };
+    auto column = [&](int x) {
+        ColX c;
+        c.any = false; c.wx0 = c.wx1 = 0.f; c.xa = c.xb = 0;
+        if (x < cx0 || x >= cx1) return c;
         const float ix = paste_unnormalize(paste_coord(x, b.x0, b.x1), M);
+        if (!(ix > -1.f && ix < (float)M)) return c;
+        const float xf = floorf(ix);
+        c.wx1 = __fsub_rn(ix, xf); c.wx0 = __fsub_rn(__fadd_rn(xf, 1.f), ix);
+        c.xa = (int)xf; c.xb = c.xa + 1; c.any = true;
+        return c;
+    };
+    auto bit = [&](const ColX &c, int y) -> bool {                     // same op order as paste_sample
+        if (y < ry0 || y >= ry1) return zero_bit;
+        float v = 0.f;
         const float iy = paste_unnormalize(paste_coord(y, b.y0, b.y1), M);
-        return paste_sample(sm, M, ix, iy) >= thr;
+        if (c.any && iy > -1.f && iy < (float)M) {
+            const float yf = floorf(iy);
+            const float wy1 = __fsub_rn(iy, yf), wy0 = __fsub_rn(__fadd_rn(yf, 1.f), iy);
+            const int ya = (int)yf, yb = ya + 1;
+            const bool xa_ok = c.xa >= 0, xb_ok = c.xb < M, ya_ok = ya >= 0, yb_ok = yb < M;
+            const float nw = (xa_ok && ya_ok) ? sm[ya * M + c.xa] : 0.f;
+            const float ne = (xb_ok && ya_ok) ? sm[ya * M + c.xb] : 0.f;
+            const float sw = (xa_ok && yb_ok) ? sm[yb * M + c.xa] : 0.f;
+            const float se = (xb_ok && yb_ok) ? sm[yb * M + c.xb] : 0.f;
+            v = __fmul_rn(nw, __fmul_rn(wy0, c.wx0));
+            v = __fadd_rn(v, __fmul_rn(ne, __fmul_rn(wy0, c.wx1)));
+            v = __fadd_rn(v, __fmul_rn(sw, __fmul_rn(wy1, c.wx0)));
+            v = __fadd_rn(v, __fmul_rn(se, __fmul_rn(wy1, c.wx1)));
+        }
+        return v >= thr;
     };
 
-    // Positions where a run can start: inside the region, the pixel just below it in every column, and the top
-    // pixel of every column (its predecessor is the bottom pixel of the column to the left).  Column-major.
-    const int xe = min(cx1, W - 1);                    // last examined column
+    // A thread takes 32 consecutive rows of one column (a "word") and marks where a run starts:
+    //   start[k] = bit[k] != bit[k-1].  The rows walked per column are the region's [ry0, ry1) plus the row just
+    // below (it reads zero_bit, so a run that reaches the region's bottom edge ends there); the bit before a
+    // column's first walked row is zero_bit, or -- when the region starts at row 0 -- the bottom pixel of the
+    // column to the left.  When the region reaches the bottom row but not the top one, the top pixel of the next
+    // column (outside the region) can start a run too: the column's first word carries that extra position.
+    const int xe = min(cx1, W - 1);                    // last examined column (cx1 itself: runs ending at its top)
     const int ncx = xe - cx0 + 1;
-    const int ys = max(ry0, 1), ye = min(ry1, H - 1);  // examined rows: 0 and [ys, ye]
-    const int nry = 1 + max(0, ye - ys + 1);
-    const long long E = (long long)ncx * nry;
+    const int re = min(ry1 + 1, H);                    // walked rows [ry0, re)
+    const int nwc = max(1, (re - ry0 + 31) >> 5);      // words per column
+    const bool top_extra = ry0 > 0 && ry1 == H;
+    const long long U = (long long)ncx * nwc;
     int base = 0;
-    for (long long e0 = 0; e0 < E; e0 += kPasteThreads) {
-        const long long e = e0 + tid;
-        bool flag = false;
-        long long t = 0;
-        if (e < E) {
-            const int xi = (int)(e / nry), j = (int)(e - (long long)xi * nry);
-            const int x = cx0 + xi, y = j == 0 ? 0 : ys + j - 1;
-            const bool cur = bit(x, y);
-            const bool prev = y > 0 ? bit(x, y - 1) : (x > 0 ? bit(x - 1, H - 1) : false);
-            flag = cur != prev;
-            t = (long long)x * H + y;
+    for (long long u0 = 0; u0 < U; u0 += kPasteThreads) {
+        const long long u = u0 + tid;
+        unsigned starts = 0u;
+        bool pre = false;
+        int x = 0, yw = 0;
+        if (u < U) {
+            const int xi = (int)(u / nwc), wi = (int)(u - (long long)xi * nwc);
+            x = cx0 + xi; yw = ry0 + 32 * wi;
+            const ColX c = column(x);
+            bool prev;
+            if (wi > 0) prev = bit(c, yw - 1);
+            else {
+                const bool left_bottom = x > 0 ? bit(column(x - 1), H - 1) : false;
+                prev = ry0 > 0 ? zero_bit : left_bottom;
+                pre = top_extra && x > 0 && left_bottom != zero_bit;     // run starting at (x, 0)
+            }
+            unsigned bits = 0u;
+            const int n = min(32, re - yw);
+            for (int k = 0; k < n; ++k) bits |= (bit(c, yw + k) ? 1u : 0u) << k;
+            starts = bits ^ ((bits << 1) | (prev ? 1u : 0u));
+            if (n < 32) starts &= (1u << max(n, 0)) - 1u;
         }
         int total;
-        const int pos = base + block_scan_excl(flag ? 1 : 0, warp_sums, total);
-        if (flag && pos < cap - 1) cnt[pos] = (int32_t)t;      // run starts, for now
+        int pos = base + block_scan_excl((pre ? 1 : 0) + __popc(starts), warp_sums, total);
+        if (pre) { if (pos < cap - 1) cnt[pos] = (int32_t)((long long)x * H); ++pos; }
+        while (starts != 0u) {
+            const int k = __ffs(starts) - 1;
+            starts &= starts - 1u;
+            if (pos < cap - 1) cnt[pos] = (int32_t)((long long)x * H + yw + k);      // run starts, for now
+            ++pos;
+        }
         base += total;
     }
     const int ntr = base, m = ntr + 1;                 // runs = boundaries + 1 (the first run may be empty: t = 0)
