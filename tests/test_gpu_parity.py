@@ -988,3 +988,38 @@ def test_roi_head_get_seg_masks_and_rles():
     assert [r["counts"] for r in rles[0]] == [r["counts"] for r in O.encode_mask_results(np.stack(segms[0]))]
     segms2 = head.get_seg_masks(lt, bt, None, None, ori_shape=(60, 70, 3), scale_factor=sf, rescale=False)
     assert segms2[0][0].shape == (120, 105)              # round(ori * scale): (60*2.0, 70*1.5)
+
+
+def test_fgn_detector_chain_to_result_dict():
+    """FGN.simple_test with a mask head, down to the per-image result dict of fgn.py:262-303: detections, the RLE of
+    every pasted mask (get_seg_masks + encode_mask_results in one kernel) and the YXYX boxes."""
+    import fgn_b200
+    from fgn_b200.episodes import CONFIGS, build_heads
+    cfg = CONFIGS["cfg2_omniiseg_n3k1_c4"]
+    rpn, head = build_heads(cfg, dev(), shared_head=None)
+    torch.manual_seed(5)
+    head.mask_head = torch.nn.ConvTranspose2d(cfg.channels, 1, 4, stride=4).to(dev())      # toy 7x7 -> 28x28 mask head
+    backbone = torch.nn.Sequential(torch.nn.Conv2d(3, cfg.channels, 16, stride=16), torch.nn.ReLU()).to(dev())
+    test_cfg = dict(rpn=dict(nms_pre=6000, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300, min_bbox_size=0),
+                    rcnn=dict(score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=100, mask_thr_binary=0.5))
+    head.test_cfg = test_cfg["rcnn"]
+    det = fgn_b200.FGN(cfg.n_ways, cfg.k_shots, backbone, rpn, head, test_cfg).eval()
+    g = torch.Generator().manual_seed(12)
+    S, H, W = 128, 256, 320
+    qry = torch.randn(1, 3, H, W, generator=g).to(dev())
+    spp = torch.randn(1, cfg.n_ways, cfg.k_shots, 3, S, S, generator=g).to(dev())
+    spp_boxes_yxyx = torch.tensor([12.0, 10.0, 110.0, 100.0]).repeat(1, cfg.n_ways, cfg.k_shots, 1).to(dev())
+    masks = (torch.rand(1, cfg.n_ways, cfg.k_shots, S, S, generator=g) > 0.5).to(dev())
+    out = det.simple_test(qry, spp, spp_boxes_yxyx, masks, img_shape=[(H, W, 3)])
+    dets, labels, res = out
+    d = dets[0].shape[0]
+    assert d > 0 and res["mask_pred"].shape == (d, 1, 28, 28) and len(res["segm_rles"]) == 1 and len(res["segm_rles"][0]) == d
+    values = O.paste_values(res["mask_pred"].cpu().numpy(), dets[0][:, :4].cpu().numpy(), H, W)
+    got = np.stack([O.rle_decode(O.rle_from_string(r["counts"]), H, W) for r in res["segm_rles"][0]])
+    _assert_masks_match(got, values, 0.5)
+    assert all(r["size"] == [H, W] for r in res["segm_rles"][0])
+    fmt = det.format_results(out)
+    assert set(fmt[0]) == {"dt_scores", "dt_bboxes", "dt_cat_ids", "dt_isegmaps_rle"}
+    db = dets[0].cpu().numpy()
+    assert np.array_equal(fmt[0]["dt_bboxes"], db[:, [1, 0, 3, 2]]) and np.array_equal(fmt[0]["dt_scores"], db[:, 4])
+    assert np.array_equal(fmt[0]["dt_cat_ids"], labels[0].cpu().numpy()) and fmt[0]["dt_isegmaps_rle"] is res["segm_rles"][0]
