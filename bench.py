@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying one CUDA graph per episode")
     ap.add_argument("--no-bf16", action="store_true", help="skip the separately reported bf16 variant")
+    ap.add_argument("--no-fold", action="store_true", help="skip the separately reported folded-attention variant")
     ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
     ap.add_argument("--e2e-streams", type=int, default=8, help="streams the end-to-end leg overlaps copies and compute on")
     args = ap.parse_args()
@@ -389,6 +390,26 @@ def main():
                      "stated_tolerance": 3e-2, "dtype": "bf16 maps/operands, f32 accumulate"}
         del runner16, eps16
 
+    # ---- folded-attention variant, reported separately: the AG-RPN channel attention is folded into the RPN conv's
+    #      weights (conv(q*v) = conv(q, W*v): class vectors + B*N*L folded weight sets, 2 + 1 launches) instead of
+    #      writing the attended pyramid (the reference's order, which `value` keeps); everything else identical
+    fold_line = None
+    if not args.no_fold:
+        runner_f = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, with_attention="fold", n_streams=args.streams)
+
+        def step_fold():
+            runner_f.begin()
+            for i in range(E):
+                runner_f.run(i, sink)
+            runner_f.end()
+
+        ms_f, _, _ = timed(step_fold, args.steps, args.warmup)
+        l_f = sum(runner_f.launches_per_episode) * args.steps if runner_f.launches_per_episode else 0
+        fold_line = {"value": E * world * args.steps * cfg.num_rois * cfg.batch / (ms_f * 1e-3), "unit": "RoIs/s",
+                     "ms_per_step": ms_f / args.steps, "gpu_launches": int(l_f),
+                     "what": "AG-RPN attention as rpn_conv weight sets (fgn_fold_attention_weights); attended pyramid not materialised"}
+        del runner_f
+
     if rank == 0:
         line = {"metric": "guided RoIAlign+fusion RoIs/s", "value": value, "unit": "RoIs/s",
                 "episodes_per_s": episodes / (ms * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -396,7 +417,8 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "host_layout": "NCHW fp32 pinned"},
-                "gpu_launches": int(launches), "roofline": roofline, "bf16_variant": bf16_line}
+                "gpu_launches": int(launches), "roofline": roofline, "bf16_variant": bf16_line,
+                "folded_attention_variant": fold_line}
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             n, dt = time_cpu_reference(cfg, 1, 1, 1)

@@ -48,6 +48,7 @@ SIGNATURES = {
     "fgn_det_postprocess": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                     POINTER(c_float), POINTER(c_float), c_float, c_float, c_float, c_int,
                                     _P, _P, _P, _P, c_size_t, _P]),
+    "fgn_fold_attention_weights": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_mask_paste_rle": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P, c_int, c_int, _P]),
     "fgn_mask_paste": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
     "fgn_debug_roi_window_violations": (ctypes.c_uint, []),

@@ -51,6 +51,9 @@ class AGRPNHead(nn.Module):
         self.bbox_coder = dict(target_means=list(coder.get("target_means", [0., 0., 0., 0.])),
                                target_stds=list(coder.get("target_stds", [1., 1., 1., 1.])))
         self.test_cfg = kwargs.get("test_cfg")
+        # True: the channel attention is folded into rpn_conv's weights (qry_fmap_mod is never materialised);
+        # False (default): the reference's own order of operations
+        self.fold_attention = bool(kwargs.get("fold_attention", False))
 
     def get_bboxes(self, cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], img_metas=None,
                    cfg: Optional[dict] = None, rescale: bool = False):
@@ -85,6 +88,25 @@ class AGRPNHead(nn.Module):
         vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
         return vec, ops.channel_attention(qry_fmap, vec)
 
+    def folded_rpn_conv(self, qry_fmap: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+        """relu(rpn_conv(qry_fmap_mod)) without qry_fmap_mod: conv(q * v) = conv(q, W * v) -- one grouped cuDNN conv
+        on the unmodified query map with the B*N weight sets of ops.fold_attention_weights.  [B*N,Cf,H,W]."""
+        b, c, h, w = qry_fmap.shape
+        n = vec.shape[1]
+        wf = ops.fold_attention_weights(self.rpn_conv.weight, vec)                   # [B*N,Cf,C,3,3]
+        cf = wf.shape[1]
+        bias = self.rpn_conv.bias.repeat(b * n) if self.rpn_conv.bias is not None else None
+        x = F.conv2d(qry_fmap.reshape(1, b * c, h, w), wf.view(b * n * cf, c, *wf.shape[-2:]), bias,
+                     padding=self.rpn_conv.padding, groups=b)
+        return F.relu(x.view(b * n, cf, h, w), inplace=True)
+
+    def folded_weights_multilevel(self, spp_feats: Sequence[torch.Tensor]):
+        """FPN mode: the class vectors of every level and rpn_conv's weights folded with them -- everything the
+        attention contributes when the RPN conv consumes the unmodified pyramid.  (vec [L,B*N,C], w' [L,B*N,Cf,C,3,3])."""
+        vec = ops.attention_vectors_multilevel(spp_feats, self.n_ways, self.k_shots)
+        wf = ops.fold_attention_weights(self.rpn_conv.weight, vec)
+        return vec, wf.view(vec.shape[0], vec.shape[1], *wf.shape[1:])
+
     def attention_multilevel(self, qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor]):
         """``attention`` for every pyramid level at once (FPN mode; three launches for channels_last inputs)."""
         return ops.attention_multilevel(qry_feats, spp_feats, self.n_ways, self.k_shots)
@@ -97,8 +119,13 @@ class AGRPNHead(nn.Module):
             raise NotImplementedError("AGRPNHead train_mode (RPN loss over per-class GT lists, "
                                       "fgn_ag_rpn_head.py:58-79) is outside the forward hot path")
         batch = qry_fmap.shape[0]
-        _, qry_fmap_mod = self.attention(qry_fmap, spp_fmaps)
-        rpn_cls_score, rpn_bbox_pred = self._rpn_forward_single(qry_fmap_mod)
+        if self.fold_attention and not log_mode:
+            vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
+            x = self.folded_rpn_conv(qry_fmap, vec)
+            rpn_cls_score, rpn_bbox_pred = self.rpn_cls(x), self.rpn_reg(x)
+        else:
+            _, qry_fmap_mod = self.attention(qry_fmap, spp_fmaps)
+            rpn_cls_score, rpn_bbox_pred = self._rpn_forward_single(qry_fmap_mod)
         if log_mode:
             self.qry_fmap_mod, self.rpn_cls_score, self.rpn_bbox_pred = qry_fmap_mod, rpn_cls_score, rpn_bbox_pred
         if self.n_ways > 1:

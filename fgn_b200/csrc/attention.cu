@@ -1,6 +1,7 @@
 // attention.cu -- AG-RPN channel attention, best-class selection and layout repacks.
 // Reference: AGRPNHead.forward_single (fgn_ag_rpn_head.py:44-46 and :87-108).
 #include "common.cuh"
+#include <algorithm>
 
 namespace fgn {
 
@@ -169,4 +170,37 @@ extern "C" int fgn_nchw_to_nhwc(const float *in, int B, int C, int H, int W, flo
 extern "C" int fgn_nhwc_to_nchw(const float *in, int B, int C, int H, int W, float *out, void *stream)
 {
     return launch_transpose(in, B, H * W, C, out, (cudaStream_t)stream);   // [HW,C] -> [C,HW]
+}
+
+// ---- channel attention folded into the consumer's weights ----------------------------------------------------
+// conv(qry * vec[bn]) == conv'(qry) with w'[bn,o,c,k] = w[o,c,k] * vec[bn,c]: the [B*N,C,H,W] product of
+// fgn_ag_rpn_head.py:44-46 is never written or re-read; the RPN conv (mmdet RPNHead [3P], cuDNN) runs on the
+// unmodified query map with B*N weight sets (one grouped conv).
+namespace fgn {
+namespace {
+__global__ void __launch_bounds__(256)
+fold_attention_weights_kernel(const float *__restrict__ w, const float *__restrict__ vec, const int Co, const int Ci,
+                              const int KK, const size_t total, float *__restrict__ out)
+{
+    const size_t per = (size_t)Co * Ci * KK;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bn = i / per, r = i - bn * per;
+        const int c = (int)((r / KK) % Ci);
+        out[i] = __fmul_rn(w[r], vec[bn * Ci + c]);
+    }
+}
+}  // namespace
+}  // namespace fgn
+
+extern "C" int fgn_fold_attention_weights(const float *weight, const float *vec, int BN, int Co, int Ci, int KK,
+                                          float *out, void *stream)
+{
+    FGN_CHECK_ARG(BN >= 0 && Co >= 1 && Ci >= 1 && KK >= 1, "bad dims BN=%d Co=%d Ci=%d KK=%d", BN, Co, Ci, KK);
+    if (BN == 0) return FGN_OK;
+    FGN_CHECK_ARG(weight && vec && out, "NULL pointer");
+    const size_t total = (size_t)BN * Co * Ci * KK;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+    fgn::fold_attention_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, vec, Co, Ci, KK, total, out);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
 }

@@ -21,7 +21,7 @@ namespace fgn {
 
 namespace {
 
-constexpr int kPasteThreads = 512;
+constexpr int kPasteThreads = 1024;   // one CTA per detection, at most one per SM at cfg3 sizes: the largest box sets the time
 
 struct PasteBox {
     float x0, y0, x1, y1;

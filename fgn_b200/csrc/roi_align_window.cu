@@ -768,6 +768,15 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const int grid = min(per_sm * sm_count, sorted_scheme ? R * ((P + 1) / 2) : R * nblk);
     // size classes of the sorted ticket scheme (footprint cells): > x: 4 chunks, > y: 2 chunks, > z / rest: whole
     float3 thr = make_float3(1000.f, 500.f, 250.f);
+    // A launch with few RoIs per resident CTA (the mask branch: 100 detections on 296 CTAs) is as long as its
+    // largest item -- one CTA streams about 33 GB/s -- so its RoIs are cut finer: the thresholds shrink with
+    // RoIs per 2 CTAs, down to 1/8.
+    if (sorted_scheme) {
+        const char *ea = getenv("FGN_RA_ADAPT");              // development knob: 0 = fixed thresholds
+        const float sc = (ea != nullptr && atoi(ea) == 0) ? 1.f
+                         : fminf(1.f, fmaxf(0.125f, (float)R / (2.f * (float)(per_sm * sm_count))));
+        thr = make_float3(thr.x * sc, thr.y * sc, thr.z * sc);
+    }
     if (const char *et = getenv("FGN_RA_THR")) sscanf(et, "%f,%f,%f", &thr.x, &thr.y, &thr.z);
     (void)CB;
     kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,

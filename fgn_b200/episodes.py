@@ -171,14 +171,16 @@ def build_heads(cfg: EpisodeConfig, device, seed: int = 0, shared_head=None):
     return rpn.to(device).eval(), head.to(device).eval()
 
 
-def run_guided_path(rpn, head, ep: Dict[str, object], with_attention: bool = True, with_mask: bool = True):
+def run_guided_path(rpn, head, ep: Dict[str, object], with_attention=True, with_mask: bool = True):
     """One pass of the hot path over one episode call (device tensors):
        a1 AG-RPN attention on every RPN level, a2 support vectors, a4-a8 guided RoIAlign + relation
        fusion + heads, a9 mask-branch RoIAlign with AG-FCN attention.  Returns the result dict."""
     cfg: EpisodeConfig = ep["cfg"]
     out = {}
     n_ext = len(cfg.strides)
-    if with_attention:
+    if with_attention == "fold":      # attention folded into the RPN conv's weights: nothing of the pyramid's size is written
+        out["spp_fvecs"], out["rpn_conv_weights"] = rpn.folded_weights_multilevel(ep["spp"])
+    elif with_attention:
         _, out["qry_fmap_mod"] = rpn.attention_multilevel(ep["qry"], ep["spp"])
     ext_levels = ep["qry"][:n_ext] if cfg.mode == "fpn" else ep["qry"][0]
     spp_levels = ep["spp"][:n_ext] if cfg.mode == "fpn" else ep["spp"][0]
@@ -202,7 +204,7 @@ class EpisodeRunner:
     """
 
     def __init__(self, rpn, head, episodes: Sequence[Dict[str, object]], use_graphs: bool = True,
-                 with_attention: bool = True, with_mask: bool = True, n_streams: int = 1):
+                 with_attention=True, with_mask: bool = True, n_streams: int = 1):
         from . import ops
         self.rpn, self.head, self.episodes = rpn, head, list(episodes)
         self.kw = dict(with_attention=with_attention, with_mask=with_mask)

@@ -314,6 +314,43 @@ def channel_attention(qry: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def fold_attention_weights(weight: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    """Channel attention folded into the consumer's weights: ``conv(qry * vec[bn]) == conv(qry, w'[bn])`` with
+    ``w'[bn,o,c,ky,kx] = weight[o,c,ky,kx] * vec[bn,c]``.  ``weight`` [Co,Ci,kh,kw]; ``vec`` [...,Ci] or
+    [B,N,Ci,1,1] (any leading shape).  Returns [BN,Co,Ci,kh,kw]."""
+    _need_cuda(weight, vec)
+    w = _f32(weight, "weight").contiguous()
+    co, ci, kh, kw = w.shape
+    v = _f32(vec, "vec").reshape(-1, ci).contiguous()
+    out = torch.empty((v.shape[0], co, ci, kh, kw), device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().fgn_fold_attention_weights(w.data_ptr(), v.data_ptr(), v.shape[0], co, ci, kh * kw,
+                                                      out.data_ptr(), _stream()), "fgn_fold_attention_weights")
+    return out
+
+
+def attention_vectors_multilevel(spp_feats: Sequence[torch.Tensor], n_ways: int, k_shots: int) -> torch.Tensor:
+    """The class vectors of every level in two launches (channels_last fp32 support maps): [L,B*N,C]."""
+    ss = list(spp_feats)
+    _need_cuda(*ss)
+    c = ss[0].shape[1]
+    if not (c % 4 == 0 and c <= 1024 and all(storage_layout(t) == LAYOUT_NHWC and t.dtype == torch.float32 for t in ss)):
+        return torch.stack([attention_vectors(s, n_ways, k_shots).reshape(-1, c) for s in ss])
+    bn = ss[0].shape[0] // k_shots
+    spyr = Pyramid()
+    spyr.num_levels = len(ss)
+    for i, s in enumerate(ss):
+        if s.shape[0] != bn * k_shots or s.shape[1] != c:
+            raise FgnError("attention_vectors_multilevel: level shapes must be [B*N*K,C,h,w]")
+        spyr.feat[i], spyr.H[i], spyr.W[i] = s.data_ptr(), s.shape[2], s.shape[3]
+    lib = _lib.load()
+    vec = torch.empty((len(ss), bn, c), device=ss[0].device, dtype=torch.float32)
+    wsb = lib.fgn_attention_vectors_ml_workspace_bytes(ctypes.byref(spyr), bn, k_shots, c)
+    ws = torch.empty((max(wsb, 1),), device=vec.device, dtype=torch.uint8)
+    _lib.check(lib.fgn_attention_vectors_ml(ctypes.byref(spyr), bn, int(k_shots), c, vec.data_ptr(), ws.data_ptr(), wsb,
+                                            _stream()), "fgn_attention_vectors_ml")
+    return vec
+
+
 def attention_multilevel(qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor], n_ways: int,
                          k_shots: int):
     """AG-RPN attention for every level of a pyramid in three launches (channels_last inputs).

@@ -122,6 +122,14 @@ int fgn_attention_vectors(const float *spp_fmaps, int layout, int BN, int K, int
 int fgn_channel_attention(const float *qry, const float *vec, int B, int N, int C, int H, int W,
                           int layout, float *out, void *stream);
 
+/* The same attention without its [B*N,C,H,W] output: conv(qry * vec[bn]) == conv'(qry) with
+ *   out[bn, o, c, k] = weight[o, c, k] * vec[bn, c]      (weight [Co,Ci,KK] = rpn_conv.weight, KK = kh*kw)
+ * so the RPN conv that consumes qry_fmap_mod (fgn_ag_rpn_head.py:48, mmdet RPNHead [3P]) runs on the unmodified
+ * query map with B*N weight sets; (1+N) * |qry| bytes of traffic per level disappear.  vec may hold the vectors
+ * of several levels back to back (BN = L*B*N). */
+int fgn_fold_attention_weights(const float *weight, const float *vec, int BN, int Co, int Ci, int KK,
+                               float *out, void *stream);
+
 /* The two calls above for a whole pyramid (FPN mode, SURVEY A.9: per level, the vector comes from
  * the same level's support maps) in three launches.  NHWC storage only.
  *   spp: level l = [B*N*K,h_l,w_l,C]; vec [L,B*N,C];  qry: level l = [B,H_l,W_l,C];

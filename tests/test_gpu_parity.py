@@ -1023,3 +1023,51 @@ def test_fgn_detector_chain_to_result_dict():
     db = dets[0].cpu().numpy()
     assert np.array_equal(fmt[0]["dt_bboxes"], db[:, [1, 0, 3, 2]]) and np.array_equal(fmt[0]["dt_scores"], db[:, 4])
     assert np.array_equal(fmt[0]["dt_cat_ids"], labels[0].cpu().numpy()) and fmt[0]["dt_isegmaps_rle"] is res["segm_rles"][0]
+
+
+# ---- AG-RPN attention folded into the RPN conv's weights (fgn_fold_attention_weights) ---------------------------
+def test_fold_attention_weights_is_the_broadcast_product():
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(24, 16, 3, 3, generator=g)
+    v = torch.randn(2, 3, 16, 1, 1, generator=g)
+    got = ops.fold_attention_weights(w.to(dev()), v.to(dev())).cpu()
+    want = w[None] * v.reshape(6, 1, 16, 1, 1)
+    assert got.shape == (6, 24, 16, 3, 3) and torch.equal(got, want)
+    assert ops.fold_attention_weights(w.to(dev()), v[:0].to(dev())).shape == (0, 24, 16, 3, 3)
+
+
+@pytest.mark.parametrize("batch,n_ways,k_shots", [(1, 1, 1), (2, 3, 2), (1, 5, 1)])
+def test_agrpn_forward_single_with_folded_attention(batch, n_ways, k_shots):
+    """conv(q * v) == conv(q, W * v): AGRPNHead.forward_single with fold_attention=True (qry_fmap_mod never
+    materialised, one grouped conv) against the reference's order of operations on the same weights, and against the
+    CPU restatement (fgn_ag_rpn_head.py:33-48 + RPNHead convs)."""
+    from fgn_b200 import AGRPNHead
+    c, h, w, s = 32, 20, 28, 8
+    torch.manual_seed(21)
+    ref = AGRPNHead(in_channels=c, feat_channels=c, n_ways=n_ways, k_shots=k_shots).to(dev()).eval()
+    fold = AGRPNHead(in_channels=c, feat_channels=c, n_ways=n_ways, k_shots=k_shots, fold_attention=True).to(dev()).eval()
+    fold.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(22)
+    q = torch.randn(batch, c, h, w, generator=g)
+    sp = torch.randn(batch * n_ways * k_shots, c, s, s, generator=g).abs()
+    with torch.no_grad():
+        a = ref.forward_single(q.to(dev()), sp.to(dev()))
+        b = fold.forward_single(q.to(dev()), sp.to(dev()))
+        _, qmod = O.agrpn_attention(q, sp, n_ways, k_shots)
+        cpu = ref.to("cpu")
+        x = torch.relu(cpu.rpn_conv(qmod))
+        cls_cpu, reg_cpu = cpu.rpn_cls(x), cpu.rpn_reg(x)
+        sure = torch.ones(batch, cls_cpu.shape[1], h, w, dtype=torch.bool)
+        if n_ways > 1:
+            # anchors whose two best classes score within rounding of each other may pick either class
+            top2 = cls_cpu.view(batch, n_ways, -1, h, w).topk(2, dim=1).values
+            sure = (top2[:, 0] - top2[:, 1]) > 1e-4
+            cls_cpu, reg_cpu = O.best_class_selection(cls_cpu, reg_cpu, batch, n_ways)
+        else:
+            cls_cpu, reg_cpu = cls_cpu.reshape(batch, -1, h, w), reg_cpu.reshape(batch, -1, h, w)
+    assert sure.float().mean() > 0.99
+    sure4 = sure.repeat_interleave(4, dim=1)
+    for got, want, cpuw, m, what in ((b[0], a[0], cls_cpu, sure, "cls"), (b[1], a[1], reg_cpu, sure4, "reg")):
+        close(got.cpu()[m], want.cpu()[m], what=f"folded vs materialised {what}")
+        close(got.cpu()[m], cpuw[m], what=f"folded vs CPU restatement {what}")

@@ -26,9 +26,19 @@ n_ext = len(cfg.strides)
 scales = [1.0 / s for s in cfg.strides]
 
 
+MASK = os.environ.get("TUNE_MASK") == "1"        # the mask-branch launch instead: cfg.mask_rois RoIs with the AG-FCN multiply
+if MASK:
+    for ep in eps:
+        ep["cs"] = torch.rand(ep["det_rois"].shape[0], cfg.channels, device=dev)
+
+
 def run():
     for ep in eps:
-        ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], scales, 7, 0, True, out_format=out_fmt)
+        if MASK:
+            ops.roi_align_multilevel(ep["qry"][:n_ext], ep["det_rois"], scales, cfg.mask_size, 0, True, chan_scale=ep["cs"],
+                                     out_format=out_fmt)
+        else:
+            ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], scales, 7, 0, True, out_format=out_fmt)
 
 
 def timeit(reps=10):
