@@ -6,6 +6,7 @@ import torch
 from fgn_b200.episodes import CONFIGS, EpisodeRunner, build_heads, episode_to_device, make_episode
 
 dev = torch.device("cuda:0")
+FOLD = os.environ.get("BENCH_FOLD") == "1"     # AG-RPN attention folded into the RPN conv's weights instead of materialised
 names = sys.argv[1:] or ["cfg1_mnistiseg_n1k1_c4", "cfg2_omniiseg_n3k1_c4", "cfg3_coco2voc_n1k1_fpn",
                          "cfg4_coco2voc_n20k5_fpn", "cfg5_coco2voc_mask_fpn", "cfg3_c4_exact"]
 for name in names:
@@ -16,7 +17,7 @@ for name in names:
     # C4 mode: the res5 shared_head (cuDNN, adjacent) is left out so the line measures the path's own kernels
     rpn, head = build_heads(cfg, dev, shared_head=None)
     streams = min(E, 8)
-    runner = EpisodeRunner(rpn, head, eps, use_graphs=True, n_streams=streams)
+    runner = EpisodeRunner(rpn, head, eps, use_graphs=True, n_streams=streams, with_attention="fold" if FOLD else True)
 
     def step():
         runner.begin()
@@ -35,7 +36,7 @@ for name in names:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     rois = E * cfg.num_rois * cfg.batch
-    print(json.dumps({"config": name, "mode": cfg.mode, "N": cfg.n_ways, "K": cfg.k_shots, "C": cfg.channels,
+    print(json.dumps({"config": name, "attention": "folded into rpn_conv weights" if FOLD else "materialised", "mode": cfg.mode, "N": cfg.n_ways, "K": cfg.k_shots, "C": cfg.channels,
                       "R_per_call": cfg.num_rois * cfg.batch, "mask_P": cfg.mask_size, "episodes_per_step": E,
                       "streams": streams, "us_per_episode_call": round(ms * 1e3 / E, 1),
                       "RoIs_per_s": round(rois / ms * 1e3), "launches_per_episode": runner.launches_per_episode[0]}), flush=True)
