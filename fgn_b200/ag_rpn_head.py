@@ -53,7 +53,9 @@ class AGRPNHead(nn.Module):
         self.test_cfg = kwargs.get("test_cfg")
         # True: the channel attention is folded into rpn_conv's weights (qry_fmap_mod is never materialised);
         # False (default): the reference's own order of operations
-        self.fold_attention = bool(kwargs.get("fold_attention", False))
+        #   "auto": fold where it moves fewer bytes, (1+N)*H*W > N*kh*kw*feat_channels (large maps: FPN P2-P4)
+        fa = kwargs.get("fold_attention", False)
+        self.fold_attention = "auto" if fa == "auto" else bool(fa)
 
     def get_bboxes(self, cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], img_metas=None,
                    cfg: Optional[dict] = None, rescale: bool = False):
@@ -119,7 +121,11 @@ class AGRPNHead(nn.Module):
             raise NotImplementedError("AGRPNHead train_mode (RPN loss over per-class GT lists, "
                                       "fgn_ag_rpn_head.py:58-79) is outside the forward hot path")
         batch = qry_fmap.shape[0]
-        if self.fold_attention and not log_mode:
+        fold = self.fold_attention
+        if fold == "auto":
+            kk = self.rpn_conv.kernel_size[0] * self.rpn_conv.kernel_size[1]
+            fold = (1 + self.n_ways) * qry_fmap.shape[2] * qry_fmap.shape[3] > self.n_ways * kk * self.feat_channels
+        if fold and not log_mode:
             vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
             x = self.folded_rpn_conv(qry_fmap, vec)
             rpn_cls_score, rpn_bbox_pred = self.rpn_cls(x), self.rpn_reg(x)

@@ -1046,7 +1046,9 @@ def test_agrpn_forward_single_with_folded_attention(batch, n_ways, k_shots):
     c, h, w, s = 32, 20, 28, 8
     torch.manual_seed(21)
     ref = AGRPNHead(in_channels=c, feat_channels=c, n_ways=n_ways, k_shots=k_shots).to(dev()).eval()
-    fold = AGRPNHead(in_channels=c, feat_channels=c, n_ways=n_ways, k_shots=k_shots, fold_attention=True).to(dev()).eval()
+    fold = AGRPNHead(in_channels=c, feat_channels=c, n_ways=n_ways, k_shots=k_shots,
+                     fold_attention="auto" if n_ways == 5 else True).to(dev()).eval()       # 20x28 map, Cf=32: auto folds
+    assert fold.fold_attention in (True, "auto")
     fold.load_state_dict(ref.state_dict())
     g = torch.Generator().manual_seed(22)
     q = torch.randn(batch, c, h, w, generator=g)
