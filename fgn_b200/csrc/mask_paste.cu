@@ -16,12 +16,16 @@
 // _do_paste_mask and of torch's CUDA grid sampler (oracle/fgn_oracle.py::paste_values restates the same chain),
 // so a pixel can differ from the reference only where sigmoid/expf rounding moves a value across the threshold.
 #include "common.cuh"
+#include <algorithm>
 
 namespace fgn {
 
 namespace {
 
-constexpr int kPasteThreads = 1024;   // one CTA per detection, at most one per SM at cfg3 sizes: the largest box sets the time
+constexpr int kPasteThreads = 512;
+constexpr int kPasteIters = 1;                         // scan steps (of kPasteThreads 32-row words) per CTA of the walk kernel:
+                                                       // one step is ~18 K issue cycles of an SM, coarser pieces leave SMs idle
+constexpr int kPasteMaxChunks = 4096;                  // (CTA, step) chunks per detection the encode kernel can order
 
 struct PasteBox {
     float x0, y0, x1, y1;
@@ -39,7 +43,7 @@ __device__ __forceinline__ float paste_coord(int p, float b0, float b1)
 // grid sampler, align_corners=False: ((g + 1) * M - 1) / 2
 __device__ __forceinline__ float paste_unnormalize(float g, int M)
 {
-    return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)M), 1.f), 2.f);
+    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)M), 1.f), 0.5f);   // (/ 2 is exact either way)
 }
 
 // bilinear sample with zero padding of the [M,M] probability map in shared memory
@@ -136,25 +140,23 @@ __device__ __forceinline__ int rle_chars(long long x, unsigned char *dst)
     return n;
 }
 
+// Workspace per call: cursor[D] | chunk_off[D][G] | chunk_cnt[D][G] | starts[D][cap]   (G = segs * kPasteIters)
+// Walk kernel, grid (segs, D): CTA (s, d) walks kPasteIters * kPasteThreads words of detection d's region and appends
+// the run starts of every scan step as one chunk to starts[d] (atomic cursor; the chunk table keeps the order).
 __global__ void __launch_bounds__(kPasteThreads)
-mask_paste_rle_kernel(const float *__restrict__ mask_pred, const float *__restrict__ boxes, const int box_stride,
-                      const int32_t *__restrict__ det_img, const int32_t *__restrict__ img_hw, const int M,
-                      const float thr, int32_t *__restrict__ counts_out, int32_t *__restrict__ ncounts_out,
-                      unsigned char *__restrict__ str_out, int32_t *__restrict__ strlen_out, const int cap,
-                      const int cap_bytes)
+mask_paste_walk_kernel(const float *__restrict__ mask_pred, const float *__restrict__ boxes, const int box_stride,
+                       const int32_t *__restrict__ det_img, const int32_t *__restrict__ img_hw, const int M,
+                       const float thr, int32_t *__restrict__ cursor, int32_t *__restrict__ chunk_off,
+                       int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ starts_ws, const int cap)
 {
     extern __shared__ float sm[];                      // [M*M] probabilities
     __shared__ int warp_sums[kPasteThreads / 32];
-    const int d = blockIdx.x, tid = threadIdx.x;
+    __shared__ int chunk_base;
+    const int d = blockIdx.y, seg = blockIdx.x, G = gridDim.x * kPasteIters, tid = threadIdx.x;
     const PasteBox b = load_box(boxes, box_stride, det_img, img_hw, d);
     const int H = b.H, W = b.W;
-    int32_t *cnt = counts_out + (size_t)d * cap;
-    if (H <= 0 || W <= 0) {                            // empty image: pycocotools emits no run
-        if (tid == 0) { ncounts_out[d] = 0; if (strlen_out != nullptr) strlen_out[d] = 0; }
-        return;
-    }
-    load_probabilities(sm, mask_pred, d, M);
-    __syncthreads();
+    int32_t *cnt = starts_ws + (size_t)d * cap;
+    if (H <= 0 || W <= 0) return;
 
     const bool zero_bit = 0.f >= thr;                  // what a pixel no mask cell reaches compares to
     int cx0, cx1, ry0, ry1;
@@ -207,8 +209,13 @@ mask_paste_rle_kernel(const float *__restrict__ mask_pred, const float *__restri
     const int nwc = max(1, (re - ry0 + 31) >> 5);      // words per column
     const bool top_extra = ry0 > 0 && ry1 == H;
     const long long U = (long long)ncx * nwc;
-    int base = 0;
-    for (long long u0 = 0; u0 < U; u0 += kPasteThreads) {
+    const long long u_begin = (long long)seg * (kPasteIters * kPasteThreads);
+    if (u_begin >= U) return;                          // (before the probabilities are needed: most CTAs of a small box)
+    load_probabilities(sm, mask_pred, d, M);
+    __syncthreads();
+    for (int it = 0; it < kPasteIters; ++it) {
+        const long long u0 = u_begin + (long long)it * kPasteThreads;
+        if (u0 >= U) break;
         const long long u = u0 + tid;
         unsigned starts = 0u;
         bool pre = false;
@@ -231,7 +238,15 @@ mask_paste_rle_kernel(const float *__restrict__ mask_pred, const float *__restri
             if (n < 32) starts &= (1u << max(n, 0)) - 1u;
         }
         int total;
-        int pos = base + block_scan_excl((pre ? 1 : 0) + __popc(starts), warp_sums, total);
+        int pos = block_scan_excl((pre ? 1 : 0) + __popc(starts), warp_sums, total);
+        if (tid == 0) {
+            const int at = total > 0 ? atomicAdd(&cursor[d], total) : 0;
+            chunk_base = at;
+            chunk_off[(size_t)d * G + seg * kPasteIters + it] = at;
+            chunk_cnt[(size_t)d * G + seg * kPasteIters + it] = total;
+        }
+        __syncthreads();
+        pos += chunk_base;
         if (pre) { if (pos < cap - 1) cnt[pos] = (int32_t)((long long)x * H); ++pos; }
         while (starts != 0u) {
             const int k = __ffs(starts) - 1;
@@ -239,12 +254,52 @@ mask_paste_rle_kernel(const float *__restrict__ mask_pred, const float *__restri
             if (pos < cap - 1) cnt[pos] = (int32_t)((long long)x * H + yw + k);      // run starts, for now
             ++pos;
         }
+        __syncthreads();                               // chunk_base is rewritten by the next step
+    }
+}
+
+// Encode kernel, grid D: orders the chunks of a detection, turns run starts into run lengths and writes the string.
+__global__ void __launch_bounds__(kPasteThreads)
+mask_paste_encode_kernel(const int32_t *__restrict__ det_img, const int32_t *__restrict__ img_hw,
+                         const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ chunk_cnt,
+                         const int32_t *__restrict__ starts_ws, const int G, int32_t *__restrict__ counts_out,
+                         int32_t *__restrict__ ncounts_out, unsigned char *__restrict__ str_out,
+                         int32_t *__restrict__ strlen_out, const int cap, const int cap_bytes)
+{
+    __shared__ int warp_sums[kPasteThreads / 32];
+    __shared__ int prefix[kPasteMaxChunks];            // exclusive prefix of the chunk sizes, chunk order
+    const int d = blockIdx.x, tid = threadIdx.x;
+    const int im = det_img != nullptr ? det_img[d] : 0;
+    const int H = img_hw[2 * im], W = img_hw[2 * im + 1];
+    int32_t *cnt = counts_out + (size_t)d * cap;
+    if (H <= 0 || W <= 0) {                            // empty image: pycocotools emits no run
+        if (tid == 0) { ncounts_out[d] = 0; if (strlen_out != nullptr) strlen_out[d] = 0; }
+        return;
+    }
+    int base = 0;
+    for (int g0 = 0; g0 < G; g0 += kPasteThreads) {
+        const int g = g0 + tid;
+        const int n = g < G ? chunk_cnt[(size_t)d * G + g] : 0;
+        int total;
+        const int ex = base + block_scan_excl(n, warp_sums, total);
+        if (g < G) prefix[g] = ex;
         base += total;
     }
     const int ntr = base, m = ntr + 1;                 // runs = boundaries + 1 (the first run may be empty: t = 0)
     if (m > cap) {
         if (tid == 0) { ncounts_out[d] = -m; if (strlen_out != nullptr) strlen_out[d] = 0; }
         return;
+    }
+    __syncthreads();
+    // run starts in image order: entry i lives in the last chunk whose prefix is <= i
+    const int32_t *src = starts_ws + (size_t)d * cap;
+    for (int i = tid; i < ntr; i += kPasteThreads) {
+        int lo = 0, hi = G - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (prefix[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        cnt[i] = src[chunk_off[(size_t)d * G + lo] + (i - prefix[lo])];
     }
     __syncthreads();
     // run starts -> run lengths, in place, from the back (a chunk only reads entries no later chunk has rewritten)
@@ -315,25 +370,50 @@ mask_paste_dense_kernel(const float *__restrict__ mask_pred, const float *__rest
 
 using namespace fgn;
 
+static int paste_segments(int Hmax, int Wmax)
+{
+    const long long words = (long long)Wmax * ((Hmax + 1 + 31) / 32 + 1);
+    const long long per = (long long)kPasteIters * kPasteThreads;
+    return (int)std::max<long long>(1, (words + per - 1) / per);
+}
+
+extern "C" size_t fgn_mask_paste_rle_workspace_bytes(int D, int cap, int Hmax, int Wmax)
+{
+    if (D <= 0 || cap <= 0 || Hmax <= 0 || Wmax <= 0) return 0;
+    const size_t G = (size_t)paste_segments(Hmax, Wmax) * kPasteIters;
+    return ((size_t)D * (1 + 2 * G) + (size_t)D * cap) * sizeof(int32_t);
+}
+
 extern "C" int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, int box_stride,
                                   const int32_t *det_img, const int32_t *img_hw, int D, int M, float mask_thr,
-                                  int32_t *counts_out, int32_t *ncounts_out, unsigned char *str_out,
-                                  int32_t *strlen_out, int cap, int cap_bytes, void *stream)
+                                  int Hmax, int Wmax, int32_t *counts_out, int32_t *ncounts_out,
+                                  unsigned char *str_out, int32_t *strlen_out, int cap, int cap_bytes,
+                                  void *workspace, size_t workspace_bytes, void *stream)
 {
     FGN_CHECK_ARG(D >= 0 && M >= 1 && M <= 112 && box_stride >= 4, "bad dims D=%d M=%d box_stride=%d", D, M, box_stride);
     if (D == 0) return FGN_OK;
     FGN_CHECK_ARG(mask_pred && boxes && img_hw && counts_out && ncounts_out, "NULL pointer");
-    FGN_CHECK_ARG(cap >= 2, "cap=%d", cap);
+    FGN_CHECK_ARG(cap >= 2 && Hmax >= 1 && Wmax >= 1 && D <= 65535, "cap=%d Hmax=%d Wmax=%d D=%d", cap, Hmax, Wmax, D);
     FGN_CHECK_ARG(str_out == nullptr || (strlen_out != nullptr && cap_bytes >= 1), "str_out needs strlen_out and cap_bytes");
+    const int segs = paste_segments(Hmax, Wmax), G = segs * kPasteIters;
+    FGN_CHECK_ARG(G <= kPasteMaxChunks, "image %dx%d needs %d chunks per detection (max %d)", Hmax, Wmax, G, kPasteMaxChunks);
+    const size_t need = fgn_mask_paste_rle_workspace_bytes(D, cap, Hmax, Wmax);
+    FGN_CHECK_ARG(workspace && workspace_bytes >= need, "workspace %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *cursor = static_cast<int32_t *>(workspace);
+    int32_t *chunk_off = cursor + D, *chunk_cnt = chunk_off + (size_t)D * G, *starts = chunk_cnt + (size_t)D * G;
+    FGN_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)D * (1 + 2 * (size_t)G) * sizeof(int32_t), st));
     const size_t smem = (size_t)M * M * sizeof(float);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(mask_paste_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FGN_CUDA_OK(cudaFuncSetAttribute(mask_paste_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    mask_paste_rle_kernel<<<D, kPasteThreads, smem, (cudaStream_t)stream>>>(
-        mask_pred, boxes, box_stride, det_img, img_hw, M, mask_thr, counts_out, ncounts_out, str_out, strlen_out, cap,
-        cap_bytes);
+    mask_paste_walk_kernel<<<dim3(segs, D), kPasteThreads, smem, st>>>(mask_pred, boxes, box_stride, det_img, img_hw, M,
+                                                                      mask_thr, cursor, chunk_off, chunk_cnt, starts, cap);
+    FGN_LAUNCH_OK();
+    mask_paste_encode_kernel<<<D, kPasteThreads, 0, st>>>(det_img, img_hw, chunk_off, chunk_cnt, starts, G, counts_out,
+                                                          ncounts_out, str_out, strlen_out, cap, cap_bytes);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

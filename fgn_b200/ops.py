@@ -701,15 +701,19 @@ def mask_paste_rle(mask_pred: torch.Tensor, boxes: torch.Tensor, img_hw: Sequenc
     else:
         img_of = [0] * d
     lib = _lib.load()
+    hmax, wmax = max(1, max(s[0] for s in hw)), max(1, max(s[1] for s in hw))
     while True:
         cap_bytes = 2 * cap                           # a run costs 1-2 characters in practice, 7 at most
         counts = torch.empty((d, cap), device=dev, dtype=torch.int32)
         ncounts = torch.empty((d,), device=dev, dtype=torch.int32)
         sbuf = torch.empty((d, cap_bytes), device=dev, dtype=torch.uint8)
         slen = torch.empty((d,), device=dev, dtype=torch.int32)
+        wsb = int(lib.fgn_mask_paste_rle_workspace_bytes(d, cap, hmax, wmax))
+        ws = torch.empty((max(wsb, 4),), device=dev, dtype=torch.uint8)
         _lib.check(lib.fgn_mask_paste_rle(_ptr(mask_pred), _ptr(boxes), int(boxes.shape[1]), _ptr(det_img), _ptr(hw_t),
-                                          d, m, float(mask_thr_binary), _ptr(counts), _ptr(ncounts), _ptr(sbuf),
-                                          _ptr(slen), cap, cap_bytes, _stream()), "fgn_mask_paste_rle")
+                                          d, m, float(mask_thr_binary), hmax, wmax, _ptr(counts), _ptr(ncounts),
+                                          _ptr(sbuf), _ptr(slen), cap, cap_bytes, ws.data_ptr(), wsb, _stream()),
+                   "fgn_mask_paste_rle")
         nc, sl = ncounts.tolist(), slen.tolist()
         need = max([-v for v in nc] + [(-v + 1) // 2 for v in sl] + [0])
         if need == 0:

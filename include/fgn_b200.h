@@ -291,8 +291,10 @@ int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const in
  * F.grid_sample(bilinear, zeros padding, align_corners=False) of every [M,M] mask over the whole image,
  * ">= mask_thr_binary", test_cfg.rcnn fgn_r50_c4_densecl.py:186), then mmdet.core.encode_mask_results ->
  * pycocotools mask.encode [3P] as called from fgn.py:281 (column-major run lengths + their compressed string).
- * The dense [D,img_h,img_w] masks are never materialised: one CTA per detection walks the pixels its box can
- * touch and emits the runs directly.
+ * The dense [D,img_h,img_w] masks are never materialised: the pixels a box can touch are walked in column-major
+ * order by as many CTAs as the box needs (32 rows of a column per thread and step) and the runs are emitted directly;
+ * a second kernel orders the pieces, takes differences and writes the string.  Hmax, Wmax: the largest image in
+ * img_hw (sizes the launch and the workspace).
  *   mask_pred [D,M,M] logits of a class-agnostic mask head (fgn_r50_c4_densecl.py:123,127; labels forced to 0,
  *   fgn_roi_head.py:716); boxes: D rows of box_stride floats starting with x1,y1,x2,y2 (box_stride 5 takes
  *   det_bboxes as they are); det_img [D] int32 image of every detection or NULL (all image 0); img_hw [B,2] int32
@@ -302,10 +304,12 @@ int fgn_rpn_proposals(const float *const *cls, const float *const *reg, const in
  *   its length, or -(bytes needed).
  * Integer contract: identical runs to the reference wherever no pixel value lies within fp32 rounding of the
  * threshold. */
+size_t fgn_mask_paste_rle_workspace_bytes(int D, int cap, int Hmax, int Wmax);
 int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, int box_stride,
                        const int32_t *det_img, const int32_t *img_hw, int D, int M, float mask_thr,
-                       int32_t *counts_out, int32_t *ncounts_out, unsigned char *str_out,
-                       int32_t *strlen_out, int cap, int cap_bytes, void *stream);
+                       int Hmax, int Wmax, int32_t *counts_out, int32_t *ncounts_out, unsigned char *str_out,
+                       int32_t *strlen_out, int cap, int cap_bytes,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* get_seg_masks' own return value for one image: out [D,img_h,img_w] bytes (0/1). */
 int fgn_mask_paste(const float *mask_pred, const float *boxes, int box_stride, int D, int M, int img_h,

@@ -29,10 +29,14 @@ lib = _lib.load()
 st = torch.cuda.current_stream().cuda_stream
 
 
+wsb = int(lib.fgn_mask_paste_rle_workspace_bytes(D, cap, H, W))
+ws = torch.empty((wsb,), device=dev, dtype=torch.uint8)
+
+
 def fused():
-    _lib.check(lib.fgn_mask_paste_rle(lt.data_ptr(), bt.data_ptr(), 4, None, hw_t.data_ptr(), D, M, 0.5, counts.data_ptr(),
-                                      ncounts.data_ptr(), sbuf.data_ptr(), slen.data_ptr(), cap, 2 * cap,
-                                      torch.cuda.current_stream().cuda_stream), "fgn_mask_paste_rle")
+    _lib.check(lib.fgn_mask_paste_rle(lt.data_ptr(), bt.data_ptr(), 4, None, hw_t.data_ptr(), D, M, 0.5, H, W,
+                                      counts.data_ptr(), ncounts.data_ptr(), sbuf.data_ptr(), slen.data_ptr(), cap, 2 * cap,
+                                      ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "fgn_mask_paste_rle")
 
 
 def timeit(fn, reps=30):
