@@ -6,11 +6,12 @@
 // pycocotools mask.encode [3P]: run lengths of the column-major scan and their compressed string.
 //
 // The reference materialises a [D, img_h, img_w] bool tensor on the device (107 MB for 100 detections at
-// 800x1333), copies it to the host and encodes it there.  Here one CTA per detection walks only the part of
-// the image its box can touch, in column-major order, finds the run boundaries with ballots and a block scan,
-// turns them into run lengths in place and writes the compressed string: the dense mask never exists and the
-// device->host copy is the RLE itself (a few KB per detection).  fgn_mask_paste writes the dense masks for
-// callers that want get_seg_masks' own return value.
+// 800x1333), copies it to the host and encodes it there.  Here the walk kernel visits only the part of the image a
+// box can touch, in column-major order and in pieces of 512 32-row words (as many CTAs as the box needs), and finds
+// the run boundaries with bit tricks and a block scan; the encode kernel (one CTA per detection) puts the pieces in
+// order, turns run starts into run lengths in place and writes the compressed string.  The dense mask never exists
+// and the device->host copy is the RLE itself (a few KB per detection).  fgn_mask_paste writes the dense masks
+// for callers that want get_seg_masks' own return value.
 //
 // Arithmetic: every operation of the coordinate chain is an explicitly rounded fp32 op in the order of
 // _do_paste_mask and of torch's CUDA grid sampler (oracle/fgn_oracle.py::paste_values restates the same chain),
