@@ -172,14 +172,20 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ WinSlot<P> slot[kPlanSlots];
-    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], plan_full[kPlanSlots], plan_empty[kPlanSlots];
+    __shared__ __align__(8) uint64_t bars[2 * NS + 2 * kPlanSlots];
+    uint64_t *const full_bar = bars, *const empty_bar = bars + NS, *const plan_full = bars + 2 * NS,
+                   *const plan_empty = bars + 2 * NS + kPlanSlots;
     __shared__ unsigned int cls_mask[4][kSortCap / 32];   // size-class membership of every RoI (sorted ticket scheme)
 
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *wtab = ring + (size_t)NS * kStageFloats;
     const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
-    const uint32_t full32 = smem_u32(full_bar), empty32 = smem_u32(empty_bar);
-    const uint32_t pfull32 = smem_u32(plan_full), pempty32 = smem_u32(plan_empty);
+    // one opaque register holds the barriers' shared address: left to itself ptxas re-derives it before every wait
+    // (S2UR SR_CgaCtaId + ULEA, ~40 cycles of latency per ring stage)
+    uint32_t bar32;
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar32) : "r"(smem_u32(bars)));
+    const uint32_t full32 = bar32, empty32 = bar32 + 8 * NS;
+    const uint32_t pfull32 = bar32 + 16 * NS, pempty32 = bar32 + 16 * NS + 8 * kPlanSlots;
 
     const int nblk  = (C + CB - 1) / CB;
     const int items = R * S * nblk;                 // tickets = (RoI, bin-row chunk, channel block); unused chunks are skipped
