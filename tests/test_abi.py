@@ -66,6 +66,12 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         ops.roi_align_multilevel([torch.zeros(1, 4, 8, 8)], torch.zeros(2, 5), [1 / 16])
     with pytest.raises(FgnError):
         ops.channel_attention(torch.zeros(1, 4, 8, 8), torch.zeros(1, 2, 4, 1, 1))
+    with pytest.raises(FgnError):
+        ops.fold_attention_weights(torch.zeros(4, 4, 3, 3), torch.zeros(2, 4))
+    with pytest.raises(FgnError):
+        ops.mask_paste(torch.zeros(2, 1, 28, 28), torch.zeros(2, 4), 32, 32)
+    with pytest.raises(FgnError):
+        ops.mask_paste_rle(torch.zeros(2, 1, 28, 28), torch.zeros(2, 4), [(32, 32)])
 
 
 def test_product_package_never_imports_the_oracle():
