@@ -1073,3 +1073,25 @@ def test_agrpn_forward_single_with_folded_attention(batch, n_ways, k_shots):
     for got, want, cpuw, m, what in ((b[0], a[0], cls_cpu, sure, "cls"), (b[1], a[1], reg_cpu, sure4, "reg")):
         close(got.cpu()[m], want.cpu()[m], what=f"folded vs materialised {what}")
         close(got.cpu()[m], cpuw[m], what=f"folded vs CPU restatement {what}")
+
+
+def test_mask_paste_rle_against_the_golden_fixture():
+    """tests/golden/mask_paste_kat.npz: masks pasted by torch's own grid_sample, run lengths counted with numpy.  The
+    CUDA path reproduces the run lengths wherever no pixel value lies within rounding of the threshold."""
+    from fgn_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "mask_paste_kat.npz"))
+    h, w = [int(v) for v in z["img_hw"]]
+    thr = float(z["thr"])
+    lens, flat = z["counts_len"].tolist(), z["counts_flat"].tolist()
+    lt, bt = _t(z["logits"]).to(dev()), _t(z["boxes"]).to(dev())
+    dense = ops.mask_paste(lt, bt, h, w, thr).cpu().numpy()
+    _assert_masks_match(dense, z["values"], thr)
+    rles, counts = ops.mask_paste_rle(lt, bt, [(h, w)], mask_thr_binary=thr, return_counts=True)
+    k = 0
+    for i, n in enumerate(lens):
+        want = flat[k:k + n]
+        k += n
+        if np.array_equal(dense[i], z["masks"][i]):            # (no near-threshold pixel flipped in this mask)
+            assert counts[i] == want, i
+            assert O.rle_from_string(rles[i]["counts"]) == want
+    assert sum(np.array_equal(dense[i], z["masks"][i]) for i in range(len(lens))) >= len(lens) - 1

@@ -323,3 +323,28 @@ def test_rle_restatement_round_trip_and_known_runs():
         assert (O.rle_decode(c, h, w) == mk).all()
     big = [0, 1066400] + [3, 70000, 5, 2] * 3                   # multi-character values, negative differences
     assert O.rle_from_string(O.rle_to_string(big)) == big
+
+
+def _paste_golden():
+    z = np.load(os.path.join(GOLDEN, "mask_paste_kat.npz"))
+    lens = z["counts_len"].tolist()
+    flat = z["counts_flat"].tolist()
+    counts, k = [], 0
+    for n in lens:
+        counts.append(flat[k:k + n])
+        k += n
+    return z, counts
+
+
+def test_paste_and_rle_restatements_reproduce_the_golden_fixture():
+    """tests/golden/mask_paste_kat.npz (minted with torch's own sigmoid + F.grid_sample, make_golden_paste.py): the
+    restatement's masks and run lengths are the fixture's."""
+    z, counts = _paste_golden()
+    h, w = [int(v) for v in z["img_hw"]]
+    got = O.paste_values(z["logits"], z["boxes"], h, w)
+    assert np.abs(got - z["values"]).max() < 5e-6
+    masks = got >= np.float32(z["thr"])
+    assert np.array_equal(masks, z["masks"])
+    for m, c in zip(masks, counts):
+        assert O.rle_counts(m) == c
+        assert O.rle_from_string(O.rle_to_string(c)) == c
