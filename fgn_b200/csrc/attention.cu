@@ -13,8 +13,8 @@ channel_attention_nchw_kernel(const float *__restrict__ qry, const float *__rest
                               const int B, const int N, const int C, const int HW,
                               float *__restrict__ out)
 {
-    // grid.y = b*C + c (one plane), grid.x strides over the plane
-    const int plane = blockIdx.y;
+    // grid.y strides over the planes b*C + c, grid.x over one plane
+    for (int plane = blockIdx.y; plane < B * C; plane += gridDim.y) {
     const int b = plane / C, c = plane % C;
     const float *q = qry + (size_t)plane * HW;
     const size_t plane_elems = (size_t)HW;
@@ -35,6 +35,25 @@ channel_attention_nchw_kernel(const float *__restrict__ qry, const float *__rest
                 const float s = __ldg(vec + ((size_t)b * N + n) * C + c);
                 __stcs(out + (((size_t)b * N + n) * C + c) * plane_elems + i, v * s);
             }
+        }
+    }
+    }
+}
+
+// Small planes (RoI features, HW = 49 / 196): flat index over [B*C*HW], one element per thread step.
+__global__ void __launch_bounds__(256)
+channel_attention_nchw_small_kernel(const float *__restrict__ qry, const float *__restrict__ vec,
+                                    const int B, const int N, const int C, const int HW,
+                                    float *__restrict__ out)
+{
+    const size_t total = (size_t)B * C * HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t plane = i / HW;
+        const int p = (int)(i - plane * HW), b = (int)(plane / C), c = (int)(plane - (size_t)b * C);
+        const float v = __ldg(qry + i);
+        for (int n = 0; n < N; ++n) {
+            const float s = __ldg(vec + ((size_t)b * N + n) * C + c);
+            __stcs(out + (((size_t)b * N + n) * C + c) * HW + p, v * s);
         }
     }
 }
@@ -122,10 +141,15 @@ extern "C" int fgn_channel_attention(const float *qry, const float *vec, int B, 
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
     if (layout == FGN_LAYOUT_NCHW) {
-        FGN_CHECK_ARG((long)B * C <= 65535, "B*C=%ld exceeds grid.y", (long)B * C);
-        const int per = (HW & 3) == 0 ? HW >> 2 : HW;
-        dim3 grid(max(1, min(ceil_div(per, 256), 64)), B * C);
-        channel_attention_nchw_kernel<<<grid, 256, 0, st>>>(qry, vec, B, N, C, HW, out);
+        if (HW < 1024) {
+            const size_t total = (size_t)B * C * HW;
+            const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
+            channel_attention_nchw_small_kernel<<<blocks, 256, 0, st>>>(qry, vec, B, N, C, HW, out);
+        } else {
+            const int per = (HW & 3) == 0 ? HW >> 2 : HW;
+            dim3 grid(max(1, min(ceil_div(per, 256), 64)), (unsigned)min((long)B * C, 65535L));
+            channel_attention_nchw_kernel<<<grid, 256, 0, st>>>(qry, vec, B, N, C, HW, out);
+        }
     } else if (layout == FGN_LAYOUT_NHWC) {
         if (C & 3) { set_error("channel_attention NHWC needs C%%4==0 (C=%d)", C); return FGN_ERR_UNSUPPORTED; }
         const size_t total = (size_t)B * HW * (C >> 2);

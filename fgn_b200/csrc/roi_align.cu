@@ -389,10 +389,18 @@ int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *ro
 
 int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
                             int aligned, float finest_scale, const float *chan_scale,
-                            const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
-                            int ns_pref, bool *taken);
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
+                            size_t workspace_bytes, cudaStream_t st, int ns_pref, bool *taken);
+size_t roi_align_window_workspace_bytes(const Pyramid &d, int R, int P);
+int launch_roi_align_gather(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                            int aligned, float finest_scale, const float *chan_scale,
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
+                            size_t workspace_bytes, cudaStream_t st, bool *taken);
+size_t roi_align_gather_workspace_bytes(const Pyramid &d, int R, int P);
+unsigned int roi_align_gather_violations();
 unsigned int roi_align_window_violations();
 void roi_align_window_trace(unsigned long long *dst, int n);
+void roi_align_window_trace_reset();
 
 }  // namespace fgn
 
@@ -414,11 +422,18 @@ extern "C" int fgn_map_roi_levels(const float *rois, int R, int num_levels, floa
     return FGN_OK;
 }
 
+extern "C" size_t fgn_roi_align_ml_workspace_bytes(const fgn_pyramid_t *pyr, int R, int P)
+{
+    if (pyr == nullptr || validate_pyramid(pyr) != 0 || R <= 0 || P <= 0) return 0;
+    const Pyramid d = to_device_pyramid(pyr);
+    return max(roi_align_window_workspace_bytes(d, R, P), roi_align_gather_workspace_bytes(d, R, P));
+}
+
 extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int in_layout,
                                     const float *rois, int R, int P, int sampling_ratio,
                                     int aligned, float finest_scale, const float *chan_scale,
                                     const int32_t *scale_index, float *out, int out_layout,
-                                    int32_t *lvl_out, void *stream)
+                                    int32_t *lvl_out, void *workspace, size_t workspace_bytes, void *stream)
 {
     int rc = validate_pyramid(pyr);
     if (rc) return rc;
@@ -432,11 +447,18 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     cudaStream_t st = (cudaStream_t)stream;
     // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
     // 3 / 2 = row-streaming kernel (one CTA per RoI), 1 = bin-centric, 0 = direct
-    const int impl = env_int("FGN_RA_IMPL", 4);
+    const int impl = env_int("FGN_RA_IMPL", 5);
+    if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 5) {
+        bool taken = false;
+        rc = launch_roi_align_gather(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                     scale_index, out, lvl_out, workspace, workspace_bytes, st, &taken);
+        if (rc || taken) return rc;
+    }
     if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4) {
         bool taken = false;
         rc = launch_roi_align_window(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
-                                     scale_index, out, lvl_out, st, env_int("FGN_RA_NS", 0), &taken);
+                                     scale_index, out, lvl_out, workspace, workspace_bytes, st,
+                                     env_int("FGN_RA_NS", 0), &taken);
         if (rc || taken) return rc;
     }
     if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 2) {
@@ -466,13 +488,14 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
 // that fell outside the register window since the library was loaded.  Must be 0.
 extern "C" unsigned int fgn_debug_roi_window_violations(void)
 {
-    return roi_align_window_violations();
+    return roi_align_window_violations() + roi_align_gather_violations();
 }
 
 // Development trace of the rotating-window kernel (FGN_RA_DEBUG bit 5); not declared in the public header.
 extern "C" void fgn_debug_roi_window_trace(unsigned long long *dst, int n)
 {
-    roi_align_window_trace(dst, n);
+    if (dst == nullptr) roi_align_window_trace_reset();
+    else roi_align_window_trace(dst, n);
 }
 
 // Same entry, forcing the direct kernel (exported for the in-library cross-check in tests).

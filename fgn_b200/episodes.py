@@ -187,6 +187,8 @@ def run_guided_path(rpn, head, ep: Dict[str, object], with_attention=True, with_
     head.count_spp(spp_levels, ep["spp_bboxes"].clone(), ep["spp_masks"])     # clone: count_spp divides in place
     res = head._bbox_forward(ext_levels, ep["rois"], need_feats=False)
     out["cls_score"], out["bbox_pred"] = res["cls_score"], res["bbox_pred"]
+    if res.get("bbox_feats") is not None:
+        out["bbox_feats"] = res["bbox_feats"]
     if with_mask:
         head.gather_mask_vectors(ep["det_labels_list"])
         out["mask_feats"] = head._mask_forward(ext_levels, ep["det_rois"])["mask_feats"]

@@ -218,7 +218,7 @@ def test_roi_align_window_kernel_chunked_and_ragged(P, C, B, monkeypatch):
     got, lvl = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, **kw)
     got_s, _ = ops.roi_align_multilevel(fd, rois.to(dev()), scales, P, 0, True, chan_scale=vec.to(dev()),
                                         scale_index=idx.to(dev()), **kw)
-    assert _lib.load().fgn_launch_count() == before + 2      # one kernel per call
+    assert _lib.load().fgn_launch_count() == before + 4      # plan pre-pass + pooling kernel per call
     assert torch.equal(lvl.cpu(), lv)
     close(got, want, what="window vs oracle")
     close(got_s, want_s, what="window + channel attention vs oracle")
@@ -267,6 +267,41 @@ def test_roi_align_window_ticket_schemes():
         assert torch.equal(got, ref) and torch.equal(plain, ref), f"R={R}"
     torch.cuda.synchronize()
     assert _lib.load().fgn_debug_roi_window_violations() == 0
+
+
+def test_roi_align_window_concurrent_launches_on_two_streams():
+    """P=7 and P=14 launches of the window kernel in flight at the same time on two streams (the episode runner's
+    multi-stream mode: bbox + mask branches of different episodes).  Every call owns its ticket counter and plans in
+    its own workspace, so overlapping persistent kernels cannot share tickets; results equal the direct kernel's
+    within tolerance and the serial results bitwise."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(777)
+    strides, B, C = [4, 8, 16, 32], 2, 256
+    feats = [torch.randn(B, C, 320 // s, 448 // s, generator=g) for s in strides]
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    scales = [1 / s for s in strides]
+    r7 = synth_rois(g, 1500, 320, 448, B, smin=8.0).to(dev())
+    r14 = synth_rois(g, 600, 320, 448, B, smin=8.0).to(dev())
+    serial7 = ops.roi_align_multilevel(fd, r7, scales, 7, 0, True, out_format="nhwc")
+    serial14 = ops.roi_align_multilevel(fd, r14, scales, 14, 0, True, out_format="nhwc")
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs7, outs14 = [], []
+    for _ in range(6):
+        with torch.cuda.stream(s1):
+            outs7.append(ops.roi_align_multilevel(fd, r7, scales, 7, 0, True, out_format="nhwc"))
+        with torch.cuda.stream(s2):
+            outs14.append(ops.roi_align_multilevel(fd, r14, scales, 14, 0, True, out_format="nhwc"))
+    torch.cuda.synchronize()
+    for o in outs7:
+        assert torch.equal(o, serial7)
+    for o in outs14:
+        assert torch.equal(o, serial14)
+    d7 = ops.roi_align_multilevel(fd, r7[::10].contiguous(), scales, 7, 0, True, out_format="nhwc", force_direct=True)
+    close(serial7[::10], d7, what="window P=7 vs direct kernel")
+    d14 = ops.roi_align_multilevel(fd, r14[::10].contiguous(), scales, 14, 0, True, out_format="nhwc", force_direct=True)
+    close(serial14[::10], d14, what="window P=14 vs direct kernel")
 
 
 def test_roi_align_edge_cases():

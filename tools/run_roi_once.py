@@ -1,4 +1,5 @@
-"""One warm-up + a few roi_align_multilevel launches on cfg3 (for ncu captures)."""
+"""One warm-up + a few roi_align_multilevel launches on cfg3 (for ncu captures).
+usage: run_roi_once.py [cfg] [fmt] [distinct episodes]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,11 +7,12 @@ from fgn_b200 import ops
 from fgn_b200.episodes import CONFIGS, episode_to_device, make_episode
 cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "cfg3_coco2voc_n1k1_fpn"]
 fmt = sys.argv[2] if len(sys.argv) > 2 else "nhwc"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0")
-eps = [episode_to_device(make_episode(cfg, seed=i), dev) for i in range(2)]
+eps = [episode_to_device(make_episode(cfg, seed=i), dev) for i in range(n)]
 n_ext = len(cfg.strides)
-for i in range(4):
-    ep = eps[i % 2]
+for i in range(6):
+    ep = eps[i % n]
     ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], [1.0 / s for s in cfg.strides], 7, 0, True, out_format=fmt)
 torch.cuda.synchronize()
 print("ok")

@@ -14,11 +14,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg3_coco2voc_n1k1_fpn"
 out_fmt = sys.argv[2] if len(sys.argv) > 2 else "nhwc"
 cfg = CONFIGS[name]
 dev = torch.device("cuda:0")
-E = 8
-base = [episode_to_device(make_episode(cfg, seed=i), dev) for i in range(2)]
+E = int(os.environ.get("TUNE_E", "8"))
+base = [episode_to_device(make_episode(cfg, seed=i), dev) for i in range(min(2, E))]
 eps = []
 for i in range(E):
-    ep = dict(base[i % 2])
+    ep = dict(base[i % len(base)])
     if i >= 2:
         ep["qry"] = [q + 0.01 * i for q in ep["qry"]]
     eps.append(ep)
