@@ -14,7 +14,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfgn_b200.so")
 
 FGN_MAX_LEVELS = 8
-ABI_VERSION = 2
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 
@@ -56,9 +55,8 @@ SIGNATURES = {
     "fgn_mask_paste": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
     "fgn_debug_roi_window_violations": (ctypes.c_uint, []),
     "fgn_map_roi_levels": (c_int, [_P, c_int, c_int, c_float, _P, _P]),
-    "fgn_roi_align_ml_workspace_bytes": (c_size_t, [POINTER(Pyramid), c_int, c_int]),
     "fgn_roi_align_ml_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int,
-                                     c_float, _P, _P, _P, c_int, _P, _P, c_size_t, _P]),
+                                     c_float, _P, _P, _P, c_int, _P, _P]),
     "fgn_roi_align_ml_fwd_direct": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, c_int, c_int, c_int,
                                             c_int, c_float, _P, _P, _P, c_int, _P, _P]),
     "fgn_roi_align_sample_indices": (c_int, [POINTER(Pyramid), _P, c_int, c_int, c_int, c_int, c_float, c_int,
@@ -95,7 +93,7 @@ SIGNATURES = {
     "fgn_channel_attention_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "fgn_attention_vectors_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_support_pool_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
-    "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [POINTER(Pyramid), c_int, c_int, c_int, c_int]),
+    "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_guided_roi_fused_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
                                          _P, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                          _P, _P, _P, c_int, _P, c_size_t, _P]),
@@ -118,8 +116,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.fgn_abi_version() != ABI_VERSION:
-        raise FgnError(f"libfgn_b200 ABI {lib.fgn_abi_version()} != {ABI_VERSION}")
+    if lib.fgn_abi_version() != 1:
+        raise FgnError(f"libfgn_b200 ABI {lib.fgn_abi_version()} != 1")
     _lib = lib
     return lib
 

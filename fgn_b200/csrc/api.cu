@@ -20,21 +20,23 @@ void set_error(const char *fmt, ...)
 // T_k = smallest fp32 v with floorf((float)log2((double)v)) >= k (see roi_level in common.cuh).
 void level_thresholds(float *thr)
 {
-    static float cached[FGN_MAX_LEVELS];
-    static bool ready = false;
-    if (!ready) {
-        cached[0] = 0.f;
-        for (int k = 1; k < FGN_MAX_LEVELS; ++k) {
-            float v = ldexpf(1.0f, k);
-            for (;;) {
-                const float pred = nextafterf(v, 0.0f);
-                if (floorf((float)log2((double)pred)) >= (float)k) v = pred; else break;
+    struct Table {                                    // built once; C++11 guarantees a race-free initialisation
+        float v[FGN_MAX_LEVELS];
+        Table()
+        {
+            v[0] = 0.f;
+            for (int k = 1; k < FGN_MAX_LEVELS; ++k) {
+                float x = ldexpf(1.0f, k);
+                for (;;) {
+                    const float pred = nextafterf(x, 0.0f);
+                    if (floorf((float)log2((double)pred)) >= (float)k) x = pred; else break;
+                }
+                v[k] = x;
             }
-            cached[k] = v;
         }
-        ready = true;
-    }
-    for (int k = 0; k < FGN_MAX_LEVELS; ++k) thr[k] = cached[k];
+    };
+    static const Table table;
+    for (int k = 0; k < FGN_MAX_LEVELS; ++k) thr[k] = table.v[k];
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

@@ -28,6 +28,21 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only and a process may drive several GPUs, so nothing about a
+// device is cached in process-wide statics: launches that need more than the default 48 KB of dynamic shared memory opt
+// in on every call (a host-side write, no synchronisation), and persistent grids are sized from the current device.
+#define FGN_SMEM_OPTIN(kernel, bytes)                                                                   \
+    do { if ((size_t)(bytes) > 48 * 1024)                                                               \
+        FGN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); } while (0)
+
+static inline int current_sm_count(int *out)
+{
+    int dev = 0;
+    FGN_CUDA_OK(cudaGetDevice(&dev));
+    FGN_CUDA_OK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return FGN_OK;
+}
+
 // ---- RoI geometry: the integer/coordinate contract -----------------------------------------
 // Mirrors oracle/roi_align_ref.c (= mmcv RoIAlign / torchvision roi_align CPU).
 // Every coordinate operation is an explicitly rounded fp32 op (__f*_rn are never contracted

@@ -611,11 +611,7 @@ extern "C" int fgn_det_postprocess(const float *rois, const float *cls_score, co
         const size_t diag_bytes = (size_t)Rmax * sizeof(unsigned long long);
         const int smem_rows = (int)min((size_t)Rmax, (200 * 1024 - row_bytes - diag_bytes) / row_bytes);
         const size_t smem = row_bytes * (1 + (size_t)smem_rows) + diag_bytes;
-        static size_t attr = 48 * 1024;
-        if (smem > attr) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
+        FGN_SMEM_OPTIN(det_nms_reduce_kernel, smem);
         det_nms_reduce_kernel<<<dim3(N, B), 256, smem, st>>>(p, ws, L, smem_rows);
         FGN_LAUNCH_OK();
     }
@@ -719,11 +715,7 @@ extern "C" int fgn_rpn_proposals(const float *const *cls, const float *const *re
         FGN_LAUNCH_OK();
         rpn_hist_lo_kernel<<<dim3(hb, L, B), 1024, 0, st>>>(q, hist_hi, hist_lo);
         FGN_LAUNCH_OK();
-        static bool sel_attr = false;
-        if (!sel_attr) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(rpn_select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 8));
-            sel_attr = true;
-        }
+        FGN_SMEM_OPTIN(rpn_select_sort_kernel, kSelCap * 8);
         rpn_select_sort_kernel<<<dim3(L, B), 1024, kSelCap * 8, st>>>(q, hist_hi, hist_lo, keys_out, vals_out);
         FGN_LAUNCH_OK();
     } else {
@@ -746,11 +738,7 @@ extern "C" int fgn_rpn_proposals(const float *const *cls, const float *const *re
         const size_t diag_bytes = (size_t)K * sizeof(unsigned long long);
         const int smem_rows = (int)min((size_t)K, (200 * 1024 - row_bytes - diag_bytes) / row_bytes);
         const size_t smem = row_bytes * (1 + (size_t)smem_rows) + diag_bytes;
-        static size_t attr = 48 * 1024;
-        if (smem > attr) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(det_nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
+        FGN_SMEM_OPTIN(det_nms_reduce_kernel, smem);
         det_nms_reduce_kernel<<<dim3(L, B), 256, smem, st>>>(p, ws, Ld, smem_rows);
         FGN_LAUNCH_OK();
     }

@@ -315,329 +315,6 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
-// ---- paired variant: two 128-row tiles share every B k-block ---------------------------------------
-// The 3xTF32 contraction is bound by operand traffic, not by the tensor pipe: B_hi+B_lo (512 KB at
-// C=256) is re-streamed from L2 for every 128-row tile, 4x the bytes of the A tile it multiplies.
-// Here one CTA owns BOTH accumulators of tensor memory (2 x 256 columns) and multiplies two A tiles by
-// each B stage, halving the B traffic; the price is that the epilogue no longer overlaps the next MMAs.
-// Stage (BK=16): A0 | A0_lo | A1 | A1_lo | B_hi | B_lo = 64 KB, 3 stages.
-struct TcPairSmem {
-    static constexpr int kBK = 16, kStages = 3;
-    static constexpr int kA = TC_BM * kBK * 4;              // 8 KB
-    static constexpr int kB = TC_BN_MAX * kBK * 4;          // 16 KB
-    static constexpr int kStage = 4 * kA + 2 * kB;          // 64 KB
-    static constexpr int kTotal = kStages * kStage + 1024 + 256 + 4 * 32 * 36 * 4;
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                         const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
-                         float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN)
-{
-    using Sm = TcPairSmem;
-    constexpr int BK = Sm::kBK, ST = Sm::kStages;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ST * Sm::kStage);
-    uint64_t *full_bar = bars, *conv_bar = bars + ST, *empty_bar = bars + 2 * ST;
-    uint64_t *tmem_full = bars + 3 * ST, *tmem_empty = tmem_full + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_pairs = (M + 2 * TC_BM - 1) / (2 * TC_BM), n_tiles = (N + BN - 1) / BN;
-    const int num_pairs = m_pairs * n_tiles, num_kb = K / BK;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&conv_bar[s], 4); tc_mbar_init(&empty_bar[s], 1); }
-        tc_mbar_init(tmem_full, 1);
-        tc_mbar_init(tmem_empty, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-                const int m0 = (pair / n_tiles) * 2 * TC_BM, n0 = (pair % n_tiles) * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % ST;
-                    tc_mbar_wait(&empty_bar[s], ((it / ST) & 1) ^ 1);
-                    unsigned char *st = smem + (size_t)s * Sm::kStage;
-                    tc_mbar_expect_tx(&full_bar[s], (uint32_t)(2 * TC_BM * BK * 4 + 2 * BN * BK * 4));
-                    tma_load_2d(st, &map_a, kb * BK, m0, &full_bar[s]);
-                    tma_load_2d(st + 2 * Sm::kA, &map_a, kb * BK, m0 + TC_BM, &full_bar[s]);   // rows past M zero-fill
-                    tma_load_2d(st + 4 * Sm::kA, &map_bhi, kb * BK, n0, &full_bar[s]);
-                    tma_load_2d(st + 4 * Sm::kA + Sm::kB, &map_blo, kb * BK, n0, &full_bar[s]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        int it = 0, local = 0;
-        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++local) {
-            tc_mbar_wait(tmem_empty, (local & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % ST;
-                const uint32_t par = (it / ST) & 1;
-                tc_mbar_wait(&full_bar[s], par);
-                tc_mbar_wait(&conv_bar[s], par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t st = s_u32(smem + (size_t)s * Sm::kStage);
-                    const uint64_t b_hi = umma_desc_kmajor<BK>(st + 4 * Sm::kA), b_lo = umma_desc_kmajor<BK>(st + 4 * Sm::kA + Sm::kB);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const uint64_t a_hi = umma_desc_kmajor<BK>(st + 2 * t * Sm::kA), a_lo = umma_desc_kmajor<BK>(st + (2 * t + 1) * Sm::kA);
-                        const uint32_t tmem_d = tmem_base + (uint32_t)(t * TC_BN_MAX);
-#pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
-                            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
-                            umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-                            umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
-                        }
-                    }
-                    umma_commit(&empty_bar[s]);
-                    if (kb == num_kb - 1) umma_commit(tmem_full);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 8) {
-        const int tid = threadIdx.x - 256;
-        int it = 0;
-        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % ST;
-                tc_mbar_wait(&full_bar[s], (it / ST) & 1);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage + 2 * t * Sm::kA);
-                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage + (2 * t + 1) * Sm::kA);
-#pragma unroll
-                    for (int j = 0; j < Sm::kA / 16 / 128; ++j) {
-                        const int i = j * 128 + tid;
-                        const float4 x = hi[i];
-                        float4 h;
-                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-                        hi[i] = h;
-                        lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&conv_bar[s]);
-            }
-        }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;
-        float *epi_tile = reinterpret_cast<float *>(smem + ST * Sm::kStage + 256) + ew * 32 * kEpiPitch;
-        int local = 0;
-        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++local) {
-            const int m0 = (pair / n_tiles) * 2 * TC_BM, n0 = (pair % n_tiles) * BN;
-            tc_mbar_wait(tmem_full, local & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int row = m0 + t * TC_BM + ew * 32 + lane;
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * TC_BN_MAX);
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + (uint32_t)c0, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    store_chunk(r, epi_tile, lane, m0 + t * TC_BM + ew * 32, M, n0 + c0, N, bias, C, ldc);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tc_mbar_arrive(tmem_empty);
-        }
-    }
-
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-    }
-}
-
-// ---- cluster variant: a CTA pair shares every B stage through TMA multicast ------------------------
-// At M=128 rows per tile the 3xTF32 contraction needs 640 KB of operands per 12.3k tensor-pipe cycles
-// -- more than the L2 can feed all 148 SMs (measured: tensor pipe 49% busy, the rest waiting on
-// operands).  Two CTAs of a cluster work on neighbouring row tiles of the same column tile; each
-// loads its own A tile and HALF of the B stage, multicast into both CTAs' shared memory
-// (cp.async.bulk.tensor ... .multicast::cluster), so B costs one L2 read per pair.  A stage is free
-// when BOTH CTAs' MMAs retired it: tcgen05.commit ... .multicast::cluster arrives on both empty barriers.
-template <int BK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-gemm_tf32_tc_mc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                       const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
-                       float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN)
-{
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    using Sm = TcSmem<BK>;
-    constexpr int ST = Sm::kStages;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ST * Sm::kStage);
-    uint64_t *full_bar = bars, *conv_bar = bars + ST, *empty_bar = bars + 2 * ST;
-    uint64_t *tmem_full = bars + 3 * ST, *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = (N + BN - 1) / BN;
-    const int m_pairs = (m_tiles + 1) / 2;
-    const int num_pairs = m_pairs * n_tiles, num_kb = K / BK;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int half_rows = BN / 2;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) {
-            tc_mbar_init(&full_bar[s], 1);
-            tc_mbar_init(&conv_bar[s], 4);
-            tc_mbar_init(&empty_bar[s], 2);                // both CTAs of the pair retire the stage
-        }
-        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");     // peer's barriers are initialised
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
-                const int m0 = (2 * (pair / n_tiles) + (int)rank) * TC_BM, n0 = (pair % n_tiles) * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % ST;
-                    tc_mbar_wait(&empty_bar[s], ((it / ST) & 1) ^ 1);
-                    unsigned char *st = smem + (size_t)s * Sm::kStage;
-                    tc_mbar_expect_tx(&full_bar[s], (uint32_t)(TC_BM * BK * 4 + 2 * BN * BK * 4));
-                    tma_load_2d(st, &map_a, kb * BK, m0, &full_bar[s]);
-                    const size_t hoff = (size_t)rank * half_rows * BK * 4;     // my half of the B rows, in both CTAs
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-                                 " [%0], [%1, {%3, %4}], [%2], %5;"
-                                 ::"r"(s_u32(st + 2 * Sm::kA + hoff)), "l"(&map_bhi), "r"(s_u32(&full_bar[s])),
-                                   "r"(kb * BK), "r"(n0 + (int)rank * half_rows), "h"((unsigned short)3) : "memory");
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-                                 " [%0], [%1, {%3, %4}], [%2], %5;"
-                                 ::"r"(s_u32(st + 2 * Sm::kA + Sm::kB + hoff)), "l"(&map_blo), "r"(s_u32(&full_bar[s])),
-                                   "r"(kb * BK), "r"(n0 + (int)rank * half_rows), "h"((unsigned short)3) : "memory");
-                }
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        int it = 0, local_tile = 0;
-        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++local_tile) {
-            const int a = local_tile & 1;
-            tc_mbar_wait(&tmem_empty[a], ((local_tile >> 1) & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(a * TC_BN_MAX);
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % ST;
-                const uint32_t par = (it / ST) & 1;
-                tc_mbar_wait(&full_bar[s], par);
-                tc_mbar_wait(&conv_bar[s], par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t st = s_u32(smem + (size_t)s * Sm::kStage);
-                    const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + Sm::kA);
-                    const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * Sm::kA), b_lo = umma_desc_kmajor<BK>(st + 2 * Sm::kA + Sm::kB);
-#pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
-                        umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-                        umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                 ::"r"(s_u32(&empty_bar[s])), "h"((unsigned short)3) : "memory");
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[a]);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 8) {
-        const int tid = threadIdx.x - 256;
-        int it = 0;
-        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % ST;
-                tc_mbar_wait(&full_bar[s], (it / ST) & 1);
-                float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage);
-                float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * Sm::kStage + Sm::kA);
-#pragma unroll
-                for (int j = 0; j < Sm::kA / 16 / 128; ++j) {
-                    const int i = j * 128 + tid;
-                    const float4 x = hi[i];
-                    float4 h;
-                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-                    hi[i] = h;
-                    lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&conv_bar[s]);
-            }
-        }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;
-        float *epi_tile = reinterpret_cast<float *>(smem + ST * Sm::kStage + 256) + ew * 32 * kEpiPitch;
-        int local_tile = 0;
-        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++local_tile) {
-            const int a = local_tile & 1;
-            const int m0 = (2 * (pair / n_tiles) + (int)rank) * TC_BM, n0 = (pair % n_tiles) * BN;
-            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + ew * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)c0, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                store_chunk(r, epi_tile, lane, m0 + ew * 32, M, n0 + c0, N, bias, C, ldc);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tc_mbar_arrive(&tmem_empty[a]);
-        }
-    }
-
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    // neither CTA may leave while the peer can still multicast into it or arrive on its barriers
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (warp == 2) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-    }
-}
-
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -645,16 +322,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 static EncodeTiledFn get_encode()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // (a driver entry point is per process, not per device; C++11 makes the one-time initialisation race-free)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
+            return (EncodeTiledFn)p;
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -698,64 +374,13 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
         set_error("cuTensorMapEncodeTiled unavailable or failed");
         return FGN_ERR_CUDA;
     }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        FGN_CUDA_OK(cudaGetDevice(&dev));
-        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int sm_count = 0;
+    if (int rc_sm = current_sm_count(&sm_count)) return rc_sm;
     const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
     const int grid = min(sm_count, m_tiles * n_tiles);
-    // two tiles per B stage: measured SLOWER on B200 (62 vs 50 us at M=49000, N=K=256: pair quantisation
-    // and the exposed epilogue outweigh the halved B traffic), so it is opt-in: FGN_GEMM_PAIR=1
-    const char *ep = getenv("FGN_GEMM_PAIR");
-    const bool want_pair = ep != nullptr && atoi(ep) != 0;
-    if (passes == 3 && want_pair && m_tiles >= 2 * sm_count) {
-        static bool pair_attr = false;
-        if (!pair_attr) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPairSmem::kTotal));
-            pair_attr = true;
-        }
-        CUtensorMap pa, pbh, pbl;
-        if (!make_map(&pa, A, M, K, lda, TC_BM, 16) || !make_map(&pbh, bhi, N, K, K, BN, 16) || !make_map(&pbl, blo, N, K, K, BN, 16)) {
-            set_error("cuTensorMapEncodeTiled unavailable or failed");
-            return FGN_ERR_CUDA;
-        }
-        const int pairs = ceil_div(m_tiles, 2) * n_tiles;
-        gemm_tf32_tc_pair_kernel<<<min(sm_count, pairs), TC_THREADS, TcPairSmem::kTotal, st>>>(pa, pbh, pbl, bias, C, ldc, M, N, K, BN);
-        FGN_LAUNCH_OK();
-        *taken = true;
-        return FGN_OK;
-    }
-    // CTA-pair multicast of the B stages: FGN_GEMM_MC=1
-    const char *emc = getenv("FGN_GEMM_MC");
-    const bool want_mc = emc != nullptr && atoi(emc) != 0;   // measured equal to the plain kernel (44 us): opt-in
-    if (passes == 3 && want_mc && m_tiles >= 2 && (BN % 16) == 0 && sm_count >= 2) {
-        static bool mc_attr = false;
-        if (!mc_attr) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_mc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16>::kTotal));
-            mc_attr = true;
-        }
-        CUtensorMap pa, pbh, pbl;
-        if (!make_map(&pa, A, M, K, lda, TC_BM, 16) || !make_map(&pbh, bhi, N, K, K, BN / 2, 16) || !make_map(&pbl, blo, N, K, K, BN / 2, 16)) {
-            set_error("cuTensorMapEncodeTiled unavailable or failed");
-            return FGN_ERR_CUDA;
-        }
-        const int pairs = ceil_div(m_tiles, 2) * n_tiles;
-        const int clusters = min(sm_count / 2, pairs);
-        gemm_tf32_tc_mc_kernel<16><<<2 * clusters, TC_THREADS, TcSmem<16>::kTotal, st>>>(pa, pbh, pbl, bias, C, ldc, M, N, K, BN);
-        FGN_LAUNCH_OK();
-        *taken = true;
-        return FGN_OK;
-    }
-    static bool attr_done[4] = {false, false, false, false};
 #define FGN_TC_LAUNCH(PS, BKV, IDX)                                                                                  \
     do {                                                                                                           \
-        if (!attr_done[IDX]) {                                                                                     \
-            FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<PS, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             TcSmem<BKV>::kTotal));                                                \
-            attr_done[IDX] = true;                                                                                 \
-        }                                                                                                          \
+        FGN_SMEM_OPTIN((gemm_tf32_tc_kernel<PS, BKV>), TcSmem<BKV>::kTotal);                                        \
         gemm_tf32_tc_kernel<PS, BKV><<<grid, TC_THREADS, TcSmem<BKV>::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN); \
     } while (0)
     if (passes == 3 && bk == 32) FGN_TC_LAUNCH(3, 32, 0);
@@ -786,19 +411,11 @@ int gemm_nt_tc_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, cons
         set_error("cuTensorMapEncodeTiled unavailable or failed");
         return FGN_ERR_CUDA;
     }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        FGN_CUDA_OK(cudaGetDevice(&dev));
-        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int sm_count = 0;
+    if (int rc_sm = current_sm_count(&sm_count)) return rc_sm;
     const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
     const int grid = min(sm_count, m_tiles * n_tiles);
-    static bool attr = false;
-    if (!attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tc_kernel<1, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::kTotal));
-        attr = true;
-    }
+    FGN_SMEM_OPTIN((gemm_tf32_tc_kernel<1, 32, true>), TcSmem<32>::kTotal);
     gemm_tf32_tc_kernel<1, 32, true><<<grid, TC_THREADS, TcSmem<32>::kTotal, st>>>(ma, mb, mb, bias, C, ldc, M, N, K, BN);
     FGN_LAUNCH_OK();
     return FGN_OK;

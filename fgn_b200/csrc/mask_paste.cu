@@ -405,11 +405,7 @@ extern "C" int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, in
     int32_t *chunk_off = cursor + D, *chunk_cnt = chunk_off + (size_t)D * G, *starts = chunk_cnt + (size_t)D * G;
     FGN_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)D * (1 + 2 * (size_t)G) * sizeof(int32_t), st));
     const size_t smem = (size_t)M * M * sizeof(float);
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(mask_paste_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    FGN_SMEM_OPTIN(mask_paste_walk_kernel, smem);
     mask_paste_walk_kernel<<<dim3(segs, D), kPasteThreads, smem, st>>>(mask_pred, boxes, box_stride, det_img, img_hw, M,
                                                                       mask_thr, cursor, chunk_off, chunk_cnt, starts, cap);
     FGN_LAUNCH_OK();
@@ -428,11 +424,7 @@ extern "C" int fgn_mask_paste(const float *mask_pred, const float *boxes, int bo
     FGN_CHECK_ARG(mask_pred && boxes && out, "NULL pointer");
     FGN_CHECK_ARG(D <= 65535, "D=%d > 65535", D);
     const size_t smem = (size_t)M * M * sizeof(float);
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(mask_paste_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    FGN_SMEM_OPTIN(mask_paste_dense_kernel, smem);
     const size_t HW = (size_t)img_h * img_w;
     const int gx = (int)min((HW + 255) / 256, (size_t)2048);
     mask_paste_dense_kernel<<<dim3(gx, D), 256, smem, (cudaStream_t)stream>>>(mask_pred, boxes, box_stride, M, img_h, img_w,

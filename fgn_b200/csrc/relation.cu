@@ -260,12 +260,8 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
     FGN_CHECK_ARG(nblk <= 65535, "nblk");
     // production shapes (every thread owns a channel, a GroupNorm group inside one warp) take the unpredicated kernel
     const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
-    static int epi_attr[2] = {48 * 1024, 48 * 1024};
-    if ((int)smem > epi_attr[fast]) {
-        if (fast) FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else      FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        epi_attr[fast] = (int)smem;
-    }
+    if (fast) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true>), smem);
+    else      FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, false>), smem);
     if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
             w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
@@ -372,12 +368,8 @@ extern "C" int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, in
     const int nwarps = kEpiThreads / 32;
     const size_t smem = ((size_t)N * 6 * nwarps + kEpiThreads) * 4;
     const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
-    static int epi_attr[2] = {48 * 1024, 48 * 1024};
-    if ((int)smem > epi_attr[fast]) {
-        if (fast) FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else      FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_kernel<kMaxPP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        epi_attr[fast] = (int)smem;
-    }
+    if (fast) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true>), smem);
+    else      FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, false>), smem);
     if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
                                                                                         fc_cls_w, fc_reg_w, partial);
@@ -391,15 +383,10 @@ extern "C" int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, in
     return FGN_OK;
 }
 
-extern "C" size_t fgn_roi_align_ml_workspace_bytes(const fgn_pyramid_t *, int, int);
-extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *, int, int, int, const float *, int, int, int, int, float,
-                                    const float *, const int32_t *, float *, int, int32_t *, void *, size_t, void *);
-
-extern "C" size_t fgn_guided_roi_fused_workspace_bytes(const fgn_pyramid_t *pyr, int R, int BN, int C, int P)
+extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P)
 {
     if (R < 0 || BN <= 0 || C <= 0 || P <= 0) return 0;
     return align256((size_t)R * P * P * C * 4) + align256((size_t)R * 4) +
-           align256(fgn_roi_align_ml_workspace_bytes(pyr, R, P)) +
            fgn_relation_fusion_workspace_bytes(R, BN, C, P);
 }
 
@@ -417,7 +404,7 @@ extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, 
 {
     FGN_CHECK_ARG(R >= 0 && B > 0 && N > 0 && C > 0 && P > 0, "bad dims");
     if (R == 0) return FGN_OK;
-    const size_t need = fgn_guided_roi_fused_workspace_bytes(pyr, R, B * N, C, P);
+    const size_t need = fgn_guided_roi_fused_workspace_bytes(R, B * N, C, P);
     if (!workspace || workspace_bytes < need) {
         set_error("guided_roi_fused: workspace %zu B < required %zu B", workspace_bytes, need);
         return FGN_ERR_WORKSPACE;
@@ -425,10 +412,8 @@ extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, 
     char *ws = (char *)workspace;
     float *feat = (float *)ws;                ws += align256((size_t)R * P * P * C * 4);
     int32_t *rb = (int32_t *)ws;              ws += align256((size_t)R * 4);
-    const size_t ra_bytes = fgn_roi_align_ml_workspace_bytes(pyr, R, P);
-    void *ra_ws = ws;                         ws += align256(ra_bytes);
     int rc = fgn_roi_align_ml_fwd(pyr, B, C, FGN_LAYOUT_NHWC, rois, R, P, sampling_ratio, aligned,
-                                  finest_scale, nullptr, nullptr, feat, FGN_LAYOUT_NHWC, lvl_out, ra_ws, ra_bytes, stream);
+                                  finest_scale, nullptr, nullptr, feat, FGN_LAYOUT_NHWC, lvl_out, stream);
     if (rc) return rc;
     roi_batch_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(rois, R, rb);
     FGN_LAUNCH_OK();

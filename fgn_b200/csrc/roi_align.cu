@@ -19,192 +19,6 @@
 
 namespace fgn {
 
-constexpr int kMaxP = 16;
-
-struct RoiPlan {               // lives in shared memory, one per CTA
-    int   level, batch, H, W;
-    float count;
-    int   lo[2][kMaxP];        // first touched cell per (axis, bin); axis 0 = y, 1 = x
-    int   n[2][kMaxP];         // number of touched cells (0 = bin has no valid sample)
-    int   off[2][kMaxP];       // offset of the bin's weights inside wtab
-    int   overflow;            // weight table did not fit (never with a table sized by the host)
-};
-
-// Builds RoiPlan + weight table.  All threads of the CTA must call it; contains __syncthreads.
-template <int P>
-__device__ __forceinline__ void build_plan(const Pyramid &pyr, const float *rois, int r,
-                                           int sampling_ratio, int aligned, float finest_scale,
-                                           RoiPlan &plan, float *wtab, int wtab_cap,
-                                           RoiGeom &g_out)
-{
-    __shared__ RoiGeom g_s;
-    const int t = threadIdx.x;
-    if (t == 0) {
-        const float *roi = rois + 5 * (size_t)r;
-        const int lvl = roi_level(roi, pyr, finest_scale);
-        g_s = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
-        plan.level = lvl; plan.batch = g_s.batch;
-        plan.H = pyr.H[lvl]; plan.W = pyr.W[lvl];
-        plan.count = g_s.count; plan.overflow = 0;
-    }
-    __syncthreads();
-    const RoiGeom g = g_s;
-    // phase A: touched-cell range per (axis, bin)
-    if (t < 2 * P) {
-        const int axis = t / P, p = t % P;
-        const float start = axis ? g.start_w : g.start_h;
-        const float bin   = axis ? g.bin_w : g.bin_h;
-        const int   grid  = axis ? g.grid_w : g.grid_h;
-        const int   size  = axis ? plan.W : plan.H;
-        int lo = 0x7fffffff, hi = -1;
-        for (int i = 0; i < grid; ++i) {
-            const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-            if (s.valid) { lo = min(lo, s.low); hi = max(hi, s.high); }
-        }
-        plan.lo[axis][p] = hi >= 0 ? lo : 0;
-        plan.n[axis][p]  = hi >= 0 ? hi - lo + 1 : 0;
-    }
-    __syncthreads();
-    // phase B: offsets (tiny serial prefix sum) + phase C: weights
-    if (t < 2 * P) {
-        const int axis = t / P, p = t % P;
-        int off = 0;
-        for (int a = 0; a <= axis; ++a)
-            for (int q = 0; q < (a == axis ? p : P); ++q) off += plan.n[a][q];
-        plan.off[axis][p] = off;
-        const int n = plan.n[axis][p];
-        if (off + n > wtab_cap) { plan.overflow = 1; }
-        else {
-            float *w = wtab + off;
-            for (int i = 0; i < n; ++i) w[i] = 0.f;
-            const float start = axis ? g.start_w : g.start_h;
-            const float bin   = axis ? g.bin_w : g.bin_h;
-            const int   grid  = axis ? g.grid_w : g.grid_h;
-            const int   size  = axis ? plan.W : plan.H;
-            const int   lo    = plan.lo[axis][p];
-            for (int i = 0; i < grid; ++i) {
-                const AxisSample s = axis_sample(start, bin, grid, size, p, i);
-                if (s.valid) { w[s.low - lo] += s.h; w[s.high - lo] += s.l; }
-            }
-        }
-    }
-    __syncthreads();
-    g_out = g;
-}
-
-// One CTA = one RoI x one block of CB channels; one warp = (bin-row ph, 128-channel chunk).
-// NHWC input.  Output NHWC ([R,P,P,C], direct 512 B warp stores) or NCHW ([R,C,P,P], staged
-// through shared memory and written as one contiguous CB*P*P*4-byte run).
-template <int P, int NB>
-__global__ void __launch_bounds__(448)
-roi_align_sep_nhwc_kernel(const Pyramid pyr, const int C, const int CB,
-                          const float *__restrict__ rois, const int R,
-                          const int sampling_ratio, const int aligned, const float finest_scale,
-                          const float *__restrict__ chan_scale,
-                          const int32_t *__restrict__ scale_index,
-                          float *__restrict__ out, const int out_layout,
-                          int32_t *__restrict__ lvl_out, const int wtab_cap)
-{
-    extern __shared__ __align__(16) float smem[];
-    __shared__ RoiPlan plan;
-    float *wtab  = smem;                      // [wtab_cap]
-    float *stage = smem + wtab_cap;           // [CB][P*P] only for NCHW output
-
-    const int nblk = (C + CB - 1) / CB;
-    const int r    = blockIdx.x / nblk;
-    const int cb0  = (blockIdx.x % nblk) * CB;
-    RoiGeom g;
-    build_plan<P>(pyr, rois, r, sampling_ratio, aligned, finest_scale, plan, wtab, wtab_cap, g);
-    if (lvl_out != nullptr && cb0 == 0 && threadIdx.x == 0) lvl_out[r] = plan.level;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
-    const int chunks = (CB + 127) / 128;
-    const int H = plan.H, W = plan.W;
-    const float *fbase = pyr.feat[plan.level] + (size_t)plan.batch * H * W * C;
-
-    for (int item = warp; item < P * chunks; item += nwarps) {
-        const int ph = item % P, chunk = item / P;
-        const int cl = chunk * 128 + lane * 4;            // channel inside the CTA's block
-        const int c  = cb0 + cl;
-        const bool active = (cl < CB) && (c < C);
-        float4 acc[P];
-#pragma unroll
-        for (int pw = 0; pw < P; ++pw) acc[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        if (active && !plan.overflow) {
-            const int ylo = plan.lo[0][ph], ny = plan.n[0][ph];
-            const float *wy = wtab + plan.off[0][ph];
-            for (int yi = 0; yi < ny; ++yi) {
-                const float wyv = wy[yi];
-                const float *row = fbase + ((size_t)(ylo + yi) * W) * C + c;
-#pragma unroll
-                for (int pw = 0; pw < P; ++pw) {
-                    const int nx = plan.n[1][pw];
-                    const float *wx = wtab + plan.off[1][pw];
-                    const float *cell = row + (size_t)plan.lo[1][pw] * C;
-                    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    // first NB cells of the bin as one batch of independent, predicated 128-bit
-                    // loads (memory-level parallelism); adaptive grids rarely need more
-                    float4 v[NB];
-#pragma unroll
-                    for (int k = 0; k < NB; ++k)
-                        v[k] = k < nx ? ldg4(cell + (size_t)k * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) fma4(racc, k < nx ? wx[k] : 0.f, v[k]);
-                    for (int xi = NB; xi < nx; ++xi) {
-                        const float4 u = ldg4(cell + (size_t)xi * C);
-                        fma4(racc, wx[xi], u);
-                    }
-                    fma4(acc[pw], wyv, racc);
-                }
-            }
-        }
-        // epilogue: divide by the sample count, optional AG-FCN channel attention
-        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (active && chan_scale != nullptr) {
-            const int si = scale_index != nullptr ? scale_index[r] : r;
-            cs = ldg4(chan_scale + (size_t)si * C + c);
-        }
-#pragma unroll
-        for (int pw = 0; pw < P; ++pw) {
-            // acc/count as in the reference; count is an integer-valued float, and x*(1/count)
-            // differs from x/count by at most 1 ulp -- use the true division to stay closest.
-            acc[pw].x = __fdiv_rn(acc[pw].x, plan.count) * cs.x;
-            acc[pw].y = __fdiv_rn(acc[pw].y, plan.count) * cs.y;
-            acc[pw].z = __fdiv_rn(acc[pw].z, plan.count) * cs.z;
-            acc[pw].w = __fdiv_rn(acc[pw].w, plan.count) * cs.w;
-        }
-        if (out_layout == FGN_LAYOUT_NHWC) {
-            if (active) {
-                float *o = out + (((size_t)r * P + ph) * P) * C + c;
-#pragma unroll
-                for (int pw = 0; pw < P; ++pw)
-                    *reinterpret_cast<float4 *>(o + (size_t)pw * C) = acc[pw];
-            }
-        } else if (active) {
-            float *s = stage + (size_t)cl * (P * P) + ph * P;
-#pragma unroll
-            for (int pw = 0; pw < P; ++pw) {
-                s[pw]             = acc[pw].x;
-                s[pw + P * P]     = acc[pw].y;
-                s[pw + 2 * P * P] = acc[pw].z;
-                s[pw + 3 * P * P] = acc[pw].w;
-            }
-        }
-    }
-    if (out_layout == FGN_LAYOUT_NCHW) {
-        __syncthreads();
-        const int cb_n = min(CB, C - cb0);
-        const int n = cb_n * P * P;                       // contiguous run in out
-        float *o = out + ((size_t)r * C + cb0) * (P * P);
-        // ((r*C+cb0)*P*P) % 4 == 0 whenever C % 4 == 0 and cb0 % 4 == 0 -> 16 B aligned
-        const int n4 = n >> 2;
-        for (int i = threadIdx.x; i < n4; i += blockDim.x)
-            reinterpret_cast<float4 *>(o)[i] = reinterpret_cast<const float4 *>(stage)[i];
-        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) o[i] = stage[i];
-    }
-}
 
 // Direct (one thread per output element) RoIAlign in the reference's own NCHW layout and
 // summation order.  Used for NCHW inputs, channel counts that are not a multiple of 4, pooled
@@ -325,58 +139,6 @@ static int env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
-template <int P, int NB>
-static int launch_sep_nb(const Pyramid &d, int C, int CB, const float *rois, int R, int sampling_ratio,
-                         int aligned, float finest_scale, const float *chan_scale,
-                         const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
-                         int wtab_cap, cudaStream_t st)
-{
-    const int warps = P * (CB / 128);
-    size_t smem = (size_t)wtab_cap * 4;
-    if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
-    auto kern = roi_align_sep_nhwc_kernel<P, NB>;
-    static int attr_set = 48 * 1024;      // per instantiation
-    if ((int)smem > attr_set) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = (int)smem;
-    }
-    const int nblk = (C + CB - 1) / CB;
-    kern<<<R * nblk, warps * 32, smem, st>>>(d, C, CB, rois, R, sampling_ratio, aligned,
-                                              finest_scale, chan_scale, scale_index, out,
-                                              out_layout, lvl_out, wtab_cap);
-    FGN_LAUNCH_OK();
-    return FGN_OK;
-}
-
-template <int P>
-static int launch_sep(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
-                      int aligned, float finest_scale, const float *chan_scale,
-                      const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
-                      cudaStream_t st)
-{
-    int maxH = 0, maxW = 0;
-    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
-    // sum of touched cells over the bins of one axis <= extent + 2 per bin boundary
-    int wtab_cap = maxH + maxW + 6 * P + 16;
-    wtab_cap = (wtab_cap + 3) & ~3;
-    // channel block per CTA: bounded by 32 warps (P * CB/128) and by the NCHW staging tile
-    int CB = env_int("FGN_RA_CB", 256);
-    if (P > 8) CB = 128;
-    if (C < CB) CB = ((C + 127) / 128) * 128;
-    const int nb = env_int("FGN_RA_NB", 4);
-#define FGN_SEP(NBV) launch_sep_nb<P, NBV>(d, C, CB, rois, R, sampling_ratio, aligned, finest_scale, \
-                                           chan_scale, scale_index, out, out_layout, lvl_out, wtab_cap, st)
-    if (P == 7) {
-        if (nb <= 1) return FGN_SEP(1);
-        if (nb == 2) return FGN_SEP(2);
-        if (nb == 3) return FGN_SEP(3);
-        if (nb == 6) return FGN_SEP(6);
-        if (nb >= 8) return FGN_SEP(8);
-    }
-    return FGN_SEP(4);
-#undef FGN_SEP
-}
-
 int launch_roi_align_stream(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
                             int aligned, float finest_scale, const float *chan_scale,
                             const int32_t *scale_index, float *out, int out_layout, int32_t *lvl_out,
@@ -389,18 +151,10 @@ int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *ro
 
 int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
                             int aligned, float finest_scale, const float *chan_scale,
-                            const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
-                            size_t workspace_bytes, cudaStream_t st, int ns_pref, bool *taken);
-size_t roi_align_window_workspace_bytes(const Pyramid &d, int R, int P);
-int launch_roi_align_gather(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
-                            int aligned, float finest_scale, const float *chan_scale,
-                            const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
-                            size_t workspace_bytes, cudaStream_t st, bool *taken);
-size_t roi_align_gather_workspace_bytes(const Pyramid &d, int R, int P);
-unsigned int roi_align_gather_violations();
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                            int ns_pref, bool *taken);
 unsigned int roi_align_window_violations();
 void roi_align_window_trace(unsigned long long *dst, int n);
-void roi_align_window_trace_reset();
 
 }  // namespace fgn
 
@@ -422,18 +176,11 @@ extern "C" int fgn_map_roi_levels(const float *rois, int R, int num_levels, floa
     return FGN_OK;
 }
 
-extern "C" size_t fgn_roi_align_ml_workspace_bytes(const fgn_pyramid_t *pyr, int R, int P)
-{
-    if (pyr == nullptr || validate_pyramid(pyr) != 0 || R <= 0 || P <= 0) return 0;
-    const Pyramid d = to_device_pyramid(pyr);
-    return max(roi_align_window_workspace_bytes(d, R, P), roi_align_gather_workspace_bytes(d, R, P));
-}
-
 extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int in_layout,
                                     const float *rois, int R, int P, int sampling_ratio,
                                     int aligned, float finest_scale, const float *chan_scale,
                                     const int32_t *scale_index, float *out, int out_layout,
-                                    int32_t *lvl_out, void *workspace, size_t workspace_bytes, void *stream)
+                                    int32_t *lvl_out, void *stream)
 {
     int rc = validate_pyramid(pyr);
     if (rc) return rc;
@@ -446,19 +193,12 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     const Pyramid d = to_device_pyramid(pyr);
     cudaStream_t st = (cudaStream_t)stream;
     // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
-    // 3 / 2 = row-streaming kernel (one CTA per RoI), 1 = bin-centric, 0 = direct
-    const int impl = env_int("FGN_RA_IMPL", 5);
-    if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 5) {
-        bool taken = false;
-        rc = launch_roi_align_gather(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
-                                     scale_index, out, lvl_out, workspace, workspace_bytes, st, &taken);
-        if (rc || taken) return rc;
-    }
+    // 2 = row-streaming kernel (one CTA per RoI: NCHW output and the shapes the window kernel declines), 0 = direct
+    const int impl = env_int("FGN_RA_IMPL", 4);
     if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4) {
         bool taken = false;
         rc = launch_roi_align_window(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
-                                     scale_index, out, lvl_out, workspace, workspace_bytes, st,
-                                     env_int("FGN_RA_NS", 0), &taken);
+                                     scale_index, out, lvl_out, st, env_int("FGN_RA_NS", 0), &taken);
         if (rc || taken) return rc;
     }
     if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 2) {
@@ -468,12 +208,6 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
                                      impl == 3 ? env_int("FGN_RA_VEC", 2) : -env_int("FGN_RA_VEC", 2),
                                      env_int("FGN_RA_NS", 0), &taken);
         if (rc || taken) return rc;
-    }
-    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 1) {
-        if (P == 7)  return launch_sep<7>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
-                                          chan_scale, scale_index, out, out_layout, lvl_out, st);
-        if (P == 14) return launch_sep<14>(d, C, rois, R, sampling_ratio, aligned, finest_scale,
-                                           chan_scale, scale_index, out, out_layout, lvl_out, st);
     }
     const size_t total = (size_t)R * C * P * P;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
@@ -488,14 +222,13 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
 // that fell outside the register window since the library was loaded.  Must be 0.
 extern "C" unsigned int fgn_debug_roi_window_violations(void)
 {
-    return roi_align_window_violations() + roi_align_gather_violations();
+    return roi_align_window_violations();
 }
 
 // Development trace of the rotating-window kernel (FGN_RA_DEBUG bit 5); not declared in the public header.
 extern "C" void fgn_debug_roi_window_trace(unsigned long long *dst, int n)
 {
-    if (dst == nullptr) roi_align_window_trace_reset();
-    else roi_align_window_trace(dst, n);
+    roi_align_window_trace(dst, n);
 }
 
 // Same entry, forcing the direct kernel (exported for the in-library cross-check in tests).

@@ -603,13 +603,12 @@ int launch_roi_align_stream_bf16(const Pyramid &d, int C, int P, const float *ro
     const size_t smem = (size_t)NS * kStageCells * 256 * 2 + (size_t)wx_cap * 4 + (size_t)wyd_rows * PP8 * 4;
     if (smem > 200 * 1024) { set_error("bf16 RoIAlign: feature map too tall for the weight table (%d rows)", maxH); return FGN_ERR_UNSUPPORTED; }
     const int nblk = (C + 255) / 256;
-    static int attr7 = 0, attr14 = 0;
     if (P == 7) {
-        if ((int)smem > attr7) { FGN_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_bf16_kernel<7, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr7 = (int)smem; }
+        FGN_SMEM_OPTIN((roi_align_stream_bf16_kernel<7, NS>), smem);
         roi_align_stream_bf16_kernel<7, NS><<<R * nblk, 8 * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                                                          scale_index, out, out_is_bf16, lvl_out, wx_cap, wyd_rows);
     } else {
-        if ((int)smem > attr14) { FGN_CUDA_OK(cudaFuncSetAttribute(roi_align_stream_bf16_kernel<14, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr14 = (int)smem; }
+        FGN_SMEM_OPTIN((roi_align_stream_bf16_kernel<14, NS>), smem);
         roi_align_stream_bf16_kernel<14, NS><<<R * nblk, 15 * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                                                            scale_index, out, out_is_bf16, lvl_out, wx_cap, wyd_rows);
     }
@@ -633,11 +632,7 @@ static int launch_stream_cfg(const Pyramid &d, int C, const float *rois, int R, 
     if (out_layout == FGN_LAYOUT_NCHW) smem += (size_t)CB * P * P * 4;
     if (smem > 200 * 1024) { *taken = false; return FGN_OK; }
     auto kern = roi_align_stream_kernel<P, VEC, NS, WS>;
-    static int attr_set = 0;          // per instantiation
-    if ((int)smem > attr_set) {
-        FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = (int)smem;
-    }
+    FGN_SMEM_OPTIN(kern, smem);
     const int nblk = (C + CB - 1) / CB;
     const char *e = getenv("FGN_RA_CLASSES");
     // default 1: the 3-class order shortens the kernel alone by ~3% but its retiring CTAs cost more than that

@@ -1,34 +1,36 @@
-// roi_align_window.cu -- plan pre-pass + persistent rotating-window multi-level RoIAlign (sm_100a).
+// roi_align_window.cu -- persistent, planner-fed, rotating-window multi-level RoIAlign (sm_100a).
 //
-// Separable formulation with the reference's exact coordinate arithmetic (common.cuh):
+// Same separable formulation and exact coordinate arithmetic as roi_align_stream.cu
 //   out[ph,pw] = 1/count * sum_y Ay[ph][y] * sum_x Ax[pw][x] * v[y,x]
-// Two kernels per call:
+// reorganised so that the SMs spend their issue slots on the row pass and nothing else:
 //
-//   roi_plan_kernel     one warp per (RoI, item slot).  Assigns the FPN level, evaluates the reference
-//                       coordinate arithmetic once per (axis, bin, sample) and writes a compact PLAN RECORD
-//                       (footprint, ring schedule, per-bin-column x weights, per-footprint-row window y
-//                       weights) to the caller's workspace, plus the RoI's footprint size class.  It also
-//                       arms the ticket counter of the call (no global state: everything lives in the
-//                       caller's workspace).  Depends on the RoIs only, not on the feature maps.
-//   roi_align_window_kernel  PERSISTENT CTAs (2 per SM at P=7) that pull work items from the ticket counter,
-//                       largest footprint class first; big RoIs are 2 or 4 items that different CTAs take.
-//       * a FETCHER warp turns tickets into items: it copies the item's plan record (L2-resident, ~0.7 KB)
-//         into one of three shared-memory plan slots.  No coordinate arithmetic is left in this kernel.
-//       * a PRODUCER warp streams the footprint rows NHWC -> shared-memory ring with bulk async copies
-//         (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); the ring keeps running across items.
-//       * P CONSUMER warps (warp = bin column) do the row pass out of shared memory with 128-bit loads
-//         at compile-time offsets, then fold the row into a WINDOW of kWin bin rows held in registers.
-//         Footprint rows are visited top to bottom and the set of bin rows a footprint row touches is a
-//         contiguous range whose first member never decreases, so the window only ever slides down:
-//         when the row passes the last row of the window's first bin, that bin is scaled by 1/count
-//         (and the AG-FCN channel attention) and stored, and the window rotates.
-//       * a footprint row can touch more than kWin bin rows only when a bin is shorter than 2/3 of a
-//         cell ((dph - 1 + 1/g) * bin_h < 2); such RoIs are planned as ceil(P / kWin) items of kWin
-//         bin rows each, for which the bound holds trivially.
-// Measurements: DESIGN.md section 5.
+//   * PERSISTENT CTAs (2 per SM at P=7) pull work items from a ticket counter.  An item is
+//     (RoI, range of bin rows, channel block).  With one channel block the tickets are handed out
+//     largest-footprint-class first (the warps that idle during the first plan classify all RoIs into
+//     ballot masks; every CTA derives the same order), big RoIs as 2 or 4 items that different CTAs
+//     take, and CTA i starts on RoI i without a ticket when it is small.
+//   * a PLANNER warp works ahead of everyone else: it takes the ticket, assigns the FPN level,
+//     evaluates the reference coordinate arithmetic once per (axis, bin, sample) and leaves the
+//     footprint, ring schedule and weight tables in one of three shared-memory plan slots.  The
+//     per-RoI prologue is therefore off the critical path of the copy and the math.
+//   * a PRODUCER warp streams the footprint rows NHWC -> shared-memory ring with bulk async copies
+//     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); the ring keeps running across items.
+//   * P CONSUMER warps (warp = bin column) do the row pass out of shared memory with 128-bit loads
+//     at compile-time offsets, then fold the row into a WINDOW of kWin bin rows held in registers.
+//     Footprint rows are visited top to bottom and the set of bin rows a footprint row touches is a
+//     contiguous range whose first member never decreases, so the window only ever slides down:
+//     when the row passes the last row of the window's first bin, that bin is scaled by 1/count
+//     (and the AG-FCN channel attention) and stored, and the window rotates.  The accumulators of
+//     one RoI shrink from P to kWin rows of registers, the fold loses its P compare-and-branch
+//     pairs, and the output stores are spread over the item instead of bursting at its end.
+//   * a footprint row can touch more than kWin bin rows only when a bin is shorter than 2/3 of a
+//     cell ((dph - 1 + 1/g) * bin_h < 2); such RoIs are planned as ceil(P / kWin) items of kWin
+//     bin rows each, for which the bound holds trivially.
+// What bounds it on B200 (measurements in DESIGN.md section 5): the ring (bytes in flight / copy latency),
+// the planner and the consumers' per-row instruction chains all sit at 40-48 us per 1000 cfg3 RoIs.
 #include "common.cuh"
 #include <stdlib.h>
-#include <stddef.h>
+#include <atomic>
 
 namespace fgn {
 
@@ -36,8 +38,12 @@ namespace {
 
 constexpr int kWin        = 4;      // bin rows held in registers per consumer warp
 constexpr int kStageCells = 32;     // cells (of CB channels) per ring stage
-constexpr int kPlanWarps  = 8;      // warps (= items) per CTA of the plan kernel
+constexpr unsigned kTicketSlots = 65536;   // ticket counters: [0, half) for launches baked into CUDA graphs, [half, end) eager
 
+__device__ unsigned int g_window_ticket[kTicketSlots];
+// Slot allocators shared by EVERY instantiation of the launcher (P=7 and P=14 launches in flight at the same time on
+// different streams must never share a counter) and safe against concurrent host threads.
+std::atomic<unsigned int> g_eager_seq{0}, g_captured_seq{0};
 __device__ unsigned int g_window_violation;           // planner self-check (must stay 0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,14 +132,9 @@ __device__ __forceinline__ void bulk_g2s32(uint32_t dst, const void *src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// One work item: bin rows [pa, pb) of RoI r.  The same struct is the header of the item's plan record in the
-// workspace and of the shared-memory plan slot the fetcher copies it into.
+
 template <int P>
-struct alignas(16) WinSlot {
-    int   wx_used;                                 // floats of the x-weight runs (multiple of 4, 8 floats of read slack included)
-    int   rec_bytes;                               // header + x runs + nrows float4 window weights
-    int   nitems;                                  // record 0 of a RoI: items a whole-RoI ticket publishes
-    int   valid;                                   // 0: this (RoI, slot) has no item
+struct WinSlot {
     int   r, cb0, level, batch, H, W;
     int   pa, pb;                                  // bin rows [pa, pb) of this item
     float count;
@@ -141,25 +142,6 @@ struct alignas(16) WinSlot {
     int   xlo[P], xn[P], xoff[P];
     int   hi[P + 1];                               // last footprint row (relative to Y0) of bins <= ph
 };
-
-// workspace: [0,256) ticket counter | class bytes [R] | records [R * S0] of rec_stride bytes
-struct WindowWs {
-    unsigned int  *ticket;
-    unsigned char *cls;
-    unsigned char *recs;
-    size_t         bytes;
-};
-__host__ __device__ inline size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
-inline WindowWs carve_window_ws(void *base, int R, int S0, int rec_stride)
-{
-    WindowWs w;
-    unsigned char *p = (unsigned char *)base;
-    w.ticket = (unsigned int *)p;
-    w.cls    = p + 256;
-    w.recs   = p + 256 + ws_align((size_t)R);
-    w.bytes  = 256 + ws_align((size_t)R) + (size_t)R * S0 * rec_stride;
-    return w;
-}
 
 // development trace (debug_mode bit 5): per CTA, per item (first 16), 12 globaltimer stamps
 constexpr int kTraceItems = 16, kTraceEvents = 12, kTraceCtas = 296;
@@ -173,185 +155,23 @@ __device__ __forceinline__ void trace(int debug_mode, int item, int ev, int lane
     }
 }
 
-// Sorted ticket scheme: footprint class c in 0..3 (largest first) -> bin rows per item, items per RoI.  Class 3 RoIs are
-// one item (or ceil(P/kWin) window chunks when their bins are tiny).
-template <int P> __host__ __device__ constexpr int win_rpc(int c)
-{
-    return P <= 8 ? (c == 0 ? 1 : (c == 1 ? 2 : (c == 2 ? 4 : P))) : (c == 0 ? 2 : (c == 1 ? 4 : (c == 2 ? 7 : P)));
-}
-template <int P> __host__ __device__ constexpr int win_nch(int c) { return (P + win_rpc<P>(c) - 1) / win_rpc<P>(c); }
-template <int P> __host__ __device__ constexpr int win_slots() { return win_nch<P>(0); }
-
-__device__ __forceinline__ int footprint_class(const float est, const float3 thr)
-{
-    return est > thr.x ? 0 : (est > thr.y ? 1 : (est > thr.z ? 2 : 3));   // 0 = largest ... 3 = smallest (NaN -> 3)
-}
-
 }  // namespace
 
-// ---- plan pre-pass: one warp per (RoI, item slot) ------------------------------------------------------------
-// Item slots of a RoI (S0 = ceil(P/2) of them), by ticket scheme:
-//   sorted (one channel block, R <= kSortCap): class 0 -> S0 items of 2 bin rows, class 1 -> S1 items of 4,
-//     class 2/3 -> one item [0,P), or ceil(P/kWin) items of kWin rows when a bin is shorter than 3/4 cell;
-//   plain: ceil(P/kWin) items of kWin rows when split (tiny bins, or footprint > split_cells), else one.
-template <int P>
-__global__ void __launch_bounds__(kPlanWarps * 32)
-roi_plan_kernel(const Pyramid pyr, const float *__restrict__ rois, const int R, const int sampling_ratio,
-                const int aligned, const float finest_scale, int32_t *__restrict__ lvl_out,
-                unsigned int *__restrict__ ticket, unsigned char *__restrict__ cls_out,
-                unsigned char *__restrict__ recs, const int rec_stride, const int wx_cap, const int wyd_rows,
-                const int sorted, const float split_cells, const float3 thr, const unsigned int first_ticket)
-{
-    constexpr int S0 = win_slots<P>(), S = (P + kWin - 1) / kWin;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char stage_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wg = blockIdx.x * kPlanWarps + warp;
-    if (wg == 0 && lane == 0) *ticket = first_ticket;            // CTA i of the main kernel starts on ticket i
-    const int r = wg / S0, j = wg - r * S0;
-    if (r >= R) return;
-
-    const float *roi = rois + 5 * (size_t)r;
-    const int level = roi_level(roi, pyr, finest_scale);
-    const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
-    const int H = pyr.H[level], W = pyr.W[level];
-    const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);      // cells, from the box alone
-    int c = sorted ? footprint_class(est, thr) : 3;
-    // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned as items of
-    // kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
-    const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && est > split_cells));
-    // (tiny bins need items of at most kWin bin rows: a class whose items are taller hands such a RoI to class 3)
-    if (split && c < 3 && (c == 0 ? win_rpc<P>(0) : (c == 1 ? win_rpc<P>(1) : win_rpc<P>(2))) > kWin) c = 3;
-    bool exists;
-    int pa, pb, nitems = 1;
-    if (sorted && c < 3) {
-        const int rpc = c == 0 ? win_rpc<P>(0) : (c == 1 ? win_rpc<P>(1) : win_rpc<P>(2));
-        exists = j * rpc < P; pa = j * rpc; pb = min(P, pa + rpc);
-    }
-    else if (split)            { exists = j < S;  pa = j * kWin; pb = min(P, pa + kWin); nitems = sorted ? S : 1; }
-    else                       { exists = j == 0; pa = 0; pb = P; }
-    unsigned char *rec = recs + ((size_t)r * S0 + j) * rec_stride;
-    if (j == 0 && lane == 0) {
-        cls_out[r] = (unsigned char)c;
-        if (lvl_out != nullptr) lvl_out[r] = level;
-    }
-    if (!exists) {
-        if (lane == 0) reinterpret_cast<WinSlot<P> *>(rec)->valid = 0;
-        return;
-    }
-
-    WinSlot<P> &ps = *reinterpret_cast<WinSlot<P> *>(stage_raw + (size_t)warp * rec_stride);
-    float *wx = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(&ps) + sizeof(WinSlot<P>));
-
-    // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns.  Sample coordinates are monotone in
-    // the sample index, so when the first and last sample of a bin are valid they bound its cells.
-    const int axis = lane >= P ? 1 : 0, p = lane - axis * P;
-    const bool isx = lane >= P && lane < 2 * P, isy = lane < P && p >= pa && p < pb;
-    const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
-    const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
-    int lo = 0x7fffffff, hi = -1;
-    if ((isx || isy) && grid > 0) {
-        const AxisSample s0 = axis_sample(start, bin, grid, size, p, 0);
-        const AxisSample s1 = axis_sample(start, bin, grid, size, p, grid - 1);
-        if (s0.valid && s1.valid) { lo = min(s0.low, s1.low); hi = max(s0.high, s1.high); }   // either direction (x2 < x1)
-        else {
-            for (int i = 0; i < grid; ++i) {
-                const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-                if (sm.valid) { lo = min(lo, sm.low); hi = max(hi, sm.high); }
-            }
-        }
-    }
-    int n = hi >= 0 ? hi - lo + 1 : 0;
-    if (hi < 0) lo = 0;
-    const int big = 0x7fffffff;
-    int X0 = __reduce_min_sync(FULL, (isx && n > 0) ? lo : big);
-    int X1 = __reduce_max_sync(FULL, (isx && n > 0) ? lo + n : -1);
-    int Y0 = __reduce_min_sync(FULL, (isy && n > 0) ? lo : big);
-    int Y1 = __reduce_max_sync(FULL, (isy && n > 0) ? lo + n : -1);
-    int n4 = (n + 3) & ~3;                                       // weight runs start 16 B aligned
-    int xsum = __reduce_add_sync(FULL, isx ? n4 : 0);
-    if (X1 < 0 || Y1 < 0 || xsum + 8 > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; n4 = 0; xsum = 0; }
-    const int ncols = X1 - X0, nrows = Y1 - Y0;
-    int nseg, rps, nstages;
-    if (ncols <= kStageCells) {
-        nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
-    } else {
-        nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
-    }
-    if (ncols == 0 || nrows == 0) nstages = 0;
-    int off = 0;                                                 // exclusive scan of the padded x runs
-    int hiall[P];                                                // running max of the bin rows' last footprint row
-    int him = -1, myhi = -1;
-#pragma unroll
-    for (int qq = 0; qq < P; ++qq) {
-        const int nq = __shfl_sync(FULL, n4, P + qq);
-        if (isx && qq < p) off += nq;
-        const int hq = __shfl_sync(FULL, (isy && n > 0) ? lo + n - 1 - Y0 : -1, qq);
-        him = max(him, hq);
-        hiall[qq] = him;
-        if (qq == lane) myhi = him;
-    }
-    const int wx_used = xsum + 8;                                // consumers read 8 weights per bin column whatever nx is
-    float *wrow = wx + wx_used;                                  // [nrows][4]
-    if (lane == 0) {
-        ps.wx_used = wx_used; ps.rec_bytes = (int)sizeof(WinSlot<P>) + 4 * (wx_used + 4 * nrows);
-        ps.nitems = nitems; ps.valid = 1;
-        ps.r = r; ps.cb0 = 0; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
-        ps.pa = pa; ps.pb = pb; ps.count = g.count;
-        ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
-        ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
-    }
-    if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
-    if (lane < P) ps.hi[lane] = myhi;
-    if (lane == P) ps.hi[P] = him;
-    for (int i = lane; i < ((wx_used + 4 * nrows) >> 2); i += 32)
-        reinterpret_cast<float4 *>(wx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    if (nstages > 0 && n > 0) {
-        // Both axes run ONE instruction stream: a sample adds its two bilinear weights to two entries of
-        // the record's table.  x: entry = run offset + cell.  y: footprint row j lives in window slot
-        // (p - base_j) of wrow[j], base_j = first bin row of the item whose (running-max) last row is >= j.
-        auto entry = [&](int cell) {
-            if (isx) return off + cell - lo;
-            const int jj = cell - Y0;
-            int base = pa;
-#pragma unroll
-            for (int qq = 0; qq < P; ++qq) base += (qq >= pa && qq < pb && hiall[qq] < jj) ? 1 : 0;
-            const int comp = p - base;
-            if (comp < 0 || comp >= kWin) { atomicAdd(&g_window_violation, 1u); return -1; }
-            return wx_used + 4 * jj + comp;
-        };
-        for (int i = 0; i < grid; ++i) {
-            const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
-            if (sm.valid) {
-                const int e0 = entry(sm.low), e1 = entry(sm.high);
-                if (e0 >= 0) wx[e0] += sm.h;
-                if (e1 >= 0) wx[e1] += sm.l;
-            }
-        }
-    }
-    __syncwarp();
-    const int nvec = ps.rec_bytes >> 4;
-    const uint4 *srcv = reinterpret_cast<const uint4 *>(&ps);
-    uint4 *dstv = reinterpret_cast<uint4 *>(rec);
-    for (int i = lane; i < nvec; i += 32) dstv[i] = srcv[i];
-}
-
-// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = fetcher.
-// Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { x runs | [nrows] float4 window weights }
+// Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
+// Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
 template <int P, int VEC, int NS, int MINB, bool SCALED>
 __global__ void __launch_bounds__((P + 2) * 32, MINB)
-roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
+roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
+                        const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
-                        float *__restrict__ out, unsigned int *__restrict__ ticket_ctr,
-                        const unsigned char *__restrict__ cls_bytes, const unsigned char *__restrict__ recs,
-                        const int rec_stride, const int wslot_floats, const int sorted_flag, const int debug_mode)
+                        float *__restrict__ out, int32_t *__restrict__ lvl_out,
+                        const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells,
+                        const float3 thr, const int debug_mode)
 {
     // debug_mode (development only): bit 0 = no copies (producer only signals), bit 1 = no row math,
     // bit 5 = record the per-CTA timeline
     constexpr int CB = 128 * VEC;                   // channels per item; cell stride in the ring
     constexpr int S  = (P + kWin - 1) / kWin;       // bin-row chunks of a split RoI
-    constexpr int S0 = win_slots<P>(), N0 = win_nch<P>(0), N1 = win_nch<P>(1), N2 = win_nch<P>(2);
     constexpr int kStageFloats = kStageCells * CB;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -363,7 +183,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
 
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *wtab = ring + (size_t)NS * kStageFloats;
-    const int wslot = wslot_floats;                 // floats per plan slot
+    const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
     // one opaque register holds the barriers' shared address: left to itself ptxas re-derives it before every wait
     // (S2UR SR_CgaCtaId + ULEA, ~40 cycles of latency per ring stage)
     uint32_t bar32;
@@ -372,6 +192,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
     const uint32_t pfull32 = bar32 + 16 * NS, pempty32 = bar32 + 16 * NS + 8 * kPlanSlots;
 
     const int nblk  = (C + CB - 1) / CB;
+    const int items = R * S * nblk;                 // tickets = (RoI, bin-row chunk, channel block); unused chunks are skipped
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
@@ -381,36 +202,58 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
     }
     __syncthreads();
 
-    // Sorted ticket scheme: ticket t means "the t-th item in largest-class-first order".  Every CTA builds the same
-    // class membership masks (one ballot per class and 32-RoI block) from the plan kernel's class bytes.
-    const bool sorted = sorted_flag != 0;
+    // Sorted ticket scheme (see the planner): while the planner works on the CTA's first RoI, the other warps
+    // classify every RoI by footprint size -- 32 RoIs per warp step, one ballot mask per class and block.
+    const bool sorted = (nblk == 1) && (R <= kSortCap) && !(debug_mode & 64);
+    const int nstatic = sorted ? min(R, (int)gridDim.x) : 0;             // CTAs past R start on a ticket (small launches)
     const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
+    auto size_class = [&](const float *roi) {                            // 0 = largest footprints ... 3 = smallest (NaN -> 3)
+        const int lv = roi_level(roi, pyr, finest_scale);
+        const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned);
+        const float est = (gg.bin_h * (float)P + 2.f) * (gg.bin_w * (float)P + 2.f);   // cells, from the box alone
+        return est > thr.x ? 0 : (est > thr.y ? 1 : (est > thr.z ? 2 : 3));
+    };
     if (sorted && warp <= P) {
         for (int blk = warp; blk < nsb; blk += P + 1) {
             const int idx = blk * 32 + lane;
-            const int c = idx < R ? (int)cls_bytes[idx] : -1;
+            int c = -1;
+            if (idx < R) {
+                c = size_class(rois + 5 * (size_t)idx);
+                if (idx < nstatic && c >= 2) c = -1;                     // CTA idx starts on it without a ticket
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const unsigned m = __ballot_sync(FULL, c == q);
                 if (lane == q) cls_mask[q][blk] = m;
             }
         }
-        // announce the masks to the fetcher without waiting for it
+        // announce the masks to the planner without waiting for it (it reads them before its first lookup;
+        // blocking here could deadlock: a first RoI split into more items than plan slots needs the consumers)
         __threadfence_block();
         asm volatile("bar.arrive 1, %0;" ::"n"((P + 2) * 32) : "memory");
     }
 
     if (warp == P + 1) {
-        // ===== fetcher: ticket -> item -> plan record (workspace, L2) -> plan slot ===========================
-        //  * sorted: tickets enumerate class 0 RoIs x S0 chunks, class 1 RoIs x S1 chunks, then class 2 and class 3
-        //    RoIs whole (a whole-RoI ticket publishes the nitems records of its RoI).
-        //  * plain: ticket = (RoI, item slot in [0,S), channel block) in index order; slots without an item are skipped.
-        // CTA i starts on ticket i; later tickets come from the counter the plan kernel armed with gridDim.x, and
-        // one ticket is always in flight while the current item is fetched.
-        int ntickets = sorted ? 0x3fffffff : R * S * nblk;               // sorted: known once the class totals are
+        // ===== planner ===================================================================================
+        // Two ticket schemes.
+        //  * sorted (one channel block, R <= kSortCap): CTA i starts on RoI i with no ticket at all; while its
+        //    consumers work on that, the planner classifies every other RoI by footprint size into four classes
+        //    (ballot masks in shared memory, identical in every CTA because every CTA computes them from the
+        //    same rois) and ticket t then means "the t-th RoI in largest-class-first order".  Big footprints
+        //    start early, the launch ends on small ones, and nobody has to be split to balance the tail.
+        //  * plain (otherwise): ticket = (RoI, bin-row chunk, channel block) in index order; chunks a RoI does
+        //    not use are skipped.
+        // The planner always holds one prefetched ticket, so a launch draws ntickets + 2 per CTA in all; the
+        // last one resets the counter for the next launch that uses this slot.
+        constexpr int S0 = (P + 1) / 2, S1 = (P + 3) / 4;                // chunks (of 2 / 4 bin rows) of a class 0 / 1 RoI
+        int ntickets = sorted ? 0x3fffffff : items;                      // sorted: known once the class totals are
+        unsigned last_ticket = sorted ? 0xffffffffu : (unsigned)items + 2u * gridDim.x - 1u;
         auto take = [&]() {
             unsigned int tk = 0;
-            if (lane == 0) tk = atomicAdd(ticket_ctr, 1u);
+            if (lane == 0) {
+                tk = atomicAdd(&g_window_ticket[ticket_slot], 1u);
+                if (tk == last_ticket) g_window_ticket[ticket_slot] = 0u;
+            }
             return tk;                                                   // valid in lane 0; broadcast at use
         };
         int cls_total = 0;                                               // lane c < 4: RoIs in size class c
@@ -423,18 +266,21 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
                 n = __reduce_add_sync(FULL, n);
                 if (lane == q) cls_total = n;
             }
-            ntickets = __shfl_sync(FULL, cls_total, 0) * N0 + __shfl_sync(FULL, cls_total, 1) * N1
-                       + __shfl_sync(FULL, cls_total, 2) * N2 + __shfl_sync(FULL, cls_total, 3);
+            ntickets = __shfl_sync(FULL, cls_total, 0) * S0 + __shfl_sync(FULL, cls_total, 1) * S1
+                       + __shfl_sync(FULL, cls_total, 2) + __shfl_sync(FULL, cls_total, 3);
+            // (the one ticket this planner drew before it knew the totals is < 2 * gridDim.x - 1 <= last_ticket,
+            //  and the draw that returns exactly last_ticket comes after every planner's first, so none is missed)
+            last_ticket = (unsigned)ntickets + 2u * gridDim.x - 1u;
         };
-        auto lookup = [&](int tk, int &j0, bool &whole) {                // ticket -> (RoI, first item slot), largest class first
+        auto lookup = [&](int tk, int &ba, int &bb) {                    // ticket -> (RoI, bin rows [ba, bb)), largest class first
             const int t0 = __shfl_sync(FULL, cls_total, 0), t1 = __shfl_sync(FULL, cls_total, 1),
                       t2 = __shfl_sync(FULL, cls_total, 2);
-            int c, krem;
-            j0 = 0; whole = false;
-            if (tk < t0 * N0)                     { c = 0; krem = tk / N0; j0 = tk - krem * N0; }
-            else if ((tk -= t0 * N0) < t1 * N1)   { c = 1; krem = tk / N1; j0 = tk - krem * N1; }
-            else if ((tk -= t1 * N1) < t2 * N2)   { c = 2; krem = tk / N2; j0 = tk - krem * N2; }
-            else                                  { c = 3; krem = tk - t2 * N2; whole = true; }
+            int c, krem, chunk = 0, cw = P;
+            if (tk < t0 * S0)                     { c = 0; krem = tk / S0; chunk = tk - krem * S0; cw = 2; }
+            else if ((tk -= t0 * S0) < t1 * S1)   { c = 1; krem = tk / S1; chunk = tk - krem * S1; cw = 4; }
+            else if ((tk -= t1 * S1) < t2)        { c = 2; krem = tk; }
+            else                                  { c = 3; krem = tk - t2; }
+            ba = chunk * cw; bb = min(P, ba + cw);
             int r = 0;
             for (int b0 = 0; b0 < nsb; b0 += 32) {                       // 32 blocks per round
                 const unsigned m = (b0 + lane < nsb) ? cls_mask[c][b0 + lane] : 0u;
@@ -458,61 +304,152 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
             return r;
         };
 
-        constexpr int kHdr = (int)sizeof(WinSlot<P>);
-        unsigned int tnext = 0;
+        unsigned int tnext = take();
         int k = 0, b = 0;                                                // items published so far, their slot
         unsigned eparity = 1;                                            // plan_empty: item k - kPlanSlots consumed
+        bool totals_known = false;
         for (unsigned int it = 0;; ++it) {
-            const unsigned int ticket = it == 0 ? blockIdx.x : __shfl_sync(FULL, tnext, 0);
-            if (sorted && it == 0) class_totals();
-            tnext = take();                                              // in flight while this item is fetched
-            if ((int)ticket >= ntickets) {
-                mbar_wait32(pempty32 + 8 * b, eparity);
-                if (lane == 0) slot[b].r = -1;
-                __syncwarp();
-                if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
-                break;
+            // the ticket's RoI, channel block and bin rows [ba, bb); window chunks [chunk_lo, chunk_hi) of them
+            int r = 0, cbi = 0, ba = 0, bb = P, chunk_lo = 0, chunk_hi = S;
+            bool have = false;
+            if (sorted && it == 0 && (int)blockIdx.x < nstatic) {        // small first RoI: start on it right away
+                r = (int)blockIdx.x;
+                have = size_class(rois + 5 * (size_t)r) >= 2;
             }
-            int r, j0 = 0, cbi = 0;
-            bool whole = false;
-            if (sorted) r = lookup((int)ticket, j0, whole);
-            else {
-                cbi = (int)ticket % nblk; j0 = ((int)ticket / nblk) % S;
-                r = (int)ticket / (nblk * S);
+            if (!have) {
+                const unsigned int ticket = __shfl_sync(FULL, tnext, 0);
+                if (sorted && !totals_known) {
+                    class_totals();
+                    totals_known = true;
+                    // `ticket` was drawn before last_ticket was known (a CTA that starts late can draw the last one)
+                    if (lane == 0 && ticket == last_ticket) g_window_ticket[ticket_slot] = 0u;
+                }
+                tnext = take();                                          // in flight while this item is planned
+                if ((int)ticket >= ntickets) {
+                    mbar_wait32(pempty32 + 8 * b, eparity);
+                    if (lane == 0) slot[b].r = -1;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
+                    break;
+                }
+                if (sorted) r = lookup((int)ticket, ba, bb);
+                else {
+                    cbi = (int)ticket % nblk; chunk_lo = ((int)ticket / nblk) % S; chunk_hi = chunk_lo + 1;
+                    r = (int)ticket / (nblk * S);
+                }
             }
-            int jn = 1;                                                  // items of this ticket (whole-RoI tickets: record 0 says)
-            for (int j = 0; j < jn; ++j) {
-                trace(debug_mode, k, 0, lane);
-                const unsigned char *rec = recs + ((size_t)r * S0 + j0 + j) * rec_stride;
-                // first KB of the record (the header is its first bytes; most records fit entirely)
-                const uint4 v0 = *reinterpret_cast<const uint4 *>(rec + lane * 16);
-                uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
-                const int rec_bytes = __shfl_sync(FULL, (int)v0.y, 0);
-                const int valid = __shfl_sync(FULL, (int)v0.w, 0);
-                if (j == 0 && whole) jn = __shfl_sync(FULL, (int)v0.z, 0);
-                if (!valid) break;                                       // plain scheme: slot without an item
-                if (512 + lane * 16 < rec_bytes) v1 = *reinterpret_cast<const uint4 *>(rec + 512 + lane * 16);
-                unsigned char *hdst = reinterpret_cast<unsigned char *>(&slot[b]);
-                unsigned char *tdst = reinterpret_cast<unsigned char *>(wtab + (size_t)b * wslot);
-                auto put = [&](int off, const uint4 v) {
-                    if (off < kHdr) *reinterpret_cast<uint4 *>(hdst + off) = v;
-                    else            *reinterpret_cast<uint4 *>(tdst + (off - kHdr)) = v;
+            trace(debug_mode, k, 0, lane);
+            const float *roi = rois + 5 * (size_t)r;
+            const int level = roi_level(roi, pyr, finest_scale);
+            const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
+            const int H = pyr.H[level], W = pyr.W[level];
+            // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
+            // as items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
+            const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
+            const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && est > split_cells));
+            if (!split) { if (chunk_lo > 0) continue; chunk_hi = 1; }
+            else if (sorted) chunk_hi = (bb - ba + kWin - 1) / kWin;
+            if (lane == 0 && lvl_out != nullptr && cbi == 0 && chunk_lo == 0 && ba == 0) lvl_out[r] = level;
+
+            for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+            WinSlot<P> &ps = slot[b];
+            const int pa = split ? ba + chunk * kWin : ba, pb = split ? min(bb, pa + kWin) : bb;
+
+            // per-lane bin: lanes [0,P) = bin rows, [P,2P) = bin columns.  Sample coordinates are monotone in
+            // the sample index, so when the first and last sample of a bin are valid they bound its cells.
+            const int axis = lane >= P ? 1 : 0, p = lane - axis * P;
+            const bool isx = lane >= P && lane < 2 * P, isy = lane < P && p >= pa && p < pb;
+            const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
+            const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
+            int lo = 0x7fffffff, hi = -1;
+            if ((isx || isy) && grid > 0) {
+                const AxisSample s0 = axis_sample(start, bin, grid, size, p, 0);
+                const AxisSample s1 = axis_sample(start, bin, grid, size, p, grid - 1);
+                if (s0.valid && s1.valid) { lo = min(s0.low, s1.low); hi = max(s0.high, s1.high); }   // either direction (x2 < x1)
+                else {
+                    for (int i = 0; i < grid; ++i) {
+                        const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                        if (sm.valid) { lo = min(lo, sm.low); hi = max(hi, sm.high); }
+                    }
+                }
+            }
+            int n = hi >= 0 ? hi - lo + 1 : 0;
+            if (hi < 0) lo = 0;
+            const int big = 0x7fffffff;
+            int X0 = __reduce_min_sync(FULL, (isx && n > 0) ? lo : big);
+            int X1 = __reduce_max_sync(FULL, (isx && n > 0) ? lo + n : -1);
+            int Y0 = __reduce_min_sync(FULL, (isy && n > 0) ? lo : big);
+            int Y1 = __reduce_max_sync(FULL, (isy && n > 0) ? lo + n : -1);
+            const int n4 = (n + 3) & ~3;                                 // weight runs start 16 B aligned
+            const int xsum = __reduce_add_sync(FULL, isx ? n4 : 0);
+            if (X1 < 0 || Y1 < 0 || xsum + 8 > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; }
+            const int ncols = X1 - X0, nrows = Y1 - Y0;
+            int nseg, rps, nstages;
+            if (ncols <= kStageCells) {
+                nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
+            } else {
+                nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
+            }
+            if (ncols == 0 || nrows == 0) nstages = 0;
+            int off = 0;                                                 // exclusive scan of the padded x runs
+            int hiall[P];                                                // running max of the bin rows' last footprint row
+            int him = -1, myhi = -1;
+#pragma unroll
+            for (int qq = 0; qq < P; ++qq) {
+                const int nq = __shfl_sync(FULL, n4, P + qq);
+                if (isx && qq < p) off += nq;
+                const int hq = __shfl_sync(FULL, (isy && n > 0) ? lo + n - 1 - Y0 : -1, qq);
+                him = max(him, hq);
+                hiall[qq] = him;
+                if (qq == lane) myhi = him;
+            }
+            float *wx = wtab + (size_t)b * wslot;
+            float *wrow = wx + wx_cap;                                   // [nrows][4]
+            trace(debug_mode, k, 1, lane);
+            mbar_wait32(pempty32 + 8 * b, eparity);
+            trace(debug_mode, k, 2, lane);
+            if (lane == 0) {
+                ps.r = r; ps.cb0 = cbi * CB; ps.level = level; ps.batch = g.batch; ps.H = H; ps.W = W;
+                ps.pa = pa; ps.pb = pb; ps.count = g.count;
+                ps.X0 = X0; ps.Y0 = Y0; ps.ncols = ncols; ps.nrows = nrows;
+                ps.nseg = nseg; ps.rps = rps; ps.nstages = nstages;
+            }
+            if (isx) { ps.xlo[p] = lo; ps.xn[p] = n; ps.xoff[p] = off; }
+            if (lane < P) ps.hi[lane] = myhi;
+            for (int i = lane; i < nrows; i += 32)
+                reinterpret_cast<float4 *>(wrow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = lane; i < (xsum >> 2); i += 32)
+                reinterpret_cast<float4 *>(wx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (nstages > 0 && n > 0) {
+                // Both axes run ONE instruction stream: a sample adds its two bilinear weights to two entries of
+                // the slot's table.  x: entry = run offset + cell.  y: footprint row j lives in window slot
+                // (p - base_j) of wrow[j], base_j = first bin row of the item whose (running-max) last row is >= j.
+                auto entry = [&](int cell) {
+                    if (isx) return off + cell - lo;
+                    const int j = cell - Y0;
+                    int base = pa;
+#pragma unroll
+                    for (int qq = 0; qq < P; ++qq) base += (qq >= pa && qq < pb && hiall[qq] < j) ? 1 : 0;
+                    const int comp = p - base;
+                    if (comp < 0 || comp >= kWin) { atomicAdd(&g_window_violation, 1u); return -1; }
+                    return wx_cap + 4 * j + comp;
                 };
-                trace(debug_mode, k, 1, lane);
-                mbar_wait32(pempty32 + 8 * b, eparity);
-                trace(debug_mode, k, 2, lane);
-                if (lane * 16 < rec_bytes) put(lane * 16, v0);
-                if (512 + lane * 16 < rec_bytes) put(512 + lane * 16, v1);
-                for (int off = 1024 + lane * 16; off < rec_bytes; off += 512)
-                    put(off, *reinterpret_cast<const uint4 *>(rec + off));
-                __syncwarp();
-                if (lane == 0 && cbi != 0) slot[b].cb0 = cbi * CB;
-                __syncwarp();
-                trace(debug_mode, k, 3, lane);
-                if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
-                ++k;
-                if (++b == kPlanSlots) { b = 0; eparity ^= 1; }
+                for (int i = 0; i < grid; ++i) {
+                    const AxisSample sm = axis_sample(start, bin, grid, size, p, i);
+                    if (sm.valid) {
+                        const int e0 = entry(sm.low), e1 = entry(sm.high);
+                        if (e0 >= 0) wx[e0] += sm.h;
+                        if (e1 >= 0) wx[e1] += sm.l;
+                    }
+                }
             }
+            __syncwarp();
+            trace(debug_mode, k, 3, lane);
+            if (lane == 0) mbar_arrive32(pfull32 + 8 * b);
+            ++k;
+            if (++b == kPlanSlots) { b = 0; eparity ^= 1; }
+            }   // chunks of this RoI
         }
     } else if (warp == P) {
         // ===== producer: bulk async copies of footprint rows, ring runs across items =======================
@@ -604,7 +541,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
             if (r < 0) break;
             if (pw == 0) trace(debug_mode, k, 8, lane);
             const float *wx = wtab + (size_t)b * wslot;
-            const float4 *wr = reinterpret_cast<const float4 *>(wx + ps.wx_used);   // y weights of the next footprint row
+            const float4 *wr = reinterpret_cast<const float4 *>(wx + wx_cap);   // y weights of the next footprint row
             const int cb0 = ps.cb0, cbn = min(CB, C - cb0);
             const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
             const int xlo = ps.xlo[pw] - ps.X0, nx = ps.xn[pw];
@@ -784,69 +721,44 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const int R,
         }
     }
 }
-template <int P> static int window_rec_stride(int wx_cap, int wyd_rows)
-{
-    return ((int)sizeof(WinSlot<P>) + 4 * (wx_cap + 4 * wyd_rows) + 15) & ~15;
-}
-static void window_table_caps(const Pyramid &d, int P, int *wx_cap, int *wyd_rows)
-{
-    int maxH = 0, maxW = 0;
-    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
-    *wx_cap = (maxW + 9 * P + 24 + 3) & ~3;                    // touched cells <= extent + 2 per bin boundary, runs padded to 4, 8 slack
-    *wyd_rows = maxH;
-}
-
-// Bytes of caller workspace one window-kernel call needs (ticket counter, class bytes, plan records); 0 when the
-// kernel has no instantiation for P.
-size_t roi_align_window_workspace_bytes(const Pyramid &d, int R, int P)
-{
-    int wx_cap, wyd_rows;
-    window_table_caps(d, P, &wx_cap, &wyd_rows);
-    if (P == 7)  return carve_window_ws(nullptr, R, win_slots<7>(), window_rec_stride<7>(wx_cap, wyd_rows)).bytes;
-    if (P == 14) return carve_window_ws(nullptr, R, win_slots<14>(), window_rec_stride<14>(wx_cap, wyd_rows)).bytes;
-    return 0;
-}
-
-static int device_sm_count(int *out)
-{
-    // per device (a process may drive several GPUs); the query is a cached attribute read
-    int dev = 0;
-    FGN_CUDA_OK(cudaGetDevice(&dev));
-    FGN_CUDA_OK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
-    return FGN_OK;
-}
 
 template <int P, int VEC, int NS, int MINB>
 static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
                              int aligned, float finest_scale, const float *chan_scale,
-                             const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
-                             size_t workspace_bytes, cudaStream_t st, bool *taken)
+                             const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                             bool *taken)
 {
     constexpr int CB = 128 * VEC;
     constexpr int S  = (P + kWin - 1) / kWin;
-    constexpr int S0 = win_slots<P>();
-    int wx_cap, wyd_rows;
-    window_table_caps(d, P, &wx_cap, &wyd_rows);
-    const int wslot = wx_cap + 4 * wyd_rows;
-    const int rec_stride = window_rec_stride<P>(wx_cap, wyd_rows);
-    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * wslot * 4;
+    int maxH = 0, maxW = 0;
+    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
+    const int wx_cap = (maxW + 9 * P + 24 + 3) & ~3;           // touched cells <= extent + 2 per bin boundary, runs padded to 4, 8 slack
+    const int wyd_rows = maxH;
+    const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * (wx_cap + 4 * wyd_rows) * 4;
     const size_t smem_cap = MINB == 2 ? 115200 : 230000;           // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
-    const size_t plan_smem = (size_t)kPlanWarps * rec_stride;
-    if (smem > smem_cap || plan_smem > 200 * 1024) { *taken = false; return FGN_OK; }
-    const WindowWs ws = carve_window_ws(workspace, R, S0, rec_stride);
-    if (workspace == nullptr || workspace_bytes < ws.bytes) {
-        set_error("roi_align: workspace %zu B < required %zu B (fgn_roi_align_ml_workspace_bytes)", workspace_bytes, ws.bytes);
-        return FGN_ERR_WORKSPACE;
-    }
+    if (smem > smem_cap) { *taken = false; return FGN_OK; }
     auto kern = chan_scale != nullptr ? roi_align_window_kernel<P, VEC, NS, MINB, true>
                                       : roi_align_window_kernel<P, VEC, NS, MINB, false>;
-    // (cudaFuncSetAttribute applies to the current device only: set it on every call, it is a cheap host-side write)
+    // cudaFuncSetAttribute applies to the current device only and a process may drive several GPUs: set it on every
+    // call (a host-side write) and size the persistent grid for the current device
     FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (plan_smem > 48 * 1024)
-        FGN_CUDA_OK(cudaFuncSetAttribute(roi_plan_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
-    int sm_count = 0;
-    int rc = device_sm_count(&sm_count);
-    if (rc) return rc;
+    int sm_count = 0, dev = 0;
+    FGN_CUDA_OK(cudaGetDevice(&dev));
+    FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    // One ticket counter per launch that can be in flight.  A launch captured into a CUDA graph bakes its
+    // counter in and may run at any later time, so captured launches draw from a range that is never
+    // recycled (when it is exhausted the caller falls back to the non-persistent kernel); eager launches
+    // cycle through the other half, far more slots than launches can be in flight at once.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    FGN_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+    int slot;
+    if (cap != cudaStreamCaptureStatusNone) {
+        const unsigned int seq = g_captured_seq.fetch_add(1u, std::memory_order_relaxed);
+        if (seq >= kTicketSlots / 2) { *taken = false; return FGN_OK; }
+        slot = (int)seq;
+    } else {
+        slot = (int)(kTicketSlots / 2 + (g_eager_seq.fetch_add(1u, std::memory_order_relaxed) % (kTicketSlots / 2)));
+    }
     const int nblk = (C + CB - 1) / CB;
     const char *e = getenv("FGN_RA_SPLIT");
     const float split_cells = e != nullptr ? (float)atof(e) : 512.f;
@@ -857,7 +769,7 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     // launches with fewer RoIs than resident CTAs still fill the machine: the chunks of their big RoIs (up to
     // ceil(P/2) per RoI in the sorted ticket scheme) are taken by the extra CTAs
     const bool sorted_scheme = nblk == 1 && R <= kSortCap && !(dbg & 64);
-    const int grid = min(per_sm * sm_count, sorted_scheme ? R * S0 : R * nblk);
+    const int grid = min(per_sm * sm_count, sorted_scheme ? R * ((P + 1) / 2) : R * nblk);
     // size classes of the sorted ticket scheme (footprint cells): > x: 4 chunks, > y: 2 chunks, > z / rest: whole
     float3 thr = make_float3(1000.f, 500.f, 250.f);
     // A launch with few RoIs per resident CTA (the mask branch: 100 detections on 296 CTAs) is as long as its
@@ -870,16 +782,11 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
         thr = make_float3(thr.x * sc, thr.y * sc, thr.z * sc);
     }
     if (const char *et = getenv("FGN_RA_THR")) sscanf(et, "%f,%f,%f", &thr.x, &thr.y, &thr.z);
-    const int plan_ctas = (R * S0 + kPlanWarps - 1) / kPlanWarps;
-    roi_plan_kernel<P><<<plan_ctas, kPlanWarps * 32, plan_smem, st>>>(
-        d, rois, R, sampling_ratio, aligned, finest_scale, lvl_out, ws.ticket, ws.cls, ws.recs, rec_stride, wx_cap,
-        wyd_rows, sorted_scheme ? 1 : 0, split_cells > 0.f ? split_cells : 3.0e38f, thr, (unsigned)grid);
+    (void)CB;
+    kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                           scale_index, out, lvl_out, wx_cap, wyd_rows, slot,
+                                           split_cells > 0.f ? split_cells : 3.0e38f, thr, dbg);
     FGN_LAUNCH_OK();
-    if (!(dbg & 128)) {                                       // (development: bit 7 = plan pre-pass only)
-        kern<<<grid, (P + 2) * 32, smem, st>>>(d, C, R, chan_scale, scale_index, out, ws.ticket, ws.cls, ws.recs,
-                                               rec_stride, wslot, sorted_scheme ? 1 : 0, dbg);
-        FGN_LAUNCH_OK();
-    }
     (void)S;
     *taken = true;
     return FGN_OK;
@@ -888,14 +795,13 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
 // NHWC in, NHWC out.  Declines (taken=false) shapes it has no instantiation for.
 int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
                             int aligned, float finest_scale, const float *chan_scale,
-                            const int32_t *scale_index, float *out, int32_t *lvl_out, void *workspace,
-                            size_t workspace_bytes, cudaStream_t st, int ns_pref, bool *taken)
+                            const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                            int ns_pref, bool *taken)
 {
     *taken = false;
     if ((C & 3) != 0) return FGN_OK;
 #define FGN_WIN(PV, VV, NV, MB) launch_window_cfg<PV, VV, NV, MB>(d, C, rois, R, sampling_ratio, aligned, finest_scale, \
-                                                                  chan_scale, scale_index, out, lvl_out, workspace,     \
-                                                                  workspace_bytes, st, taken)
+                                                                  chan_scale, scale_index, out, lvl_out, st, taken)
     if (P == 7) {
         if (C > 128) return ns_pref == 2 ? FGN_WIN(7, 2, 2, 2) : FGN_WIN(7, 2, 3, 2);
         return ns_pref == 3 ? FGN_WIN(7, 1, 3, 2) : FGN_WIN(7, 1, 4, 2);
@@ -906,12 +812,6 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
     }
 #undef FGN_WIN
     return FGN_OK;
-}
-
-void roi_align_window_trace_reset()
-{
-    void *p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_window_trace) == cudaSuccess) cudaMemset(p, 0, sizeof(g_window_trace));
 }
 
 void roi_align_window_trace(unsigned long long *dst, int n)

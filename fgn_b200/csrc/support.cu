@@ -288,12 +288,11 @@ extern "C" int fgn_support_mask_pool(const uint8_t *mask, const float *boxes, in
     const int gcap = 64;                                          // staged samples per bin (adaptive grid <= 64)
     const size_t smem = ((size_t)2 * cap + (size_t)S_h * P + (size_t)4 * 2 * P * gcap) * 4;
     cudaStream_t st = (cudaStream_t)stream;
-    static int attr7 = 48 * 1024, attr14 = 48 * 1024;
     if (P == 7) {
-        if ((int)smem > attr7) { FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr7 = (int)smem; }
+        FGN_SMEM_OPTIN(support_mask_pool_kernel<7>, smem);
         support_mask_pool_kernel<7><<<M, kMaskThreads, smem, st>>>(mask, boxes, S_h, S_w, out, cap, gcap);
     } else {
-        if ((int)smem > attr14) { FGN_CUDA_OK(cudaFuncSetAttribute(support_mask_pool_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr14 = (int)smem; }
+        FGN_SMEM_OPTIN(support_mask_pool_kernel<14>, smem);
         support_mask_pool_kernel<14><<<M, kMaskThreads, smem, st>>>(mask, boxes, S_h, S_w, out, cap, gcap);
     }
     FGN_LAUNCH_OK();

@@ -206,18 +206,10 @@ def roi_align_multilevel(feats: Sequence[torch.Tensor], rois: torch.Tensor, scal
         if scale_index is not None:
             scale_index = scale_index.to(torch.int32).contiguous()
     lib = _lib.load()
-    if force_direct:
-        _lib.check(lib.fgn_roi_align_ml_fwd_direct(
-            ctypes.byref(pyr), b, c, lay, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)),
-            float(finest_scale), _ptr(chan_scale), _ptr(scale_index), out.data_ptr(), out_lay, _ptr(lvl), _stream()),
-            "fgn_roi_align_ml_fwd_direct")
-    else:
-        wsb = int(lib.fgn_roi_align_ml_workspace_bytes(ctypes.byref(pyr), r, p))
-        ws = torch.empty((max(wsb, 256),), device=rois.device, dtype=torch.uint8)
-        _lib.check(lib.fgn_roi_align_ml_fwd(
-            ctypes.byref(pyr), b, c, lay, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)),
-            float(finest_scale), _ptr(chan_scale), _ptr(scale_index), out.data_ptr(), out_lay, _ptr(lvl),
-            ws.data_ptr(), wsb, _stream()), "fgn_roi_align_ml_fwd")
+    fn = lib.fgn_roi_align_ml_fwd_direct if force_direct else lib.fgn_roi_align_ml_fwd
+    _lib.check(fn(ctypes.byref(pyr), b, c, lay, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)),
+                  float(finest_scale), _ptr(chan_scale), _ptr(scale_index), out.data_ptr(), out_lay,
+                  _ptr(lvl), _stream()), "fgn_roi_align_ml_fwd")
     return (out, lvl.long()) if return_levels else out
 
 
@@ -508,7 +500,7 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
             pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), ws.data_ptr(), wsb, _stream()),
             "fgn_guided_roi_fused_fwd_bf16")
         return (cls, reg, lvl.long()) if return_levels else (cls, reg)
-    wsb = lib.fgn_guided_roi_fused_workspace_bytes(ctypes.byref(pyr), r, bn, c, p)
+    wsb = lib.fgn_guided_roi_fused_workspace_bytes(r, bn, c, p)
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
     _lib.check(lib.fgn_guided_roi_fused_fwd(
         ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FGN_ABI_VERSION 2
+#define FGN_ABI_VERSION 1
 
 #define FGN_OK                 0
 #define FGN_ERR_INVALID_ARG   -1
@@ -72,19 +72,12 @@ typedef struct {
  *     (the AG-FCN attention multiply fgn_roi_head.py:379 with the gather :707-714 fused in);
  *   lvl_out (optional): [R] int32 level each RoI was pooled from.
  * in_layout NHWC is the fast path (128-bit channel-vector loads); NCHW input is served by a
- * direct kernel that keeps the reference layout.
- * workspace: fgn_roi_align_ml_workspace_bytes(pyr, R, P) bytes of device memory, 256-byte aligned, contents
- *   irrelevant on entry.  The fast path runs two kernels: a plan pre-pass (one warp per RoI item: level, exact
- *   sample coordinates -> per-item footprint + separable weight tables + the call's ticket counter, all written
- *   to the workspace) and the persistent pooling kernel that consumes those plans.  Nothing else is kept:
- *   the library holds no per-call state of its own. */
-size_t fgn_roi_align_ml_workspace_bytes(const fgn_pyramid_t *pyr, int R, int P);
+ * direct kernel that keeps the reference layout. */
 int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int in_layout,
                          const float *rois, int R, int P, int sampling_ratio, int aligned,
                          float finest_scale,
                          const float *chan_scale, const int32_t *scale_index,
-                         float *out, int out_layout, int32_t *lvl_out,
-                         void *workspace, size_t workspace_bytes, void *stream);
+                         float *out, int out_layout, int32_t *lvl_out, void *stream);
 
 /* Integer side of the same kernel for the bit-exact check (test/debug export).  For RoI r,
  * pooled from the level fgn_roi_align_ml_fwd would choose:
@@ -197,7 +190,7 @@ int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, i
 /* FPN-mode single pass (no shared_head between RoIAlign and the relation conv): level
  * assignment + RoIAlign + relation fusion + heads; RoI features never reach HBM.
  * Same arguments as the two calls it replaces. */
-size_t fgn_guided_roi_fused_workspace_bytes(const fgn_pyramid_t *pyr, int R, int BN, int C, int P);
+size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P);
 int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
                              int P, int sampling_ratio, int aligned, float finest_scale,
                              const float *spp_cat_mean /* [B*N,P,P,C] NHWC */, int N,

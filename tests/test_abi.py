@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/fgn_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in fgn_b200/_lib.py"
-    assert lib.fgn_abi_version() == 2
+    assert lib.fgn_abi_version() == 1
 
 
 def test_zero_size_calls_do_not_touch_the_device():
@@ -42,7 +42,7 @@ def test_zero_size_calls_do_not_touch_the_device():
     pyr = _lib.Pyramid()
     pyr.num_levels = 1
     pyr.H[0], pyr.W[0], pyr.spatial_scale[0] = 8, 8, 1.0 / 16
-    assert lib.fgn_roi_align_ml_fwd(ctypes.byref(pyr), 1, 64, 1, None, 0, 7, 0, 1, 56.0, None, None, None, 0, None, None, 0, None) == 0
+    assert lib.fgn_roi_align_ml_fwd(ctypes.byref(pyr), 1, 64, 1, None, 0, 7, 0, 1, 56.0, None, None, None, 0, None, None) == 0
 
 
 def test_bad_arguments_set_the_error_string():
