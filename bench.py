@@ -16,7 +16,11 @@ the per-episode results.
 `value`  : inputs resident in HBM (channels_last) when the timed region starts.
 `e2e`    : same path through the module API from pinned HOST buffers in the reference's NCHW
            layout; H2D of every input, device repack, D2H of cls/bbox results inside the timed region.
-`roofline`: the multi-level RoIAlign kernel, timed alone with CUDA events on its launch stream.
+`roofline`: the multi-level RoIAlign kernel, timed alone with CUDA events on its launch stream; `roofline_tensor`: the
+           relation contraction the same way; `roofline_step`: the whole step's algorithmic bytes (fused accounting)
+           over ms_per_step.  `traffic` / tensor-pipe figures are read from the committed profiles/*.json they came from.
+`parity`  : episode 0 through the product path against the CPU oracle on a strided RoI subset, BEFORE any timing.
+`sustained`: the same step looped for seconds, with its clock record.  `strong_scaling`, `gather_overhead_w1`: SURVEY 8e.
 `cpu_baseline`: the oracle (torchvision CPU roi_align + torch CPU fusion, materialised concat form)
            on this box's host cores, rank 0, N=1 only, on a bounded sample.
 """
@@ -176,6 +180,9 @@ def main():
     ap.add_argument("--no-fold", action="store_true", help="skip the separately reported folded-attention variant")
     ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
     ap.add_argument("--e2e-streams", type=int, default=8, help="streams the end-to-end leg overlaps copies and compute on")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle subset check of episode 0 before timing")
+    ap.add_argument("--no-gather-overhead", action="store_true", help="skip the W=1 run with the result gather enabled")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -201,6 +208,8 @@ def main():
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": dict(config, episodes_per_gpu_per_step=1),
                 "cpu_baseline": {"value": rois_s, "unit": "RoIs/s", "cores": cores, "kind": "port", "sample": sample},
+                "reference_arm_note": ("one CPU process on rank 0's host cores; at N>1 the driver's ratio is N GPUs against this ONE process"
+                                       if args.gpus > 1 else "the oracle port on this box's host cores"),
                 "e2e": {"value": rois_s, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -210,13 +219,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the fgn_b200 arm has no CPU fallback (use --impl reference)")
     import torch.distributed as dist
     from fgn_b200 import ops
-    from fgn_b200.episodes import EpisodeRunner, build_heads, episode_to_device, gather_results, make_episode, run_guided_path
+    from fgn_b200.episodes import (EpisodeRunner, ResultGatherer, build_heads, episode_to_device, gather_results,
+                                   make_episode, make_weights, run_guided_path)
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     E = args.episodes_per_step
+    n_ext = len(cfg.strides)
+    rois_per_episode = cfg.num_rois * cfg.batch
 
     # ---- inputs: E distinct episodes per rank, resident in HBM (channels_last) and mirrored in pinned host memory
     host_eps = [make_episode(cfg, seed=rank * E + i) for i in range(min(E, 4))]
@@ -230,32 +242,60 @@ def main():
     bytes_resident = sum(t.numel() * 4 for ep in dev_eps for t in ep["qry"] + ep["spp"])
     config["l2"] = f"no flush: episode stream of {E} x {bytes_resident / E / 1e6:.0f} MB distinct inputs > 126 MB L2"
 
+    # ---- parity first: episode 0 through the product path, a strided subset of its rows against the CPU oracle
+    #      (oracle/parity.py: the checker, outside every timed region).  A bench number cannot outlive a broken kernel.
+    parity_line = None
+    if rank == 0 and not args.no_parity:
+        from oracle import parity
+        with torch.no_grad():
+            out0 = run_guided_path(rpn, head, dev_eps[0])
+            torch.cuda.synchronize()
+            rep = parity.episode_parity(host_eps[0], out0, head, make_weights(cfg.channels, 0), roi_subset=48, det_subset=16)
+        parity_line = parity.summarize(rep)
+        parity_line["tolerance"] = "|a-b| <= 1e-4 + 1e-5|b| vs oracle/fgn_oracle.py, episode 0, strided RoI subset; attention and support vectors in full"
+        if not parity_line["ok"]:
+            raise SystemExit(f"bench.py: parity check failed before timing: {json.dumps(parity_line)}")
+        del out0
+
     runner = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, n_streams=args.streams)
     config["launch"] = ("eager" if args.no_graphs else "one CUDA graph per resident episode") + \
         f", episodes round-robin on {max(1, args.streams)} stream(s)"
-    res_buf = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), device=device)
+    W5 = 5 * cfg.n_ways + 1
+    gath = ResultGatherer((E, rois_per_episode, W5), device) if world > 1 else None
+    res_single = torch.empty((E, rois_per_episode, W5), device=device)
+    state = {"k": 0, "buf": res_single}
 
     def sink(i, o):
-        res_buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
-        res_buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+        buf = state["buf"]
+        buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
+        buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
 
-    def step_resident():
+    def run_block(n_eps, buf):
+        state["buf"] = buf
         runner.begin()
-        for i in range(E):
+        for i in range(n_eps):
             runner.run(i, sink)
         runner.end()
-        res = res_buf                                         # [E, R, 5N+1]
-        if world > 1:
-            res = gather_results(res, E * world)
-        return res
+
+    def step_resident():
+        if gath is None:
+            run_block(E, res_single)
+            return res_single
+        k = state["k"]
+        run_block(E, gath.local(k))          # waits for the gather that last read this staging buffer (two steps ago)
+        gath.submit(k)                       # all_gather on the side stream, overlapped with the next step
+        state["k"] = k + 1
+        return None
 
     def sync_all():
+        if gath is not None:
+            gath.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, after=None):
         with torch.no_grad():
             for _ in range(warmup):
                 fn()
@@ -267,6 +307,8 @@ def main():
             e0.record()
             for _ in range(steps):
                 fn()
+            if after is not None:
+                after()                      # e.g. the compute stream waits for the gathers still in flight
             e1.record()
             sync_all()
             ms = e0.elapsed_time(e1)
@@ -280,57 +322,146 @@ def main():
 
     # the overlapped graph replay must reproduce the plain eager, single-stream results bit for bit
     with torch.no_grad():
-        step_resident()
+        run_block(E, res_single)
         torch.cuda.synchronize()
         for i in (0, E // 2, E - 1):
             ref = run_guided_path(rpn, head, dev_eps[i])
             torch.cuda.synchronize()
-            if not (torch.equal(res_buf[i, :, : cfg.n_ways + 1], ref["cls_score"]) and
-                    torch.equal(res_buf[i, :, cfg.n_ways + 1:], ref["bbox_pred"])):
+            if not (torch.equal(res_single[i, :, : cfg.n_ways + 1], ref["cls_score"]) and
+                    torch.equal(res_single[i, :, cfg.n_ways + 1:], ref["bbox_pred"])):
                 raise SystemExit(f"bench.py: episode {i} differs between graph/multi-stream replay and eager execution")
+    if gath is not None:                     # ... and the gathered block of this rank is what this rank computed
+        with torch.no_grad():
+            step_resident()
+            got = gath.result(state["k"] - 1)
+            torch.cuda.synchronize()
+            if not torch.equal(got[rank * E:(rank + 1) * E], res_single):
+                raise SystemExit("bench.py: gathered results differ from the local results")
 
     sampler = ClockSampler(local_rank)
-    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler,
+                                 after=(gath.drain if gath is not None else None))
     episodes = E * world * args.steps
-    rois_total = episodes * cfg.num_rois * cfg.batch
+    rois_total = episodes * rois_per_episode
     value = rois_total / (ms * 1e-3)
 
-    # ---- e2e: pinned host buffers in the reference's NCHW layout -> H2D -> path -> D2H of results
-    pinned = []
-    for ep in host_eps:
-        p = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else (v.pin_memory() if torch.is_tensor(v) else v))
-             for k, v in ep.items()}
-        pinned.append(p)
-    h2d = sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
-              for k, v in pinned[0].items() if isinstance(v, list) or torch.is_tensor(v)) * E
-    out_host = torch.empty((E, cfg.num_rois * cfg.batch, 5 * cfg.n_ways + 1), dtype=torch.float32).pin_memory()
-    d2h = out_host.numel() * 4
+    # ---- sustained: the same step looped for >= args.sustained_seconds (the headline region above is a burst of a few
+    #      tens of milliseconds at boost clocks), with its own clock record
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+        s2 = ClockSampler(local_rank)
+        ms_s, _, clocks_s = timed(step_resident, n_sus, 1, s2, after=(gath.drain if gath is not None else None))
+        sustained = {"value": E * world * n_sus * rois_per_episode / (ms_s * 1e-3), "unit": "RoIs/s", "steps": n_sus,
+                     "seconds": ms_s * 1e-3, "ms_per_step": ms_s / n_sus, "clocks": clocks_s}
 
+    # ---- strong scaling: the SAME total of E episodes per step split over the ranks (E/world each)
+    strong = None
+    if world > 1 and E % world == 0:
+        e_loc = E // world
+        g_strong = ResultGatherer((e_loc, rois_per_episode, W5), device)
+        st = {"k": 0}
+
+        def step_strong():
+            k = st["k"]
+            run_block(e_loc, g_strong.local(k))
+            g_strong.submit(k)
+            st["k"] = k + 1
+
+        ms_st, _, _ = timed(step_strong, args.steps, args.warmup, after=g_strong.drain)
+        g_strong.drain()
+        strong = {"total_episodes_per_step": E, "episodes_per_gpu_per_step": e_loc,
+                  "value": E * args.steps * rois_per_episode / (ms_st * 1e-3), "unit": "RoIs/s",
+                  "ms_per_step": ms_st / args.steps,
+                  "note": "same total work at every N; efficiency = value(N) / (N * value(1) of this key's N=1 run = the headline value at N=1)"}
+
+    # ---- harness overhead at W=1: the same step with the result gather enabled in a one-rank NCCL group
+    gather_w1 = None
+    if world == 1 and not args.no_gather_overhead:
+        try:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", str(29500 + (os.getpid() % 2000)))
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=device)
+            g1 = ResultGatherer((E, rois_per_episode, W5), device)
+            st1 = {"k": 0}
+
+            def step_g1():
+                k = st1["k"]
+                run_block(E, g1.local(k))
+                g1.submit(k)
+                st1["k"] = k + 1
+
+            ms_g1, _, _ = timed(step_g1, args.steps, args.warmup, after=g1.drain)
+            g1.drain()
+            torch.cuda.synchronize()
+            gather_w1 = {"ms_per_step_with_gather": ms_g1 / args.steps, "ms_per_step_without": ms / args.steps,
+                         "overhead_pct": 100.0 * (ms_g1 - ms) / ms,
+                         "what": "all_gather_into_tensor of the [E,R,5N+1] results in a one-rank NCCL group on a side stream"}
+            dist.destroy_process_group()
+        except Exception as e:  # pragma: no cover
+            gather_w1 = {"unavailable": repr(e)[:200]}
+
+    # ---- e2e: pinned host buffers -> H2D -> path -> D2H of results.  fp32 NCHW (the reference's layout; the headline
+    #      e2e) and, beside it, bf16 channels_last host buffers through the bf16 variant (half the PCIe bytes)
+    def pin(ep, bf16=False):
+        out = {}
+        for k, v in ep.items():
+            if isinstance(v, list):
+                out[k] = [(t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if bf16 and t.dim() == 4 else t).pin_memory()
+                          for t in v]
+            elif torch.is_tensor(v):
+                out[k] = v.pin_memory()
+            else:
+                out[k] = v
+        return out
+
+    def bytes_of(ep):
+        return sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
+                   for k, v in ep.items() if isinstance(v, list) or torch.is_tensor(v))
+
+    out_host = torch.empty((E, rois_per_episode, W5), dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * 4
     e2e_streams = [torch.cuda.Stream() for _ in range(max(1, args.e2e_streams))]   # copies of episode i+1 overlap compute of episode i
 
-    def step_e2e():
-        main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for i in range(E):
-            st = e2e_streams[i % len(e2e_streams)]
-            st.wait_event(fork)
-            with torch.cuda.stream(st):
-                ep = episode_to_device(pinned[i % len(pinned)], device, channels_last=False)   # H2D, NCHW
-                o = run_guided_path(rpn, head, ep)                                              # repack + path
-                out_host[i].copy_(torch.cat([o["cls_score"], o["bbox_pred"]], 1), non_blocking=True)
-        for st in e2e_streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
-        main.synchronize()                                                                      # results on host
+    def make_e2e_step(pinned, channels_last):
+        def step_e2e():
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for i in range(E):
+                st_ = e2e_streams[i % len(e2e_streams)]
+                st_.wait_event(fork)
+                with torch.cuda.stream(st_):
+                    ep = episode_to_device(pinned[i % len(pinned)], device, channels_last=channels_last)   # H2D
+                    o = run_guided_path(rpn, head, ep)                                                  # repack + path
+                    out_host[i].copy_(torch.cat([o["cls_score"], o["bbox_pred"]], 1), non_blocking=True)
+            for st_ in e2e_streams:
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                main.wait_event(ev)
+            main.synchronize()                                                                          # results on host
+        return step_e2e
 
     e2e_steps = max(2, min(args.steps, 5))
-    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 1)
-    e2e_value = E * world * e2e_steps * cfg.num_rois * cfg.batch / (ms_e2e * 1e-3)
+    pinned32 = [pin(ep) for ep in host_eps]
+    h2d = bytes_of(pinned32[0]) * E
+    ms_e2e, _, _ = timed(make_e2e_step(pinned32, False), e2e_steps, 1)
+    e2e_value = E * world * e2e_steps * rois_per_episode / (ms_e2e * 1e-3)
+    e2e = {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "host_layout": "NCHW fp32 pinned",
+           "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / (ms_e2e * 1e-3) / 1e9,
+           "note": "PCIe-bound: the H2D copy of the fp32 pyramids is the step; per-GPU rate above, all ranks share the host's memory / root complexes"}
+    del pinned32
+    if not args.no_bf16:
+        pinned16 = [pin(ep, bf16=True) for ep in host_eps]
+        h2d16 = bytes_of(pinned16[0]) * E
+        ms16e, _, _ = timed(make_e2e_step(pinned16, True), e2e_steps, 1)
+        e2e["bf16_host_buffers"] = {"value": E * world * e2e_steps * rois_per_episode / (ms16e * 1e-3), "unit": "RoIs/s",
+                                    "h2d_bytes_per_step": int(h2d16), "host_layout": "channels_last bf16 pinned (bf16 variant, reported separately)",
+                                    "pcie_gbs_per_gpu": (h2d16 + d2h) * e2e_steps / (ms16e * 1e-3) / 1e9}
+        del pinned16
 
-    # ---- roofline of the dominant kernel: multi-level RoIAlign, timed alone on its stream
-    n_ext = len(cfg.strides)
+    # ---- rooflines.  (1) the dominant kernel: multi-level RoIAlign, timed alone on its stream
     scales = [1.0 / s for s in cfg.strides]
     alg_bytes = roi_align_algorithmic_bytes(cfg, host_eps[0]["rois"])
 
@@ -354,14 +485,68 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     achieved = alg_bytes / per_launch_s / 1e9
+
+    def committed(name):
+        """Per-launch figures of a committed ncu --set full capture (tools/ncu_summary.py --json)."""
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            return None
+
+    ncu_roi = committed("r02_ncu_roi_align_window.json") if cfg.name == WORKLOAD else None
     roofline = {"kernel": "roi_align_window_kernel<7,2,3,2> (level assignment + multi-level RoIAlign, NHWC in/out)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-                # (profiles/r01_roi_align_window_ncu.txt): 96.2 MB + 27.3 MB
-                "traffic": 123.4e6 if cfg.name == WORKLOAD else None}
+                "traffic": (ncu_roi or {}).get("traffic"),
+                "traffic_source": "profiles/r02_ncu_roi_align_window.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)" if ncu_roi else None}
+
+    # (2) the tensor-bound kernel: the relation head's contraction (split-weight count: (R + B*N) * 49 * C * C * 2 FLOP)
+    M_q = rois_per_episode * 49
+    a_q = [torch.randn(M_q, cfg.channels, device=device) for _ in range(4)]
+    w_q = head.cls_reg_shared_conv.weight.detach().reshape(cfg.channels, 2 * cfg.channels)[:, : cfg.channels]
+
+    def gemm_only():
+        for a in a_q:
+            ops.gemm_nt(a, w_q, None, "fp32")
+
+    with torch.no_grad():
+        gemm_only()
+        torch.cuda.synchronize()
+        gemm_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gemm_graph):
+            gemm_only()
+    ms_g, _, _ = timed(gemm_graph.replay, max(args.steps, 10), args.warmup)
+    g_s = ms_g * 1e-3 / (max(args.steps, 10) * len(a_q))
+    flops_split = 2.0 * M_q * cfg.channels * cfg.channels
+    ncu_gemm = committed("r02_ncu_gemm_tcgen05.json")
+    tf32_nominal = 1100.0
+    roofline_tensor = {"kernel": "gemm_tf32_tc_kernel<3,16> (relation conv as split-weight GEMM, tcgen05 kind::tf32, 3xTF32)",
+                       "bound": "tensor", "achieved": flops_split / g_s / 1e12, "unit": "TFLOP/s",
+                       "achieved_tensor_work": 3 * flops_split / g_s / 1e12, "peak": tf32_nominal,
+                       "frac": 3 * flops_split / g_s / 1e12 / tf32_nominal,
+                       "peak_source": "nominal dense TF32 (MEASURED_PEAKS.json holds bf16 only: %.0f TFLOP/s burst; TF32 runs at half the bf16 rate)" % float(peaks.get("bf16_tflops", 0.0)),
+                       "what": "achieved = split-weight FLOP count / time (SURVEY 8d); achieved_tensor_work counts the three TF32 passes of the fp32-parity scheme, frac = that / nominal TF32",
+                       "us_per_launch": g_s * 1e6, "M": M_q, "N": cfg.channels, "K": cfg.channels,
+                       "tensor_pipe_pct_of_active": (ncu_gemm or {}).get("tensor_pipe_pct_of_active"),
+                       "tensor_pipe_source": "profiles/r02_ncu_gemm_tcgen05.json" if ncu_gemm else None}
+    del a_q
+
+    # (3) the whole step against HBM: fused accounting (SURVEY 8d) -- every input map read once, every output written
+    #     once, RoI features and the split-conv output never counted (they are workspace traffic, not algorithmic)
+    q_bytes = sum(t.numel() * 4 for t in host_eps[0]["qry"])
+    s_bytes = sum(t.numel() * 4 for t in host_eps[0]["spp"]) + host_eps[0]["spp_masks"].numel()
+    step_bytes = ((1 + cfg.n_ways) * q_bytes                     # a1: read qry once, write N attended copies
+                  + s_bytes                                       # a1 vectors + a2 support branch: supports read once
+                  + (alg_bytes - rois_per_episode * cfg.channels * 49 * 4)   # a4/a5: unique footprint cells + rois
+                  + 2 * cfg.channels * cfg.channels * 4 + rois_per_episode * W5 * 4      # a6-a8: weights + logits
+                  + cfg.mask_rois * cfg.batch * cfg.channels * cfg.mask_size ** 2 * 4)   # a9: attended mask features out
+    step_s = ms * 1e-3 / (args.steps * E)
+    roofline_step = {"bound": "hbm", "accounting": "fused (RoI features / split-conv output not counted)",
+                     "algorithmic_bytes_per_episode": int(step_bytes), "us_per_episode": step_s * 1e6,
+                     "achieved": step_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s", "frac": step_bytes / step_s / 1e9 / peak,
+                     "peak_source": peak_src}
 
     # ---- bf16 variant, reported separately (bf16 NHWC maps + bf16 contraction operands; stated tolerance 3e-2
     #      abs on logits, see tests/test_gpu_parity.py::test_bf16_guided_path_variant)
@@ -385,7 +570,7 @@ def main():
         with torch.no_grad():
             a = run_guided_path(rpn, head, eps16[0])["cls_score"]
             b = run_guided_path(rpn, head, dev_eps[0])["cls_score"]
-        bf16_line = {"value": E * world * args.steps * cfg.num_rois * cfg.batch / (ms16 * 1e-3), "unit": "RoIs/s",
+        bf16_line = {"value": E * world * args.steps * rois_per_episode / (ms16 * 1e-3), "unit": "RoIs/s",
                      "ms_per_step": ms16 / args.steps, "max_abs_logit_diff_vs_fp32": float((a - b).abs().max()),
                      "stated_tolerance": 3e-2, "dtype": "bf16 maps/operands, f32 accumulate"}
         del runner16, eps16
@@ -398,6 +583,7 @@ def main():
         runner_f = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, with_attention="fold", n_streams=args.streams)
 
         def step_fold():
+            state["buf"] = res_single
             runner_f.begin()
             for i in range(E):
                 runner_f.run(i, sink)
@@ -405,7 +591,7 @@ def main():
 
         ms_f, _, _ = timed(step_fold, args.steps, args.warmup)
         l_f = sum(runner_f.launches_per_episode) * args.steps if runner_f.launches_per_episode else 0
-        fold_line = {"value": E * world * args.steps * cfg.num_rois * cfg.batch / (ms_f * 1e-3), "unit": "RoIs/s",
+        fold_line = {"value": E * world * args.steps * rois_per_episode / (ms_f * 1e-3), "unit": "RoIs/s",
                      "ms_per_step": ms_f / args.steps, "gpu_launches": int(l_f),
                      "what": "AG-RPN attention as rpn_conv weight sets (fgn_fold_attention_weights); attended pyramid not materialised"}
         del runner_f
@@ -414,18 +600,22 @@ def main():
         line = {"metric": "guided RoIAlign+fusion RoIs/s", "value": value, "unit": "RoIs/s",
                 "episodes_per_s": episodes / (ms * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "host_layout": "NCHW fp32 pinned"},
-                "gpu_launches": int(launches), "roofline": roofline, "bf16_variant": bf16_line,
-                "folded_attention_variant": fold_line}
+                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "parity": parity_line,
+                "e2e": e2e, "gpu_launches": int(launches),
+                "launches_per_episode": (runner.launches_per_episode[0] if runner.launches_per_episode else None),
+                "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_step": roofline_step,
+                "sustained": sustained, "strong_scaling": strong, "gather_overhead_w1": gather_w1,
+                "collective": (None if world == 1 else "all_gather_into_tensor of [E,R,5N+1] per step on a side stream, double-buffered, overlapped with the next step"),
+                "bf16_variant": bf16_line, "folded_attention_variant": fold_line,
+                "reference_arm_note": ("--impl reference runs the CPU path on rank 0 only: at N>1 the driver's ratio is N GPUs against ONE CPU process"
+                                       if world > 1 else "--impl reference: the oracle port on this box's host cores")}
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             n, dt = time_cpu_reference(cfg, 1, 1, 1)
             reps = max(1, min(20, int(args.cpu_seconds / max(dt, 1e-3)) - 1))
             if reps > 1:
                 n, dt = time_cpu_reference(cfg, reps, 0, 1)
-            v = n * cfg.num_rois * cfg.batch / dt
+            v = n * rois_per_episode / dt
             line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{n} episodes of {cfg.name}, {cpu_model()}, {time.perf_counter() - t0:.1f}s"}
         print(json.dumps(line))

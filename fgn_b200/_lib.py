@@ -52,6 +52,7 @@ SIGNATURES = {
     "fgn_mask_paste_rle_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_mask_paste_rle": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_float, c_int, c_int, _P, _P, _P, _P, c_int, c_int,
                                    _P, c_size_t, _P]),
+    "fgn_mask_rle_encode": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     "fgn_mask_paste": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
     "fgn_debug_roi_window_violations": (ctypes.c_uint, []),
     "fgn_map_roi_levels": (c_int, [_P, c_int, c_int, c_float, _P, _P]),

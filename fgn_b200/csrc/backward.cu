@@ -39,7 +39,7 @@ roi_align_bwd_kernel(const Pyramid pyr /* feat[l] = gradient buffer of level l, 
     if (t == 0) {
         const float *roi = rois + 5 * (size_t)r;
         const int lvl = roi_level(roi, pyr, finest_scale);
-        g_s = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
+        g_s = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned, pyr.B);
         plan.level = lvl; plan.batch = g_s.batch; plan.H = pyr.H[lvl]; plan.W = pyr.W[lvl];
         plan.count = g_s.count; plan.overflow = 0;
     }
@@ -239,7 +239,7 @@ extern "C" int fgn_roi_align_ml_bwd(const fgn_pyramid_t *grad_pyr, int B, int C,
     FGN_CHECK_ARG(rois && grad_out, "NULL pointer");
     for (int l = 0; l < grad_pyr->num_levels; ++l) FGN_CHECK_ARG(grad_pyr->feat[l], "gradient level %d is NULL", l);
     if (P != 7 && P != 14) { set_error("roi_align_bwd: P=%d not instantiated (7, 14)", P); return FGN_ERR_UNSUPPORTED; }
-    const Pyramid d = to_device_pyramid(grad_pyr);
+    const Pyramid d = to_device_pyramid(grad_pyr, B);
     int maxH = 0, maxW = 0;
     for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
     const int cap = (maxH + maxW + 6 * P + 16 + 3) & ~3;

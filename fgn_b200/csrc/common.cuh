@@ -55,8 +55,11 @@ struct RoiGeom {
     float count;
 };
 
+// `B` (images in the feature maps): a RoI whose batch index lies outside [0, B) -- a stale or corrupt rois[:,0] -- is
+// given an empty sampling grid: every forward kernel then writes zeros for it and the backward kernels add nothing,
+// instead of reading or writing out of bounds.  (The reference would raise an index error on the host.)
 __device__ __forceinline__ RoiGeom roi_geometry(const float *roi, float spatial_scale, int P,
-                                                int sampling_ratio, int aligned)
+                                                int sampling_ratio, int aligned, int B = 0x7fffffff)
 {
     RoiGeom g;
     const float off = aligned ? 0.5f : 0.0f;
@@ -72,6 +75,7 @@ __device__ __forceinline__ RoiGeom roi_geometry(const float *roi, float spatial_
     g.bin_w = __fdiv_rn(rw, (float)P);
     g.grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)P));
     g.grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)P));
+    if ((unsigned)g.batch >= (unsigned)B) { g.batch = 0; g.grid_h = g.grid_w = 0; }
     const int cnt = g.grid_h * g.grid_w;
     g.count = (float)(cnt > 1 ? cnt : 1);
     return g;
@@ -101,6 +105,7 @@ __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int gr
 // Pyramid by value in kernel parameter space.
 struct Pyramid {
     int          L;
+    int          B;                          // images per level (batch indices outside [0,B) pool zeros)
     const float *feat[FGN_MAX_LEVELS];
     int          H[FGN_MAX_LEVELS];
     int          W[FGN_MAX_LEVELS];
@@ -128,10 +133,11 @@ __device__ __forceinline__ int roi_level(const float *roi, const Pyramid &pyr, f
 
 void level_thresholds(float *thr /* [FGN_MAX_LEVELS] */);
 
-static inline Pyramid to_device_pyramid(const fgn_pyramid_t *p)
+static inline Pyramid to_device_pyramid(const fgn_pyramid_t *p, int B = 0x7fffffff)
 {
     Pyramid d;
     d.L = p->num_levels;
+    d.B = B > 0 ? B : 0x7fffffff;
     for (int i = 0; i < FGN_MAX_LEVELS; ++i) {
         d.feat[i]  = i < p->num_levels ? p->feat[i] : nullptr;
         d.H[i]     = i < p->num_levels ? p->H[i] : 0;

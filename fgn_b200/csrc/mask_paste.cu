@@ -259,19 +259,72 @@ mask_paste_walk_kernel(const float *__restrict__ mask_pred, const float *__restr
     }
 }
 
+// The same walk over GIVEN masks (encode_mask_results of the ground-truth qry_isegmaps, fgn.py:296-298): masks [D,H,W]
+// bytes (0 / non-zero), every pixel is walked, same chunk protocol, same encode kernel.
+__global__ void __launch_bounds__(kPasteThreads)
+mask_rle_walk_dense_kernel(const unsigned char *__restrict__ masks, const int H, const int W,
+                           int32_t *__restrict__ cursor, int32_t *__restrict__ chunk_off,
+                           int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ starts_ws, const int cap)
+{
+    __shared__ int warp_sums[kPasteThreads / 32];
+    __shared__ int chunk_base;
+    const int d = blockIdx.y, seg = blockIdx.x, G = gridDim.x * kPasteIters, tid = threadIdx.x;
+    const unsigned char *m = masks + (size_t)d * H * W;
+    int32_t *cnt = starts_ws + (size_t)d * cap;
+    const int nwc = (H + 31) >> 5;                     // words per column
+    const long long U = (long long)W * nwc;
+    const long long u_begin = (long long)seg * (kPasteIters * kPasteThreads);
+    if (u_begin >= U) return;
+    for (int it = 0; it < kPasteIters; ++it) {
+        const long long u0 = u_begin + (long long)it * kPasteThreads;
+        if (u0 >= U) break;
+        const long long u = u0 + tid;
+        unsigned starts = 0u;
+        int x = 0, yw = 0;
+        if (u < U) {
+            x = (int)(u / nwc);
+            yw = 32 * (int)(u - (long long)x * nwc);
+            const bool prev = yw > 0 ? m[(size_t)(yw - 1) * W + x] != 0 : (x > 0 ? m[(size_t)(H - 1) * W + x - 1] != 0 : false);
+            unsigned bits = 0u;
+            const int n = min(32, H - yw);
+            for (int k = 0; k < n; ++k) bits |= (m[(size_t)(yw + k) * W + x] != 0 ? 1u : 0u) << k;
+            starts = bits ^ ((bits << 1) | (prev ? 1u : 0u));
+            if (n < 32) starts &= (1u << max(n, 0)) - 1u;
+        }
+        int total;
+        int pos = block_scan_excl(__popc(starts), warp_sums, total);
+        if (tid == 0) {
+            const int at = total > 0 ? atomicAdd(&cursor[d], total) : 0;
+            chunk_base = at;
+            chunk_off[(size_t)d * G + seg * kPasteIters + it] = at;
+            chunk_cnt[(size_t)d * G + seg * kPasteIters + it] = total;
+        }
+        __syncthreads();
+        pos += chunk_base;
+        while (starts != 0u) {
+            const int k = __ffs(starts) - 1;
+            starts &= starts - 1u;
+            if (pos < cap - 1) cnt[pos] = (int32_t)((long long)x * H + yw + k);
+            ++pos;
+        }
+        __syncthreads();
+    }
+}
+
 // Encode kernel, grid D: orders the chunks of a detection, turns run starts into run lengths and writes the string.
 __global__ void __launch_bounds__(kPasteThreads)
 mask_paste_encode_kernel(const int32_t *__restrict__ det_img, const int32_t *__restrict__ img_hw,
                          const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ chunk_cnt,
                          const int32_t *__restrict__ starts_ws, const int G, int32_t *__restrict__ counts_out,
                          int32_t *__restrict__ ncounts_out, unsigned char *__restrict__ str_out,
-                         int32_t *__restrict__ strlen_out, const int cap, const int cap_bytes)
+                         int32_t *__restrict__ strlen_out, const int cap, const int cap_bytes,
+                         const int fixed_h, const int fixed_w)
 {
     __shared__ int warp_sums[kPasteThreads / 32];
     __shared__ int prefix[kPasteMaxChunks];            // exclusive prefix of the chunk sizes, chunk order
     const int d = blockIdx.x, tid = threadIdx.x;
     const int im = det_img != nullptr ? det_img[d] : 0;
-    const int H = img_hw[2 * im], W = img_hw[2 * im + 1];
+    const int H = img_hw != nullptr ? img_hw[2 * im] : fixed_h, W = img_hw != nullptr ? img_hw[2 * im + 1] : fixed_w;
     int32_t *cnt = counts_out + (size_t)d * cap;
     if (H <= 0 || W <= 0) {                            // empty image: pycocotools emits no run
         if (tid == 0) { ncounts_out[d] = 0; if (strlen_out != nullptr) strlen_out[d] = 0; }
@@ -410,7 +463,34 @@ extern "C" int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, in
                                                                       mask_thr, cursor, chunk_off, chunk_cnt, starts, cap);
     FGN_LAUNCH_OK();
     mask_paste_encode_kernel<<<D, kPasteThreads, 0, st>>>(det_img, img_hw, chunk_off, chunk_cnt, starts, G, counts_out,
-                                                          ncounts_out, str_out, strlen_out, cap, cap_bytes);
+                                                          ncounts_out, str_out, strlen_out, cap, cap_bytes, 0, 0);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+extern "C" int fgn_mask_rle_encode(const unsigned char *masks, int D, int H, int W, int32_t *counts_out,
+                                   int32_t *ncounts_out, unsigned char *str_out, int32_t *strlen_out, int cap,
+                                   int cap_bytes, void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(D >= 0 && H >= 0 && W >= 0, "bad dims D=%d H=%d W=%d", D, H, W);
+    if (D == 0) return FGN_OK;
+    FGN_CHECK_ARG(masks && counts_out && ncounts_out, "NULL pointer");
+    FGN_CHECK_ARG(cap >= 2 && D <= 65535, "cap=%d D=%d", cap, D);
+    FGN_CHECK_ARG(str_out == nullptr || (strlen_out != nullptr && cap_bytes >= 1), "str_out needs strlen_out and cap_bytes");
+    const int segs = paste_segments(max(H, 1), max(W, 1)), G = segs * kPasteIters;
+    FGN_CHECK_ARG(G <= kPasteMaxChunks, "image %dx%d needs %d chunks per mask (max %d)", H, W, G, kPasteMaxChunks);
+    const size_t need = fgn_mask_paste_rle_workspace_bytes(D, cap, max(H, 1), max(W, 1));
+    FGN_CHECK_ARG(workspace && workspace_bytes >= need, "workspace %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *cursor = static_cast<int32_t *>(workspace);
+    int32_t *chunk_off = cursor + D, *chunk_cnt = chunk_off + (size_t)D * G, *starts = chunk_cnt + (size_t)D * G;
+    FGN_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)D * (1 + 2 * (size_t)G) * sizeof(int32_t), st));
+    if (H > 0 && W > 0) {
+        mask_rle_walk_dense_kernel<<<dim3(segs, D), kPasteThreads, 0, st>>>(masks, H, W, cursor, chunk_off, chunk_cnt, starts, cap);
+        FGN_LAUNCH_OK();
+    }
+    mask_paste_encode_kernel<<<D, kPasteThreads, 0, st>>>(nullptr, nullptr, chunk_off, chunk_cnt, starts, G, counts_out,
+                                                          ncounts_out, str_out, strlen_out, cap, cap_bytes, H, W);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

@@ -41,7 +41,7 @@ __global__ void roi_align_direct_kernel(const Pyramid pyr, const int C, const in
         const int r = idx / ((size_t)P * P * C);
         const float *roi = rois + 5 * (size_t)r;
         const int lvl = roi_level(roi, pyr, finest_scale);
-        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
+        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned, pyr.B);
         const int H = pyr.H[lvl], W = pyr.W[lvl];
         if (lvl_out != nullptr && c == 0 && ph == 0 && pw == 0) lvl_out[r] = lvl;
         const float *f = pyr.feat[lvl];
@@ -97,7 +97,7 @@ __global__ void roi_align_sample_indices_kernel(const Pyramid pyr, const float *
         const int p = (rem / max_grid) % P, i = rem % max_grid;
         const float *roi = rois + 5 * (size_t)r;
         const int lvl = roi_level(roi, pyr, finest_scale);
-        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned);
+        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned, pyr.B);
         if (rem == 0) {
             if (lvl_out) lvl_out[r] = lvl;
             grid_out[2 * r] = g.grid_h; grid_out[2 * r + 1] = g.grid_w;
@@ -190,7 +190,7 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     if (R == 0) return FGN_OK;
     FGN_CHECK_ARG(rois && out, "NULL pointer");
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
-    const Pyramid d = to_device_pyramid(pyr);
+    const Pyramid d = to_device_pyramid(pyr, B);
     cudaStream_t st = (cudaStream_t)stream;
     // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
     // 2 = row-streaming kernel (one CTA per RoI: NCHW output and the shapes the window kernel declines), 0 = direct
@@ -240,10 +240,13 @@ extern "C" int fgn_roi_align_ml_fwd_direct(const fgn_pyramid_t *pyr, int B, int 
 {
     int rc = validate_pyramid(pyr);
     if (rc) return rc;
-    FGN_CHECK_ARG(R >= 0 && C > 0 && P > 0, "bad dims");
-    (void)B;
+    FGN_CHECK_ARG(R >= 0 && B >= 0 && C > 0 && P > 0, "bad dims R=%d B=%d C=%d P=%d", R, B, C, P);
+    FGN_CHECK_ARG(in_layout == FGN_LAYOUT_NCHW || in_layout == FGN_LAYOUT_NHWC, "in_layout=%d", in_layout);
+    FGN_CHECK_ARG(out_layout == FGN_LAYOUT_NCHW || out_layout == FGN_LAYOUT_NHWC, "out_layout=%d", out_layout);
     if (R == 0) return FGN_OK;
-    const Pyramid d = to_device_pyramid(pyr);
+    FGN_CHECK_ARG(rois && out, "NULL pointer");
+    for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
+    const Pyramid d = to_device_pyramid(pyr, B);
     const size_t total = (size_t)R * C * P * P;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
     roi_align_direct_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -285,7 +288,7 @@ extern "C" int fgn_roi_align_ml_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C,
     if (R == 0) return FGN_OK;
     FGN_CHECK_ARG(rois && out, "NULL pointer");
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
-    const Pyramid d = to_device_pyramid(pyr);
+    const Pyramid d = to_device_pyramid(pyr, B);
     return launch_roi_align_stream_bf16(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                         scale_index, out, out_is_bf16, lvl_out, (cudaStream_t)stream);
 }

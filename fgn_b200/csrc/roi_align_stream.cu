@@ -87,7 +87,7 @@ __device__ __forceinline__ WarpPlan warp_plan(const Pyramid &pyr, const float *_
     WarpPlan wp;
     const float *roi = rois + 5 * (size_t)r;
     wp.level = roi_level(roi, pyr, finest_scale);
-    wp.g = roi_geometry(roi, pyr.scale[wp.level], P, sampling_ratio, aligned);
+    wp.g = roi_geometry(roi, pyr.scale[wp.level], P, sampling_ratio, aligned, pyr.B);
     wp.H = pyr.H[wp.level]; wp.W = pyr.W[wp.level];
     const int axis = lane / P, p = lane % P;
     int lo = 0x7fffffff, hi = -1;

@@ -209,7 +209,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
     auto size_class = [&](const float *roi) {                            // 0 = largest footprints ... 3 = smallest (NaN -> 3)
         const int lv = roi_level(roi, pyr, finest_scale);
-        const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned);
+        const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned, pyr.B);
         const float est = (gg.bin_h * (float)P + 2.f) * (gg.bin_w * (float)P + 2.f);   // cells, from the box alone
         return est > thr.x ? 0 : (est > thr.y ? 1 : (est > thr.z ? 2 : 3));
     };
@@ -341,7 +341,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             trace(debug_mode, k, 0, lane);
             const float *roi = rois + 5 * (size_t)r;
             const int level = roi_level(roi, pyr, finest_scale);
-            const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned);
+            const RoiGeom g = roi_geometry(roi, pyr.scale[level], P, sampling_ratio, aligned, pyr.B);
             const int H = pyr.H[level], W = pyr.W[level];
             // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
             // as items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)

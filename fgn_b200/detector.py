@@ -73,11 +73,17 @@ class FGN(nn.Module):
                                          spp_fmaps=spp_fmaps, spp_bboxes=spp_bboxes, spp_isegmaps=spp_isegmaps)
 
     @staticmethod
-    def format_results(outputs_all) -> List[dict]:
-        """fgn.py:262-303, the detector's own part of the per-image result dict consumed by FSISEGEval
-        (fsisegeval.py:51-104): ``dt_scores`` [D], ``dt_bboxes`` [D,4] back in the dataset's YXYX order
-        (fgn.py:275), ``dt_cat_ids`` [D], ``dt_isegmaps_rle`` (COCO RLE dicts, fgn.py:281) as numpy / bytes.
-        ``outputs_all`` = what ``simple_test`` returned: (det_bboxes, det_labels[, mask-branch dict])."""
+    def format_results(outputs_all, inputs_all: Optional[dict] = None) -> List[dict]:
+        """fgn.py:262-303: the per-image result dicts consumed by FSISEGEval (fsisegeval.py:51-104).
+        ``outputs_all`` = what ``simple_test`` returned: (det_bboxes, det_labels[, mask-branch dict]);
+        ``inputs_all`` = the batch-level inputs the reference copies through (fgn.py:242-260: ``qry_img_id``,
+        ``qry_bboxes``, ``qry_cat_ids``, ``qry_isegmaps``, ``qry_child_idx``, ``cats_ids_to_sample_real``,
+        ``spp_insts_ids`` ...), each indexable by image.  Per image: ``dt_scores`` [D], ``dt_bboxes`` [D,4] back in
+        the dataset's YXYX order (fgn.py:275), ``dt_cat_ids`` [D], ``dt_isegmaps_rle`` (COCO RLE dicts, fgn.py:281),
+        every input key of that image (fgn.py:284-285), tensors as numpy (fgn.py:287-291), and
+        ``qry_isegmaps`` replaced by ``qry_isegmaps_rle`` (fgn.py:297-299; device masks are encoded on the device by
+        ops.mask_rle_encode, never copied to the host as dense masks)."""
+        from . import ops
         det_bboxes, det_labels = outputs_all[0], outputs_all[1]
         rles = outputs_all[2].get("segm_rles") if len(outputs_all) > 2 and isinstance(outputs_all[2], dict) else None
         out = []
@@ -87,6 +93,56 @@ class FGN(nn.Module):
                        dt_cat_ids=dl.detach().cpu().numpy().reshape(-1))
             if rles is not None:
                 one["dt_isegmaps_rle"] = rles[i]
+            for key in (inputs_all or {}):
+                one[key] = inputs_all[key][i]
+            if "qry_isegmaps" in one:
+                qm = one.pop("qry_isegmaps")
+                if torch.is_tensor(qm) and qm.is_cuda:
+                    one["qry_isegmaps_rle"] = ops.mask_rle_encode(qm.reshape(-1, qm.shape[-2], qm.shape[-1]))
+                else:                                  # host masks: move them once, encode on the device
+                    qt = torch.as_tensor(qm)
+                    dev = det_bboxes[i].device
+                    one["qry_isegmaps_rle"] = ops.mask_rle_encode(qt.reshape(-1, qt.shape[-2], qt.shape[-1]).to(dev)) \
+                        if dev.type == "cuda" else None
+            for key, value in list(one.items()):
+                if torch.is_tensor(value):
+                    one[key] = value.detach().cpu().numpy()
             out.append(one)
         return out
 
+
+class ChunkedResultWriter:
+    """The evaluation hook's on-disk format (main.py:285-309): results accumulate over ``simple_test`` calls and are
+    written as ``ResultsChunked/NN.pkl`` every ``chunk`` (1000) items and at the end.  ``add`` takes the list
+    ``FGN.format_results`` returns; ``close`` flushes the remainder.  Returns / keeps the written paths."""
+
+    def __init__(self, work_dir: str, chunk: int = 1000, subdir: str = "ResultsChunked"):
+        import os
+        self.dir = os.path.join(work_dir, subdir)
+        os.makedirs(self.dir, exist_ok=True)
+        self.chunk, self.results, self.counter, self.paths = int(chunk), [], 0, []
+
+    def _flush(self):
+        import os
+        import pickle
+        path = os.path.join(self.dir, f"{self.counter:02}.pkl")
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:                     # write_pkl_safe: never leave a half-written chunk behind
+            pickle.dump(self.results, f, protocol=pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, path)
+        self.paths.append(path)
+        self.counter += 1
+        self.results = []
+
+    def add(self, results) -> None:
+        if isinstance(results, dict):
+            results = [results]
+        for r in results:
+            self.results.append(r)
+            if len(self.results) == self.chunk:
+                self._flush()
+
+    def close(self) -> List[str]:
+        if self.results:
+            self._flush()
+        return self.paths

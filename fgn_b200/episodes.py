@@ -283,18 +283,87 @@ def shard_range(num_episodes: int, world_size: int, rank: int) -> Tuple[int, int
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_results(local: torch.Tensor, num_episodes: int, group=None) -> torch.Tensor:
+def gather_results(local: torch.Tensor, num_episodes: int, group=None, force: bool = False) -> torch.Tensor:
     """all_gather of per-episode results [E_local, ...] -> [E, ...] on every rank (NCCL on GPU, gloo
-    in the CPU tests).  Blocks may differ by one episode, so they are padded to the largest block."""
+    in the CPU tests).  Blocks may differ by one episode, so they are padded to the largest block.
+    ``force``: run the collective even in a one-rank group (harness-overhead measurement)."""
     import torch.distributed as dist
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    if not dist.is_available() or not dist.is_initialized() or (dist.get_world_size(group) == 1 and not force):
         return local
     world = dist.get_world_size(group)
     sizes = [shard_range(num_episodes, world, r) for r in range(world)]
     emax = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == emax for lo, hi in sizes) and local.shape[0] == emax:     # equal blocks: no pad, no cat
+        out = local.new_empty((world * emax,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = local.new_zeros((emax,) + tuple(local.shape[1:]))
     pad[: local.shape[0]] = local
     out = local.new_empty((world * emax,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, pad, group=group)
     chunks = [out[r * emax: r * emax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
     return torch.cat(chunks, 0)
+
+
+class ResultGatherer:
+    """Overlapped result gather ("issue the gather on a side stream while the next episode block
+    computes").  Every rank owns ``depth`` staging buffers [E_local, ...] and as many gathered buffers
+    [world * E_local, ...], all allocated once.  Per step: the caller fills ``local(k)`` on its compute stream and
+    calls ``submit(k)``; the all_gather of step k then runs on a side stream while step k+1 computes, and
+    ``local(k + depth)`` waits for it before the buffer is overwritten.  Equal blocks per rank (the benchmark's
+    case) make the gathered buffer the result itself: no pad, no cat, no allocation inside the timed region.
+    Works in a one-rank group too (``force=True`` path of the harness-overhead measurement)."""
+
+    def __init__(self, shape, device, dtype=torch.float32, depth: int = 2, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.depth = depth
+        self.locals = [torch.empty(tuple(shape), device=device, dtype=dtype) for _ in range(depth)]
+        self.outs = [torch.empty((self.world * shape[0],) + tuple(shape[1:]), device=device, dtype=dtype)
+                     for _ in range(depth)]
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if self.cuda else None
+        self.ready = [torch.cuda.Event() for _ in range(depth)] if self.cuda else []      # local(k) filled
+        self.done = [torch.cuda.Event() for _ in range(depth)] if self.cuda else []       # gather of k finished
+        self.pending = [False] * depth
+
+    def local(self, k: int) -> torch.Tensor:
+        """Staging buffer of step k; the caller's stream first waits for the gather that last read it."""
+        i = k % self.depth
+        if self.cuda and self.pending[i]:
+            torch.cuda.current_stream().wait_event(self.done[i])
+            self.pending[i] = False
+        return self.locals[i]
+
+    def submit(self, k: int) -> torch.Tensor:
+        """Start the gather of step k (asynchronous on GPU); returns the buffer it lands in."""
+        i = k % self.depth
+        if not self.dist.is_initialized():
+            self.outs[i].copy_(self.locals[i])
+            return self.outs[i]
+        if not self.cuda:
+            self.dist.all_gather_into_tensor(self.outs[i], self.locals[i], group=self.group)
+            return self.outs[i]
+        self.ready[i].record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ready[i])
+            self.dist.all_gather_into_tensor(self.outs[i], self.locals[i], group=self.group)
+            self.done[i].record(self.side)
+        self.pending[i] = True
+        return self.outs[i]
+
+    def result(self, k: int) -> torch.Tensor:
+        """Gathered results of step k, valid on the caller's stream."""
+        i = k % self.depth
+        if self.cuda and self.pending[i]:
+            torch.cuda.current_stream().wait_event(self.done[i])
+        return self.outs[i]
+
+    def drain(self) -> None:
+        """The caller's stream waits for every gather in flight (end of a timed region)."""
+        if self.cuda:
+            for i in range(self.depth):
+                if self.pending[i]:
+                    torch.cuda.current_stream().wait_event(self.done[i])
+                    self.pending[i] = False

@@ -20,12 +20,38 @@ from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, FgnError, Pyramid
 __all__ = [
     "map_roi_levels", "roi_align_multilevel", "roi_align_sample_indices", "to_nhwc", "support_mask_pool",
     "support_pool", "attention_vectors", "channel_attention", "attention_multilevel", "best_class_select",
-    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count",
+    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count", "mask_rle_encode",
 ]
 
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_CONST_CACHE: "dict" = {}
+
+
+def _const_tensor(values, dtype: torch.dtype, device) -> torch.Tensor:
+    """A small constant (per-image offsets, image sizes, scale factors) as a PERSISTENT device tensor.
+
+    These used to be staged through temporary pinned tensors; a CUDA-graph capture of that copy bakes the pinned
+    host pointer into the graph, and the temporary goes back to the allocator right after capture -- a later replay
+    would read whatever occupies the block by then.  Here the device tensor itself is kept (keyed by its values), so
+    a captured kernel reads memory that stays valid and constant; a value set first seen during capture raises instead
+    of capturing a host copy (warm up once before capturing, as torch.cuda.graph requires anyway)."""
+    dev = torch.device(device)
+    flat = tuple(float(v) if dtype.is_floating_point else int(v) for v in torch.as_tensor(values).reshape(-1).tolist())
+    shape = tuple(torch.as_tensor(values).shape)
+    key = (dev.type, dev.index, dtype, shape, flat)
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise FgnError("constant operands first seen during CUDA-graph capture: run the call once before capturing")
+        if len(_CONST_CACHE) > 4096:
+            _CONST_CACHE.clear()
+        t = torch.tensor(flat, dtype=dtype).reshape(shape).to(dev)
+        _CONST_CACHE[key] = t
+    return t
 
 
 def _need_cuda(*ts: torch.Tensor) -> None:
@@ -580,15 +606,13 @@ def det_postprocess(rois: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torc
         acc += int(x)
         offs.append(acc)
     rmax = max(int(x) for x in num_per_img)
-    off_t = torch.tensor(offs, dtype=torch.int32, pin_memory=True).to(dev, non_blocking=True)   # (pinned: graph-capturable)
+    off_t = _const_tensor(offs, torch.int32, dev)           # persistent device constants (see _const_tensor)
     hw_t = None
     if img_shapes is not None:
-        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32,
-                            pin_memory=True).to(dev, non_blocking=True)
+        hw_t = _const_tensor([[float(s[0]), float(s[1])] for s in img_shapes], torch.float32, dev)
     sf_t = None
     if scale_factors is not None:
-        sf_t = torch.tensor([[float(v) for v in s] for s in scale_factors], dtype=torch.float32,
-                            pin_memory=True).reshape(b, 4).to(dev, non_blocking=True)
+        sf_t = _const_tensor([[float(v) for v in s][:4] for s in scale_factors], torch.float32, dev).reshape(b, 4)
     lib = _lib.load()
     nbytes = int(lib.fgn_det_postprocess_workspace_bytes(r, n, b, rmax))
     ws = torch.empty((max(nbytes, 256),), device=dev, dtype=torch.uint8)
@@ -633,8 +657,8 @@ def rpn_proposals(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch
             raise FgnError(f"rpn_proposals: cls {tuple(c.shape)} / reg {tuple(r.shape)} do not match B={b} A={a}")
     dev = cls_scores[0].device
     anchors = _f32(anchors, "anchors").reshape(nl, a, 4).contiguous()
-    if anchors.device != dev:                                    # (pinned staging: graph-capturable)
-        anchors = anchors.pin_memory().to(dev, non_blocking=True)
+    if anchors.device != dev:
+        anchors = _const_tensor(anchors, torch.float32, dev)
     hs = (ctypes.c_int * nl)(*[int(c.shape[2]) for c in cls_scores])
     wsz = (ctypes.c_int * nl)(*[int(c.shape[3]) for c in cls_scores])
     st = (ctypes.c_int * nl)(*[int(s) for s in strides])
@@ -642,8 +666,7 @@ def rpn_proposals(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch
     rp = (ctypes.c_void_p * nl)(*[r.data_ptr() for r in bbox_preds])
     hw_t = None
     if img_shapes is not None:
-        hw_t = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32,
-                            pin_memory=True).to(dev, non_blocking=True)
+        hw_t = _const_tensor([[float(s[0]), float(s[1])] for s in img_shapes], torch.float32, dev)
     prop = torch.empty((b, max_per_img, 5), device=dev, dtype=torch.float32)
     lvl = torch.empty((b, max_per_img), device=dev, dtype=torch.int32)
     cnt = torch.empty((b,), device=dev, dtype=torch.int32)
@@ -694,7 +717,7 @@ def mask_paste_rle(mask_pred: torch.Tensor, boxes: torch.Tensor, img_hw: Sequenc
     if d == 0:
         return ([], []) if return_counts else []
     dev = mask_pred.device
-    hw_t = torch.tensor(hw, dtype=torch.int32, pin_memory=True).to(dev, non_blocking=True)
+    hw_t = _const_tensor(hw, torch.int32, dev)
     if det_img is not None:
         det_img = det_img.to(torch.int32).contiguous()
         img_of = det_img.tolist()
@@ -726,4 +749,40 @@ def mask_paste_rle(mask_pred: torch.Tensor, boxes: torch.Tensor, img_hw: Sequenc
         return rles
     cmax = max(nc)
     ch = counts[:, :max(cmax, 1)].cpu().numpy()
+    return rles, [ch[i, :nc[i]].tolist() for i in range(d)]
+
+
+def mask_rle_encode(masks: torch.Tensor, cap: int = 4096, return_counts: bool = False):
+    """mmdet.core.encode_mask_results / pycocotools mask.encode [3P] of given masks (fgn.py:296-298, the
+    ``qry_isegmaps`` of the result dict): ``masks`` [D,H,W] bool / uint8 on the device -> list of
+    ``dict(size=[H, W], counts=bytes)``; with ``return_counts`` also the uncompressed run lengths."""
+    _need_cuda(masks)
+    if masks.dim() != 3:
+        raise FgnError(f"masks {tuple(masks.shape)}: expected [D,H,W]")
+    m8 = masks.contiguous().view(torch.uint8) if masks.dtype == torch.bool else masks.to(torch.uint8).contiguous()
+    d, h, w = m8.shape
+    if d == 0:
+        return ([], []) if return_counts else []
+    dev = m8.device
+    lib = _lib.load()
+    while True:
+        cap_bytes = 2 * cap
+        counts = torch.empty((d, cap), device=dev, dtype=torch.int32)
+        ncounts = torch.empty((d,), device=dev, dtype=torch.int32)
+        sbuf = torch.empty((d, cap_bytes), device=dev, dtype=torch.uint8)
+        slen = torch.empty((d,), device=dev, dtype=torch.int32)
+        wsb = int(lib.fgn_mask_paste_rle_workspace_bytes(d, cap, max(h, 1), max(w, 1)))
+        ws = torch.empty((max(wsb, 4),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.fgn_mask_rle_encode(_ptr(m8), d, h, w, _ptr(counts), _ptr(ncounts), _ptr(sbuf), _ptr(slen), cap, cap_bytes,
+                                           ws.data_ptr(), wsb, _stream()), "fgn_mask_rle_encode")
+        nc, sl = ncounts.tolist(), slen.tolist()
+        need = max([-v for v in nc] + [(-v + 1) // 2 for v in sl] + [0])
+        if need == 0:
+            break
+        cap = max(2 * cap, need + 16)
+    sbytes = sbuf[:, :max(max(sl), 1)].cpu().numpy()
+    rles = [dict(size=[h, w], counts=sbytes[i, :sl[i]].tobytes()) for i in range(d)]
+    if not return_counts:
+        return rles
+    ch = counts[:, :max(max(nc), 1)].cpu().numpy()
     return rles, [ch[i, :nc[i]].tolist() for i in range(d)]

@@ -311,6 +311,13 @@ int fgn_mask_paste_rle(const float *mask_pred, const float *boxes, int box_strid
                        int32_t *strlen_out, int cap, int cap_bytes,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* encode_mask_results of GIVEN masks (fgn.py:296-298: the ground-truth qry_isegmaps travel in the result dict as COCO
+ * RLE, pycocotools mask.encode [3P]): masks [D,H,W] bytes (0 / non-zero) -> the same outputs as fgn_mask_paste_rle,
+ * through the same run-length / string encoder.  workspace: fgn_mask_paste_rle_workspace_bytes(D, cap, H, W). */
+int fgn_mask_rle_encode(const unsigned char *masks, int D, int H, int W, int32_t *counts_out, int32_t *ncounts_out,
+                        unsigned char *str_out, int32_t *strlen_out, int cap, int cap_bytes,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* get_seg_masks' own return value for one image: out [D,img_h,img_w] bytes (0/1). */
 int fgn_mask_paste(const float *mask_pred, const float *boxes, int box_stride, int D, int M, int img_h,
                    int img_w, float mask_thr, unsigned char *out, void *stream);

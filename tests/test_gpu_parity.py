@@ -315,6 +315,39 @@ def test_roi_align_edge_cases():
     assert (out[0] == 0).all()
 
 
+def test_roi_batch_index_outside_the_batch_pools_zeros():
+    """A stale / corrupt rois[:,0] (negative, == B, huge) never reads or writes out of bounds: every forward kernel
+    returns zeros for that RoI, the backward adds nothing, the other RoIs are untouched."""
+    from fgn_b200 import autograd as A
+    from fgn_b200 import ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(5)
+    B, C = 2, 256
+    strides = [4, 8, 16, 32]
+    feats = [torch.randn(B, C, 128 // s, 160 // s, generator=g).to(dev()).contiguous(memory_format=torch.channels_last) for s in strides]
+    scales = [1 / s for s in strides]
+    rois = synth_rois(g, 64, 128, 160, B, smin=8.0).to(dev())
+    good = ops.roi_align_multilevel(feats, rois, scales, 7, 0, True, out_format="nhwc")
+    bad = rois.clone()
+    bad_rows = torch.tensor([3, 17, 40, 63], device=dev())
+    bad[bad_rows, 0] = torch.tensor([-1.0, float(B), 1.0e6, -3.0e9], device=dev())
+    for kw in (dict(out_format="nhwc"), dict(out_format="nchw"), dict(out_format="nhwc", force_direct=True)):
+        got = ops.roi_align_multilevel(feats, bad, scales, 7, 0, True, **kw)
+        assert (got[bad_rows] == 0).all(), kw
+        keep = torch.ones(64, dtype=torch.bool, device=dev())
+        keep[bad_rows] = False
+        want = good if kw.get("out_format") == "nhwc" and not kw.get("force_direct") else \
+            ops.roi_align_multilevel(feats, rois, scales, 7, 0, True, **kw)
+        assert torch.equal(got[keep], want[keep]), kw
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    A.roi_align_multilevel(fr, bad, scales, 7, 0, True).sum().backward()
+    fr2 = [f.clone().requires_grad_(True) for f in feats]
+    keep_rois = bad[torch.tensor([i for i in range(64) if i not in (3, 17, 40, 63)], device=dev())]
+    A.roi_align_multilevel(fr2, keep_rois, scales, 7, 0, True).sum().backward()
+    for a, b in zip(fr, fr2):
+        assert torch.allclose(a.grad, b.grad, atol=1e-5, rtol=1e-5)
+
+
 # ---- full-size, size-independent properties (cfg3 pyramid) ---------------------------------------
 def test_full_size_properties_cfg3():
     from fgn_b200 import ops

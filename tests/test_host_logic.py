@@ -115,3 +115,74 @@ def test_gather_results_world_size_2_gloo(num_episodes):
     want = np.stack([np.full((3, 2), float(e)) + np.arange(6).reshape(3, 2) for e in range(num_episodes)])
     for r in range(2):
         assert np.array_equal(got[r], want)      # world-size-2 result == unsharded result, on every rank
+
+
+def _gatherer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = E.ResultGatherer((3, 4, 2), "cpu", depth=2)
+    outs = []
+    for k in range(5):                                     # five steps through two rotating buffers
+        buf = g.local(k)
+        buf.copy_(torch.arange(24, dtype=torch.float32).view(3, 4, 2) + 100 * rank + 1000 * k)
+        g.submit(k)
+        outs.append(g.result(k).clone())
+    g.drain()
+    q.put((rank, torch.stack(outs).numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_result_gatherer_world_size_2_gloo():
+    """The overlapped gatherer (double-buffered, preallocated, no pad / cat for equal blocks) returns rank-major
+    blocks on every rank, step after step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    base = np.arange(24, dtype=np.float32).reshape(3, 4, 2)
+    want = np.stack([np.concatenate([base + 100 * r + 1000 * k for r in range(2)]) for k in range(5)])
+    for r in range(2):
+        assert np.array_equal(got[r], want)
+
+
+def test_gather_results_force_in_a_one_rank_group():
+    """world size 1 with the collective forced (the harness-overhead measurement of SURVEY 8e) is the identity."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_force_worker, args=(_free_port(), q))
+    p.start()
+    out = q.get(timeout=120)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    assert np.array_equal(out, np.arange(12, dtype=np.float32).reshape(2, 3, 2))
+
+
+def _force_worker(port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    x = torch.arange(12, dtype=torch.float32).view(2, 3, 2)
+    q.put(E.gather_results(x, 2, force=True).numpy())
+    dist.destroy_process_group()
+
+
+def test_chunked_result_writer_matches_the_eval_hook_layout(tmp_path):
+    """main.py:285-309: results are dumped as ResultsChunked/NN.pkl every 1000 items and once more at the end."""
+    import pickle
+    from fgn_b200.detector import ChunkedResultWriter
+    w = ChunkedResultWriter(str(tmp_path), chunk=4)
+    for i in range(10):
+        w.add([dict(qry_img_id=i, dt_scores=np.arange(i, dtype=np.float32))])       # one simple_test call = a list
+    paths = w.close()
+    assert [os.path.basename(p) for p in paths] == ["00.pkl", "01.pkl", "02.pkl"]
+    assert os.path.dirname(paths[0]).endswith("ResultsChunked")
+    got = [r for p in paths for r in pickle.load(open(p, "rb"))]
+    assert [len(pickle.load(open(p, "rb"))) for p in paths] == [4, 4, 2]
+    assert [r["qry_img_id"] for r in got] == list(range(10))
+    assert w.close() == paths                                                       # nothing left to flush
