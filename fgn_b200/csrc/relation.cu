@@ -171,6 +171,11 @@ __global__ void roi_batch_kernel(const float *__restrict__ rois, int R, int32_t 
     if (r < R) out[r] = (int)rois[5 * (size_t)r];
 }
 
+int relation_fused_tc(const float *Xq, const float *Wq, int ldw, const float *Ys, const int32_t *roi_batch, int R, int B,
+                      int N, int C, float eps, const float *gn_w, const float *gn_b, const float *fc_cls_w,
+                      const float *fc_cls_b, const float *fc_reg_w, const float *fc_reg_b, float *cls_out,
+                      float *reg_out, float *raw_cls, float *raw_reg, float *split_ws, cudaStream_t st, bool *taken);
+
 struct RelationWs {
     float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc, *split_q, *split_s;
     size_t bytes;
@@ -245,10 +250,19 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
         if (rc) return rc;
         xq = w.xq_nhwc; xs = w.xs_nhwc;
     }
-    // Yq = Xq Wq^T ; Ys = Xs Ws^T + bias        (conv_w is [C, 2C] row-major)
-    int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, w.split_q, st);
+    // Ys = Xs Ws^T + bias: the class term, once per class       (conv_w is [C, 2C] row-major)
+    int rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, w.split_s, st);
     if (rc) return rc;
-    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, w.split_s, st);
+    // FPN shapes at fp32 parity: the query half of the conv, GroupNorm, ReLU, pool, FC heads and the score re-assembly
+    // in ONE tcgen05 kernel whose epilogue works out of tensor memory (gemm_tc.cu: relation_fused_tc_kernel)
+    if (precision == 0 && gn_groups == 32) {
+        bool taken = false;
+        rc = relation_fused_tc(xq, conv_w, 2 * C, w.ys, roi_batch, R, B, N, C, gn_eps, gn_w, gn_b, fc_cls_w, fc_cls_b,
+                               fc_reg_w, fc_reg_b, cls_out, reg_out, raw_cls_out, raw_reg_out, w.split_q, st, &taken);
+        if (rc || taken) return rc;
+    }
+    // Yq = Xq Wq^T
+    rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, w.split_q, st);
     if (rc) return rc;
 
     const int cg = C / gn_groups;

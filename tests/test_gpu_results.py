@@ -14,7 +14,7 @@ def _masks(seed, d, h, w):
     m = np.zeros((d, h, w), dtype=bool)
     yy, xx = np.mgrid[:h, :w]
     for i in range(d):
-        cy, cx, ry, rx = g.uniform(0, h), g.uniform(0, w), g.uniform(2, h / 2), g.uniform(2, w / 2)
+        cy, cx, ry, rx = g.uniform(0, h), g.uniform(0, w), g.uniform(1, max(2, h / 2)), g.uniform(1, max(2, w / 2))
         m[i] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
         m[i] ^= g.random((h, w)) < 0.02                      # speckle: many short runs
     return m
