@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfgn_b200.so")
 
 FGN_MAX_LEVELS = 8
+ABI_VERSION = 2
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 
@@ -74,8 +75,10 @@ SIGNATURES = {
     "fgn_channel_attention_ml": (c_int, [POINTER(Pyramid), _P, c_int, c_int, c_int, POINTER(c_void_p), _P]),
     "fgn_best_class_select": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "fgn_relation_fusion_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "fgn_relation_split_weights_bytes": (c_size_t, [c_int]),
+    "fgn_relation_split_weights": (c_int, [_P, c_int, _P, _P]),
     "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
-                                        _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
+                                        _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                         _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
@@ -96,7 +99,7 @@ SIGNATURES = {
     "fgn_support_pool_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_guided_roi_fused_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
-                                         _P, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
+                                         _P, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                          _P, _P, _P, c_int, _P, c_size_t, _P]),
 }
 
@@ -117,8 +120,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.fgn_abi_version() != 1:
-        raise FgnError(f"libfgn_b200 ABI {lib.fgn_abi_version()} != 1")
+    if lib.fgn_abi_version() != ABI_VERSION:
+        raise FgnError(f"libfgn_b200 ABI {lib.fgn_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -5,18 +5,20 @@
 namespace fgn {
 
 int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken);
+               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken, bool presplit);
 
 int gemm_nt_tc_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C, int ldc,
                     int M, int N, int K, cudaStream_t st);
 
 int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-            int M, int N, int K, int precision, float *split_ws, cudaStream_t st)
+            int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool presplit)
 {
     bool taken = false;
     const char *force = getenv("FGN_GEMM_IMPL");          // "simt" forces the fp32 SIMT kernel (cross-checks)
-    const bool simt_only = force != nullptr && force[0] == 's';
-    const int rc = simt_only ? FGN_OK : gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, &taken);
+    // A class-term contraction (M = B*N*49 rows: 49 at cfg3) on the tcgen05 kernel is ONE tile paying the whole
+    // pipeline latency (TMEM allocation, 16 dependent k-blocks: ~15 us); the fp32 SIMT kernel does it in a few us, exactly.
+    const bool simt_only = (force != nullptr && force[0] == 's') || (precision == 0 && M <= 512 && (force == nullptr || force[0] != 't'));
+    const int rc = simt_only ? FGN_OK : gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, &taken, presplit);
     if (rc) return rc;
     if (taken) return FGN_OK;
     if (precision != 0) {

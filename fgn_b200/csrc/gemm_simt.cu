@@ -79,6 +79,34 @@ sgemm_nt_kernel(const float *__restrict__ A, const int lda, const float *__restr
     }
 }
 
+// Few rows (the class term of the relation conv: M = B*N*49, 49 at cfg3): one CTA per output row; a warp takes output
+// columns n = warp, warp + 8, ...: its lanes stride over k with coalesced 128-bit loads of the weight row against the
+// shared-memory copy of the A row, fp32 FMA, fixed-order shuffle reduction (deterministic).  The 128x128-tile kernel
+// above would run this shape on two CTAs (34 us).
+__global__ void __launch_bounds__(256)
+sgemm_nt_skinny_kernel(const float *__restrict__ A, const int lda, const float *__restrict__ B, const int ldb,
+                       const float *__restrict__ bias, float *__restrict__ C, const int ldc, const int N, const int K)
+{
+    extern __shared__ __align__(16) float a_row[];               // [K]
+    const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(a_row + k) = ldg4(A + (size_t)m * lda + k);
+    __syncthreads();
+    const int n_lo = blockIdx.y * 64;                            // 64 columns per CTA: 8 per warp
+    for (int n = n_lo + warp; n < min(N, n_lo + 64); n += 8) {
+        const float *b = B + (size_t)n * ldb;
+        float acc = 0.f;
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 w = ldg4(b + k);
+            const float4 a = *reinterpret_cast<const float4 *>(a_row + k);
+            acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc);
+            acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) C[(size_t)m * ldc + n] = acc + (bias ? __ldg(bias + n) : 0.f);
+    }
+}
+
 int gemm_nt_simt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C,
                  int ldc, int M, int N, int K, cudaStream_t st)
 {
@@ -86,6 +114,11 @@ int gemm_nt_simt(const float *A, int lda, const float *B, int ldb, const float *
     FGN_CHECK_ARG((K & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0, "gemm needs K, lda, ldb multiples of 4 (K=%d lda=%d ldb=%d)", K, lda, ldb);
     FGN_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm operands must be 16-byte aligned");
     if (M == 0) return FGN_OK;
+    if (M <= 512 && (size_t)K * 4 <= 48 * 1024) {
+        sgemm_nt_skinny_kernel<<<dim3(M, ceil_div(N, 64)), 256, (size_t)K * 4, st>>>(A, lda, B, ldb, bias, C, ldc, N, K);
+        FGN_LAUNCH_OK();
+        return FGN_OK;
+    }
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
     FGN_CHECK_ARG(grid.y <= 65535, "gemm N too large");
     sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);

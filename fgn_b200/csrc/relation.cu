@@ -39,8 +39,14 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
                          const int C, const int cblk, const int cg, const float eps,
                          const float *__restrict__ gn_w, const float *__restrict__ gn_b,
                          const float *__restrict__ fc_cls_w, const float *__restrict__ fc_reg_w,
-                         float *__restrict__ partial)
+                         float *__restrict__ partial,
+                         const float *__restrict__ rois5, const float *__restrict__ fc_cls_b,
+                         const float *__restrict__ fc_reg_b, float *__restrict__ cls_out, float *__restrict__ reg_out,
+                         float *__restrict__ raw_cls, float *__restrict__ raw_reg)
 {
+    // rois5 (optional): the [R,5] RoI tensor itself -- the batch index is read from its first column, no separate
+    // roi_batch launch.  cls_out (optional, one channel block only): the FC biases and count_modified_cls_bbox are
+    // applied here and the final [R,N+1] / [R,4N] rows written, no partial buffer and no finalize launch.
     extern __shared__ float sm[];                 // [N][6][nwarps] + [blockDim] scratch
     const int r = blockIdx.x, blk = blockIdx.y, nblk = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -49,7 +55,7 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
     const int c = blk * cblk + tid;
     const bool active = FAST || (tid < cblk && c < C);
     const bool shfl_ok = FAST || ((cg & (cg - 1)) == 0 && cg <= 32);
-    int b = roi_batch[r];
+    int b = rois5 != nullptr ? (int)rois5[5 * (size_t)r] : roi_batch[r];
     b = b < 0 ? 0 : (b >= B ? B - 1 : b);
 
     float yq[PP];
@@ -103,10 +109,39 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
         }
     }
     __syncthreads();
+    if (cls_out == nullptr || nblk != 1) {
+        for (int i = tid; i < N * 6; i += blockDim.x) {
+            float s = 0.f;
+            for (int w = 0; w < nwarps; ++w) s += fc_part[(size_t)i * nwarps + w];
+            partial[((size_t)r * N * 6 + i) * nblk + blk] = s;
+        }
+        return;
+    }
+    // one channel block: this CTA holds the RoI's complete head outputs (same order of additions as the finalize kernel)
     for (int i = tid; i < N * 6; i += blockDim.x) {
         float s = 0.f;
         for (int w = 0; w < nwarps; ++w) s += fc_part[(size_t)i * nwarps + w];
-        partial[((size_t)r * N * 6 + i) * nblk + blk] = s;
+        const int j = i % 6;
+        fc_part[(size_t)i * nwarps] = (0.f + s) + (j == 0 ? fc_cls_b[0] : j == 1 ? fc_cls_b[1] : fc_reg_b[j - 2]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float best_fg = 0.f, best_bg = 0.f;
+        for (int n = 0; n < N; ++n) {
+            float v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] = fc_part[((size_t)n * 6 + j) * nwarps];
+            if (raw_cls) { raw_cls[((size_t)r * N + n) * 2] = v[0]; raw_cls[((size_t)r * N + n) * 2 + 1] = v[1]; }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                reg_out[(size_t)r * 4 * N + 4 * n + d] = v[2 + d];
+                if (raw_reg) raw_reg[((size_t)r * N + n) * 4 + d] = v[2 + d];
+            }
+            cls_out[(size_t)r * (N + 1) + n] = v[1];
+            const bool better = n == 0 || v[1] > best_fg || (v[1] != v[1] && best_fg == best_fg);
+            if (better) { best_fg = v[1]; best_bg = v[0]; }
+        }
+        cls_out[(size_t)r * (N + 1) + N] = best_bg;
     }
 }
 
@@ -171,11 +206,6 @@ __global__ void roi_batch_kernel(const float *__restrict__ rois, int R, int32_t 
     if (r < R) out[r] = (int)rois[5 * (size_t)r];
 }
 
-int relation_fused_tc(const float *Xq, const float *Wq, int ldw, const float *Ys, const int32_t *roi_batch, int R, int B,
-                      int N, int C, float eps, const float *gn_w, const float *gn_b, const float *fc_cls_w,
-                      const float *fc_cls_b, const float *fc_reg_w, const float *fc_reg_b, float *cls_out,
-                      float *reg_out, float *raw_cls, float *raw_reg, float *split_ws, cudaStream_t st, bool *taken);
-
 struct RelationWs {
     float *yq, *ys, *partial, *xq_nhwc, *xs_nhwc, *split_q, *split_s;
     size_t bytes;
@@ -215,22 +245,23 @@ extern "C" size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int 
 
 extern "C" int fgn_nchw_to_nhwc(const float *, int, int, int, int, float *, void *);
 
-extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
-                                       const int32_t *roi_batch, const float *spp_cat_mean, int R,
-                                       int B, int N, int C, int P, const float *conv_w,
-                                       const float *conv_b, const float *gn_w, const float *gn_b,
-                                       int gn_groups, float gn_eps, const float *fc_cls_w,
-                                       const float *fc_cls_b, const float *fc_reg_w,
-                                       const float *fc_reg_b, float *cls_out, float *reg_out,
-                                       float *raw_cls_out, float *raw_reg_out, int precision,
-                                       void *workspace, size_t workspace_bytes, void *stream)
+// conv_w_split (optional): fgn_relation_split_weights' output for this conv_w -- the TF32 split of Wq and Ws made once
+// when the weights were loaded instead of by two launches per call.  rois5 (optional, instead of roi_batch): the [R,5]
+// RoI tensor, whose first column is the batch index.
+static int relation_fusion_impl(const float *roi_feat, int feat_layout, const int32_t *roi_batch, const float *rois5,
+                                const float *spp_cat_mean, int R, int B, int N, int C, int P, const float *conv_w,
+                                const float *conv_w_split, const float *conv_b, const float *gn_w, const float *gn_b,
+                                int gn_groups, float gn_eps, const float *fc_cls_w, const float *fc_cls_b,
+                                const float *fc_reg_w, const float *fc_reg_b, float *cls_out, float *reg_out,
+                                float *raw_cls_out, float *raw_reg_out, int precision, void *workspace,
+                                size_t workspace_bytes, void *stream)
 {
     FGN_CHECK_ARG(R >= 0 && B > 0 && N > 0 && C > 0 && P > 0, "bad dims R=%d B=%d N=%d C=%d P=%d", R, B, N, C, P);
     FGN_CHECK_ARG(gn_groups > 0 && C % gn_groups == 0, "GroupNorm groups=%d does not divide C=%d", gn_groups, C);
     FGN_CHECK_ARG(precision == 0 || precision == 1, "precision=%d", precision);
     if (R == 0) return FGN_OK;
     if (P * P != kMaxPP) { set_error("relation_fusion: P=%d not instantiated (7)", P); return FGN_ERR_UNSUPPORTED; }
-    FGN_CHECK_ARG(roi_feat && roi_batch && spp_cat_mean && conv_w && conv_b && gn_w && gn_b &&
+    FGN_CHECK_ARG(roi_feat && (roi_batch || rois5) && spp_cat_mean && conv_w && conv_b && gn_w && gn_b &&
                   fc_cls_w && fc_cls_b && fc_reg_w && fc_reg_b && cls_out && reg_out, "NULL pointer");
     const int BN = B * N, PP = P * P;
     const size_t need = fgn_relation_fusion_workspace_bytes(R, BN, C, P);
@@ -250,19 +281,12 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
         if (rc) return rc;
         xq = w.xq_nhwc; xs = w.xs_nhwc;
     }
-    // Ys = Xs Ws^T + bias: the class term, once per class       (conv_w is [C, 2C] row-major)
-    int rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, w.split_s, st);
+    // Yq = Xq Wq^T ; Ys = Xs Ws^T + bias        (conv_w is [C, 2C] row-major)
+    float *split_q = conv_w_split ? const_cast<float *>(conv_w_split) : w.split_q;
+    float *split_s = conv_w_split ? const_cast<float *>(conv_w_split) + (size_t)2 * C * C : w.split_s;
+    int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, split_q, st, conv_w_split != nullptr);
     if (rc) return rc;
-    // FPN shapes at fp32 parity: the query half of the conv, GroupNorm, ReLU, pool, FC heads and the score re-assembly
-    // in ONE tcgen05 kernel whose epilogue works out of tensor memory (gemm_tc.cu: relation_fused_tc_kernel)
-    if (precision == 0 && gn_groups == 32) {
-        bool taken = false;
-        rc = relation_fused_tc(xq, conv_w, 2 * C, w.ys, roi_batch, R, B, N, C, gn_eps, gn_w, gn_b, fc_cls_w, fc_cls_b,
-                               fc_reg_w, fc_reg_b, cls_out, reg_out, raw_cls_out, raw_reg_out, w.split_q, st, &taken);
-        if (rc || taken) return rc;
-    }
-    // Yq = Xq Wq^T
-    rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, w.split_q, st);
+    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, split_s, st, conv_w_split != nullptr);
     if (rc) return rc;
 
     const int cg = C / gn_groups;
@@ -276,17 +300,51 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
     const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
     if (fast) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true>), smem);
     else      FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, false>), smem);
+    // one channel block (C <= 256): the epilogue writes the final rows itself, no partial buffer, no finalize launch
+    float *direct = nblk == 1 ? cls_out : nullptr;
     if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
-            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
+            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
+            rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);
     else
         relation_epilogue_kernel<kMaxPP, false><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
-            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial);
+            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
+            rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);
     FGN_LAUNCH_OK();
-    relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(w.partial, R, N, nblk, fc_cls_b, fc_reg_b,
-                                                              cls_out, reg_out, raw_cls_out, raw_reg_out);
-    FGN_LAUNCH_OK();
+    if (direct == nullptr) {
+        relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(w.partial, R, N, nblk, fc_cls_b, fc_reg_b,
+                                                                  cls_out, reg_out, raw_cls_out, raw_reg_out);
+        FGN_LAUNCH_OK();
+    }
     return FGN_OK;
+}
+
+extern "C" size_t fgn_relation_split_weights_bytes(int C)
+{
+    return C > 0 ? (size_t)4 * C * C * sizeof(float) : 0;       // { Wq_hi, Wq_lo, Ws_hi, Ws_lo }, each [C,C]
+}
+
+extern "C" int fgn_relation_split_weights(const float *conv_w, int C, float *out, void *stream)
+{
+    FGN_CHECK_ARG(conv_w && out && C > 0, "bad arguments");
+    int rc = gemm_split_weights(conv_w, 2 * C, C, C, out, (cudaStream_t)stream);
+    if (rc) return rc;
+    return gemm_split_weights(conv_w + C, 2 * C, C, C, out + (size_t)2 * C * C, (cudaStream_t)stream);
+}
+
+extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
+                                       const int32_t *roi_batch, const float *spp_cat_mean, int R,
+                                       int B, int N, int C, int P, const float *conv_w, const float *conv_w_split,
+                                       const float *conv_b, const float *gn_w, const float *gn_b,
+                                       int gn_groups, float gn_eps, const float *fc_cls_w,
+                                       const float *fc_cls_b, const float *fc_reg_w,
+                                       const float *fc_reg_b, float *cls_out, float *reg_out,
+                                       float *raw_cls_out, float *raw_reg_out, int precision,
+                                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    return relation_fusion_impl(roi_feat, feat_layout, roi_batch, nullptr, spp_cat_mean, R, B, N, C, P, conv_w, conv_w_split,
+                                conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b, fc_reg_w, fc_reg_b, cls_out,
+                                reg_out, raw_cls_out, raw_reg_out, precision, workspace, workspace_bytes, stream);
 }
 
 extern "C" int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, int N,
@@ -386,10 +444,12 @@ extern "C" int fgn_guided_roi_fused_fwd_bf16(const fgn_pyramid_t *pyr, int B, in
     else      FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, false>), smem);
     if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
-                                                                                        fc_cls_w, fc_reg_w, partial);
+                                                                                        fc_cls_w, fc_reg_w, partial,
+                                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
         relation_epilogue_kernel<kMaxPP, false><<<dim3(R, nblk), kEpiThreads, smem, st>>>(yq, ys, rb, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b,
-                                                                                         fc_cls_w, fc_reg_w, partial);
+                                                                                         fc_cls_w, fc_reg_w, partial,
+                                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     FGN_LAUNCH_OK();
     relation_finalize_kernel<<<ceil_div(R, 128), 128, 0, st>>>(partial, R, N, nblk, fc_cls_b, fc_reg_b, cls_out, reg_out,
                                                               nullptr, nullptr);
@@ -408,7 +468,7 @@ extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int
 extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois,
                                         int R, int P, int sampling_ratio, int aligned,
                                         float finest_scale, const float *spp_cat_mean, int N,
-                                        const float *conv_w, const float *conv_b,
+                                        const float *conv_w, const float *conv_w_split, const float *conv_b,
                                         const float *gn_w, const float *gn_b, int gn_groups,
                                         float gn_eps, const float *fc_cls_w, const float *fc_cls_b,
                                         const float *fc_reg_w, const float *fc_reg_b,
@@ -429,10 +489,9 @@ extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, 
     int rc = fgn_roi_align_ml_fwd(pyr, B, C, FGN_LAYOUT_NHWC, rois, R, P, sampling_ratio, aligned,
                                   finest_scale, nullptr, nullptr, feat, FGN_LAYOUT_NHWC, lvl_out, stream);
     if (rc) return rc;
-    roi_batch_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(rois, R, rb);
-    FGN_LAUNCH_OK();
-    return fgn_relation_fusion_fwd(feat, FGN_LAYOUT_NHWC, rb, spp_cat_mean, R, B, N, C, P, conv_w,
-                                   conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b,
-                                   fc_reg_w, fc_reg_b, cls_out, reg_out, nullptr, nullptr, precision,
-                                   ws, workspace_bytes - (size_t)(ws - (char *)workspace), stream);
+    (void)rb;                                 // the epilogue reads the batch index from rois[:,0] itself
+    return relation_fusion_impl(feat, FGN_LAYOUT_NHWC, nullptr, rois, spp_cat_mean, R, B, N, C, P, conv_w, conv_w_split,
+                                conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b,
+                                fc_reg_w, fc_reg_b, cls_out, reg_out, nullptr, nullptr, precision,
+                                ws, workspace_bytes - (size_t)(ws - (char *)workspace), stream);
 }

@@ -80,6 +80,67 @@ __global__ void roi_align_direct_kernel(const Pyramid pyr, const int C, const in
     }
 }
 
+// Few RoIs (the support branch: one box per support image, fgn_roi_head.py:432): the persistent window kernel is
+// one CTA per RoI chunk and a 26x26-cell support box then costs ~27 us of per-row latency on an otherwise idle GPU.
+// Here a warp takes (RoI, bin, 128-channel block), lane = 4 channels: the samples of the bin are visited in the
+// reference's own (iy, ix) order with four 128-bit corner loads each -- the corner cells of neighbouring samples
+// hit in L1 -- so the whole launch is R * P * P * C/128 independent warps.  Same summation order as the direct kernel
+// (bit-exact against torchvision), NHWC in, NHWC or NCHW out.
+__global__ void __launch_bounds__(256)
+roi_align_small_nhwc_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R, const int P,
+                            const int sampling_ratio, const int aligned, const float finest_scale,
+                            const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
+                            float *__restrict__ out, const int out_layout, int32_t *__restrict__ lvl_out)
+{
+    const int nblk = (C + 127) >> 7;
+    const size_t warps = (size_t)R * P * P * nblk;
+    const int lane = threadIdx.x & 31;
+    for (size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; w < warps; w += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const int cb = (int)(w % nblk);
+        const int pw = (int)((w / nblk) % P), ph = (int)((w / ((size_t)nblk * P)) % P);
+        const int r = (int)(w / ((size_t)nblk * P * P));
+        const int c = cb * 128 + lane * 4;
+        const float *roi = rois + 5 * (size_t)r;
+        const int lvl = roi_level(roi, pyr, finest_scale);
+        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, sampling_ratio, aligned, pyr.B);
+        const int H = pyr.H[lvl], W = pyr.W[lvl];
+        if (lvl_out != nullptr && cb == 0 && ph == 0 && pw == 0 && lane == 0) lvl_out[r] = lvl;
+        if (c >= C) continue;
+        const float *f = pyr.feat[lvl] + (size_t)g.batch * H * W * C + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+            const AxisSample y = axis_sample(g.start_h, g.bin_h, g.grid_h, H, ph, iy);
+            if (!y.valid) continue;
+            for (int ix = 0; ix < g.grid_w; ++ix) {
+                const AxisSample x = axis_sample(g.start_w, g.bin_w, g.grid_w, W, pw, ix);
+                if (!x.valid) continue;
+                const float w1 = __fmul_rn(y.h, x.h), w2 = __fmul_rn(y.h, x.l);
+                const float w3 = __fmul_rn(y.l, x.h), w4 = __fmul_rn(y.l, x.l);
+                const float4 v1 = ldg4(f + ((size_t)y.low * W + x.low) * C), v2 = ldg4(f + ((size_t)y.low * W + x.high) * C);
+                const float4 v3 = ldg4(f + ((size_t)y.high * W + x.low) * C), v4 = ldg4(f + ((size_t)y.high * W + x.high) * C);
+                // ((w1v1 + w2v2) + w3v3) + w4v4, then += : the reference's order, unfused
+#define FGN_S(q) acc.q = __fadd_rn(acc.q, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.q), __fmul_rn(w2, v2.q)), \
+                                                              __fmul_rn(w3, v3.q)), __fmul_rn(w4, v4.q)))
+                FGN_S(x); FGN_S(y); FGN_S(z); FGN_S(w);
+#undef FGN_S
+            }
+        }
+        float4 o = make_float4(__fdiv_rn(acc.x, g.count), __fdiv_rn(acc.y, g.count), __fdiv_rn(acc.z, g.count), __fdiv_rn(acc.w, g.count));
+        if (chan_scale != nullptr) {
+            const int si = scale_index != nullptr ? scale_index[r] : r;
+            const float4 cs = ldg4(chan_scale + (size_t)si * C + c);
+            o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
+        }
+        if (out_layout == FGN_LAYOUT_NHWC)
+            *reinterpret_cast<float4 *>(out + (((size_t)r * P + ph) * P + pw) * C + c) = o;
+        else {
+            float *q = out + (((size_t)r * C + c) * P + ph) * P + pw;
+            const size_t pp = (size_t)P * P;
+            q[0] = o.x; q[pp] = o.y; q[2 * pp] = o.z; q[3 * pp] = o.w;
+        }
+    }
+}
+
 __global__ void roi_align_sample_indices_kernel(const Pyramid pyr, const float *__restrict__ rois,
                                                 const int R, const int P, const int sampling_ratio,
                                                 const int aligned, const float finest_scale,
@@ -195,6 +256,15 @@ extern "C" int fgn_roi_align_ml_fwd(const fgn_pyramid_t *pyr, int B, int C, int 
     // FGN_RA_IMPL (development knob): 4 = persistent rotating-window kernel (default, NHWC out),
     // 2 = row-streaming kernel (one CTA per RoI: NCHW output and the shapes the window kernel declines), 0 = direct
     const int impl = env_int("FGN_RA_IMPL", 4);
+    // a handful of RoIs (the support branch): the wide small-launch kernel, see roi_align_small_nhwc_kernel
+    if (in_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4 && R <= env_int("FGN_RA_SMALL", 16)) {
+        const size_t warps = (size_t)R * P * P * ((C + 127) / 128);
+        const int blocks = (int)min((size_t)148 * 8, (warps + 7) / 8);
+        roi_align_small_nhwc_kernel<<<blocks, 256, 0, st>>>(d, C, rois, R, P, sampling_ratio, aligned, finest_scale,
+                                                            chan_scale, scale_index, out, out_layout, lvl_out);
+        FGN_LAUNCH_OK();
+        return FGN_OK;
+    }
     if (in_layout == FGN_LAYOUT_NHWC && out_layout == FGN_LAYOUT_NHWC && (C % 4) == 0 && impl >= 4) {
         bool taken = false;
         rc = launch_roi_align_window(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,

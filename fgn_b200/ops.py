@@ -457,6 +457,12 @@ class RelationParams:
             raise FgnError("relation head expects fc_cls [2,C] (num_classes=1) and fc_reg [4,C]")
         self.gn_groups, self.gn_eps = int(gn_groups), float(gn_eps)
         _need_cuda(self.conv_w, self.gn_w, self.fc_cls_w, self.fc_reg_w)
+        # load-time TF32 split of the conv weights (fgn_relation_split_weights): two launches less per call
+        lib = _lib.load()
+        self.conv_w_split = torch.empty((max(int(lib.fgn_relation_split_weights_bytes(c)) // 4, 1),),
+                                        device=self.conv_w.device, dtype=torch.float32)
+        _lib.check(lib.fgn_relation_split_weights(self.conv_w.data_ptr(), c, self.conv_w_split.data_ptr(), _stream()),
+                   "fgn_relation_split_weights")
 
 
 def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mean: torch.Tensor, n_ways: int,
@@ -486,7 +492,8 @@ def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mea
     pr = params
     _lib.check(lib.fgn_relation_fusion_fwd(
         x.data_ptr(), lay, rb.data_ptr(), s.data_ptr(), r, b, n_ways, c, p,
-        pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(), pr.gn_groups, pr.gn_eps,
+        pr.conv_w.data_ptr(), pr.conv_w_split.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
+        pr.gn_groups, pr.gn_eps,
         pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(), pr.fc_reg_b.data_ptr(),
         cls.data_ptr(), reg.data_ptr(), _ptr(raw_c), _ptr(raw_r), {"fp32": 0, "tf32": 1}[precision],
         ws.data_ptr(), wsb, _stream()), "fgn_relation_fusion_fwd")
@@ -530,7 +537,8 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
     _lib.check(lib.fgn_guided_roi_fused_fwd(
         ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
-        s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
+        s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_w_split.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(),
+        pr.gn_b.data_ptr(),
         pr.gn_groups, pr.gn_eps, pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(),
         pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), {"fp32": 0, "tf32": 1}[precision],
         ws.data_ptr(), wsb, _stream()), "fgn_guided_roi_fused_fwd")

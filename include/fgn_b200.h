@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FGN_ABI_VERSION 1
+#define FGN_ABI_VERSION 2
 
 #define FGN_OK                 0
 #define FGN_ERR_INVALID_ARG   -1
@@ -158,9 +158,14 @@ int fgn_best_class_select(const float *cls, const float *reg, int B, int N, int 
  *              1 = single-pass TF32 on tcgen05 (reduced precision, reported separately).
  * workspace: fgn_relation_fusion_workspace_bytes(R, BN, C, P) bytes. */
 size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P);
+/* Load-time preparation of the relation conv's weights: the TF32 hi/lo split of Wq = conv_w[:, :C] and
+ * Ws = conv_w[:, C:] that the 3xTF32 contraction consumes (out: fgn_relation_split_weights_bytes(C) bytes, valid as
+ * long as conv_w is unchanged).  Passing it as conv_w_split below removes two launches per call; NULL = split per call. */
+size_t fgn_relation_split_weights_bytes(int C);
+int fgn_relation_split_weights(const float *conv_w, int C, float *out, void *stream);
 int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout, const int32_t *roi_batch,
                             const float *spp_cat_mean, int R, int B, int N, int C, int P,
-                            const float *conv_w, const float *conv_b,
+                            const float *conv_w, const float *conv_w_split /* optional */, const float *conv_b,
                             const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
                             const float *fc_cls_w, const float *fc_cls_b,
                             const float *fc_reg_w, const float *fc_reg_b,
@@ -187,14 +192,17 @@ int fgn_gemm_nt_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, con
 int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, int N,
                             float *cls_out, float *reg_out, void *stream);
 
-/* FPN-mode single pass (no shared_head between RoIAlign and the relation conv): level
- * assignment + RoIAlign + relation fusion + heads; RoI features never reach HBM.
- * Same arguments as the two calls it replaces. */
+/* FPN-mode single call (no shared_head between RoIAlign and the relation conv): level assignment + RoIAlign +
+ * relation fusion + heads, four kernels (RoIAlign, class-term contraction, RoI contraction, epilogue).  The RoI features
+ * (NHWC, R*49*C*4 bytes) and the conv output travel through the caller's workspace between them: at the benchmark size
+ * that is L2-resident traffic for the most part, but it is NOT zero -- the committed captures show 26 MB of DRAM writes by
+ * the RoIAlign kernel and 51 MB of DRAM reads by the contraction per 1000 RoIs (profiles/r02_ncu_*.json).  A single kernel
+ * that keeps them on chip was built and measured slower.  Same arguments as the two calls it replaces. */
 size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P);
 int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
                              int P, int sampling_ratio, int aligned, float finest_scale,
                              const float *spp_cat_mean /* [B*N,P,P,C] NHWC */, int N,
-                             const float *conv_w, const float *conv_b,
+                             const float *conv_w, const float *conv_w_split /* optional */, const float *conv_b,
                              const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
                              const float *fc_cls_w, const float *fc_cls_b,
                              const float *fc_reg_w, const float *fc_reg_b,

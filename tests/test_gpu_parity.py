@@ -711,8 +711,8 @@ def test_full_size_properties_cfg4_relation():
     assert cls.shape == (R, N + 1) and reg.shape == (R, 4 * N) and torch.isfinite(cls).all()
     for n in (0, 7, 19):                                                     # (1)
         c1, r1 = ops.relation_fusion(feats, rb, cat[:, n:n + 1].contiguous(), 1, params)
-        # (a 1-way call runs the fused tcgen05 kernel, the 20-way call the separate epilogue kernel: same numbers
-        #  up to summation order)
+        # (the class term of a 1-way call is a 49-row contraction and runs on the exact fp32 SIMT kernel, the 20-way
+        #  call's 980 rows on the 3xTF32 tcgen05 kernel: same numbers up to the contraction's rounding)
         close(c1[:, 0], cls[:, n], atol=2e-5, what="1-way fg vs 20-way column")
         close(r1, reg[:, 4 * n:4 * n + 4], atol=2e-5, what="1-way deltas vs 20-way columns")
         close(c1[:, 1], rawc.view(R, N, 2)[:, n, 0], atol=2e-5, what="1-way bg vs 20-way raw")
