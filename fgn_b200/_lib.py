@@ -80,6 +80,10 @@ SIGNATURES = {
     "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                         _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "fgn_relation_fusion_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "fgn_relation_fusion_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                        _P, _P, _P, c_int, c_float, _P, _P,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fgn_gemm_nt_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),

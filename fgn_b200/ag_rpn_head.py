@@ -56,6 +56,9 @@ class AGRPNHead(nn.Module):
         #   "auto": fold where it moves fewer bytes, (1+N)*H*W > N*kh*kw*feat_channels (large maps: FPN P2-P4)
         fa = kwargs.get("fold_attention", False)
         self.fold_attention = "auto" if fa == "auto" else bool(fa)
+        # mmdet's RPNHead.loss [3P] (anchor targets, assigner, sampler, loss_cls / loss_bbox) is not part of this package:
+        # a callable with its signature (cls_scores, bbox_preds, gt_bboxes, img_metas) -> dict can be plugged in here
+        self.loss_fn = kwargs.get("loss_fn")
 
     def get_bboxes(self, cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], img_metas=None,
                    cfg: Optional[dict] = None, rescale: bool = False):
@@ -87,8 +90,9 @@ class AGRPNHead(nn.Module):
         batch, c = qry_fmap.shape[:2]
         if spp_fmaps.shape[0] != batch * self.n_ways * self.k_shots or spp_fmaps.shape[1] != c:
             raise ops.FgnError(f"spp_fmaps {tuple(spp_fmaps.shape)} is not [B*N*K={batch * self.n_ways * self.k_shots}, C={c}, h, w]")
-        vec = ops.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
-        return vec, ops.channel_attention(qry_fmap, vec)
+        from . import autograd as A                      # the adjoint kernels take over when autograd is recording
+        vec = A.attention_vectors(spp_fmaps, self.n_ways, self.k_shots)
+        return vec, A.channel_attention(qry_fmap, vec)
 
     def folded_rpn_conv(self, qry_fmap: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
         """relu(rpn_conv(qry_fmap_mod)) without qry_fmap_mod: conv(q * v) = conv(q, W * v) -- one grouped cuDNN conv
@@ -117,11 +121,8 @@ class AGRPNHead(nn.Module):
                        qry_cat_ids=None, img_metas_cpu: Optional[list] = None, train_mode: bool = False,
                        log_mode: bool = False):
         assert train_mode ^ (qry_bboxes is None and qry_cat_ids is None)
-        if train_mode:
-            raise NotImplementedError("AGRPNHead train_mode (RPN loss over per-class GT lists, "
-                                      "fgn_ag_rpn_head.py:58-79) is outside the forward hot path")
         batch = qry_fmap.shape[0]
-        fold = self.fold_attention
+        fold = False if train_mode else self.fold_attention       # training keeps the reference's order (and its autograd graph)
         if fold == "auto":
             kk = self.rpn_conv.kernel_size[0] * self.rpn_conv.kernel_size[1]
             fold = (1 + self.n_ways) * qry_fmap.shape[2] * qry_fmap.shape[3] > self.n_ways * kk * self.feat_channels
@@ -134,11 +135,32 @@ class AGRPNHead(nn.Module):
             rpn_cls_score, rpn_bbox_pred = self._rpn_forward_single(qry_fmap_mod)
         if log_mode:
             self.qry_fmap_mod, self.rpn_cls_score, self.rpn_bbox_pred = qry_fmap_mod, rpn_cls_score, rpn_bbox_pred
+        rpn_losses: dict = {}
+        if train_mode:
+            # fgn_ag_rpn_head.py:58-79: one GT-box list per (image, class) row of the attended batch -- the boxes of class j
+            # in image i for row i*N + j (empty [0,4] when the class is absent), the image's meta repeated N times
+            gts, metas = [], []
+            for i in range(batch):
+                for j in range(self.n_ways):
+                    idx = torch.where(qry_cat_ids[i] == j)[0]
+                    gts.append(qry_bboxes[i][idx].view(-1, 4) if len(idx) != 0 else qry_bboxes[i][:0])
+                    metas.append(img_metas_cpu[i] if img_metas_cpu is not None else None)
+            loss_inputs = ([rpn_cls_score], [rpn_bbox_pred], gts, metas)
+            if self.loss_fn is not None:
+                rpn_losses = self.loss_fn(*loss_inputs)
+                rpn_losses["loss_rpn_cls"][0] = rpn_losses["loss_rpn_cls"][0] / self.n_ways     # :77-78 "balancer"
+                rpn_losses["loss_rpn_bbox"][0] = rpn_losses["loss_rpn_bbox"][0] / self.n_ways
+            else:
+                rpn_losses = dict(loss_inputs=loss_inputs, balancer=1.0 / self.n_ways)
         if self.n_ways > 1:
-            return ops.best_class_select(rpn_cls_score, rpn_bbox_pred, batch, self.n_ways)
-        c, h, w = rpn_cls_score.shape[-3:]
-        c4 = rpn_bbox_pred.shape[1]
-        return rpn_cls_score.reshape(batch, c, h, w), rpn_bbox_pred.reshape(batch, c4, h, w)
+            # the selected maps feed proposal generation only (mmdet detaches proposals): no adjoint needed
+            with torch.no_grad():
+                out = ops.best_class_select(rpn_cls_score.detach(), rpn_bbox_pred.detach(), batch, self.n_ways)
+        else:
+            c, h, w = rpn_cls_score.shape[-3:]
+            c4 = rpn_bbox_pred.shape[1]
+            out = (rpn_cls_score.reshape(batch, c, h, w), rpn_bbox_pred.reshape(batch, c4, h, w))
+        return (out[0], out[1], rpn_losses) if train_mode else out
 
     def forward(self, qry_feats: Sequence[torch.Tensor], spp_feats: Sequence[torch.Tensor]):
         """FPN mode (SURVEY A.9, A-FPN): forward_single per level with that level's support maps."""

@@ -17,7 +17,7 @@ int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias,
     const char *force = getenv("FGN_GEMM_IMPL");          // "simt" forces the fp32 SIMT kernel (cross-checks)
     // A class-term contraction (M = B*N*49 rows: 49 at cfg3) on the tcgen05 kernel is ONE tile paying the whole
     // pipeline latency (TMEM allocation, 16 dependent k-blocks: ~15 us); the fp32 SIMT kernel does it in a few us, exactly.
-    const bool simt_only = (force != nullptr && force[0] == 's') || (precision == 0 && M <= 512 && (force == nullptr || force[0] != 't'));
+    const bool simt_only = (force != nullptr && force[0] == 's') || (precision == 0 && M <= 512 && K <= 4096 && (force == nullptr || force[0] != 't'));
     const int rc = simt_only ? FGN_OK : gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, &taken, presplit);
     if (rc) return rc;
     if (taken) return FGN_OK;

@@ -47,8 +47,9 @@ class RoIAlign(nn.Module):
         self.aligned = bool(aligned)
 
     def forward(self, input: torch.Tensor, rois: torch.Tensor, out_format: str = "nchw") -> torch.Tensor:
-        return ops.roi_align_multilevel([input], rois, [self.spatial_scale], self.output_size[0],
-                                        self.sampling_ratio, self.aligned, out_format=out_format)
+        from . import autograd as A                      # differentiable w.r.t. `input` when autograd is recording
+        return A.roi_align_multilevel([input], rois, [self.spatial_scale], self.output_size[0],
+                                      self.sampling_ratio, self.aligned, out_format=out_format)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale}, "
@@ -88,7 +89,8 @@ class SingleRoIExtractor(nn.Module):
             raise NotImplementedError("roi_scale_factor is not used on the FGN path")
         feats = list(feats)[: self.num_inputs]
         layer = self.roi_layers[0]
-        return ops.roi_align_multilevel(
+        from . import autograd as A                      # differentiable w.r.t. `feats` when autograd is recording
+        return A.roi_align_multilevel(
             feats, rois, [l.spatial_scale for l in self.roi_layers][: len(feats)], layer.output_size[0],
-            layer.sampling_ratio, layer.aligned, float(self.finest_scale), chan_scale, scale_index,
+            layer.sampling_ratio, layer.aligned, float(self.finest_scale), chan_scale=chan_scale, scale_index=scale_index,
             out_format=out_format, return_levels=return_levels)

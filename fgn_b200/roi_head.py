@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import autograd as A
 from . import ops
 from .roi_extractor import SingleRoIExtractor, bbox2roi
 
@@ -158,6 +159,15 @@ class FGNRoIHead(nn.Module):
                 self.bbox_head.fc_reg.weight, self.bbox_head.fc_reg.bias, n.num_groups, n.eps)
         return self._params_cache
 
+    def _recording(self, *tensors) -> bool:
+        """True when autograd is recording and any of `tensors` or of this head's parameters requires grad."""
+        if not torch.is_grad_enabled():
+            return False
+        flat = []
+        for t in tensors:
+            flat.extend(t if isinstance(t, (list, tuple)) else [t])
+        return A._needs_grad(*flat) or any(p.requires_grad for p in self.parameters())
+
     @staticmethod
     def _as_levels(fmap) -> List[torch.Tensor]:
         # the reference emulates mmdet's tuple-of-levels with unsqueeze(0) (fgn_roi_head.py:330,365)
@@ -172,7 +182,11 @@ class FGNRoIHead(nn.Module):
         """
         levels = self._as_levels(spp_fmaps)
         m = spp_bboxes.shape[0]
-        mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429
+        # training (fgn_roi_head.py:451-529 reaches count_spp with a backbone that may require grad): the adjoint kernels
+        # of fgn_b200.autograd take over wherever autograd is recording
+        grad = A._needs_grad(*levels) or (self.with_shared_head and A._needs_grad(*self.shared_head.parameters()))
+        roi_align = A.roi_align_multilevel if grad else ops.roi_align_multilevel
+        mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429 (masks carry no grad)
         idx = torch.arange(m, device=spp_bboxes.device, dtype=torch.float32).view(m, 1)
         # without a shared_head the class maps feed the relation GEMM directly: keep them channels_last
         fmt = "nchw" if self.with_shared_head else "nhwc"
@@ -183,17 +197,22 @@ class FGNRoIHead(nn.Module):
             else:
                 boxes = spp_bboxes / self.subsampling_ratio
             rois = torch.cat([idx, boxes.reshape(m, 4).float()], 1)
-            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0], 7, -1, aligned=False, out_format=fmt,
-                                               out_dtype=torch.float32)                          # :432
+            feat_ra = roi_align(levels, rois, [1.0], 7, -1, aligned=False, out_format=fmt,
+                                out_dtype=torch.float32)                                         # :432
         else:   # A-FPN: level from map_roi_levels on the pixel box, spatial_scale = 1/stride
             rois = torch.cat([idx, spp_bboxes.reshape(m, 4).float()], 1)
             ext = self.bbox_roi_extractor
-            feat_ra = ops.roi_align_multilevel(levels, rois, [1.0 / s for s in ext.featmap_strides[: len(levels)]],
-                                               7, -1, aligned=False, finest_scale=float(ext.finest_scale), out_format=fmt,
-                                               out_dtype=torch.float32)
+            feat_ra = roi_align(levels, rois, [1.0 / s for s in ext.featmap_strides[: len(levels)]],
+                                7, -1, aligned=False, finest_scale=float(ext.finest_scale), out_format=fmt,
+                                out_dtype=torch.float32)
         if self.with_shared_head:
             feat_ra = self.shared_head_layer(feat_ra)                                            # :435-436
-        cat_mean, mp = ops.support_pool(feat_ra, mask_ra, self.n_ways, self.k_shots)             # :439-447
+        cat_mean, mp = (A.support_pool if A._needs_grad(feat_ra) else ops.support_pool)(
+            feat_ra, mask_ra, self.n_ways, self.k_shots)                                         # :439-447
+        if cat_mean.dim() == 4:                                                                  # (autograd path: [B*N,C,P,P])
+            c = cat_mean.shape[1]
+            cat_mean = cat_mean.unflatten(0, (-1, self.n_ways))
+            mp = mp.reshape(-1, self.n_ways, c, 1, 1)
         self.spp_fmaps_roi_aligned_cat_mean = cat_mean
         self.spp_fvecs_roi_aligned_cat_mean_mp = mp
         return
@@ -217,6 +236,18 @@ class FGNRoIHead(nn.Module):
             return dict(cls_score=z((0, self.n_ways + 1)), bbox_pred=z((0, 4 * self.n_ways)), bbox_feats=None)
         ext = self.bbox_roi_extractor
         layer = ext.roi_layers[0]
+        if self._recording(levels, self.spp_fmaps_roi_aligned_cat_mean):
+            # autograd is recording and something upstream (backbone maps, class maps, the shared_head or the relation
+            # head's own parameters) requires grad: the differentiable wrappers (fgn_b200.autograd), RoI features materialised
+            bbox_feats = ext(levels, rois, out_format="nhwc")
+            if self.with_shared_head:
+                bbox_feats = self.shared_head_layer(bbox_feats)
+            n_ = self.cls_reg_shared_conv_norm
+            cls, reg = A.relation_fusion(bbox_feats, rois[:, 0], self.spp_fmaps_roi_aligned_cat_mean, self.n_ways,
+                                         self.cls_reg_shared_conv.weight, self.cls_reg_shared_conv.bias, n_.weight, n_.bias,
+                                         self.bbox_head.fc_cls.weight, self.bbox_head.fc_cls.bias,
+                                         self.bbox_head.fc_reg.weight, self.bbox_head.fc_reg.bias, n_.num_groups, n_.eps)
+            return dict(cls_score=cls, bbox_pred=reg, bbox_feats=bbox_feats)
         if not self.with_shared_head and not need_feats and layer.output_size[0] == 7:
             cls, reg = ops.guided_roi_fused(levels, rois, [l.spatial_scale for l in ext.roi_layers][: len(levels)],
                                             self.spp_fmaps_roi_aligned_cat_mean, self.n_ways, params, 7,
@@ -244,7 +275,12 @@ class FGNRoIHead(nn.Module):
         vec = self.spp_vecs_mask
         if rois is not None:
             levels = self._as_levels(qry_fmap)[: self.mask_roi_extractor.num_inputs]
-            if not self.with_shared_head:
+            if not self.with_shared_head and A._needs_grad(*levels, vec):
+                # training: the fused multiply has no adjoint of its own -- RoIAlign and the attention as two
+                # differentiable steps
+                mask_feats = self.mask_roi_extractor(levels, rois, out_format="nhwc")
+                mask_feats = A.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
+            elif not self.with_shared_head:
                 # RoIAlign with the channel attention multiply in its epilogue (K12 fused into K1)
                 # channels_last storage (logical shape unchanged): the fast RoIAlign kernel, and the layout cuDNN
                 # prefers for the mask head's convs
@@ -252,10 +288,10 @@ class FGNRoIHead(nn.Module):
                                                      out_format="nhwc")
             else:
                 mask_feats = self.shared_head(self.mask_roi_extractor(levels, rois))
-                mask_feats = ops.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
+                mask_feats = A.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
         else:
             pos_inds_new = torch.nonzero(pos_inds).view(-1)
-            mask_feats = ops.channel_attention(bbox_feats[pos_inds_new], vec.reshape(vec.shape[0], 1, -1, 1, 1))
+            mask_feats = A.channel_attention(bbox_feats[pos_inds_new], vec.reshape(vec.shape[0], 1, -1, 1, 1))
         assert mask_feats.shape[:2] == vec.shape[:2]
         mask_pred = self.mask_head(mask_feats) if self.mask_head is not None else None
         return dict(mask_pred=mask_pred, mask_feats=mask_feats)

@@ -256,6 +256,23 @@ int fgn_attention_vectors_bwd(const float *grad_vec, int BN, int K, int C, int H
 int fgn_support_pool_bwd(const float *grad_cat, const float *grad_gap, const float *m, int BN, int K, int C, int P,
                          float *grad_f, void *stream);
 
+/* Adjoint of fgn_relation_fusion_fwd (the reference: autograd over fgn_roi_head.py:253-279,338,302-326 in forward_train,
+ * :344-358).  All feature tensors NHWC.  Yq [R*49,C] = roi_feat Wq^T and Ys [B*N*49,C] = spp_cat_mean Ws^T + conv_b are
+ * the forward's split-conv outputs (re-derive them with fgn_gemm_nt); cls_fwd [R,N+1] = the forward's cls_out (its
+ * first-max foreground class receives the background column's gradient).  Every output may be NULL:
+ * d_roi_feat [R,49,C], d_spp [B*N,49,C], d_conv_w [C,2C], d_conv_b [C], d_gn_w / d_gn_b [C], d_fc_cls_w [2,C],
+ * d_fc_cls_b [2], d_fc_reg_w [4,C], d_fc_reg_b [4].  GroupNorm of <= 32 groups of a power-of-two (<= 32) channels. */
+size_t fgn_relation_fusion_bwd_workspace_bytes(int R, int BN, int N, int C);
+int fgn_relation_fusion_bwd(const float *roi_feat, const float *spp_cat_mean, const int32_t *roi_batch,
+                            const float *Yq, const float *Ys, const float *cls_fwd,
+                            const float *d_cls, const float *d_reg, int R, int B, int N, int C, int P,
+                            const float *conv_w, const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
+                            const float *fc_cls_w, const float *fc_reg_w,
+                            float *d_roi_feat, float *d_spp, float *d_conv_w, float *d_conv_b,
+                            float *d_gn_w, float *d_gn_b, float *d_fc_cls_w, float *d_fc_cls_b,
+                            float *d_fc_reg_w, float *d_fc_reg_b,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* Test-time step between the relation head's outputs and the mask branch: BBoxHead.get_bboxes [3P, mmdet 2.18]
  * as called from fgn_roi_head.py:606-613 with test_cfg.rcnn (fgn_r50_c4_densecl.py:181-185) -- softmax over the
  * N+1 scores (background last), DeltaXYWHBBoxCoder.decode of the per-class deltas (bbox_coder, :91-94) against the
