@@ -86,6 +86,7 @@ SIGNATURES = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "fgn_conv1x1_nhwc": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fgn_gemm_nt_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fgn_cls_bbox_reassemble": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "fgn_attention_vectors_ml_bf16": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, _P, c_size_t, _P]),

@@ -9,7 +9,7 @@ constexpr int BM = 128, BN = 128, BK = 16;
 __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float *__restrict__ A, const int lda, const float *__restrict__ B, const int ldb,
                 const float *__restrict__ bias, float *__restrict__ C, const int ldc,
-                const int M, const int N, const int K)
+                const int M, const int N, const int K, const float *__restrict__ residual, const int relu)
 {
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -74,7 +74,11 @@ sgemm_nt_kernel(const float *__restrict__ A, const int lda, const float *__restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = n0 + tx * 8 + j;
-            if (n < N) C[(size_t)m * ldc + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+            if (n < N) {
+                float o = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+                if (residual) o += __ldg(residual + (size_t)m * ldc + n);
+                C[(size_t)m * ldc + n] = relu ? fmaxf(o, 0.f) : o;
+            }
         }
     }
 }
@@ -85,7 +89,8 @@ sgemm_nt_kernel(const float *__restrict__ A, const int lda, const float *__restr
 // above would run this shape on two CTAs (34 us).
 __global__ void __launch_bounds__(256)
 sgemm_nt_skinny_kernel(const float *__restrict__ A, const int lda, const float *__restrict__ B, const int ldb,
-                       const float *__restrict__ bias, float *__restrict__ C, const int ldc, const int N, const int K)
+                       const float *__restrict__ bias, float *__restrict__ C, const int ldc, const int N, const int K,
+                       const float *__restrict__ residual, const int relu)
 {
     extern __shared__ __align__(16) float a_row[];               // [K]
     const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,25 +108,29 @@ sgemm_nt_skinny_kernel(const float *__restrict__ A, const int lda, const float *
             acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
         }
         acc = warp_sum(acc);
-        if (lane == 0) C[(size_t)m * ldc + n] = acc + (bias ? __ldg(bias + n) : 0.f);
+        if (lane == 0) {
+            float o = acc + (bias ? __ldg(bias + n) : 0.f);
+            if (residual) o += __ldg(residual + (size_t)m * ldc + n);
+            C[(size_t)m * ldc + n] = relu ? fmaxf(o, 0.f) : o;
+        }
     }
 }
 
 int gemm_nt_simt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C,
-                 int ldc, int M, int N, int K, cudaStream_t st)
+                 int ldc, int M, int N, int K, cudaStream_t st, const float *residual, bool relu)
 {
     FGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm dims M=%d N=%d K=%d", M, N, K);
     FGN_CHECK_ARG((K & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0, "gemm needs K, lda, ldb multiples of 4 (K=%d lda=%d ldb=%d)", K, lda, ldb);
     FGN_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm operands must be 16-byte aligned");
     if (M == 0) return FGN_OK;
     if (M <= 512 && (size_t)K * 4 <= 48 * 1024) {
-        sgemm_nt_skinny_kernel<<<dim3(M, ceil_div(N, 64)), 256, (size_t)K * 4, st>>>(A, lda, B, ldb, bias, C, ldc, N, K);
+        sgemm_nt_skinny_kernel<<<dim3(M, ceil_div(N, 64)), 256, (size_t)K * 4, st>>>(A, lda, B, ldb, bias, C, ldc, N, K, residual, relu ? 1 : 0);
         FGN_LAUNCH_OK();
         return FGN_OK;
     }
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
     FGN_CHECK_ARG(grid.y <= 65535, "gemm N too large");
-    sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, residual, relu ? 1 : 0);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

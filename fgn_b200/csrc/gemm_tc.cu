@@ -121,7 +121,8 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;              // four epilogue 
 
 __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile, int lane, int row0, int M,
                                             int col0, int N, const float *__restrict__ bias,
-                                            float *__restrict__ C, int ldc)
+                                            float *__restrict__ C, int ldc,
+                                            const float *__restrict__ residual = nullptr, const bool relu = false)
 {
     float4 *mine = reinterpret_cast<float4 *>(tile + lane * kEpiPitch);
 #pragma unroll
@@ -138,7 +139,14 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile
         const int rr = i * 4 + sub;
         float4 o = *reinterpret_cast<const float4 *>(tile + rr * kEpiPitch + c4);
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-        if (row0 + rr < M && col_ok) *reinterpret_cast<float4 *>(C + (size_t)(row0 + rr) * ldc + col0 + c4) = o;
+        if (row0 + rr < M && col_ok) {
+            if (residual != nullptr) {               // (+ identity branch of a bottleneck, same leading dimension as C)
+                const float4 q = ldg4(residual + (size_t)(row0 + rr) * ldc + col0 + c4);
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4 *>(C + (size_t)(row0 + rr) * ldc + col0 + c4) = o;
+        }
     }
     __syncwarp();
 }
@@ -162,7 +170,8 @@ template <int PASSES, int BK, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                     const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
-                    float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN)
+                    float *__restrict__ C, const int ldc, const int M, const int N, const int K, const int BN,
+                    const float *__restrict__ residual = nullptr, const int relu = 0)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -300,7 +309,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                store_chunk(r, epi_tile, lane, m0 + ew * 32, M, n0 + c0, N, bias, C, ldc);
+                store_chunk(r, epi_tile, lane, m0 + ew * 32, M, n0 + c0, N, bias, C, ldc, residual, relu != 0);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             tc_mbar_arrive(&tmem_empty[a]);
@@ -361,7 +370,8 @@ int gemm_split_weights(const float *B, int ldb, int N, int K, float *split_ws, c
 
 // presplit: split_ws already holds the TF32 split of B (gemm_split_weights, done once when the weights were loaded)
 int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken, bool presplit)
+               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken, bool presplit,
+               const float *residual, bool relu)
 {
     *taken = false;
     if (M <= 0) return FGN_OK;
@@ -392,7 +402,7 @@ int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bi
 #define FGN_TC_LAUNCH(PS, BKV, IDX)                                                                                  \
     do {                                                                                                           \
         FGN_SMEM_OPTIN((gemm_tf32_tc_kernel<PS, BKV>), TcSmem<BKV>::kTotal);                                        \
-        gemm_tf32_tc_kernel<PS, BKV><<<grid, TC_THREADS, TcSmem<BKV>::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN); \
+        gemm_tf32_tc_kernel<PS, BKV><<<grid, TC_THREADS, TcSmem<BKV>::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN, residual, relu ? 1 : 0); \
     } while (0)
     if (passes == 3 && bk == 32) FGN_TC_LAUNCH(3, 32, 0);
     else if (passes == 3)        FGN_TC_LAUNCH(3, 16, 1);

@@ -20,7 +20,7 @@ from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, FgnError, Pyramid
 __all__ = [
     "map_roi_levels", "roi_align_multilevel", "roi_align_sample_indices", "to_nhwc", "support_mask_pool",
     "support_pool", "attention_vectors", "channel_attention", "attention_multilevel", "best_class_select",
-    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count", "mask_rle_encode",
+    "relation_fusion", "guided_roi_fused", "cls_bbox_reassemble", "gemm_nt", "launch_count", "mask_rle_encode", "conv1x1",
 ]
 
 
@@ -794,3 +794,36 @@ def mask_rle_encode(masks: torch.Tensor, cap: int = 4096, return_counts: bool = 
         return rles
     ch = counts[:, :max(max(nc), 1)].cpu().numpy()
     return rles, [ch[i, :nc[i]].tolist() for i in range(d)]
+
+
+def conv1x1(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, relu: bool = False, precision: Optional[str] = None) -> torch.Tensor:
+    """A 1x1 convolution on RoI tiles through the tcgen05 contraction (fgn_conv1x1_nhwc): ``x`` [R,Cin,H,W] (repacked to
+    channels_last if it is not), ``weight`` [Cout,Cin] or [Cout,Cin,1,1] with any BatchNorm already folded in, optional
+    ``residual`` [R,Cout,H,W] and ReLU in the epilogue.  Returns [R,Cout,H,W] in channels_last storage.
+    ``precision``: "fp32" (3xTF32, fp32 parity), "tf32" (single pass), None = follow ``torch.backends.cudnn.allow_tf32``,
+    i.e. the precision cuDNN gives the convolutions around this one."""
+    _need_cuda(x, weight, bias, residual)
+    x = _f32(x, "x")
+    if storage_layout(x) != LAYOUT_NHWC:
+        x = to_nhwc(x if storage_layout(x) is not None else x.contiguous())
+    r, cin, h, w = x.shape
+    wt = _f32(weight, "weight").reshape(weight.shape[0], -1).contiguous()
+    cout = wt.shape[0]
+    if wt.shape[1] != cin or cin % 4 or cout % 4:
+        raise FgnError(f"conv1x1: weight {tuple(weight.shape)} does not match Cin={cin} (channel counts must be multiples of 4)")
+    if residual is not None:
+        residual = _f32(residual, "residual")
+        if tuple(residual.shape) != (r, cout, h, w):
+            raise FgnError("conv1x1: residual must be [R,Cout,H,W]")
+        if storage_layout(residual) != LAYOUT_NHWC:
+            residual = to_nhwc(residual if storage_layout(residual) is not None else residual.contiguous())
+    out = _empty_like_format((r, cout, h, w), x.device, LAYOUT_NHWC)
+    lib = _lib.load()
+    wsb = int(lib.fgn_gemm_workspace_bytes(cout, cin))
+    ws = torch.empty((max(wsb, 1),), device=x.device, dtype=torch.uint8)
+    _lib.check(lib.fgn_conv1x1_nhwc(x.data_ptr(), wt.data_ptr(), _ptr(None if bias is None else _f32(bias, "bias").contiguous()),
+                                    _ptr(residual), int(bool(relu)), out.data_ptr(), r * h * w, cin, cout,
+                                    {"fp32": 0, "tf32": 1}[precision or ("tf32" if torch.backends.cudnn.allow_tf32 else "fp32")],
+                                    ws.data_ptr(), wsb, _stream()), "fgn_conv1x1_nhwc")
+    return out

@@ -21,9 +21,14 @@ from .roi_extractor import SingleRoIExtractor, bbox2roi
 
 
 class _Bottleneck(nn.Module):
-    """mmdet Bottleneck [3P] with expansion=2 and no downsample (fgn_roi_head.py:202-233)."""
+    """mmdet Bottleneck [3P] with expansion=2 and no downsample (fgn_roi_head.py:202-233).
 
-    def __init__(self, inplanes: int, planes: int):
+    At inference (eval mode, CUDA, autograd not recording) the two 1x1 convolutions run on the library's tcgen05
+    contraction over the NHWC RoI tiles -- BatchNorm folded into the weights, ReLU and the identity branch in the
+    epilogue (ops.conv1x1, SURVEY 8f row 3, first piece); the 3x3 stays on cuDNN, in channels_last.  ``tc_1x1=False``
+    (or training) runs the plain torch modules."""
+
+    def __init__(self, inplanes: int, planes: int, tc_1x1: bool = True):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
@@ -32,12 +37,38 @@ class _Bottleneck(nn.Module):
         self.conv3 = nn.Conv2d(planes, inplanes, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(inplanes)
         self.relu = nn.ReLU(inplace=True)
+        self.tc_1x1 = tc_1x1
+        self._folded = None
+
+    def train(self, mode: bool = True):
+        self._folded = None                                          # running statistics / weights may change
+        return super().train(mode)
+
+    @staticmethod
+    def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        """eval-mode BatchNorm folded into the convolution: w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps)."""
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+        w = conv.weight.detach().reshape(conv.out_channels, -1) * scale[:, None]
+        b = bn.bias.detach() - bn.running_mean.detach() * scale
+        if conv.bias is not None:
+            b = b + conv.bias.detach() * scale
+        return w.contiguous(), b.contiguous()
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
+        use_tc = (self.tc_1x1 and not self.training and x.is_cuda and x.dtype == torch.float32 and
+                  not (torch.is_grad_enabled() and (x.requires_grad or self.conv1.weight.requires_grad)))
+        if not use_tc:
+            out = self.relu(self.bn1(self.conv1(x)))
+            out = self.relu(self.bn2(self.conv2(out)))
+            out = self.bn3(self.conv3(out))
+            return self.relu(out + x)
+        if self._folded is None or self._folded[0].device != x.device:
+            self._folded = self._fold(self.conv1, self.bn1) + self._fold(self.conv3, self.bn3)
+        w1, b1, w3, b3 = self._folded
+        xc = x if ops.storage_layout(x) == ops.LAYOUT_NHWC else ops.to_nhwc(x.contiguous())
+        out = ops.conv1x1(xc, w1, b1, relu=True)
         out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return self.relu(out + x)
+        return ops.conv1x1(out, w3, b3, residual=xc, relu=True)
 
 
 def make_c4_shared_head(inplanes: int = 1024, planes: int = 512, num_blocks: int = 3) -> nn.Module:

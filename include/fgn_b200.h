@@ -180,6 +180,16 @@ size_t fgn_gemm_workspace_bytes(int N, int K);
 int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
                 int M, int N, int K, int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Post-RoI head 1x1 convolutions on NHWC RoI tiles (the C4 res5 shared_head's conv1 / conv3,
+ * fgn_roi_head.py:202-238, and FCNMaskHead's conv_logits [3P], fgn_r50_c4_densecl.py:115-129) through the same tcgen05
+ * contraction:  out[M,Cout] = [relu]( x[M,Cin] weight[Cout,Cin]^T + bias [+ residual[M,Cout]] ),  M = R*H*W rows.
+ * BatchNorm (eval) is folded into weight / bias by the caller.  precision as in fgn_gemm_nt (0 = 3xTF32 fp32 parity,
+ * 1 = single-pass TF32: what cuDNN runs the neighbouring 3x3 convolution in when torch.backends.cudnn.allow_tf32 is set).
+ * workspace: fgn_gemm_workspace_bytes(Cout, Cin). */
+int fgn_conv1x1_nhwc(const float *x, const float *weight, const float *bias, const float *residual, int relu,
+                     float *out, int M, int Cin, int Cout, int precision, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
 /* bf16 variant of the contraction (reported separately, never the fp32 default): A [M,K] and B [N,K]
  * hold bf16 (uint16 storage), accumulation and C are fp32; tcgen05 kind::f16, one pass.
  * Needs K%64==0, N%16==0 (N<=256 or N%256==0), 16-byte aligned rows. */

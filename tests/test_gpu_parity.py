@@ -1165,3 +1165,38 @@ def test_mask_paste_rle_against_the_golden_fixture():
             assert counts[i] == want, i
             assert O.rle_from_string(rles[i]["counts"]) == want
     assert sum(np.array_equal(dense[i], z["masks"][i]) for i in range(len(lens))) >= len(lens) - 1
+
+
+def test_conv1x1_and_bottleneck_on_the_contraction_kernel():
+    """SURVEY 8f row 3, first piece: the res5 bottleneck's 1x1 convolutions (BatchNorm folded, ReLU / identity branch in
+    the epilogue) on the tcgen05 contraction against the plain torch modules, and ops.conv1x1 against F.conv2d."""
+    from fgn_b200 import ops
+    from fgn_b200.roi_head import _Bottleneck
+    g = torch.Generator().manual_seed(808)
+    x = torch.randn(60, 256, 7, 7, generator=g)
+    w = torch.randn(128, 256, generator=g) / 16
+    b = torch.randn(128, generator=g)
+    res = torch.randn(60, 128, 7, 7, generator=g)
+    want = torch.relu(torch.nn.functional.conv2d(x, w.view(128, 256, 1, 1), b) + res)
+    got = ops.conv1x1(x.to(dev()), w.to(dev()), b.to(dev()), residual=res.to(dev()), relu=True)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    close(got, want, atol=2e-4, what="conv1x1 + residual + relu")
+    close(ops.conv1x1(x.to(dev()).contiguous(memory_format=torch.channels_last), w.to(dev())),
+          torch.nn.functional.conv2d(x, w.view(128, 256, 1, 1)), atol=2e-4, what="conv1x1 plain")
+    blk = _Bottleneck(256, 128)
+    with torch.no_grad():
+        for bn in (blk.bn1, blk.bn2, blk.bn3):                       # non-trivial running statistics and affine
+            bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.2)
+            bn.running_var.copy_(torch.rand(bn.num_features, generator=g) + 0.5)
+            bn.weight.copy_(1 + 0.2 * torch.randn(bn.num_features, generator=g))
+            bn.bias.copy_(0.1 * torch.randn(bn.num_features, generator=g))
+    blk = blk.to(dev()).eval()
+    xd = x.to(dev())
+    with torch.no_grad():
+        from fgn_b200 import _lib
+        before = _lib.load().fgn_launch_count()
+        fast = blk(xd)
+        assert _lib.load().fgn_launch_count() > before             # the library's kernels ran
+        blk.tc_1x1 = False
+        ref = blk(xd)
+    close(fast, ref, atol=5e-4, rtol=1e-4, what="bottleneck: tcgen05 1x1 convs vs torch modules")
