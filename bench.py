@@ -224,6 +224,17 @@ def main():
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # Pinned host buffers next to the GPU: bind this rank to the CPUs NVML lists for its GPU BEFORE anything is pinned, so
+    # that cudaHostAlloc's first touch lands on the GPU's NUMA node and 8 ranks do not all stream through one socket.
+    affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:
+        affinity = None
+    config["host_affinity_cpus"] = affinity
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     E = args.episodes_per_step
