@@ -227,6 +227,7 @@ def main():
     # Pinned host buffers next to the GPU: bind this rank to the CPUs NVML lists for its GPU BEFORE anything is pinned, so
     # that cudaHostAlloc's first touch lands on the GPU's NUMA node and 8 ranks do not all stream through one socket.
     affinity = None
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -621,6 +622,8 @@ def main():
                 "reference_arm_note": ("--impl reference runs the CPU path on rank 0 only: at N>1 the driver's ratio is N GPUs against ONE CPU process"
                                        if world > 1 else "--impl reference: the oracle port on this box's host cores")}
         if world == 1 and not args.no_cpu_baseline:
+            if full_affinity is not None:                     # the CPU leg gets every host core back
+                os.sched_setaffinity(0, full_affinity)
             t0 = time.perf_counter()
             n, dt = time_cpu_reference(cfg, 1, 1, 1)
             reps = max(1, min(20, int(args.cpu_seconds / max(dt, 1e-3)) - 1))

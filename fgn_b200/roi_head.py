@@ -220,7 +220,9 @@ class FGNRoIHead(nn.Module):
         mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429 (masks carry no grad)
         idx = torch.arange(m, device=spp_bboxes.device, dtype=torch.float32).view(m, 1)
         # without a shared_head the class maps feed the relation GEMM directly: keep them channels_last
-        fmt = "nchw" if self.with_shared_head else "nhwc"
+        # channels_last storage everywhere (logical shapes stay the reference's NCHW): the relation GEMM reads it directly,
+        # and the res5 shared_head (tcgen05 1x1 convs + a cuDNN 3x3) prefers it -- so C4 mode runs the window kernel too
+        fmt = "nhwc"
         if len(levels) == 1:
             if self.mutate_inputs:
                 spp_bboxes /= self.subsampling_ratio                                             # :430
@@ -284,7 +286,7 @@ class FGNRoIHead(nn.Module):
                                             self.spp_fmaps_roi_aligned_cat_mean, self.n_ways, params, 7,
                                             layer.sampling_ratio, layer.aligned, float(ext.finest_scale), self.precision)
             return dict(cls_score=cls, bbox_pred=reg, bbox_feats=None)
-        bbox_feats = ext(levels, rois, out_format="nhwc" if not self.with_shared_head else "nchw")
+        bbox_feats = ext(levels, rois, out_format="nhwc")
         if self.with_shared_head:
             bbox_feats = self.shared_head_layer(bbox_feats)
         cls, reg = ops.relation_fusion(bbox_feats, rois[:, 0], self.spp_fmaps_roi_aligned_cat_mean, self.n_ways,
@@ -318,7 +320,7 @@ class FGNRoIHead(nn.Module):
                 mask_feats = self.mask_roi_extractor(levels, rois, chan_scale=vec.reshape(vec.shape[0], -1),
                                                      out_format="nhwc")
             else:
-                mask_feats = self.shared_head(self.mask_roi_extractor(levels, rois))
+                mask_feats = self.shared_head(self.mask_roi_extractor(levels, rois, out_format="nhwc"))
                 mask_feats = A.channel_attention(mask_feats, vec.reshape(vec.shape[0], 1, -1, 1, 1))
         else:
             pos_inds_new = torch.nonzero(pos_inds).view(-1)
