@@ -17,6 +17,7 @@ from ._lib import FgnError, load as load_library  # noqa: F401
 from . import ops  # noqa: F401
 from .roi_extractor import RoIAlign, SingleRoIExtractor, bbox2roi  # noqa: F401
 from .ag_rpn_head import AGRPNHead  # noqa: F401
+from .mask_head import FCNMaskHead  # noqa: F401
 from .roi_head import FGNBBoxHead, FGNRoIHead  # noqa: F401
 from .detector import FGN  # noqa: F401
 

@@ -87,6 +87,11 @@ SIGNATURES = {
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fgn_conv1x1_nhwc": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "fgn_conv_split_weights_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fgn_conv_split_weights": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "fgn_conv3x3_nhwc": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "fgn_deconv2x2_logits_nhwc": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          _P, c_size_t, _P]),
     "fgn_gemm_nt_bf16": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fgn_cls_bbox_reassemble": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "fgn_attention_vectors_ml_bf16": (c_int, [POINTER(Pyramid), c_int, c_int, c_int, _P, _P, c_size_t, _P]),

@@ -1,0 +1,392 @@
+// conv_tc.cu -- the post-RoI heads' convolutions as implicit GEMMs on tcgen05:
+//   * the 3x3 / pad 1 convolutions of the C4 res5 shared_head (fgn_roi_head.py:202-233, mmdet Bottleneck.conv2 [3P]) and
+//     of FCNMaskHead.convs (fgn_r50_c4_densecl.py:115-129, num_convs=4 [3P]) over NHWC RoI tiles [R,H,W,Cin];
+//   * FCNMaskHead's tail -- ConvTranspose2d(k=2, s=2) + ReLU + conv_logits (1x1) -- as ONE contraction whose epilogue takes
+//     the ReLU and the logits' dot product straight out of tensor memory: the [R,2H,2W,Cout] upsampled map (80 MB for 100
+//     detections at 14x14 -> 28x28, 256 channels) is never written.
+//
+// No im2col buffer: the A operand of tap (dy,dx) is the SAME activation tensor read through a 4D TMA descriptor
+// (C, W, H, R) with the box origin shifted by (dx-1, dy-1); what falls outside the RoI tile is zero-filled by the TMA
+// unit, which is exactly the convolution's zero padding.  A tile is a box of whole rows: RB whole RoIs (7x7: two RoIs = 98
+// of the 128 MMA rows) or HB rows of one RoI (14x14: nine rows = 126); the MMA rows beyond the box hold stale shared
+// memory and produce accumulator rows nobody reads.  The k loop runs over taps x Cin/16; weights are laid out
+// [tap][Cout][Cin] (K-major rows, one 2D descriptor).  Precision as in gemm_tc.cu: 3xTF32 (fp32 parity) or one TF32 pass.
+// Pipeline = gemm_tc.cu's: TMA producer warp, MMA issuer warp, four splitter warps (A_lo), four epilogue warps,
+// double-buffered accumulators in tensor memory.
+#include "gemm.cuh"
+#include "tc_common.cuh"
+
+namespace fgn {
+
+constexpr int CV_BM = 128, CV_BN_MAX = 256, CV_THREADS = 384, CV_BK = 16, CV_STAGES = 4;
+constexpr int CV_A = CV_BM * CV_BK * 4;                      // 8 KB
+constexpr int CV_B = CV_BN_MAX * CV_BK * 4;                  // 16 KB
+constexpr int CV_STAGE = 2 * CV_A + 2 * CV_B;                // A(hi) | A_lo | B_hi | B_lo = 48 KB
+constexpr int CV_SMEM = CV_STAGES * CV_STAGE + 1024 + 256 + kEpiBytes;
+constexpr int CV_MAX_CLS = 4;
+
+struct ConvArgs {
+    const float *bias, *residual;
+    float *out;
+    int R, H, W, Cin, Cout;        // activations [R,H,W,Cin]
+    int N, BN;                     // GEMM columns per tap (conv: Cout; deconv: 4*Cout) and columns per tile
+    int flat;                      // 1: rows are plain [M, Cin] (1x1-type contraction), 128 rows per tile
+    int HB, RB, h_blocks;          // box of a tile: W x HB x RB rows
+    int taps;                      // 9 (3x3, pad 1) or 1
+    int relu;
+    const float *w_l, *b_l;        // MODE 1: conv_logits [ncls, Cout], [ncls]
+    int ncls;
+};
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct ConvTile { int m0, nv, n0, c1, c2, c3; };
+
+__device__ __forceinline__ ConvTile conv_tile(const ConvArgs &a, int tile, int n_tiles)
+{
+    ConvTile t;
+    const int mt = tile / n_tiles;
+    t.n0 = (tile % n_tiles) * a.BN;
+    if (a.flat) {
+        const int M = a.R * a.H * a.W;
+        t.m0 = mt * CV_BM;
+        t.nv = min(CV_BM, M - t.m0);
+        t.c1 = t.m0; t.c2 = 0; t.c3 = 0;
+    } else {
+        const int r0 = (mt / a.h_blocks) * a.RB, h0 = (mt % a.h_blocks) * a.HB;
+        t.m0 = (r0 * a.H + h0) * a.W;
+        t.nv = a.HB == a.H ? min(a.RB, a.R - r0) * a.H * a.W : min(a.HB, a.H - h0) * a.W;
+        t.c1 = 0; t.c2 = h0; t.c3 = r0;
+    }
+    return t;
+}
+
+// MODE 0: out = [relu](conv + bias [+ residual]) stored NHWC.  MODE 1: mask logits of the deconv tail.
+template <int PASSES, int MODE>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+               const __grid_constant__ CUtensorMap map_blo, const ConvArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CV_STAGES * CV_STAGE);
+    uint64_t *full_bar = bars, *conv_bar = bars + CV_STAGES, *empty_bar = bars + 2 * CV_STAGES;
+    uint64_t *tmem_full = bars + 3 * CV_STAGES, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *epi_smem = reinterpret_cast<float *>(smem + CV_STAGES * CV_STAGE + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = args.BN;
+    const int m_tiles = args.flat ? (args.R * args.H * args.W + CV_BM - 1) / CV_BM
+                                  : ((args.R + args.RB - 1) / args.RB) * args.h_blocks;
+    const int n_tiles = args.N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int kb_per_tap = args.Cin / CV_BK, num_kb = args.taps * kb_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CV_STAGES; ++s) {
+            tc_mbar_init(&full_bar[s], 1);
+            tc_mbar_init(&conv_bar[s], 4);
+            tc_mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (MODE == 1) {
+        // deconv bias [Cout] and logits weights [ncls, Cout] staged once: the epilogue reads them as broadcasts
+        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += CV_THREADS)
+            epi_smem[i] = i < args.Cout ? (args.bias != nullptr ? __ldg(args.bias + i) : 0.f) : __ldg(args.w_l + i - args.Cout);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: per (tap, k-block) one shifted activation box + the tap's weight rows =====
+        if (lane == 0) {
+            const uint32_t a_bytes = (args.flat ? CV_BM : args.W * args.HB * args.RB) * CV_BK * 4;
+            const uint32_t bytes = a_bytes + (PASSES == 3 ? 2 : 1) * BN * CV_BK * 4;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const ConvTile t = conv_tile(args, tile, n_tiles);
+                for (int tap = 0; tap < args.taps; ++tap) {
+                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0, dx = args.taps == 9 ? tap % 3 - 1 : 0;
+                    const int brow = tap * args.N + t.n0;
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+                        const int s = it % CV_STAGES;
+                        tc_mbar_wait(&empty_bar[s], ((it / CV_STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * CV_STAGE;
+                        tc_mbar_expect_tx(&full_bar[s], bytes);
+                        tma_load_4d(st, &map_a, kb * CV_BK, t.c1 + dx, t.c2 + dy, t.c3, &full_bar[s]);
+                        tma_load_2d(st + 2 * CV_A, &map_bhi, kb * CV_BK, brow, &full_bar[s]);
+                        if (PASSES == 3) tma_load_2d(st + 2 * CV_A + CV_B, &map_blo, kb * CV_BK, brow, &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (instruction descriptor as in gemm_tc.cu: D=F32, A=B=TF32, K-major, N>>3, M>>4) =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+        int it = 0, local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const int a = local_tile & 1;
+            tc_mbar_wait(&tmem_empty[a], ((local_tile >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(a * CV_BN_MAX);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % CV_STAGES;
+                const uint32_t par = (it / CV_STAGES) & 1;
+                tc_mbar_wait(&full_bar[s], par);
+                if (PASSES == 3) tc_mbar_wait(&conv_bar[s], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t st = s_u32(smem + (size_t)s * CV_STAGE);
+                    const uint64_t a_hi = umma_desc_kmajor<CV_BK>(st), a_lo = umma_desc_kmajor<CV_BK>(st + CV_A);
+                    const uint64_t b_hi = umma_desc_kmajor<CV_BK>(st + 2 * CV_A);
+                    const uint64_t b_lo = umma_desc_kmajor<CV_BK>(st + 2 * CV_A + CV_B);
+#pragma unroll
+                    for (int k = 0; k < CV_BK / 8; ++k) {
+                        const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+                        umma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (PASSES == 3) {
+                            umma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                            umma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== operand splitters: landed fp32 A tile -> A_hi in place, A_lo beside it =====
+        if (PASSES == 3) {
+            const int tid = threadIdx.x - 256;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % CV_STAGES;
+                    tc_mbar_wait(&full_bar[s], (it / CV_STAGES) & 1);
+                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * CV_STAGE);
+                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * CV_STAGE + CV_A);
+#pragma unroll
+                    for (int j = 0; j < CV_A / 16 / 128; ++j) {
+                        const int i = j * 128 + tid;
+                        const float4 x = hi[i];
+                        float4 h;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                        hi[i] = h;
+                        lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive(&conv_bar[s]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int ew = warp - 4;
+        float *epi_tile = epi_smem + ew * 32 * kEpiPitch;
+        int local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const int a = local_tile & 1;
+            const ConvTile t = conv_tile(args, tile, n_tiles);
+            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * CV_BN_MAX);
+            if (MODE == 0) {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)c0, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    store_chunk(r, epi_tile, lane, t.m0 + ew * 32, t.m0 + t.nv, t.n0 + c0, args.N, args.bias, args.out, args.Cout,
+                                args.residual, args.relu != 0);
+                }
+            } else {
+                // deconv tail: this tile's columns are the Cout channels of output pixel (2h+i, 2w+j), ij = n-tile index
+                const float *b_d = epi_smem, *w_l = epi_smem + args.Cout;
+                float lg[CV_MAX_CLS];
+#pragma unroll
+                for (int c = 0; c < CV_MAX_CLS; ++c) lg[c] = 0.f;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)c0, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (c0 + j >= BN) break;                                  // BN need not be a multiple of the chunk
+                        const float v = fmaxf(__uint_as_float(r[j]) + b_d[c0 + j], 0.f);
+#pragma unroll
+                        for (int c = 0; c < CV_MAX_CLS; ++c)
+                            if (c < args.ncls) lg[c] = fmaf(v, w_l[c * args.Cout + c0 + j], lg[c]);
+                    }
+                }
+                const int i = ew * 32 + lane;
+                if (i < t.nv) {
+                    const int m = t.m0 + i, hw = args.H * args.W;
+                    const int rr = m / hw, h = (m % hw) / args.W, w = m % args.W;
+                    const int ij = t.n0 / BN, oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
+#pragma unroll
+                    for (int c = 0; c < CV_MAX_CLS; ++c)
+                        if (c < args.ncls)
+                            args.out[(((size_t)rr * args.ncls + c) * (2 * args.H) + oy) * (2 * args.W) + ox] =
+                                lg[c] + (args.b_l != nullptr ? __ldg(args.b_l + c) : 0.f);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&tmem_empty[a]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+static bool make_map_nd(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                        const cuuint32_t *box)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;               // out-of-bounds elements read as zero
+}
+
+// w_taps [taps, N, Cin] (rows K-major).  w_split = { hi [taps*N, Cin], lo [taps*N, Cin] } or NULL (then split into ws).
+static int conv_tc_launch(int mode, const float *x, const float *w_taps, const float *w_split, ConvArgs a, int precision,
+                          float *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const int rows = a.taps * a.N;
+    const float *bhi = w_taps, *blo = w_taps;
+    if (precision == 0) {
+        if (w_split != nullptr) { bhi = w_split; blo = w_split + (size_t)rows * a.Cin; }
+        else {
+            FGN_CHECK_ARG(ws != nullptr && ws_bytes >= (size_t)2 * rows * a.Cin * sizeof(float),
+                          "conv: fp32 precision needs w_split or %zu bytes of workspace", (size_t)2 * rows * a.Cin * sizeof(float));
+            if (int rc = gemm_split_weights(w_taps, a.Cin, rows, a.Cin, ws, st)) return rc;
+            bhi = ws; blo = ws + (size_t)rows * a.Cin;
+        }
+    }
+    CUtensorMap ma, mbh, mbl;
+    bool ok;
+    {
+        const cuuint64_t M = (cuuint64_t)a.R * a.H * a.W;
+        cuuint64_t dims[4], strides[3];
+        cuuint32_t box[4];
+        if (a.flat) {
+            dims[0] = a.Cin; dims[1] = M; dims[2] = 1; dims[3] = 1;
+            strides[0] = (cuuint64_t)a.Cin * 4; strides[1] = strides[2] = M * a.Cin * 4;
+            box[0] = CV_BK; box[1] = CV_BM; box[2] = 1; box[3] = 1;
+        } else {
+            dims[0] = a.Cin; dims[1] = a.W; dims[2] = a.H; dims[3] = a.R;
+            strides[0] = (cuuint64_t)a.Cin * 4; strides[1] = (cuuint64_t)a.W * a.Cin * 4; strides[2] = (cuuint64_t)a.H * a.W * a.Cin * 4;
+            box[0] = CV_BK; box[1] = a.W; box[2] = a.HB; box[3] = a.RB;
+        }
+        ok = make_map_nd(&ma, x, 4, dims, strides, box);
+        cuuint64_t bd[2] = {(cuuint64_t)a.Cin, (cuuint64_t)rows}, bs[1] = {(cuuint64_t)a.Cin * 4};
+        cuuint32_t bb[2] = {CV_BK, (cuuint32_t)a.BN};
+        ok = ok && make_map_nd(&mbh, bhi, 2, bd, bs, bb) && make_map_nd(&mbl, blo, 2, bd, bs, bb);
+    }
+    if (!ok) { set_error("cuTensorMapEncodeTiled unavailable or failed (conv)"); return FGN_ERR_CUDA; }
+    int sm_count = 0;
+    if (int rc = current_sm_count(&sm_count)) return rc;
+    const int m_tiles = a.flat ? ceil_div(a.R * a.H * a.W, CV_BM) : ceil_div(a.R, a.RB) * a.h_blocks;
+    const int grid = min(sm_count, m_tiles * (a.N / a.BN));
+#define FGN_CV_LAUNCH(PS, MD)                                                                        \
+    do {                                                                                             \
+        FGN_SMEM_OPTIN((conv_tc_kernel<PS, MD>), CV_SMEM);                                           \
+        conv_tc_kernel<PS, MD><<<grid, CV_THREADS, CV_SMEM, st>>>(ma, mbh, mbl, a);                  \
+    } while (0)
+    if (mode == 0) { if (precision == 0) FGN_CV_LAUNCH(3, 0); else FGN_CV_LAUNCH(1, 0); }
+    else           { if (precision == 0) FGN_CV_LAUNCH(3, 1); else FGN_CV_LAUNCH(1, 1); }
+#undef FGN_CV_LAUNCH
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+}  // namespace fgn
+
+using namespace fgn;
+
+static int conv_common_checks(const void *x, const void *w, const void *out, int R, int H, int W, int Cin, int Cout, int precision)
+{
+    FGN_CHECK_ARG(precision == 0 || precision == 1, "precision=%d", precision);
+    FGN_CHECK_ARG(R >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv dims R=%d H=%d W=%d Cin=%d Cout=%d", R, H, W, Cin, Cout);
+    FGN_CHECK_ARG(x && w && out, "NULL pointer");
+    FGN_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) == 0, "conv: pointers must be 16-byte aligned");
+    if ((Cin % CV_BK) != 0 || (Cout % 16) != 0 || (Cout > CV_BN_MAX && (Cout % CV_BN_MAX) != 0)) {
+        set_error("conv: the tcgen05 path needs Cin%%16==0, Cout%%16==0 and (Cout<=256 or Cout%%256==0) (Cin=%d Cout=%d)", Cin, Cout);
+        return FGN_ERR_UNSUPPORTED;
+    }
+    return FGN_OK;
+}
+
+extern "C" size_t fgn_conv_split_weights_bytes(int taps, int Cout, int Cin)
+{
+    return (taps > 0 && Cout > 0 && Cin > 0) ? (size_t)2 * taps * Cout * Cin * sizeof(float) : 0;
+}
+
+extern "C" int fgn_conv_split_weights(const float *w_taps, int taps, int Cout, int Cin, float *out, void *stream)
+{
+    FGN_CHECK_ARG(w_taps && out && taps > 0 && Cout > 0 && Cin > 0, "conv_split_weights: bad arguments");
+    return gemm_split_weights(w_taps, Cin, taps * Cout, Cin, out, (cudaStream_t)stream);
+}
+
+extern "C" int fgn_conv3x3_nhwc(const float *x, const float *w_taps, const float *w_split, const float *bias,
+                                const float *residual, int relu, float *out, int R, int H, int W, int Cin, int Cout,
+                                int precision, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = conv_common_checks(x, w_taps, out, R, H, W, Cin, Cout, precision)) return rc;
+    if (R == 0) return FGN_OK;
+    if (W > CV_BM) { set_error("conv3x3: tiles wider than %d cells are not supported (W=%d)", CV_BM, W); return FGN_ERR_UNSUPPORTED; }
+    ConvArgs a = {};
+    a.bias = bias; a.residual = residual; a.out = out;
+    a.R = R; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+    a.N = Cout; a.BN = Cout > CV_BN_MAX ? CV_BN_MAX : Cout;
+    a.flat = 0; a.taps = 9; a.relu = relu;
+    if (H * W <= CV_BM) { a.HB = H; a.RB = CV_BM / (H * W); if (a.RB > 256) a.RB = 256; }
+    else                { a.HB = CV_BM / W; a.RB = 1; }
+    a.h_blocks = ceil_div(H, a.HB);
+    return conv_tc_launch(0, x, w_taps, w_split, a, precision, (float *)workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int fgn_deconv2x2_logits_nhwc(const float *x, const float *w_taps, const float *w_split, const float *b_deconv,
+                                         const float *w_logits, const float *b_logits, float *mask_pred, int R, int H, int W,
+                                         int Cin, int Cout, int ncls, int precision, void *workspace, size_t workspace_bytes,
+                                         void *stream)
+{
+    if (int rc = conv_common_checks(x, w_taps, mask_pred, R, H, W, Cin, Cout, precision)) return rc;
+    FGN_CHECK_ARG(w_logits != nullptr && ncls >= 1, "deconv2x2_logits: w_logits NULL or ncls=%d", ncls);
+    if (Cout > CV_BN_MAX || ncls > CV_MAX_CLS) {
+        set_error("deconv2x2_logits: needs Cout<=256 and ncls<=%d (Cout=%d ncls=%d)", CV_MAX_CLS, Cout, ncls);
+        return FGN_ERR_UNSUPPORTED;
+    }
+    if (R == 0) return FGN_OK;
+    ConvArgs a = {};
+    a.bias = b_deconv; a.out = mask_pred;
+    a.R = R; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+    a.N = 4 * Cout; a.BN = Cout;                  // one column tile per output sub-pixel (i,j)
+    a.flat = 1; a.taps = 1; a.HB = 1; a.RB = 1; a.h_blocks = 1;
+    a.w_l = w_logits; a.b_l = b_logits; a.ncls = ncls;
+    return conv_tc_launch(1, x, w_taps, w_split, a, precision, (float *)workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -827,3 +827,90 @@ def conv1x1(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] 
                                     {"fp32": 0, "tf32": 1}[precision or ("tf32" if torch.backends.cudnn.allow_tf32 else "fp32")],
                                     ws.data_ptr(), wsb, _stream()), "fgn_conv1x1_nhwc")
     return out
+
+
+def _precision_code(precision: Optional[str]) -> int:
+    return {"fp32": 0, "tf32": 1}[precision or ("tf32" if torch.backends.cudnn.allow_tf32 else "fp32")]
+
+
+def conv_taps(weight: torch.Tensor, transposed: bool = False) -> torch.Tensor:
+    """Weights in the layout the tcgen05 convolutions read: ``[taps, Cout, Cin]`` (K-major rows per tap).
+    Conv2d weight [Cout,Cin,kh,kw] -> tap = ky*kw+kx; ConvTranspose2d weight [Cin,Cout,2,2] (``transposed``) -> tap = i*2+j."""
+    w = _f32(weight, "weight")
+    w = w.permute(2, 3, 1, 0) if transposed else w.permute(2, 3, 0, 1)
+    return w.reshape(-1, w.shape[2], w.shape[3]).contiguous()
+
+
+def conv_split_weights(w_taps: torch.Tensor) -> torch.Tensor:
+    """Load-time TF32 hi/lo split of ``conv_taps`` weights (fgn_conv_split_weights) for the fp32-parity passes."""
+    _need_cuda(w_taps)
+    t, cout, cin = w_taps.shape
+    lib = _lib.load()
+    out = torch.empty((2, t, cout, cin), device=w_taps.device, dtype=torch.float32)
+    _lib.check(lib.fgn_conv_split_weights(w_taps.data_ptr(), t, cout, cin, out.data_ptr(), _stream()), "fgn_conv_split_weights")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            relu: bool = False, precision: Optional[str] = None, w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on RoI tiles as a tcgen05 implicit GEMM (fgn_conv3x3_nhwc): ``x`` [R,Cin,H,W]
+    (repacked to channels_last if it is not), ``w_taps`` = ``conv_taps(conv.weight)`` with any BatchNorm folded in,
+    optional ``bias`` / ``residual`` / ReLU in the epilogue.  Returns [R,Cout,H,W] in channels_last storage.
+    ``precision`` as in ``conv1x1``."""
+    _need_cuda(x, w_taps, bias, residual, w_split)
+    x = _f32(x, "x")
+    r, cin, h, w = x.shape
+    if w_taps.dim() != 3 or w_taps.shape[0] != 9 or w_taps.shape[2] != cin:
+        raise FgnError(f"conv3x3: w_taps {tuple(w_taps.shape)} must be [9,Cout,{cin}] (ops.conv_taps)")
+    cout = w_taps.shape[1]
+    if r == 0:
+        return _empty_like_format((0, cout, h, w), x.device, LAYOUT_NHWC)
+    if storage_layout(x) != LAYOUT_NHWC:
+        x = to_nhwc(x if storage_layout(x) is not None else x.contiguous())
+    if residual is not None:
+        residual = _f32(residual, "residual")
+        if tuple(residual.shape) != (r, cout, h, w):
+            raise FgnError("conv3x3: residual must be [R,Cout,H,W]")
+        if storage_layout(residual) != LAYOUT_NHWC:
+            residual = to_nhwc(residual if storage_layout(residual) is not None else residual.contiguous())
+    out = _empty_like_format((r, cout, h, w), x.device, LAYOUT_NHWC)
+    lib = _lib.load()
+    prec = _precision_code(precision)
+    wsb = int(lib.fgn_conv_split_weights_bytes(9, cout, cin)) if (prec == 0 and w_split is None) else 0
+    ws = torch.empty((max(wsb, 1),), device=x.device, dtype=torch.uint8)
+    _lib.check(lib.fgn_conv3x3_nhwc(x.data_ptr(), w_taps.contiguous().data_ptr(), _ptr(w_split),
+                                    _ptr(None if bias is None else _f32(bias, "bias").contiguous()), _ptr(residual),
+                                    int(bool(relu)), out.data_ptr(), r, h, w, cin, cout, prec, ws.data_ptr(), wsb, _stream()),
+               "fgn_conv3x3_nhwc")
+    return out
+
+
+def deconv2x2_logits(x: torch.Tensor, w_taps: torch.Tensor, b_deconv: Optional[torch.Tensor], w_logits: torch.Tensor,
+                     b_logits: Optional[torch.Tensor], precision: Optional[str] = None,
+                     w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FCNMaskHead's tail in one launch (fgn_deconv2x2_logits_nhwc): ConvTranspose2d(k=2, s=2) + ReLU + 1x1 logits on
+    ``x`` [R,Cin,H,W]; ``w_taps`` = ``conv_taps(upsample.weight, transposed=True)`` [4,Cout,Cin], ``w_logits`` [ncls,Cout]
+    (or [ncls,Cout,1,1]).  Returns mask_pred [R,ncls,2H,2W] (contiguous NCHW)."""
+    _need_cuda(x, w_taps, b_deconv, w_logits, b_logits, w_split)
+    x = _f32(x, "x")
+    if storage_layout(x) != LAYOUT_NHWC:
+        x = to_nhwc(x if storage_layout(x) is not None else x.contiguous())
+    r, cin, h, w = x.shape
+    if w_taps.dim() != 3 or w_taps.shape[0] != 4 or w_taps.shape[2] != cin:
+        raise FgnError(f"deconv2x2_logits: w_taps {tuple(w_taps.shape)} must be [4,Cout,{cin}] (ops.conv_taps(..., transposed=True))")
+    cout = w_taps.shape[1]
+    wl = _f32(w_logits, "w_logits").reshape(w_logits.shape[0], -1).contiguous()
+    if wl.shape[1] != cout:
+        raise FgnError("deconv2x2_logits: w_logits must be [ncls,Cout]")
+    ncls = wl.shape[0]
+    out = torch.empty((r, ncls, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    prec = _precision_code(precision)
+    wsb = int(lib.fgn_conv_split_weights_bytes(4, cout, cin)) if (prec == 0 and w_split is None) else 0
+    ws = torch.empty((max(wsb, 1),), device=x.device, dtype=torch.uint8)
+    _lib.check(lib.fgn_deconv2x2_logits_nhwc(x.data_ptr(), w_taps.contiguous().data_ptr(), _ptr(w_split),
+                                             _ptr(None if b_deconv is None else _f32(b_deconv, "b_deconv").contiguous()),
+                                             wl.data_ptr(), _ptr(None if b_logits is None else _f32(b_logits, "b_logits").contiguous()),
+                                             out.data_ptr(), r, h, w, cin, cout, ncls, prec, ws.data_ptr(), wsb, _stream()),
+               "fgn_deconv2x2_logits_nhwc")
+    return out

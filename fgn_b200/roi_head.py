@@ -23,12 +23,13 @@ from .roi_extractor import SingleRoIExtractor, bbox2roi
 class _Bottleneck(nn.Module):
     """mmdet Bottleneck [3P] with expansion=2 and no downsample (fgn_roi_head.py:202-233).
 
-    At inference (eval mode, CUDA, autograd not recording) the two 1x1 convolutions run on the library's tcgen05
-    contraction over the NHWC RoI tiles -- BatchNorm folded into the weights, ReLU and the identity branch in the
-    epilogue (ops.conv1x1, SURVEY 8f row 3, first piece); the 3x3 stays on cuDNN, in channels_last.  ``tc_1x1=False``
-    (or training) runs the plain torch modules."""
+    At inference (eval mode, CUDA, autograd not recording) all three convolutions run on the library's tcgen05 kernels
+    over the NHWC RoI tiles -- BatchNorm folded into the weights, ReLU and the identity branch in the
+    epilogues: the 1x1s on the contraction kernel (ops.conv1x1), the 3x3 as an implicit GEMM whose taps are shifted,
+    zero-filled TMA boxes of the same tensor (ops.conv3x3).  ``tc_1x1=False`` / ``tc_3x3=False`` (or training) run the plain
+    torch modules."""
 
-    def __init__(self, inplanes: int, planes: int, tc_1x1: bool = True):
+    def __init__(self, inplanes: int, planes: int, tc_1x1: bool = True, tc_3x3: bool = True):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
@@ -37,7 +38,7 @@ class _Bottleneck(nn.Module):
         self.conv3 = nn.Conv2d(planes, inplanes, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(inplanes)
         self.relu = nn.ReLU(inplace=True)
-        self.tc_1x1 = tc_1x1
+        self.tc_1x1, self.tc_3x3 = tc_1x1, tc_3x3
         self._folded = None
 
     def train(self, mode: bool = True):
@@ -48,7 +49,7 @@ class _Bottleneck(nn.Module):
     def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
         """eval-mode BatchNorm folded into the convolution: w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps)."""
         scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
-        w = conv.weight.detach().reshape(conv.out_channels, -1) * scale[:, None]
+        w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
         b = bn.bias.detach() - bn.running_mean.detach() * scale
         if conv.bias is not None:
             b = b + conv.bias.detach() * scale
@@ -62,13 +63,22 @@ class _Bottleneck(nn.Module):
             out = self.relu(self.bn2(self.conv2(out)))
             out = self.bn3(self.conv3(out))
             return self.relu(out + x)
-        if self._folded is None or self._folded[0].device != x.device:
-            self._folded = self._fold(self.conv1, self.bn1) + self._fold(self.conv3, self.bn3)
-        w1, b1, w3, b3 = self._folded
+        prec = "tf32" if torch.backends.cudnn.allow_tf32 else "fp32"
+        if self._folded is None or self._folded["device"] != x.device or self._folded["prec"] != prec:
+            w1, b1 = self._fold(self.conv1, self.bn1)
+            w2, b2 = self._fold(self.conv2, self.bn2)
+            w3, b3 = self._fold(self.conv3, self.bn3)
+            t2 = ops.conv_taps(w2)
+            self._folded = dict(device=x.device, prec=prec, w1=w1.flatten(1), b1=b1, t2=t2, b2=b2, w3=w3.flatten(1), b3=b3,
+                                s2=ops.conv_split_weights(t2) if (prec == "fp32" and self.tc_3x3) else None)
+        f = self._folded
         xc = x if ops.storage_layout(x) == ops.LAYOUT_NHWC else ops.to_nhwc(x.contiguous())
-        out = ops.conv1x1(xc, w1, b1, relu=True)
-        out = self.relu(self.bn2(self.conv2(out)))
-        return ops.conv1x1(out, w3, b3, residual=xc, relu=True)
+        out = ops.conv1x1(xc, f["w1"], f["b1"], relu=True)
+        if self.tc_3x3:
+            out = ops.conv3x3(out, f["t2"], f["b2"], relu=True, precision=prec, w_split=f["s2"])
+        else:
+            out = self.relu(self.bn2(self.conv2(out)))
+        return ops.conv1x1(out, f["w3"], f["b3"], residual=xc, relu=True)
 
 
 def make_c4_shared_head(inplanes: int = 1024, planes: int = 512, num_blocks: int = 3) -> nn.Module:
@@ -116,7 +126,7 @@ class FGNRoIHead(nn.Module):
     spp_vecs_mask: torch.Tensor
 
     def __init__(self, bbox_roi_extractor: Optional[dict] = None, bbox_head: Optional[dict] = None,
-                 mask_roi_extractor: Optional[dict] = None, mask_head: Optional[nn.Module] = None,
+                 mask_roi_extractor: Optional[dict] = None, mask_head: Union[None, dict, nn.Module] = None,
                  shared_head: Union[None, str, nn.Module] = "c4", channels: int = 1024, n_ways: Optional[int] = None,
                  k_shots: Optional[int] = None, mutate_inputs: bool = True, precision: str = "fp32",
                  train_cfg=None, test_cfg=None, **kwargs):
@@ -140,6 +150,10 @@ class FGNRoIHead(nn.Module):
         bh.pop("type", None)
         bh.setdefault("in_channels", channels)
         self.bbox_head = FGNBBoxHead(**bh)
+        if isinstance(mask_head, dict):                            # config form (fgn_r50_c4_densecl.py:115-129)
+            from .mask_head import FCNMaskHead
+            mh = {k: v for k, v in mask_head.items() if k not in ("type", "loss_mask", "init_cfg", "norm_cfg")}
+            mask_head = FCNMaskHead(**mh)
         self.mask_head = mask_head
         if shared_head == "c4":
             self.shared_head = make_c4_shared_head(channels, channels // 2, 3)

@@ -190,6 +190,33 @@ int fgn_conv1x1_nhwc(const float *x, const float *weight, const float *bias, con
                      float *out, int M, int Cin, int Cout, int precision, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* Post-RoI head 3x3 / pad 1 convolution over NHWC RoI tiles as an implicit GEMM on tcgen05 (no im2col buffer: tap
+ * (dy,dx) reads the activation tensor through a 4D TMA descriptor shifted by (dx-1, dy-1), out-of-tile cells are
+ * zero-filled by the TMA unit).  Replaces mmdet Bottleneck.conv2 of the C4 shared_head (fgn_roi_head.py:202-233) and
+ * FCNMaskHead.convs[i] (fgn_r50_c4_densecl.py:115-129) at inference.
+ *   x [R,H,W,Cin] NHWC; w_taps [9,Cout,Cin] = weight.permute(2,3,0,1) with any BatchNorm folded in (tap = ky*3+kx);
+ *   w_split optional: fgn_conv_split_weights(w_taps, 9, Cout, Cin) (else split per call into workspace, which must then
+ *   hold fgn_conv_split_weights_bytes(9, Cout, Cin)); bias [Cout] / residual [R,H,W,Cout] optional; out [R,H,W,Cout].
+ *   precision 0 = 3xTF32 (fp32 parity), 1 = one TF32 pass (what cuDNN does under allow_tf32).
+ * Needs Cin%16==0, Cout%16==0, (Cout<=256 or Cout%256==0), W<=128; else FGN_ERR_UNSUPPORTED. */
+size_t fgn_conv_split_weights_bytes(int taps, int Cout, int Cin);
+int fgn_conv_split_weights(const float *w_taps, int taps, int Cout, int Cin, float *out, void *stream);
+int fgn_conv3x3_nhwc(const float *x, const float *w_taps, const float *w_split, const float *bias,
+                     const float *residual, int relu, float *out, int R, int H, int W, int Cin, int Cout,
+                     int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* FCNMaskHead's tail in one launch (mmdet FCNMaskHead.forward [3P]: upsample = ConvTranspose2d(Cin, Cout, 2, stride=2),
+ * ReLU, conv_logits = Conv2d(Cout, ncls, 1); called at fgn_roi_head.py:380): a [R*H*W, Cin] x [4*Cout, Cin]^T contraction
+ * whose epilogue applies the deconv bias, the ReLU and the logits' dot product straight out of tensor memory -- the
+ * upsampled [R,2H,2W,Cout] map is never written.
+ *   x [R,H,W,Cin] NHWC; w_taps [4,Cout,Cin] = upsample.weight.permute(2,3,1,0) (tap = i*2+j, output pixel (2h+i, 2w+j));
+ *   b_deconv [Cout]; w_logits [ncls,Cout]; b_logits [ncls]; mask_pred [R,ncls,2H,2W] (NCHW, the reference's layout).
+ * Needs Cin%16==0, Cout%16==0, Cout<=256, ncls<=4. */
+int fgn_deconv2x2_logits_nhwc(const float *x, const float *w_taps, const float *w_split, const float *b_deconv,
+                              const float *w_logits, const float *b_logits, float *mask_pred, int R, int H, int W,
+                              int Cin, int Cout, int ncls, int precision, void *workspace, size_t workspace_bytes,
+                              void *stream);
+
 /* bf16 variant of the contraction (reported separately, never the fp32 default): A [M,K] and B [N,K]
  * hold bf16 (uint16 storage), accumulation and C are fp32; tcgen05 kind::f16, one pass.
  * Needs K%64==0, N%16==0 (N<=256 or N%256==0), 16-byte aligned rows. */

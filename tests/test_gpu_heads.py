@@ -1,0 +1,142 @@
+"""Post-RoI heads on tcgen05: the 3x3 implicit-GEMM convolution, FCNMaskHead's fused
+deconv + ReLU + logits tail, the whole FCNMaskHead and the res5 bottleneck, against plain PyTorch fp32 on the CPU
+(the operators the reference calls: fgn_roi_head.py:202-233,380; fgn_r50_c4_densecl.py:115-129)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+# fp32 route = 3xTF32 error-compensated passes: 1e-4 + 1e-5|b| on O(1) outputs; tf32 route = one pass (10-bit mantissas),
+# the precision cuDNN gives the same convolutions under allow_tf32 -- stated tolerance 2e-2 on O(1) outputs
+TOL = {"fp32": (1e-4, 1e-5), "tf32": (2e-2, 1e-2)}
+
+
+def close(got, want, prec, what):
+    atol, rtol = TOL[prec]
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs()
+    bad = err > atol + rtol * want.abs()
+    assert not bad.any(), f"{what} [{prec}]: {int(bad.sum())}/{bad.numel()} outside tol, max abs err {float(err.max()):.3e}"
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("r,cin,cout,h,w", [
+    (37, 64, 48, 7, 7),        # two RoIs per 98-row tile, odd RoI count (half-empty last tile)
+    (5, 32, 256, 14, 14),      # nine-row boxes of one RoI (126 rows) + a five-row remainder
+    (3, 64, 512, 7, 7),        # two column tiles
+    (1, 16, 16, 5, 9),         # non-square tile, a single k-block per tap
+    (131, 16, 32, 3, 3),       # fourteen RoIs per tile
+    (2, 48, 64, 10, 20),       # wide rows: six rows per box, ragged last box
+])
+def test_conv3x3_against_torch(prec, r, cin, cout, h, w):
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(r * 1000 + cin + cout)
+    x = torch.randn(r, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(r, cout, h, w, generator=g)
+    taps = ops.conv_taps(wt.to(DEV))
+    assert taps.shape == (9, cout, cin)
+    got = ops.conv3x3(x.to(DEV), taps, precision=prec)
+    assert got.is_contiguous(memory_format=torch.channels_last) or min(h, w, cout) == 1
+    close(got, F.conv2d(x, wt, padding=1), prec, "conv3x3 plain")
+    got = ops.conv3x3(x.to(DEV).contiguous(memory_format=torch.channels_last), taps, b.to(DEV), residual=res.to(DEV), relu=True,
+                      precision=prec, w_split=ops.conv_split_weights(taps) if prec == "fp32" else None)
+    close(got, torch.relu(F.conv2d(x, wt, b, padding=1) + res), prec, "conv3x3 + bias + residual + relu")
+
+
+def test_conv3x3_zero_rois_and_unsupported_shapes():
+    from fgn_b200 import ops, FgnError
+    taps = torch.zeros(9, 32, 32, device=DEV)
+    assert ops.conv3x3(torch.zeros(0, 32, 7, 7, device=DEV), taps).shape == (0, 32, 7, 7)
+    with pytest.raises(FgnError):
+        ops.conv3x3(torch.zeros(2, 24, 7, 7, device=DEV), torch.zeros(9, 32, 24, device=DEV))      # Cin % 16
+    with pytest.raises(FgnError):
+        ops.conv3x3(torch.zeros(2, 32, 7, 7), taps.cpu())                                           # no CPU path
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("r,cin,cout,ncls,h,w", [(7, 64, 256, 1, 14, 14), (3, 32, 48, 3, 7, 7), (1, 16, 16, 4, 2, 3)])
+def test_deconv2x2_logits_against_torch(prec, r, cin, cout, ncls, h, w):
+    from fgn_b200 import ops
+    g = torch.Generator().manual_seed(77 + r + cin)
+    x = torch.randn(r, cin, h, w, generator=g)
+    up = torch.nn.ConvTranspose2d(cin, cout, 2, stride=2)
+    lg = torch.nn.Conv2d(cout, ncls, 1)
+    with torch.no_grad():
+        up.weight.copy_(torch.randn(up.weight.shape, generator=g) / cin ** 0.5)
+        up.bias.copy_(torch.randn(cout, generator=g) * 0.3)
+        lg.weight.copy_(torch.randn(lg.weight.shape, generator=g) / cout ** 0.5)
+        lg.bias.copy_(torch.randn(ncls, generator=g))
+        want = lg(torch.relu(up(x)))
+    got = ops.deconv2x2_logits(x.to(DEV), ops.conv_taps(up.weight.detach().to(DEV), transposed=True), up.bias.detach().to(DEV),
+                               lg.weight.detach().to(DEV), lg.bias.detach().to(DEV), precision=prec)
+    assert got.shape == (r, ncls, 2 * h, 2 * w) and got.is_contiguous()
+    close(got, want, prec, "deconv2x2 + relu + logits")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_fcn_mask_head_fused_route_against_torch_modules(prec):
+    """The config's head (num_convs=4, conv_out_channels=256, class_agnostic) at a reduced input width: five library
+    launches, state-dict names of mmdet's FCNMaskHead, values against the same modules run by PyTorch on the CPU."""
+    from fgn_b200 import FCNMaskHead, _lib
+    torch.manual_seed(5)
+    head = FCNMaskHead(num_convs=4, in_channels=64, conv_out_channels=256, num_classes=1, class_agnostic=True, precision=prec)
+    keys = set(head.state_dict().keys())
+    assert {"convs.0.conv.weight", "convs.3.conv.bias", "upsample.weight", "upsample.bias", "conv_logits.weight",
+            "conv_logits.bias"} <= keys
+    with torch.no_grad():
+        for m in head.convs:
+            m.conv.bias.copy_(torch.randn_like(m.conv.bias) * 0.1)
+        head.upsample.bias.copy_(torch.randn_like(head.upsample.bias) * 0.1)
+    head.eval()
+    x = torch.randn(9, 64, 14, 14)
+    with torch.no_grad():
+        want = head(x)                                                   # CPU tensors -> the torch modules
+        hd = head.to(DEV)
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+        hd(xd)                                                           # first call prepares the tap-major / split weights
+        before = _lib.load().fgn_launch_count()
+        got = hd(xd)
+        launches = _lib.load().fgn_launch_count() - before
+    assert want.shape == (9, 1, 28, 28)
+    assert launches == 5, launches                                       # four convolutions + the fused tail, nothing per call
+    close(got, want, prec, "FCNMaskHead")
+    # training / autograd: the torch modules, with a grad_fn
+    hd.train()
+    out = hd(x.to(DEV).requires_grad_(True))
+    assert out.grad_fn is not None
+
+
+@pytest.mark.parametrize("prec_tf32", [False, True])
+def test_bottleneck_three_convs_on_tcgen05(prec_tf32):
+    from fgn_b200 import _lib
+    from fgn_b200.roi_head import _Bottleneck
+    g = torch.Generator().manual_seed(909)
+    blk = _Bottleneck(256, 128)
+    with torch.no_grad():
+        for bn in (blk.bn1, blk.bn2, blk.bn3):
+            bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.2)
+            bn.running_var.copy_(torch.rand(bn.num_features, generator=g) + 0.5)
+            bn.weight.copy_(1 + 0.2 * torch.randn(bn.num_features, generator=g))
+            bn.bias.copy_(0.1 * torch.randn(bn.num_features, generator=g))
+    blk.eval()
+    x = torch.randn(61, 256, 7, 7, generator=g)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = prec_tf32
+        with torch.no_grad():
+            want = blk(x)                                                # CPU: plain torch modules in fp32
+            bd = blk.to(DEV)
+            before = _lib.load().fgn_launch_count()
+            got = bd(x.to(DEV))
+            assert _lib.load().fgn_launch_count() - before >= 3
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    prec = "tf32" if prec_tf32 else "fp32"
+    atol = 5e-2 if prec_tf32 else 5e-4                                   # three chained convolutions of O(1..10) activations
+    err = (got.cpu() - want).abs()
+    assert bool((err <= atol + (1e-2 if prec_tf32 else 1e-4) * want.abs()).all()), f"bottleneck [{prec}] max abs err {float(err.max()):.3e}"

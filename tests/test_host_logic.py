@@ -186,3 +186,20 @@ def test_chunked_result_writer_matches_the_eval_hook_layout(tmp_path):
     assert [len(pickle.load(open(p, "rb"))) for p in paths] == [4, 4, 2]
     assert [r["qry_img_id"] for r in got] == list(range(10))
     assert w.close() == paths                                                       # nothing left to flush
+
+
+def test_roi_head_builds_the_configs_mask_head():
+    """fgn_r50_c4_densecl.py:115-129: mask_head given as a config dict becomes the package's FCNMaskHead with mmdet's
+    module names (a reference checkpoint's keys load)."""
+    from fgn_b200 import FCNMaskHead, FGNRoIHead
+    head = FGNRoIHead(shared_head=None, channels=64,
+                      mask_head=dict(type="FCNMaskHead", init_cfg=None, num_convs=4, in_channels=64, conv_out_channels=32,
+                                     num_classes=1, class_agnostic=True,
+                                     loss_mask=dict(type="CrossEntropyLoss", use_mask=True, loss_weight=1.0)))
+    assert isinstance(head.mask_head, FCNMaskHead) and head.with_mask
+    keys = set(head.mask_head.state_dict())
+    assert {"convs.0.conv.weight", "convs.3.conv.bias", "upsample.weight", "conv_logits.weight"} <= keys
+    assert head.mask_head.conv_logits.out_channels == 1 and head.mask_head.convs[0].conv.in_channels == 64
+    import torch
+    x = torch.randn(2, 64, 14, 14)
+    assert head.mask_head(x).shape == (2, 1, 28, 28)                     # CPU tensors: the plain torch modules
