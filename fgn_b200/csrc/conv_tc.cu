@@ -15,6 +15,7 @@
 // double-buffered accumulators in tensor memory.
 #include "gemm.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace fgn {
 
@@ -36,6 +37,7 @@ struct ConvArgs {
     int relu;
     const float *w_l, *b_l;        // MODE 1: conv_logits [ncls, Cout], [ncls]
     int ncls;
+    int debug;                     // FGN_TC_DEBUG (development): bit 0 = epilogue does not read / store, bit 1 = splitters do not split
 };
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
@@ -63,6 +65,52 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvArgs &a, int tile, int n
         t.c1 = 0; t.c2 = h0; t.c3 = r0;
     }
     return t;
+}
+
+// One tile's epilogue for one epilogue warp (TMEM lanes 32*ew .. +31 of the accumulator at taddr).
+template <int MODE>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvArgs &args, const ConvTile &t, uint32_t taddr, float *epi_tile,
+                                                   const float *epi_smem, int lane, int ew, int BN)
+{
+    if (MODE == 0) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            store_chunk(r, epi_tile, lane, t.m0 + ew * 32, t.m0 + t.nv, t.n0 + c0, args.N, args.bias, args.out, args.Cout,
+                        args.residual, args.relu != 0);
+        }
+    } else {
+        // deconv tail: this tile's columns are the Cout channels of output pixel (2h+i, 2w+j), ij = n-tile index
+        const float *b_d = epi_smem, *w_l = epi_smem + args.Cout;
+        float lg[CV_MAX_CLS];
+#pragma unroll
+        for (int c = 0; c < CV_MAX_CLS; ++c) lg[c] = 0.f;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (c0 + j >= BN) break;                                  // BN need not be a multiple of the chunk
+                const float v = fmaxf(__uint_as_float(r[j]) + b_d[c0 + j], 0.f);
+#pragma unroll
+                for (int c = 0; c < CV_MAX_CLS; ++c)
+                    if (c < args.ncls) lg[c] = fmaf(v, w_l[c * args.Cout + c0 + j], lg[c]);
+            }
+        }
+        const int i = ew * 32 + lane;
+        if (i < t.nv) {
+            const int m = t.m0 + i, hw = args.H * args.W;
+            const int rr = m / hw, h = (m % hw) / args.W, w = m % args.W;
+            const int ij = t.n0 / BN, oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
+#pragma unroll
+            for (int c = 0; c < CV_MAX_CLS; ++c)
+                if (c < args.ncls)
+                    args.out[(((size_t)rr * args.ncls + c) * (2 * args.H) + oy) * (2 * args.W) + ox] =
+                        lg[c] + (args.b_l != nullptr ? __ldg(args.b_l + c) : 0.f);
+        }
+    }
 }
 
 // MODE 0: out = [relu](conv + bias [+ residual]) stored NHWC.  MODE 1: mask logits of the deconv tail.
@@ -208,45 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * CV_BN_MAX);
-            if (MODE == 0) {
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + (uint32_t)c0, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    store_chunk(r, epi_tile, lane, t.m0 + ew * 32, t.m0 + t.nv, t.n0 + c0, args.N, args.bias, args.out, args.Cout,
-                                args.residual, args.relu != 0);
-                }
-            } else {
-                // deconv tail: this tile's columns are the Cout channels of output pixel (2h+i, 2w+j), ij = n-tile index
-                const float *b_d = epi_smem, *w_l = epi_smem + args.Cout;
-                float lg[CV_MAX_CLS];
-#pragma unroll
-                for (int c = 0; c < CV_MAX_CLS; ++c) lg[c] = 0.f;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + (uint32_t)c0, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (c0 + j >= BN) break;                                  // BN need not be a multiple of the chunk
-                        const float v = fmaxf(__uint_as_float(r[j]) + b_d[c0 + j], 0.f);
-#pragma unroll
-                        for (int c = 0; c < CV_MAX_CLS; ++c)
-                            if (c < args.ncls) lg[c] = fmaf(v, w_l[c * args.Cout + c0 + j], lg[c]);
-                    }
-                }
-                const int i = ew * 32 + lane;
-                if (i < t.nv) {
-                    const int m = t.m0 + i, hw = args.H * args.W;
-                    const int rr = m / hw, h = (m % hw) / args.W, w = m % args.W;
-                    const int ij = t.n0 / BN, oy = 2 * h + (ij >> 1), ox = 2 * w + (ij & 1);
-#pragma unroll
-                    for (int c = 0; c < CV_MAX_CLS; ++c)
-                        if (c < args.ncls)
-                            args.out[(((size_t)rr * args.ncls + c) * (2 * args.H) + oy) * (2 * args.W) + ox] =
-                                lg[c] + (args.b_l != nullptr ? __ldg(args.b_l + c) : 0.f);
-                }
-            }
+            conv_epilogue_tile<MODE>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             tc_mbar_arrive(&tmem_empty[a]);
         }
@@ -257,6 +267,204 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ---- CTA-pair kernel (cta_group::2) ----------------------------------------------------------------------------------
+// The single-CTA kernel above is bound by what the L2 can deliver: per 16-wide k-block an SM needs its 8 KB of A and the
+// WHOLE 256-column B tile (16 KB, 32 KB with B_lo), and at ~68 GB/s per SM (148 SMs x that = the L2's ~10 TB/s) the operands
+// arrive slower than the tensor core consumes them (profiles/r02_ncu_gemm_tcgen05.json: tensor pipe 57 % of active).  Here two
+// CTAs on the SMs of one TPC run one 256-row MMA: each loads its own 128 rows of A and HALF of the B tile (rows
+// n0 + rank*BN/2 ..), the tensor cores read both halves, and each SM's tensor memory receives its own 128 x BN block of D.
+// Per SM and k-block that is 16 KB instead of 24 KB (one TF32 pass) or 24 KB instead of 40 KB (3xTF32), six ring stages deep.
+// Rank 0 issues every MMA; its barriers are the ones the loads of both CTAs count on.
+constexpr int C2_BH = (CV_BN_MAX / 2) * CV_BK * 4;           // half B tile: 8 KB
+template <int PASSES>
+struct C2Ring {                                               // 192 KB of ring either way
+    static constexpr int kStage = PASSES == 3 ? 2 * CV_A + 2 * C2_BH : CV_A + C2_BH;   // A(hi) | A_lo | B_hi | B_lo = 32 KB, or A | B = 16 KB
+    static constexpr int kStages = PASSES == 3 ? 6 : 12;     // the loop is latency-bound (~2.5 us from a freed slot to its MMAs): depth is throughput
+    static constexpr int kOffB = PASSES == 3 ? 2 * CV_A : CV_A;
+};
+constexpr int C2_RING = 6 * (2 * CV_A + 2 * C2_BH);
+constexpr int C2_SMEM = C2_RING + 1024 + 512 + kEpiBytes;
+
+template <int PASSES, int MODE>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                const __grid_constant__ CUtensorMap map_blo, const ConvArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int C2_STAGES = C2Ring<PASSES>::kStages, C2_STAGE = C2Ring<PASSES>::kStage, C2_OFFB = C2Ring<PASSES>::kOffB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C2_RING);
+    uint64_t *full_bar = bars;                          // rank 0's: B halves of both CTAs (and both A tiles when PASSES == 1)
+    uint64_t *afull_bar = bars + C2_STAGES;             // local: this CTA's A tile landed (PASSES == 3: the splitters wait on it)
+    uint64_t *conv_bar = bars + 2 * C2_STAGES;          // rank 0's: the eight splitter warps of the pair
+    uint64_t *empty_bar = bars + 3 * C2_STAGES;         // local: the MMAs that read this stage retired (multicast commit)
+    uint64_t *tmem_full = bars + 4 * C2_STAGES;         // local, multicast commit
+    uint64_t *tmem_empty = tmem_full + 2;               // rank 0's: the eight epilogue warps of the pair
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *epi_smem = reinterpret_cast<float *>(smem + C2_RING + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int BN = args.BN, BH = BN >> 1;
+    const int m_tiles = args.flat ? (args.R * args.H * args.W + CV_BM - 1) / CV_BM
+                                  : ((args.R + args.RB - 1) / args.RB) * args.h_blocks;
+    const int pm_tiles = (m_tiles + 1) >> 1;
+    const int n_tiles = args.N / BN;
+    const int num_ptiles = pm_tiles * n_tiles;
+    const int kb_per_tap = args.Cin / CV_BK, num_kb = args.taps * kb_per_tap;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    // this CTA's tile of pair-tile pt: m-tile 2*pm + rank, same n-tile
+#define C2_TILE(pt) conv_tile(args, (((pt) / n_tiles) * 2 + rank) * n_tiles + (pt) % n_tiles, n_tiles)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C2_STAGES; ++s) {
+            tc_mbar_init(&full_bar[s], 1);
+            tc_mbar_init(&afull_bar[s], 1);
+            tc_mbar_init(&conv_bar[s], 8);
+            tc_mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    if (MODE == 1) {
+        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += CV_THREADS)
+            epi_smem[i] = i < args.Cout ? (args.bias != nullptr ? __ldg(args.bias + i) : 0.f) : __ldg(args.w_l + i - args.Cout);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                  // both CTAs' barriers exist before anyone arrives on the peer's
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of the B tile =====
+        if (lane == 0) {
+            const uint32_t a_bytes = (args.flat ? CV_BM : args.W * args.HB * args.RB) * CV_BK * 4;
+            const uint32_t b_bytes = (PASSES == 3 ? 2 : 1) * BH * CV_BK * 4;
+            int it = 0;
+            for (int pt = pair; pt < num_ptiles; pt += num_pairs) {
+                const ConvTile t = C2_TILE(pt);
+                for (int tap = 0; tap < args.taps; ++tap) {
+                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0, dx = args.taps == 9 ? tap % 3 - 1 : 0;
+                    const int brow = tap * args.N + t.n0 + rank * BH;
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+                        const int s = it % C2_STAGES;
+                        tc_mbar_wait(&empty_bar[s], ((it / C2_STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * C2_STAGE;
+                        if (PASSES == 3) {
+                            tc_mbar_expect_tx(&afull_bar[s], a_bytes);
+                            tma_load_4d(st, &map_a, kb * CV_BK, t.c1 + dx, t.c2 + dy, t.c3, &afull_bar[s]);
+                            if (rank == 0) tc_mbar_expect_tx(&full_bar[s], 2 * b_bytes);
+                            tma_load_2d_2sm(st + C2_OFFB, &map_bhi, kb * CV_BK, brow, &full_bar[s]);
+                            tma_load_2d_2sm(st + C2_OFFB + C2_BH, &map_blo, kb * CV_BK, brow, &full_bar[s]);
+                        } else {
+                            if (rank == 0) tc_mbar_expect_tx(&full_bar[s], 2 * (a_bytes + b_bytes));
+                            tma_load_4d_2sm(st, &map_a, kb * CV_BK, t.c1 + dx, t.c2 + dy, t.c3, &full_bar[s]);
+                            tma_load_2d_2sm(st + C2_OFFB, &map_bhi, kb * CV_BK, brow, &full_bar[s]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: rank 0 only, one 256 x BN instruction per k step and pass =====
+        if (rank == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * CV_BM) >> 4) << 24);
+            int it = 0, local_tile = 0;
+            for (int pt = pair; pt < num_ptiles; pt += num_pairs, ++local_tile) {
+                const int a = local_tile & 1;
+                tc_mbar_wait(&tmem_empty[a], ((local_tile >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(a * CV_BN_MAX);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % C2_STAGES;
+                    const uint32_t par = (it / C2_STAGES) & 1;
+                    tc_mbar_wait(&full_bar[s], par);
+                    if (PASSES == 3) tc_mbar_wait(&conv_bar[s], par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t st = s_u32(smem + (size_t)s * C2_STAGE);
+                        const uint64_t a_hi = umma_desc_kmajor<CV_BK>(st), a_lo = umma_desc_kmajor<CV_BK>(st + CV_A);
+                        const uint64_t b_hi = umma_desc_kmajor<CV_BK>(st + C2_OFFB);
+                        const uint64_t b_lo = umma_desc_kmajor<CV_BK>(st + C2_OFFB + C2_BH);
+#pragma unroll
+                        for (int k = 0; k < CV_BK / 8; ++k) {
+                            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+                            umma_tf32_2sm(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if (PASSES == 3) {
+                                umma_tf32_2sm(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                                umma_tf32_2sm(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
+                            }
+                        }
+                        umma_commit_2sm(&empty_bar[s]);                       // both CTAs' ring slots
+                        if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[a]); // both CTAs' epilogues
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== operand splitters (both CTAs): own A tile -> A_hi in place, A_lo; arrive on rank 0's barrier =====
+        if (PASSES == 3) {
+            const int tid = threadIdx.x - 256;
+            int it = 0;
+            for (int pt = pair; pt < num_ptiles; pt += num_pairs) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % C2_STAGES;
+                    tc_mbar_wait(&afull_bar[s], (it / C2_STAGES) & 1);
+                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * C2_STAGE);
+                    float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * C2_STAGE + CV_A);
+                    if (!(args.debug & 2))
+#pragma unroll
+                    for (int j = 0; j < CV_A / 16 / 128; ++j) {
+                        const int i = j * 128 + tid;
+                        const float4 x = hi[i];
+                        float4 h;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                        hi[i] = h;
+                        lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive_leader(&conv_bar[s]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own 128 rows of D out of own tensor memory =====
+        const int ew = warp - 4;
+        float *epi_tile = epi_smem + ew * 32 * kEpiPitch;
+        int local_tile = 0;
+        for (int pt = pair; pt < num_ptiles; pt += num_pairs, ++local_tile) {
+            const int a = local_tile & 1;
+            const ConvTile t = C2_TILE(pt);
+            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * CV_BN_MAX);
+            if (!(args.debug & 1)) conv_epilogue_tile<MODE>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_leader(&tmem_empty[a]);
+        }
+    }
+#undef C2_TILE
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                  // the peer may still be reading this CTA's shared / tensor memory
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
 
@@ -287,6 +495,10 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
             bhi = ws; blo = ws + (size_t)rows * a.Cin;
         }
     }
+    const int m_tiles = a.flat ? ceil_div(a.R * a.H * a.W, CV_BM) : ceil_div(a.R, a.RB) * a.h_blocks;
+    if (const char *ed = getenv("FGN_TC_DEBUG")) a.debug = atoi(ed);
+    const char *e2 = getenv("FGN_TC_2SM");                       // development knob: 0 = single-CTA kernel
+    const bool two_sm = (a.BN % 32) == 0 && m_tiles >= 2 && !(e2 != nullptr && e2[0] == '0');
     CUtensorMap ma, mbh, mbl;
     bool ok;
     {
@@ -304,13 +516,31 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
         }
         ok = make_map_nd(&ma, x, 4, dims, strides, box);
         cuuint64_t bd[2] = {(cuuint64_t)a.Cin, (cuuint64_t)rows}, bs[1] = {(cuuint64_t)a.Cin * 4};
-        cuuint32_t bb[2] = {CV_BK, (cuuint32_t)a.BN};
+        cuuint32_t bb[2] = {CV_BK, (cuuint32_t)(two_sm ? a.BN / 2 : a.BN)};   // the pair kernel: half a B tile per CTA
         ok = ok && make_map_nd(&mbh, bhi, 2, bd, bs, bb) && make_map_nd(&mbl, blo, 2, bd, bs, bb);
     }
     if (!ok) { set_error("cuTensorMapEncodeTiled unavailable or failed (conv)"); return FGN_ERR_CUDA; }
     int sm_count = 0;
     if (int rc = current_sm_count(&sm_count)) return rc;
-    const int m_tiles = a.flat ? ceil_div(a.R * a.H * a.W, CV_BM) : ceil_div(a.R, a.RB) * a.h_blocks;
+    if (two_sm) {
+        const int pairs = min(sm_count / 2, ceil_div(m_tiles, 2) * (a.N / a.BN));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(CV_THREADS); cfg.dynamicSmemBytes = C2_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+#define FGN_C2_LAUNCH(PS, MD)                                                                        \
+    do {                                                                                             \
+        FGN_SMEM_OPTIN((conv_tc2_kernel<PS, MD>), C2_SMEM);                                          \
+        FGN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<PS, MD>, ma, mbh, mbl, a));             \
+    } while (0)
+        if (mode == 0) { if (precision == 0) FGN_C2_LAUNCH(3, 0); else FGN_C2_LAUNCH(1, 0); }
+        else           { if (precision == 0) FGN_C2_LAUNCH(3, 1); else FGN_C2_LAUNCH(1, 1); }
+#undef FGN_C2_LAUNCH
+        FGN_LAUNCH_OK();
+        return FGN_OK;
+    }
     const int grid = min(sm_count, m_tiles * (a.N / a.BN));
 #define FGN_CV_LAUNCH(PS, MD)                                                                        \
     do {                                                                                             \
@@ -322,6 +552,28 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
 #undef FGN_CV_LAUNCH
     FGN_LAUNCH_OK();
     return FGN_OK;
+}
+
+// The plain contraction C[M,N] = A[M,K] B[N,K]^T (+ bias [+ residual], ReLU) on the CTA-pair kernel: the relation conv and the
+// heads' 1x1 convolutions (dense operands: lda == ldb == K, ldc == N).  *taken = false when the shape does not qualify.
+int gemm_nt_tc2(const float *A, const float *B, int ldb, const float *bias, float *C, int M, int N, int K, int precision,
+                float *split_ws, cudaStream_t st, bool presplit, const float *residual, bool relu, bool *taken)
+{
+    *taken = false;
+    if (precision != 0 && ldb != K) return FGN_OK;                 // one TF32 pass reads B in place: dense rows only
+    if (M < 2 * CV_BM || (K % CV_BK) != 0 || (N % 32) != 0 || (N > CV_BN_MAX && (N % CV_BN_MAX) != 0)) return FGN_OK;
+    if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return FGN_OK;
+    if (precision == 0 && split_ws == nullptr) return FGN_OK;
+    ConvArgs a = {};
+    a.bias = bias; a.residual = residual; a.out = C;
+    a.R = M; a.H = 1; a.W = 1; a.Cin = K; a.Cout = N;
+    a.N = N; a.BN = N > CV_BN_MAX ? CV_BN_MAX : N;
+    a.flat = 1; a.taps = 1; a.HB = 1; a.RB = 1; a.h_blocks = 1; a.relu = relu ? 1 : 0;
+    if (precision == 0 && !presplit)
+        if (int rcs = gemm_split_weights(B, ldb, N, K, split_ws, st)) return rcs;
+    const int rc = conv_tc_launch(0, A, B, split_ws, a, precision, nullptr, 0, st);
+    if (rc == FGN_OK) *taken = true;
+    return rc;
 }
 
 }  // namespace fgn

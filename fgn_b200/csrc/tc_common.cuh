@@ -117,6 +117,63 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile
     __syncwarp();
 }
 
+// ---- CTA-pair (cta_group::2) variants ---------------------------------------------------------------
+// Two CTAs of a cluster on the two SMs of a TPC run ONE 256-row MMA: each holds its own 128 rows of A and HALF of the
+// B tile, so a k-block costs each SM half the B bytes of the single-CTA kernel.  Barriers the MMA issuer (CTA rank 0)
+// waits on live in rank 0's shared memory; rank 1 reaches them by clearing the rank bit of the shared::cluster address
+// (cute::Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on rank 0's copy of `bar`.  Default (cta-scope release) semantics as in cutlass::arch::umma_arrive_2x1SM_sm0: an
+// explicit .release.cluster makes ptxas emit MEMBAR.ALL.GPU in front of every arrive (measured: the 3xTF32 pair kernel
+// ran 1.6x SLOWER than the single-CTA one with it); the splitters' writes are ordered by their fence.proxy.async.
+__device__ __forceinline__ void tc_mbar_arrive_leader(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// loads issued by either CTA of the pair whose bytes are counted on rank 0's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & kPeerMask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar)            // arrives on `bar` in BOTH CTAs when the MMAs retire
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(s_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // ---- host side: the driver entry point that encodes TMA descriptors ---------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

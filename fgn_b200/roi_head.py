@@ -27,9 +27,13 @@ class _Bottleneck(nn.Module):
     over the NHWC RoI tiles -- BatchNorm folded into the weights, ReLU and the identity branch in the
     epilogues: the 1x1s on the contraction kernel (ops.conv1x1), the 3x3 as an implicit GEMM whose taps are shifted,
     zero-filled TMA boxes of the same tensor (ops.conv3x3).  ``tc_1x1=False`` / ``tc_3x3=False`` (or training) run the plain
-    torch modules."""
+    torch modules.  ``tc_3x3="auto"`` (default): the library's 3x3 whenever the convolutions run in TF32
+    (``torch.backends.cudnn.allow_tf32``, PyTorch's default and the reference's); under strict fp32 the 3x3 stays on cuDNN,
+    because the tensor core's fp32 accumulator truncates -- over K = 9*512 products the 3xTF32 route ends 1.2e-3 (7e-5 of
+    the output scale) from fp64 after three bottlenecks where cuDNN fp32 ends 1.6e-5 (tools/diag_c4_head.py); ``True``
+    takes the 3xTF32 route anyway (5x faster than cuDNN fp32, profiles/r02_heads_tcgen05_vs_cudnn.jsonl)."""
 
-    def __init__(self, inplanes: int, planes: int, tc_1x1: bool = True, tc_3x3: bool = True):
+    def __init__(self, inplanes: int, planes: int, tc_1x1: bool = True, tc_3x3="auto"):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
@@ -70,11 +74,11 @@ class _Bottleneck(nn.Module):
             w3, b3 = self._fold(self.conv3, self.bn3)
             t2 = ops.conv_taps(w2)
             self._folded = dict(device=x.device, prec=prec, w1=w1.flatten(1), b1=b1, t2=t2, b2=b2, w3=w3.flatten(1), b3=b3,
-                                s2=ops.conv_split_weights(t2) if (prec == "fp32" and self.tc_3x3) else None)
+                                s2=ops.conv_split_weights(t2) if (prec == "fp32" and self.tc_3x3 is True) else None)
         f = self._folded
         xc = x if ops.storage_layout(x) == ops.LAYOUT_NHWC else ops.to_nhwc(x.contiguous())
         out = ops.conv1x1(xc, f["w1"], f["b1"], relu=True)
-        if self.tc_3x3:
+        if self.tc_3x3 is True or (self.tc_3x3 == "auto" and prec == "tf32"):
             out = ops.conv3x3(out, f["t2"], f["b2"], relu=True, precision=prec, w_split=f["s2"])
         else:
             out = self.relu(self.bn2(self.conv2(out)))

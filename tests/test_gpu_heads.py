@@ -124,6 +124,7 @@ def test_bottleneck_three_convs_on_tcgen05(prec_tf32):
             bn.weight.copy_(1 + 0.2 * torch.randn(bn.num_features, generator=g))
             bn.bias.copy_(0.1 * torch.randn(bn.num_features, generator=g))
     blk.eval()
+    blk.tc_3x3 = True                                                    # ("auto" keeps the 3x3 on cuDNN under strict fp32)
     x = torch.randn(61, 256, 7, 7, generator=g)
     old = torch.backends.cudnn.allow_tf32
     try:

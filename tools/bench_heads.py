@@ -31,7 +31,7 @@ for tf32 in (True, False):
         x = torch.randn(r, 7, 7, 1024, device=dev).permute(0, 3, 1, 2)
         with torch.no_grad():
             for m in head:
-                m.tc_1x1, m.tc_3x3 = True, True
+                m.tc_1x1, m.tc_3x3 = True, True              # (True: the library's 3x3 under strict fp32 too)
             a = head(x)
             t_tc = timed(lambda: head(x))
             for m in head:

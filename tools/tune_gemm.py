@@ -10,21 +10,23 @@ for M, N, K in shapes:
     a = [torch.randn(M, K, generator=g).to(dev) for _ in range(4)]
     w = (torch.randn(N, 2 * K, generator=g) * (1.0 / K) ** 0.5).to(dev)
     want = (a[0].double() @ w[:, :K].double().t()).float()
-    for bk, pair in ((16, 0), (32, 0)):
+    wq = w[:, :K].contiguous()
+    for bk, pair in ((16, 0), (16, 2)):
         for prec in ("fp32", "tf32"):
             os.environ["FGN_GEMM_BK"] = str(bk)
-            got = ops.gemm_nt(a[0], w[:, :K], None, prec)
+            os.environ["FGN_GEMM_2SM"] = "1" if pair else "0"
+            got = ops.gemm_nt(a[0], wq, None, prec)
             err = float((got - want).abs().max())
             for _ in range(3):
                 for x in a:
-                    ops.gemm_nt(x, w[:, :K], None, prec)
+                    ops.gemm_nt(x, wq, None, prec)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             reps = 10
             for _ in range(reps):
                 for x in a:
-                    ops.gemm_nt(x, w[:, :K], None, prec)
+                    ops.gemm_nt(x, wq, None, prec)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (reps * len(a))
