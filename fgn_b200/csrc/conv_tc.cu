@@ -68,12 +68,13 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvArgs &a, int tile, int n
 }
 
 // One tile's epilogue for one epilogue warp (TMEM lanes 32*ew .. +31 of the accumulator at taddr).
+// MODE 0 covers the tile's columns [cbeg, cend) (two warp groups can share a tile); MODE 1 reduces over all of them.
 template <int MODE>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs &args, const ConvTile &t, uint32_t taddr, float *epi_tile,
-                                                   const float *epi_smem, int lane, int ew, int BN)
+                                                   const float *epi_smem, int lane, int ew, int BN, int cbeg = 0, int cend = 1 << 30)
 {
     if (MODE == 0) {
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cbeg; c0 < min(BN, cend); c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)c0, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -150,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (MODE == 1) {
         // deconv bias [Cout] and logits weights [ncls, Cout] staged once: the epilogue reads them as broadcasts
-        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += CV_THREADS)
+        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += blockDim.x)
             epi_smem[i] = i < args.Cout ? (args.bias != nullptr ? __ldg(args.bias + i) : 0.f) : __ldg(args.w_l + i - args.Cout);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -285,11 +286,12 @@ struct C2Ring {                                               // 192 KB of ring 
     static constexpr int kStages = PASSES == 3 ? 6 : 12;     // the loop is latency-bound (~2.5 us from a freed slot to its MMAs): depth is throughput
     static constexpr int kOffB = PASSES == 3 ? 2 * CV_A : CV_A;
 };
+constexpr int C2_THREADS = 512;                               // + warps 12-15: a second epilogue group
 constexpr int C2_RING = 6 * (2 * CV_A + 2 * C2_BH);
-constexpr int C2_SMEM = C2_RING + 1024 + 512 + kEpiBytes;
+constexpr int C2_SMEM = C2_RING + 1024 + 512 + 2 * kEpiBytes;
 
 template <int PASSES, int MODE>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                 const __grid_constant__ CUtensorMap map_blo, const ConvArgs args)
 {
@@ -326,7 +328,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tc_mbar_init(&conv_bar[s], 8);
             tc_mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], MODE == 0 ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -334,7 +336,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += CV_THREADS)
+        for (int i = threadIdx.x; i < args.Cout * (1 + args.ncls); i += blockDim.x)
             epi_smem[i] = i < args.Cout ? (args.bias != nullptr ? __ldg(args.bias + i) : 0.f) : __ldg(args.w_l + i - args.Cout);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -410,7 +412,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ===== operand splitters (both CTAs): own A tile -> A_hi in place, A_lo; arrive on rank 0's barrier =====
         if (PASSES == 3) {
             const int tid = threadIdx.x - 256;
@@ -441,20 +443,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue (both CTAs): own 128 rows of D out of own tensor memory =====
-        const int ew = warp - 4;
-        float *epi_tile = epi_smem + ew * 32 * kEpiPitch;
-        int local_tile = 0;
-        for (int pt = pair; pt < num_ptiles; pt += num_pairs, ++local_tile) {
-            const int a = local_tile & 1;
-            const ConvTile t = C2_TILE(pt);
-            tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * CV_BN_MAX);
-            if (!(args.debug & 1)) conv_epilogue_tile<MODE>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive_leader(&tmem_empty[a]);
+        // ===== epilogue (both CTAs): own 128 rows of D out of own tensor memory.  MODE 0: two groups of four warps (4-7 and
+        // 12-15; a warp reaches the TMEM lane quarter warp % 4) take half of the tile's columns each -- one group needs
+        // ~8.5 us per 128 x 256 tile, more than the 6.8 us of a K = 256 mainloop it is supposed to hide behind.
+        const int ew = warp & 3, grp = warp >= 12 ? 1 : 0;
+        if (MODE == 0 || grp == 0) {
+            float *epi_tile = epi_smem + (grp * 4 + ew) * 32 * kEpiPitch;
+            const int half = ((BN / 32 + 1) / 2) * 32;                      // column split between the groups (chunk-aligned)
+            int local_tile = 0;
+            for (int pt = pair; pt < num_ptiles; pt += num_pairs, ++local_tile) {
+                const int a = local_tile & 1;
+                const ConvTile t = C2_TILE(pt);
+                tc_mbar_wait(&tmem_full[a], (local_tile >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * CV_BN_MAX);
+                if (!(args.debug & 1)) {
+                    if (MODE == 0) conv_epilogue_tile<MODE>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN, grp ? half : 0, grp ? BN : half);
+                    else           conv_epilogue_tile<MODE>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive_leader(&tmem_empty[a]);
+            }
         }
     }
 #undef C2_TILE
@@ -525,7 +535,7 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
     if (two_sm) {
         const int pairs = min(sm_count / 2, ceil_div(m_tiles, 2) * (a.N / a.BN));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(CV_THREADS); cfg.dynamicSmemBytes = C2_SMEM; cfg.stream = st;
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(C2_THREADS); cfg.dynamicSmemBytes = C2_SMEM; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

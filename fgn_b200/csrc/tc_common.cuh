@@ -80,9 +80,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 // Epilogue store of one 32-row x 32-column accumulator chunk held row-per-lane (tcgen05.ld 32x32b.x32).
 // Storing it straight from registers makes every warp-wide 128-bit store touch 32 different rows
 // (32 half-written sectors); that alone bounded the K=256 contraction (epilogue ~12 us per tile vs
-// 6.3 us of MMAs).  The chunk is transposed through a padded shared-memory tile instead, and each
+// 6.3 us of MMAs).  The chunk is transposed through a 4 KB shared-memory tile instead (128-byte rows, the 16-byte
+// chunk j of row r stored at chunk j ^ (r & 7): conflict-free both ways without padding), and each
 // store instruction then writes 4 complete 128-byte row segments.
-constexpr int kEpiPitch = 36;                                  // floats per staged row: 16-byte aligned, conflict-free
+constexpr int kEpiPitch = 32;                                  // floats per staged row
 constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;              // four epilogue warps
 
 __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile, int lane, int row0, int M,
@@ -93,8 +94,8 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile
     float4 *mine = reinterpret_cast<float4 *>(tile + lane * kEpiPitch);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        mine[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        mine[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     __syncwarp();
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     const bool col_ok = col0 + c4 < N;
@@ -103,7 +104,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], float *tile
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + sub;
-        float4 o = *reinterpret_cast<const float4 *>(tile + rr * kEpiPitch + c4);
+        float4 o = *reinterpret_cast<const float4 *>(tile + rr * kEpiPitch + (((lane & 7) ^ (rr & 7)) << 2));
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
         if (row0 + rr < M && col_ok) {
             if (residual != nullptr) {               // (+ identity branch of a bottleneck, same leading dimension as C)
