@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfgn_b200.so")
 
 FGN_MAX_LEVELS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 
@@ -66,6 +66,9 @@ SIGNATURES = {
     "fgn_nchw_to_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_nhwc_to_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_support_mask_pool": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "fgn_support_prologue_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fgn_support_prologue_fwd": (c_int, [POINTER(Pyramid), c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+                                         _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "fgn_support_pool": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P]),
     "fgn_attention_vectors_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "fgn_attention_vectors": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
@@ -77,7 +80,7 @@ SIGNATURES = {
     "fgn_relation_fusion_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_relation_split_weights_bytes": (c_size_t, [c_int]),
     "fgn_relation_split_weights": (c_int, [_P, c_int, _P, _P]),
-    "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
+    "fgn_relation_fusion_fwd": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                         _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "fgn_relation_fusion_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -109,7 +112,7 @@ SIGNATURES = {
     "fgn_support_pool_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "fgn_guided_roi_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fgn_guided_roi_fused_fwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float,
-                                         _P, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
+                                         _P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                          _P, _P, _P, c_int, _P, c_size_t, _P]),
 }
 

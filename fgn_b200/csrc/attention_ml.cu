@@ -1,5 +1,5 @@
-// attention_ml.cu -- AG-RPN attention (fgn_ag_rpn_head.py:37-46) for a whole pyramid in three
-// launches instead of three per level: the coarse levels (P5, P6) are a few KB and purely
+// attention_ml.cu -- AG-RPN attention (fgn_ag_rpn_head.py:37-46) for a whole pyramid in two
+// launches (class vectors; multiply) instead of three per level: the coarse levels (P5, P6) are a few KB and purely
 // launch-latency bound when done one by one.  NHWC (channels_last) only; other layouts go through
 // the per-level entry points.
 #include "common.cuh"
@@ -25,10 +25,37 @@ __device__ __forceinline__ int ml_level_of(const MlLevels &lv, int blk)
     return l;
 }
 
+// The last slab block of a (level, class) to arrive adds that pair's partial sums in slab order (the order of the old
+// finalize launch: bitwise the same vectors) -- one launch instead of two; the counters are zeroed by a memset node.
+__device__ __forceinline__ void ml_finish(const MlLevels &lv, const int l, const int bn, const int BN, const int K, const int C,
+                                          const float *partial, float *__restrict__ vec, unsigned int *counters)
+{
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&counters[l * BN + bn], 1u) == (unsigned)(lv.blk_off[l + 1] - lv.blk_off[l] - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float inv = 1.0f / (float)(K * lv.HW[l]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int b0 = lv.blk_off[l]; b0 < lv.blk_off[l + 1]; b0 += 8) {   // eight loads in flight, added in slab order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = b0 + j < lv.blk_off[l + 1] ? __ldcg(partial + ((size_t)(b0 + j) * BN + bn) * C + c) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (b0 + j < lv.blk_off[l + 1]) s += v[j];
+        }
+        vec[((size_t)l * BN + bn) * C + c] = s * inv;
+    }
+}
+
 // partial[(blk_off[l] + slab) * BN + bn][C] = sum over the slab's pixels (K consecutive images = one run)
 __global__ void __launch_bounds__(256)
 attention_vec_ml_partial_kernel(const MlLevels lv, const int BN, const int K, const int C,
-                                float *__restrict__ partial)
+                                float *partial, float *__restrict__ vec, unsigned int *counters)
 {
     const int bn = blockIdx.y;
     const int l = ml_level_of(lv, blockIdx.x), slab = blockIdx.x - lv.blk_off[l];
@@ -53,18 +80,7 @@ attention_vec_ml_partial_kernel(const MlLevels lv, const int BN, const int K, co
         for (int rr = 0; rr < rows; ++rr) s += red[(size_t)rr * C + c];
         partial[((size_t)blockIdx.x * BN + bn) * C + c] = s;
     }
-}
-
-// vec[l][bn][c] = (sum of the level's slabs, in slab order) / (K*HW_l)
-__global__ void attention_vec_ml_finalize_kernel(const MlLevels lv, const int BN, const int K, const int C,
-                                                 const float *__restrict__ partial, float *__restrict__ vec)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= lv.L * BN * C) return;
-    const int c = idx % C, bn = (idx / C) % BN, l = idx / (C * BN);
-    float s = 0.f;
-    for (int b = lv.blk_off[l]; b < lv.blk_off[l + 1]; ++b) s += partial[((size_t)b * BN + bn) * C + c];
-    vec[idx] = s * (1.0f / (float)(K * lv.HW[l]));
+    ml_finish(lv, l, bn, BN, K, C, partial, vec, counters);
 }
 
 // out_l[b*N+n, :, :, c] = qry_l[b, :, :, c] * vec[l][b*N+n][c]; one read, N streaming writes
@@ -117,7 +133,7 @@ __device__ __forceinline__ unsigned pack2(float a, float b)       // round to ne
 
 __global__ void __launch_bounds__(256)
 attention_vec_ml_partial_bf16_kernel(const MlLevels lv, const int BN, const int K, const int C,
-                                     float *__restrict__ partial)
+                                     float *partial, float *__restrict__ vec, unsigned int *counters)
 {
     const int bn = blockIdx.y;
     const int l = ml_level_of(lv, blockIdx.x), slab = blockIdx.x - lv.blk_off[l];
@@ -145,6 +161,7 @@ attention_vec_ml_partial_bf16_kernel(const MlLevels lv, const int BN, const int 
         for (int rr = 0; rr < rows; ++rr) s += red[(size_t)rr * C + c];
         partial[((size_t)blockIdx.x * BN + bn) * C + c] = s;
     }
+    ml_finish(lv, l, bn, BN, K, C, partial, vec, counters);
 }
 
 __global__ void __launch_bounds__(256)
@@ -206,7 +223,7 @@ extern "C" size_t fgn_attention_vectors_ml_workspace_bytes(const fgn_pyramid_t *
     size_t blocks = 0;
     for (int l = 0; l < spp->num_levels && l < FGN_MAX_LEVELS; ++l)
         blocks += (size_t)ceil_div(K * spp->H[l] * spp->W[l], kMlSlab);
-    return blocks * BN * C * sizeof(float);
+    return ((blocks * BN * C * sizeof(float) + 255) & ~(size_t)255) + (size_t)FGN_MAX_LEVELS * BN * sizeof(unsigned int);
 }
 
 static int attention_vectors_ml_impl(const fgn_pyramid_t *spp, int BN, int K, int C, float *vec, void *workspace,
@@ -245,12 +262,12 @@ static int attention_vectors_ml_impl(const fgn_pyramid_t *spp, int BN, int K, in
     FGN_CHECK_ARG(BN <= 65535, "BN too large");
     cudaStream_t st = (cudaStream_t)stream;
     const int cvec = bf16 ? C >> 3 : C >> 2, rows = max(1, 256 / cvec);
+    unsigned int *counters = (unsigned int *)((char *)workspace + (((size_t)lv.blk_off[lv.L] * BN * C * sizeof(float) + 255) & ~(size_t)255));
+    FGN_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)lv.L * BN * sizeof(unsigned int), st));
     if (bf16) attention_vec_ml_partial_bf16_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
-                  lv, BN, K, C, (float *)workspace);
+                  lv, BN, K, C, (float *)workspace, vec, counters);
     else      attention_vec_ml_partial_kernel<<<dim3(lv.blk_off[lv.L], BN), 256, (size_t)rows * C * 4, st>>>(
-                  lv, BN, K, C, (float *)workspace);
-    FGN_LAUNCH_OK();
-    attention_vec_ml_finalize_kernel<<<ceil_div(lv.L * BN * C, 256), 256, 0, st>>>(lv, BN, K, C, (const float *)workspace, vec);
+                  lv, BN, K, C, (float *)workspace, vec, counters);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

@@ -249,7 +249,7 @@ extern "C" int fgn_nchw_to_nhwc(const float *, int, int, int, int, float *, void
 // when the weights were loaded instead of by two launches per call.  rois5 (optional, instead of roi_batch): the [R,5]
 // RoI tensor, whose first column is the batch index.
 static int relation_fusion_impl(const float *roi_feat, int feat_layout, const int32_t *roi_batch, const float *rois5,
-                                const float *spp_cat_mean, int R, int B, int N, int C, int P, const float *conv_w,
+                                const float *spp_cat_mean, const float *class_term, int R, int B, int N, int C, int P, const float *conv_w,
                                 const float *conv_w_split, const float *conv_b, const float *gn_w, const float *gn_b,
                                 int gn_groups, float gn_eps, const float *fc_cls_w, const float *fc_cls_b,
                                 const float *fc_reg_w, const float *fc_reg_b, float *cls_out, float *reg_out,
@@ -261,7 +261,7 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     FGN_CHECK_ARG(precision == 0 || precision == 1, "precision=%d", precision);
     if (R == 0) return FGN_OK;
     if (P * P != kMaxPP) { set_error("relation_fusion: P=%d not instantiated (7)", P); return FGN_ERR_UNSUPPORTED; }
-    FGN_CHECK_ARG(roi_feat && (roi_batch || rois5) && spp_cat_mean && conv_w && conv_b && gn_w && gn_b &&
+    FGN_CHECK_ARG(roi_feat && (roi_batch || rois5) && (spp_cat_mean || class_term) && conv_w && conv_b && gn_w && gn_b &&
                   fc_cls_w && fc_cls_b && fc_reg_w && fc_reg_b && cls_out && reg_out, "NULL pointer");
     const int BN = B * N, PP = P * P;
     const size_t need = fgn_relation_fusion_workspace_bytes(R, BN, C, P);
@@ -277,8 +277,10 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     if (feat_layout == FGN_LAYOUT_NCHW) {
         int rc = fgn_nchw_to_nhwc(roi_feat, R, C, P, P, w.xq_nhwc, stream);
         if (rc) return rc;
-        rc = fgn_nchw_to_nhwc(spp_cat_mean, BN, C, P, P, w.xs_nhwc, stream);
-        if (rc) return rc;
+        if (class_term == nullptr) {
+            rc = fgn_nchw_to_nhwc(spp_cat_mean, BN, C, P, P, w.xs_nhwc, stream);
+            if (rc) return rc;
+        }
         xq = w.xq_nhwc; xs = w.xs_nhwc;
     }
     // Yq = Xq Wq^T ; Ys = Xs Ws^T + bias        (conv_w is [C, 2C] row-major)
@@ -286,8 +288,13 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     float *split_s = conv_w_split ? const_cast<float *>(conv_w_split) + (size_t)2 * C * C : w.split_s;
     int rc = gemm_nt(xq, C, conv_w, 2 * C, nullptr, w.yq, C, R * PP, C, C, precision, split_q, st, conv_w_split != nullptr);
     if (rc) return rc;
-    rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, split_s, st, conv_w_split != nullptr);
-    if (rc) return rc;
+    // class_term: Ys precomputed by fgn_support_prologue_fwd (exact fp32) -- one launch less per call
+    const float *ys = class_term;
+    if (ys == nullptr) {
+        rc = gemm_nt(xs, C, conv_w + C, 2 * C, conv_b, w.ys, C, BN * PP, C, C, precision, split_s, st, conv_w_split != nullptr);
+        if (rc) return rc;
+        ys = w.ys;
+    }
 
     const int cg = C / gn_groups;
     FGN_CHECK_ARG(cg <= kEpiThreads, "channels per group %d > %d", cg, kEpiThreads);
@@ -304,11 +311,11 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     float *direct = nblk == 1 ? cls_out : nullptr;
     if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
-            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
+            w.yq, ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
             rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);
     else
         relation_epilogue_kernel<kMaxPP, false><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
-            w.yq, w.ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
+            w.yq, ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
             rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);
     FGN_LAUNCH_OK();
     if (direct == nullptr) {
@@ -333,7 +340,7 @@ extern "C" int fgn_relation_split_weights(const float *conv_w, int C, float *out
 }
 
 extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
-                                       const int32_t *roi_batch, const float *spp_cat_mean, int R,
+                                       const int32_t *roi_batch, const float *spp_cat_mean, const float *class_term, int R,
                                        int B, int N, int C, int P, const float *conv_w, const float *conv_w_split,
                                        const float *conv_b, const float *gn_w, const float *gn_b,
                                        int gn_groups, float gn_eps, const float *fc_cls_w,
@@ -342,7 +349,7 @@ extern "C" int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout,
                                        float *raw_cls_out, float *raw_reg_out, int precision,
                                        void *workspace, size_t workspace_bytes, void *stream)
 {
-    return relation_fusion_impl(roi_feat, feat_layout, roi_batch, nullptr, spp_cat_mean, R, B, N, C, P, conv_w, conv_w_split,
+    return relation_fusion_impl(roi_feat, feat_layout, roi_batch, nullptr, spp_cat_mean, class_term, R, B, N, C, P, conv_w, conv_w_split,
                                 conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b, fc_reg_w, fc_reg_b, cls_out,
                                 reg_out, raw_cls_out, raw_reg_out, precision, workspace, workspace_bytes, stream);
 }
@@ -467,7 +474,7 @@ extern "C" size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int
 
 extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois,
                                         int R, int P, int sampling_ratio, int aligned,
-                                        float finest_scale, const float *spp_cat_mean, int N,
+                                        float finest_scale, const float *spp_cat_mean, const float *class_term, int N,
                                         const float *conv_w, const float *conv_w_split, const float *conv_b,
                                         const float *gn_w, const float *gn_b, int gn_groups,
                                         float gn_eps, const float *fc_cls_w, const float *fc_cls_b,
@@ -490,7 +497,7 @@ extern "C" int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, 
                                   finest_scale, nullptr, nullptr, feat, FGN_LAYOUT_NHWC, lvl_out, stream);
     if (rc) return rc;
     (void)rb;                                 // the epilogue reads the batch index from rois[:,0] itself
-    return relation_fusion_impl(feat, FGN_LAYOUT_NHWC, nullptr, rois, spp_cat_mean, R, B, N, C, P, conv_w, conv_w_split,
+    return relation_fusion_impl(feat, FGN_LAYOUT_NHWC, nullptr, rois, spp_cat_mean, class_term, R, B, N, C, P, conv_w, conv_w_split,
                                 conv_b, gn_w, gn_b, gn_groups, gn_eps, fc_cls_w, fc_cls_b,
                                 fc_reg_w, fc_reg_b, cls_out, reg_out, nullptr, nullptr, precision,
                                 ws, workspace_bytes - (size_t)(ws - (char *)workspace), stream);

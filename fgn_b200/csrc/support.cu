@@ -200,6 +200,220 @@ support_pool_nhwc_kernel(const float *__restrict__ f, const float *__restrict__ 
     }
 }
 
+// ---- the whole support branch in one launch (count_spp, fgn_roi_head.py:419-449, + the class term of :272) ----------
+// One CTA per (class bn, bin p): everything count_spp produces for that bin is local to it --
+//   K2  the mask's pooled value of bin p for each of the K shots: the bin's adaptive sampling grid (~30 x 30 samples of a
+//       256-px support) spread over the CTA's threads, per-axis samples (exact reference arithmetic) staged once;
+//   K3  the RoIAligned support features of bin p, all C channels, per shot: a warp per (shot, 128 channels) visiting the
+//       samples in the reference's order (the arithmetic of roi_align_small_nhwc_kernel, bit-exact against torchvision);
+//   K4  the class mean over the shots -> cat_mean[bn, p, :];  K5  this bin's share of the masked GAP;
+//   and the row of the relation conv's class term Ys[bn*P*P + p, :] = cat_mean[bn, p, :] Ws^T + bias (exact fp32: a warp
+//       per output channel, lanes striding k, fixed-order shuffle reduction) that the relation head otherwise computes
+//       with a launch of its own.
+// The masked GAP is the one cross-bin quantity: bins leave their shares in workspace and the LAST CTA of a class to
+// arrive (a counter per class, zeroed by a memset node in front of the launch) adds them in bin order -- deterministic,
+// no spinning, no co-residency assumption.  4 launches (16 + 14 + 11 + 10 us at cfg3) -> 1.
+constexpr int kProThreads = 256;
+constexpr int kProGcap = 64;                 // staged samples per axis; larger adaptive grids are evaluated on the fly
+
+__global__ void __launch_bounds__(kProThreads)
+support_prologue_kernel(const Pyramid pyr, const int C, const float *__restrict__ boxes, const uint8_t *__restrict__ mask,
+                        const int S_h, const int S_w, const int K, const int P, const float finest_scale,
+                        const float *__restrict__ conv_w, const float *__restrict__ conv_b,
+                        float *__restrict__ cat_mean, float *__restrict__ masked_gap, float *__restrict__ class_term,
+                        float *__restrict__ gap_part, unsigned int *__restrict__ counters)
+{
+    extern __shared__ __align__(16) float sm[];
+    // layout: f_s[K][C] | cm_s[C] | m_s[K] | red[8] | axis tables: low[2][gcap] high[2][gcap] (int), l[2][gcap] h[2][gcap]
+    float *f_s = sm, *cm_s = sm + (size_t)K * C, *m_s = cm_s + C, *red = m_s + K;
+    int   *t_low = reinterpret_cast<int *>(red + 8), *t_high = t_low + 2 * kProGcap;
+    float *t_l = reinterpret_cast<float *>(t_high + 2 * kProGcap), *t_h = t_l + 2 * kProGcap;
+    __shared__ int s_last;
+    const int PP = P * P;
+    const int bn = blockIdx.x / PP, p = blockIdx.x % PP, ph = p / P, pw = p % P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- K2: pooled mask value of bin (ph, pw) for each shot (spatial_scale 1, adaptive grid, aligned=False) ----
+    for (int k = 0; k < K; ++k) {
+        const int m = bn * K + k;
+        const float roi[5] = {0.f, boxes[4 * m], boxes[4 * m + 1], boxes[4 * m + 2], boxes[4 * m + 3]};
+        const RoiGeom g = roi_geometry(roi, 1.0f, P, -1, 0);
+        const bool staged = g.grid_h <= kProGcap && g.grid_w <= kProGcap;
+        if (staged) {
+            for (int i = tid; i < 2 * kProGcap; i += kProThreads) {
+                const int axis = i / kProGcap, j = i % kProGcap;
+                if (j < (axis ? g.grid_w : g.grid_h)) {
+                    const AxisSample a = axis ? axis_sample(g.start_w, g.bin_w, g.grid_w, S_w, pw, j)
+                                              : axis_sample(g.start_h, g.bin_h, g.grid_h, S_h, ph, j);
+                    t_low[i] = a.valid ? a.low : -1; t_high[i] = a.high; t_l[i] = a.l; t_h[i] = a.h;
+                }
+            }
+        }
+        __syncthreads();
+        const uint8_t *mk = mask + (size_t)m * S_h * S_w;
+        float acc = 0.f;
+        const int ns = g.grid_h * g.grid_w;
+        for (int i = tid; i < ns; i += kProThreads) {
+            const int iy = i / g.grid_w, ix = i % g.grid_w;
+            int yl, yh, xl, xh; float fyl, fyh, fxl, fxh;
+            if (staged) {
+                yl = t_low[iy]; yh = t_high[iy]; fyl = t_l[iy]; fyh = t_h[iy];
+                xl = t_low[kProGcap + ix]; xh = t_high[kProGcap + ix]; fxl = t_l[kProGcap + ix]; fxh = t_h[kProGcap + ix];
+            } else {
+                const AxisSample y = axis_sample(g.start_h, g.bin_h, g.grid_h, S_h, ph, iy);
+                const AxisSample x = axis_sample(g.start_w, g.bin_w, g.grid_w, S_w, pw, ix);
+                yl = y.valid ? y.low : -1; yh = y.high; fyl = y.l; fyh = y.h;
+                xl = x.valid ? x.low : -1; xh = x.high; fxl = x.l; fxh = x.h;
+            }
+            if (yl < 0 || xl < 0) continue;
+            const float v1 = mk[(size_t)yl * S_w + xl] ? 1.f : 0.f, v2 = mk[(size_t)yl * S_w + xh] ? 1.f : 0.f;
+            const float v3 = mk[(size_t)yh * S_w + xl] ? 1.f : 0.f, v4 = mk[(size_t)yh * S_w + xh] ? 1.f : 0.f;
+            acc += __fmul_rn(fyh, fxh) * v1 + __fmul_rn(fyh, fxl) * v2 + __fmul_rn(fyl, fxh) * v3 + __fmul_rn(fyl, fxl) * v4;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < kProThreads / 32; ++w) s += red[w];
+            m_s[k] = __fdiv_rn(s, g.count);
+        }
+        __syncthreads();
+    }
+
+    // ---- K3: RoIAligned support features of this bin, per shot, all channels ----
+    // The bin's per-axis samples are evaluated one per lane (exact reference arithmetic) and handed round by shuffles, so
+    // the (iy, ix) loop is nothing but independent 128-bit corner loads -- visited and added in the reference's order.
+    const int nblk = (C + 127) >> 7;
+    for (int t = warp; t < K * nblk; t += kProThreads / 32) {
+        const int k = t / nblk, c = min((t % nblk) * 128 + lane * 4, C - 4);   // (lanes past C recompute the last vector)
+        const int m = bn * K + k;
+        const float roi[5] = {(float)m, boxes[4 * m], boxes[4 * m + 1], boxes[4 * m + 2], boxes[4 * m + 3]};
+        const int lvl = roi_level(roi, pyr, finest_scale);
+        const RoiGeom g = roi_geometry(roi, pyr.scale[lvl], P, -1, 0, pyr.B);
+        const int H = pyr.H[lvl], W = pyr.W[lvl];
+        const float *f = pyr.feat[lvl] + (size_t)g.batch * H * W * C + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#define FGN_S(q) acc.q = __fadd_rn(acc.q, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.q), __fmul_rn(w2, v2.q)), \
+                                                              __fmul_rn(w3, v3.q)), __fmul_rn(w4, v4.q)))
+        if (g.grid_h <= 32 && g.grid_w <= 32) {
+            const AxisSample ys = axis_sample(g.start_h, g.bin_h, g.grid_h, H, ph, min(lane, max(g.grid_h - 1, 0)));
+            const AxisSample xs = axis_sample(g.start_w, g.bin_w, g.grid_w, W, pw, min(lane, max(g.grid_w - 1, 0)));
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const int yv = __shfl_sync(0xffffffffu, ys.valid, iy), ylo = __shfl_sync(0xffffffffu, ys.low, iy);
+                const int yhi = __shfl_sync(0xffffffffu, ys.high, iy);
+                const float yl = __shfl_sync(0xffffffffu, ys.l, iy), yh = __shfl_sync(0xffffffffu, ys.h, iy);
+                if (!yv) continue;
+#pragma unroll 4
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const int xv = __shfl_sync(0xffffffffu, xs.valid, ix), xlo = __shfl_sync(0xffffffffu, xs.low, ix);
+                    const int xhi = __shfl_sync(0xffffffffu, xs.high, ix);
+                    const float xl = __shfl_sync(0xffffffffu, xs.l, ix), xh = __shfl_sync(0xffffffffu, xs.h, ix);
+                    if (!xv) continue;
+                    const float w1 = __fmul_rn(yh, xh), w2 = __fmul_rn(yh, xl), w3 = __fmul_rn(yl, xh), w4 = __fmul_rn(yl, xl);
+                    const float4 v1 = ldg4(f + ((size_t)ylo * W + xlo) * C), v2 = ldg4(f + ((size_t)ylo * W + xhi) * C);
+                    const float4 v3 = ldg4(f + ((size_t)yhi * W + xlo) * C), v4 = ldg4(f + ((size_t)yhi * W + xhi) * C);
+                    FGN_S(x); FGN_S(y); FGN_S(z); FGN_S(w);
+                }
+            }
+        } else {
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const AxisSample y = axis_sample(g.start_h, g.bin_h, g.grid_h, H, ph, iy);
+                if (!y.valid) continue;
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const AxisSample x = axis_sample(g.start_w, g.bin_w, g.grid_w, W, pw, ix);
+                    if (!x.valid) continue;
+                    const float w1 = __fmul_rn(y.h, x.h), w2 = __fmul_rn(y.h, x.l);
+                    const float w3 = __fmul_rn(y.l, x.h), w4 = __fmul_rn(y.l, x.l);
+                    const float4 v1 = ldg4(f + ((size_t)y.low * W + x.low) * C), v2 = ldg4(f + ((size_t)y.low * W + x.high) * C);
+                    const float4 v3 = ldg4(f + ((size_t)y.high * W + x.low) * C), v4 = ldg4(f + ((size_t)y.high * W + x.high) * C);
+                    FGN_S(x); FGN_S(y); FGN_S(z); FGN_S(w);
+                }
+            }
+        }
+#undef FGN_S
+        *reinterpret_cast<float4 *>(f_s + (size_t)k * C + c) =
+            make_float4(__fdiv_rn(acc.x, g.count), __fdiv_rn(acc.y, g.count), __fdiv_rn(acc.z, g.count), __fdiv_rn(acc.w, g.count));
+    }
+    __syncthreads();
+
+    // ---- K4 + K5: class mean of the bin, and the bin's share of the masked GAP ----
+    const float invK = 1.0f / (float)K;
+    const size_t row = (size_t)bn * PP + p;
+    for (int c = tid; c < C; c += kProThreads) {
+        float s = 0.f, gap = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float v = f_s[(size_t)k * C + c];
+            s += v;
+            gap = fmaf(v, m_s[k], gap);
+        }
+        const float mean = K == 1 ? s : s * invK;
+        cm_s[c] = mean;
+        cat_mean[row * C + c] = mean;
+        gap_part[row * C + c] = gap;
+    }
+    __syncthreads();
+
+    // ---- the class term's row: Ys[row, n] = sum_c cat_mean[row, c] * conv_w[n, C + c] + conv_b[n] ----
+    if (class_term != nullptr) {
+        // a warp takes 8 output channels at a time: their weight vectors are all in flight before the first FMA
+        constexpr int NB = 8, NW = kProThreads / 32;
+        for (int n0 = warp * NB; n0 < C; n0 += NW * NB) {
+            float acc[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+            for (int k4 = lane * 4; k4 < C; k4 += 256) {              // two 128-wide k steps per trip: 16 vectors in flight
+                float4 w[2][NB];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        w[h][j] = (n0 + j < C && k4 + 128 * h < C) ? ldg4(conv_w + (size_t)(n0 + j) * 2 * C + C + k4 + 128 * h)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (k4 + 128 * h >= C) break;
+                    const float4 a = *reinterpret_cast<const float4 *>(cm_s + k4 + 128 * h);
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        acc[j] = fmaf(a.x, w[h][j].x, acc[j]); acc[j] = fmaf(a.y, w[h][j].y, acc[j]);
+                        acc[j] = fmaf(a.z, w[h][j].z, acc[j]); acc[j] = fmaf(a.w, w[h][j].w, acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = warp_sum(acc[j]);
+            if (lane < NB && n0 + lane < C) {
+                float o = acc[0];
+#pragma unroll
+                for (int j = 1; j < NB; ++j) o = lane == j ? acc[j] : o;
+                class_term[row * C + n0 + lane] = o + __ldg(conv_b + n0 + lane);
+            }
+        }
+    }
+
+    // ---- masked GAP: the last CTA of the class adds the bins' shares in bin order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&counters[bn], 1u) == (unsigned)(PP - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const float d = (float)(K * PP);
+        for (int c = tid; c < C; c += kProThreads) {
+            float s = 0.f;
+            for (int q0 = 0; q0 < PP; q0 += 8) {                  // eight loads in flight, added in bin order
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = q0 + j < PP ? __ldcg(gap_part + ((size_t)bn * PP + q0 + j) * C + c) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (q0 + j < PP) s += v[j];
+            }
+            masked_gap[(size_t)bn * C + c] = s / d;
+        }
+    }
+}
+
 // ---- K6: AG-RPN class attention vector (fgn_ag_rpn_head.py:37-41) ----------------------------
 // vec[bn,c] = mean over (k,h,w).  NCHW: one warp per (bn,c) streams K contiguous h*w planes
 // with 128-bit loads where alignment allows and shuffle-reduces.  NHWC: two deterministic
@@ -362,6 +576,45 @@ extern "C" int fgn_attention_vectors(const float *x, int layout, int BN, int K, 
     FGN_LAUNCH_OK();
     attention_vec_finalize_kernel<<<ceil_div(BN * C, 256), 256, 0, st>>>(
         (const float *)workspace, BN, C, slabs, 1.0f / (float)total, vec);
+    FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+static size_t align256s(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t fgn_support_prologue_workspace_bytes(int BN, int C, int P)
+{
+    if (BN <= 0 || C <= 0 || P <= 0) return 0;
+    return align256s((size_t)BN * P * P * C * sizeof(float)) + align256s((size_t)BN * sizeof(unsigned int));
+}
+
+extern "C" int fgn_support_prologue_fwd(const fgn_pyramid_t *spp, int C, const float *boxes, const uint8_t *masks,
+                                        int S_h, int S_w, int BN, int K, int P, float finest_scale,
+                                        const float *conv_w, const float *conv_b, float *cat_mean, float *masked_gap,
+                                        float *class_term, void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(spp != nullptr && spp->num_levels >= 1 && spp->num_levels <= FGN_MAX_LEVELS, "bad pyramid");
+    FGN_CHECK_ARG(BN >= 0 && K > 0 && C > 0 && P > 0 && S_h > 0 && S_w > 0, "bad dims BN=%d K=%d C=%d P=%d S=%dx%d", BN, K, C, P, S_h, S_w);
+    if (BN == 0) return FGN_OK;
+    FGN_CHECK_ARG(boxes && masks && cat_mean && masked_gap, "NULL pointer");
+    FGN_CHECK_ARG(class_term == nullptr || (conv_w != nullptr && conv_b != nullptr), "class_term needs conv_w and conv_b");
+    for (int l = 0; l < spp->num_levels; ++l) FGN_CHECK_ARG(spp->feat[l], "level %d pointer is NULL", l);
+    if ((C & 3) != 0) { set_error("support_prologue: C=%d must be a multiple of 4", C); return FGN_ERR_UNSUPPORTED; }
+    const size_t smem = ((size_t)K * C + C + K + 8 + 8 * kProGcap) * sizeof(float);
+    if (smem > 200 * 1024) { set_error("support_prologue: K*C = %d*%d does not fit shared memory", K, C); return FGN_ERR_UNSUPPORTED; }
+    const size_t need = fgn_support_prologue_workspace_bytes(BN, C, P);
+    if (!workspace || workspace_bytes < need) {
+        set_error("support_prologue: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    float *gap_part = (float *)workspace;
+    unsigned int *counters = (unsigned int *)((char *)workspace + align256s((size_t)BN * P * P * C * sizeof(float)));
+    cudaStream_t st = (cudaStream_t)stream;
+    FGN_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)BN * sizeof(unsigned int), st));
+    const Pyramid d = to_device_pyramid(spp, BN * K);
+    FGN_SMEM_OPTIN(support_prologue_kernel, smem);
+    support_prologue_kernel<<<BN * P * P, kProThreads, smem, st>>>(d, C, boxes, masks, S_h, S_w, K, P, finest_scale, conv_w, conv_b,
+                                                                 cat_mean, masked_gap, class_term, gap_part, counters);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }

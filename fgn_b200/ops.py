@@ -306,6 +306,48 @@ def support_pool(f: torch.Tensor, m: torch.Tensor, n_ways: int, k_shots: int, ou
         gap.view(b, n_ways, c, 1, 1)
 
 
+def support_prologue(spp_feats: Sequence[torch.Tensor], scales: Sequence[float], spp_bboxes: torch.Tensor,
+                     spp_isegmaps: torch.Tensor, n_ways: int, k_shots: int, output_size: int = 7, finest_scale: float = 56.0,
+                     conv_w: Optional[torch.Tensor] = None, conv_b: Optional[torch.Tensor] = None):
+    """count_spp in one launch (fgn_support_prologue_fwd; fgn_roi_head.py:419-449): mask pooling, support RoIAlign with
+    level assignment, class mean, masked GAP and -- when the relation conv's ``conv_w`` [C,2C] / ``conv_b`` are given -- the
+    class half of that convolution.  ``spp_feats``: levels [B*N*K,C,H_l,W_l] (repacked to channels_last if they are not),
+    ``spp_bboxes`` [B*N*K,4] XYXY px, ``spp_isegmaps`` [B*N*K,(1,)S,S] bool.
+    -> cat_mean [B,N,C,P,P] (channels_last storage), masked_gap [B,N,C,1,1], class_term [B*N*P*P, C] or None."""
+    _need_cuda(spp_bboxes, spp_isegmaps, conv_w, conv_b, *spp_feats)
+    feats = [to_nhwc(_f32(f, "spp_feats")) if storage_layout(f) != LAYOUT_NHWC else _f32(f, "spp_feats") for f in spp_feats]
+    pyr, keep, lay, m, c = _make_pyramid(feats, scales, torch.float32)
+    if m % (n_ways * k_shots):
+        raise FgnError(f"{m} support maps is not a multiple of N*K={n_ways * k_shots}")
+    bn, p = m // k_shots, int(output_size)
+    boxes = _f32(spp_bboxes, "spp_bboxes").reshape(m, 4).contiguous()
+    masks = spp_isegmaps.reshape(m, spp_isegmaps.shape[-2], spp_isegmaps.shape[-1])
+    if masks.dtype == torch.bool:
+        masks = masks.contiguous().view(torch.uint8)
+    elif masks.dtype != torch.uint8:
+        raise FgnError(f"spp_isegmaps: expected bool or uint8, got {masks.dtype}")
+    masks = masks.contiguous()
+    dev = boxes.device
+    cat = _empty_like_format((bn, c, p, p), dev, LAYOUT_NHWC)
+    gap = torch.empty((bn, c), device=dev, dtype=torch.float32)
+    term = None
+    if conv_w is not None:
+        cw = _f32(conv_w, "conv_w").reshape(conv_w.shape[0], -1).contiguous()
+        if tuple(cw.shape) != (c, 2 * c) or conv_b is None:
+            raise FgnError(f"support_prologue: conv_w must be [C,2C] = [{c},{2 * c}] with its bias")
+        term = torch.empty((bn * p * p, c), device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    wsb = int(lib.fgn_support_prologue_workspace_bytes(bn, c, p))
+    ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
+    _lib.check(lib.fgn_support_prologue_fwd(ctypes.byref(pyr), c, boxes.data_ptr(), masks.data_ptr(), masks.shape[1], masks.shape[2],
+                                            bn, int(k_shots), p, float(finest_scale), _ptr(cw if conv_w is not None else None),
+                                            _ptr(None if conv_b is None else _f32(conv_b, "conv_b").contiguous()),
+                                            cat.data_ptr(), gap.data_ptr(), _ptr(term), ws.data_ptr(), wsb, _stream()),
+               "fgn_support_prologue_fwd")
+    b = bn // n_ways
+    return cat.unflatten(0, (b, n_ways)), gap.view(b, n_ways, c, 1, 1), term
+
+
 def attention_vectors(spp_fmaps: torch.Tensor, n_ways: int, k_shots: int) -> torch.Tensor:
     """fgn_ag_rpn_head.py:37-41 -> [B,N,C,1,1]."""
     _need_cuda(spp_fmaps)
@@ -466,7 +508,8 @@ class RelationParams:
 
 
 def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mean: torch.Tensor, n_ways: int,
-                    params: RelationParams, precision: str = "fp32", return_raw: bool = False):
+                    params: RelationParams, precision: str = "fp32", return_raw: bool = False,
+                    class_term: Optional[torch.Tensor] = None):
     """count_one_roi_by_n_spp + bbox_head.forward + count_modified_cls_bbox (fgn_roi_head.py:336-339).
 
     roi_feat [R,C,P,P]; roi_batch [R] (rois[:,0]); spp_cat_mean [B,N,C,P,P] -> cls [R,N+1], reg [R,4N].
@@ -491,7 +534,7 @@ def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mea
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
     pr = params
     _lib.check(lib.fgn_relation_fusion_fwd(
-        x.data_ptr(), lay, rb.data_ptr(), s.data_ptr(), r, b, n_ways, c, p,
+        x.data_ptr(), lay, rb.data_ptr(), s.data_ptr(), _ptr(class_term), r, b, n_ways, c, p,
         pr.conv_w.data_ptr(), pr.conv_w_split.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
         pr.gn_groups, pr.gn_eps,
         pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(), pr.fc_reg_b.data_ptr(),
@@ -503,8 +546,9 @@ def relation_fusion(roi_feat: torch.Tensor, roi_batch: torch.Tensor, spp_cat_mea
 def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: Sequence[float],
                      spp_cat_mean: torch.Tensor, n_ways: int, params: RelationParams, output_size: int = 7,
                      sampling_ratio: int = 0, aligned: bool = True, finest_scale: float = 56.0,
-                     precision: str = "fp32", return_levels: bool = False):
-    """FPN-mode single call: level assignment + RoIAlign + relation fusion + heads."""
+                     precision: str = "fp32", return_levels: bool = False, class_term: Optional[torch.Tensor] = None):
+    """FPN-mode single call: level assignment + RoIAlign + relation fusion + heads.  ``class_term``: the class half of the
+    relation convolution as ``support_prologue`` leaves it ([B*N*P*P, C]); saves the class-term launch."""
     _need_cuda(rois, spp_cat_mean)
     rois = _f32(rois, "rois").contiguous()
     bf16 = _is_bf16(list(feats))
@@ -537,8 +581,8 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
     ws = torch.empty((max(wsb, 1),), device=dev, dtype=torch.uint8)
     _lib.check(lib.fgn_guided_roi_fused_fwd(
         ctypes.byref(pyr), b, c, rois.data_ptr(), r, p, int(sampling_ratio), int(bool(aligned)), float(finest_scale),
-        s.data_ptr(), n_ways, pr.conv_w.data_ptr(), pr.conv_w_split.data_ptr(), pr.conv_b.data_ptr(), pr.gn_w.data_ptr(),
-        pr.gn_b.data_ptr(),
+        s.data_ptr(), _ptr(class_term), n_ways, pr.conv_w.data_ptr(), pr.conv_w_split.data_ptr(), pr.conv_b.data_ptr(),
+        pr.gn_w.data_ptr(), pr.gn_b.data_ptr(),
         pr.gn_groups, pr.gn_eps, pr.fc_cls_w.data_ptr(), pr.fc_cls_b.data_ptr(), pr.fc_reg_w.data_ptr(),
         pr.fc_reg_b.data_ptr(), cls.data_ptr(), reg.data_ptr(), _ptr(lvl), {"fp32": 0, "tf32": 1}[precision],
         ws.data_ptr(), wsb, _stream()), "fgn_guided_roi_fused_fwd")

@@ -159,6 +159,8 @@ class FGNRoIHead(nn.Module):
             mh = {k: v for k, v in mask_head.items() if k not in ("type", "loss_mask", "init_cfg", "norm_cfg")}
             mask_head = FCNMaskHead(**mh)
         self.mask_head = mask_head
+        self.fused_prologue = True        # count_spp as one launch where no shared_head intervenes (False: the four separate ops)
+        self._class_term = None
         if shared_head == "c4":
             self.shared_head = make_c4_shared_head(channels, channels // 2, 3)
         else:
@@ -208,6 +210,14 @@ class FGNRoIHead(nn.Module):
                 self.bbox_head.fc_reg.weight, self.bbox_head.fc_reg.bias, n.num_groups, n.eps)
         return self._params_cache
 
+    def _valid_class_term(self, params) -> Optional[torch.Tensor]:
+        """count_spp's precomputed class half of the relation conv, if it still belongs to the class maps on ``self`` and to
+        the weights about to be used (someone may have assigned ``spp_fmaps_roi_aligned_cat_mean`` by hand since)."""
+        ct = self._class_term
+        if ct is None or ct[1] is not self.spp_fmaps_roi_aligned_cat_mean or ct[2] is not params:
+            return None
+        return ct[0]
+
     def _recording(self, *tensors) -> bool:
         """True when autograd is recording and any of `tensors` or of this head's parameters requires grad."""
         if not torch.is_grad_enabled():
@@ -235,6 +245,25 @@ class FGNRoIHead(nn.Module):
         # of fgn_b200.autograd take over wherever autograd is recording
         grad = A._needs_grad(*levels) or (self.with_shared_head and A._needs_grad(*self.shared_head.parameters()))
         roi_align = A.roi_align_multilevel if grad else ops.roi_align_multilevel
+        self._class_term = None
+        if (not grad and not self.with_shared_head and self.fused_prologue and spp_isegmaps.dtype in (torch.bool, torch.uint8)
+                and all(l.dtype == torch.float32 for l in levels)):               # (the bf16 variant keeps its own kernels)
+            # inference without a shared_head between RoIAlign and the class mean: all of count_spp -- and the class half
+            # of the relation convolution -- in ONE launch (fgn_support_prologue_fwd)
+            ext = self.bbox_roi_extractor
+            if len(levels) == 1:
+                scales = [1.0 / self.subsampling_ratio]       # = boxes / 16 with scale 1 (:430-432): a power of two, same cells
+            else:
+                scales = [1.0 / s for s in ext.featmap_strides[: len(levels)]]
+            pr = self.relation_params()
+            cat_mean, mp, term = ops.support_prologue(levels, scales, spp_bboxes.reshape(m, 4), spp_isegmaps, self.n_ways,
+                                                      self.k_shots, 7, float(ext.finest_scale), pr.conv_w, pr.conv_b)
+            if len(levels) == 1 and self.mutate_inputs:
+                spp_bboxes /= self.subsampling_ratio                                             # :430 (the reference's side effect)
+            self.spp_fmaps_roi_aligned_cat_mean = cat_mean
+            self.spp_fvecs_roi_aligned_cat_mean_mp = mp
+            self._class_term = (term, cat_mean, pr)           # valid for exactly these class maps and these weights
+            return
         mask_ra = ops.support_mask_pool(spp_isegmaps, spp_bboxes.reshape(m, 4), 7)          # :429 (masks carry no grad)
         idx = torch.arange(m, device=spp_bboxes.device, dtype=torch.float32).view(m, 1)
         # without a shared_head the class maps feed the relation GEMM directly: keep them channels_last
@@ -302,13 +331,14 @@ class FGNRoIHead(nn.Module):
         if not self.with_shared_head and not need_feats and layer.output_size[0] == 7:
             cls, reg = ops.guided_roi_fused(levels, rois, [l.spatial_scale for l in ext.roi_layers][: len(levels)],
                                             self.spp_fmaps_roi_aligned_cat_mean, self.n_ways, params, 7,
-                                            layer.sampling_ratio, layer.aligned, float(ext.finest_scale), self.precision)
+                                            layer.sampling_ratio, layer.aligned, float(ext.finest_scale), self.precision,
+                                            class_term=self._valid_class_term(params))
             return dict(cls_score=cls, bbox_pred=reg, bbox_feats=None)
         bbox_feats = ext(levels, rois, out_format="nhwc")
         if self.with_shared_head:
             bbox_feats = self.shared_head_layer(bbox_feats)
         cls, reg = ops.relation_fusion(bbox_feats, rois[:, 0], self.spp_fmaps_roi_aligned_cat_mean, self.n_ways,
-                                       params, self.precision)
+                                       params, self.precision, class_term=self._valid_class_term(params))
         return dict(cls_score=cls, bbox_pred=reg, bbox_feats=bbox_feats)
 
     # ---- attention-guided FCN (fgn_roi_head.py:360-382) -----------------------------------------

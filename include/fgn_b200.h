@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FGN_ABI_VERSION 2
+#define FGN_ABI_VERSION 3
 
 #define FGN_OK                 0
 #define FGN_ERR_INVALID_ARG   -1
@@ -109,6 +109,21 @@ int fgn_support_mask_pool(const uint8_t *mask, const float *boxes, int M, int S_
 int fgn_support_pool(const float *f, int f_layout, const float *m, int BN, int K, int C, int P,
                      float *cat_mean, int out_layout, float *masked_gap, void *stream);
 
+/* The whole of count_spp (fgn_roi_head.py:419-449) in ONE launch, for heads without a shared_head between RoIAlign and
+ * the class mean (FPN mode): mask pooling (:429), support RoIAlign with level assignment (:432; aligned=False,
+ * sampling_ratio=-1), class mean (:439-442), masked GAP (:444-447) -- and, when conv_w is given, the class half of the
+ * relation convolution (:272) Ys = cat_mean Ws^T + conv_b, which fgn_relation_fusion_fwd / fgn_guided_roi_fused_fwd accept
+ * as class_term.  One CTA per (class, bin); the masked GAP's cross-bin sum is finished by the last CTA of a class.
+ *   spp: NHWC support maps per level, [M = BN*K, H_l, W_l, C] with spatial_scale[l] (C4: one level, scale 1/16 -- the same
+ *        cells as the reference's boxes /= 16 with scale 1, a power of two); boxes [M,4] XYXY px; masks [M,S_h,S_w] uint8;
+ *   cat_mean [BN,P,P,C] (NHWC), masked_gap [BN,C], class_term [BN*P*P,C] (optional, needs conv_w [C,2C] and conv_b [C]).
+ * workspace: fgn_support_prologue_workspace_bytes(BN, C, P) bytes. */
+size_t fgn_support_prologue_workspace_bytes(int BN, int C, int P);
+int fgn_support_prologue_fwd(const fgn_pyramid_t *spp, int C, const float *boxes, const uint8_t *masks,
+                             int S_h, int S_w, int BN, int K, int P, float finest_scale,
+                             const float *conv_w, const float *conv_b, float *cat_mean, float *masked_gap,
+                             float *class_term, void *workspace, size_t workspace_bytes, void *stream);
+
 /* AGRPNHead class attention vector (fgn_ag_rpn_head.py:37-41):
  *   vec[b,n,c] = mean_{k,h,w} spp_fmaps[(b*N+n)*K+k, c, h, w]      -> vec [B*N,C]
  * workspace: fgn_attention_vectors_workspace_bytes(...) bytes (may be 0). */
@@ -156,6 +171,8 @@ int fgn_best_class_select(const float *cls, const float *reg, int B, int N, int 
  *   cls_out [R,N+1], reg_out [R,4N];  raw_cls_out/raw_reg_out optional ([R*N,2]/[R*N,4]).
  *   precision: 0 = fp32 parity (3xTF32 error-compensated tcgen05 contraction),
  *              1 = single-pass TF32 on tcgen05 (reduced precision, reported separately).
+ *   class_term (optional) [B*N*P*P, C]: the class half of the split convolution, Ys = spp_cat_mean Ws^T + conv_b, as
+ *              fgn_support_prologue_fwd leaves it; when given, spp_cat_mean may be NULL and one launch is saved.
  * workspace: fgn_relation_fusion_workspace_bytes(R, BN, C, P) bytes. */
 size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P);
 /* Load-time preparation of the relation conv's weights: the TF32 hi/lo split of Wq = conv_w[:, :C] and
@@ -164,7 +181,7 @@ size_t fgn_relation_fusion_workspace_bytes(int R, int BN, int C, int P);
 size_t fgn_relation_split_weights_bytes(int C);
 int fgn_relation_split_weights(const float *conv_w, int C, float *out, void *stream);
 int fgn_relation_fusion_fwd(const float *roi_feat, int feat_layout, const int32_t *roi_batch,
-                            const float *spp_cat_mean, int R, int B, int N, int C, int P,
+                            const float *spp_cat_mean, const float *class_term /* optional */, int R, int B, int N, int C, int P,
                             const float *conv_w, const float *conv_w_split /* optional */, const float *conv_b,
                             const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
                             const float *fc_cls_w, const float *fc_cls_b,
@@ -238,7 +255,7 @@ int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, i
 size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P);
 int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
                              int P, int sampling_ratio, int aligned, float finest_scale,
-                             const float *spp_cat_mean /* [B*N,P,P,C] NHWC */, int N,
+                             const float *spp_cat_mean /* [B*N,P,P,C] NHWC */, const float *class_term /* optional */, int N,
                              const float *conv_w, const float *conv_w_split /* optional */, const float *conv_b,
                              const float *gn_w, const float *gn_b, int gn_groups, float gn_eps,
                              const float *fc_cls_w, const float *fc_cls_b,

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/fgn_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in fgn_b200/_lib.py"
-    assert lib.fgn_abi_version() == 2
+    assert lib.fgn_abi_version() == 3
 
 
 def test_zero_size_calls_do_not_touch_the_device():
@@ -50,7 +50,7 @@ def test_bad_arguments_set_the_error_string():
     lib = _lib.load()
     assert lib.fgn_map_roi_levels(None, 5, 99, 56.0, None, None) == -1
     assert b"num_levels" in lib.fgn_last_error_string()
-    assert lib.fgn_relation_fusion_fwd(None, 0, None, None, 4, 1, 1, 30, 7, None, None, None, None, None, 32, 1e-5,
+    assert lib.fgn_relation_fusion_fwd(None, 0, None, None, None, 4, 1, 1, 30, 7, None, None, None, None, None, 32, 1e-5,
                                        None, None, None, None, None, None, None, None, 0, None, 0, None) == -1
     assert b"GroupNorm" in lib.fgn_last_error_string()
     with pytest.raises(_lib.FgnError):

@@ -141,3 +141,53 @@ def test_bottleneck_three_convs_on_tcgen05(prec_tf32):
     atol = 5e-2 if prec_tf32 else 5e-4                                   # three chained convolutions of O(1..10) activations
     err = (got.cpu() - want).abs()
     assert bool((err <= atol + (1e-2 if prec_tf32 else 1e-4) * want.abs()).all()), f"bottleneck [{prec}] max abs err {float(err.max()):.3e}"
+
+
+@pytest.mark.parametrize("name", ["tiny_fpn", "tiny_c4", "cfg3_coco2voc_n1k1_fpn", "cfg4_coco2voc_n20k5_fpn"])
+def test_support_prologue_one_launch_against_the_separate_ops_and_the_oracle(name):
+    """count_spp as ONE launch (fgn_support_prologue_fwd) against the four separate library ops it replaces and, for the
+    class maps / vectors, against the oracle's count_spp (fgn_roi_head.py:419-449); its class term against the exact
+    fp32 expression cat_mean Ws^T + b."""
+    from fgn_b200 import _lib
+    from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
+    from oracle import fgn_oracle as O
+    dev = torch.device(DEV)
+    cfg = CONFIGS[name]
+    ep = make_episode(cfg, seed=3)
+    _, head = build_heads(cfg, dev, seed=0, shared_head=None)
+    epd = episode_to_device(ep, dev)
+    n_ext = len(cfg.strides)
+    spp = epd["spp"][:n_ext] if cfg.mode == "fpn" else epd["spp"][0]
+    with torch.no_grad():
+        head.fused_prologue = False
+        head.count_spp(spp, epd["spp_bboxes"].clone(), epd["spp_masks"])
+        cat0, mp0 = head.spp_fmaps_roi_aligned_cat_mean, head.spp_fvecs_roi_aligned_cat_mean_mp
+        assert head._class_term is None
+        head.fused_prologue = True
+        head.relation_params()                                           # (packs / splits the weights once: not part of count_spp)
+        before = _lib.load().fgn_launch_count()
+        head.count_spp(spp, epd["spp_bboxes"].clone(), epd["spp_masks"])
+        assert _lib.load().fgn_launch_count() - before == 1
+        cat1, mp1 = head.spp_fmaps_roi_aligned_cat_mean, head.spp_fvecs_roi_aligned_cat_mean_mp
+        term = head._valid_class_term(head.relation_params())
+    assert term is not None and cat1.shape == cat0.shape and mp1.shape == mp0.shape
+    close(cat1, cat0, "fp32", "cat_mean fused vs separate")              # (same sampling order: differences are the mean's only)
+    close(mp1, mp0, "fp32", "masked_gap fused vs separate")
+    if cfg.mode == "fpn":
+        want_cat, want_mp, _, _ = O.count_spp_fpn(ep["spp"][:n_ext], cfg.strides, ep["spp_bboxes"].clone(), ep["spp_masks"],
+                                                  cfg.n_ways, cfg.k_shots)
+        close(cat1, want_cat.view(cat1.shape), "fp32", "cat_mean vs oracle")
+        close(mp1, want_mp.view(mp1.shape), "fp32", "masked_gap vs oracle")
+    c = cfg.channels
+    w = head.cls_reg_shared_conv.weight.detach().reshape(c, 2 * c).double().cpu()
+    rows = cat1.permute(0, 1, 3, 4, 2).reshape(-1, c).double().cpu()     # [B*N*49, C] in bin order
+    want_term = rows @ w[:, c:].t() + head.cls_reg_shared_conv.bias.detach().double().cpu()
+    close(term, want_term.float(), "fp32", "class term")
+    # the box head gives the same logits with and without the precomputed class term
+    with torch.no_grad():
+        qry = epd["qry"][:n_ext] if cfg.mode == "fpn" else epd["qry"][0]
+        a = head._bbox_forward(qry, epd["rois"])
+        head._class_term = None
+        b = head._bbox_forward(qry, epd["rois"])
+    close(a["cls_score"], b["cls_score"], "fp32", "cls_score with / without precomputed class term")
+    close(a["bbox_pred"], b["bbox_pred"], "fp32", "bbox_pred with / without precomputed class term")
