@@ -519,9 +519,12 @@ def main():
     a_q = [torch.randn(M_q, cfg.channels, device=device) for _ in range(4)]
     w_q = head.cls_reg_shared_conv.weight.detach().reshape(cfg.channels, 2 * cfg.channels)[:, : cfg.channels]
 
+    w_q = w_q.contiguous()
+    w_q_split = ops.conv_split_weights(w_q[None])                 # as the head holds it after loading its weights
+
     def gemm_only():
         for a in a_q:
-            ops.gemm_nt(a, w_q, None, "fp32")
+            ops.gemm_nt(a, w_q, None, "fp32", b_split=w_q_split)
 
     with torch.no_grad():
         gemm_only()
@@ -532,9 +535,9 @@ def main():
     ms_g, _, _ = timed(gemm_graph.replay, max(args.steps, 10), args.warmup)
     g_s = ms_g * 1e-3 / (max(args.steps, 10) * len(a_q))
     flops_split = 2.0 * M_q * cfg.channels * cfg.channels
-    ncu_gemm = committed("r02_ncu_gemm_tcgen05.json")
+    ncu_gemm = committed("r02_ncu_gemm_tcgen05_pair.json")
     tf32_nominal = 1100.0
-    roofline_tensor = {"kernel": "gemm_tf32_tc_kernel<3,16> (relation conv as split-weight GEMM, tcgen05 kind::tf32, 3xTF32)",
+    roofline_tensor = {"kernel": "conv_tc2_kernel<3,0> (relation conv as split-weight GEMM on CTA pairs: tcgen05 cta_group::2 kind::tf32, 256-row MMAs, 3xTF32)",
                        "bound": "tensor", "achieved": flops_split / g_s / 1e12, "unit": "TFLOP/s",
                        "achieved_tensor_work": 3 * flops_split / g_s / 1e12, "peak": tf32_nominal,
                        "frac": 3 * flops_split / g_s / 1e12 / tf32_nominal,
@@ -542,7 +545,7 @@ def main():
                        "what": "achieved = split-weight FLOP count / time (SURVEY 8d); achieved_tensor_work counts the three TF32 passes of the fp32-parity scheme, frac = that / nominal TF32",
                        "us_per_launch": g_s * 1e6, "M": M_q, "N": cfg.channels, "K": cfg.channels,
                        "tensor_pipe_pct_of_active": (ncu_gemm or {}).get("tensor_pipe_pct_of_active"),
-                       "tensor_pipe_source": "profiles/r02_ncu_gemm_tcgen05.json" if ncu_gemm else None}
+                       "tensor_pipe_source": "profiles/r02_ncu_gemm_tcgen05_pair.json" if ncu_gemm else None}
     del a_q
 
     # (3) the whole step against HBM: fused accounting -- every input map read once, every output written

@@ -89,6 +89,7 @@ SIGNATURES = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "fgn_gemm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fgn_gemm_nt": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "fgn_gemm_nt_presplit": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fgn_conv1x1_nhwc": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fgn_conv_split_weights_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fgn_conv_split_weights": (c_int, [_P, c_int, c_int, c_int, _P, _P]),

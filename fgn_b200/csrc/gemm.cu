@@ -60,6 +60,17 @@ extern "C" int fgn_gemm_nt(const float *A, int lda, const float *B, int ldb, con
     return gemm_nt(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, ws, (cudaStream_t)stream);
 }
 
+// The fp32-parity contraction with the weights' TF32 split made beforehand (fgn_conv_split_weights(B, 1, N, K, ...) or a
+// quarter of fgn_relation_split_weights' output): what the relation head runs per call once its weights are loaded.
+extern "C" int fgn_gemm_nt_presplit(const float *A, int lda, const float *b_split, const float *bias, float *C, int ldc,
+                                    int M, int N, int K, void *stream)
+{
+    FGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm dims M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return FGN_OK;
+    FGN_CHECK_ARG(A && b_split && C, "NULL pointer");
+    return gemm_nt(A, lda, b_split, K, bias, C, ldc, M, N, K, 0, const_cast<float *>(b_split), (cudaStream_t)stream, true);
+}
+
 extern "C" int fgn_gemm_nt_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C,
                                 int ldc, int M, int N, int K, void *stream)
 {

@@ -590,15 +590,22 @@ def guided_roi_fused(feats: Sequence[torch.Tensor], rois: torch.Tensor, scales: 
 
 
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, precision: str = "fp32",
-            use_workspace: bool = True) -> torch.Tensor:
-    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias): the relation head's contraction alone (rows may be strided)."""
-    _need_cuda(a, b, bias)
+            use_workspace: bool = True, b_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias): the relation head's contraction alone (rows may be strided).
+    ``b_split`` = ``conv_split_weights(b.contiguous()[None])`` (fp32 precision only): the weights' TF32 split made once."""
+    _need_cuda(a, b, bias, b_split)
     if a.stride(1) != 1 or b.stride(1) != 1:
         raise FgnError("gemm_nt operands must be K-major (unit stride along K)")
     m, k = a.shape
     n = b.shape[0]
     c = torch.empty((m, n), device=a.device, dtype=torch.float32)
     lib = _lib.load()
+    if b_split is not None:
+        if precision != "fp32" or b_split.numel() != 2 * n * k or b_split.dtype != torch.float32:
+            raise FgnError("gemm_nt: b_split is the fp32 route's [2,N,K] split of b")
+        _lib.check(lib.fgn_gemm_nt_presplit(_f32(a, "a").data_ptr(), a.stride(0), b_split.contiguous().data_ptr(), _ptr(bias),
+                                            c.data_ptr(), n, m, n, k, _stream()), "fgn_gemm_nt_presplit")
+        return c
     if a.dtype == torch.bfloat16 or b.dtype == torch.bfloat16:
         if not (a.dtype == b.dtype == torch.bfloat16):
             raise FgnError("bf16 contraction needs both operands in bfloat16")

@@ -160,6 +160,7 @@ class FGNRoIHead(nn.Module):
             mask_head = FCNMaskHead(**mh)
         self.mask_head = mask_head
         self.fused_prologue = True        # count_spp as one launch where no shared_head intervenes (False: the four separate ops)
+        self.fused_prologue_max_supports = 32
         self._class_term = None
         if shared_head == "c4":
             self.shared_head = make_c4_shared_head(channels, channels // 2, 3)
@@ -246,7 +247,11 @@ class FGNRoIHead(nn.Module):
         grad = A._needs_grad(*levels) or (self.with_shared_head and A._needs_grad(*self.shared_head.parameters()))
         roi_align = A.roi_align_multilevel if grad else ops.roi_align_multilevel
         self._class_term = None
+        # (the one-launch form is latency-optimal for a handful of supports -- 1-way 1-shot: 50 -> 25 us, 4 launches -> 1;
+        #  with a hundred of them (cfg4: N=20, K=5) its (class, bin) CTAs loop over the shots at two CTAs per SM and the four
+        #  wide kernels win: 792 against 711 us per episode, profiles/r02_configs.jsonl -- hence the size rule)
         if (not grad and not self.with_shared_head and self.fused_prologue and spp_isegmaps.dtype in (torch.bool, torch.uint8)
+                and (m <= self.fused_prologue_max_supports or self.fused_prologue == "always")
                 and all(l.dtype == torch.float32 for l in levels)):               # (the bf16 variant keeps its own kernels)
             # inference without a shared_head between RoIAlign and the class mean: all of count_spp -- and the class half
             # of the relation convolution -- in ONE launch (fgn_support_prologue_fwd)

@@ -207,6 +207,11 @@ int fgn_conv1x1_nhwc(const float *x, const float *weight, const float *bias, con
                      float *out, int M, int Cin, int Cout, int precision, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* fgn_gemm_nt at precision 0 with the TF32 hi/lo split of B made beforehand: b_split = { B_hi [N,K], B_lo [N,K] } as
+ * fgn_conv_split_weights(B, 1, N, K, b_split) writes it (B dense).  No per-call split launch, no workspace. */
+int fgn_gemm_nt_presplit(const float *A, int lda, const float *b_split, const float *bias, float *C, int ldc,
+                         int M, int N, int K, void *stream);
+
 /* Post-RoI head 3x3 / pad 1 convolution over NHWC RoI tiles as an implicit GEMM on tcgen05 (no im2col buffer: tap
  * (dy,dx) reads the activation tensor through a 4D TMA descriptor shifted by (dx-1, dy-1), out-of-tile cells are
  * zero-filled by the TMA unit).  Replaces mmdet Bottleneck.conv2 of the C4 shared_head (fgn_roi_head.py:202-233) and

@@ -163,7 +163,7 @@ def test_support_prologue_one_launch_against_the_separate_ops_and_the_oracle(nam
         head.count_spp(spp, epd["spp_bboxes"].clone(), epd["spp_masks"])
         cat0, mp0 = head.spp_fmaps_roi_aligned_cat_mean, head.spp_fvecs_roi_aligned_cat_mean_mp
         assert head._class_term is None
-        head.fused_prologue = True
+        head.fused_prologue = "always"                                   # (cfg4's hundred supports are past the size rule)
         head.relation_params()                                           # (packs / splits the weights once: not part of count_spp)
         before = _lib.load().fgn_launch_count()
         head.count_spp(spp, epd["spp_bboxes"].clone(), epd["spp_masks"])
