@@ -252,7 +252,8 @@ int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, i
                             float *cls_out, float *reg_out, void *stream);
 
 /* FPN-mode single call (no shared_head between RoIAlign and the relation conv): level assignment + RoIAlign +
- * relation fusion + heads, four kernels (RoIAlign, class-term contraction, RoI contraction, epilogue).  The RoI features
+ * relation fusion + heads, three kernels (RoIAlign, RoI contraction, epilogue; a fourth, the class-term contraction, when
+ * class_term is not handed over).  The RoI features
  * (NHWC, R*49*C*4 bytes) and the conv output travel through the caller's workspace between them: at the benchmark size
  * that is L2-resident traffic for the most part, but it is NOT zero -- the committed captures show 26 MB of DRAM writes by
  * the RoIAlign kernel and 51 MB of DRAM reads by the contraction per 1000 RoIs (profiles/r02_ncu_*.json).  A single kernel

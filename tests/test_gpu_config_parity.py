@@ -4,8 +4,9 @@ Each test runs the CUDA path on one whole episode at the BASELINE size (SURVEY 8
 compares with the CPU oracle through oracle/parity.py: AG-RPN attention on every level and the
 support vectors in full; logits, box deltas, RoI features and attended mask features on a strided
 RoI subset (rows are per-RoI independent).  Bar: |a-b| <= 1e-4 + 1e-5*|b| (BASELINE.json north_star).
-Quantities downstream of the C4 res5 `shared_head` (an adjacent cuDNN module, not a kernel of this
-library) are compared with 1e-3 absolute: cuDNN and MKL convolutions do not share a summation order.
+Quantities downstream of the C4 res5 `shared_head` are compared with 1e-3 absolute: its 1x1 convolutions run on the
+3xTF32 contraction, whose truncating tensor-core accumulator leaves ~3e-4 on activations of magnitude ~17 after three
+bottlenecks (tools/diag_c4_head.py, against fp64; under strict fp32 the 3x3 stays on cuDNN).
 """
 import copy
 
