@@ -37,6 +37,8 @@ struct ConvArgs {
     int relu;
     const float *w_l, *b_l;        // MODE 1: conv_logits [ncls, Cout], [ncls]
     int ncls;
+    int lda, ldc;                  // flat mode: row pitch (floats) of A and of out / residual (conv modes: Cin, Cout)
+    int ldb;                       // host side: row pitch of w_taps when it is read in place (one TF32 pass); 0 = Cin
     int debug;                     // FGN_TC_DEBUG (development): bit 0 = epilogue does not read / store, bit 1 = splitters do not split
 };
 
@@ -78,7 +80,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs &args, const C
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)c0, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            store_chunk(r, epi_tile, lane, t.m0 + ew * 32, t.m0 + t.nv, t.n0 + c0, args.N, args.bias, args.out, args.Cout,
+            store_chunk(r, epi_tile, lane, t.m0 + ew * 32, t.m0 + t.nv, t.n0 + c0, args.N, args.bias, args.out, args.ldc,
                         args.residual, args.relu != 0);
         }
     } else {
@@ -495,6 +497,8 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
                           float *ws, size_t ws_bytes, cudaStream_t st)
 {
     const int rows = a.taps * a.N;
+    if (a.lda == 0) a.lda = a.Cin;
+    if (a.ldc == 0) a.ldc = a.Cout;
     const float *bhi = w_taps, *blo = w_taps;
     if (precision == 0) {
         if (w_split != nullptr) { bhi = w_split; blo = w_split + (size_t)rows * a.Cin; }
@@ -517,7 +521,7 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
         cuuint32_t box[4];
         if (a.flat) {
             dims[0] = a.Cin; dims[1] = M; dims[2] = 1; dims[3] = 1;
-            strides[0] = (cuuint64_t)a.Cin * 4; strides[1] = strides[2] = M * a.Cin * 4;
+            strides[0] = (cuuint64_t)a.lda * 4; strides[1] = strides[2] = M * a.lda * 4;
             box[0] = CV_BK; box[1] = CV_BM; box[2] = 1; box[3] = 1;
         } else {
             dims[0] = a.Cin; dims[1] = a.W; dims[2] = a.H; dims[3] = a.R;
@@ -525,7 +529,8 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
             box[0] = CV_BK; box[1] = a.W; box[2] = a.HB; box[3] = a.RB;
         }
         ok = make_map_nd(&ma, x, 4, dims, strides, box);
-        cuuint64_t bd[2] = {(cuuint64_t)a.Cin, (cuuint64_t)rows}, bs[1] = {(cuuint64_t)a.Cin * 4};
+        const cuuint64_t b_pitch = (precision != 0 && a.ldb != 0) ? (cuuint64_t)a.ldb : (cuuint64_t)a.Cin;   // the split is dense
+        cuuint64_t bd[2] = {(cuuint64_t)a.Cin, (cuuint64_t)rows}, bs[1] = {b_pitch * 4};
         cuuint32_t bb[2] = {CV_BK, (cuuint32_t)(two_sm ? a.BN / 2 : a.BN)};   // the pair kernel: half a B tile per CTA
         ok = ok && make_map_nd(&mbh, bhi, 2, bd, bs, bb) && make_map_nd(&mbl, blo, 2, bd, bs, bb);
     }
@@ -564,21 +569,23 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
     return FGN_OK;
 }
 
-// The plain contraction C[M,N] = A[M,K] B[N,K]^T (+ bias [+ residual], ReLU) on the CTA-pair kernel: the relation conv and the
-// heads' 1x1 convolutions (dense operands: lda == ldb == K, ldc == N).  *taken = false when the shape does not qualify.
-int gemm_nt_tc2(const float *A, const float *B, int ldb, const float *bias, float *C, int M, int N, int K, int precision,
-                float *split_ws, cudaStream_t st, bool presplit, const float *residual, bool relu, bool *taken)
+// The plain contraction C[M,N] = A[M,K] B[N,K]^T (+ bias [+ residual], ReLU): the relation conv, its adjoint's contractions
+// and the heads' 1x1 convolutions.  CTA-pair kernel when the column tile splits in two legal halves and there are at least
+// two row tiles, else the single-CTA kernel.  *taken = false when the shape does not qualify for either.
+int gemm_nt_tc2(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc, int M, int N, int K,
+                int precision, float *split_ws, cudaStream_t st, bool presplit, const float *residual, bool relu, bool *taken)
 {
     *taken = false;
-    if (precision != 0 && ldb != K) return FGN_OK;                 // one TF32 pass reads B in place: dense rows only
-    if (M < 2 * CV_BM || (K % CV_BK) != 0 || (N % 32) != 0 || (N > CV_BN_MAX && (N % CV_BN_MAX) != 0)) return FGN_OK;
-    if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return FGN_OK;
+    if ((K % CV_BK) != 0 || (N % 16) != 0 || (N > CV_BN_MAX && (N % CV_BN_MAX) != 0)) return FGN_OK;
+    if ((lda & 3) || (ldb & 3) || (ldc & 3) || (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)) return FGN_OK;
     if (precision == 0 && split_ws == nullptr) return FGN_OK;
     ConvArgs a = {};
+    a.ldb = ldb;
     a.bias = bias; a.residual = residual; a.out = C;
     a.R = M; a.H = 1; a.W = 1; a.Cin = K; a.Cout = N;
     a.N = N; a.BN = N > CV_BN_MAX ? CV_BN_MAX : N;
     a.flat = 1; a.taps = 1; a.HB = 1; a.RB = 1; a.h_blocks = 1; a.relu = relu ? 1 : 0;
+    a.lda = lda; a.ldc = ldc;
     if (precision == 0 && !presplit)
         if (int rcs = gemm_split_weights(B, ldb, N, K, split_ws, st)) return rcs;
     const int rc = conv_tc_launch(0, A, B, split_ws, a, precision, nullptr, 0, st);

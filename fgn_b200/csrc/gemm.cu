@@ -4,12 +4,8 @@
 
 namespace fgn {
 
-int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken, bool presplit,
-               const float *residual, bool relu);
-
-int gemm_nt_tc2(const float *A, const float *B, int ldb, const float *bias, float *C, int M, int N, int K, int precision,
-                float *split_ws, cudaStream_t st, bool presplit, const float *residual, bool relu, bool *taken);
+int gemm_nt_tc2(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc, int M, int N, int K,
+                int precision, float *split_ws, cudaStream_t st, bool presplit, const float *residual, bool relu, bool *taken);
 
 int gemm_nt_tc_bf16(const uint16_t *A, int lda, const uint16_t *B, int ldb, const float *bias, float *C, int ldc,
                     int M, int N, int K, cudaStream_t st);
@@ -23,14 +19,10 @@ int gemm_nt(const float *A, int lda, const float *B, int ldb, const float *bias,
     // A class-term contraction (M = B*N*49 rows: 49 at cfg3) on the tcgen05 kernel is ONE tile paying the whole
     // pipeline latency (TMEM allocation, 16 dependent k-blocks: ~15 us); the fp32 SIMT kernel does it in a few us, exactly.
     const bool simt_only = (force != nullptr && force[0] == 's') || (precision == 0 && M <= 512 && K <= 4096 && (force == nullptr || force[0] != 't'));
-    // CTA-pair kernel (conv_tc.cu, cta_group::2): half the B bytes per SM and k-block.  FGN_GEMM_2SM=0 keeps the single-CTA kernel.
-    const char *e2 = getenv("FGN_GEMM_2SM");
-    if (!simt_only && lda == K && ldc == N && !(e2 != nullptr && e2[0] == '0')) {
-        if (int rc2 = gemm_nt_tc2(A, B, ldb, bias, C, M, N, K, precision, split_ws, st, presplit, residual, relu, &taken)) return rc2;
-        if (taken) return FGN_OK;
-    }
-    const int rc = simt_only ? FGN_OK : gemm_nt_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, &taken, presplit, residual, relu);
-    if (rc) return rc;
+    // tcgen05 kernels of conv_tc.cu: CTA pairs (cta_group::2: half the B bytes per SM and k-block) where the shape allows,
+    // else one CTA per tile
+    if (!simt_only)
+        if (int rc2 = gemm_nt_tc2(A, lda, B, ldb, bias, C, ldc, M, N, K, precision, split_ws, st, presplit, residual, relu, &taken)) return rc2;
     if (taken) return FGN_OK;
     if (precision != 0) {
         set_error("gemm: tf32 precision needs the tcgen05 path (M=%d N=%d K=%d not supported by it)", M, N, K);

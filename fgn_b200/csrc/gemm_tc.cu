@@ -1,4 +1,7 @@
-// gemm_tc.cu -- tcgen05 (5th-gen tensor core) contraction for the relation head's 1x1 conv
+// gemm_tc.cu -- the single-CTA tcgen05 contraction kernel of round 1.  Since round 2 the fp32 contractions (relation conv, its
+// adjoint, the heads' convolutions) run on conv_tc.cu's kernels (CTA pairs where the shape allows); what is launched from
+// this file is the bf16 variant (kind::f16) and the weights' TF32 split.  Original header:
+// tcgen05 (5th-gen tensor core) contraction for the relation head's 1x1 conv
 // (fgn_roi_head.py:272): C[M,N] = A[M,K] * B[N,K]^T (+ bias), fp32 in / fp32 out.
 //
 // fp32 parity on tensor cores: 3xTF32 error compensation.  Every operand is split as
@@ -237,52 +240,6 @@ int gemm_split_weights(const float *B, int ldb, int N, int K, float *split_ws, c
 {
     split_tf32_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(B, N, K, ldb, split_ws, split_ws + (size_t)N * K);
     FGN_LAUNCH_OK();
-    return FGN_OK;
-}
-
-// presplit: split_ws already holds the TF32 split of B (gemm_split_weights, done once when the weights were loaded)
-int gemm_nt_tc(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-               int M, int N, int K, int precision, float *split_ws, cudaStream_t st, bool *taken, bool presplit,
-               const float *residual, bool relu)
-{
-    *taken = false;
-    if (M <= 0) return FGN_OK;
-    // shapes the kernel takes: K in whole 128-byte k-blocks, N tiles of <=256 that are UMMA_N-legal
-    if ((K % 32) != 0 || (N % 16) != 0 || (N > TC_BN_MAX && (N % TC_BN_MAX) != 0)) return FGN_OK;
-    if ((lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15)) return FGN_OK;
-    if (split_ws == nullptr) return FGN_OK;
-    const int BN = N > TC_BN_MAX ? TC_BN_MAX : N;
-    const int passes = precision == 0 ? 3 : 1;
-    const char *e = getenv("FGN_GEMM_BK");
-    const int bk = (e != nullptr && atoi(e) == 32) ? 32 : 16;
-
-    float *bhi = split_ws, *blo = split_ws + (size_t)N * K;
-    if (!presplit) {
-        split_tf32_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(B, N, K, ldb, bhi, blo);
-        FGN_LAUNCH_OK();
-    }
-
-    CUtensorMap ma, mbh, mbl;
-    if (!make_map(&ma, A, M, K, lda, TC_BM, bk) || !make_map(&mbh, bhi, N, K, K, BN, bk) || !make_map(&mbl, blo, N, K, K, BN, bk)) {
-        set_error("cuTensorMapEncodeTiled unavailable or failed");
-        return FGN_ERR_CUDA;
-    }
-    int sm_count = 0;
-    if (int rc_sm = current_sm_count(&sm_count)) return rc_sm;
-    const int m_tiles = ceil_div(M, TC_BM), n_tiles = ceil_div(N, BN);
-    const int grid = min(sm_count, m_tiles * n_tiles);
-#define FGN_TC_LAUNCH(PS, BKV, IDX)                                                                                  \
-    do {                                                                                                           \
-        FGN_SMEM_OPTIN((gemm_tf32_tc_kernel<PS, BKV>), TcSmem<BKV>::kTotal);                                        \
-        gemm_tf32_tc_kernel<PS, BKV><<<grid, TC_THREADS, TcSmem<BKV>::kTotal, st>>>(ma, mbh, mbl, bias, C, ldc, M, N, K, BN, residual, relu ? 1 : 0); \
-    } while (0)
-    if (passes == 3 && bk == 32) FGN_TC_LAUNCH(3, 32, 0);
-    else if (passes == 3)        FGN_TC_LAUNCH(3, 16, 1);
-    else if (bk == 32)           FGN_TC_LAUNCH(1, 32, 2);
-    else                         FGN_TC_LAUNCH(1, 16, 3);
-#undef FGN_TC_LAUNCH
-    FGN_LAUNCH_OK();
-    *taken = true;
     return FGN_OK;
 }
 

@@ -1,4 +1,4 @@
-"""Times the relation contraction (ops.gemm_nt) for the FGN_GEMM_BK knob; development tool."""
+"""Times the relation contraction (ops.gemm_nt) on the CTA-pair and the single-CTA kernel (FGN_TC_2SM); development tool."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,8 +13,7 @@ for M, N, K in shapes:
     wq = w[:, :K].contiguous()
     for bk, pair in ((16, 0), (16, 2)):
         for prec in ("fp32", "tf32"):
-            os.environ["FGN_GEMM_BK"] = str(bk)
-            os.environ["FGN_GEMM_2SM"] = "1" if pair else "0"
+            os.environ["FGN_TC_2SM"] = "1" if pair else "0"       # 0 = the single-CTA kernel of conv_tc.cu
             got = ops.gemm_nt(a[0], wq, None, prec)
             err = float((got - want).abs().max())
             for _ in range(3):
