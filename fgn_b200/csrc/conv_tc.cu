@@ -63,7 +63,7 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvArgs &a, int tile, int n
     } else {
         const int r0 = (mt / a.h_blocks) * a.RB, h0 = (mt % a.h_blocks) * a.HB;
         t.m0 = (r0 * a.H + h0) * a.W;
-        t.nv = a.HB == a.H ? min(a.RB, a.R - r0) * a.H * a.W : min(a.HB, a.H - h0) * a.W;
+        t.nv = r0 >= a.R ? 0 : (a.HB == a.H ? min(a.RB, a.R - r0) * a.H * a.W : min(a.HB, a.H - h0) * a.W);   // (padding tiles of a pair / quad: nothing to store)
         t.c1 = 0; t.c2 = h0; t.c3 = r0;
     }
     return t;
@@ -480,6 +480,138 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+// ---- CTA-pair kernel with TWO row tiles per CTA sharing one B tile (3x3 convolutions, one TF32 pass) --------------------
+// One TF32 pass is bound by what the L2 delivers per MMA (pair kernel: 6.3-8 KB of A + 8 KB of B per SM and k-block).  A 3x3
+// convolution's k loop is long (9 x Cin / 16 k-blocks), so the epilogue need not hide behind the next tile: both 256-column
+// accumulators serve ONE step -- two 128-row tiles per CTA against the same half B tile -- and a k-block costs each SM
+// 2 x A + B for twice the tensor work: 10.3 instead of 14.3 KB per MMA at 7x7 tiles.  Eight 24 KB stages; no splitters.
+constexpr int C2D_STAGES = 8;
+constexpr int C2D_STAGE = 2 * CV_A + C2_BH;                  // A (tile 0) | A (tile 1) | B half
+
+__global__ void __launch_bounds__(C2_THREADS, 1)
+conv_tc2d_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C2_RING);
+    uint64_t *full_bar = bars;                          // rank 0's: both CTAs' two A boxes and B halves
+    uint64_t *empty_bar = bars + C2D_STAGES;            // local (multicast commit)
+    uint64_t *tmem_full = bars + 2 * C2D_STAGES;        // local (multicast commit)
+    uint64_t *tmem_empty = tmem_full + 1;               // rank 0's: the sixteen epilogue warps of the pair
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    float *epi_smem = reinterpret_cast<float *>(smem + C2_RING + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int BN = args.BN, BH = BN >> 1;
+    const int m_tiles = args.flat ? (args.R * args.H * args.W + CV_BM - 1) / CV_BM
+                                  : ((args.R + args.RB - 1) / args.RB) * args.h_blocks;
+    const int qm_tiles = (m_tiles + 3) >> 2;
+    const int n_tiles = args.N / BN;
+    const int num_qtiles = qm_tiles * n_tiles;
+    const int kb_per_tap = args.Cin / CV_BK, num_kb = args.taps * kb_per_tap;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    // this CTA's row tile j of step qt: m-tile 4*qm + 2*j + rank (accumulator j = the pair's 256 rows {4qm+2j, 4qm+2j+1})
+#define C2D_TILE(qt, j) conv_tile(args, (((qt) / n_tiles) * 4 + 2 * (j) + rank) * n_tiles + (qt) % n_tiles, n_tiles)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C2D_STAGES; ++s) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], 1); }
+        tc_mbar_init(tmem_full, 1);
+        tc_mbar_init(tmem_empty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t a_bytes = (args.flat ? CV_BM : args.W * args.HB * args.RB) * CV_BK * 4;
+            const uint32_t b_bytes = BH * CV_BK * 4;
+            int it = 0;
+            for (int qt = pair; qt < num_qtiles; qt += num_pairs) {
+                const ConvTile t0 = C2D_TILE(qt, 0), t1 = C2D_TILE(qt, 1);
+                for (int tap = 0; tap < args.taps; ++tap) {
+                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0, dx = args.taps == 9 ? tap % 3 - 1 : 0;
+                    const int brow = tap * args.N + t0.n0 + rank * BH;
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+                        const int s = it % C2D_STAGES;
+                        tc_mbar_wait(&empty_bar[s], ((it / C2D_STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * C2D_STAGE;
+                        if (rank == 0) tc_mbar_expect_tx(&full_bar[s], 2 * (2 * a_bytes + b_bytes));
+                        tma_load_4d_2sm(st, &map_a, kb * CV_BK, t0.c1 + dx, t0.c2 + dy, t0.c3, &full_bar[s]);
+                        tma_load_4d_2sm(st + CV_A, &map_a, kb * CV_BK, t1.c1 + dx, t1.c2 + dy, t1.c3, &full_bar[s]);
+                        tma_load_2d_2sm(st + 2 * CV_A, &map_b, kb * CV_BK, brow, &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * CV_BM) >> 4) << 24);
+            int it = 0, local_tile = 0;
+            for (int qt = pair; qt < num_qtiles; qt += num_pairs, ++local_tile) {
+                tc_mbar_wait(tmem_empty, (local_tile & 1) ^ 1);           // both accumulators drained by every epilogue warp
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % C2D_STAGES;
+                    tc_mbar_wait(&full_bar[s], (it / C2D_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t st = s_u32(smem + (size_t)s * C2D_STAGE);
+                        const uint64_t a0 = umma_desc_kmajor<CV_BK>(st), a1 = umma_desc_kmajor<CV_BK>(st + CV_A);
+                        const uint64_t b = umma_desc_kmajor<CV_BK>(st + 2 * CV_A);
+#pragma unroll
+                        for (int k = 0; k < CV_BK / 8; ++k) {
+                            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                            umma_tf32_2sm(tmem_base, a0 + ko, b + ko, idesc, acc);
+                            umma_tf32_2sm(tmem_base + (uint32_t)CV_BN_MAX, a1 + ko, b + ko, idesc, acc);
+                        }
+                        umma_commit_2sm(&empty_bar[s]);
+                        if (kb == num_kb - 1) umma_commit_2sm(tmem_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+        // epilogue: two warp groups split each accumulator's columns, accumulator 0 then 1
+        const int ew = warp & 3, grp = warp >= 12 ? 1 : 0;
+        float *epi_tile = epi_smem + (grp * 4 + ew) * 32 * kEpiPitch;
+        const int half = ((BN / 32 + 1) / 2) * 32;
+        int local_tile = 0;
+        for (int qt = pair; qt < num_qtiles; qt += num_pairs, ++local_tile) {
+            tc_mbar_wait(tmem_full, local_tile & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const ConvTile t = C2D_TILE(qt, j);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * CV_BN_MAX);
+                conv_epilogue_tile<0>(args, t, taddr, epi_tile, epi_smem, lane, ew, BN, grp ? half : 0, grp ? BN : half);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_leader(tmem_empty);
+        }
+    }
+#undef C2D_TILE
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 static bool make_map_nd(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                         const cuuint32_t *box)
@@ -537,6 +669,21 @@ static int conv_tc_launch(int mode, const float *x, const float *w_taps, const f
     if (!ok) { set_error("cuTensorMapEncodeTiled unavailable or failed (conv)"); return FGN_ERR_CUDA; }
     int sm_count = 0;
     if (int rc = current_sm_count(&sm_count)) return rc;
+    const char *ed2 = getenv("FGN_TC_DUAL");                      // development knob: 0 = one row tile per CTA also for 3x3 / one pass
+    const bool dual = two_sm && mode == 0 && precision != 0 && a.taps == 9 && m_tiles >= 4 && !(ed2 != nullptr && ed2[0] == '0');
+    if (dual) {
+        const int pairs = min(sm_count / 2, ceil_div(m_tiles, 4) * (a.N / a.BN));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(C2_THREADS); cfg.dynamicSmemBytes = C2_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        FGN_SMEM_OPTIN(conv_tc2d_kernel, C2_SMEM);
+        FGN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc2d_kernel, ma, mbh, a));
+        FGN_LAUNCH_OK();
+        return FGN_OK;
+    }
     if (two_sm) {
         const int pairs = min(sm_count / 2, ceil_div(m_tiles, 2) * (a.N / a.BN));
         cudaLaunchConfig_t cfg = {};
