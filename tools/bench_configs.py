@@ -14,8 +14,14 @@ for name in names:
     E = 2 if cfg.batch > 1 or cfg.n_ways > 8 else 8
     eps = [episode_to_device(make_episode(cfg, seed=i), dev) for i in range(min(E, 2))]
     eps = [eps[i % len(eps)] for i in range(E)]
-    # C4 mode: the res5 shared_head (cuDNN, adjacent) is left out so the line measures the path's own kernels
-    rpn, head = build_heads(cfg, dev, shared_head=None)
+    # C4 mode: by default the res5 shared_head is left out so the line measures the guided path's own kernels;
+    # BENCH_SHARED_HEAD=tc / cudnn puts the reference's real res5 head in (the library's tcgen05 convolutions / the plain
+    # torch modules on cuDNN, both under torch's default allow_tf32) -- the reference's actual C4 mode end to end
+    sh = os.environ.get("BENCH_SHARED_HEAD", "")
+    rpn, head = build_heads(cfg, dev, shared_head="c4" if (sh and cfg.mode == "c4") else None)
+    if sh == "cudnn" and head.with_shared_head:
+        for m in head.shared_head:
+            m.tc_1x1, m.tc_3x3 = False, False
     streams = min(E, 8)
     runner = EpisodeRunner(rpn, head, eps, use_graphs=True, n_streams=streams, with_attention="fold" if FOLD else True)
 
@@ -36,7 +42,7 @@ for name in names:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     rois = E * cfg.num_rois * cfg.batch
-    print(json.dumps({"config": name, "attention": "folded into rpn_conv weights" if FOLD else "materialised", "mode": cfg.mode, "N": cfg.n_ways, "K": cfg.k_shots, "C": cfg.channels,
+    print(json.dumps({"config": name, "shared_head": (sh if head.with_shared_head else "none"), "attention": "folded into rpn_conv weights" if FOLD else "materialised", "mode": cfg.mode, "N": cfg.n_ways, "K": cfg.k_shots, "C": cfg.channels,
                       "R_per_call": cfg.num_rois * cfg.batch, "mask_P": cfg.mask_size, "episodes_per_step": E,
                       "streams": streams, "us_per_episode_call": round(ms * 1e3 / E, 1),
                       "RoIs_per_s": round(rois / ms * 1e3), "launches_per_episode": runner.launches_per_episode[0]}), flush=True)
