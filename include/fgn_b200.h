@@ -254,9 +254,9 @@ int fgn_cls_bbox_reassemble(const float *raw_cls, const float *raw_reg, int R, i
 /* FPN-mode single call (no shared_head between RoIAlign and the relation conv): level assignment + RoIAlign +
  * relation fusion + heads, three kernels (RoIAlign, RoI contraction, epilogue; a fourth, the class-term contraction, when
  * class_term is not handed over).  The RoI features
- * (NHWC, R*49*C*4 bytes) and the conv output travel through the caller's workspace between them: at the benchmark size
- * that is L2-resident traffic for the most part, but it is NOT zero -- the committed captures show 26 MB of DRAM writes by
- * the RoIAlign kernel and 51 MB of DRAM reads by the contraction per 1000 RoIs (profiles/r02_ncu_*.json).  A single kernel
+ * (NHWC, R*49*C*4 bytes) and the conv output travel through the caller's workspace between them.  Measured with the
+ * kernels chained and the caches left alone (profiles/r02_chained_fused_call_ncu.txt): per 1000 RoIs the contraction
+ * re-reads ~30 of the 50 MB of RoI features from DRAM (the rest is still in L2), the epilogue finds the conv output in L2.  A single kernel
  * that keeps them on chip was built and measured slower.  Same arguments as the two calls it replaces. */
 size_t fgn_guided_roi_fused_workspace_bytes(int R, int BN, int C, int P);
 int fgn_guided_roi_fused_fwd(const fgn_pyramid_t *pyr, int B, int C, const float *rois, int R,
