@@ -3,6 +3,7 @@
 // launch-latency bound when done one by one.  NHWC (channels_last) only; other layouts go through
 // the per-level entry points.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fgn {
 
@@ -15,6 +16,7 @@ struct MlLevels {
     float       *out[FGN_MAX_LEVELS];
     int          HW[FGN_MAX_LEVELS];
     int          blk_off[FGN_MAX_LEVELS + 1];   // block ranges per level (grid.x)
+    int          stream_loads;                  // multiply kernel: evict-first loads of the query maps (FGN_ATT_LDCS)
 };
 
 __device__ __forceinline__ int ml_level_of(const MlLevels &lv, int blk)
@@ -83,25 +85,36 @@ attention_vec_ml_partial_kernel(const MlLevels lv, const int BN, const int K, co
     ml_finish(lv, l, bn, BN, K, C, partial, vec, counters);
 }
 
-// out_l[b*N+n, :, :, c] = qry_l[b, :, :, c] * vec[l][b*N+n][c]; one read, N streaming writes
-__global__ void __launch_bounds__(256)
-channel_attention_ml_kernel(const MlLevels lv, const float *__restrict__ vec, const int B, const int N, const int C)
+// out_l[b*N+n, :, :, c] = qry_l[b, :, :, c] * vec[l][b*N+n][c]; one read, N streaming writes.
+// CH float4 per thread; MINB resident CTAs per SM asked of ptxas.  <4,5> (48 registers) is the production instantiation.
+// The lean ones (<4,6>: 40 registers, <2,8>: 32) and the persistent form (FGN_ATT_GRID CTAs per SM, grid-stride) were built to
+// let this HBM-bound kernel run UNDER the L2- / tensor-bound persistent kernels of other episodes -- a 256-thread CTA of 32
+// registers fits in what two RoIAlign CTAs or the contraction's CTA leave free.  Measured (tools/overlap_probe.py,
+// profiles/r02_overlap_probe.jsonl): it does not happen -- RoIAlign + attention on two streams take 81 us against 100 us back
+// to back whatever the form (a one-CTA-per-SM persistent attention of 110 us + RoIAlign: 142 us), the overlapped bench step
+// is 7.19-7.23 M RoIs/s for every variant; streaming (evict-first) loads of the query maps change nothing either.
+template <int CH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+channel_attention_ml_kernel(const MlLevels lv, const float *__restrict__ vec, const int B, const int N, const int C,
+                            const int nblocks)
 {
-    const int l = ml_level_of(lv, blockIdx.x), blk = blockIdx.x - lv.blk_off[l];
+  for (int gb = blockIdx.x; gb < nblocks; gb += gridDim.x) {         // (grid < nblocks: the persistent form, FGN_ATT_GRID)
+    const int l = ml_level_of(lv, gb), blk = gb - lv.blk_off[l];
     const int c4 = C >> 2;
     const size_t per_img = (size_t)lv.HW[l] * c4, total = (size_t)B * per_img;
     const float *q = lv.in[l];
     float *o = lv.out[l];
     const float *v = vec + (size_t)l * B * N * C;
-    const size_t i0 = (size_t)blk * (256 * kMlChunk) + threadIdx.x;
-    float4 x[kMlChunk];
+    const size_t i0 = (size_t)blk * (256 * CH) + threadIdx.x;
+    float4 x[CH];
 #pragma unroll
-    for (int j = 0; j < kMlChunk; ++j) {
+    for (int j = 0; j < CH; ++j) {
         const size_t i = i0 + (size_t)j * 256;
-        x[j] = i < total ? ldg4(q + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[j] = i < total ? (lv.stream_loads ? __ldcs(reinterpret_cast<const float4 *>(q) + i) : ldg4(q + 4 * i))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < kMlChunk; ++j) {
+    for (int j = 0; j < CH; ++j) {
         const size_t i = i0 + (size_t)j * 256;
         if (i >= total) continue;
         const int b = i / per_img;
@@ -113,6 +126,7 @@ channel_attention_ml_kernel(const MlLevels lv, const float *__restrict__ vec, co
                    make_float4(x[j].x * s.x, x[j].y * s.y, x[j].z * s.z, x[j].w * s.w));
         }
     }
+  }
 }
 
 // ---- bf16 variants: 8 channels per 128-bit access, fp32 accumulation / multiply ----------------
@@ -297,16 +311,47 @@ static int channel_attention_ml_impl(const fgn_pyramid_t *qry, const float *vec,
     int rc = fill_levels(qry, lv);
     if (rc) return rc;
     FGN_CHECK_ARG(vec && out_host, "NULL pointer");
+    // FGN_ATT_LEAN (development knob): 0 = 4 float4 per thread, 48 registers (round 1); 1 = same at <= 40 registers; 2 = lean
+    const char *el = getenv("FGN_ATT_LEAN");
+    const int lean = el != nullptr ? atoi(el) : 0;
+    const int chunk = bf16 ? kMlChunk : (lean >= 2 ? 2 : 4);
     lv.blk_off[0] = 0;
     for (int l = 0; l < lv.L; ++l) {
         FGN_CHECK_ARG(out_host[l] != nullptr, "output level %d is NULL", l);
         lv.out[l] = out_host[l];
         const size_t elems = (size_t)B * lv.HW[l] * (bf16 ? C >> 3 : C >> 2);
-        lv.blk_off[l + 1] = lv.blk_off[l] + (int)((elems + 256 * kMlChunk - 1) / (256 * kMlChunk));
+        lv.blk_off[l + 1] = lv.blk_off[l] + (int)((elems + 256 * chunk - 1) / (256 * chunk));
     }
     for (int l = lv.L + 1; l <= FGN_MAX_LEVELS; ++l) lv.blk_off[l] = lv.blk_off[lv.L];
-    if (bf16) channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
-    else      channel_attention_ml_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    const int nblocks = lv.blk_off[lv.L];
+    { const char *es = getenv("FGN_ATT_LDCS"); lv.stream_loads = es != nullptr ? atoi(es) : 0; }
+    int grid = nblocks;
+    if (const char *eg = getenv("FGN_ATT_GRID")) {                  // development knob: persistent form, CTAs per SM
+        int sm = 0;
+        if (int rcs = current_sm_count(&sm)) return rcs;
+        if (atoi(eg) > 0) grid = min(nblocks, atoi(eg) * sm);
+    }
+    if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    const int nblocks = lv.blk_off[lv.L];
+    { const char *es = getenv("FGN_ATT_LDCS"); lv.stream_loads = es != nullptr ? atoi(es) : 0; }
+    int grid = nblocks;
+    if (const char *eg = getenv("FGN_ATT_GRID")) {                  // development knob: persistent form, CTAs per SM
+        int sm = 0;
+        if (int rcs = current_sm_count(&sm)) return rcs;
+        if (atoi(eg) > 0) grid = min(nblocks, atoi(eg) * sm);
+    }
+    if (const char *ec = getenv("FGN_ATT_CARVEOUT")) {            // experiment: the SM configuration the persistent kernels use
+        const int co = atoi(ec);
+        if (co >= 0) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(channel_attention_ml_kernel<4, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+            FGN_CUDA_OK(cudaFuncSetAttribute(channel_attention_ml_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        }
+    }
+    if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
+    else if (lean == 0)  channel_attention_ml_kernel<4, 5><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C, nblocks);
+    else if (lean == 1)  channel_attention_ml_kernel<4, 6><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C, nblocks);
+    else                 channel_attention_ml_kernel<2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C, nblocks);
     FGN_LAUNCH_OK();
     return FGN_OK;
 }
