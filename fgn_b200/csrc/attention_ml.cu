@@ -323,7 +323,6 @@ static int channel_attention_ml_impl(const fgn_pyramid_t *qry, const float *vec,
         lv.blk_off[l + 1] = lv.blk_off[l] + (int)((elems + 256 * chunk - 1) / (256 * chunk));
     }
     for (int l = lv.L + 1; l <= FGN_MAX_LEVELS; ++l) lv.blk_off[l] = lv.blk_off[lv.L];
-    if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
     const int nblocks = lv.blk_off[lv.L];
     { const char *es = getenv("FGN_ATT_LDCS"); lv.stream_loads = es != nullptr ? atoi(es) : 0; }
     int grid = nblocks;
@@ -331,22 +330,6 @@ static int channel_attention_ml_impl(const fgn_pyramid_t *qry, const float *vec,
         int sm = 0;
         if (int rcs = current_sm_count(&sm)) return rcs;
         if (atoi(eg) > 0) grid = min(nblocks, atoi(eg) * sm);
-    }
-    if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
-    const int nblocks = lv.blk_off[lv.L];
-    { const char *es = getenv("FGN_ATT_LDCS"); lv.stream_loads = es != nullptr ? atoi(es) : 0; }
-    int grid = nblocks;
-    if (const char *eg = getenv("FGN_ATT_GRID")) {                  // development knob: persistent form, CTAs per SM
-        int sm = 0;
-        if (int rcs = current_sm_count(&sm)) return rcs;
-        if (atoi(eg) > 0) grid = min(nblocks, atoi(eg) * sm);
-    }
-    if (const char *ec = getenv("FGN_ATT_CARVEOUT")) {            // experiment: the SM configuration the persistent kernels use
-        const int co = atoi(ec);
-        if (co >= 0) {
-            FGN_CUDA_OK(cudaFuncSetAttribute(channel_attention_ml_kernel<4, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-            FGN_CUDA_OK(cudaFuncSetAttribute(channel_attention_ml_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        }
     }
     if (bf16)            channel_attention_ml_bf16_kernel<<<lv.blk_off[lv.L], 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C);
     else if (lean == 0)  channel_attention_ml_kernel<4, 5><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, vec, B, N, C, nblocks);
