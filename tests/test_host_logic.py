@@ -203,3 +203,22 @@ def test_roi_head_builds_the_configs_mask_head():
     import torch
     x = torch.randn(2, 64, 14, 14)
     assert head.mask_head(x).shape == (2, 1, 28, 28)                     # CPU tensors: the plain torch modules
+
+
+def test_count_spp_class_term_is_bound_to_its_class_maps_and_weights():
+    """The class half of the relation conv that the one-launch support branch leaves on the head is used only while it
+    belongs to the class maps on ``self`` and to the packed weights about to be used (host logic, no device work)."""
+    import torch
+    from fgn_b200 import FGNRoIHead
+    head = FGNRoIHead(shared_head=None, channels=64)
+    assert head.fused_prologue is True and head.fused_prologue_max_supports == 32
+    cat, params, other = torch.zeros(1, 1, 64, 7, 7), object(), object()
+    term = torch.zeros(49, 64)
+    head.spp_fmaps_roi_aligned_cat_mean = cat
+    head._class_term = (term, cat, params)
+    assert head._valid_class_term(params) is term
+    assert head._valid_class_term(other) is None                         # re-packed weights
+    head.spp_fmaps_roi_aligned_cat_mean = torch.zeros_like(cat)           # class maps assigned by hand since
+    assert head._valid_class_term(params) is None
+    head._class_term = None
+    assert head._valid_class_term(params) is None
