@@ -143,7 +143,7 @@ def test_bottleneck_three_convs_on_tcgen05(prec_tf32):
     assert bool((err <= atol + (1e-2 if prec_tf32 else 1e-4) * want.abs()).all()), f"bottleneck [{prec}] max abs err {float(err.max()):.3e}"
 
 
-@pytest.mark.parametrize("name", ["tiny_fpn", "tiny_c4", "cfg3_coco2voc_n1k1_fpn", "cfg4_coco2voc_n20k5_fpn"])
+@pytest.mark.parametrize("name", ["tiny_fpn", "tiny_c4", "tiny_fpn_big_support", "cfg3_coco2voc_n1k1_fpn", "cfg4_coco2voc_n20k5_fpn"])
 def test_support_prologue_one_launch_against_the_separate_ops_and_the_oracle(name):
     """count_spp as ONE launch (fgn_support_prologue_fwd) against the four separate library ops it replaces and, for the
     class maps / vectors, against the oracle's count_spp (fgn_roi_head.py:419-449); its class term against the exact
@@ -152,7 +152,12 @@ def test_support_prologue_one_launch_against_the_separate_ops_and_the_oracle(nam
     from fgn_b200.episodes import CONFIGS, build_heads, episode_to_device, make_episode
     from oracle import fgn_oracle as O
     dev = torch.device(DEV)
-    cfg = CONFIGS[name]
+    if name == "tiny_fpn_big_support":
+        # a 640-px support: the mask bin's adaptive grid is 74 x 74 samples, past the 64 staged per axis (on-the-fly path)
+        import dataclasses
+        cfg = dataclasses.replace(CONFIGS["tiny_fpn"], name=name, spp_size=640, n_ways=2, k_shots=1)
+    else:
+        cfg = CONFIGS[name]
     ep = make_episode(cfg, seed=3)
     _, head = build_heads(cfg, dev, seed=0, shared_head=None)
     epd = episode_to_device(ep, dev)
@@ -191,3 +196,52 @@ def test_support_prologue_one_launch_against_the_separate_ops_and_the_oracle(nam
         b = head._bbox_forward(qry, epd["rois"])
     close(a["cls_score"], b["cls_score"], "fp32", "cls_score with / without precomputed class term")
     close(a["bbox_pred"], b["bbox_pred"], "fp32", "bbox_pred with / without precomputed class term")
+
+
+def _guarded(numel, device, pad=4096):
+    """fp32 buffer of `numel` elements between two canary regions (compute-sanitizer is not available on the GPU pool)"""
+    buf = torch.full((numel + 2 * pad,), 777.25, device=device, dtype=torch.float32)
+    return buf, buf[pad:pad + numel], pad
+
+
+def _canaries_intact(buf, numel, pad):
+    return bool((buf[:pad] == 777.25).all()) and bool((buf[pad + numel:] == 777.25).all())
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("r,cin,cout,h,w", [(37, 64, 64, 7, 7), (5, 32, 256, 14, 14), (7, 64, 512, 7, 7), (9, 16, 32, 3, 3),
+                                            (3, 48, 64, 10, 20), (1, 16, 48, 7, 7)])
+def test_conv_kernels_write_nothing_outside_their_output(prec, r, cin, cout, h, w):
+    """Raw C-ABI calls with the output between canaries: the single-CTA, CTA-pair and two-row-tile kernels pad their last
+    tiles (pairs / quads of row tiles, 98- and 126-row boxes) -- none of the padding may reach memory."""
+    import ctypes
+    from fgn_b200 import _lib, ops
+    lib = _lib.load()
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(r + cin)
+    x = torch.randn(r, h, w, cin, generator=g).to(dev)
+    taps = (torch.randn(9, cout, cin, generator=g) / (3 * cin ** 0.5)).to(dev)
+    n = r * h * w * cout
+    buf, out, pad = _guarded(n, dev)
+    wsb = int(lib.fgn_conv_split_weights_bytes(9, cout, cin))
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.fgn_conv3x3_nhwc(x.data_ptr(), taps.data_ptr(), None, None, None, 0, out.data_ptr(), r, h, w, cin, cout, prec,
+                                    ws.data_ptr(), wsb, st), "fgn_conv3x3_nhwc")
+    torch.cuda.synchronize()
+    assert _canaries_intact(buf, n, pad)
+    want = F.conv2d(x.permute(0, 3, 1, 2).cpu(), taps.cpu().view(3, 3, cout, cin).permute(2, 3, 0, 1), padding=1)
+    close(out.view(r, h, w, cout).permute(0, 3, 1, 2), want, "fp32" if prec == 0 else "tf32", "conv3x3 through the raw ABI")
+    # deconv tail on the same activations
+    ncls = 2
+    up = (torch.randn(4, 32, cin, generator=g) / cin ** 0.5).to(dev)
+    wl, bl, bd = torch.randn(ncls, 32, generator=g).to(dev) / 6, torch.randn(ncls, generator=g).to(dev), torch.randn(32, generator=g).to(dev)
+    m = r * ncls * 4 * h * w
+    buf2, out2, pad2 = _guarded(m, dev)
+    wsb2 = int(lib.fgn_conv_split_weights_bytes(4, 32, cin))
+    ws2 = torch.empty(wsb2, device=dev, dtype=torch.uint8)
+    _lib.check(lib.fgn_deconv2x2_logits_nhwc(x.data_ptr(), up.data_ptr(), None, bd.data_ptr(), wl.data_ptr(), bl.data_ptr(), out2.data_ptr(),
+                                             r, h, w, cin, 32, ncls, prec, ws2.data_ptr(), wsb2, st), "fgn_deconv2x2_logits_nhwc")
+    torch.cuda.synchronize()
+    assert _canaries_intact(buf2, m, pad2)
+    assert bool(torch.isfinite(out2).all())
