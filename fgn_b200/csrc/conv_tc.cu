@@ -1,18 +1,25 @@
-// conv_tc.cu -- the post-RoI heads' convolutions as implicit GEMMs on tcgen05:
-//   * the 3x3 / pad 1 convolutions of the C4 res5 shared_head (fgn_roi_head.py:202-233, mmdet Bottleneck.conv2 [3P]) and
+// conv_tc.cu -- every fp32 contraction of the library on tcgen05: the relation head's 1x1 conv (fgn_roi_head.py:272) and
+// its adjoint's contractions, and the post-RoI heads' convolutions as implicit GEMMs:
+//   * the 1x1 / 3x3 (pad 1) convolutions of the C4 res5 shared_head (fgn_roi_head.py:202-233, mmdet Bottleneck [3P]) and
 //     of FCNMaskHead.convs (fgn_r50_c4_densecl.py:115-129, num_convs=4 [3P]) over NHWC RoI tiles [R,H,W,Cin];
 //   * FCNMaskHead's tail -- ConvTranspose2d(k=2, s=2) + ReLU + conv_logits (1x1) -- as ONE contraction whose epilogue takes
 //     the ReLU and the logits' dot product straight out of tensor memory: the [R,2H,2W,Cout] upsampled map (80 MB for 100
 //     detections at 14x14 -> 28x28, 256 channels) is never written.
+//
+// Three kernels, one pipeline (TMA producer warp, MMA issuer warp, operand splitters for the 3xTF32 route, epilogue warps,
+// accumulators in tensor memory):
+//   conv_tc2_kernel   CTA pairs, tcgen05.mma.cta_group::2 (256-row MMAs, half a B tile per SM): the production kernel;
+//   conv_tc2d_kernel  the same with two row tiles per CTA against one half B tile: 3x3 convolutions under one TF32 pass;
+//   conv_tc_kernel    one CTA per tile: shapes the pair kernels decline (column tiles not a multiple of 32, one row tile).
 //
 // No im2col buffer: the A operand of tap (dy,dx) is the SAME activation tensor read through a 4D TMA descriptor
 // (C, W, H, R) with the box origin shifted by (dx-1, dy-1); what falls outside the RoI tile is zero-filled by the TMA
 // unit, which is exactly the convolution's zero padding.  A tile is a box of whole rows: RB whole RoIs (7x7: two RoIs = 98
 // of the 128 MMA rows) or HB rows of one RoI (14x14: nine rows = 126); the MMA rows beyond the box hold stale shared
 // memory and produce accumulator rows nobody reads.  The k loop runs over taps x Cin/16; weights are laid out
-// [tap][Cout][Cin] (K-major rows, one 2D descriptor).  Precision as in gemm_tc.cu: 3xTF32 (fp32 parity) or one TF32 pass.
-// Pipeline = gemm_tc.cu's: TMA producer warp, MMA issuer warp, four splitter warps (A_lo), four epilogue warps,
-// double-buffered accumulators in tensor memory.
+// [tap][Cout][Cin] (K-major rows, one 2D descriptor).  Precision: 3xTF32 (x = hi + lo with hi = x's top 19 bits;
+// D += A_hi B_hi + A_hi B_lo + A_lo B_hi in fp32 tensor memory -- fp32 parity up to the accumulator's truncation, DESIGN.md
+// section 2) or one TF32 pass.
 #include "gemm.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
