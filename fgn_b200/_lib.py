@@ -107,6 +107,9 @@ SIGNATURES = {
                                               _P, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
                                               _P, _P, _P, _P, c_size_t, _P]),
     "fgn_roi_align_ml_bwd": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "fgn_roi_align_ml_bwd_det_workspace_bytes": (c_size_t, [POINTER(Pyramid), c_int, c_int]),
+    "fgn_roi_align_ml_bwd_det": (c_int, [POINTER(Pyramid), c_int, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, _P,
+                                         _P, c_size_t, _P]),
     "fgn_channel_attention_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "fgn_channel_attention_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "fgn_attention_vectors_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -27,6 +27,20 @@ def _needs_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
 
 
+_DETERMINISTIC = None          # None: follow torch.are_deterministic_algorithms_enabled()
+
+
+def set_deterministic_backward(flag) -> None:
+    """RoIAlign backward with order-independent (64-bit fixed-point) accumulation: True / False, or None to follow
+    ``torch.use_deterministic_algorithms``.  The default scatter uses float atomics like mmcv's own backward."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = flag
+
+
+def deterministic_backward() -> bool:
+    return torch.are_deterministic_algorithms_enabled() if _DETERMINISTIC is None else bool(_DETERMINISTIC)
+
+
 class _RoIAlignML(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rois, scales, output_size, sampling_ratio, aligned, finest_scale, *feats):
@@ -51,9 +65,18 @@ class _RoIAlignML(torch.autograd.Function):
         for i, (gr, s) in enumerate(zip(grads, shapes)):
             pyr.feat[i], pyr.H[i], pyr.W[i], pyr.spatial_scale[i] = gr.data_ptr(), s[2], s[3], float(scales[i])
         r = rois.shape[0]
-        _lib.check(_lib.load().fgn_roi_align_ml_bwd(ctypes.byref(pyr), b, c, rois.contiguous().data_ptr(), r, p, sr,
-                                                    int(aligned), finest, None, None, g.data_ptr(),
-                                                    torch.cuda.current_stream().cuda_stream), "fgn_roi_align_ml_bwd")
+        lib = _lib.load()
+        if deterministic_backward():
+            # bit-identical gradients from run to run: 64-bit fixed-point accumulation (fgn_roi_align_ml_bwd_det)
+            wsb = int(lib.fgn_roi_align_ml_bwd_det_workspace_bytes(ctypes.byref(pyr), b, c))
+            ws = torch.empty((max(wsb, 1),), device=g.device, dtype=torch.uint8)
+            _lib.check(lib.fgn_roi_align_ml_bwd_det(ctypes.byref(pyr), b, c, rois.contiguous().data_ptr(), r, p, sr, int(aligned),
+                                                    finest, None, 0, None, g.data_ptr(), ws.data_ptr(), wsb,
+                                                    torch.cuda.current_stream().cuda_stream), "fgn_roi_align_ml_bwd_det")
+        else:
+            _lib.check(lib.fgn_roi_align_ml_bwd(ctypes.byref(pyr), b, c, rois.contiguous().data_ptr(), r, p, sr,
+                                                int(aligned), finest, None, None, g.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "fgn_roi_align_ml_bwd")
         return (None,) * 6 + tuple(grads)
 
 

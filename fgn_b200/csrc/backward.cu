@@ -22,13 +22,50 @@ struct BwdPlan {
     int   overflow;
 };
 
-template <int P>
+__global__ void absmax_bits_kernel(const float *__restrict__ x, const size_t n, unsigned int *__restrict__ out)
+{
+    unsigned int m = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(x[i])) & 0x7fffffffu);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m);       // max of non-negative float bit patterns: order-independent
+}
+
+// DET: deterministic mode.  Float atomics make the sum depend on the order the RoIs' CTAs happen to run in; here every
+// contribution is rounded once to a 64-bit fixed-point number (value * 2^e, e chosen from max |grad_out| and max |chan_scale|
+// so that the largest term sits near 2^40: 2^-40 of it in resolution, 2^22 terms of headroom) and added with integer atomics
+// -- integer addition is associative, so the result is bit-identical from run to run whatever the schedule.  feat[l] then
+// points at the level's int64 accumulators; fgn_roi_align_ml_bwd_det converts and adds them to the gradient maps.
+struct DetScale { unsigned int max_g, max_cs; };           // float bits of the maxima (non-negative floats order like uints)
+
+__device__ __forceinline__ double det_multiplier(const DetScale *det)
+{
+    // 2^e with 2^e * (max|g| * max(1, max|cs|)) in [2^39, 2^40]: exponent arithmetic only, the same on every thread
+    float top = __uint_as_float(det->max_g);
+    const float cs = __uint_as_float(det->max_cs);
+    if (cs > 1.f) top *= cs;
+    if (!(top > 0.f) || !(top < 3.0e38f)) return 1.0;                // all-zero or non-finite gradients: nothing to scale
+    int ex;
+    frexpf(top, &ex);                                                // top = m * 2^ex, m in [0.5, 1)
+    return ldexp(1.0, 40 - ex);
+}
+
+__global__ void det_finish_kernel(const long long *__restrict__ acc, float *__restrict__ grad, const size_t n, const DetScale *__restrict__ det)
+{
+    const double inv = 1.0 / det_multiplier(det);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const long long a = acc[i];
+        if (a != 0) grad[i] += (float)((double)a * inv);
+    }
+}
+
+template <int P, bool DET>
 __global__ void __launch_bounds__(P * 32)
 roi_align_bwd_kernel(const Pyramid pyr /* feat[l] = gradient buffer of level l, accumulated into */, const int C,
                      const float *__restrict__ rois, const int R, const int sampling_ratio, const int aligned,
                      const float finest_scale, const float *__restrict__ chan_scale,
                      const int32_t *__restrict__ scale_index, const float *__restrict__ grad_out,
-                     const int wtab_cap)
+                     const int wtab_cap, const DetScale *__restrict__ det = nullptr)
 {
     extern __shared__ __align__(16) float wtab[];
     __shared__ BwdPlan plan;
@@ -90,6 +127,8 @@ roi_align_bwd_kernel(const Pyramid pyr /* feat[l] = gradient buffer of level l, 
         cs = ldg4(chan_scale + (size_t)si * C + c);
     }
     const float inv = 1.0f / plan.count;
+    double det_mul = 1.0;
+    if (DET) det_mul = det_multiplier(det);
     float4 gv[P];
 #pragma unroll
     for (int pw = 0; pw < P; ++pw) {
@@ -109,6 +148,14 @@ roi_align_bwd_kernel(const Pyramid pyr /* feat[l] = gradient buffer of level l, 
             for (int xi = 0; xi < nx; ++xi) {
                 const float w = wyv * wx[xi];
                 if (w == 0.f) continue;
+                if (DET) {
+                    unsigned long long *acc = reinterpret_cast<unsigned long long *>(const_cast<float *>(pyr.feat[plan.level])) +
+                                              ((size_t)plan.batch * plan.H * W + (size_t)(ylo + yi) * W + (xlo + xi)) * C + c;
+                    atomicAdd(acc + 0, (unsigned long long)__double2ll_rn((double)(w * gv[pw].x) * det_mul));
+                    atomicAdd(acc + 1, (unsigned long long)__double2ll_rn((double)(w * gv[pw].y) * det_mul));
+                    atomicAdd(acc + 2, (unsigned long long)__double2ll_rn((double)(w * gv[pw].z) * det_mul));
+                    atomicAdd(acc + 3, (unsigned long long)__double2ll_rn((double)(w * gv[pw].w) * det_mul));
+                } else
                 atomicAdd(reinterpret_cast<float4 *>(row + (size_t)(xlo + xi) * C),
                           make_float4(w * gv[pw].x, w * gv[pw].y, w * gv[pw].z, w * gv[pw].w));
             }
@@ -245,11 +292,73 @@ extern "C" int fgn_roi_align_ml_bwd(const fgn_pyramid_t *grad_pyr, int B, int C,
     const int cap = (maxH + maxW + 6 * P + 16 + 3) & ~3;
     const int nblk = (C + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (P == 7) roi_align_bwd_kernel<7><<<R * nblk, 7 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
-                                                                                 finest_scale, chan_scale, scale_index, grad_out, cap);
-    else        roi_align_bwd_kernel<14><<<R * nblk, 14 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
-                                                                                   finest_scale, chan_scale, scale_index, grad_out, cap);
+    if (P == 7) roi_align_bwd_kernel<7, false><<<R * nblk, 7 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
+                                                                                        finest_scale, chan_scale, scale_index, grad_out, cap);
+    else        roi_align_bwd_kernel<14, false><<<R * nblk, 14 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
+                                                                                          finest_scale, chan_scale, scale_index, grad_out, cap);
     FGN_LAUNCH_OK();
+    return FGN_OK;
+}
+
+static size_t det_level_elems(const fgn_pyramid_t *p, int B, int C, int l) { return (size_t)B * p->H[l] * p->W[l] * C; }
+
+extern "C" size_t fgn_roi_align_ml_bwd_det_workspace_bytes(const fgn_pyramid_t *grad_pyr, int B, int C)
+{
+    if (!grad_pyr || B <= 0 || C <= 0) return 0;
+    size_t n = 0;
+    for (int l = 0; l < grad_pyr->num_levels && l < FGN_MAX_LEVELS; ++l) n += det_level_elems(grad_pyr, B, C, l);
+    return 256 + n * sizeof(long long);
+}
+
+// Deterministic form of fgn_roi_align_ml_bwd (same arguments + workspace): bit-identical gradients from run to run.
+// chan_scale_rows: rows of chan_scale ([rows, C]; 0 when chan_scale is NULL).
+extern "C" int fgn_roi_align_ml_bwd_det(const fgn_pyramid_t *grad_pyr, int B, int C, const float *rois, int R, int P,
+                                        int sampling_ratio, int aligned, float finest_scale, const float *chan_scale,
+                                        int chan_scale_rows, const int32_t *scale_index, const float *grad_out,
+                                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    FGN_CHECK_ARG(grad_pyr != nullptr && grad_pyr->num_levels >= 1 && grad_pyr->num_levels <= FGN_MAX_LEVELS, "bad pyramid");
+    FGN_CHECK_ARG(R >= 0 && B >= 0 && C > 0 && (C & 3) == 0, "roi_align_bwd needs C%%4==0 (C=%d)", C);
+    if (R == 0) return FGN_OK;
+    FGN_CHECK_ARG(rois && grad_out, "NULL pointer");
+    FGN_CHECK_ARG(chan_scale == nullptr || chan_scale_rows > 0, "chan_scale_rows");
+    for (int l = 0; l < grad_pyr->num_levels; ++l) FGN_CHECK_ARG(grad_pyr->feat[l], "gradient level %d is NULL", l);
+    if (P != 7 && P != 14) { set_error("roi_align_bwd: P=%d not instantiated (7, 14)", P); return FGN_ERR_UNSUPPORTED; }
+    const size_t need = fgn_roi_align_ml_bwd_det_workspace_bytes(grad_pyr, B, C);
+    if (!workspace || workspace_bytes < need) {
+        set_error("roi_align_bwd_det: workspace %zu B < required %zu B", workspace_bytes, need);
+        return FGN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    FGN_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+    DetScale *det = (DetScale *)workspace;
+    long long *acc0 = (long long *)((char *)workspace + 256);
+    absmax_bits_kernel<<<296, 256, 0, st>>>(grad_out, (size_t)R * P * P * C, &det->max_g);
+    FGN_LAUNCH_OK();
+    if (chan_scale != nullptr) {
+        absmax_bits_kernel<<<64, 256, 0, st>>>(chan_scale, (size_t)chan_scale_rows * C, &det->max_cs);
+        FGN_LAUNCH_OK();
+    }
+    fgn_pyramid_t accp = *grad_pyr;                                  // same geometry, feat[l] = the level's int64 accumulators
+    size_t off = 0;
+    for (int l = 0; l < grad_pyr->num_levels; ++l) { accp.feat[l] = (float *)(acc0 + off); off += det_level_elems(grad_pyr, B, C, l); }
+    const Pyramid d = to_device_pyramid(&accp, B);
+    int maxH = 0, maxW = 0;
+    for (int l = 0; l < d.L; ++l) { maxH = max(maxH, d.H[l]); maxW = max(maxW, d.W[l]); }
+    const int cap = (maxH + maxW + 6 * P + 16 + 3) & ~3;
+    const int nblk = (C + 127) / 128;
+    if (P == 7) roi_align_bwd_kernel<7, true><<<R * nblk, 7 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
+                                                                                       finest_scale, chan_scale, scale_index, grad_out, cap, det);
+    else        roi_align_bwd_kernel<14, true><<<R * nblk, 14 * 32, (size_t)cap * 4, st>>>(d, C, rois, R, sampling_ratio, aligned,
+                                                                                         finest_scale, chan_scale, scale_index, grad_out, cap, det);
+    FGN_LAUNCH_OK();
+    off = 0;
+    for (int l = 0; l < grad_pyr->num_levels; ++l) {
+        const size_t n = det_level_elems(grad_pyr, B, C, l);
+        det_finish_kernel<<<(int)min((size_t)148 * 8, (n + 255) / 256), 256, 0, st>>>(acc0 + off, const_cast<float *>(grad_pyr->feat[l]), n, det);
+        FGN_LAUNCH_OK();
+        off += n;
+    }
     return FGN_OK;
 }
 

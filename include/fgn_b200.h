@@ -303,6 +303,16 @@ int fgn_roi_align_ml_bwd(const fgn_pyramid_t *grad_pyr, int B, int C, const floa
                          int sampling_ratio, int aligned, float finest_scale,
                          const float *chan_scale, const int32_t *scale_index,
                          const float *grad_out, void *stream);
+/* Deterministic form of fgn_roi_align_ml_bwd: every contribution is rounded once to 64-bit fixed point (scale chosen from
+ * max |grad_out| and max |chan_scale|: 2^-40 of the largest term in resolution) and added with integer atomics, so the
+ * gradient maps are bit-identical from run to run whatever order the RoIs' CTAs run in (float atomics -- this library's
+ * default and mmcv's own backward -- are not).  chan_scale_rows: rows of chan_scale (0 if NULL).
+ * workspace: fgn_roi_align_ml_bwd_det_workspace_bytes(grad_pyr, B, C) bytes. */
+size_t fgn_roi_align_ml_bwd_det_workspace_bytes(const fgn_pyramid_t *grad_pyr, int B, int C);
+int fgn_roi_align_ml_bwd_det(const fgn_pyramid_t *grad_pyr, int B, int C, const float *rois, int R, int P,
+                             int sampling_ratio, int aligned, float finest_scale, const float *chan_scale,
+                             int chan_scale_rows, const int32_t *scale_index, const float *grad_out,
+                             void *workspace, size_t workspace_bytes, void *stream);
 /* Adjoint of fgn_channel_attention: grad_qry [B,H,W,C] = sum_n g*vec, grad_vec [B*N,C] = sum_hw g*qry;
  * either output may be NULL. */
 size_t fgn_channel_attention_bwd_workspace_bytes(int B, int N, int C, int H, int W);

@@ -200,3 +200,34 @@ def test_agrpn_train_mode_builds_the_per_class_loss_inputs_and_backpropagates():
     (losses["loss_rpn_cls"][0] + losses["loss_rpn_bbox"][0]).backward()
     assert q.grad is not None and s.grad is not None and float(q.grad.abs().max()) > 0 and float(s.grad.abs().max()) > 0
     assert head.rpn_conv.weight.grad is not None
+
+
+def test_roi_align_backward_deterministic_option():
+    """fgn_roi_align_ml_bwd_det: 64-bit fixed-point accumulation -- the gradients of many heavily overlapping RoIs are
+    bit-identical from run to run (the float-atomic default is allowed not to be) and match autograd over the oracle."""
+    from fgn_b200 import autograd as A
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(311)
+    strides, B, C = [4, 8, 16, 32], 2, 64
+    feats = [torch.randn(B, C, 256 // s, 320 // s, generator=g) for s in strides]
+    rois = synth_rois(g, 600, 256, 320, B, smin=24.0)                     # large boxes: hundreds of terms per cell
+    gout = torch.randn(600, C, 7, 7, generator=g) * 3.0
+    fc = [f.clone().requires_grad_(True) for f in feats]
+    want, _ = O.single_roi_extractor(fc, rois, strides, 7, 0, True, 56.0, "tv")
+    want.backward(gout)
+    runs = []
+    A.set_deterministic_backward(True)
+    try:
+        for _ in range(3):
+            fd = [f.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+            got = A.roi_align_multilevel(fd, rois.to(dev()), [1 / s for s in strides], 7, 0, True)
+            got.backward(gout.to(dev()))
+            runs.append([f.grad.clone() for f in fd])
+    finally:
+        A.set_deterministic_backward(None)
+    for l in range(4):
+        assert torch.equal(runs[0][l], runs[1][l]) and torch.equal(runs[0][l], runs[2][l]), f"level {l} differs between runs"
+        if fc[l].grad is not None:
+            close(runs[0][l], fc[l].grad, atol=5e-4, rtol=1e-5, what=f"deterministic grad level {l}")
+    # the switch follows torch.use_deterministic_algorithms when left at None
+    assert A.deterministic_backward() == torch.are_deterministic_algorithms_enabled()
