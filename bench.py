@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="fgn_b200", choices=["fgn_b200", "reference"])
-    ap.add_argument("--episodes-per-step", type=int, default=16, help="distinct episodes per GPU per step")
+    ap.add_argument("--episodes-per-step", type=int, default=24, help="distinct episodes per GPU per step")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,6 +181,10 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="side streams episodes are replayed on round-robin")
     ap.add_argument("--e2e-streams", type=int, default=8, help="streams the end-to-end leg overlaps copies and compute on")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--images-per-call", type=int, default=12,
+                    help="query images (episodes) batched into one call of the path, as the reference batches them "
+                         "(main.py:492-499: batch = 12 for 1-way 1-shot, 10 for N3K1, 8 for N3K3); 1 = one call per episode")
+    ap.add_argument("--no-large-launch", action="store_true", help="skip the RoIAlign roofline at cfg5's 8192-RoI launch")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle subset check of episode 0 before timing")
     ap.add_argument("--no-gather-overhead", action="store_true", help="skip the W=1 run with the result gather enabled")
     args = ap.parse_args()
@@ -219,8 +223,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the fgn_b200 arm has no CPU fallback (use --impl reference)")
     import torch.distributed as dist
     from fgn_b200 import ops
-    from fgn_b200.episodes import (EpisodeRunner, ResultGatherer, build_heads, episode_to_device, gather_results,
-                                   make_episode, make_weights, run_guided_path)
+    from fgn_b200.episodes import (EpisodeRunner, ResultGatherer, batch_episodes, build_heads, episode_to_device,
+                                   gather_results, make_episode, make_weights, run_guided_path)
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -250,6 +254,14 @@ def main():
         if i >= len(host_eps):      # distinct data without the CPU RNG cost: perturb on device
             ep["qry"] = [q + 0.01 * i for q in ep["qry"]]
         dev_eps.append(ep)
+    # Episodes are batched into calls of B_call query images -- the reference's own way of running them (B query images x
+    # N x K supports per step, main.py:492-499: batch = 12 for 1-way 1-shot); per-image work and results are unchanged (checked below,
+    # bit for bit, against one eager call per episode), the launches are B_call times larger.
+    B_call = max(1, min(args.images_per_call, E))
+    if E % B_call or cfg.batch != 1:
+        B_call = 1
+    n_calls = E // B_call
+    call_eps = [batch_episodes(dev_eps[j * B_call:(j + 1) * B_call]) for j in range(n_calls)] if B_call > 1 else dev_eps
     rpn, head = build_heads(cfg, device, seed=0, shared_head=None if cfg.mode == "fpn" else "c4")
     bytes_resident = sum(t.numel() * 4 for ep in dev_eps for t in ep["qry"] + ep["spp"])
     config["l2"] = f"no flush: episode stream of {E} x {bytes_resident / E / 1e6:.0f} MB distinct inputs > 126 MB L2"
@@ -269,24 +281,26 @@ def main():
             raise SystemExit(f"bench.py: parity check failed before timing: {json.dumps(parity_line)}")
         del out0
 
-    runner = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, n_streams=args.streams)
-    config["launch"] = ("eager" if args.no_graphs else "one CUDA graph per resident episode") + \
-        f", episodes round-robin on {max(1, args.streams)} stream(s)"
+    runner = EpisodeRunner(rpn, head, call_eps, use_graphs=not args.no_graphs, n_streams=min(args.streams, n_calls))
+    config["images_per_call"] = B_call
+    config["launch"] = (f"{n_calls} call(s) of {B_call} query image(s) each (the reference's image batch: main.py:492-499 sets 12 for 1-way 1-shot), " +
+                        ("eager" if args.no_graphs else "one CUDA graph per call") +
+                        f", calls round-robin on {max(1, min(args.streams, n_calls))} stream(s)")
     W5 = 5 * cfg.n_ways + 1
     gath = ResultGatherer((E, rois_per_episode, W5), device) if world > 1 else None
     res_single = torch.empty((E, rois_per_episode, W5), device=device)
     state = {"k": 0, "buf": res_single}
 
-    def sink(i, o):
-        buf = state["buf"]
-        buf[i, :, : cfg.n_ways + 1].copy_(o["cls_score"])
-        buf[i, :, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+    def sink(j, o):                                      # call j = episodes [j*B_call, (j+1)*B_call) of the block
+        rows = state["buf"][j * B_call:(j + 1) * B_call].view(B_call * rois_per_episode, W5)
+        rows[:, : cfg.n_ways + 1].copy_(o["cls_score"])
+        rows[:, cfg.n_ways + 1:].copy_(o["bbox_pred"])
 
     def run_block(n_eps, buf):
         state["buf"] = buf
         runner.begin()
-        for i in range(n_eps):
-            runner.run(i, sink)
+        for j in range(n_eps // B_call):
+            runner.run(j, sink)
         runner.end()
 
     def step_resident():
@@ -369,7 +383,7 @@ def main():
 
     # ---- strong scaling: the SAME total of E episodes per step split over the ranks (E/world each)
     strong = None
-    if world > 1 and E % world == 0:
+    if world > 1 and E % world == 0 and (E // world) % B_call == 0:
         e_loc = E // world
         g_strong = ResultGatherer((e_loc, rois_per_episode, W5), device)
         st = {"k": 0}
@@ -475,10 +489,11 @@ def main():
 
     # ---- rooflines.  (1) the dominant kernel: multi-level RoIAlign, timed alone on its stream
     scales = [1.0 / s for s in cfg.strides]
-    alg_bytes = roi_align_algorithmic_bytes(cfg, host_eps[0]["rois"])
+    alg_bytes_call = roi_align_algorithmic_bytes(call_eps[0]["cfg"], call_eps[0]["rois"].cpu())   # one launch = one call's RoIs
+    alg_bytes = alg_bytes_call / B_call                                                            # per episode
 
     def roi_only():
-        for ep in dev_eps:
+        for ep in call_eps:
             ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], scales, 7, 0, True, out_format="nhwc")
 
     # the E launches (one per resident episode, 16 x 92 MB of distinct maps) are replayed as one CUDA graph so
@@ -490,7 +505,7 @@ def main():
         with torch.cuda.graph(roi_graph):
             roi_only()
     ms_roi, l_roi, _ = timed(roi_graph.replay, max(args.steps, 10), args.warmup)
-    per_launch_s = ms_roi * 1e-3 / (max(args.steps, 10) * E)
+    per_launch_s = ms_roi * 1e-3 / (max(args.steps, 10) * n_calls)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -498,7 +513,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    achieved = alg_bytes / per_launch_s / 1e9
+    achieved = alg_bytes_call / per_launch_s / 1e9
 
     def committed(name):
         """Per-launch figures of a committed ncu --set full capture (tools/ncu_summary.py --json)."""
@@ -507,15 +522,61 @@ def main():
         except Exception:
             return None
 
-    ncu_roi = committed("r02_ncu_roi_align_window.json") if cfg.name == WORKLOAD else None
+    ncu_roi = (committed("r02_ncu_roi_align_window_b12.json" if B_call == 12 else "r02_ncu_roi_align_window.json" if B_call == 1 else "none")
+               if cfg.name == WORKLOAD else None)
     roofline = {"kernel": "roi_align_window_kernel<7,2,3,2> (level assignment + multi-level RoIAlign, NHWC in/out)", "bound": "hbm",
+                "rois_per_launch": B_call * rois_per_episode, "images_per_launch": B_call,
+                "us_per_1000_rois": per_launch_s * 1e6 / (B_call * rois_per_episode / 1000.0),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6,
+                "algorithmic_bytes_per_launch": alg_bytes_call, "us_per_launch": per_launch_s * 1e6,
                 "traffic": (ncu_roi or {}).get("traffic"),
-                "traffic_source": "profiles/r02_ncu_roi_align_window.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)" if ncu_roi else None}
+                "traffic_source": (("profiles/" + ncu_roi.get("file", "r02_ncu_roi_align_window.json") +
+                                    " (dram__bytes_read.sum + dram__bytes_write.sum per launch)") if ncu_roi else None)}
+
+    # (1b) the same kernel on a large launch: cfg5's 16 images x 512 proposals in one call (8192 RoIs).  The fraction at the
+    #      benchmark workload (1000 RoIs per launch, every cell re-read ~4.5x through L2) is bound by load balance and by what
+    #      the L2 delivers; with 28 instead of 5 items per CTA and half the re-read factor the unchanged kernel sits at the HBM
+    #      roofline.  Device-generated maps (the values are irrelevant to the timing; parity at this size: tests/).
+    roofline_large = None
+    if world == 1 and cfg.name == WORKLOAD and not args.no_large_launch:
+        from fgn_b200.episodes import CONFIGS as _CFGS, level_hw as _lhw, synth_rois as _srois
+        c5 = _CFGS["cfg5_coco2voc_mask_fpn"]
+        g5 = torch.Generator().manual_seed(555)
+        sets = []
+        for i in range(2):                                                       # 2 x 1.46 GB of distinct maps >> L2
+            feats = [torch.randn(c5.batch, *_lhw(c5.img_h, c5.img_w, s_), c5.channels, device=device).permute(0, 3, 1, 2)
+                     for s_ in c5.strides]
+            sets.append((feats, _srois(g5, c5.num_rois * c5.batch, c5.img_h, c5.img_w, c5.batch)))
+        alg5 = roi_align_algorithmic_bytes(c5, sets[0][1])
+        sets = [(f, r.to(device)) for f, r in sets]
+        sc5 = [1.0 / s_ for s_ in c5.strides]
+
+        def roi_large():
+            for f, r in sets:
+                ops.roi_align_multilevel(f, r, sc5, 7, 0, True, out_format="nhwc")
+
+        with torch.no_grad():
+            roi_large()
+            torch.cuda.synchronize()
+            g_large = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_large):
+                roi_large()
+        ms_l, _, _ = timed(g_large.replay, 10, 3)
+        t5 = ms_l * 1e-3 / (10 * len(sets))
+        ncu5 = committed("r02_ncu_roi_align_window_cfg5.json") or {}
+        roofline_large = {"kernel": "roi_align_window_kernel<7,2,3,2> (the same kernel, unchanged)",
+                          "workload": "cfg5_coco2voc_mask_fpn: 16 images x 512 proposals = 8192 RoIs in one launch",
+                          "bound": "hbm", "us_per_launch": t5 * 1e6, "us_per_1000_rois": t5 * 1e6 / (c5.num_rois * c5.batch / 1000.0),
+                          "algorithmic_bytes_per_launch": alg5, "achieved": alg5 / t5 / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": alg5 / t5 / 1e9 / peak, "peak_source": peak_src,
+                          "traffic": ncu5.get("traffic"),
+                          "frac_of_peak_by_measured_traffic": (ncu5["traffic"] / t5 / 1e9 / peak) if ncu5.get("traffic") else None,
+                          "traffic_source": "profiles/r02_ncu_roi_align_window_cfg5.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch)" if ncu5 else None}
+        del sets, g_large
+        torch.cuda.empty_cache()
 
     # (2) the tensor-bound kernel: the relation head's contraction (split-weight count: (R + B*N) * 49 * C * C * 2 FLOP)
-    M_q = rois_per_episode * 49
+    M_q = B_call * rois_per_episode * 49
     a_q = [torch.randn(M_q, cfg.channels, device=device) for _ in range(4)]
     w_q = head.cls_reg_shared_conv.weight.detach().reshape(cfg.channels, 2 * cfg.channels)[:, : cfg.channels]
 
@@ -568,23 +629,23 @@ def main():
     bf16_line = None
     if not args.no_bf16:
         eps16 = []
-        for ep in dev_eps:
+        for ep in call_eps:
             e16 = dict(ep)
             e16["qry"] = [q.bfloat16().contiguous(memory_format=torch.channels_last) for q in ep["qry"]]
             e16["spp"] = [q.bfloat16().contiguous(memory_format=torch.channels_last) for q in ep["spp"]]
             eps16.append(e16)
-        runner16 = EpisodeRunner(rpn, head, eps16, use_graphs=not args.no_graphs, n_streams=args.streams)
+        runner16 = EpisodeRunner(rpn, head, eps16, use_graphs=not args.no_graphs, n_streams=min(args.streams, n_calls))
 
         def step16():
             runner16.begin()
-            for i in range(E):
+            for i in range(n_calls):
                 runner16.run(i)
             runner16.end()
 
         ms16, _, _ = timed(step16, args.steps, args.warmup)
         with torch.no_grad():
             a = run_guided_path(rpn, head, eps16[0])["cls_score"]
-            b = run_guided_path(rpn, head, dev_eps[0])["cls_score"]
+            b = run_guided_path(rpn, head, call_eps[0])["cls_score"]
         bf16_line = {"value": E * world * args.steps * rois_per_episode / (ms16 * 1e-3), "unit": "RoIs/s",
                      "ms_per_step": ms16 / args.steps, "max_abs_logit_diff_vs_fp32": float((a - b).abs().max()),
                      "stated_tolerance": 3e-2, "dtype": "bf16 maps/operands, f32 accumulate"}
@@ -595,12 +656,13 @@ def main():
     #      writing the attended pyramid (the reference's order, which `value` keeps); everything else identical
     fold_line = None
     if not args.no_fold:
-        runner_f = EpisodeRunner(rpn, head, dev_eps, use_graphs=not args.no_graphs, with_attention="fold", n_streams=args.streams)
+        runner_f = EpisodeRunner(rpn, head, call_eps, use_graphs=not args.no_graphs, with_attention="fold",
+                                 n_streams=min(args.streams, n_calls))
 
         def step_fold():
             state["buf"] = res_single
             runner_f.begin()
-            for i in range(E):
+            for i in range(n_calls):
                 runner_f.run(i, sink)
             runner_f.end()
 
@@ -617,8 +679,9 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "parity": parity_line,
                 "e2e": e2e, "gpu_launches": int(launches),
-                "launches_per_episode": (runner.launches_per_episode[0] if runner.launches_per_episode else None),
-                "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_step": roofline_step,
+                "launches_per_call": (runner.launches_per_episode[0] if runner.launches_per_episode else None),
+                "launches_per_episode": (runner.launches_per_episode[0] / B_call if runner.launches_per_episode else None),
+                "roofline": roofline, "roofline_large_launch": roofline_large, "roofline_tensor": roofline_tensor, "roofline_step": roofline_step,
                 "sustained": sustained, "strong_scaling": strong, "gather_overhead_w1": gather_w1,
                 "collective": (None if world == 1 else "all_gather_into_tensor of [E,R,5N+1] per step on a side stream, double-buffered, overlapped with the next step"),
                 "bf16_variant": bf16_line, "folded_attention_variant": fold_line,

@@ -126,6 +126,37 @@ def episode_to_device(ep: Dict[str, object], device, channels_last: bool = True,
     return out
 
 
+def batch_episodes(eps: Sequence[Dict[str, object]]) -> Dict[str, object]:
+    """Several episodes as ONE call, the way the reference batches them (B query images with their own N x K supports per
+    step: main.py:492-499, B in {8, 10, 12}): maps concatenated along the image axis (channels_last kept), support sets in
+    image order, the image index written into column 0 of the RoIs (bbox2roi's layout).  Per-image results are rows
+    [i*R, (i+1)*R) of the call's outputs; per-RoI arithmetic does not depend on the batching."""
+    import dataclasses
+    cfg0: EpisodeConfig = eps[0]["cfg"]
+    b = sum(e["cfg"].batch for e in eps)
+
+    def cat_maps(key):
+        out = []
+        for l in range(len(eps[0][key])):
+            t = torch.cat([e[key][l] for e in eps], 0)
+            out.append(t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t)
+        return out
+
+    def cat_rois(key):
+        parts, off = [], 0
+        for e in eps:
+            r = e[key].clone()
+            r[:, 0] += off
+            off += e["cfg"].batch
+            parts.append(r)
+        return torch.cat(parts, 0)
+
+    return dict(cfg=dataclasses.replace(cfg0, batch=b), qry=cat_maps("qry"), spp=cat_maps("spp"),
+                spp_bboxes=torch.cat([e["spp_bboxes"] for e in eps], 0), spp_masks=torch.cat([e["spp_masks"] for e in eps], 0),
+                rois=cat_rois("rois"), det_rois=cat_rois("det_rois"), det_labels=torch.cat([e["det_labels"] for e in eps], 0),
+                det_labels_list=[t for e in eps for t in e["det_labels_list"]])
+
+
 def make_weights(channels: int, seed: int = 0) -> Dict[str, torch.Tensor]:
     """Relation-head parameters: Kaiming-normal conv (fgn_roi_head.py:247), Xavier-normal FCs,
     GN affine perturbed around (1,0) so the affine path is exercised."""

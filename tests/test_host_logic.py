@@ -222,3 +222,26 @@ def test_count_spp_class_term_is_bound_to_its_class_maps_and_weights():
     assert head._valid_class_term(params) is None
     head._class_term = None
     assert head._valid_class_term(params) is None
+
+
+def test_batch_episodes_is_the_references_image_batch():
+    """episodes.batch_episodes: B episodes as one call -- maps concatenated along the image axis, support sets in image
+    order, the image index in column 0 of the RoIs (bbox2roi's layout), per-image labels kept as a list."""
+    import torch
+    from fgn_b200.episodes import CONFIGS, batch_episodes, make_episode
+    cfg = CONFIGS["tiny_fpn"]
+    eps = [make_episode(cfg, seed=i) for i in range(3)]
+    b = batch_episodes(eps)
+    m = cfg.n_ways * cfg.k_shots
+    assert b["cfg"].batch == 3 and b["cfg"].num_rois == cfg.num_rois
+    assert b["qry"][0].shape[0] == 3 and b["spp"][0].shape[0] == 3 * m
+    assert b["qry"][0].is_contiguous(memory_format=torch.channels_last)
+    assert tuple(b["spp_bboxes"].shape) == (3 * m, 1, 4) and b["spp_masks"].shape[0] == 3 * m
+    r = cfg.num_rois
+    for i in range(3):
+        assert torch.equal(b["qry"][1][i], eps[i]["qry"][1][0])
+        assert torch.equal(b["spp"][0][i * m:(i + 1) * m], eps[i]["spp"][0])
+        rows = b["rois"][i * r:(i + 1) * r]
+        assert bool((rows[:, 0] == i).all()) and torch.equal(rows[:, 1:], eps[i]["rois"][:, 1:])
+        assert torch.equal(b["det_labels_list"][i], eps[i]["det_labels_list"][0])
+    assert bool((eps[1]["rois"][:, 0] == 0).all())                        # the inputs are left alone
