@@ -227,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp >= 8) {
-        // ===== operand splitters: landed fp32 A tile -> A_hi in place, A_lo beside it =====
+        // ===== operand splitters: landed fp32 A tile -> A_lo beside it (A_hi = A as loaded) =====
         if (PASSES == 3) {
             const int tid = threadIdx.x - 256;
             int it = 0;
@@ -246,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
                         h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
                         h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-                        hi[i] = h;
+                        // (A itself serves as A_hi: the MMA truncates its operands to TF32, see the pair kernel)
                         lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -422,7 +422,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp >= 8 && warp < 12) {
-        // ===== operand splitters (both CTAs): own A tile -> A_hi in place, A_lo; arrive on rank 0's barrier =====
+        // ===== operand splitters (both CTAs): own A tile -> A_lo (A_hi = A as loaded); arrive on rank 0's barrier =====
         if (PASSES == 3) {
             const int tid = threadIdx.x - 256;
             int it = 0;
@@ -442,7 +442,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
                         h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
                         h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-                        hi[i] = h;
+                        // (A itself serves as A_hi: kind::tf32 reads the top 19 bits of an fp32 operand -- clearing the low 13
+                        //  here changed no result bit and cost 8 KB of shared-memory writes per k-block)
                         lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
