@@ -383,20 +383,39 @@ def main():
 
     # ---- strong scaling: the SAME total of E episodes per step split over the ranks (E/world each)
     strong = None
-    if world > 1 and E % world == 0 and (E // world) % B_call == 0:
+    if world > 1 and E % world == 0:
         e_loc = E // world
         g_strong = ResultGatherer((e_loc, rois_per_episode, W5), device)
         st = {"k": 0}
+        if e_loc % B_call == 0:
+            run_strong = lambda buf: run_block(e_loc, buf)
+            b_strong = B_call
+        else:   # this rank's share is not a whole number of B_call-image calls: its own calls of gcd(share, B_call) images
+            import math as _m
+            b_strong = _m.gcd(e_loc, B_call)
+            eps_s = [batch_episodes(dev_eps[j * b_strong:(j + 1) * b_strong]) if b_strong > 1 else dev_eps[j]
+                     for j in range(e_loc // b_strong)]
+            runner_s = EpisodeRunner(rpn, head, eps_s, use_graphs=not args.no_graphs, n_streams=min(args.streams, len(eps_s)))
+
+            def run_strong(buf):
+                def sink_s(j, o):
+                    rows = buf[j * b_strong:(j + 1) * b_strong].view(b_strong * rois_per_episode, W5)
+                    rows[:, : cfg.n_ways + 1].copy_(o["cls_score"])
+                    rows[:, cfg.n_ways + 1:].copy_(o["bbox_pred"])
+                runner_s.begin()
+                for j in range(len(eps_s)):
+                    runner_s.run(j, sink_s)
+                runner_s.end()
 
         def step_strong():
             k = st["k"]
-            run_block(e_loc, g_strong.local(k))
+            run_strong(g_strong.local(k))
             g_strong.submit(k)
             st["k"] = k + 1
 
         ms_st, _, _ = timed(step_strong, args.steps, args.warmup, after=g_strong.drain)
         g_strong.drain()
-        strong = {"total_episodes_per_step": E, "episodes_per_gpu_per_step": e_loc,
+        strong = {"total_episodes_per_step": E, "episodes_per_gpu_per_step": e_loc, "images_per_call": b_strong,
                   "value": E * args.steps * rois_per_episode / (ms_st * 1e-3), "unit": "RoIs/s",
                   "ms_per_step": ms_st / args.steps,
                   "note": "same total work at every N; efficiency = value(N) / (N * value(1) of this key's N=1 run = the headline value at N=1)"}
