@@ -464,11 +464,50 @@ def main():
         return sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
                    for k, v in ep.items() if isinstance(v, list) or torch.is_tensor(v))
 
+    # One staging buffer per episode: every input tensor of an episode at a 256-byte aligned offset of ONE pinned allocation, so
+    # an episode crosses PCIe as one copy (14 separate copies of 0.3 KB .. 69 MB leave ~5 % of the link idle between them) into
+    # a per-stream device slot that is reused (no allocator work inside the timed region); the tensors are views of the slot.
+    class PackedEpisode:
+        def __init__(self, ep):
+            self.meta, off = [], 0
+            for k, v in ep.items():
+                for j, t in enumerate(v if isinstance(v, list) else [v]):
+                    if torch.is_tensor(t):
+                        t = t.contiguous(memory_format=torch.channels_last) if (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+                                                                                  and not t.is_contiguous()) else t.contiguous()
+                        cl = t.dim() == 4 and not t.is_contiguous()
+                        src = t.permute(0, 2, 3, 1) if cl else t
+                        nbytes = src.numel() * src.element_size()
+                        self.meta.append((k, isinstance(v, list), j, off, nbytes, src.dtype, tuple(src.shape), cl, src))
+                        off = (off + nbytes + 255) & ~255
+            self.nbytes = off
+            self.host = torch.empty(off, dtype=torch.uint8).pin_memory()
+            for (_, _, _, o, nb, dt, shp, _, src) in self.meta:
+                self.host[o:o + nb].view(dt).view(shp).copy_(src)
+            self.meta = [m[:8] for m in self.meta]
+            self.rest = {k: v for k, v in ep.items() if not (torch.is_tensor(v) or (isinstance(v, list) and v and torch.is_tensor(v[0])))}
+            self.label_lens = [int(t.numel()) for t in ep["det_labels_list"]] if "det_labels_list" in ep else None
+
+        def to_device(self, slot):
+            slot[: self.nbytes].copy_(self.host, non_blocking=True)                      # ONE H2D copy
+            out = dict(self.rest)
+            for (k, is_list, j, o, nb, dt, shp, cl) in self.meta:
+                t = slot[o:o + nb].view(dt).view(shp)
+                t = t.permute(0, 3, 1, 2) if cl else t
+                if is_list:
+                    out.setdefault(k, []).append(t)
+                else:
+                    out[k] = t
+            return out
+
     out_host = torch.empty((E, rois_per_episode, W5), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
     e2e_streams = [torch.cuda.Stream() for _ in range(max(1, args.e2e_streams))]   # copies of episode i+1 overlap compute of episode i
 
     def make_e2e_step(pinned, channels_last):
+        packed = [PackedEpisode(ep) for ep in pinned]
+        slots = [torch.empty(max(p.nbytes for p in packed), dtype=torch.uint8, device=device) for _ in e2e_streams]
+
         def step_e2e():
             main = torch.cuda.current_stream()
             fork = torch.cuda.Event()
@@ -477,7 +516,7 @@ def main():
                 st_ = e2e_streams[i % len(e2e_streams)]
                 st_.wait_event(fork)
                 with torch.cuda.stream(st_):
-                    ep = episode_to_device(pinned[i % len(pinned)], device, channels_last=channels_last)   # H2D
+                    ep = packed[i % len(packed)].to_device(slots[i % len(e2e_streams)])                    # H2D (one copy)
                     o = run_guided_path(rpn, head, ep)                                                  # repack + path
                     out_host[i].copy_(torch.cat([o["cls_score"], o["bbox_pred"]], 1), non_blocking=True)
             for st_ in e2e_streams:
@@ -490,7 +529,17 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     pinned32 = [pin(ep) for ep in host_eps]
     h2d = bytes_of(pinned32[0]) * E
-    ms_e2e, _, _ = timed(make_e2e_step(pinned32, False), e2e_steps, 1)
+    step32 = make_e2e_step(pinned32, False)
+    ms_e2e, _, _ = timed(step32, e2e_steps, 1)
+    # what came back over PCIe is what the resident step computes for the same episodes, bit for bit
+    if gath is None:
+        with torch.no_grad():
+            run_block(E, res_single)
+            step32()
+            torch.cuda.synchronize()
+        for i in range(min(len(pinned32), E)):
+            if not torch.equal(out_host[i], res_single[i].cpu()):
+                raise SystemExit(f"bench.py: end-to-end results of episode {i} differ from the resident step's")
     e2e_value = E * world * e2e_steps * rois_per_episode / (ms_e2e * 1e-3)
     e2e = {"value": e2e_value, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "host_layout": "NCHW fp32 pinned",
