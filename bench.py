@@ -574,6 +574,23 @@ def main():
             roi_only()
     ms_roi, l_roi, _ = timed(roi_graph.replay, max(args.steps, 10), args.warmup)
     per_launch_s = ms_roi * 1e-3 / (max(args.steps, 10) * n_calls)
+    # for the record, the same kernel on single-image launches (1000 RoIs: what rounds 1 and early 2 measured)
+    single = None
+    if B_call > 1:
+        def roi_single():
+            for ep in dev_eps[:8]:
+                ops.roi_align_multilevel(ep["qry"][:n_ext], ep["rois"], scales, 7, 0, True, out_format="nhwc")
+        with torch.no_grad():
+            roi_single()
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                roi_single()
+        ms_1, _, _ = timed(g1.replay, 10, 3)
+        t1 = ms_1 * 1e-3 / (10 * min(8, len(dev_eps)))
+        single = {"rois_per_launch": rois_per_episode, "us_per_launch": t1 * 1e6,
+                  "algorithmic_bytes_per_launch": roi_align_algorithmic_bytes(cfg, host_eps[0]["rois"])}
+        del g1
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -597,6 +614,9 @@ def main():
                 "us_per_1000_rois": per_launch_s * 1e6 / (B_call * rois_per_episode / 1000.0),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_call, "us_per_launch": per_launch_s * 1e6,
+                "single_image_launch": (dict(single, frac=single["algorithmic_bytes_per_launch"] / (single["us_per_launch"] * 1e-6) / 1e9 / peak,
+                                             note="one image, 1000 RoIs per launch: bound by load balance across the persistent CTAs (DESIGN.md section 7)")
+                                        if single else None),
                 "traffic": (ncu_roi or {}).get("traffic"),
                 "traffic_source": (("profiles/" + ncu_roi.get("file", "r02_ncu_roi_align_window.json") +
                                     " (dram__bytes_read.sum + dram__bytes_write.sum per launch)") if ncu_roi else None)}
