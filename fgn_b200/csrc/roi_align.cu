@@ -214,6 +214,10 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
                             int aligned, float finest_scale, const float *chan_scale,
                             const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
                             int ns_pref, bool *taken);
+int launch_roi_align_window_bf16(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                                 int aligned, float finest_scale, const float *chan_scale,
+                                 const int32_t *scale_index, void *out, int out_is_bf16, int32_t *lvl_out,
+                                 cudaStream_t st, int ns_pref, bool *taken);
 unsigned int roi_align_window_violations();
 void roi_align_window_trace(unsigned long long *dst, int n);
 
@@ -359,6 +363,15 @@ extern "C" int fgn_roi_align_ml_fwd_bf16(const fgn_pyramid_t *pyr, int B, int C,
     FGN_CHECK_ARG(rois && out, "NULL pointer");
     for (int l = 0; l < pyr->num_levels; ++l) FGN_CHECK_ARG(pyr->feat[l], "level %d pointer is NULL", l);
     const Pyramid d = to_device_pyramid(pyr, B);
+    // the rotating-window kernel with half-width cells; a handful of RoIs (the support branch) and the shapes it
+    // declines stay on the one-CTA-per-RoI kernel (FGN_RA_IMPL=2 forces that one)
+    if (env_int("FGN_RA_IMPL", 4) >= 4 && R > env_int("FGN_RA_SMALL", 16)) {
+        bool taken = false;
+        rc = launch_roi_align_window_bf16(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
+                                          scale_index, out, out_is_bf16, lvl_out, (cudaStream_t)stream,
+                                          env_int("FGN_RA_NS", 0), &taken);
+        if (rc || taken) return rc;
+    }
     return launch_roi_align_stream_bf16(d, C, P, rois, R, sampling_ratio, aligned, finest_scale, chan_scale,
                                         scale_index, out, out_is_bf16, lvl_out, (cudaStream_t)stream);
 }

@@ -31,6 +31,8 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <atomic>
+#include <type_traits>
+#include <cuda_bf16.h>
 
 namespace fgn {
 
@@ -157,14 +159,34 @@ __device__ __forceinline__ void trace(int debug_mode, int item, int ev, int lane
 
 }  // namespace
 
+// bf16 cells -> fp32 (exact: a bf16 is the upper half of an fp32); half 0 = channels 0..3 of the lane's 8, half 1 = 4..7
+__device__ __forceinline__ float4 bf16x4_lo(const uint4 q)
+{
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                       __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 bf16x4_hi(const uint4 q)
+{
+    return make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
+                       __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+}
+__device__ __forceinline__ float4 bf16x4(const uint2 q)
+{
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                       __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+}
+
 // Warps: 0..P-1 consumers (warp = bin column), P = producer, P+1 = planner.
-// Dynamic shared memory: ring[NS][kStageCells*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
-template <int P, int VEC, int NS, int MINB, bool SCALED>
+// Dynamic shared memory: ring[NS][SC*CB] | kPlanSlots x { wx[wx_cap] | wrow[wyd_rows] float4 }
+// H16: the pyramid holds bf16 (NHWC, uint16 storage): a cell moves half the bytes, a stage holds twice the cells, a lane
+// owns 8 contiguous channels (one 128-bit LDS per cell); weights, accumulation and scaling stay fp32.  O16: bf16 output
+// (round to nearest even), H16 kernels only.
+template <int P, int VEC, int NS, int MINB, bool SCALED, bool H16 = false, bool O16 = false>
 __global__ void __launch_bounds__((P + 2) * 32, MINB)
 roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict__ rois, const int R,
                         const int sampling_ratio, const int aligned, const float finest_scale,
                         const float *__restrict__ chan_scale, const int32_t *__restrict__ scale_index,
-                        float *__restrict__ out, int32_t *__restrict__ lvl_out,
+                        void *__restrict__ out_v, int32_t *__restrict__ lvl_out,
                         const int wx_cap, const int wyd_rows, const int ticket_slot, const float split_cells,
                         const float3 thr, const int debug_mode)
 {
@@ -172,7 +194,13 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     // bit 5 = record the per-CTA timeline
     constexpr int CB = 128 * VEC;                   // channels per item; cell stride in the ring
     constexpr int S  = (P + kWin - 1) / kWin;       // bin-row chunks of a split RoI
-    constexpr int kStageFloats = kStageCells * CB;
+    static_assert(!H16 || VEC == 2, "bf16 cells: a lane owns 8 channels of a 256-channel block");
+    static_assert(!O16 || H16, "bf16 output comes with bf16 input");
+    typedef typename std::conditional<H16, unsigned short, float>::type in_t;
+    constexpr int ES = (int)sizeof(in_t);
+    constexpr int SC = kStageCells * (4 / ES);      // cells per ring stage (a stage is 32 fp32 cells' worth of bytes)
+    constexpr int kStageFloats = SC * CB;           // elements per stage
+    constexpr int V1 = H16 ? 4 : 128;               // channel offset of a lane's second float4
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ WinSlot<P> slot[kPlanSlots];
@@ -181,8 +209,8 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                    *const plan_empty = bars + 2 * NS + kPlanSlots;
     __shared__ unsigned int cls_mask[4][kSortCap / 32];   // size-class membership of every RoI (sorted ticket scheme)
 
-    float *ring = reinterpret_cast<float *>(smem_raw);
-    float *wtab = ring + (size_t)NS * kStageFloats;
+    in_t *ring = reinterpret_cast<in_t *>(smem_raw);
+    float *wtab = reinterpret_cast<float *>(smem_raw + (size_t)NS * kStageFloats * ES);
     const int wslot = wx_cap + 4 * wyd_rows;        // floats per plan slot
     // one opaque register holds the barriers' shared address: left to itself ptxas re-derives it before every wait
     // (S2UR SR_CgaCtaId + ULEA, ~40 cycles of latency per ring stage)
@@ -385,10 +413,10 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             if (X1 < 0 || Y1 < 0 || xsum + 8 > wx_cap || (Y1 - Y0) > wyd_rows) { X0 = X1 = Y0 = Y1 = 0; n = 0; }
             const int ncols = X1 - X0, nrows = Y1 - Y0;
             int nseg, rps, nstages;
-            if (ncols <= kStageCells) {
-                nseg = 1; rps = ncols > 0 ? kStageCells / ncols : 1; nstages = (nrows + rps - 1) / rps;
+            if (ncols <= SC) {
+                nseg = 1; rps = ncols > 0 ? min(32, SC / ncols) : 1; nstages = (nrows + rps - 1) / rps;   // a producer lane per row
             } else {
-                nseg = (ncols + kStageCells - 1) / kStageCells; rps = 1; nstages = nrows * nseg;
+                nseg = (ncols + SC - 1) / SC; rps = 1; nstages = nrows * nseg;
             }
             if (ncols == 0 || nrows == 0) nstages = 0;
             int off = 0;                                                 // exclusive scan of the padded x runs
@@ -465,8 +493,8 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             const int cbn = min(CB, C - ps.cb0);
             const bool rowcopy = (C == CB);                              // a row segment is one contiguous run
             const int nrows = ps.nrows, ncols = ps.ncols, nstages = ps.nstages, rps = ps.rps, nseg = ps.nseg;
-            const float *fbase = pyr.feat[ps.level] + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
-                                 + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
+            const in_t *fbase = reinterpret_cast<const in_t *>(pyr.feat[ps.level]) + ((size_t)ps.batch * ps.H * ps.W) * C + ps.cb0
+                                + ((size_t)ps.Y0 * ps.W + ps.X0) * C;
             const size_t row_pitch = (size_t)ps.W * C;
             __syncwarp();
             if (lane == 0) mbar_arrive32(pempty32 + 8 * b);              // everything needed is in registers now
@@ -477,8 +505,8 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 // is rps whole rows; lane i owns row i of every stage, so its source and destination only advance
                 // by constants.  (No ordering is needed between lane 0's expect_tx and the other lanes' copies:
                 // the phase cannot complete before the expect_tx arrival.)
-                const uint32_t row_bytes = (uint32_t)ncols * (CB * 4);
-                const float *src = fbase + (size_t)lane * row_pitch;
+                const uint32_t row_bytes = (uint32_t)ncols * (CB * ES);
+                const in_t *src = fbase + (size_t)lane * row_pitch;
                 const size_t src_step = (size_t)rps * row_pitch;
                 const uint32_t dst_lane = ring32 + (uint32_t)lane * row_bytes;
                 int rows_left = nrows;
@@ -488,7 +516,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     mbar_wait32(empty32 + 8 * s, par);
                     const uint32_t fb = full32 + 8 * s;
                     if (lane == 0) mbar_expect_tx32(fb, (uint32_t)nr * row_bytes);
-                    if (lane < nr) bulk_g2s32(dst_lane + (uint32_t)s * (kStageFloats * 4), src, row_bytes, fb);
+                    if (lane < nr) bulk_g2s32(dst_lane + (uint32_t)s * (kStageFloats * ES), src, row_bytes, fb);
                     src += src_step;
                     if (++s == NS) { s = 0; par ^= 1; }
                 }
@@ -499,24 +527,24 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             for (int st = 0; st < nstages; ++st) {
                 int nr, nc;
                 if (nseg == 1) { nr = min(rps, nrows - row0); nc = ncols; }
-                else           { nr = 1; nc = min(kStageCells, ncols - col0); }
+                else           { nr = 1; nc = min(SC, ncols - col0); }
                 mbar_wait32(empty32 + 8 * s, par);
-                const uint32_t dst = ring32 + (uint32_t)s * (kStageFloats * 4), fb = full32 + 8 * s;
+                const uint32_t dst = ring32 + (uint32_t)s * (kStageFloats * ES), fb = full32 + 8 * s;
                 if (debug_mode & 1) {
                     if (lane == 0) mbar_arrive32(fb);
                 } else {
-                    if (lane == 0) mbar_expect_tx32(fb, (uint32_t)(nr * nc * cbn * 4));
+                    if (lane == 0) mbar_expect_tx32(fb, (uint32_t)(nr * nc * cbn * ES));
                     __syncwarp();
-                    const float *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
+                    const in_t *src = fbase + (size_t)row0 * row_pitch + (size_t)col0 * C;
                     if (rowcopy) {
                         if (lane < nr)
-                            bulk_g2s32(dst + (uint32_t)(lane * nc) * (CB * 4), src + (size_t)lane * row_pitch,
-                                       (uint32_t)(nc * CB * 4), fb);
+                            bulk_g2s32(dst + (uint32_t)(lane * nc) * (CB * ES), src + (size_t)lane * row_pitch,
+                                       (uint32_t)(nc * CB * ES), fb);
                     } else {
                         for (int cell = lane; cell < nr * nc; cell += 32) {
                             const int rr = cell / nc, cc = cell - rr * nc;
-                            bulk_g2s32(dst + (uint32_t)cell * (CB * 4), src + (size_t)rr * row_pitch + (size_t)cc * C,
-                                       (uint32_t)(cbn * 4), fb);
+                            bulk_g2s32(dst + (uint32_t)cell * (CB * ES), src + (size_t)rr * row_pitch + (size_t)cc * C,
+                                       (uint32_t)(cbn * ES), fb);
                         }
                     }
                 }
@@ -529,7 +557,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     } else {
         // ===== consumers: warp = bin column pw ==============================================================
         const int pw = warp;
-        const int lch = lane * 4;                        // lane -> channels [4*lane, 4*lane+4) + 128*v of the block
+        const int lch = H16 ? lane * 8 : lane * 4;       // lane -> channels [4*lane, 4*lane+4) + 128*v of the block (bf16 cells: 8 contiguous)
         int s = 0;
         unsigned par = 0;
         int b = 0;
@@ -560,9 +588,11 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 const int si = scale_index != nullptr ? scale_index[r] : r;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (v * 128 + lch < cbn) cs[v] = ldg4(chan_scale + (size_t)si * C + cb0 + v * 128 + lch);
+                    if (v * V1 + lch < cbn) cs[v] = ldg4(chan_scale + (size_t)si * C + cb0 + v * V1 + lch);
             }
-            float *op = out + ((size_t)(r * P + ps.pa) * P + pw) * C + cb0 + lch;   // output of the window's first bin
+            const size_t o0 = ((size_t)(r * P + ps.pa) * P + pw) * C + cb0 + lch;     // output of the window's first bin
+            float *op = reinterpret_cast<float *>(out_v) + o0;
+            unsigned short *op16 = reinterpret_cast<unsigned short *>(out_v) + o0;
             // the bin column's weights live in registers for the whole item (runs are padded to 4 floats and
             // the table has 8 floats of slack, so reading 8 is always in bounds; entries past nx are unused)
             float wreg[8];
@@ -584,6 +614,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
 
             // store the window's first bin row and slide the window down by one
             auto rotate = [&]() {
+                unsigned o16[2 * VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     const float4 qv = a[0][v];
@@ -594,12 +625,19 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     }
                     else
                         o = make_float4(qv.x * inv, qv.y * inv, qv.z * inv, qv.w * inv);
-                    if (v * 128 + lch < cbn) *reinterpret_cast<float4 *>(op + v * 128) = o;
+                    if (O16) {                          // round to nearest even; the lane's 8 channels leave as one 128-bit store
+                        const __nv_bfloat162 t0 = __floats2bfloat162_rn(o.x, o.y), t1 = __floats2bfloat162_rn(o.z, o.w);
+                        o16[2 * v] = *reinterpret_cast<const unsigned *>(&t0);
+                        o16[2 * v + 1] = *reinterpret_cast<const unsigned *>(&t1);
+                    }
+                    else if (v * V1 + lch < cbn) *reinterpret_cast<float4 *>(op + v * V1) = o;
 #pragma unroll
                     for (int w = 0; w + 1 < kWin; ++w) a[w][v] = a[w + 1][v];
                     a[kWin - 1][v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (O16 && lch < cbn) *reinterpret_cast<uint4 *>(op16) = make_uint4(o16[0], o16[1], o16[2 * VEC - 2], o16[2 * VEC - 1]);
                 op += (size_t)P * C;
+                op16 += (size_t)P * C;
                 --bins_left;
             };
             // the footprint row in racc is complete: fold it into the window
@@ -624,28 +662,44 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     for (int v = 0; v < VEC; ++v) { fma4x2(a[2][v], w4.z, racc[v]); fma4x2(a[3][v], w4.w, racc[v]); }
                 }
             };
-            // cell i of the row at rp: 128-bit LDS at a compile-time offset + packed FMAs (first cell: MUL)
-#define FGN_CELL0()                                                                                          \
-    _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                           \
-        racc[v] = mul4x2(wreg[0], *reinterpret_cast<const float4 *>(rp + v * 128))
-#define FGN_CELL(i)                                                                                          \
-    _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                           \
-        fma4x2(racc[v], wreg[i], *reinterpret_cast<const float4 *>(rp + (i) * CB + v * 128))
-
             // Row pass over whole-row stages, specialised on the number of cells NX of this warp's bin column
             // (constant over the item; NX = 0 is the generic loop): straight-line LDS / packed-FMA code per row.
             auto run_rows = [&](auto nx_tag) {
                 constexpr int NX = decltype(nx_tag)::value;
                 int rows_todo = nrows;
                 const int rstride = ncols * CB;
-                const float *sp = ring + (size_t)s * kStageFloats + xlo * CB + lch;   // this warp's first cell in stage s
+                const in_t *sp = ring + (size_t)s * kStageFloats + xlo * CB + lch;   // this warp's first cell in stage s
                 for (int st = 0; st < nstages; ++st) {
                     const int nr = min(rps, rows_todo);
                     rows_todo -= nr;
                     mbar_wait32(full32 + 8 * s, par);
-                    const float *rp = sp;
+                    const in_t *rp = sp;
                     for (int rr = 0; rr < nr; ++rr, rp += rstride) {
                         if (!(debug_mode & 2)) {
+                            if constexpr (H16) {
+                                if (NX > 0) {
+                                    // all NX 128-bit loads of the row first (8 channels each), then the two packed-FMA chains
+                                    uint4 cell[NX > 0 ? NX : 1];
+#pragma unroll
+                                    for (int i = 0; i < NX; ++i) cell[i] = *reinterpret_cast<const uint4 *>(rp + i * CB);
+                                    racc[0] = mul4x2(wreg[0], bf16x4_lo(cell[0]));
+                                    racc[1] = mul4x2(wreg[0], bf16x4_hi(cell[0]));
+#pragma unroll
+                                    for (int i = 1; i < NX; ++i) {
+                                        fma4x2(racc[0], wreg[i], bf16x4_lo(cell[i]));
+                                        fma4x2(racc[1], wreg[i], bf16x4_hi(cell[i]));
+                                    }
+                                } else {
+                                    racc[0] = make_float4(0.f, 0.f, 0.f, 0.f); racc[1] = racc[0];
+                                    const in_t *cp = rp;
+                                    for (int i = 0; i < nx; ++i, cp += CB) {
+                                        const float w = wxp[i];
+                                        const uint4 q = *reinterpret_cast<const uint4 *>(cp);
+                                        fma4x2(racc[0], w, bf16x4_lo(q));
+                                        fma4x2(racc[1], w, bf16x4_hi(q));
+                                    }
+                                }
+                            } else
                             if (NX > 0) {
                                 // one channel half at a time: all NX loads of the half are issued back to back
                                 // into their own registers, then the packed-FMA chain (first cell: MUL)
@@ -653,7 +707,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                                 for (int v = 0; v < VEC; ++v) {
                                     float4 cell[NX > 0 ? NX : 1];
 #pragma unroll
-                                    for (int i = 0; i < NX; ++i) cell[i] = *reinterpret_cast<const float4 *>(rp + i * CB + v * 128);
+                                    for (int i = 0; i < NX; ++i) cell[i] = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(rp) + i * CB + v * 128);
                                     racc[v] = mul4x2(wreg[0], cell[0]);
 #pragma unroll
                                     for (int i = 1; i < NX; ++i) fma4x2(racc[v], wreg[i], cell[i]);
@@ -661,7 +715,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                             } else {
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) racc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float *cp = rp;
+                                const float *cp = reinterpret_cast<const float *>(rp);
                                 for (int i = 0; i < nx; ++i, cp += CB) {
                                     const float w = wxp[i];
 #pragma unroll
@@ -689,16 +743,22 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                 }
             } else {
                 for (int row = 0; row < nrows; ++row)
-                    for (int col0 = 0; col0 < ncols; col0 += kStageCells) {
-                        const int nc = min(kStageCells, ncols - col0);
+                    for (int col0 = 0; col0 < ncols; col0 += SC) {
+                        const int nc = min(SC, ncols - col0);
                         mbar_wait32(full32 + 8 * s, par);
-                        const float *sb = ring + (size_t)s * kStageFloats + lch;
+                        const in_t *sb = ring + (size_t)s * kStageFloats + lch;
                         const int c_beg = max(xlo, col0), c_end = min(xlo + nx, col0 + nc);
                         for (int cx = c_beg; cx < c_end; ++cx) {
                             const float w = wxp[cx - xlo];
+                            if constexpr (H16) {
+                                const uint4 q = *reinterpret_cast<const uint4 *>(sb + (cx - col0) * CB);
+                                fma4x2(racc[0], w, bf16x4_lo(q));
+                                fma4x2(racc[1], w, bf16x4_hi(q));
+                            } else {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v)
-                                fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(sb + (cx - col0) * CB + v * 128));
+                                for (int v = 0; v < VEC; ++v)
+                                    fma4x2(racc[v], w, *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(sb) + (cx - col0) * CB + v * 128));
+                            }
                         }
                         if (col0 + nc >= ncols) {
                             fold();
@@ -710,8 +770,6 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                         if (++s == NS) { s = 0; par ^= 1; }
                     }
             }
-#undef FGN_CELL0
-#undef FGN_CELL
             if (pw == 0) trace(debug_mode, k, 9, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive32(pempty32 + 8 * b);  // the slot's tables are no longer needed
@@ -722,10 +780,10 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     }
 }
 
-template <int P, int VEC, int NS, int MINB>
+template <int P, int VEC, int NS, int MINB, bool H16 = false>
 static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, int sampling_ratio,
                              int aligned, float finest_scale, const float *chan_scale,
-                             const int32_t *scale_index, float *out, int32_t *lvl_out, cudaStream_t st,
+                             const int32_t *scale_index, void *out, bool out16, int32_t *lvl_out, cudaStream_t st,
                              bool *taken)
 {
     constexpr int CB = 128 * VEC;
@@ -737,8 +795,11 @@ static int launch_window_cfg(const Pyramid &d, int C, const float *rois, int R, 
     const size_t smem = (size_t)NS * kStageCells * CB * 4 + (size_t)kPlanSlots * (wx_cap + 4 * wyd_rows) * 4;
     const size_t smem_cap = MINB == 2 ? 115200 : 230000;           // MINB CTAs (+1 KB reserved each) must fit one SM's 228 KB
     if (smem > smem_cap) { *taken = false; return FGN_OK; }
-    auto kern = chan_scale != nullptr ? roi_align_window_kernel<P, VEC, NS, MINB, true>
-                                      : roi_align_window_kernel<P, VEC, NS, MINB, false>;
+    auto kern = chan_scale != nullptr ? roi_align_window_kernel<P, VEC, NS, MINB, true, H16, false>
+                                      : roi_align_window_kernel<P, VEC, NS, MINB, false, H16, false>;
+    if (H16 && out16)
+        kern = chan_scale != nullptr ? roi_align_window_kernel<P, VEC, NS, MINB, true, H16, H16>
+                                     : roi_align_window_kernel<P, VEC, NS, MINB, false, H16, H16>;
     // cudaFuncSetAttribute applies to the current device only and a process may drive several GPUs: set it on every
     // call (a host-side write) and size the persistent grid for the current device
     FGN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -801,7 +862,7 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
     *taken = false;
     if ((C & 3) != 0) return FGN_OK;
 #define FGN_WIN(PV, VV, NV, MB) launch_window_cfg<PV, VV, NV, MB>(d, C, rois, R, sampling_ratio, aligned, finest_scale, \
-                                                                  chan_scale, scale_index, out, lvl_out, st, taken)
+                                                                  chan_scale, scale_index, out, false, lvl_out, st, taken)
     if (P == 7) {
         if (C > 128) return ns_pref == 2 ? FGN_WIN(7, 2, 2, 2) : FGN_WIN(7, 2, 3, 2);
         return ns_pref == 3 ? FGN_WIN(7, 1, 3, 2) : FGN_WIN(7, 1, 4, 2);
@@ -811,6 +872,23 @@ int launch_roi_align_window(const Pyramid &d, int C, int P, const float *rois, i
         return FGN_WIN(14, 1, 6, 1);
     }
 #undef FGN_WIN
+    return FGN_OK;
+}
+
+// bf16 NHWC pyramid (uint16 storage behind the Pyramid's pointers) -> bf16 or fp32 NHWC RoI features: the same kernel
+// with half-width cells (template H16).  Channel blocks are 256 wide whatever C is; lanes past C idle.
+int launch_roi_align_window_bf16(const Pyramid &d, int C, int P, const float *rois, int R, int sampling_ratio,
+                                 int aligned, float finest_scale, const float *chan_scale,
+                                 const int32_t *scale_index, void *out, int out_is_bf16, int32_t *lvl_out,
+                                 cudaStream_t st, int ns_pref, bool *taken)
+{
+    *taken = false;
+    if ((C & 7) != 0) return FGN_OK;
+#define FGN_WIN16(PV, NV, MB) launch_window_cfg<PV, 2, NV, MB, true>(d, C, rois, R, sampling_ratio, aligned, finest_scale, \
+                                                                     chan_scale, scale_index, out, out_is_bf16 != 0, lvl_out, st, taken)
+    if (P == 7) return ns_pref == 2 ? FGN_WIN16(7, 2, 2) : (ns_pref == 4 ? FGN_WIN16(7, 4, 2) : FGN_WIN16(7, 3, 2));
+    if (P == 14) return ns_pref == 3 ? FGN_WIN16(14, 3, 1) : FGN_WIN16(14, 5, 1);
+#undef FGN_WIN16
     return FGN_OK;
 }
 

@@ -235,6 +235,64 @@ def test_roi_align_window_kernel_chunked_and_ragged(P, C, B, monkeypatch):
     assert _lib.load().fgn_debug_roi_window_violations() == 0
 
 
+@pytest.mark.parametrize("P,C,B", [(7, 256, 2), (14, 256, 1), (7, 64, 1), (7, 512, 1), (7, 328, 1)])
+def test_roi_align_window_kernel_bf16_cells(P, C, B, monkeypatch):
+    """bf16 variant (reported separately): the rotating-window kernel with half-width cells (bf16 NHWC pyramid, bf16 or
+    fp32 out) on the planner-stressing RoIs of the fp32 test, rows wider than a 64-cell stage, channel counts below /
+    above / not a multiple of the 256-channel block, the fused channel attention.  Levels bit-exact; bitwise equal to
+    the one-CTA-per-RoI bf16 kernel where both use the same rounding order (no channel attention); the oracle on the
+    SAME bf16-rounded maps within fp32 summation order (fp32 out) or one bf16 rounding (bf16 out)."""
+    from fgn_b200 import _lib, ops
+    from fgn_b200.episodes import synth_rois
+    g = torch.Generator().manual_seed(900 + P + C)
+    strides = [4, 8, 16, 32]
+    feats = [torch.randn(B, C, 192 // s, 320 // s, generator=g).bfloat16() for s in strides]
+    rois = synth_rois(g, 300, 192, 320, B, smin=4.0)
+    n = rois.shape[0]
+    rois[0, 1:] = torch.tensor([10.2, 11.7, 12.9, 13.1])
+    rois[1, 1:] = torch.tensor([100., 50., 100.5, 120.])
+    rois[2, 1:] = torch.tensor([-40., -40., 30., 20.])
+    rois[3, 1:] = torch.tensor([0., 100., 320., 104.])              # 80 cells wide on level 0: segmented rows
+    rois[4, 1:] = torch.tensor([0., 0., 320., 192.])
+    rois[5, 1:] = torch.tensor([-500., -500., -400., -300.])
+    rois[6, 1:] = torch.tensor([3., 3., 9., 30.])
+    rois[7, 1:] = torch.tensor([60., 60., 60., 60.])
+    for i in range(8, 40):
+        cx, cy = float(torch.rand(1, generator=g)) * 320, float(torch.rand(1, generator=g)) * 192
+        w, h = 1 + 11 * float(torch.rand(1, generator=g)), 1 + 11 * float(torch.rand(1, generator=g))
+        rois[i, 1:] = torch.tensor([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+    vec = torch.randn(5, C, generator=g)
+    idx = torch.randint(0, 5, (n,), generator=g)
+    fr = [f.float().contiguous() for f in feats]                    # the rounded maps, as fp32, for the oracle
+    want, lv = O.single_roi_extractor(fr, rois, strides, P, 0, True, 56.0, "tv")
+    want_s = want * vec[idx][:, :, None, None]
+    fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
+    scales = [1 / s for s in strides]
+    rd = rois.to(dev())
+    sc = dict(chan_scale=vec.to(dev()), scale_index=idx.to(dev()))
+    before = _lib.load().fgn_launch_count()
+    got16, lvl = ops.roi_align_multilevel(fd, rd, scales, P, 0, True, return_levels=True)
+    got32 = ops.roi_align_multilevel(fd, rd, scales, P, 0, True, out_dtype=torch.float32)
+    got16_s = ops.roi_align_multilevel(fd, rd, scales, P, 0, True, **sc)
+    got32_s = ops.roi_align_multilevel(fd, rd, scales, P, 0, True, out_dtype=torch.float32, **sc)
+    assert _lib.load().fgn_launch_count() == before + 4      # one kernel per call
+    assert got16.dtype == torch.bfloat16 and got32.dtype == torch.float32 and torch.equal(lvl.cpu(), lv)
+    close(got32, want, what="bf16 cells, fp32 out vs oracle")
+    close(got32_s, want_s, what="bf16 cells + channel attention, fp32 out vs oracle")
+    close(got16.float(), want, atol=1e-3, rtol=2 ** -8, what="bf16 cells, bf16 out vs oracle")
+    close(got16_s.float(), want_s, atol=1e-3, rtol=2 ** -8, what="bf16 cells + channel attention, bf16 out vs oracle")
+    assert torch.equal(got16, got32.bfloat16()), "bf16 out = round-to-nearest-even of the fp32 out"
+    monkeypatch.setenv("FGN_RA_NS", "2")                      # a shallower ring gives the same answer
+    assert torch.equal(ops.roi_align_multilevel(fd, rd, scales, P, 0, True, out_dtype=torch.float32), got32)
+    monkeypatch.delenv("FGN_RA_NS")
+    monkeypatch.setenv("FGN_RA_IMPL", "2")
+    ref16 = ops.roi_align_multilevel(fd, rd, scales, P, 0, True)
+    ref32 = ops.roi_align_multilevel(fd, rd, scales, P, 0, True, out_dtype=torch.float32)
+    assert torch.equal(got32, ref32) and torch.equal(got16, ref16), "window and streaming bf16 kernels share one summation order"
+    torch.cuda.synchronize()
+    assert _lib.load().fgn_debug_roi_window_violations() == 0
+
+
 def test_roi_align_window_ticket_schemes():
     """The window kernel's two ticket schemes give the same answer: R above its sort capacity (plain tickets in
     index order), R below the number of resident CTAs (every RoI is some CTA's first, ticket-less item), the
