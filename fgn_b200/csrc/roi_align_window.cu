@@ -220,7 +220,6 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     const uint32_t pfull32 = bar32 + 16 * NS, pempty32 = bar32 + 16 * NS + 8 * kPlanSlots;
 
     const int nblk  = (C + CB - 1) / CB;
-    const int items = R * S * nblk;                 // tickets = (RoI, bin-row chunk, channel block); unused chunks are skipped
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
@@ -235,6 +234,13 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
     const bool sorted = (nblk == 1) && (R <= kSortCap) && !(debug_mode & 64);
     const int nstatic = sorted ? min(R, (int)gridDim.x) : 0;             // CTAs past R start on a ticket (small launches)
     const int nsb = (R + 31) >> 5;                                       // 32-RoI blocks
+    // Plain tickets are (RoI, bin-row chunk, channel block), unused chunks skipped, so that different CTAs can take the
+    // chunks of a big RoI and the launch's tail stays short.  A launch with many items per CTA has no tail to balance and
+    // a skipped ticket is a planner round trip (geometry + an exposed atomic, ~2 us of a 7 us plan period at 12 000
+    // RoIs): there a ticket is (RoI, channel block) and the planner walks the chunks of the few RoIs that need them.
+    // (32 items per CTA: cfg5's 8192-RoI launch, 28 per CTA and HBM-bound, still gains 2.6 % from the chunk tickets)
+    const bool roi_tickets = !sorted && (long long)R * nblk >= 32ll * gridDim.x;
+    const int items = roi_tickets ? R * nblk : R * S * nblk;
     auto size_class = [&](const float *roi) {                            // 0 = largest footprints ... 3 = smallest (NaN -> 3)
         const int lv = roi_level(roi, pyr, finest_scale);
         const RoiGeom gg = roi_geometry(roi, pyr.scale[lv], P, sampling_ratio, aligned, pyr.B);
@@ -361,6 +367,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
                     break;
                 }
                 if (sorted) r = lookup((int)ticket, ba, bb);
+                else if (roi_tickets) { cbi = (int)ticket % nblk; r = (int)ticket / nblk; }
                 else {
                     cbi = (int)ticket % nblk; chunk_lo = ((int)ticket / nblk) % S; chunk_hi = chunk_lo + 1;
                     r = (int)ticket / (nblk * S);
@@ -374,7 +381,7 @@ roi_align_window_kernel(const Pyramid pyr, const int C, const float *__restrict_
             // bins shorter than 3/4 cell can put > kWin bin rows on one footprint row: such RoIs are planned
             // as items of kWin bin rows each (plain scheme: big footprints too, to shorten the launch's tail)
             const float est = (g.bin_h * (float)P + 2.f) * (g.bin_w * (float)P + 2.f);
-            const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && est > split_cells));
+            const bool split = S > 1 && (g.bin_h < 0.75f || (!sorted && !roi_tickets && est > split_cells));
             if (!split) { if (chunk_lo > 0) continue; chunk_hi = 1; }
             else if (sorted) chunk_hi = (bb - ba + kWin - 1) / kWin;
             if (lane == 0 && lvl_out != nullptr && cbi == 0 && chunk_lo == 0 && ba == 0) lvl_out[r] = level;

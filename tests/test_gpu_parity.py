@@ -294,8 +294,8 @@ def test_roi_align_window_kernel_bf16_cells(P, C, B, monkeypatch):
 
 
 def test_roi_align_window_ticket_schemes():
-    """The window kernel's two ticket schemes give the same answer: R above its sort capacity (plain tickets in
-    index order), R below the number of resident CTAs (every RoI is some CTA's first, ticket-less item), the
+    """The window kernel's ticket schemes give the same answer: R above its sort capacity (plain tickets in
+    index order: per RoI when a CTA gets many items, per bin-row chunk otherwise), R below the number of resident CTAs (every RoI is some CTA's first, ticket-less item), the
     sorted scheme switched off, and the default -- all bitwise equal to the row-streaming kernel."""
     from fgn_b200 import _lib, ops
     from fgn_b200.episodes import synth_rois
@@ -304,8 +304,8 @@ def test_roi_align_window_ticket_schemes():
     feats = [torch.randn(B, C, 160 // s, 224 // s, generator=g) for s in strides]
     fd = [f.to(dev()).contiguous(memory_format=torch.channels_last) for f in feats]
     scales = [1 / s for s in strides]
-    for R in (2500, 1100, 40):
-        rois = synth_rois(g, R, 160, 224, B, smin=6.0)
+    for R in (10000, 2500, 1100, 40):                          # 10000: one ticket per RoI (many items per CTA)
+        rois = synth_rois(g, R, 160, 224, B, smin=4.0 if R == 10000 else 6.0)
         rd = rois.to(dev())
         got, lvl = ops.roi_align_multilevel(fd, rd, scales, 7, 0, True, out_format="nhwc", return_levels=True)
         assert torch.equal(lvl.cpu(), O.map_roi_levels_c(rois, 4))
