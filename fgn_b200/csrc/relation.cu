@@ -13,12 +13,20 @@
 // registers by relation_epilogue_kernel; the re-assembly to [R,N+1]/[R,4N] rides in the finalize
 // kernel.
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm.cuh"
 
 namespace fgn {
 
 constexpr int kEpiThreads = 256;
 constexpr int kMaxPP = 49;          // epilogue register tile is P*P = 49 (P = 7)
+
+__device__ __forceinline__ float ld_nc_ordered(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 __device__ __forceinline__ float group_sum_shfl(float v, int cg)
 {
@@ -32,11 +40,15 @@ __device__ __forceinline__ float group_sum_shfl(float v, int cg)
 // 2 cls rows and 4 reg rows.
 // FAST: every thread owns a channel (C is a multiple of the block's channel count) and a GroupNorm group lies inside
 // one warp -- the production shapes (C = 256 / 1024, 32 groups); no per-element predication, reductions by shuffle.
-template <int PP, bool FAST>
-__global__ void __launch_bounds__(kEpiThreads, 2)
+// ONE: a single class (N = 1, the headline configuration): the RoI term is added to the class term as it arrives instead
+// of being held across a class loop -- 49 fewer live registers, three CTAs per SM instead of two, i.e. half as many
+// bytes again in flight for a kernel that is one read of the conv output.  Same operations in the same order.
+// (C is a compile-time 256 there: with a run-time row pitch ptxas materialises the 98 load addresses and spills them.)
+template <int PP, bool FAST, bool ONE = false>
+__global__ void __launch_bounds__(kEpiThreads, ONE ? 3 : 2)
 relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__ Ys,
                          const int32_t *__restrict__ roi_batch, const int R, const int B, const int N,
-                         const int C, const int cblk, const int cg, const float eps,
+                         const int C_rt, const int cblk, const int cg, const float eps,
                          const float *__restrict__ gn_w, const float *__restrict__ gn_b,
                          const float *__restrict__ fc_cls_w, const float *__restrict__ fc_reg_w,
                          float *__restrict__ partial,
@@ -47,6 +59,7 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
     // rois5 (optional): the [R,5] RoI tensor itself -- the batch index is read from its first column, no separate
     // roi_batch launch.  cls_out (optional, one channel block only): the FC biases and count_modified_cls_bbox are
     // applied here and the final [R,N+1] / [R,4N] rows written, no partial buffer and no finalize launch.
+    const int C = ONE ? kEpiThreads : C_rt;
     extern __shared__ float sm[];                 // [N][6][nwarps] + [blockDim] scratch
     const int r = blockIdx.x, blk = blockIdx.y, nblk = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -58,9 +71,11 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
     int b = rois5 != nullptr ? (int)rois5[5 * (size_t)r] : roi_batch[r];
     b = b < 0 ? 0 : (b >= B ? B - 1 : b);
 
-    float yq[PP];
+    float yq[ONE ? 1 : PP];
+    if (!ONE) {
 #pragma unroll
-    for (int p = 0; p < PP; ++p) yq[p] = active ? __ldg(Yq + ((size_t)r * PP + p) * C + c) : 0.f;
+        for (int p = 0; p < PP; ++p) yq[ONE ? 0 : p] = active ? __ldg(Yq + ((size_t)r * PP + p) * C + c) : 0.f;
+    }
     const float gamma = active ? __ldg(gn_w + c) : 0.f, beta = active ? __ldg(gn_b + c) : 0.f;
     float wfc[6];
 #pragma unroll
@@ -74,9 +89,15 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
         float s1 = 0.f;
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
-            y[p] = active ? yq[p] + __ldg(ys + (size_t)p * C) : 0.f;
-            s1 += y[p];
+            if (ONE) y[p] = ld_nc_ordered(Yq + ((size_t)r * PP + p) * C + c);
+            else     y[p] = active ? yq[ONE ? 0 : p] + __ldg(ys + (size_t)p * C) : 0.f;
         }
+        if (ONE) {                                  // the class term (L2-resident) behind the 49 loads above, in program order
+#pragma unroll                                      // (volatile: left to itself nvcc hoists all 98 loads and spills at 80 registers)
+            for (int p = 0; p < PP; ++p) y[p] = y[p] + ld_nc_ordered(ys + (size_t)p * C);
+        }
+#pragma unroll
+        for (int p = 0; p < PP; ++p) s1 += y[p];
         float gs;
         if (shfl_ok) gs = group_sum_shfl(s1, cg);
         else {
@@ -142,6 +163,180 @@ relation_epilogue_kernel(const float *__restrict__ Yq, const float *__restrict__
             if (better) { best_fg = v[1]; best_bg = v[0]; }
         }
         cls_out[(size_t)r * (N + 1) + N] = best_bg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same epilogue for the headline shape (N = 1, C = 256, P = 7) as a persistent, bulk-copy-fed kernel.  The
+// one-CTA-per-RoI kernel above is a read of the conv output with its loads in flight only during the first third of
+// every CTA's life (3.8 TB/s).  Here one CTA per SM owns a contiguous range of RoIs; a producer thread keeps a ring of
+// three 50 KB RoI tiles ([49,256] fp32, contiguous in the conv output) filled with cp.async.bulk, so ~150 KB per SM are
+// always in flight; two teams of 256 consumer threads (thread = channel) take alternate RoIs: a tile goes into registers,
+// the stage is freed at once, and the arithmetic is exactly relation_epilogue_kernel's, in the same order (one team
+// alone is latency-bound on its shuffle chains: 1.5 us per RoI).  The class term of the RoI's image (also one 50 KB
+// tile) sits in shared memory and is reloaded, behind a barrier of both teams, when the image changes (RoIs are grouped
+// by image: once or twice per CTA).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t ep_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ep_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ep_s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ep_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ep_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ep_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ep_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void ep_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(ep_s32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void ep_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ep_s32(dst)), "l"(src), "r"(bytes), "r"(ep_s32(bar)) : "memory");
+}
+constexpr int kRingStages = 3;
+constexpr int kRingTeams = 2;
+}  // namespace
+
+// grid = persistent CTAs, block = 2 x 256 consumers + 1 producer warp; dynamic smem = (kRingStages + 1) tiles of PP*256 floats
+template <int PP, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * kEpiThreads + 32, 1)
+relation_epilogue_ring_kernel(const float *__restrict__ Yq, const float *__restrict__ Ys,
+                              const int32_t *__restrict__ roi_batch, const float *__restrict__ rois5,
+                              const int R, const int B, const float eps,
+                              const float *__restrict__ gn_w, const float *__restrict__ gn_b,
+                              const float *__restrict__ fc_cls_w, const float *__restrict__ fc_reg_w,
+                              const float *__restrict__ fc_cls_b, const float *__restrict__ fc_reg_b,
+                              float *__restrict__ cls_out, float *__restrict__ reg_out,
+                              float *__restrict__ raw_cls, float *__restrict__ raw_reg)
+{
+    constexpr int C = kEpiThreads, cg = C / 32, nwarps = kEpiThreads / 32;
+    constexpr int kTile = PP * C;                                   // floats per tile
+    constexpr uint32_t kTileBytes = kTile * 4;
+    extern __shared__ __align__(128) float ring[];                  // [kRingStages][kTile] | ys[kTile]
+    float *ys_tile = ring + (size_t)kRingStages * kTile;
+    constexpr int kFull = kRingStages * TEAMS;                      // (stage, team) pairs: RoI k signals full_bar[k % kFull]
+    static_assert(TEAMS == 1 || (kRingStages % TEAMS) != 0, "stages and teams must interleave");
+    __shared__ __align__(8) uint64_t full_bar[kFull], empty_bar[kRingStages], ys_bar;
+    __shared__ float fc_part[TEAMS][2][6 * nwarps];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int team = tid / kEpiThreads, warp = (tid >> 5) % nwarps;     // team TEAMS = the producer warp
+    const int per = (R + gridDim.x - 1) / gridDim.x;
+    const int r_beg = blockIdx.x * per, r_end = min(R, r_beg + per);
+    if (tid == 0) {
+        for (int s = 0; s < kRingStages; ++s) ep_mbar_init(&empty_bar[s], nwarps);
+        for (int s = 0; s < kFull; ++s) ep_mbar_init(&full_bar[s], 1);
+        ep_mbar_init(&ys_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (r_beg >= r_end) return;
+
+    if (team == TEAMS) {
+        // ===== producer: one RoI tile per stage ==========================================================
+        if (lane == 0) {
+            int s = 0, f = 0;
+            unsigned par = 1;                                        // first pass over fresh barriers
+            for (int r = r_beg; r < r_end; ++r) {
+                ep_mbar_wait(&empty_bar[s], par);
+                ep_mbar_expect_tx(&full_bar[f], kTileBytes);
+                ep_bulk_g2s(ring + (size_t)s * kTile, Yq + (size_t)r * kTile, kTileBytes, &full_bar[f]);
+                if (++s == kRingStages) { s = 0; par ^= 1; }
+                if (++f == kFull) f = 0;
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread = channel, team = RoI parity ================================================
+    const int c = tid % kEpiThreads;
+    const float gamma = __ldg(gn_w + c), beta = __ldg(gn_b + c);
+    float wfc[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) wfc[j] = j < 2 ? __ldg(fc_cls_w + (size_t)j * C + c) : __ldg(fc_reg_w + (size_t)(j - 2) * C + c);
+    const float inv_cnt = 1.0f / (float)(cg * PP);
+    float bias = 0.f;                                                // lanes 0..5 of warp 0 finish output j = lane
+    if (c < 6) bias = c == 0 ? fc_cls_b[0] : c == 1 ? fc_cls_b[1] : fc_reg_b[c - 2];
+    int cur_b = -1;
+    unsigned ys_par = 0;
+    for (int r = r_beg, k = 0; r < r_end; ++r, ++k) {
+        int b = rois5 != nullptr ? (int)rois5[5 * (size_t)r] : roi_batch[r];
+        b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+        if (b != cur_b) {
+            // both teams walk the same RoI sequence, so both arrive here: everybody is done with the old class term
+            asm volatile("bar.sync 3, %0;" ::"n"(TEAMS * kEpiThreads) : "memory");
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                ep_mbar_expect_tx(&ys_bar, kTileBytes);
+                ep_bulk_g2s(ys_tile, Ys + (size_t)b * kTile, kTileBytes, &ys_bar);
+            }
+            ep_mbar_wait(&ys_bar, ys_par);
+            ys_par ^= 1;
+            cur_b = b;
+        }
+        if ((k % TEAMS) != team) continue;
+        const int s = k % kRingStages;
+        const unsigned par = (unsigned)(k / kFull) & 1u;
+        // A parity wait only tells the current phase from the one before it, and with two teams a stage's previous use
+        // belongs to the other team: on a per-stage barrier a team that runs ahead would find "its" parity already
+        // satisfied by the use before that one.  So a "full" barrier per (stage, team): each is waited on by one team, in
+        // order, phase by phase.
+        ep_mbar_wait(&full_bar[k % kFull], par);
+        const float *tq = ring + (size_t)s * kTile + c;
+        float y[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) y[p] = tq[p * C];
+        __syncwarp();
+        if (lane == 0) ep_mbar_arrive(&empty_bar[s]);               // the tile is in registers: refill the stage
+        float s1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) y[p] = y[p] + ys_tile[p * C + c];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) s1 += y[p];
+        float gs = group_sum_shfl(s1, cg);
+        const float mean = gs * inv_cnt;
+        float s2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) { const float d = y[p] - mean; s2 = fmaf(d, d, s2); }
+        gs = group_sum_shfl(s2, cg);
+        const float rstd = 1.0f / sqrtf(gs * inv_cnt + eps);
+        const float scale = rstd * gamma, shift = beta - mean * scale;
+        float z = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) z += fmaxf(fmaf(y[p], scale, shift), 0.f);
+        z = z / (float)PP;
+        float *fp = fc_part[team][(k / TEAMS) & 1];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float v = warp_sum(z * wfc[j]);
+            if (lane == 0) fp[j * nwarps + warp] = v;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kEpiThreads) : "memory");
+        // (fc_part is double-buffered per team: nobody writes this half again before the team's warp 0 has passed its next barrier)
+        if (c < 6) {
+            float sum = 0.f;
+            for (int w = 0; w < nwarps; ++w) sum += fp[c * nwarps + w];
+            const float v = (0.f + sum) + bias;
+            if (c < 2) {                                             // N = 1: cls_out = (fg, bg) = raw[:, [1, 0]]
+                cls_out[(size_t)r * 2 + (1 - c)] = v;
+                if (raw_cls) raw_cls[(size_t)r * 2 + c] = v;
+            } else {
+                reg_out[(size_t)r * 4 + (c - 2)] = v;
+                if (raw_reg) raw_reg[(size_t)r * 4 + (c - 2)] = v;
+            }
+        }
     }
 }
 
@@ -305,11 +500,39 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     FGN_CHECK_ARG(nblk <= 65535, "nblk");
     // production shapes (every thread owns a channel, a GroupNorm group inside one warp) take the unpredicated kernel
     const bool fast = cblk == kEpiThreads && (C % cblk) == 0 && (cg & (cg - 1)) == 0 && cg <= 32;
-    if (fast) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true>), smem);
+    const char *eo = getenv("FGN_EPI_ONE");                   // development knob: 0 = the general kernel for N = 1 too
+    const bool one = fast && N == 1 && C == kEpiThreads && !(eo != nullptr && atoi(eo) == 0);
+    if (one) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true, true>), smem);
+    else if (fast) FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, true>), smem);
     else      FGN_SMEM_OPTIN((relation_epilogue_kernel<kMaxPP, false>), smem);
     // one channel block (C <= 256): the epilogue writes the final rows itself, no partial buffer, no finalize launch
     float *direct = nblk == 1 ? cls_out : nullptr;
-    if (fast)
+    const char *er = getenv("FGN_EPI_RING");                  // development knob: 0 = one CTA per RoI for the headline shape too
+    if (one && direct != nullptr && R >= 512 && !(er != nullptr && atoi(er) == 0)) {
+        int sm_count = 0, devi = 0;
+        FGN_CUDA_OK(cudaGetDevice(&devi));
+        FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, devi));
+        const size_t ring_smem = (size_t)(kRingStages + 1) * kMaxPP * kEpiThreads * sizeof(float);
+        const char *et = getenv("FGN_EPI_TEAMS");             // development knob: consumer teams per CTA (1 or 2)
+        if (et != nullptr && atoi(et) == 1) {
+            FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_ring_kernel<kMaxPP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+            relation_epilogue_ring_kernel<kMaxPP, 1><<<sm_count, kEpiThreads + 32, ring_smem, st>>>(
+                w.yq, ys, roi_batch, rois5, R, B, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, fc_cls_b, fc_reg_b,
+                cls_out, reg_out, raw_cls_out, raw_reg_out);
+        } else {
+            FGN_CUDA_OK(cudaFuncSetAttribute(relation_epilogue_ring_kernel<kMaxPP, kRingTeams>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+            relation_epilogue_ring_kernel<kMaxPP, kRingTeams><<<sm_count, kRingTeams * kEpiThreads + 32, ring_smem, st>>>(
+                w.yq, ys, roi_batch, rois5, R, B, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, fc_cls_b, fc_reg_b,
+                cls_out, reg_out, raw_cls_out, raw_reg_out);
+        }
+        FGN_LAUNCH_OK();
+        return FGN_OK;
+    }
+    if (one)
+        relation_epilogue_kernel<kMaxPP, true, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
+            w.yq, ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
+            rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);
+    else if (fast)
         relation_epilogue_kernel<kMaxPP, true><<<dim3(R, nblk), kEpiThreads, smem, st>>>(
             w.yq, ys, roi_batch, R, B, N, C, cblk, cg, gn_eps, gn_w, gn_b, fc_cls_w, fc_reg_w, w.partial,
             rois5, fc_cls_b, fc_reg_b, direct, reg_out, raw_cls_out, raw_reg_out);

@@ -562,6 +562,46 @@ def test_guided_path_small_configs_vs_oracle(name, R):
     close(out["mask_feats"], mf, what="mask_feats")
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("R,images,order", [(600, 1, "grouped"), (1000, 3, "grouped"), (2311, 5, "grouped"),
+                                            (1500, 4, "interleaved"), (12000, 12, "grouped")])
+def test_relation_epilogue_ring_kernel_bitwise(R, images, order, monkeypatch):
+    """The persistent, bulk-copy-fed epilogue of the headline shape (N = 1, C = 256, P = 7; launches of 512+ RoIs) gives
+    bit for bit the results of the one-CTA-per-RoI kernels it stands in for -- RoI counts that leave CTAs with ragged or
+    empty ranges, image changes inside a CTA's range (the class-term reload behind the two teams' barrier), RoIs NOT
+    grouped by image (a reload on every RoI), one consumer team instead of two -- and those agree with the oracle."""
+    from fgn_b200 import ops
+    from fgn_b200.episodes import CONFIGS, build_heads, make_weights
+    cfg = CONFIGS["cfg3_coco2voc_n1k1_fpn"]
+    rpn, head = build_heads(cfg, dev(), seed=0)
+    params = head.relation_params()
+    g = torch.Generator().manual_seed(R + images)
+    C = cfg.channels
+    feat = torch.randn(R, 7, 7, C, generator=g).permute(0, 3, 1, 2)
+    rb = (torch.arange(R) % images) if order == "interleaved" else (torch.arange(R) * images // R)
+    spp = torch.randn(images, 1, C, 7, 7, generator=g)
+    fd, rbd, sd = feat.to(dev()), rb.to(dev()), spp.to(dev())
+    got = ops.relation_fusion(fd, rbd, sd, 1, params, return_raw=True)
+    monkeypatch.setenv("FGN_EPI_TEAMS", "1")
+    one_team = ops.relation_fusion(fd, rbd, sd, 1, params, return_raw=True)
+    monkeypatch.setenv("FGN_EPI_RING", "0")
+    per_roi = ops.relation_fusion(fd, rbd, sd, 1, params, return_raw=True)
+    monkeypatch.setenv("FGN_EPI_ONE", "0")
+    general = ops.relation_fusion(fd, rbd, sd, 1, params, return_raw=True)
+    for a, b, c, d in zip(got, one_team, per_roi, general):
+        assert torch.equal(a, d) and torch.equal(b, d) and torch.equal(c, d)
+    if R <= 1000:
+        w = make_weights(C, 0)
+        sub = slice(0, R, 7)
+        rois = torch.zeros(R, 5)
+        rois[:, 0] = rb.float()
+        n_r, fused = O.count_one_roi_by_n_spp(feat[sub].contiguous(), rois[sub], spp, 1, w["conv_w"], w["conv_b"], w["gn_w"], w["gn_b"])
+        rc, rr = O.bbox_head_forward(fused, w["fc_cls_w"], w["fc_cls_b"], w["fc_reg_w"], w["fc_reg_b"])
+        wc, wr = O.count_modified_cls_bbox(n_r, rc, rr, 1)
+        close(got[0][sub], wc, what="ring epilogue cls vs oracle")
+        close(got[1][sub], wr, what="ring epilogue reg vs oracle")
+
+
 def test_relation_stress_n20_k5_vs_oracle():
     """cfg4's shape family (N=20, K=5, C=256) at a RoI count the CPU oracle finishes in seconds."""
     from fgn_b200 import ops
