@@ -1,5 +1,5 @@
 """Relation fusion (contraction + epilogue) on 12 000 RoIs, N = 1: the persistent ring-fed epilogue, the one-CTA-per-RoI
-single-class epilogue (FGN_EPI_RING=0) and the general one (FGN_EPI_ONE=0 too), graph-replayed, same process."""
+single-class epilogue (FGN_EPI_RING=0) and the general one (FGN_EPI_ONE=0 too), graph-replayed, same process.  usage: [RoIs]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,10 +10,11 @@ dev = torch.device("cuda:0")
 rpn, head = build_heads(cfg, dev, seed=0)
 params = head.relation_params()
 g = torch.Generator(device="cpu").manual_seed(0)
-R, C = 12000, cfg.channels
+R, C = (int(sys.argv[1]) if len(sys.argv) > 1 else 12000), cfg.channels
+IM = max(1, R // 1000)
 feats = [torch.randn(R, 7, 7, C, generator=g).to(dev).permute(0, 3, 1, 2) for _ in range(3)]
-rb = (torch.arange(R) * 12 // R).to(dev)
-spp = torch.randn(12, 1, C, 7, 7, generator=g).to(dev)
+rb = (torch.arange(R) * IM // R).to(dev)
+spp = torch.randn(IM, 1, C, 7, 7, generator=g).to(dev)
 outs = {}
 for name, env in (("ring epilogue", {}), ("single-class epilogue", {"FGN_EPI_RING": "0"}),
                   ("general epilogue", {"FGN_EPI_RING": "0", "FGN_EPI_ONE": "0"}), ("ring epilogue (again)", {})):
