@@ -508,7 +508,9 @@ static int relation_fusion_impl(const float *roi_feat, int feat_layout, const in
     // one channel block (C <= 256): the epilogue writes the final rows itself, no partial buffer, no finalize launch
     float *direct = nblk == 1 ? cls_out : nullptr;
     const char *er = getenv("FGN_EPI_RING");                  // development knob: 0 = one CTA per RoI for the headline shape too
-    if (one && direct != nullptr && R >= 512 && !(er != nullptr && atoi(er) == 0)) {
+    // (bulk copies need 16-byte aligned tiles: a caller's class term at an odd offset takes the one-CTA-per-RoI kernel)
+    const bool tiles_aligned = (((uintptr_t)w.yq | (uintptr_t)ys) & 15u) == 0;
+    if (one && direct != nullptr && R >= 512 && tiles_aligned && !(er != nullptr && atoi(er) == 0)) {
         int sm_count = 0, devi = 0;
         FGN_CUDA_OK(cudaGetDevice(&devi));
         FGN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, devi));
